@@ -1,0 +1,217 @@
+"""CPU restatement of the EMIP motion-stream hot path (the parity oracle).
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Every function is a
+from-scratch restatement, in explicit tensor arithmetic, of one reference
+function; the ``Reference:`` line of each docstring names the file:line it
+follows (paths relative to the reference root).  All functions are dtype
+agnostic: feed float64 tensors to get the error-attribution reference.
+
+The arithmetic of the reference lives in PyTorch/ATen (un-vendored, un-pinned
+by the reference; oracle pin = torch 2.11.0).  Where the reference calls an ATen
+kernel with non-obvious semantics (``grid_sample``), the published algorithm is
+restated here and checked against ATen in ``tests/test_oracle_golden.py``.
+"""
+import math
+
+import torch
+
+
+# --------------------------------------------------------------------------- a1
+def coords_grid(h, w, dtype=torch.float32, device="cpu"):
+    """[2, H*W] pixel grid, channel 0 = x = j mod W, channel 1 = y = j div W.
+
+    Reference: model/EMIP_short/motion/gmflow/geometry.py:5-21.
+    """
+    j = torch.arange(h * w, device=device)
+    return torch.stack([(j % w).to(dtype), (j // w).to(dtype)], dim=0)
+
+
+def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return_prob=False):
+    """GMFlow global matching.
+
+    S[b,i,j] = sum_c f0[b,c,i] f1[b,c,j] / sqrt(C); P = softmax_j S (and the
+    softmax of S^T for the backward direction); flow = sum_j P g_j - g_i.
+    Returns (flow [B or 2B,2,H,W], prob or None, corr [B,HW,H,W]) where
+    corr[b,k,y,x] = S[b,(y,x),k] exactly as the reference's permuted view.
+
+    Reference: model/EMIP_short/motion/gmflow/matching.py:8-41.
+    """
+    b, c, h, w = feature0.shape
+    n = h * w
+    f0 = feature0.reshape(b, c, n)
+    f1 = feature1.reshape(b, c, n)
+    s = torch.einsum("bci,bcj->bij", f0, f1) / (c ** 0.5)            # matching.py:16
+    corr = s.reshape(b, h, w, n).permute(0, 3, 1, 2)                  # matching.py:18-20
+    g = coords_grid(h, w, feature0.dtype, feature0.device)           # [2, N]
+    if pred_bidir_flow:
+        s = torch.cat((s, s.transpose(1, 2)), dim=0)                  # matching.py:29
+    m = s.max(dim=-1, keepdim=True).values
+    e = torch.exp(s - m)
+    prob = e / e.sum(dim=-1, keepdim=True)                            # matching.py:34
+    corresp = torch.einsum("bij,cj->bci", prob, g)                    # matching.py:36
+    flow = (corresp - g[None]).reshape(s.shape[0], 2, h, w)           # matching.py:39
+    return flow, (prob if return_prob else None), corr
+
+
+# --------------------------------------------------------------------------- a2
+def feature_flow_attention(feature0, flow, q_w, q_b, k_w, k_b):
+    """Flow propagation: single-head global self-attention, value = flow.
+
+    q = Wq x + bq;  k = Wk q + bk (the key is projected from the *projected*
+    query -- reference quirk);  out_i = sum_j softmax_j(q_i.k_j/sqrt(C)) flow_j.
+
+    Reference: model/EMIP_short/motion/gmflow/transformer.py:503-533.
+    """
+    b, c, h, w = feature0.shape
+    n = h * w
+    x = feature0.reshape(b, c, n).transpose(1, 2)                     # [B, N, C]
+    q = x @ q_w.t() + q_b                                             # transformer.py:523
+    k = q @ k_w.t() + k_b                                             # transformer.py:524
+    v = flow.reshape(b, flow.shape[1], n).transpose(1, 2)             # [B, N, 2]
+    s = torch.einsum("bic,bjc->bij", q, k) / (c ** 0.5)               # transformer.py:528
+    m = s.max(dim=-1, keepdim=True).values
+    e = torch.exp(s - m)
+    p = e / e.sum(dim=-1, keepdim=True)                               # transformer.py:529
+    out = p @ v                                                       # transformer.py:531
+    return out.transpose(1, 2).reshape(b, v.shape[-1], h, w)
+
+
+# --------------------------------------------------------------------------- a3
+def flow_warp(x, flow12, pad="border"):
+    """Bilinear backward warp of x by flow12 (align_corners=True).
+
+    u = j + flow_x, v = i + flow_y are normalised to [-1,1] (warp_utils.py:16-23)
+    and un-normalised again inside ATen's grid_sampler; that fp32 round trip is
+    reproduced in the same operation order.  pad='border' clamps the sample
+    point to [0, size-1]; pad='zeros' leaves it and drops out-of-range taps.
+    Tap weights follow ATen's CPU kernel (w = ix - floor(ix), e = 1 - w, ...).
+
+    Reference: loss/warp_utils.py:83-93 (+ mesh_grid :7-13, norm_grid :16-23);
+    ATen grid_sampler_2d, bilinear, align_corners=True (published semantics).
+    """
+    b, c, h, w = x.shape
+    dt = x.dtype
+    jx = torch.arange(w, dtype=dt, device=x.device).view(1, 1, w)
+    iy = torch.arange(h, dtype=dt, device=x.device).view(1, h, 1)
+    u = jx + flow12[:, 0]
+    v = iy + flow12[:, 1]
+    nx = 2.0 * u / (w - 1) - 1.0                                      # warp_utils.py:21
+    ny = 2.0 * v / (h - 1) - 1.0                                      # warp_utils.py:22
+    ix = ((nx + 1) / 2) * (w - 1)                                     # ATen unnormalize
+    iy_ = ((ny + 1) / 2) * (h - 1)
+    if pad == "border":
+        ix = ix.clamp(0, w - 1)
+        iy_ = iy_.clamp(0, h - 1)
+    x0 = torch.floor(ix)
+    y0 = torch.floor(iy_)
+    wx = ix - x0
+    wy = iy_ - y0
+    ex = 1 - wx
+    ey = 1 - wy
+    xf = x.reshape(b, c, h * w)
+    out = torch.zeros_like(x).reshape(b, c, h * w)
+    for dy, dx, wt in ((0, 0, ey * ex), (0, 1, ey * wx), (1, 0, wy * ex), (1, 1, wy * wx)):
+        xi = x0 + dx
+        yi = y0 + dy
+        ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+        idx = (yi.clamp(0, h - 1) * w + xi.clamp(0, w - 1)).long().reshape(b, 1, h * w)
+        tap = torch.gather(xf, 2, idx.expand(b, c, h * w))
+        out = out + tap * (wt * ok.to(dt)).reshape(b, 1, h * w)
+    return out.reshape(b, c, h, w)
+
+
+# --------------------------------------------------------------------------- a4
+def _layernorm_c(x, weight, bias):
+    """Per-pixel LayerNorm over channels, biased variance, eps 1e-5.
+
+    Reference: model/EMIP_short/motion/PromptInteract.py:333-362.
+    """
+    mu = x.mean(dim=1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + 1e-5) * weight.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+
+
+def _conv1x1(x, w):
+    return torch.einsum("oc,bchw->bohw", w.reshape(w.shape[0], w.shape[1]), x)
+
+
+def _dwconv3x3(x, w):
+    """Depthwise 3x3, stride 1, zero padding 1, no bias (cross-correlation)."""
+    b, c, h, wd = x.shape
+    xp = torch.zeros(b, c, h + 2, wd + 2, dtype=x.dtype, device=x.device)
+    xp[:, :, 1:-1, 1:-1] = x
+    out = torch.zeros_like(x)
+    for ky in range(3):
+        for kx in range(3):
+            out = out + xp[:, :, ky:ky + h, kx:kx + wd] * w[:, 0, ky, kx].view(1, c, 1, 1)
+    return out
+
+
+def _gelu_erf(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+INJECTOR_KEYS = (
+    "norm1.body.weight", "norm1.body.bias", "norm2.body.weight", "norm2.body.bias",
+    "norm3.body.weight", "norm3.body.bias", "attn.temperature", "attn.q.weight",
+    "attn.q_dwconv.weight", "attn.kv.weight", "attn.kv_dwconv.weight",
+    "attn.project_out.weight", "ffn.project_in.weight", "ffn.dwconv.weight",
+    "ffn.project_out.weight",
+)
+
+
+def injector(x, x1, p, num_heads=2):
+    """Camouflaged feeder / motion collector: one MDTA cross-attention block + GDFN.
+
+    ``p`` maps the reference's ``Injector.transformer.*`` state_dict keys
+    (INJECTOR_KEYS) to tensors.
+
+    Reference: model/EMIP_short/motion/PromptInteract.py:452-464 (Injector),
+    :436-450 (TransformerBlock_MDTA), :390-432 (Attention_MDTA), :367-385 (FeedForward).
+    """
+    b, c, h, w = x.shape
+    n = h * w
+    xn = _layernorm_c(x, p["norm1.body.weight"], p["norm1.body.bias"])
+    x1n = _layernorm_c(x1, p["norm2.body.weight"], p["norm2.body.bias"])
+    q = _dwconv3x3(_conv1x1(xn, p["attn.q.weight"]), p["attn.q_dwconv.weight"])       # :413
+    kv = _dwconv3x3(_conv1x1(x1n, p["attn.kv.weight"]), p["attn.kv_dwconv.weight"])   # :414
+    k, v = kv[:, :c], kv[:, c:]                                                       # :415
+    ch = c // num_heads
+    q = q.reshape(b, num_heads, ch, n)
+    k = k.reshape(b, num_heads, ch, n)
+    v = v.reshape(b, num_heads, ch, n)
+    q = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12)                             # :421
+    k = k / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)                             # :422
+    attn = torch.einsum("bhcn,bhdn->bhcd", q, k) * p["attn.temperature"].view(1, num_heads, 1, 1)
+    attn = attn - attn.max(dim=-1, keepdim=True).values
+    attn = torch.exp(attn)
+    attn = attn / attn.sum(dim=-1, keepdim=True)                                      # :425
+    out = torch.einsum("bhcd,bhdn->bhcn", attn, v).reshape(b, c, h, w)                # :427-429
+    x = x + _conv1x1(out, p["attn.project_out.weight"])                               # :431, :447
+    xn3 = _layernorm_c(x, p["norm3.body.weight"], p["norm3.body.bias"])
+    t = _dwconv3x3(_conv1x1(xn3, p["ffn.project_in.weight"]), p["ffn.dwconv.weight"])  # :381-382
+    hid = t.shape[1] // 2
+    g = _gelu_erf(t[:, :hid]) * t[:, hid:]                                            # :383
+    return x + _conv1x1(g, p["ffn.project_out.weight"])                               # :384, :448
+
+
+# --------------------------------------------------------------------------- a5
+def memory_read(m_in, m_out, q_in, q_out, return_prob=False):
+    """STM-style memory read: softmax over the T*H*W memory axis.
+
+    m_in [B,De,T,H,W] keys, m_out [B,Do,T,H,W] values, q_in [B,De,H,W] query keys,
+    q_out [B,Do,H,W] query values -> (cat(mem, q_out) [B,2*Do,H,W], p or None).
+
+    Reference: model/EMIP_long/LTM.py:49-68.
+    """
+    b, de, t, h, w = m_in.shape
+    do = m_out.shape[1]
+    mi = m_in.reshape(b, de, t * h * w).transpose(1, 2)               # [B, THW, De]
+    qi = q_in.reshape(b, de, h * w)
+    s = torch.bmm(mi, qi) / math.sqrt(de)                             # LTM.py:58-59
+    s = s - s.max(dim=1, keepdim=True).values
+    e = torch.exp(s)
+    p = e / e.sum(dim=1, keepdim=True)                                # LTM.py:60
+    mem = torch.bmm(m_out.reshape(b, do, t * h * w), p).reshape(b, do, h, w)
+    out = torch.cat([mem, q_out.reshape(b, do, h, w)], dim=1)         # LTM.py:66
+    return out, (p if return_prob else None)

@@ -1,0 +1,154 @@
+"""Seeded synthetic inputs shared by the golden-vector generator and the tests.
+
+Inputs are regenerated from CPU ``torch.Generator`` seeds (deterministic for the
+pinned torch 2.11.0) so that only *outputs* of the reference need to be stored.
+"""
+import torch
+
+INJECTOR_SHAPES = {
+    "norm1.body.weight": (128,), "norm1.body.bias": (128,),
+    "norm2.body.weight": (128,), "norm2.body.bias": (128,),
+    "norm3.body.weight": (128,), "norm3.body.bias": (128,),
+    "attn.temperature": (2, 1, 1),
+    "attn.q.weight": (128, 128, 1, 1), "attn.q_dwconv.weight": (128, 1, 3, 3),
+    "attn.kv.weight": (256, 128, 1, 1), "attn.kv_dwconv.weight": (256, 1, 3, 3),
+    "attn.project_out.weight": (128, 128, 1, 1),
+    "ffn.project_in.weight": (680, 128, 1, 1), "ffn.dwconv.weight": (680, 1, 3, 3),
+    "ffn.project_out.weight": (128, 340, 1, 1),
+}
+
+
+def randn(seed, shape, scale=1.0, shift=0.0):
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.randn(*shape, generator=g) * scale + shift
+
+
+def rand(seed, shape):
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.rand(*shape, generator=g)
+
+
+def injector_params(seed, temp=(1.0, 1.0)):
+    """Random (not reference-init) Injector parameters: every tensor non-trivial."""
+    p = {}
+    for i, (k, shp) in enumerate(INJECTOR_SHAPES.items()):
+        if k == "attn.temperature":
+            p[k] = torch.tensor(temp, dtype=torch.float32).view(2, 1, 1) + 0.1 * randn(seed * 100 + i, shp)
+        elif "norm" in k and k.endswith("weight"):
+            p[k] = randn(seed * 100 + i, shp, 0.2, 1.0)
+        elif "norm" in k:
+            p[k] = randn(seed * 100 + i, shp, 0.2)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            p[k] = randn(seed * 100 + i, shp, (1.0 / fan_in) ** 0.5)
+    return p
+
+
+def ffa_params(seed, c=128):
+    return {
+        "q_proj.weight": randn(seed * 10 + 1, (c, c), (1.0 / c) ** 0.5),
+        "q_proj.bias": randn(seed * 10 + 2, (c,), 0.1),
+        "k_proj.weight": randn(seed * 10 + 3, (c, c), (1.0 / c) ** 0.5),
+        "k_proj.bias": randn(seed * 10 + 4, (c,), 0.1),
+    }
+
+
+def smooth_flow(seed, b, h, w, mag, cells=8):
+    """Piecewise-smooth flow like the model's x8 convex-upsampled output."""
+    import torch.nn.functional as F
+    lo = randn(seed, (b, 2, max(2, h // cells), max(2, w // cells)), mag)
+    return F.interpolate(lo, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+
+
+# name -> spec; "full" cases store only sub-sampled outputs (stride SUB) + norms.
+SUB = 61
+
+A1_CASES = {
+    "a1_small": dict(b=2, c=128, h=6, w=8, scale=1.0, seed=11, full=False),
+    "a1_ragged": dict(b=1, c=128, h=13, w=11, scale=2.0, seed=12, full=False),
+    "a1_full": dict(b=1, c=128, h=44, w=44, scale=4.1, seed=13, full=True),
+    "a1_lowcontrast": dict(b=1, c=128, h=44, w=44, scale=0.41, seed=14, full=True),
+}
+A2_CASES = {
+    "a2_small": dict(b=2, c=128, h=6, w=8, scale=1.0, fscale=3.0, seed=21, full=False),
+    "a2_full": dict(b=2, c=128, h=44, w=44, scale=4.1, fscale=12.0, seed=22, full=True),
+}
+A3_CASES = {
+    "a3_small_border": dict(b=2, c=3, h=9, w=11, sigma=3.0, pad="border", seed=31),
+    "a3_small_zeros": dict(b=2, c=3, h=9, w=11, sigma=3.0, pad="zeros", seed=32),
+    "a3_mid_border": dict(b=2, c=3, h=40, w=56, sigma=20.0, pad="border", seed=33),
+    "a3_c5_border": dict(b=1, c=5, h=17, w=23, sigma=5.0, pad="border", seed=34),
+}
+A4_CASES = {
+    "a4_small": dict(b=2, h=6, w=8, xs=2.2, x1s=1.0, seed=41, full=False),
+    "a4_feeder": dict(b=1, h=44, w=44, xs=2.2, x1s=1.0, seed=42, full=True),
+    "a4_collector": dict(b=1, h=44, w=44, xs=1.0, x1s=32.0, seed=43, full=True),
+}
+A5_CASES = {
+    "a5_small": dict(b=1, t=2, h=5, w=6, scale=1.0, seed=51, full=False),
+    "a5_full": dict(b=1, t=4, h=44, w=44, scale=1.5, seed=52, full=True),
+}
+
+
+def a1_inputs(s):
+    shp = (s["b"], s["c"], s["h"], s["w"])
+    n = s["h"] * s["w"]
+    return dict(f0=randn(s["seed"], shp, s["scale"]), f1=randn(s["seed"] + 1000, shp, s["scale"]),
+                wflow=randn(s["seed"] + 2000, (2 * s["b"], 2, s["h"], s["w"])),
+                wcorr=randn(s["seed"] + 3000, (s["b"], n, s["h"], s["w"]), 0.05))
+
+
+def a2_inputs(s):
+    shp = (s["b"], s["c"], s["h"], s["w"])
+    d = dict(x=randn(s["seed"], shp, s["scale"]), flow=randn(s["seed"] + 1000, (s["b"], 2, s["h"], s["w"]), s["fscale"]),
+             wout=randn(s["seed"] + 2000, (s["b"], 2, s["h"], s["w"])))
+    d.update(ffa_params(s["seed"], s["c"]))
+    return d
+
+
+def a3_inputs(s):
+    return dict(x=randn(s["seed"], (s["b"], s["c"], s["h"], s["w"])),
+                flow=randn(s["seed"] + 1000, (s["b"], 2, s["h"], s["w"]), s["sigma"]),
+                wout=randn(s["seed"] + 2000, (s["b"], s["c"], s["h"], s["w"])))
+
+
+def a4_inputs(s):
+    shp = (s["b"], 128, s["h"], s["w"])
+    return dict(x=randn(s["seed"], shp, s["xs"]), x1=randn(s["seed"] + 1000, shp, s["x1s"]),
+                wout=randn(s["seed"] + 2000, shp), params=injector_params(s["seed"]))
+
+
+def a5_inputs(s):
+    b, t, h, w = s["b"], s["t"], s["h"], s["w"]
+    return dict(m_in=randn(s["seed"], (b, 128, t, h, w), s["scale"]), m_out=randn(s["seed"] + 1000, (b, 128, t, h, w)),
+                q_in=randn(s["seed"] + 2000, (b, 128, h, w), s["scale"]), q_out=randn(s["seed"] + 3000, (b, 128, 1, h, w)),
+                wout=randn(s["seed"] + 4000, (b, 256, h, w)))
+
+
+def pack(t, full):
+    """Store a tensor whole (small cases) or as (stride-SUB sample, L2 norm, sum) (full-size)."""
+    t = t.detach().contiguous()
+    if not full:
+        return {"full": t.clone()}
+    flat = t.reshape(-1).double()
+    return {"sub": t.reshape(-1)[::SUB].clone(), "l2": flat.norm().item(), "sum": flat.sum().item(),
+            "shape": tuple(t.shape)}
+
+
+def check_packed(t, packed, rtol, what=""):
+    """Assert tensor t matches a packed golden entry to rel-L2 <= rtol."""
+    t = t.detach().contiguous().cpu()
+    if "full" in packed:
+        ref = packed["full"]
+        assert tuple(t.shape) == tuple(ref.shape), (what, t.shape, ref.shape)
+        err = (t.double() - ref.double()).norm().item() / max(ref.double().norm().item(), 1e-30)
+        assert err <= rtol, f"{what}: rel-L2 {err:.3e} > {rtol:.1e}"
+        return err
+    assert tuple(t.shape) == tuple(packed["shape"]), (what, t.shape, packed["shape"])
+    sub = t.reshape(-1)[::SUB]
+    ref = packed["sub"]
+    err = (sub.double() - ref.double()).norm().item() / max(ref.double().norm().item(), 1e-30)
+    assert err <= rtol, f"{what}: sub-sample rel-L2 {err:.3e} > {rtol:.1e}"
+    l2 = t.reshape(-1).double().norm().item()
+    assert abs(l2 - packed["l2"]) <= 10 * rtol * max(packed["l2"], 1e-30), f"{what}: L2 norm {l2} vs {packed['l2']}"
+    return err

@@ -1,0 +1,149 @@
+"""Generate golden vectors by running the UNMODIFIED reference (zhangxin06/EMIP).
+
+Run in the build container, where /root/reference is mounted:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.pt.  The GPU box never sees the reference, so these files
+(plus the seeded input builders in cases.py) are what pins the oracle there.
+Recorded with torch 2.11.0+cu128 on CPU, fp32, deterministic seeds.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import cases  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+torch.set_num_threads(os.cpu_count())
+
+from model.EMIP_short.motion.gmflow.matching import global_correlation_softmax  # noqa: E402
+from model.EMIP_short.motion.gmflow.transformer import FeatureFlowAttention  # noqa: E402
+from model.EMIP_short.motion.PromptInteract import Injector  # noqa: E402
+from model.EMIP_long.LTM import Memory  # noqa: E402
+from loss.warp_utils import flow_warp  # noqa: E402
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name + ".pt")
+    torch.save(obj, path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def gen_a1():
+    for name, s in cases.A1_CASES.items():
+        d = cases.a1_inputs(s)
+        f0 = d["f0"].clone().requires_grad_(True)
+        f1 = d["f1"].clone().requires_grad_(True)
+        flow, prob, corr = global_correlation_softmax(f0, f1, True)
+        loss = (flow * d["wflow"]).sum() + (corr * d["wcorr"]).sum()
+        loss.backward()
+        save(name, dict(spec=s, flow=cases.pack(flow, False), corr=cases.pack(corr, s["full"]),
+                        prob_rowsum_err=float((prob.sum(-1) - 1).abs().max()),
+                        df0=cases.pack(f0.grad, s["full"]), df1=cases.pack(f1.grad, s["full"])))
+
+
+def gen_a2():
+    for name, s in cases.A2_CASES.items():
+        d = cases.a2_inputs(s)
+        m = FeatureFlowAttention(s["c"])
+        m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
+        x = d["x"].clone().requires_grad_(True)
+        out = m(x, d["flow"])
+        (out * d["wout"]).sum().backward()
+        save(name, dict(spec=s, out=cases.pack(out, False), dx=cases.pack(x.grad, s["full"]),
+                        dqw=cases.pack(m.q_proj.weight.grad, False), dqb=cases.pack(m.q_proj.bias.grad, False),
+                        dkw=cases.pack(m.k_proj.weight.grad, False)))  # dL/d(k bias) == 0 analytically
+
+
+def gen_a3():
+    for name, s in cases.A3_CASES.items():
+        d = cases.a3_inputs(s)
+        x = d["x"].clone().requires_grad_(True)
+        fl = d["flow"].clone().requires_grad_(True)
+        out = flow_warp(x, fl, pad=s["pad"])
+        (out * d["wout"]).sum().backward()
+        save(name, dict(spec=s, out=cases.pack(out, False), dflow=cases.pack(fl.grad, False),
+                        dx=cases.pack(x.grad, False)))
+    # the non-contiguous channel-slice call pattern of loss_flow.py:90-91
+    s = dict(b=2, c=3, h=12, w=10, sigma=4.0, pad="border", seed=35)
+    flow4 = cases.randn(s["seed"], (s["b"], 4, s["h"], s["w"]), s["sigma"])
+    x = cases.randn(s["seed"] + 1, (s["b"], 3, s["h"], s["w"]))
+    save("a3_slice", dict(spec=s, out_fw=cases.pack(flow_warp(x, flow4[:, :2]), False),
+                          out_bw=cases.pack(flow_warp(x, flow4[:, 2:]), False)))
+
+
+def gen_a4():
+    for name, s in cases.A4_CASES.items():
+        d = cases.a4_inputs(s)
+        m = Injector()
+        m.transformer.load_state_dict(d["params"])
+        x = d["x"].clone().requires_grad_(True)
+        x1 = d["x1"].clone().requires_grad_(True)
+        out = m(x, x1)
+        (out * d["wout"]).sum().backward()
+        g = {k: cases.pack(p.grad, False) for k, p in m.transformer.named_parameters()}
+        save(name, dict(spec=s, out=cases.pack(out, s["full"]), dx=cases.pack(x.grad, s["full"]),
+                        dx1=cases.pack(x1.grad, s["full"]), dparams=g))
+
+
+def gen_a5():
+    for name, s in cases.A5_CASES.items():
+        d = cases.a5_inputs(s)
+        t = {k: d[k].clone().requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
+        out, p = Memory()(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
+        (out * d["wout"]).sum().backward()
+        save(name, dict(spec=s, out=cases.pack(out, s["full"]),
+                        **{"d" + k: cases.pack(v.grad, s["full"]) for k, v in t.items()}))
+
+
+def gen_c1():
+    """config c1: CoUpdater eval forward on one seeded 352x352 pair; capture the a1/a2 call in situ."""
+    from model.EMIP_short.model import CoUpdater
+    import model.EMIP_short.motion.gmflow.gmflow as gm
+    torch.manual_seed(123)  # configs/configs.yaml:69
+    net = CoUpdater(ref_shim.model_args()).eval()
+    im1 = cases.randn(0, (1, 3, 352, 352))
+    im2 = cases.randn(1, (1, 3, 352, 352))
+    cap = {}
+    orig = gm.global_correlation_softmax
+
+    def spy(f0, f1, bidir):
+        cap["f0"], cap["f1"] = f0.detach().clone(), f1.detach().clone()
+        out = orig(f0, f1, bidir)
+        cap["flow"], cap["corr"] = out[0].detach().clone(), out[2].detach().clone()
+        return out
+
+    def ffa_hook(mod, args, kwargs, out):
+        cap["ffa_in_flow"] = args[1].detach().clone()
+        cap["ffa_out"] = out.detach().clone()
+
+    gm.global_correlation_softmax = spy
+    h = net.GMFlow.feature_flow_attn.register_forward_hook(ffa_hook, with_kwargs=True)
+    with torch.no_grad():
+        mask, ffw, fbw = net(im1, im2)
+    gm.global_correlation_softmax = orig
+    h.remove()
+    ffa = net.GMFlow.feature_flow_attn
+    s_max = (cap["corr"].max().item(), cap["corr"].min().item(), cap["corr"].std().item())
+    save("c1_insitu", dict(
+        f0=cap["f0"], f1=cap["f1"], flow=cases.pack(cap["flow"], False), corr=cases.pack(cap["corr"], True),
+        ffa_params={k: v.detach().clone() for k, v in ffa.state_dict().items()},
+        ffa_out=cases.pack(cap["ffa_out"], False),
+        mask=cases.pack(mask, True), flow_fw=cases.pack(ffw[-1], True), flow_bw=cases.pack(fbw[-1], True),
+        stats=dict(corr_max_min_std=s_max, flow_abs_mean=cap["flow"].abs().mean().item(),
+                   mask_mean=mask.mean().item(), mask_std=mask.std().item())))
+    print("c1 stats", s_max, cap["flow"].abs().mean().item())
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "c1"]
+    for w in which:
+        globals()["gen_" + w]()

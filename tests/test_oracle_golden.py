@@ -1,0 +1,129 @@
+"""Pin the CPU oracle (oracle/restate.py) against golden vectors recorded from the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+import cases
+from oracle import restate as O
+
+TOL = 2e-5      # fp32 re-association only
+GTOL = 1e-4     # gradients through near-one-hot softmaxes
+
+
+@pytest.mark.parametrize("name", list(cases.A1_CASES))
+def test_a1_global_matching(golden, name):
+    g = golden(name)
+    s = cases.A1_CASES[name]
+    d = cases.a1_inputs(s)
+    f0 = d["f0"].clone().requires_grad_(True)
+    f1 = d["f1"].clone().requires_grad_(True)
+    flow, prob, corr = O.global_correlation_softmax(f0, f1, True)
+    assert prob is None and tuple(corr.shape) == (s["b"], s["h"] * s["w"], s["h"], s["w"])
+    cases.check_packed(flow, g["flow"], TOL, "flow")
+    cases.check_packed(corr, g["corr"], TOL, "corr")
+    ((flow * d["wflow"]).sum() + (corr * d["wcorr"]).sum()).backward()
+    cases.check_packed(f0.grad, g["df0"], GTOL, "df0")
+    cases.check_packed(f1.grad, g["df1"], GTOL, "df1")
+
+
+def test_a1_unidirectional_and_prob():
+    s = cases.A1_CASES["a1_small"]
+    d = cases.a1_inputs(s)
+    flow, prob, _ = O.global_correlation_softmax(d["f0"], d["f1"], False, return_prob=True)
+    flow2, _, _ = O.global_correlation_softmax(d["f0"], d["f1"], True)
+    assert flow.shape[0] == s["b"] and torch.allclose(flow, flow2[: s["b"]], atol=1e-5)
+    assert (prob.sum(-1) - 1).abs().max() < 1e-5
+
+
+def test_a1_insitu_c1(golden):
+    g = golden("c1_insitu")
+    flow, _, corr = O.global_correlation_softmax(g["f0"], g["f1"], True)
+    cases.check_packed(flow, g["flow"], TOL, "flow")
+    cases.check_packed(corr, g["corr"], TOL, "corr")
+    p = g["ffa_params"]
+    out = O.feature_flow_attention(torch.cat((g["f0"], g["f1"]), 0), flow, p["q_proj.weight"], p["q_proj.bias"],
+                                   p["k_proj.weight"], p["k_proj.bias"])
+    cases.check_packed(out, g["ffa_out"], 5e-5, "ffa_out")
+
+
+@pytest.mark.parametrize("name", list(cases.A2_CASES))
+def test_a2_flow_attention(golden, name):
+    g = golden(name)
+    d = cases.a2_inputs(cases.A2_CASES[name])
+    x = d["x"].clone().requires_grad_(True)
+    qw = d["q_proj.weight"].clone().requires_grad_(True)
+    qb = d["q_proj.bias"].clone().requires_grad_(True)
+    kw = d["k_proj.weight"].clone().requires_grad_(True)
+    out = O.feature_flow_attention(x, d["flow"], qw, qb, kw, d["k_proj.bias"])
+    cases.check_packed(out, g["out"], TOL, "out")
+    (out * d["wout"]).sum().backward()
+    cases.check_packed(x.grad, g["dx"], GTOL, "dx")
+    cases.check_packed(qw.grad, g["dqw"], GTOL, "dqw")
+    cases.check_packed(qb.grad, g["dqb"], GTOL, "dqb")
+    cases.check_packed(kw.grad, g["dkw"], GTOL, "dkw")
+
+
+@pytest.mark.parametrize("name", list(cases.A3_CASES))
+def test_a3_flow_warp(golden, name):
+    g = golden(name)
+    s = cases.A3_CASES[name]
+    d = cases.a3_inputs(s)
+    x = d["x"].clone().requires_grad_(True)
+    fl = d["flow"].clone().requires_grad_(True)
+    out = O.flow_warp(x, fl, pad=s["pad"])
+    cases.check_packed(out, g["out"], 1e-5, "out")
+    (out * d["wout"]).sum().backward()
+    cases.check_packed(fl.grad, g["dflow"], 1e-4, "dflow")
+    cases.check_packed(x.grad, g["dx"], 1e-5, "dx")
+
+
+def test_a3_noncontiguous_slice(golden):
+    g = golden("a3_slice")
+    s = g["spec"]
+    flow4 = cases.randn(s["seed"], (s["b"], 4, s["h"], s["w"]), s["sigma"])
+    x = cases.randn(s["seed"] + 1, (s["b"], 3, s["h"], s["w"]))
+    cases.check_packed(O.flow_warp(x, flow4[:, :2]), g["out_fw"], 1e-5)
+    cases.check_packed(O.flow_warp(x, flow4[:, 2:]), g["out_bw"], 1e-5)
+
+
+def test_a3_matches_aten_grid_sample():
+    """The published ATen semantics the restatement follows, checked against the installed torch."""
+    import torch.nn.functional as F
+    x = cases.randn(5, (2, 3, 16, 20))
+    fl = cases.randn(6, (2, 2, 16, 20), 6.0)
+    for pad in ("border", "zeros"):
+        h, w = 16, 20
+        gx = torch.arange(w).view(1, 1, w) + fl[:, 0]
+        gy = torch.arange(h).view(1, h, 1) + fl[:, 1]
+        grid = torch.stack([2.0 * gx / (w - 1) - 1.0, 2.0 * gy / (h - 1) - 1.0], dim=-1)
+        ref = F.grid_sample(x, grid, mode="bilinear", padding_mode=pad, align_corners=True)
+        assert (O.flow_warp(x, fl, pad) - ref).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("name", list(cases.A4_CASES))
+def test_a4_injector(golden, name):
+    g = golden(name)
+    d = cases.a4_inputs(cases.A4_CASES[name])
+    p = {k: v.clone().requires_grad_(True) for k, v in d["params"].items()}
+    x = d["x"].clone().requires_grad_(True)
+    x1 = d["x1"].clone().requires_grad_(True)
+    out = O.injector(x, x1, p)
+    cases.check_packed(out, g["out"], TOL, "out")
+    (out * d["wout"]).sum().backward()
+    cases.check_packed(x.grad, g["dx"], GTOL, "dx")
+    cases.check_packed(x1.grad, g["dx1"], GTOL, "dx1")
+    for k in p:
+        cases.check_packed(p[k].grad, g["dparams"][k], 2e-4, "d" + k)
+
+
+@pytest.mark.parametrize("name", list(cases.A5_CASES))
+def test_a5_memory_read(golden, name):
+    g = golden(name)
+    d = cases.a5_inputs(cases.A5_CASES[name])
+    t = {k: d[k].clone().requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
+    out, p = O.memory_read(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
+    assert p is None
+    cases.check_packed(out, g["out"], TOL, "out")
+    (out * d["wout"]).sum().backward()
+    for k, v in t.items():
+        cases.check_packed(v.grad, g["d" + k], GTOL, "d" + k)
