@@ -1,0 +1,88 @@
+// a2: flow-propagation self-attention core -- C-ABI front end.
+// Replaces reference model/EMIP_short/motion/gmflow/transformer.py:526-532
+// (scores = q k^T / sqrt(C); softmax; prob @ flow) and its autograd backward
+// (value = flow.detach(), gmflow.py:137, so only dq and dk exist).  The two
+// nn.Linear projections (transformer.py:523-524) stay library GEMMs on the host side.
+#include "common.cuh"
+#include "../../include/emip_b200.h"
+#include "pair_common.cuh"
+#include "match_tc.cuh"
+#include <math.h>
+
+namespace {
+size_t d_bytes(int B, int N) { return emip_align_up(sizeof(float) * (size_t)B * N, 1024); }
+}
+
+extern "C" size_t emip_flow_attn_workspace(int B, int N, int C) {
+  if (B < 0 || N <= 0 || C <= 0) return 0;
+  return d_bytes(B, N) + 2 * match_tc_split_bytes(B, N, C);
+}
+
+extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse,
+                                  void* workspace, size_t ws_bytes, int B, int N, int C, int flags, void* stream) {
+  EMIP_CHECK_ARG(q && k && v && out, "flow_attn_fwd: null pointer");
+  EMIP_CHECK_ARG(B >= 0 && N > 0, "flow_attn_fwd: bad shape B=%d N=%d", B, N);
+  if (C != 128) {
+    emip_set_error("flow_attn_fwd: C=%d unsupported (kernels are built for the model's C=128)", C);
+    return EMIP_ENOSYS;
+  }
+  if (B == 0) return EMIP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
+    size_t sb = match_tc_split_bytes(B, N, C);
+    if (workspace == nullptr || ws_bytes < d_bytes(B, N) + 2 * sb || reinterpret_cast<uintptr_t>(workspace) % 1024) {
+      emip_set_error("flow_attn_fwd: workspace too small or not 1024-byte aligned");
+      return EMIP_ENOMEM;
+    }
+    char* p = static_cast<char*>(workspace) + d_bytes(B, N);
+    int rc;
+    if ((rc = match_tc_split(q, p, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    if ((rc = match_tc_split(k, p + sb, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    MatchTcArgs a = {};
+    a.x_split = p; a.y_split = p + sb; a.nbx = B; a.nby = B;
+    a.v = v; a.v_stride_b = 2LL * N; a.sub = nullptr;
+    a.out = out; a.lse = lse; a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0; a.y_mod = B;
+    a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
+    a.sqrt_c = sqrtf((float)C);
+    return match_tc_fwd(a, st);
+  }
+  PairFwdArgs a = {};
+  a.x = q; a.y = k; a.v = v; a.v_stride_b = 2LL * N; a.sub = nullptr;
+  a.out = out; a.lse = lse; a.s_out = nullptr;
+  a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0;
+  a.x_layout = a.y_layout = EMIP_LAYOUT_NC;
+  a.sqrt_c = sqrtf((float)C);                       // transformer.py:528
+  return pair_fwd_simt(a, st);
+}
+
+extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
+                                  const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes,
+                                  int B, int N, int C, void* stream) {
+  EMIP_CHECK_ARG(q && k && v && out && lse && dout && dq && dk, "flow_attn_bwd: null pointer");
+  if (C != 128) {
+    emip_set_error("flow_attn_bwd: C=%d unsupported (kernels are built for the model's C=128)", C);
+    return EMIP_ENOSYS;
+  }
+  if (B == 0) return EMIP_OK;
+  if (workspace == nullptr || ws_bytes < d_bytes(B, N)) {
+    emip_set_error("flow_attn_bwd: workspace too small");
+    return EMIP_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* D = static_cast<float*>(workspace);      // D_i = dO_i . O_i
+  int rc;
+  if ((rc = launch_rowdot2(dout, out, nullptr, D, B, N, st))) return rc;
+  PairBwdArgs a = {};
+  a.nb = B; a.nr = N; a.nc = N;
+  a.x_layout = a.y_layout = a.dx_layout = EMIP_LAYOUT_NC;
+  a.sqrt_c = sqrtf((float)C);
+  // dq_i = sum_j P_ij (dO_i.v_j - D_i) k_j / sqrt(C)
+  a.x = q; a.y = k; a.dx = dq;
+  a.l1 = lse; a.u = dout; a.u0 = D; a.t = v; a.t_stride_b = 2LL * N;
+  if ((rc = pair_bwd_simt(a, st))) return rc;
+  // dk_j = sum_i P_ij (dO_i.v_j - D_i) q_i / sqrt(C): rows j, softmax statistics live on the columns i
+  a.x = k; a.y = q; a.dx = dk;
+  a.l1 = a.u = a.u0 = a.t = nullptr;
+  a.l2 = lse; a.w = dout; a.w0 = D; a.t2 = v; a.t2_stride_b = 2LL * N;
+  return pair_bwd_simt(a, st);
+}

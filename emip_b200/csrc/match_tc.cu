@@ -1,0 +1,483 @@
+// K1 / K2 forward on the 5th-gen tensor cores (sm_100a): fused
+//   S = X Y^T / sqrt(C)  ->  online row softmax  ->  expectation of a 2-vector per column
+// for a1 global matching (matching.py:16-39, both directions in one launch, the
+// backward direction being the same problem with the operand roles swapped) and
+// a2 flow-propagation attention (transformer.py:528-531).  The N x N score matrix
+// lives only in TMEM; it reaches HBM only when the caller asks for `corr`.
+//
+// Numerics: fp32 features are split once into bf16 hi + bf16 lo
+// (match_tc_split) and S is accumulated in fp32 as  hi.hi + hi.lo + lo.hi
+// (24 UMMA K16-steps per 128x128 tile, one TMEM accumulator): S rel. error ~4e-6,
+// flow rel-L2 ~1e-5 versus fp32 SGEMM.  Softmax statistics are fp32.
+//
+// CTA = 192 threads, persistent, one CTA per SM (193 KB smem, 256 TMEM columns):
+//   warp 0      TMA producer   (Q tile once per work item; K chunks through a 6-stage ring)
+//   warp 1      UMMA issuer    (one elected lane; also owns the TMEM allocation)
+//   warps 2..5  softmax        (thread <-> TMEM lane <-> one query row; no shuffles)
+// Two S buffers in TMEM let the MMAs of key tile t+1 overlap the softmax of tile t.
+// Work item = (problem p, 128-row query tile); problems enumerate (sample, direction).
+#include "common.cuh"
+#include "match_tc.cuh"
+#include "pair_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TM = 128;                 // query rows per work item (UMMA M)
+constexpr int TN = 128;                 // key columns per tile (UMMA N)
+constexpr int CH_ELEMS = 64;            // bf16 per 128-byte swizzle row
+constexpr int CHUNK_BYTES = TM * 128;   // one [128 rows x 128 B] SW128 box = 16 KB
+constexpr int NCHUNK = 4;               // hi[0:64] hi[64:128] lo[0:64] lo[64:128]
+constexpr int STAGES = 6;
+constexpr int MAXK = 2048;              // value table capacity (columns)
+constexpr int NTHREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + NCHUNK * CHUNK_BYTES;
+constexpr int OFF_V = OFF_K + STAGES * CHUNK_BYTES;
+constexpr int OFF_STAGE = OFF_V + 2 * MAXK * 4;
+constexpr int OFF_BAR = OFF_STAGE + 4 * 32 * 33 * 4;
+constexpr int NBAR = 2 + 2 * STAGES + 4;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack to align the base to 1024 B
+
+// ---- PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("emip match_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct KParams {
+  const float* v;
+  long long v_stride_b;
+  const float* sub;
+  float* out;
+  float* lse;
+  float* s_out;
+  int nb, nq, nk, y_shift, y_mod, s_first, s_count;
+  float inv_sqrt_c;      // 1/sqrt(C)
+  float sqrt_c;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const uint32_t q_full = bar0, q_empty = bar0 + 8;
+  auto k_full = [&](int s) { return bar0 + 16 + 8 * s; };
+  auto k_empty = [&](int s) { return bar0 + 16 + 8 * (STAGES + s); };
+  auto s_full = [&](int b) { return bar0 + 16 + 8 * (2 * STAGES + b); };
+  auto s_empty = [&](int b) { return bar0 + 16 + 8 * (2 * STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = (p.nq + TM - 1) / TM;
+  const int nkt = (p.nk + TN - 1) / TN;
+  const int n_items = p.nb * nqt;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t kphase = 0;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int prob = item / nqt, qt = item % nqt;
+        const int by = (prob + p.y_shift) % p.y_mod;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, NCHUNK * CHUNK_BYTES);
+        for (int c = 0; c < NCHUNK; ++c)
+          tma_load_3d(sbase + OFF_Q + c * CHUNK_BYTES, &map_x, q_full, c * CH_ELEMS, qt * TM, prob);
+        for (int kt = 0; kt < nkt; ++kt) {
+          for (int c = 0; c < NCHUNK; ++c) {
+            mbar_wait(k_empty(stage), kphase ^ 1);
+            mbar_expect_tx(k_full(stage), CHUNK_BYTES);
+            tma_load_3d(sbase + OFF_K + stage * CHUNK_BYTES, &map_y, k_full(stage), c * CH_ELEMS, kt * TN, by);
+            if (++stage == STAGES) { stage = 0; kphase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t kphase = 0;
+      uint32_t it = 0, tile = 0;
+      const int n_tail = ((p.nk - (nkt - 1) * TN) + 15) & ~15;
+      const uint32_t idesc_full = make_idesc(TN), idesc_tail = make_idesc(n_tail);
+      const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
+      // descriptor start-address units are 16 B: chunk = 1024 units, K16 step inside a swizzle row = 2 units
+      const uint64_t q_hi0 = qd, q_hi1 = qd + 1024, q_lo0 = qd + 2048, q_lo1 = qd + 3072;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1);
+        tc_fence_after();
+        for (int kt = 0; kt < nkt; ++kt, ++tile) {
+          const int buf = tile & 1;
+          const uint32_t use = tile >> 1;
+          mbar_wait(s_empty(buf), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          const uint32_t idesc = (kt == nkt - 1) ? idesc_tail : idesc_full;
+          uint32_t acc = 0;
+          for (int c = 0; c < NCHUNK; ++c) {
+            mbar_wait(k_full(stage), kphase);
+            tc_fence_after();
+            const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_K + stage * CHUNK_BYTES);
+            // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
+            const uint64_t a_hi = (c & 1) ? q_hi1 : q_hi0;
+            const uint64_t a_lo = (c & 1) ? q_lo1 : q_lo0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, acc);
+              acc = 1;
+            }
+            if (c < 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1);
+            }
+            umma_commit(k_empty(stage));       // frees the smem stage when these MMAs retire
+            if (++stage == STAGES) { stage = 0; kphase ^= 1; }
+          }
+          umma_commit(s_full(buf));            // S tile complete -> softmax warps
+        }
+        umma_commit(q_empty);                  // Q tile no longer read -> producer may overwrite
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps =====================
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r_in_tile = quarter * 32 + lane;
+    const int st = threadIdx.x - 64;                    // 0..127 within the softmax group
+    float* vtab = reinterpret_cast<float*>(smem + OFF_V);
+    float* stage_buf = reinterpret_cast<float*>(smem + OFF_STAGE) + (warp - 2) * 32 * 33;
+    const float c2 = 1.4426950408889634f * p.inv_sqrt_c;   // log2(e)/sqrt(C)
+    uint32_t tile = 0;
+    int cur_v = -1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int prob = item / nqt, qt = item % nqt;
+      const int row = qt * TM + r_in_tile;
+      const int v_id = (p.v_stride_b == 0) ? 0 : prob;
+      if (v_id != cur_v) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished with the old table
+        const float* vg = p.v + (size_t)prob * p.v_stride_b;
+        for (int i = st; i < 2 * p.nk; i += 128) {
+          int ch = i / p.nk, c = i - ch * p.nk;
+          vtab[ch * MAXK + c] = __ldg(vg + i);
+        }
+        // masked tail columns are multiplied by p = 0: keep them finite
+        for (int c = p.nk + st; c < ((p.nk + 31) & ~31); c += 128) { vtab[c] = 0.f; vtab[MAXK + c] = 0.f; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_v = v_id;
+      }
+      const bool emit = p.s_out != nullptr && prob >= p.s_first && prob < p.s_first + p.s_count;
+      float* sg = emit ? p.s_out + ((size_t)(prob - p.s_first) * p.nq) * p.nk : nullptr;
+      float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;
+      for (int kt = 0; kt < nkt; ++kt, ++tile) {
+        const int buf = tile & 1;
+        const uint32_t use = tile >> 1;
+        mbar_wait(s_full(buf), use & 1);
+        tc_fence_after();
+        const int col_base = kt * TN;
+        const int n_valid = min(TN, p.nk - col_base);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN;
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          const int nv = min(32, n_valid - c0);
+          if (emit) {
+            // transpose through smem so that each store instruction writes one 128-byte row segment
+#pragma unroll
+            for (int i = 0; i < 32; ++i) stage_buf[lane * 33 + i] = __uint_as_float(r[i]) * p.inv_sqrt_c;
+            __syncwarp();
+            const int grow0 = qt * TM + quarter * 32;
+            if (lane < nv) {
+              for (int rr = 0; rr < 32; ++rr) {
+                if (grow0 + rr < p.nq) sg[(size_t)(grow0 + rr) * p.nk + col_base + c0 + lane] = stage_buf[rr * 33 + lane];
+              }
+            }
+            __syncwarp();
+          }
+          float cmax = -INFINITY;
+          if (nv == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cmax = (i < nv) ? fmaxf(cmax, __uint_as_float(r[i])) : cmax;
+          }
+          const float m_new = fmaxf(m, cmax);
+          const float corr = exp2f((m - m_new) * c2);      // first chunk: exp2(-inf) = 0
+          const float mb = m_new * c2;
+          float ls = 0.f, lx = 0.f, ly = 0.f;
+          const float4* vx4 = reinterpret_cast<const float4*>(vtab + col_base + c0);
+          const float4* vy4 = reinterpret_cast<const float4*>(vtab + MAXK + col_base + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 vx = vx4[i4], vy = vy4[i4];
+            float pr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float e = exp2f(fmaf(__uint_as_float(r[i4 * 4 + k]), c2, -mb));
+              pr[k] = (nv == 32 || i4 * 4 + k < nv) ? e : 0.f;
+            }
+            ls += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+            lx = fmaf(pr[0], vx.x, lx); lx = fmaf(pr[1], vx.y, lx); lx = fmaf(pr[2], vx.z, lx); lx = fmaf(pr[3], vx.w, lx);
+            ly = fmaf(pr[0], vy.x, ly); ly = fmaf(pr[1], vy.y, ly); ly = fmaf(pr[2], vy.z, ly); ly = fmaf(pr[3], vy.w, ly);
+          }
+          l = fmaf(l, corr, ls);
+          sx = fmaf(sx, corr, lx);
+          sy = fmaf(sy, corr, ly);
+          m = m_new;
+        }
+        tc_fence_before();
+        mbar_arrive(s_empty(buf));                         // TMEM buffer drained (128 arrivals)
+      }
+      if (row < p.nq) {
+        float ex = sx / l, ey = sy / l;
+        if (p.sub != nullptr) { ex -= __ldg(p.sub + row); ey -= __ldg(p.sub + p.nq + row); }
+        p.out[((size_t)prob * 2 + 0) * p.nq + row] = ex;
+        p.out[((size_t)prob * 2 + 1) * p.nq + row] = ey;
+        if (p.lse != nullptr) p.lse[(size_t)prob * p.nq + row] = m * p.inv_sqrt_c + logf(l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- operand split: fp32 -> bf16 hi | bf16 lo, token-major -------------------
+__device__ __forceinline__ void split2(float a, float b, __nv_bfloat162& hi, __nv_bfloat162& lo) {
+  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  hi = __halves2bfloat162(ah, bh);
+  lo = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+}
+
+// src [nb][128][n] (channel-major) -> dst [nb][n][256]
+__global__ void __launch_bounds__(256)
+split_cn_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n) {
+  __shared__ float t[128][65];
+  const int b = blockIdx.y, tok0 = blockIdx.x * 64;
+  const float* s = src + (size_t)b * 128 * n;
+  for (int i = threadIdx.x; i < 128 * 64; i += 256) {
+    int c = i >> 6, r = i & 63;
+    t[c][r] = (tok0 + r < n) ? __ldg(s + (size_t)c * n + tok0 + r) : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + ((size_t)b * n + tok0) * 256;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    int r = i >> 6, cp = i & 63;
+    if (tok0 + r < n) {
+      __nv_bfloat162 hi, lo;
+      split2(t[2 * cp][r], t[2 * cp + 1][r], hi, lo);
+      *reinterpret_cast<__nv_bfloat162*>(d + (size_t)r * 256 + 2 * cp) = hi;
+      *reinterpret_cast<__nv_bfloat162*>(d + (size_t)r * 256 + 128 + 2 * cp) = lo;
+    }
+  }
+}
+
+// src [rows][128] (token-major) -> dst [rows][256]
+__global__ void __launch_bounds__(256)
+split_nc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float2 per thread
+  if (i >= rows * 64) return;
+  long long r = i >> 6;
+  int cp = (int)(i & 63);
+  float2 v = __ldg(reinterpret_cast<const float2*>(src + r * 128) + cp);
+  __nv_bfloat162 hi, lo;
+  split2(v.x, v.y, hi, lo);
+  *reinterpret_cast<__nv_bfloat162*>(dst + r * 256 + 2 * cp) = hi;
+  *reinterpret_cast<__nv_bfloat162*>(dst + r * 256 + 128 + 2 * cp) = lo;
+}
+
+// ---- host side -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [nb][n][256] bf16, box = 64 elements x 128 rows x 1 batch, 128-byte swizzle, OOB rows read as zero
+int make_map(CUtensorMap* m, const void* base, int nb, int n) {
+  EncodeTiledFn enc = get_encoder();
+  if (enc == nullptr) {
+    emip_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return EMIP_ENOSYS;
+  }
+  cuuint64_t dims[3] = {256, (cuuint64_t)n, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {512, (cuuint64_t)n * 512};
+  cuuint32_t box[3] = {CH_ELEMS, TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    emip_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return EMIP_EINVAL;
+  }
+  return EMIP_OK;
+}
+
+}  // namespace
+
+bool match_tc_supported(int nq, int nk, int c) { return c == 128 && nk <= MAXK && nk >= 16 && nq >= 1; }
+
+size_t match_tc_split_bytes(int nb, int n, int c) { return emip_align_up((size_t)nb * n * 2 * c * 2, 1024); }
+
+int match_tc_split(const float* src, void* dst, int nb, int n, int c, int layout, int dst_batch0, cudaStream_t st) {
+  if (c != 128) { emip_set_error("match_tc_split: C=%d unsupported", c); return EMIP_ENOSYS; }
+  if (nb == 0 || n == 0) return EMIP_OK;
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)dst_batch0 * n * 256;
+  if (layout == EMIP_LAYOUT_CN) {
+    dim3 grid((n + 63) / 64, nb);
+    split_cn_kernel<<<grid, 256, 0, st>>>(src, d, n);
+  } else {
+    long long rows = (long long)nb * n;
+    split_nc_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(src, d, rows);
+  }
+  EMIP_CHECK_LAUNCH("match_tc_split");
+  return EMIP_OK;
+}
+
+int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
+  if (a.nb == 0) return EMIP_OK;
+  if (!match_tc_supported(a.nq, a.nk, 128)) { emip_set_error("match_tc_fwd: unsupported shape"); return EMIP_ENOSYS; }
+  CUtensorMap mx, my;
+  int rc;
+  if ((rc = make_map(&mx, a.x_split, a.nbx, a.nq))) return rc;
+  if ((rc = make_map(&my, a.y_split, a.nby, a.nk))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  KParams p;
+  p.v = a.v; p.v_stride_b = a.v_stride_b; p.sub = a.sub; p.out = a.out; p.lse = a.lse; p.s_out = a.s_out;
+  p.nb = a.nb; p.nq = a.nq; p.nk = a.nk; p.y_shift = a.y_shift; p.y_mod = a.y_mod;
+  p.s_first = a.s_first; p.s_count = a.s_count;
+  p.sqrt_c = a.sqrt_c; p.inv_sqrt_c = 1.0f / a.sqrt_c;
+  const int nqt = (a.nq + TM - 1) / TM;
+  int grid = a.nb * nqt;
+  if (grid > emip_num_sms()) grid = emip_num_sms();
+  match_tc_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, p);
+  EMIP_CHECK_LAUNCH("match_tc_fwd");
+  return EMIP_OK;
+}

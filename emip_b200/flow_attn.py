@@ -1,0 +1,87 @@
+"""FeatureFlowAttention: drop-in for reference gmflow/transformer.py:485-533 (K2)."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import I, SZ, ptr, stream_ptr
+from ._ws import workspace
+
+
+class _FlowAttnCore(torch.autograd.Function):
+    """out = softmax(q k^T / sqrt(C)) v  with q,k [B,N,C], v [B,2,N] (no gradient to v)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, flags):
+        B, N, C = q.shape
+        q = q.contiguous()
+        k = k.contiguous()
+        v = v.contiguous()
+        L = _lib.lib()
+        L.emip_flow_attn_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_flow_attn_workspace(I(B), I(N), I(C)), q.device)
+        out = torch.empty((B, 2, N), dtype=torch.float32, device=q.device)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        lse = torch.empty((B, N), dtype=torch.float32, device=q.device) if need_grad else None
+        _lib.check(L.emip_flow_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ctypes.c_void_p(ws_ptr), SZ(ws_n),
+                                        I(B), I(N), I(C), I(flags), stream_ptr()), "emip_flow_attn_fwd")
+        ctx.save_for_backward(q, k, v, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError("emip_b200 flow attention has no gradient w.r.t. the value: the model passes "
+                                      "flow.detach() (gmflow.py:137)")
+        B, N, C = q.shape
+        L = _lib.lib()
+        L.emip_flow_attn_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_flow_attn_workspace(I(B), I(N), I(C)), q.device)
+        dq = torch.empty_like(q)
+        dk = torch.empty_like(k)
+        _lib.check(L.emip_flow_attn_bwd(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout.contiguous()), ptr(dq),
+                                        ptr(dk), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(N), I(C), stream_ptr()),
+                   "emip_flow_attn_bwd")
+        return dq, dk, None, None
+
+
+def flow_attention_core(q, k, v, exact_fp32=False):
+    if not q.is_cuda:
+        raise _lib.EmipError("emip_b200 flow attention needs CUDA tensors (no CPU fallback)")
+    return _FlowAttnCore.apply(q, k, v, 1 if exact_fp32 else 0)
+
+
+class FeatureFlowAttention(nn.Module):
+    """Flow propagation with self-attention on features (query = key source = feature0, value = flow).
+
+    Same constructor, parameters (``q_proj``, ``k_proj``: Linear(C, C) with bias,
+    xavier-uniform weights) and forward signature as the reference module
+    (transformer.py:485-533), including its quirk that the key is projected from
+    the *projected* query (l.523-524).  ``local_window_attn=True`` is the dead
+    branch of the reference (``prop_radius_list: [-1]``) and is not implemented.
+    """
+
+    def __init__(self, in_channels, **kwargs):
+        super().__init__()
+        self.q_proj = nn.Linear(in_channels, in_channels)
+        self.k_proj = nn.Linear(in_channels, in_channels)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self.exact_fp32 = False
+
+    def forward(self, feature0, flow, local_window_attn=False, local_window_radius=1, **kwargs):
+        if local_window_attn:
+            raise NotImplementedError("local-window flow propagation is unused by EMIP (prop_radius_list: [-1])")
+        b, c, h, w = feature0.size()
+        query = feature0.view(b, c, h * w).permute(0, 2, 1)       # [B, HW, C]
+        query = self.q_proj(query)                                 # transformer.py:523
+        key = self.k_proj(query)                                   # transformer.py:524
+        value = flow.reshape(b, flow.size(1), h * w)               # [B, 2, HW]
+        if flow.size(1) != 2:
+            raise ValueError("emip_b200 flow attention propagates 2-channel flow")
+        out = flow_attention_core(query, key, value.detach() if not value.requires_grad else value,
+                                  exact_fp32=self.exact_fp32)
+        return out.view(b, 2, h, w)

@@ -1,0 +1,105 @@
+/* emip_b200 -- C ABI of the B200-native EMIP motion-stream hot path.
+ *
+ * The reference (zhangxin06/EMIP) has no FFI layer: its hot path is four Python
+ * functions/modules that call ATen.  Each entry point below replaces one of
+ * those call sites; the citation names the reference interface it stands in for
+ * (paths relative to the reference root).  The Python host side
+ * (emip_b200/*.py) binds these with ctypes; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *  - plain C: device pointers + sizes, no torch types.  Pointers are CUDA device
+ *    pointers on the current device; fp32 unless stated otherwise.
+ *  - the CALLER owns every buffer (outputs, saved-for-backward, workspace); the
+ *    library never allocates device memory, never synchronises the stream and
+ *    never throws.  `stream` is a cudaStream_t passed as void*.
+ *  - returns 0 on success, a negative errno-style code for argument errors
+ *    (-22 EINVAL, -38 ENOSYS, -12 ENOMEM = workspace too small) or a positive
+ *    cudaError_t for launch failures; emip_last_error() holds the message
+ *    (thread-local).
+ *  - re-entrant: forward is called on the Python thread, backward on autograd
+ *    engine threads.  The only shared state is a mutex-guarded tensor-map cache.
+ *  - there is NO CPU fallback: on a machine without an sm_100 device every
+ *    compute entry point fails.
+ */
+#ifndef EMIP_B200_H
+#define EMIP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMIP_ABI_VERSION 1
+
+#define EMIP_PAD_BORDER 0
+#define EMIP_PAD_ZEROS 1
+
+/* flags */
+#define EMIP_FLAG_EXACT_FP32 1 /* force the exact-fp32 CUDA-core path (no bf16 hi/lo tensor-core split) */
+
+/* ---- plumbing ------------------------------------------------------------ */
+const char* emip_last_error(void);
+int emip_abi_version(void);
+/* 0 when the current CUDA device is sm_100 (B200); error otherwise. */
+int emip_device_check(void);
+
+/* ---- a3: flow_warp ------------------------------------------------------- */
+/* Replaces loss/warp_utils.py:83-93 flow_warp(x, flow12, pad, mode='bilinear')
+ * (mesh_grid :7-13 + norm_grid :16-23 + F.grid_sample(align_corners=True)).
+ *   x    [B,C,H,W] contiguous        image to sample
+ *   flow element (b,ch,y,x) at flow[b*flow_stride_b + ch*flow_stride_c + y*W + x]
+ *        (ch 0 = dx, 1 = dy; strides in elements) -- covers the non-contiguous
+ *        flow[:, :2] / flow[:, 2:] slices of loss/loss_flow.py:90-91
+ *   out  [B,C,H,W] contiguous
+ *   pad_mode EMIP_PAD_BORDER ('border', the photometric loss) or EMIP_PAD_ZEROS. */
+int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
+                       long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream);
+/* Backward of the above.  dflow [B,2,H,W] contiguous is overwritten.  dx may be
+ * NULL (images need no gradient in the photometric loss); otherwise it must be
+ * zero-filled [B,C,H,W] and receives the scatter-added image gradient. */
+int emip_flow_warp_bwd(const float* x, const float* flow, const float* dout, float* dflow, float* dx,
+                       int B, int C, int H, int W, long long flow_stride_b, long long flow_stride_c,
+                       int pad_mode, void* stream);
+
+/* ---- a1: GMFlow global matching ------------------------------------------ */
+/* Replaces model/EMIP_short/motion/gmflow/matching.py:8-41
+ *   global_correlation_softmax(feature0, feature1, pred_bidir_flow) -> (flow, prob, corr)
+ * S[b,i,j] = f0[b,:,i].f1[b,:,j]/sqrt(C); flow_fw = softmax_j(S) g - g; flow_bw likewise on S^T.
+ *   f0, f1  [B,C,H,W] contiguous (C must be 128)
+ *   flow    [nd*B,2,H,W] out, nd = bidir ? 2 : 1 (first B forward, last B backward; matching.py:29,39)
+ *   corr    NULL, or the scaled scores (matching.py:16-20).  Memory layout: bidir -> [B,HW(j),HW(i)], i.e.
+ *           corr[b,k,y,x] contiguous; uni-directional -> [B,HW(i),HW(j)] (the reference's own layout, of which
+ *           its `corr` is a permuted view).  `prob` (matching.py:34) is never produced: no caller reads it.
+ *   lse     NULL, or [nd*B,HW] row log-sum-exp, required by the backward
+ *   workspace  >= emip_global_matching_workspace(B,C,H,W) bytes, 1024-byte aligned
+ *   flags   0 = tensor-core path (bf16 hi/lo split, fp32 accumulate); EMIP_FLAG_EXACT_FP32 = CUDA-core fp32 */
+size_t emip_global_matching_workspace(int B, int C, int H, int W);
+int emip_global_matching_fwd(const float* f0, const float* f1, float* flow, float* corr, float* lse,
+                             void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir, int flags,
+                             void* stream);
+/* Backward of the above (what autograd derives for matching.py:16-39).  dflow [nd*B,2,H,W] and/or dcorr (same
+ * layout as corr) may be NULL; flow and lse are the forward outputs.  df0, df1 [B,C,H,W] are overwritten. */
+int emip_global_matching_bwd(const float* f0, const float* f1, const float* flow, const float* lse,
+                             const float* dflow, const float* dcorr, float* df0, float* df1, void* workspace,
+                             size_t ws_bytes, int B, int C, int H, int W, int bidir, void* stream);
+
+/* ---- a2: flow-propagation attention -------------------------------------- */
+/* Replaces the attention core of FeatureFlowAttention.forward,
+ * model/EMIP_short/motion/gmflow/transformer.py:526-532: out = softmax(q k^T / sqrt(C)) v.
+ *   q, k  [B,N,C] token-major, already projected (transformer.py:523-524 stay library GEMMs)
+ *   v     [B,2,N]  (the flow viewed as [B,2,H*W])      out [B,2,N]
+ *   lse   NULL or [B,N] (needed by the backward) */
+size_t emip_flow_attn_workspace(int B, int N, int C);
+int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse, void* workspace,
+                       size_t ws_bytes, int B, int N, int C, int flags, void* stream);
+/* Backward w.r.t. q and k only: the value is flow.detach() in the model (gmflow.py:137). */
+int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
+                       const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes, int B, int N,
+                       int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMIP_B200_H */

@@ -100,8 +100,9 @@ def flow_warp(x, flow12, pad="border"):
     ix = ((nx + 1) / 2) * (w - 1)                                     # ATen unnormalize
     iy_ = ((ny + 1) / 2) * (h - 1)
     if pad == "border":
-        ix = ix.clamp(0, w - 1)
-        iy_ = iy_.clamp(0, h - 1)
+        # ATen clip_coordinates_set_grad: the gradient is zero ON and outside the border
+        ix = torch.where((ix > 0) & (ix < w - 1), ix, ix.detach().clamp(0, w - 1))
+        iy_ = torch.where((iy_ > 0) & (iy_ < h - 1), iy_, iy_.detach().clamp(0, h - 1))
     x0 = torch.floor(ix)
     y0 = torch.floor(iy_)
     wx = ix - x0

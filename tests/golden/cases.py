@@ -78,6 +78,7 @@ A3_CASES = {
     "a3_small_zeros": dict(b=2, c=3, h=9, w=11, sigma=3.0, pad="zeros", seed=32),
     "a3_mid_border": dict(b=2, c=3, h=40, w=56, sigma=20.0, pad="border", seed=33),
     "a3_c5_border": dict(b=1, c=5, h=17, w=23, sigma=5.0, pad="border", seed=34),
+    "a3_zero_flow_edge": dict(b=1, c=3, h=8, w=12, sigma=0.0, pad="border", seed=36),
 }
 A4_CASES = {
     "a4_small": dict(b=2, h=6, w=8, xs=2.2, x1s=1.0, seed=41, full=False),

@@ -1,0 +1,192 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs golden vectors recorded from the
+reference and vs the CPU oracle on identical seeded inputs.  Run with -m gpu on a B200."""
+import pytest
+import torch
+
+import cases
+from oracle import restate as O
+
+pytestmark = pytest.mark.gpu
+
+# north_star: outputs within 1e-3 relative (rel-L2 per tensor) in fp32
+TOL_OUT = 1e-3
+TOL_EXACT = 5e-5       # exact-fp32 CUDA-core path: re-association only
+TOL_GRAD = 1e-3
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ----------------------------------------------------------------------------- a3
+@pytest.mark.parametrize("name", list(cases.A3_CASES))
+def test_a3_flow_warp_golden(golden, name):
+    from emip_b200.warp import flow_warp
+    g = golden(name)
+    s = cases.A3_CASES[name]
+    d = cases.a3_inputs(s)
+    x = dev(d["x"]).requires_grad_(True)
+    fl = dev(d["flow"]).requires_grad_(True)
+    out = flow_warp(x, fl, pad=s["pad"])
+    cases.check_packed(out, g["out"], 1e-5, "out")
+    (out * dev(d["wout"])).sum().backward()
+    cases.check_packed(fl.grad, g["dflow"], 1e-4, "dflow")
+    cases.check_packed(x.grad, g["dx"], 1e-5, "dx")
+
+
+def test_a3_flow_warp_slices(golden):
+    from emip_b200.warp import flow_warp
+    g = golden("a3_slice")
+    s = g["spec"]
+    flow4 = dev(cases.randn(s["seed"], (s["b"], 4, s["h"], s["w"]), s["sigma"]))
+    x = dev(cases.randn(s["seed"] + 1, (s["b"], 3, s["h"], s["w"])))
+    cases.check_packed(flow_warp(x, flow4[:, :2]), g["out_fw"], 1e-5)
+    cases.check_packed(flow_warp(x, flow4[:, 2:]), g["out_bw"], 1e-5)
+
+
+@pytest.mark.parametrize("kind,mag", [("iid", 5.0), ("iid", 20.0), ("smooth", 30.0)])
+def test_a3_flow_warp_fullsize_vs_oracle(kind, mag):
+    """352x352 (config c5 shape, B reduced) vs the CPU oracle, incl. backward to flow."""
+    from emip_b200.warp import flow_warp
+    B, C, H, W = 2, 3, 352, 352
+    x = cases.randn(61, (B, C, H, W))
+    fl4 = cases.randn(62, (B, 4, H, W), mag) if kind == "iid" else torch.cat(
+        [cases.smooth_flow(63, B, H, W, mag), cases.smooth_flow(64, B, H, W, mag)], 1)
+    wout = cases.randn(65, (B, C, H, W))
+    flc = fl4[:, 2:].clone().requires_grad_(True)
+    ref = O.flow_warp(x, flc)
+    (ref * wout).sum().backward()
+    flg = dev(fl4).requires_grad_(True)
+    out = flow_warp(dev(x), flg[:, 2:])
+    (out * dev(wout)).sum().backward()
+    assert rel(out, ref) < 1e-5
+    assert rel(flg.grad[:, 2:], flc.grad) < 1e-4
+    assert flg.grad[:, :2].abs().max().item() == 0.0
+
+
+def test_a3_properties_full_batch():
+    """Size-independent properties at the benchmark size (B=64, 3x352x352)."""
+    from emip_b200.warp import flow_warp
+    B, C, H, W = 64, 3, 352, 352
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    zero = torch.zeros(B, 2, H, W, device="cuda")
+    assert (flow_warp(x, zero) - x).abs().max().item() < 2e-5          # identity (fp32 round trip of the grid)
+    shift = zero.clone()
+    shift[:, 0] = 3.0                                                   # integer shift: out[..., j] = x[..., min(j+3, W-1)]
+    out = flow_warp(x, shift)
+    assert (out[..., : W - 3] - x[..., 3:]).abs().max().item() < 2e-4
+    assert (out[..., W - 3:] - x[..., W - 1:]).abs().max().item() < 2e-4
+    fl = 20 * torch.randn(B, 2, H, W, device="cuda", generator=g)
+    a = torch.randn(B, 1, 1, 1, device="cuda", generator=g)
+    x2 = torch.randn(B, C, H, W, device="cuda", generator=g)
+    lhs = flow_warp(a * x + x2, fl)
+    rhs = a * flow_warp(x, fl) + flow_warp(x2, fl)                      # linear in the image
+    assert rel(lhs, rhs) < 1e-5
+    assert out.min() >= x.min() - 1e-4 and out.max() <= x.max() + 1e-4  # convex combination (border mode)
+
+
+def test_a3_empty_batch():
+    from emip_b200.warp import flow_warp
+    x = torch.zeros(0, 3, 8, 8, device="cuda")
+    assert flow_warp(x, torch.zeros(0, 2, 8, 8, device="cuda")).shape == (0, 3, 8, 8)
+
+
+# ----------------------------------------------------------------------------- a1
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
+@pytest.mark.parametrize("name", list(cases.A1_CASES))
+def test_a1_global_matching_golden(golden, name, exact):
+    from emip_b200.matching import global_correlation_softmax
+    g = golden(name)
+    s = cases.A1_CASES[name]
+    d = cases.a1_inputs(s)
+    f0 = dev(d["f0"]).requires_grad_(True)
+    f1 = dev(d["f1"]).requires_grad_(True)
+    flow, prob, corr = global_correlation_softmax(f0, f1, True, exact_fp32=exact)
+    assert prob is None
+    tol = TOL_EXACT if exact else TOL_OUT
+    e_flow = cases.check_packed(flow, g["flow"], tol, "flow")
+    e_corr = cases.check_packed(corr, g["corr"], TOL_EXACT, "corr")
+    print(f"{name} exact={exact}: flow rel-L2 {e_flow:.2e} corr rel-L2 {e_corr:.2e}")
+    ((flow * dev(d["wflow"])).sum() + (corr * dev(d["wcorr"])).sum()).backward()
+    cases.check_packed(f0.grad, g["df0"], TOL_GRAD, "df0")
+    cases.check_packed(f1.grad, g["df1"], TOL_GRAD, "df1")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
+def test_a1_insitu_c1(golden, exact):
+    """Features captured inside a real CoUpdater forward (config c1): logits 67..212, near-one-hot softmax."""
+    from emip_b200.matching import global_correlation_softmax
+    g = golden("c1_insitu")
+    flow, _, corr = global_correlation_softmax(dev(g["f0"]), dev(g["f1"]), True, exact_fp32=exact)
+    e = cases.check_packed(flow, g["flow"], TOL_EXACT if exact else TOL_OUT, "flow")
+    cases.check_packed(corr, g["corr"], TOL_EXACT, "corr")
+    print(f"c1 in-situ exact={exact}: flow rel-L2 {e:.2e}")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
+def test_a1_unidirectional_and_no_corr(exact):
+    from emip_b200.matching import global_correlation_softmax
+    s = cases.A1_CASES["a1_ragged"]
+    d = cases.a1_inputs(s)
+    ref_flow, _, ref_corr = O.global_correlation_softmax(d["f0"], d["f1"], False)
+    flow, _, corr = global_correlation_softmax(dev(d["f0"]), dev(d["f1"]), False, exact_fp32=exact)
+    assert flow.shape == ref_flow.shape and corr.shape == ref_corr.shape
+    assert rel(flow, ref_flow) < (TOL_EXACT if exact else TOL_OUT)
+    assert rel(corr, ref_corr) < TOL_EXACT
+    flow2, _, corr2 = global_correlation_softmax(dev(d["f0"]), dev(d["f1"]), True, return_corr=False, exact_fp32=exact)
+    assert corr2 is None and rel(flow2[: s["b"]], ref_flow) < (TOL_EXACT if exact else TOL_OUT)
+
+
+def test_a1_c2_properties():
+    """Config c2 (B=16, 44x44, C=128): tensor-core path vs exact path, and swap symmetry."""
+    from emip_b200.matching import global_correlation_softmax
+    f0 = dev(cases.randn(2, (16, 128, 44, 44), 4.1))
+    f1 = dev(cases.randn(3, (16, 128, 44, 44), 4.1))
+    flow_tc, _, corr_tc = global_correlation_softmax(f0, f1, True)
+    flow_ex, _, corr_ex = global_correlation_softmax(f0, f1, True, exact_fp32=True)
+    assert rel(flow_tc, flow_ex) < TOL_OUT
+    assert rel(corr_tc, corr_ex) < TOL_EXACT
+    # swapping the frames swaps the forward and backward flows and transposes corr
+    flow_sw, _, corr_sw = global_correlation_softmax(f1, f0, True)
+    assert rel(flow_sw[:16], flow_tc[16:]) < 1e-6 and rel(flow_sw[16:], flow_tc[:16]) < 1e-6
+    assert rel(corr_sw.view(16, 1936, 1936).transpose(1, 2), corr_tc.view(16, 1936, 1936)) < 1e-6
+
+
+# ----------------------------------------------------------------------------- a2
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
+@pytest.mark.parametrize("name", list(cases.A2_CASES))
+def test_a2_flow_attention_golden(golden, name, exact):
+    from emip_b200.flow_attn import FeatureFlowAttention
+    g = golden(name)
+    s = cases.A2_CASES[name]
+    d = cases.a2_inputs(s)
+    m = FeatureFlowAttention(s["c"]).cuda()
+    m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
+    m.exact_fp32 = exact
+    x = dev(d["x"]).requires_grad_(True)
+    out = m(x, dev(d["flow"]))
+    e = cases.check_packed(out, g["out"], TOL_EXACT if exact else TOL_OUT, "out")
+    print(f"{name} exact={exact}: out rel-L2 {e:.2e}")
+    (out * dev(d["wout"])).sum().backward()
+    cases.check_packed(x.grad, g["dx"], TOL_GRAD, "dx")
+    cases.check_packed(m.q_proj.weight.grad, g["dqw"], TOL_GRAD, "dqw")
+    cases.check_packed(m.q_proj.bias.grad, g["dqb"], TOL_GRAD, "dqb")
+    cases.check_packed(m.k_proj.weight.grad, g["dkw"], TOL_GRAD, "dkw")
+
+
+def test_a2_insitu_c1(golden):
+    from emip_b200.flow_attn import FeatureFlowAttention
+    g = golden("c1_insitu")
+    m = FeatureFlowAttention(128).cuda()
+    m.load_state_dict(g["ffa_params"])
+    flow = dev(g["flow"]["full"])
+    out = m(torch.cat((dev(g["f0"]), dev(g["f1"])), 0), flow)
+    e = cases.check_packed(out, g["ffa_out"], TOL_OUT, "ffa_out")
+    print(f"c1 in-situ FFA: rel-L2 {e:.2e}")
