@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the EMIP motion-stream hot path on B200 (BASELINE.json metric).
+
+Workload (config c2 of BASELINE.json): GMFlow global correlation + bidirectional softmax flow
+regression at 1/8 resolution of a 352x352 pair (44x44 tokens, C=128), batch 16 synthetic frame
+pairs per GPU.  One "step" = one call of ``global_correlation_softmax(f0, f1, True)`` through the
+C ABI: operand split pre-pass + the fused tcgen05 kernel, producing flow_fw/flow_bw and ``corr``.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
+    python bench.py --impl reference ...                          CPU arm (reference algorithm, host cores)
+
+N > 1 is launched by torchrun (one rank per GPU, batch-sharded: every rank owns 16 pairs; no
+data-path collective -- the only collectives are the timing barrier and the max-over-ranks).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+B_PER_GPU, C, H, W = 16, 128, 44, 44
+N = H * W
+FEATURE_STD = 4.1              # matches the feature scale seen inside the model
+N_INPUT_SETS = 8               # rotated so that the live footprint (8 x 32 MB in + 240 MB corr out) exceeds L2
+ALG_FLOP_PER_PAIR = 2.0 * N * N * C + 8.0 * N * N          # S counted once
+EXEC_MMA_FLOP_PER_PAIR = 2.0 * N * N * C * 3 * 2           # bf16 hi/lo split (x3), both directions (x2)
+WARP_B, WARP_C, WARP_H, WARP_W = 64, 3, 352, 352
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_arm(n_runs, batch):
+    """The reference algorithm (matching.py:8-41) restated on the CPU (oracle port), all host threads."""
+    import torch
+    import cases
+    from oracle import restate as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f0 = cases.randn(2, (batch, C, H, W), FEATURE_STD)
+    f1 = cases.randn(3, (batch, C, H, W), FEATURE_STD)
+    with torch.no_grad():
+        O.global_correlation_softmax(f0, f1, True)           # warm-up
+        times = []
+        for _ in range(n_runs):
+            t0 = time.perf_counter()
+            O.global_correlation_softmax(f0, f1, True)
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, cores = cpu_reference_arm(max(1, args.steps), B_PER_GPU)
+    for _ in range(args.warmup):
+        pass  # warm-up happened inside cpu_reference_arm (one untimed pass); steps are full passes
+    ms = 1e3 * sum(times) / len(times)
+    v = B_PER_GPU / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "frame-pairs/s", "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full passes of the c2 batch ({B_PER_GPU} pairs) on host cores"},
+        "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "c2: GMFlow global correlation + bidirectional softmax flow regression, 44x44 tokens, C=128, "
+                        "batch 16 pairs per GPU, corr emitted",
+            "pairs_per_gpu": B_PER_GPU, "global_pairs": B_PER_GPU * n_gpus, "tokens": N, "channels": C,
+            "l2_policy": f"inputs rotate over {N_INPUT_SETS} sets; live footprint > 126 MB L2",
+            "sharding": f"batch-sharded x{n_gpus}, no data-path collective"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from emip_b200 import _lib
+    from emip_b200._lib import I, SZ, LL, ptr
+    from emip_b200._ws import workspace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    _lib.check(L.emip_device_check(), "emip_device_check")
+    from emip_b200.matching import global_correlation_softmax
+    from emip_b200.warp import flow_warp
+
+    K, Wm = args.steps, max(3, args.warmup)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    sets = [(FEATURE_STD * torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g),
+             FEATURE_STD * torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g)) for _ in range(N_INPUT_SETS)]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        f0, f1 = sets[i % N_INPUT_SETS]
+        return global_correlation_softmax(f0, f1, True)
+
+    # ---------------- value: inputs resident in HBM, whole API call ----------------
+    with torch.no_grad():
+        for i in range(Wm):
+            step(i)
+        barrier()
+        with ClockSampler(local) as clk:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                step(i)
+            e1.record(stream)
+            barrier()
+        ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / K
+    value = world * B_PER_GPU / (ms_step / 1e3)
+
+    # ---------------- e2e: host buffers, H2D + call + D2H inside the timed region ----------------
+    hf0 = [s[0].cpu().pin_memory() for s in sets[:2]]
+    hf1 = [s[1].cpu().pin_memory() for s in sets[:2]]
+    d0, d1 = torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1])
+    hflow = torch.empty((2 * B_PER_GPU, 2, H, W), dtype=torch.float32).pin_memory()
+    Ke = max(5, min(K, 50))
+    with torch.no_grad():
+        for i in range(3):
+            d0.copy_(hf0[i % 2], non_blocking=True); d1.copy_(hf1[i % 2], non_blocking=True)
+            hflow.copy_(global_correlation_softmax(d0, d1, True)[0], non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            d0.copy_(hf0[i % 2], non_blocking=True)
+            d1.copy_(hf1[i % 2], non_blocking=True)
+            flow, _, corr = global_correlation_softmax(d0, d1, True)
+            hflow.copy_(flow, non_blocking=True)
+            torch.cuda.synchronize()          # the caller reads the result on the host every step
+        e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B_PER_GPU * Ke / te.item()
+    h2d = 2 * B_PER_GPU * C * N * 4
+    d2h = 2 * B_PER_GPU * 2 * N * 4
+
+    line = {
+        "metric": "frame-pairs/s", "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke},
+        "gpu_launches": 4 * K,     # per step: pixel grid + 2 operand splits + fused matching kernel
+    }
+
+    if rank == 0:
+        pk = peaks()
+        # ---------------- roofline: the fused tcgen05 kernel alone, CUDA events on its stream ----------------
+        L.emip_global_matching_workspace.restype = ctypes.c_size_t
+        nbytes = L.emip_global_matching_workspace(I(B_PER_GPU), I(C), I(H), I(W))
+        wss = [workspace(nbytes, dev) for _ in range(N_INPUT_SETS)]
+        flow = torch.empty((2 * B_PER_GPU, 2, H, W), device=dev)
+        corr = torch.empty((B_PER_GPU, N, H, W), device=dev)
+        sp = ctypes.c_void_p(stream.cuda_stream)
+
+        def kernel_only(i, flags, corr_t):
+            f0, f1 = sets[i % N_INPUT_SETS]
+            _, wp, wn = wss[i % N_INPUT_SETS]
+            _lib.check(L.emip_global_matching_fwd(ptr(f0), ptr(f1), ptr(flow), ptr(corr_t), None, ctypes.c_void_p(wp),
+                                                  SZ(wn), I(B_PER_GPU), I(C), I(H), I(W), I(1), I(flags), sp), "fwd")
+        for i in range(N_INPUT_SETS):
+            kernel_only(i, 0, corr)            # fills every workspace with its operand split
+        res = {}
+        for name, corr_t in (("with_corr", corr), ("flow_only", None)):
+            for i in range(5):
+                kernel_only(i, 2, corr_t)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                kernel_only(i, 2, corr_t)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / K
+        k_ms = res["with_corr"]
+        alg = ALG_FLOP_PER_PAIR * B_PER_GPU
+        ach = alg / (k_ms * 1e-3) / 1e12
+        line["roofline"] = {
+            "kernel": "match_tc_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": ach / pk["tf"], "traffic": None, "peak_source": pk["src"] + " burst bf16 (cuBLAS)",
+            "launch_ms": k_ms, "launch_ms_flow_only": res["flow_only"],
+            "executed_mma_tflops": EXEC_MMA_FLOP_PER_PAIR * B_PER_GPU / (k_ms * 1e-3) / 1e12,
+            "executed_mma_frac": EXEC_MMA_FLOP_PER_PAIR * B_PER_GPU / (k_ms * 1e-3) / 1e12 / pk["tf"],
+            "corr_write_gbs": B_PER_GPU * N * N * 4 / (k_ms * 1e-3) / 1e9,
+            "note": "achieved counts S once (2BN^2C+8BN^2); executed = x3 (bf16 hi/lo split) x2 (both directions)",
+        }
+        # ---------------- secondary: flow_warp (K3) HBM roofline at B=64, 3x352x352 ----------------
+        import cases
+        x = torch.randn(WARP_B, WARP_C, WARP_H, WARP_W, device=dev, generator=g)
+        fl_s = torch.cat([cases.smooth_flow(11, WARP_B, WARP_H, WARP_W, 30.0),
+                          cases.smooth_flow(12, WARP_B, WARP_H, WARP_W, 30.0)], 1).to(dev)
+        fl_i = 5.0 * torch.randn(WARP_B, 4, WARP_H, WARP_W, device=dev, generator=g)
+        out = torch.empty_like(x)
+        fw_bytes = WARP_B * WARP_H * WARP_W * (2 * WARP_C + 2) * 4
+        kw = {}
+        for name, fl in (("smooth", fl_s), ("iid5px", fl_i)):
+            def call():
+                _lib.check(L.emip_flow_warp_fwd(ptr(x), ptr(fl), ptr(out), I(WARP_B), I(WARP_C), I(WARP_H), I(WARP_W),
+                                                LL(fl.stride(0)), LL(fl.stride(1)), I(0), sp), "warp")
+            for _ in range(5):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(50):
+                call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 50
+            kw[name] = {"launch_ms": ms, "achieved": fw_bytes / (ms * 1e-3) / 1e9, "frac": fw_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
+        line["flow_warp_roofline"] = {"kernel": "flow_warp_fwd_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
+                                      "bytes_per_launch": fw_bytes, "workload": "B=64, 3x352x352 fp32 (254 MB > L2)",
+                                      "flows": kw}
+        # ---------------- CPU baseline (oracle port) on this box's host cores ----------------
+        if not args.no_cpu_baseline and world == 1:
+            times, cores = cpu_reference_arm(10, B_PER_GPU)
+            cv = B_PER_GPU / (sum(times) / len(times))
+            line["cpu_baseline"] = {"value": cv, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                                    "sample": f"{len(times)} full passes of the c2 batch ({B_PER_GPU} pairs), torch CPU fp32"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

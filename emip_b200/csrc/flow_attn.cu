@@ -20,6 +20,7 @@ extern "C" size_t emip_flow_attn_workspace(int B, int N, int C) {
 
 extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse,
                                   void* workspace, size_t ws_bytes, int B, int N, int C, int flags, void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(q && k && v && out, "flow_attn_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && N > 0, "flow_attn_fwd: bad shape B=%d N=%d", B, N);
   if (C != 128) {
@@ -58,6 +59,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
 extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
                                   const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes,
                                   int B, int N, int C, void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(q && k && v && out && lse && dout && dq && dk, "flow_attn_bwd: null pointer");
   if (C != 128) {
     emip_set_error("flow_attn_bwd: C=%d unsupported (kernels are built for the model's C=128)", C);

@@ -231,6 +231,7 @@ int grid_for(long long total_threads) {
 
 extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                                   long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && flow && out, "flow_warp_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_fwd: bad pad_mode %d", pad_mode);
@@ -252,6 +253,7 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
 extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float* dout, float* dflow, float* dx,
                                   int B, int C, int H, int W, long long flow_stride_b, long long flow_stride_c,
                                   int pad_mode, void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && flow && dout && dflow, "flow_warp_bwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_bwd: bad pad_mode %d", pad_mode);

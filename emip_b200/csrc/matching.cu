@@ -44,6 +44,7 @@ extern "C" size_t emip_global_matching_workspace(int B, int C, int H, int W) {
 extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float* flow, float* corr, float* lse,
                                         void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir,
                                         int flags, void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(f0 && f1 && flow, "global_matching_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "global_matching_fwd: bad shape B=%d H=%d W=%d", B, H, W);
   if (C != 128) {
@@ -56,12 +57,15 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
   MatchWs ws;
   int rc = carve(workspace, ws_bytes, B, C, N, nd, &ws);
   if (rc) return rc;
-  if ((rc = launch_coords_grid(ws.grid, H, W, st))) return rc;
+  const bool reuse = (flags & EMIP_FLAG_REUSE_WORKSPACE) != 0;
+  if (!reuse && (rc = launch_coords_grid(ws.grid, H, W, st))) return rc;
 
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
     // tensor-core path: one launch covers both directions
-    if ((rc = match_tc_split(f0, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
-    if ((rc = match_tc_split(f1, ws.split, B, N, C, EMIP_LAYOUT_CN, B, st))) return rc;
+    if (!reuse) {
+      if ((rc = match_tc_split(f0, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
+      if ((rc = match_tc_split(f1, ws.split, B, N, C, EMIP_LAYOUT_CN, B, st))) return rc;
+    }
     MatchTcArgs a = {};
     a.x_split = ws.split; a.y_split = ws.split; a.nbx = 2 * B; a.nby = 2 * B;
     a.v = ws.grid; a.v_stride_b = 0; a.sub = ws.grid;
@@ -94,6 +98,7 @@ extern "C" int emip_global_matching_bwd(const float* f0, const float* f1, const 
                                         const float* dflow, const float* dcorr, float* df0, float* df1,
                                         void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir,
                                         void* stream) {
+  if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(f0 && f1 && flow && lse && df0 && df1, "global_matching_bwd: null pointer");
   EMIP_CHECK_ARG(dflow || dcorr, "global_matching_bwd: both dflow and dcorr are NULL");
   if (C != 128) {

@@ -38,6 +38,9 @@ extern "C" {
 
 /* flags */
 #define EMIP_FLAG_EXACT_FP32 1 /* force the exact-fp32 CUDA-core path (no bf16 hi/lo tensor-core split) */
+#define EMIP_FLAG_REUSE_WORKSPACE 2 /* global_matching_fwd: the workspace still holds the operand split and pixel
+                                       grid of the previous call on the SAME f0/f1; skip those pre-passes (used to
+                                       time / profile the fused kernel alone) */
 
 /* ---- plumbing ------------------------------------------------------------ */
 const char* emip_last_error(void);
