@@ -74,157 +74,105 @@ __device__ __forceinline__ Tap make_tap(const Coord& c, int H, int W, float& wx,
   return t;
 }
 
-template <int VEC>
-struct VecT;
-template <>
-struct VecT<1> { using type = float; };
-template <>
-struct VecT<2> { using type = float2; };
-template <>
-struct VecT<4> { using type = float4; };
-
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
-  using T = typename VecT<VEC>::type;
-  T t = __ldg(reinterpret_cast<const T*>(p));
-  const float* f = reinterpret_cast<const float*>(&t);
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) v[i] = f[i];
-}
-template <int VEC>
-__device__ __forceinline__ void store_vec_stream(float* p, const float (&v)[VEC]) {
-  using T = typename VecT<VEC>::type;
-  T t;
-  float* f = reinterpret_cast<float*>(&t);
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) f[i] = v[i];
-  __stcs(reinterpret_cast<T*>(p), t);   // streaming store: output is not re-read by this kernel
-}
-
-// One thread = VEC horizontally adjacent output pixels, all C channels.
-template <int VEC, bool BORDER>
+// Forward.  CTA = 32 x 8 output pixels of one sample; one thread per pixel, all C channels.
+// Consecutive lanes = consecutive pixels, so for the piecewise-smooth flows the model produces the four
+// tap requests of a warp touch 1-2 cache lines each (ncu r1a: the earlier 4-pixels-per-thread mapping made
+// every tap request span ~30 sectors and held the kernel to 19 % of HBM peak).  The 8-row tile lets the
+// bottom taps of row y and the top taps of row y+1 hit the same L1 lines.
+template <bool BORDER, int CT>
 __global__ void __launch_bounds__(256)
 flow_warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                     int B, int C, int H, int W, long long fsb, long long fsc) {
-  const int wv = W / VEC;
-  const long long total = (long long)B * H * wv;
+                     int C, int H, int W, long long fsb, long long fsc, int tiles_x, int tiles_y) {
   const long long plane = (long long)H * W;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int xv = (int)(idx % wv);
-    long long r = idx / wv;
-    int y = (int)(r % H);
-    int b = (int)(r / H);
-    int x0 = xv * VEC;
-    const float* fp = flow + (long long)b * fsb + (long long)y * W + x0;
-    float fx[VEC], fy[VEC];
-    load_vec<VEC>(fp, fx);
-    load_vec<VEC>(fp + fsc, fy);
-    Tap tap[VEC];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int px = tx * 32 + (threadIdx.x & 31);
+  const int py = ty * 8 + (threadIdx.x >> 5);
+  if (px >= W || py >= H) return;
+  const long long pix = (long long)py * W + px;
+  const float* fp = flow + (long long)b * fsb + pix;
+  const float fx = __ldcs(fp), fy = __ldcs(fp + fsc);          // streamed: read exactly once
+  Coord c = sample_point<BORDER>((float)px + fx, (float)py + fy, H, W);
+  float wx, wy;
+  const Tap tap = make_tap(c, H, W, wx, wy);
+  const float* xb = x + (long long)b * C * plane;
+  float* ob = out + (long long)b * C * plane + pix;
+  if constexpr (CT > 0) {
+    float v[CT > 0 ? CT : 1][4];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      Coord c = sample_point<BORDER>((float)(x0 + i) + fx[i], (float)y + fy[i], H, W);
-      float wx, wy;
-      tap[i] = make_tap(c, H, W, wx, wy);
+    for (int ch = 0; ch < CT; ++ch) {                           // all 4*C gathers in flight before any use
+      const float* xp = xb + ch * plane;
+      v[ch][0] = __ldg(xp + tap.o00); v[ch][1] = __ldg(xp + tap.o01);
+      v[ch][2] = __ldg(xp + tap.o10); v[ch][3] = __ldg(xp + tap.o11);
     }
-    const float* xb = x + (long long)b * C * plane;
-    float* ob = out + (long long)b * C * plane + (long long)y * W + x0;
+#pragma unroll
+    for (int ch = 0; ch < CT; ++ch)
+      __stcs(ob + ch * plane, v[ch][0] * tap.w00 + v[ch][1] * tap.w01 + v[ch][2] * tap.w10 + v[ch][3] * tap.w11);
+  } else {
     for (int ch = 0; ch < C; ++ch) {
       const float* xp = xb + ch * plane;
-      float o[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float v00 = __ldg(xp + tap[i].o00), v01 = __ldg(xp + tap[i].o01);
-        float v10 = __ldg(xp + tap[i].o10), v11 = __ldg(xp + tap[i].o11);
-        o[i] = v00 * tap[i].w00 + v01 * tap[i].w01 + v10 * tap[i].w10 + v11 * tap[i].w11;
-      }
-      store_vec_stream<VEC>(ob + ch * plane, o);
+      float v00 = __ldg(xp + tap.o00), v01 = __ldg(xp + tap.o01), v10 = __ldg(xp + tap.o10), v11 = __ldg(xp + tap.o11);
+      __stcs(ob + ch * plane, v00 * tap.w00 + v01 * tap.w01 + v10 * tap.w10 + v11 * tap.w11);
     }
   }
 }
 
-// Backward: dflow per pixel (no atomics); optional dx by atomic scatter.
-template <int VEC, bool BORDER, bool WITH_DX>
+// Backward: dflow per pixel (no atomics); optional dx by atomic scatter.  Same tiling as the forward.
+template <bool BORDER, bool WITH_DX, int CT>
 __global__ void __launch_bounds__(256)
 flow_warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ dout,
                      float* __restrict__ dflow, float* __restrict__ dx,
-                     int B, int C, int H, int W, long long fsb, long long fsc) {
-  const int wv = W / VEC;
-  const long long total = (long long)B * H * wv;
+                     int C, int H, int W, long long fsb, long long fsc, int tiles_x, int tiles_y) {
   const long long plane = (long long)H * W;
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int xv = (int)(idx % wv);
-    long long r = idx / wv;
-    int y = (int)(r % H);
-    int b = (int)(r / H);
-    int x0 = xv * VEC;
-    const float* fp = flow + (long long)b * fsb + (long long)y * W + x0;
-    float fx[VEC], fy[VEC];
-    load_vec<VEC>(fp, fx);
-    load_vec<VEC>(fp + fsc, fy);
-    Tap tap[VEC];
-    Coord co[VEC];
-    float wx[VEC], wy[VEC], gx[VEC], gy[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      co[i] = sample_point<BORDER>((float)(x0 + i) + fx[i], (float)y + fy[i], H, W);
-      tap[i] = make_tap(co[i], H, W, wx[i], wy[i]);
-      gx[i] = 0.0f;
-      gy[i] = 0.0f;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int px = tx * 32 + (threadIdx.x & 31);
+  const int py = ty * 8 + (threadIdx.x >> 5);
+  if (px >= W || py >= H) return;
+  const long long pix = (long long)py * W + px;
+  const float* fp = flow + (long long)b * fsb + pix;
+  const float fx = __ldcs(fp), fy = __ldcs(fp + fsc);
+  const Coord co = sample_point<BORDER>((float)px + fx, (float)py + fy, H, W);
+  float wx, wy;
+  const Tap tap = make_tap(co, H, W, wx, wy);
+  const float ex = 1.0f - wx, ey = 1.0f - wy;
+  const float* xb = x + (long long)b * C * plane;
+  const float* gb = dout + (long long)b * C * plane + pix;
+  float gx = 0.f, gy = 0.f;
+  auto one = [&](int ch) {
+    const float* xp = xb + ch * plane;
+    const float g = __ldcs(gb + ch * plane);
+    // a tap outside the image counts as value 0 (ATen within_bounds); offsets are always safe
+    float v00 = __ldg(xp + tap.o00), v01 = __ldg(xp + tap.o01), v10 = __ldg(xp + tap.o10), v11 = __ldg(xp + tap.o11);
+    v00 = (tap.valid & 1) ? v00 : 0.f;
+    v01 = (tap.valid & 2) ? v01 : 0.f;
+    v10 = (tap.valid & 4) ? v10 : 0.f;
+    v11 = (tap.valid & 8) ? v11 : 0.f;
+    gx += g * ((v01 - v00) * ey + (v11 - v10) * wy);
+    gy += g * ((v10 - v00) * ex + (v11 - v01) * wx);
+    if (WITH_DX) {
+      float* dp = dx + ((long long)b * C + ch) * plane;
+      if (tap.w00 != 0.0f) atomicAdd(dp + tap.o00, g * tap.w00);
+      if (tap.w01 != 0.0f) atomicAdd(dp + tap.o01, g * tap.w01);
+      if (tap.w10 != 0.0f) atomicAdd(dp + tap.o10, g * tap.w10);
+      if (tap.w11 != 0.0f) atomicAdd(dp + tap.o11, g * tap.w11);
     }
-    const float* xb = x + (long long)b * C * plane;
-    const float* gb = dout + (long long)b * C * plane + (long long)y * W + x0;
-    for (int ch = 0; ch < C; ++ch) {
-      const float* xp = xb + ch * plane;
-      float g[VEC];
-      load_vec<VEC>(gb + ch * plane, g);
+  };
+  if constexpr (CT > 0) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        // a tap outside the image counts as value 0 (ATen within_bounds); offsets are always safe
-        float v00 = (tap[i].valid & 1) ? __ldg(xp + tap[i].o00) : 0.0f;
-        float v01 = (tap[i].valid & 2) ? __ldg(xp + tap[i].o01) : 0.0f;
-        float v10 = (tap[i].valid & 4) ? __ldg(xp + tap[i].o10) : 0.0f;
-        float v11 = (tap[i].valid & 8) ? __ldg(xp + tap[i].o11) : 0.0f;
-        float ex = 1.0f - wx[i], ey = 1.0f - wy[i];
-        gx[i] += g[i] * ((v01 - v00) * ey + (v11 - v10) * wy[i]);
-        gy[i] += g[i] * ((v10 - v00) * ex + (v11 - v01) * wx[i]);
-        if (WITH_DX) {
-          float* dp = dx + ((long long)b * C + ch) * plane;
-          if (tap[i].w00 != 0.0f) atomicAdd(dp + tap[i].o00, g[i] * tap[i].w00);
-          if (tap[i].w01 != 0.0f) atomicAdd(dp + tap[i].o01, g[i] * tap[i].w01);
-          if (tap[i].w10 != 0.0f) atomicAdd(dp + tap[i].o10, g[i] * tap[i].w10);
-          if (tap[i].w11 != 0.0f) atomicAdd(dp + tap[i].o11, g[i] * tap[i].w11);
-        }
-      }
-    }
-    float ox[VEC], oy[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
-      ox[i] = __fdiv_rn(gx[i] * (wm1 * 0.5f) * co[i].gmx, wm1) * 2.0f;
-      oy[i] = __fdiv_rn(gy[i] * (hm1 * 0.5f) * co[i].gmy, hm1) * 2.0f;
-    }
-    float* dp = dflow + (long long)b * 2 * plane + (long long)y * W + x0;
-    store_vec_stream<VEC>(dp, ox);
-    store_vec_stream<VEC>(dp + plane, oy);
+    for (int ch = 0; ch < CT; ++ch) one(ch);
+  } else {
+    for (int ch = 0; ch < C; ++ch) one(ch);
   }
-}
-
-int pick_vec(const void* a, const void* b, const void* c, int W, long long fsb, long long fsc) {
-  auto al = [](const void* p, int bytes) { return (reinterpret_cast<uintptr_t>(p) % bytes) == 0; };
-  if (W % 4 == 0 && fsb % 4 == 0 && fsc % 4 == 0 && al(a, 16) && al(b, 16) && al(c, 16)) return 4;
-  if (W % 2 == 0 && fsb % 2 == 0 && fsc % 2 == 0 && al(a, 8) && al(b, 8) && al(c, 8)) return 2;
-  return 1;
-}
-
-int grid_for(long long total_threads) {
-  long long blocks = (total_threads + 255) / 256;
-  long long cap = (long long)emip_num_sms() * 32;   // grid-stride above 32 CTAs/SM
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+  // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
+  float* dp = dflow + (long long)b * 2 * plane + pix;
+  __stcs(dp, __fdiv_rn(gx * (wm1 * 0.5f) * co.gmx, wm1) * 2.0f);
+  __stcs(dp + plane, __fdiv_rn(gy * (hm1 * 0.5f) * co.gmy, hm1) * 2.0f);
 }
 
 }  // namespace
@@ -235,16 +183,16 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
   EMIP_CHECK_ARG(x && flow && out, "flow_warp_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_fwd: bad pad_mode %d", pad_mode);
-  if (B == 0) return EMIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int vec = pick_vec(flow, out, flow + flow_stride_c, W, flow_stride_b, flow_stride_c);
-  long long total = (long long)B * H * (W / vec);
-  int grid = grid_for(total);
-#define LAUNCH(V, BD) flow_warp_fwd_kernel<V, BD><<<grid, 256, 0, st>>>(x, flow, out, B, C, H, W, flow_stride_b, flow_stride_c)
-  bool border = pad_mode == EMIP_PAD_BORDER;
-  if (vec == 4) { if (border) LAUNCH(4, true); else LAUNCH(4, false); }
-  else if (vec == 2) { if (border) LAUNCH(2, true); else LAUNCH(2, false); }
-  else { if (border) LAUNCH(1, true); else LAUNCH(1, false); }
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const long long nblk = (long long)B * tiles_x * tiles_y;
+  EMIP_CHECK_ARG(nblk < 0x7fffffffLL, "flow_warp_fwd: problem too large");
+#define LAUNCH(BD, CT) \
+  flow_warp_fwd_kernel<BD, CT><<<(unsigned)nblk, 256, 0, st>>>(x, flow, out, C, H, W, flow_stride_b, flow_stride_c, tiles_x, tiles_y)
+  const bool border = pad_mode == EMIP_PAD_BORDER;
+  if (C == 3) { if (border) LAUNCH(true, 3); else LAUNCH(false, 3); }
+  else if (C == 2) { if (border) LAUNCH(true, 2); else LAUNCH(false, 2); }
+  else { if (border) LAUNCH(true, 0); else LAUNCH(false, 0); }
 #undef LAUNCH
   EMIP_CHECK_LAUNCH("flow_warp_fwd");
   return EMIP_OK;
@@ -257,22 +205,21 @@ extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float
   EMIP_CHECK_ARG(x && flow && dout && dflow, "flow_warp_bwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_bwd: bad pad_mode %d", pad_mode);
-  if (B == 0) return EMIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int vec = pick_vec(flow, dout, flow + flow_stride_c, W, flow_stride_b, flow_stride_c);
-  if (vec > 1 && (reinterpret_cast<uintptr_t>(dflow) % (4 * vec)) != 0) vec = 1;
-  long long total = (long long)B * H * (W / vec);
-  int grid = grid_for(total);
-#define LAUNCH(V, BD, DX) \
-  flow_warp_bwd_kernel<V, BD, DX><<<grid, 256, 0, st>>>(x, flow, dout, dflow, dx, B, C, H, W, flow_stride_b, flow_stride_c)
-#define LAUNCH_V(V)                                                  \
-  do {                                                               \
-    if (border) { if (dx) LAUNCH(V, true, true); else LAUNCH(V, true, false); }   \
-    else { if (dx) LAUNCH(V, false, true); else LAUNCH(V, false, false); }        \
-  } while (0)
-  bool border = pad_mode == EMIP_PAD_BORDER;
-  if (vec == 4) LAUNCH_V(4); else if (vec == 2) LAUNCH_V(2); else LAUNCH_V(1);
-#undef LAUNCH_V
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const long long nblk = (long long)B * tiles_x * tiles_y;
+  EMIP_CHECK_ARG(nblk < 0x7fffffffLL, "flow_warp_bwd: problem too large");
+#define LAUNCH(BD, DX, CT)                                                                                      \
+  flow_warp_bwd_kernel<BD, DX, CT><<<(unsigned)nblk, 256, 0, st>>>(x, flow, dout, dflow, dx, C, H, W, flow_stride_b, \
+                                                                   flow_stride_c, tiles_x, tiles_y)
+  const bool border = pad_mode == EMIP_PAD_BORDER;
+  if (C == 3) {
+    if (border) { if (dx) LAUNCH(true, true, 3); else LAUNCH(true, false, 3); }
+    else { if (dx) LAUNCH(false, true, 3); else LAUNCH(false, false, 3); }
+  } else {
+    if (border) { if (dx) LAUNCH(true, true, 0); else LAUNCH(true, false, 0); }
+    else { if (dx) LAUNCH(false, true, 0); else LAUNCH(false, false, 0); }
+  }
 #undef LAUNCH
   EMIP_CHECK_LAUNCH("flow_warp_bwd");
   return EMIP_OK;

@@ -1,0 +1,35 @@
+// Small exact-fp32 batched GEMM building blocks used by the prompt-fusion (Injector) kernels.
+// The injector's inputs/outputs must stay fp32-accurate, its GEMMs are
+// 128..680-wide per-sample 1x1 convolutions on 1936 pixels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+// Y[b][m][n] = sum_k W(b)[m][k] * X'(b)[k][n]  (+ R[b][m][n])
+//   W(b)[m][k] = w[b*w_stride_b + (w_trans ? k*ldw + m : m*ldw + k)]
+//   X'(b)[k][n] = x[b*x_stride_b + k*ldx + n], optionally layer-normalised on load:
+//                 (x - mean[b][n]) * rstd[b][n] * gamma[k] + beta[k]
+struct GemmNN {
+  const float* w; long long w_stride_b; int ldw; int w_trans;
+  const float* x; long long x_stride_b; int ldx;
+  const float* mean; const float* rstd; const float* gamma; const float* beta;   // all NULL = no LN; stats are [B][N]
+  const float* res; long long res_stride_b; int ldr;                              // NULL = no residual
+  float* y; long long y_stride_b; int ldy;
+  int B, M, K, N;
+  int accumulate;                                                                  // y += instead of y =
+};
+int gemm_nn(const GemmNN& a, cudaStream_t st);
+
+// C[b][m][k] = sum_n A(b)[m][n] * B'(b)[k][n]     (contraction over the contiguous pixel axis)
+//   A(b)[m][n] = a[b*a_stride_b + m*lda + n];  B'(b)[k][n] = bm[b*b_stride_b + k*ldb + n] with optional LN as above
+struct GemmNT {
+  const float* a; long long a_stride_b; int lda;
+  const float* bm; long long b_stride_b; int ldb;
+  const float* mean; const float* rstd; const float* gamma; const float* beta;
+  float* c; long long c_stride_b; int ldc;
+  int B, M, K, N;
+};
+int gemm_nt(const GemmNT& a, cudaStream_t st);
+
+// out[i] = sum_b in[b*stride + i], i < n
+int reduce_batch(const float* in, long long stride, float* out, int B, long long n, int accumulate, cudaStream_t st);
