@@ -235,7 +235,7 @@ def main():
         "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke},
-        "gpu_launches": 4 * K,     # per step: pixel grid + 2 operand splits + fused matching kernel
+        "gpu_launches": 2 * K,     # per step: operand split pre-pass + fused tcgen05 matching kernel
     }
 
     if rank == 0:
@@ -256,14 +256,15 @@ def main():
         for i in range(N_INPUT_SETS):
             kernel_only(i, 0, corr)            # fills every workspace with its operand split
         res = {}
-        for name, corr_t in (("with_corr", corr), ("flow_only", None)):
+        for name, corr_t, fl in (("with_corr", corr, 2), ("flow_only", None, 2), ("bf16_with_corr", corr, 6),
+                                 ("bf16_flow_only", None, 6)):
             for i in range(5):
-                kernel_only(i, 2, corr_t)
+                kernel_only(i, fl, corr_t)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for i in range(K):
-                kernel_only(i, 2, corr_t)
+                kernel_only(i, fl, corr_t)
             e1.record(stream)
             torch.cuda.synchronize()
             res[name] = e0.elapsed_time(e1) / K
@@ -274,6 +275,7 @@ def main():
             "kernel": "match_tc_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": ach / pk["tf"], "traffic": None, "peak_source": pk["src"] + " burst bf16 (cuBLAS)",
             "launch_ms": k_ms, "launch_ms_flow_only": res["flow_only"],
+            "launch_ms_bf16_mode": res["bf16_with_corr"], "launch_ms_bf16_mode_flow_only": res["bf16_flow_only"],
             "executed_mma_tflops": EXEC_MMA_FLOP_PER_PAIR * B_PER_GPU / (k_ms * 1e-3) / 1e12,
             "executed_mma_frac": EXEC_MMA_FLOP_PER_PAIR * B_PER_GPU / (k_ms * 1e-3) / 1e12 / pk["tf"],
             "corr_write_gbs": B_PER_GPU * N * N * 4 / (k_ms * 1e-3) / 1e9,

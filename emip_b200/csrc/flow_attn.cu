@@ -37,11 +37,12 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
     }
     char* p = static_cast<char*>(workspace) + d_bytes(B, N);
     int rc;
-    if ((rc = match_tc_split(q, p, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
-    if ((rc = match_tc_split(k, p + sb, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    if ((rc = match_tc_split(q, nullptr, p, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    if ((rc = match_tc_split(k, nullptr, p + sb, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
     MatchTcArgs a = {};
     a.x_split = p; a.y_split = p + sb; a.nbx = B; a.nby = B;
-    a.v = v; a.v_stride_b = 2LL * N; a.sub = nullptr;
+    a.v = v; a.v_stride_b = 2LL * N; a.grid_w = 0; a.sub_grid = 0;
+    a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
     a.out = out; a.lse = lse; a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0; a.y_mod = B;
     a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
     a.sqrt_c = sqrtf((float)C);

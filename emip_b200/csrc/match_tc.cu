@@ -6,16 +6,23 @@
 // lives only in TMEM; it reaches HBM only when the caller asks for `corr`.
 //
 // Numerics: fp32 features are split once into bf16 hi + bf16 lo
-// (match_tc_split) and S is accumulated in fp32 as  hi.hi + hi.lo + lo.hi
+// (match_tc_split) and S is accumulated in fp32 as  hi.hi + lo.hi + hi.lo
 // (24 UMMA K16-steps per 128x128 tile, one TMEM accumulator): S rel. error ~4e-6,
-// flow rel-L2 ~1e-5 versus fp32 SGEMM.  Softmax statistics are fp32.
+// flow rel-L2 ~1e-5 versus fp32 SGEMM.  terms=1 keeps only hi.hi (bf16 inference
+// mode, 2e-2 tolerance).  Softmax statistics are always fp32.
 //
-// CTA = 192 threads, persistent, one CTA per SM (193 KB smem, 256 TMEM columns):
-//   warp 0      TMA producer   (Q tile once per work item; K chunks through a 6-stage ring)
-//   warp 1      UMMA issuer    (one elected lane; also owns the TMEM allocation)
-//   warps 2..5  softmax        (thread <-> TMEM lane <-> one query row; no shuffles)
-// Two S buffers in TMEM let the MMAs of key tile t+1 overlap the softmax of tile t.
-// Work item = (problem p, 128-row query tile); problems enumerate (sample, direction).
+// CTA = 320 threads, persistent, one CTA per SM (225 KB smem, all 512 TMEM columns).
+// A work item is (problem, PAIR of 128-row query tiles): every key chunk that TMA
+// brings in is used by both query tiles, which halves the L2->SM operand traffic
+// per MMA (1 MB per 256 rows; the first version of this kernel, one tile per CTA, asked
+// L2 for 11 TB/s at the MMA-bound rate).
+//   warp 0      TMA producer   (2 x 64 KB query tiles per item; key chunks through a 4-stage ring)
+//   warp 1      UMMA issuer    (one elected lane; owns the TMEM allocation)
+//   warps 2..5  softmax group 0  (query tile 0: thread <-> TMEM lane <-> one row; no shuffles)
+//   warps 6..9  softmax group 1  (query tile 1)
+// Each group has two 128-column accumulators in TMEM, so the MMAs of key tile t+1
+// overlap the softmax of tile t.  `corr` is emitted by the softmax warps through
+// a swizzled smem stage and TMA bulk stores (no strided st.global).
 #include "common.cuh"
 #include "match_tc.cuh"
 #include "pair_common.cuh"
@@ -23,24 +30,26 @@
 
 namespace {
 
-constexpr int TM = 128;                 // query rows per work item (UMMA M)
+constexpr int TM = 128;                 // query rows per tile (UMMA M)
 constexpr int TN = 128;                 // key columns per tile (UMMA N)
 constexpr int CH_ELEMS = 64;            // bf16 per 128-byte swizzle row
 constexpr int CHUNK_BYTES = TM * 128;   // one [128 rows x 128 B] SW128 box = 16 KB
 constexpr int NCHUNK = 4;               // hi[0:64] hi[64:128] lo[0:64] lo[64:128]
-constexpr int STAGES = 6;
+constexpr int STAGES = 4;
 constexpr int MAXK = 2048;              // value table capacity (columns)
-constexpr int NTHREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int NTHREADS = 320;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int STG_BYTES = 2048;         // per softmax warp: [32 rows][16 fp32], 64-byte swizzle
 
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + NCHUNK * CHUNK_BYTES;
-constexpr int OFF_V = OFF_K + STAGES * CHUNK_BYTES;
-constexpr int OFF_STAGE = OFF_V + 2 * MAXK * 4;
-constexpr int OFF_BAR = OFF_STAGE + 4 * 32 * 33 * 4;
-constexpr int NBAR = 2 + 2 * STAGES + 4;
+constexpr int OFF_Q = 0;                                        // [2 tiles][4 chunks][16 KB]
+constexpr int OFF_K = OFF_Q + 2 * NCHUNK * CHUNK_BYTES;         // ring
+constexpr int OFF_STG = OFF_K + STAGES * CHUNK_BYTES;
+constexpr int OFF_V = OFF_STG + 8 * STG_BYTES;
+constexpr int OFF_BAR = OFF_V + 2 * MAXK * 4;
+constexpr int NBAR = 3 + 2 * STAGES + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;   // + slack to align the base to 1024 B
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;                // + slack to align the base to 1024 B
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 // ---- PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,6 +94,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -114,55 +132,145 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+
+#define R32_OUT(r)                                                                                                     \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),          \
+      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define R32_INOUT(r)                                                                                                   \
+  "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),          \
+      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),           \
+      "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),          \
+      "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+
+// Asynchronous TMEM load of 32 consecutive fp32 columns of this thread's lane; pair with tmem_wait().
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : R32_OUT(r)
       : "r"(taddr)
       : "memory");
+}
+// The registers are in/out operands so that no use of r[] can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : R32_INOUT(r)::"memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 struct KParams {
   const float* v;
   long long v_stride_b;
-  const float* sub;
   float* out;
   float* lse;
-  float* s_out;
+  float* s_out;          // direct-store fallback for the scores (used when the TMA store map cannot be built)
   int nb, nq, nk, y_shift, y_mod, s_first, s_count;
-  float inv_sqrt_c;      // 1/sqrt(C)
-  float sqrt_c;
+  int grid_w, sub_grid, terms, s_mode;   // s_mode: 0 none, 1 TMA bulk store, 2 direct st.global
+  float inv_sqrt_c;
 };
 
+// Online-softmax update of one row with 32 score columns (raw accumulator values, scale folded into c2).
+template <bool FULL>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], int nv, uint32_t vx, uint32_t vy, float c2,
+                                              float& m, float& l, float& sx, float& sy) {
+  float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float s = __uint_as_float(r[i]);
+    cm[i & 3] = (FULL || i < nv) ? fmaxf(cm[i & 3], s) : cm[i & 3];
+  }
+  const float m_new = fmaxf(fmaxf(m, fmaxf(cm[0], cm[1])), fmaxf(cm[2], cm[3]));
+  const float corr = ex2f((m - m_new) * c2);         // first chunk: ex2(-inf) = 0
+  const float mb = m_new * c2;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f}, lx[4] = {0.f, 0.f, 0.f, 0.f}, ly[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i4 = 0; i4 < 8; ++i4) {
+    const float4 ax = lds128(vx + 16 * i4), ay = lds128(vy + 16 * i4);   // value table in smem (warp-wide broadcast)
+    const float xs[4] = {ax.x, ax.y, ax.z, ax.w}, ys[4] = {ay.x, ay.y, ay.z, ay.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float e = ex2f(fmaf(__uint_as_float(r[i4 * 4 + k]), c2, -mb));
+      if (!FULL) e = (i4 * 4 + k < nv) ? e : 0.f;
+      ls[k] += e;
+      lx[k] = fmaf(e, xs[k], lx[k]);
+      ly[k] = fmaf(e, ys[k], ly[k]);
+    }
+  }
+  l = fmaf(l, corr, (ls[0] + ls[1]) + (ls[2] + ls[3]));
+  sx = fmaf(sx, corr, (lx[0] + lx[1]) + (lx[2] + lx[3]));
+  sy = fmaf(sy, corr, (ly[0] + ly[1]) + (ly[2] + ly[3]));
+  m = m_new;
+}
+
+// Emit 32 score columns of 32 rows (one warp) as two [32 rows x 16 cols] TMA bulk stores.
+__device__ __forceinline__ void emit_chunk_tma(const uint32_t (&r)[32], float scale, uint32_t stg_u32,
+                                               const CUtensorMap* map, int col, int row0, int slab, int lane, int nk) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (lane == 0) bulk_wait_read0();                 // the previous store has finished reading the stage
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v;
+      v.x = __uint_as_float(r[h * 16 + q * 4 + 0]) * scale;
+      v.y = __uint_as_float(r[h * 16 + q * 4 + 1]) * scale;
+      v.z = __uint_as_float(r[h * 16 + q * 4 + 2]) * scale;
+      v.w = __uint_as_float(r[h * 16 + q * 4 + 3]) * scale;
+      // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8] = (row >> 1) & 3
+      sts128(stg_u32 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), v);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0 && col + h * 16 < nk) {             // columns past nk inside the box are clipped by TMA
+      tma_store_3d(map, stg_u32, col + h * 16, row0, slab);
+      bulk_commit();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, KParams p) {
+match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                    const __grid_constant__ CUtensorMap map_s, KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
-  const uint32_t q_full = bar0, q_empty = bar0 + 8;
-  auto k_full = [&](int s) { return bar0 + 16 + 8 * s; };
-  auto k_empty = [&](int s) { return bar0 + 16 + 8 * (STAGES + s); };
-  auto s_full = [&](int b) { return bar0 + 16 + 8 * (2 * STAGES + b); };
-  auto s_empty = [&](int b) { return bar0 + 16 + 8 * (2 * STAGES + 2 + b); };
+  auto q_full = [&](int g) { return bar0 + 8 * g; };
+  const uint32_t q_empty = bar0 + 16;
+  auto k_full = [&](int s) { return bar0 + 24 + 8 * s; };
+  auto k_empty = [&](int s) { return bar0 + 24 + 8 * (STAGES + s); };
+  auto s_full = [&](int g, int b) { return bar0 + 24 + 8 * (2 * STAGES + g * 2 + b); };
+  auto s_empty = [&](int g, int b) { return bar0 + 24 + 8 * (2 * STAGES + 4 + g * 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = (p.nq + TM - 1) / TM;
+  const int npair = (nqt + 1) / 2;
   const int nkt = (p.nk + TN - 1) / TN;
-  const int n_items = p.nb * nqt;
+  const int n_items = p.nb * npair;
+  const int nch = (p.terms == 3) ? NCHUNK : 2;        // single-pass mode streams the hi halves only
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(q_full(0), 1);
+    mbar_init(q_full(1), 1);
     mbar_init(q_empty, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 128); }
+    for (int g = 0; g < 2; ++g)
+      for (int b = 0; b < 2; ++b) { mbar_init(s_full(g, b), 1); mbar_init(s_empty(g, b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -183,14 +291,18 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       uint32_t kphase = 0;
       uint32_t it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int prob = item / nqt, qt = item % nqt;
+        const int prob = item / npair, qt0 = 2 * (item % npair);
         const int by = (prob + p.y_shift) % p.y_mod;
         mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, NCHUNK * CHUNK_BYTES);
-        for (int c = 0; c < NCHUNK; ++c)
-          tma_load_3d(sbase + OFF_Q + c * CHUNK_BYTES, &map_x, q_full, c * CH_ELEMS, qt * TM, prob);
+        for (int g = 0; g < 2; ++g) {
+          // a query tile past the end (odd tile count) is fully out of bounds: TMA fills it with zeros
+          mbar_expect_tx(q_full(g), nch * CHUNK_BYTES);
+          for (int c = 0; c < nch; ++c)
+            tma_load_3d(sbase + OFF_Q + (g * NCHUNK + c) * CHUNK_BYTES, &map_x, q_full(g), c * CH_ELEMS, (qt0 + g) * TM,
+                        prob);
+        }
         for (int kt = 0; kt < nkt; ++kt) {
-          for (int c = 0; c < NCHUNK; ++c) {
+          for (int c = 0; c < nch; ++c) {
             mbar_wait(k_empty(stage), kphase ^ 1);
             mbar_expect_tx(k_full(stage), CHUNK_BYTES);
             tma_load_3d(sbase + OFF_K + stage * CHUNK_BYTES, &map_y, k_full(stage), c * CH_ELEMS, kt * TN, by);
@@ -208,142 +320,148 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       uint32_t it = 0, tile = 0;
       const int n_tail = ((p.nk - (nkt - 1) * TN) + 15) & ~15;
       const uint32_t idesc_full = make_idesc(TN), idesc_tail = make_idesc(n_tail);
-      const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
       // descriptor start-address units are 16 B: chunk = 1024 units, K16 step inside a swizzle row = 2 units
-      const uint64_t q_hi0 = qd, q_hi1 = qd + 1024, q_lo0 = qd + 2048, q_lo1 = qd + 3072;
+      const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        mbar_wait(q_full, it & 1);
-        tc_fence_after();
         for (int kt = 0; kt < nkt; ++kt, ++tile) {
           const int buf = tile & 1;
           const uint32_t use = tile >> 1;
-          mbar_wait(s_empty(buf), (use & 1) ^ 1);
+          mbar_wait(s_empty(0, buf), (use & 1) ^ 1);
+          mbar_wait(s_empty(1, buf), (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TN;
           const uint32_t idesc = (kt == nkt - 1) ? idesc_tail : idesc_full;
-          uint32_t acc = 0;
-          for (int c = 0; c < NCHUNK; ++c) {
+          for (int c = 0; c < nch; ++c) {
             mbar_wait(k_full(stage), kphase);
             tc_fence_after();
             const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_K + stage * CHUNK_BYTES);
-            // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
-            const uint64_t a_hi = (c & 1) ? q_hi1 : q_hi0;
-            const uint64_t a_lo = (c & 1) ? q_lo1 : q_lo0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, acc);
-              acc = 1;
-            }
-            if (c < 2) {
+            for (int g = 0; g < 2; ++g) {
+              if (kt == 0 && c == 0) {
+                mbar_wait(q_full(g), it & 1);
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + (uint32_t)((g * 2 + buf) * TN);
+              // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
+              const uint64_t a_hi = qd + (uint64_t)((g * NCHUNK + (c & 1)) * (CHUNK_BYTES >> 4));
+              const uint64_t a_lo = qd + (uint64_t)((g * NCHUNK + 2 + (c & 1)) * (CHUNK_BYTES >> 4));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, (c | k) ? 1u : 0u);
+              if (c < 2 && nch == NCHUNK) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1u);
+              }
             }
             umma_commit(k_empty(stage));       // frees the smem stage when these MMAs retire
             if (++stage == STAGES) { stage = 0; kphase ^= 1; }
           }
-          umma_commit(s_full(buf));            // S tile complete -> softmax warps
+          umma_commit(s_full(0, buf));         // both S tiles complete -> softmax groups
+          umma_commit(s_full(1, buf));
         }
-        umma_commit(q_empty);                  // Q tile no longer read -> producer may overwrite
+        umma_commit(q_empty);                  // query tiles no longer read -> producer may overwrite
       }
     }
     __syncwarp();
   } else {
     // ===================== softmax warps =====================
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;                       // softmax group = query tile of the pair
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int r_in_tile = quarter * 32 + lane;
-    const int st = threadIdx.x - 64;                    // 0..127 within the softmax group
+    const int st = threadIdx.x - 64;                     // 0..255 within the softmax warps
     float* vtab = reinterpret_cast<float*>(smem + OFF_V);
-    float* stage_buf = reinterpret_cast<float*>(smem + OFF_STAGE) + (warp - 2) * 32 * 33;
+    const uint32_t stg = sbase + OFF_STG + (warp - 2) * STG_BYTES;
+    const uint32_t vtab_u32 = sbase + OFF_V;
     const float c2 = 1.4426950408889634f * p.inv_sqrt_c;   // log2(e)/sqrt(C)
+    const int nk_pad = (p.nk + 31) & ~31;
     uint32_t tile = 0;
     int cur_v = -1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int prob = item / nqt, qt = item % nqt;
+      const int prob = item / npair, qt = 2 * (item % npair) + g;
       const int row = qt * TM + r_in_tile;
-      const int v_id = (p.v_stride_b == 0) ? 0 : prob;
+      const int v_id = (p.grid_w > 0 || p.v_stride_b == 0) ? 0 : prob;
       if (v_id != cur_v) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished with the old table
-        const float* vg = p.v + (size_t)prob * p.v_stride_b;
-        for (int i = st; i < 2 * p.nk; i += 128) {
-          int ch = i / p.nk, c = i - ch * p.nk;
-          vtab[ch * MAXK + c] = __ldg(vg + i);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone finished with the old table
+        if (p.grid_w > 0) {
+          for (int c = st; c < nk_pad; c += 256) {        // geometry.py:5-21: channel 0 = x, channel 1 = y
+            vtab[c] = (c < p.nk) ? (float)(c % p.grid_w) : 0.f;
+            vtab[MAXK + c] = (c < p.nk) ? (float)(c / p.grid_w) : 0.f;
+          }
+        } else {
+          const float* vg = p.v + (size_t)prob * p.v_stride_b;
+          // masked tail columns are multiplied by p = 0: keep them finite
+          for (int c = st; c < nk_pad; c += 256) {
+            vtab[c] = (c < p.nk) ? __ldg(vg + c) : 0.f;
+            vtab[MAXK + c] = (c < p.nk) ? __ldg(vg + p.nk + c) : 0.f;
+          }
         }
-        // masked tail columns are multiplied by p = 0: keep them finite
-        for (int c = p.nk + st; c < ((p.nk + 31) & ~31); c += 128) { vtab[c] = 0.f; vtab[MAXK + c] = 0.f; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_v = v_id;
       }
-      const bool emit = p.s_out != nullptr && prob >= p.s_first && prob < p.s_first + p.s_count;
-      float* sg = emit ? p.s_out + ((size_t)(prob - p.s_first) * p.nq) * p.nk : nullptr;
+      const int row0w = qt * TM + quarter * 32;          // first row of this warp's 32-row slab
+      const bool emit = p.s_mode != 0 && prob >= p.s_first && prob < p.s_first + p.s_count && row0w < p.nq;
+      const int slab = prob - p.s_first;
       float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;
       for (int kt = 0; kt < nkt; ++kt, ++tile) {
         const int buf = tile & 1;
         const uint32_t use = tile >> 1;
-        mbar_wait(s_full(buf), use & 1);
+        mbar_wait(s_full(g, buf), use & 1);
         tc_fence_after();
         const int col_base = kt * TN;
         const int n_valid = min(TN, p.nk - col_base);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN;
-        for (int c0 = 0; c0 < n_valid; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          const int nv = min(32, n_valid - c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((g * 2 + buf) * TN);
+        auto work = [&](const uint32_t (&r)[32], int c0, int nv, bool full) {
           if (emit) {
-            // transpose through smem so that each store instruction writes one 128-byte row segment
+            if (p.s_mode == 1) {
+              emit_chunk_tma(r, p.inv_sqrt_c, stg, &map_s, col_base + c0, row0w, slab, lane, p.nk);
+            } else if (row < p.nq) {
+              float* sg = p.s_out + ((size_t)slab * p.nq + row) * p.nk + col_base + c0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stage_buf[lane * 33 + i] = __uint_as_float(r[i]) * p.inv_sqrt_c;
-            __syncwarp();
-            const int grow0 = qt * TM + quarter * 32;
-            if (lane < nv) {
-              for (int rr = 0; rr < 32; ++rr) {
-                if (grow0 + rr < p.nq) sg[(size_t)(grow0 + rr) * p.nk + col_base + c0 + lane] = stage_buf[rr * 33 + lane];
-              }
+              for (int i = 0; i < 32; ++i)
+                if (i < nv) sg[i] = __uint_as_float(r[i]) * p.inv_sqrt_c;
             }
-            __syncwarp();
           }
-          float cmax = -INFINITY;
-          if (nv == 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) cmax = (i < nv) ? fmaxf(cmax, __uint_as_float(r[i])) : cmax;
+          const uint32_t vx = vtab_u32 + 4 * (col_base + c0);
+          if (full) softmax_chunk<true>(r, 32, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
+          else softmax_chunk<false>(r, nv, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
+        };
+        if (n_valid == TN) {
+          // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+          uint32_t ra[32], rb[32];
+          tmem_ld32_async(taddr, ra);
+          tmem_wait(ra);
+          tmem_ld32_async(taddr + 32, rb);
+          work(ra, 0, 32, true);
+          tmem_wait(rb);
+          tmem_ld32_async(taddr + 64, ra);
+          work(rb, 32, 32, true);
+          tmem_wait(ra);
+          tmem_ld32_async(taddr + 96, rb);
+          work(ra, 64, 32, true);
+          tmem_wait(rb);
+          tc_fence_before();
+          mbar_arrive(s_empty(g, buf));                  // accumulator drained: the next MMAs may overwrite it
+          work(rb, 96, 32, true);
+        } else {
+          for (int c0 = 0; c0 < n_valid; c0 += 32) {
+            uint32_t ra[32];
+            tmem_ld32_async(taddr + c0, ra);
+            tmem_wait(ra);
+            const int nv = min(32, n_valid - c0);
+            work(ra, c0, nv, nv == 32);
           }
-          const float m_new = fmaxf(m, cmax);
-          const float corr = exp2f((m - m_new) * c2);      // first chunk: exp2(-inf) = 0
-          const float mb = m_new * c2;
-          float ls = 0.f, lx = 0.f, ly = 0.f;
-          const float4* vx4 = reinterpret_cast<const float4*>(vtab + col_base + c0);
-          const float4* vy4 = reinterpret_cast<const float4*>(vtab + MAXK + col_base + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 vx = vx4[i4], vy = vy4[i4];
-            float pr[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float e = exp2f(fmaf(__uint_as_float(r[i4 * 4 + k]), c2, -mb));
-              pr[k] = (nv == 32 || i4 * 4 + k < nv) ? e : 0.f;
-            }
-            ls += (pr[0] + pr[1]) + (pr[2] + pr[3]);
-            lx = fmaf(pr[0], vx.x, lx); lx = fmaf(pr[1], vx.y, lx); lx = fmaf(pr[2], vx.z, lx); lx = fmaf(pr[3], vx.w, lx);
-            ly = fmaf(pr[0], vy.x, ly); ly = fmaf(pr[1], vy.y, ly); ly = fmaf(pr[2], vy.z, ly); ly = fmaf(pr[3], vy.w, ly);
-          }
-          l = fmaf(l, corr, ls);
-          sx = fmaf(sx, corr, lx);
-          sy = fmaf(sy, corr, ly);
-          m = m_new;
+          tc_fence_before();
+          mbar_arrive(s_empty(g, buf));
         }
-        tc_fence_before();
-        mbar_arrive(s_empty(buf));                         // TMEM buffer drained (128 arrivals)
       }
       if (row < p.nq) {
         float ex = sx / l, ey = sy / l;
-        if (p.sub != nullptr) { ex -= __ldg(p.sub + row); ey -= __ldg(p.sub + p.nq + row); }
+        if (p.sub_grid) { ex -= (float)(row % p.grid_w); ey -= (float)(row / p.grid_w); }
         p.out[((size_t)prob * 2 + 0) * p.nq + row] = ex;
         p.out[((size_t)prob * 2 + 1) * p.nq + row] = ey;
         if (p.lse != nullptr) p.lse[(size_t)prob * p.nq + row] = m * p.inv_sqrt_c + logf(l);
       }
     }
+    if (lane == 0) bulk_wait0();                         // all score stores of this warp have landed
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -360,12 +478,13 @@ __device__ __forceinline__ void split2(float a, float b, __nv_bfloat162& hi, __n
   lo = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
 }
 
-// src [nb][128][n] (channel-major) -> dst [nb][n][256]
+// src [nb][128][n] (channel-major; batches >= nb come from src2) -> dst [..][n][256]
 __global__ void __launch_bounds__(256)
-split_cn_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n) {
+split_cn_kernel(const float* __restrict__ src, const float* __restrict__ src2, __nv_bfloat16* __restrict__ dst, int nb,
+                int n) {
   __shared__ float t[128][65];
   const int b = blockIdx.y, tok0 = blockIdx.x * 64;
-  const float* s = src + (size_t)b * 128 * n;
+  const float* s = (b < nb ? src + (size_t)b * 128 * n : src2 + (size_t)(b - nb) * 128 * n);
   for (int i = threadIdx.x; i < 128 * 64; i += 256) {
     int c = i >> 6, r = i & 63;
     t[c][r] = (tok0 + r < n) ? __ldg(s + (size_t)c * n + tok0 + r) : 0.f;
@@ -436,22 +555,37 @@ int make_map(CUtensorMap* m, const void* base, int nb, int n) {
   return EMIP_OK;
 }
 
+// scores [slabs][nq][nk] fp32, box = 16 columns x 32 rows x 1 slab, 64-byte swizzle (store side: OOB is clipped)
+int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk) {
+  EncodeTiledFn enc = get_encoder();
+  if (enc == nullptr) return EMIP_ENOSYS;
+  cuuint64_t dims[3] = {(cuuint64_t)nk, (cuuint64_t)nq, (cuuint64_t)slabs};
+  cuuint64_t strides[2] = {(cuuint64_t)nk * 4, (cuuint64_t)nq * nk * 4};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EMIP_OK : EMIP_EINVAL;
+}
+
 }  // namespace
 
 bool match_tc_supported(int nq, int nk, int c) { return c == 128 && nk <= MAXK && nk >= 16 && nq >= 1; }
 
 size_t match_tc_split_bytes(int nb, int n, int c) { return emip_align_up((size_t)nb * n * 2 * c * 2, 1024); }
 
-int match_tc_split(const float* src, void* dst, int nb, int n, int c, int layout, int dst_batch0, cudaStream_t st) {
+int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n, int c, int layout, int dst_batch0,
+                   cudaStream_t st) {
   if (c != 128) { emip_set_error("match_tc_split: C=%d unsupported", c); return EMIP_ENOSYS; }
   if (nb == 0 || n == 0) return EMIP_OK;
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)dst_batch0 * n * 256;
   if (layout == EMIP_LAYOUT_CN) {
-    dim3 grid((n + 63) / 64, nb);
-    split_cn_kernel<<<grid, 256, 0, st>>>(src, d, n);
+    dim3 grid((n + 63) / 64, src2 ? 2 * nb : nb);
+    split_cn_kernel<<<grid, 256, 0, st>>>(src, src2, d, nb, n);
   } else {
     long long rows = (long long)nb * n;
     split_nc_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(src, d, rows);
+    if (src2) split_nc_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(src2, d + rows * 256, rows);
   }
   EMIP_CHECK_LAUNCH("match_tc_split");
   return EMIP_OK;
@@ -460,24 +594,36 @@ int match_tc_split(const float* src, void* dst, int nb, int n, int c, int layout
 int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   if (a.nb == 0) return EMIP_OK;
   if (!match_tc_supported(a.nq, a.nk, 128)) { emip_set_error("match_tc_fwd: unsupported shape"); return EMIP_ENOSYS; }
-  CUtensorMap mx, my;
+  if (a.terms != 1 && a.terms != 3) { emip_set_error("match_tc_fwd: terms must be 1 or 3"); return EMIP_EINVAL; }
+  if (a.sub_grid && a.grid_w <= 0) { emip_set_error("match_tc_fwd: sub_grid needs grid_w"); return EMIP_EINVAL; }
+  CUtensorMap mx, my, ms;
   int rc;
   if ((rc = make_map(&mx, a.x_split, a.nbx, a.nq))) return rc;
   if ((rc = make_map(&my, a.y_split, a.nby, a.nk))) return rc;
+  ms = mx;
+  int s_mode = 0;
+  if (a.s_out != nullptr && a.s_count > 0) {
+    // TMA needs 16-byte aligned global rows; odd token counts fall back to plain stores
+    const bool tma_ok = (a.nk % 4 == 0) && (reinterpret_cast<uintptr_t>(a.s_out) % 16 == 0) &&
+                        make_store_map(&ms, a.s_out, a.s_count, a.nq, a.nk) == EMIP_OK;
+    s_mode = tma_ok ? 1 : 2;
+    if (!tma_ok) ms = mx;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   KParams p;
-  p.v = a.v; p.v_stride_b = a.v_stride_b; p.sub = a.sub; p.out = a.out; p.lse = a.lse; p.s_out = a.s_out;
+  p.v = a.v; p.v_stride_b = a.v_stride_b; p.out = a.out; p.lse = a.lse; p.s_out = a.s_out;
   p.nb = a.nb; p.nq = a.nq; p.nk = a.nk; p.y_shift = a.y_shift; p.y_mod = a.y_mod;
   p.s_first = a.s_first; p.s_count = a.s_count;
-  p.sqrt_c = a.sqrt_c; p.inv_sqrt_c = 1.0f / a.sqrt_c;
+  p.grid_w = a.grid_w; p.sub_grid = a.sub_grid; p.terms = a.terms; p.s_mode = s_mode;
+  p.inv_sqrt_c = 1.0f / a.sqrt_c;
   const int nqt = (a.nq + TM - 1) / TM;
-  int grid = a.nb * nqt;
+  int grid = a.nb * ((nqt + 1) / 2);
   if (grid > emip_num_sms()) grid = emip_num_sms();
-  match_tc_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, p);
+  match_tc_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, ms, p);
   EMIP_CHECK_LAUNCH("match_tc_fwd");
   return EMIP_OK;
 }

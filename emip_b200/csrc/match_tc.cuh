@@ -7,9 +7,11 @@ struct MatchTcArgs {
   const void* x_split;     // bf16 [nbx][nq][256]  (hi 128 | lo 128), rows of the score matrix
   const void* y_split;     // bf16 [nby][nk][256], columns of the score matrix
   int nbx, nby;
-  const float* v;          // value 2-vectors per column: v[p*v_stride_b + ch*nk + col]
-  long long v_stride_b;    // 0 = shared by all problems
-  const float* sub;        // optional [2][nq], subtracted from the expectation
+  // value 2-vector per column.  grid_w > 0: analytic pixel grid (x = col % grid_w, y = col / grid_w), `v` unused.
+  const float* v;          // v[p*v_stride_b + ch*nk + col]
+  long long v_stride_b;
+  int grid_w;
+  int sub_grid;            // subtract the row's own grid position from the expectation (matching.py:39)
   float* out;              // [nb][2][nq]
   float* lse;              // optional [nb][nq]
   int nb, nq, nk;
@@ -17,10 +19,13 @@ struct MatchTcArgs {
   float* s_out;            // optional scaled scores for problems [s_first, s_first+s_count): [s_count][nq][nk]
   int s_first, s_count;
   float sqrt_c;
+  int terms;               // 3 = bf16 hi/lo split (hi.hi + lo.hi + hi.lo, fp32-accurate); 1 = single-pass bf16
 };
 
 bool match_tc_supported(int nq, int nk, int c);
 size_t match_tc_split_bytes(int nb, int n, int c);
-// fp32 -> (bf16 hi | bf16 lo) token-major operands; writes batches [dst_batch0, dst_batch0+nb) of dst
-int match_tc_split(const float* src, void* dst, int nb, int n, int c, int layout, int dst_batch0, cudaStream_t st);
+// fp32 -> (bf16 hi | bf16 lo) token-major operands; writes batches [dst_batch0, dst_batch0+nb) of dst.
+// src2 != NULL: a second source of nb batches is written right behind the first (one launch for f0 and f1).
+int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n, int c, int layout, int dst_batch0,
+                   cudaStream_t st);
 int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st);

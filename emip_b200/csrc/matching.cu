@@ -58,24 +58,26 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
   int rc = carve(workspace, ws_bytes, B, C, N, nd, &ws);
   if (rc) return rc;
   const bool reuse = (flags & EMIP_FLAG_REUSE_WORKSPACE) != 0;
-  if (!reuse && (rc = launch_coords_grid(ws.grid, H, W, st))) return rc;
 
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
-    // tensor-core path: one launch covers both directions
-    if (!reuse) {
-      if ((rc = match_tc_split(f0, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
-      if ((rc = match_tc_split(f1, ws.split, B, N, C, EMIP_LAYOUT_CN, B, st))) return rc;
-    }
+    // tensor-core path: one operand-split launch + one fused launch covering both directions
+    if (!reuse && (rc = match_tc_split(f0, f1, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
     MatchTcArgs a = {};
     a.x_split = ws.split; a.y_split = ws.split; a.nbx = 2 * B; a.nby = 2 * B;
-    a.v = ws.grid; a.v_stride_b = 0; a.sub = ws.grid;
+    a.v = nullptr; a.v_stride_b = 0; a.grid_w = W; a.sub_grid = 1;   // analytic pixel grid (geometry.py:5-21)
     a.out = flow; a.lse = lse;
     a.nb = nd * B; a.nq = N; a.nk = N; a.y_shift = B; a.y_mod = 2 * B;
     a.s_out = corr; a.s_first = bidir ? B : 0; a.s_count = corr ? B : 0;
     a.sqrt_c = sqrtf((float)C);
+    a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
     return match_tc_fwd(a, st);
   }
+  if ((rc = launch_coords_grid(ws.grid, H, W, st))) return rc;
 
+  if (flags & EMIP_FLAG_BF16) {
+    emip_set_error("global_matching_fwd: EMIP_FLAG_BF16 needs the tensor-core path (C=128, 16 <= H*W <= 2048)");
+    return EMIP_ENOSYS;
+  }
   PairFwdArgs a = {};
   a.v = ws.grid; a.v_stride_b = 0; a.sub = ws.grid;
   a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0;

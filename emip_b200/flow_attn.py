@@ -47,10 +47,10 @@ class _FlowAttnCore(torch.autograd.Function):
         return dq, dk, None, None
 
 
-def flow_attention_core(q, k, v, exact_fp32=False):
+def flow_attention_core(q, k, v, exact_fp32=False, bf16=False):
     if not q.is_cuda:
         raise _lib.EmipError("emip_b200 flow attention needs CUDA tensors (no CPU fallback)")
-    return _FlowAttnCore.apply(q, k, v, 1 if exact_fp32 else 0)
+    return _FlowAttnCore.apply(q, k, v, 1 if exact_fp32 else (4 if bf16 else 0))
 
 
 class FeatureFlowAttention(nn.Module):
@@ -71,6 +71,7 @@ class FeatureFlowAttention(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
         self.exact_fp32 = False
+        self.bf16 = False        # bf16 inference mode (single-pass bf16 operands, 2e-2 tolerance)
 
     def forward(self, feature0, flow, local_window_attn=False, local_window_radius=1, **kwargs):
         if local_window_attn:
@@ -83,5 +84,5 @@ class FeatureFlowAttention(nn.Module):
         if flow.size(1) != 2:
             raise ValueError("emip_b200 flow attention propagates 2-channel flow")
         out = flow_attention_core(query, key, value.detach() if not value.requires_grad else value,
-                                  exact_fp32=self.exact_fp32)
+                                  exact_fp32=self.exact_fp32, bf16=self.bf16)
         return out.view(b, 2, h, w)

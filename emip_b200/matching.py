@@ -7,7 +7,8 @@ from . import _lib
 from ._lib import I, SZ, ptr, stream_ptr
 from ._ws import workspace
 
-EXACT_FP32 = 1
+EXACT_FP32 = 1   # include/emip_b200.h EMIP_FLAG_EXACT_FP32
+BF16 = 4         # EMIP_FLAG_BF16
 
 
 class _GlobalMatching(torch.autograd.Function):
@@ -57,7 +58,8 @@ class _GlobalMatching(torch.autograd.Function):
         return df0, df1, None, None, None
 
 
-def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return_corr=True, exact_fp32=False):
+def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return_corr=True, exact_fp32=False,
+                               bf16=False):
     """GMFlow global matching: returns ``(flow, prob, corr)`` like the reference.
 
     Same positional signature and results as
@@ -70,7 +72,9 @@ def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return
     only for ``corr`` (``return_corr=False`` skips it).
 
     ``exact_fp32=True`` selects the exact-fp32 CUDA-core kernel instead of the
-    tcgen05 kernel (bf16 hi/lo operand split, fp32 accumulation).
+    tcgen05 kernel (bf16 hi/lo operand split, fp32 accumulation).  ``bf16=True``
+    is the bf16 inference mode: operands rounded once to bf16 (no split), fp32
+    accumulation and softmax; forward only, 2e-2 tolerance.
     """
     if not (feature0.is_cuda and feature1.is_cuda):
         raise _lib.EmipError("emip_b200.global_correlation_softmax needs CUDA tensors (no CPU fallback)")
@@ -79,8 +83,10 @@ def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return
     if feature0.shape != feature1.shape or feature0.dim() != 4:
         raise ValueError(f"feature shapes differ: {tuple(feature0.shape)} vs {tuple(feature1.shape)}")
     B, C, H, W = feature0.shape
+    if bf16 and exact_fp32:
+        raise ValueError("exact_fp32 and bf16 are mutually exclusive")
     flow, smem = _GlobalMatching.apply(feature0, feature1, bool(pred_bidir_flow), bool(return_corr),
-                                       EXACT_FP32 if exact_fp32 else 0)
+                                       EXACT_FP32 if exact_fp32 else (BF16 if bf16 else 0))
     corr = None
     if smem is not None:
         corr = smem if pred_bidir_flow else smem.view(B, H, W, H * W).permute(0, 3, 1, 2)

@@ -42,6 +42,9 @@ extern "C" {
                                        grid of the previous call on the SAME f0/f1; skip those pre-passes (used to
                                        time / profile the fused kernel alone) */
 
+#define EMIP_FLAG_BF16 4            /* bf16 inference mode: single-pass bf16 operands (no hi/lo split), fp32 accumulate and
+                                       fp32 softmax; results within the 2e-2 tolerance instead of 1e-3 */
+
 /* ---- plumbing ------------------------------------------------------------ */
 const char* emip_last_error(void);
 int emip_abi_version(void);

@@ -159,6 +159,41 @@ def test_a1_c2_properties():
     assert rel(corr_sw.view(16, 1936, 1936).transpose(1, 2), corr_tc.view(16, 1936, 1936)) < 1e-6
 
 
+TOL_BF16 = 2e-2        # north_star: bf16 mode tolerance
+
+
+@pytest.mark.parametrize("name", ["a1_full", "a1_lowcontrast", "a1_ragged"])
+def test_a1_bf16_mode(golden, name):
+    """bf16 inference mode (single-pass bf16 operands): within 2e-2 of the fp32 reference."""
+    from emip_b200.matching import global_correlation_softmax
+    g = golden(name)
+    d = cases.a1_inputs(cases.A1_CASES[name])
+    flow, _, corr = global_correlation_softmax(dev(d["f0"]), dev(d["f1"]), True, bf16=True)
+    e_flow = cases.check_packed(flow, g["flow"], TOL_BF16, "flow")
+    e_corr = cases.check_packed(corr, g["corr"], TOL_BF16, "corr")
+    print(f"{name} bf16: flow rel-L2 {e_flow:.2e} corr rel-L2 {e_corr:.2e}")
+
+
+def test_a1_bf16_insitu_c1(golden):
+    from emip_b200.matching import global_correlation_softmax
+    g = golden("c1_insitu")
+    flow, _, corr = global_correlation_softmax(dev(g["f0"]), dev(g["f1"]), True, bf16=True)
+    e = cases.check_packed(flow, g["flow"], TOL_BF16, "flow")
+    print(f"c1 in-situ bf16: flow rel-L2 {e:.2e}")
+
+
+def test_a1_odd_tile_count_and_batches():
+    """Shapes that exercise the pair-of-tiles scheduler: odd tile counts (N=20*16=320 -> 3 tiles), many items."""
+    from emip_b200.matching import global_correlation_softmax
+    for (b, h, w) in ((3, 20, 16), (5, 12, 12), (2, 45, 43)):
+        f0 = cases.randn(70 + b, (b, 128, h, w), 1.5)
+        f1 = cases.randn(80 + b, (b, 128, h, w), 1.5)
+        ref_flow, _, ref_corr = O.global_correlation_softmax(f0, f1, True)
+        flow, _, corr = global_correlation_softmax(dev(f0), dev(f1), True)
+        assert rel(flow, ref_flow) < TOL_OUT, (b, h, w)
+        assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
+
+
 # ----------------------------------------------------------------------------- a2
 @pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
 @pytest.mark.parametrize("name", list(cases.A2_CASES))
