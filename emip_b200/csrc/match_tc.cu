@@ -16,10 +16,14 @@
 // brings in is used by both query tiles, which halves the L2->SM operand traffic
 // per MMA (1 MB per 256 rows; the first version of this kernel, one tile per CTA, asked
 // L2 for 11 TB/s at the MMA-bound rate).
-//   warp 0      TMA producer   (2 x 64 KB query tiles per item; key chunks through a 4-stage ring)
-//   warp 1      UMMA issuer    (one elected lane; owns the TMEM allocation)
-//   warps 2..5  softmax group 0  (query tile 0: thread <-> TMEM lane <-> one row; no shuffles)
-//   warps 6..9  softmax group 1  (query tile 1)
+//   warps 0..3  softmax group 0  (query tile 0: thread <-> TMEM lane <-> one row; no shuffles)
+//   warps 4..7  softmax group 1  (query tile 1)
+//   warp 8      TMA producer   (2 x 64 KB query tiles per item; key chunks through a 4-stage ring)
+//   warp 9      UMMA issuer    (one elected lane; owns the TMEM allocation)
+// The two control warps have the HIGHEST warp ids on purpose: the SM sub-partition arbiter favours
+// high warp ids, and an issuer that shares its sub-partition with two busy softmax warps at low
+// priority could only issue one UMMA per ~128 cycles (ncu r1c: tensor pipe 42 % active, softmax
+// warps stalled on s_full).
 // Each group has two 128-column accumulators in TMEM, so the MMAs of key tile t+1
 // overlap the softmax of tile t.  `corr` is emitted by the softmax warps through
 // a swizzled smem stage and TMA bulk stores (no strided st.global).
@@ -77,9 +81,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+// Returns the cycles spent waiting (0 on the fast path); used by the optional role profile.
+__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();                     // try_wait itself suspends the warp for a while
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("emip match_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
@@ -87,6 +91,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+  return clock64() - t0;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -181,6 +197,7 @@ struct KParams {
   int nb, nq, nk, y_shift, y_mod, s_first, s_count;
   int grid_w, sub_grid, terms, s_mode;   // s_mode: 0 none, 1 TMA bulk store, 2 direct st.global
   float inv_sqrt_c;
+  unsigned long long* prof;   // optional [gridDim.x][8] wait-cycle counters (emip_match_tc_set_profile_buffer)
 };
 
 // Online-softmax update of one row with 32 score columns (raw accumulator values, scale folded into c2).
@@ -273,7 +290,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int b = 0; b < 2; ++b) { mbar_init(s_full(g, b), 1); mbar_init(s_empty(g, b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -284,40 +301,50 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t kphase = 0;
       uint32_t it = 0;
+      long long w_qe = 0, w_ke = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int prob = item / npair, qt0 = 2 * (item % npair);
         const int by = (prob + p.y_shift) % p.y_mod;
-        mbar_wait(q_empty, (it & 1) ^ 1);
-        for (int g = 0; g < 2; ++g) {
-          // a query tile past the end (odd tile count) is fully out of bounds: TMA fills it with zeros
-          mbar_expect_tx(q_full(g), nch * CHUNK_BYTES);
-          for (int c = 0; c < nch; ++c)
-            tma_load_3d(sbase + OFF_Q + (g * NCHUNK + c) * CHUNK_BYTES, &map_x, q_full(g), c * CH_ELEMS, (qt0 + g) * TM,
-                        prob);
+        w_qe += mbar_wait(q_empty, (it & 1) ^ 1);
+        if (leader) {
+          for (int g = 0; g < 2; ++g) {
+            // a query tile past the end (odd tile count) is fully out of bounds: TMA fills it with zeros
+            mbar_expect_tx(q_full(g), nch * CHUNK_BYTES);
+            for (int c = 0; c < nch; ++c)
+              tma_load_3d(sbase + OFF_Q + (g * NCHUNK + c) * CHUNK_BYTES, &map_x, q_full(g), c * CH_ELEMS,
+                          (qt0 + g) * TM, prob);
+          }
         }
         for (int kt = 0; kt < nkt; ++kt) {
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(k_empty(stage), kphase ^ 1);
-            mbar_expect_tx(k_full(stage), CHUNK_BYTES);
-            tma_load_3d(sbase + OFF_K + stage * CHUNK_BYTES, &map_y, k_full(stage), c * CH_ELEMS, kt * TN, by);
+            w_ke += mbar_wait(k_empty(stage), kphase ^ 1);
+            if (leader) {
+              mbar_expect_tx(k_full(stage), CHUNK_BYTES);
+              tma_load_3d(sbase + OFF_K + stage * CHUNK_BYTES, &map_y, k_full(stage), c * CH_ELEMS, kt * TN, by);
+            }
             if (++stage == STAGES) { stage = 0; kphase ^= 1; }
           }
         }
       }
+      if (p.prof && leader) { p.prof[blockIdx.x * 8 + 0] = w_qe; p.prof[blockIdx.x * 8 + 1] = w_ke; }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===================== UMMA issuer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t kphase = 0;
       uint32_t it = 0, tile = 0;
+      long long w_se = 0, w_kf = 0, w_qf = 0;
+      const long long t_begin = clock64();
       const int n_tail = ((p.nk - (nkt - 1) * TN) + 15) & ~15;
       const uint32_t idesc_full = make_idesc(TN), idesc_tail = make_idesc(n_tail);
       // descriptor start-address units are 16 B: chunk = 1024 units, K16 step inside a swizzle row = 2 units
@@ -326,54 +353,62 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int kt = 0; kt < nkt; ++kt, ++tile) {
           const int buf = tile & 1;
           const uint32_t use = tile >> 1;
-          mbar_wait(s_empty(0, buf), (use & 1) ^ 1);
-          mbar_wait(s_empty(1, buf), (use & 1) ^ 1);
-          tc_fence_after();
           const uint32_t idesc = (kt == nkt - 1) ? idesc_tail : idesc_full;
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(k_full(stage), kphase);
+            w_kf += mbar_wait(k_full(stage), kphase);
             tc_fence_after();
             const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_K + stage * CHUNK_BYTES);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              if (kt == 0 && c == 0) {
-                mbar_wait(q_full(g), it & 1);
+              if (c == 0) {
+                // this group's accumulator must have been drained by its softmax warps (two tiles ago)
+                w_se += mbar_wait(s_empty(g, buf), (use & 1) ^ 1);
+                if (kt == 0) w_qf += mbar_wait(q_full(g), it & 1);
                 tc_fence_after();
               }
               const uint32_t d_tmem = tmem_base + (uint32_t)((g * 2 + buf) * TN);
               // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
               const uint64_t a_hi = qd + (uint64_t)((g * NCHUNK + (c & 1)) * (CHUNK_BYTES >> 4));
               const uint64_t a_lo = qd + (uint64_t)((g * NCHUNK + 2 + (c & 1)) * (CHUNK_BYTES >> 4));
+              if (leader) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, (c | k) ? 1u : 0u);
-              if (c < 2 && nch == NCHUNK) {
+                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, (c | k) ? 1u : 0u);
+                if (c < 2 && nch == NCHUNK) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1u);
+                }
+                if (c == nch - 1) umma_commit(s_full(g, buf));   // this group's S tile is complete
               }
             }
-            umma_commit(k_empty(stage));       // frees the smem stage when these MMAs retire
+            if (leader) umma_commit(k_empty(stage));   // frees the smem stage when these MMAs retire
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; kphase ^= 1; }
           }
-          umma_commit(s_full(0, buf));         // both S tiles complete -> softmax groups
-          umma_commit(s_full(1, buf));
         }
-        umma_commit(q_empty);                  // query tiles no longer read -> producer may overwrite
+        if (leader) umma_commit(q_empty);      // query tiles no longer read -> producer may overwrite
+        __syncwarp();
+      }
+      if (p.prof && leader) {
+        p.prof[blockIdx.x * 8 + 2] = w_se; p.prof[blockIdx.x * 8 + 3] = w_kf; p.prof[blockIdx.x * 8 + 4] = w_qf;
+        p.prof[blockIdx.x * 8 + 5] = clock64() - t_begin;
       }
     }
     __syncwarp();
   } else {
     // ===================== softmax warps =====================
-    const int g = (warp - 2) >> 2;                       // softmax group = query tile of the pair
+    const int g = warp >> 2;                             // softmax group = query tile of the pair
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int r_in_tile = quarter * 32 + lane;
-    const int st = threadIdx.x - 64;                     // 0..255 within the softmax warps
+    const int st = threadIdx.x;                          // 0..255 within the softmax warps
     float* vtab = reinterpret_cast<float*>(smem + OFF_V);
-    const uint32_t stg = sbase + OFF_STG + (warp - 2) * STG_BYTES;
+    const uint32_t stg = sbase + OFF_STG + warp * STG_BYTES;
     const uint32_t vtab_u32 = sbase + OFF_V;
     const float c2 = 1.4426950408889634f * p.inv_sqrt_c;   // log2(e)/sqrt(C)
     const int nk_pad = (p.nk + 31) & ~31;
     uint32_t tile = 0;
     int cur_v = -1;
+    long long w_sf = 0;
+    const long long t_begin = clock64();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int prob = item / npair, qt = 2 * (item % npair) + g;
       const int row = qt * TM + r_in_tile;
@@ -403,7 +438,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int kt = 0; kt < nkt; ++kt, ++tile) {
         const int buf = tile & 1;
         const uint32_t use = tile >> 1;
-        mbar_wait(s_full(g, buf), use & 1);
+        w_sf += mbar_wait(s_full(g, buf), use & 1);
         tc_fence_after();
         const int col_base = kt * TN;
         const int n_valid = min(TN, p.nk - col_base);
@@ -460,12 +495,13 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (p.lse != nullptr) p.lse[(size_t)prob * p.nq + row] = m * p.inv_sqrt_c + logf(l);
       }
     }
+    if (p.prof && threadIdx.x == 0) { p.prof[blockIdx.x * 8 + 6] = w_sf; p.prof[blockIdx.x * 8 + 7] = clock64() - t_begin; }
     if (lane == 0) bulk_wait0();                         // all score stores of this warp have landed
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -570,6 +606,10 @@ int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk) {
 
 }  // namespace
 
+static unsigned long long* g_prof = nullptr;
+// Diagnostics: device buffer of gridDim.x * 8 counters filled by the next launches (NULL switches it off).
+extern "C" void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf) { g_prof = dev_buf; }
+
 bool match_tc_supported(int nq, int nk, int c) { return c == 128 && nk <= MAXK && nk >= 16 && nq >= 1; }
 
 size_t match_tc_split_bytes(int nb, int n, int c) { return emip_align_up((size_t)nb * n * 2 * c * 2, 1024); }
@@ -620,6 +660,7 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   p.s_first = a.s_first; p.s_count = a.s_count;
   p.grid_w = a.grid_w; p.sub_grid = a.sub_grid; p.terms = a.terms; p.s_mode = s_mode;
   p.inv_sqrt_c = 1.0f / a.sqrt_c;
+  p.prof = g_prof;
   const int nqt = (a.nq + TM - 1) / TM;
   int grid = a.nb * ((nqt + 1) / 2);
   if (grid > emip_num_sms()) grid = emip_num_sms();

@@ -51,6 +51,12 @@ int emip_abi_version(void);
 /* 0 when the current CUDA device is sm_100 (B200); error otherwise. */
 int emip_device_check(void);
 
+/* Diagnostics for the tcgen05 kernel behind a1/a2: when set to a device buffer of (SM count) x 8 uint64, every
+ * following launch stores per-CTA wait-cycle counters
+ * [producer: q_empty, k_empty | issuer: s_empty, k_full, q_full, total | softmax warp 2: s_full, total].
+ * NULL (the default) switches it off.  Not thread-safe; for profiling scripts only. */
+void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf);
+
 /* ---- a3: flow_warp ------------------------------------------------------- */
 /* Replaces loss/warp_utils.py:83-93 flow_warp(x, flow12, pad, mode='bilinear')
  * (mesh_grid :7-13 + norm_grid :16-23 + F.grid_sample(align_corners=True)).
