@@ -281,32 +281,12 @@ def main():
             "corr_write_gbs": B_PER_GPU * N * N * 4 / (k_ms * 1e-3) / 1e9,
             "note": "achieved counts S once (2BN^2C+8BN^2); executed = x3 (bf16 hi/lo split) x2 (both directions)",
         }
-        # ---------------- secondary: flow_warp (K3) HBM roofline at B=64, 3x352x352 ----------------
-        import cases
-        x = torch.randn(WARP_B, WARP_C, WARP_H, WARP_W, device=dev, generator=g)
-        fl_s = torch.cat([cases.smooth_flow(11, WARP_B, WARP_H, WARP_W, 30.0),
-                          cases.smooth_flow(12, WARP_B, WARP_H, WARP_W, 30.0)], 1).to(dev)
-        fl_i = 5.0 * torch.randn(WARP_B, 4, WARP_H, WARP_W, device=dev, generator=g)
-        out = torch.empty_like(x)
-        fw_bytes = WARP_B * WARP_H * WARP_W * (2 * WARP_C + 2) * 4
-        kw = {}
-        for name, fl in (("smooth", fl_s), ("iid5px", fl_i)):
-            def call():
-                _lib.check(L.emip_flow_warp_fwd(ptr(x), ptr(fl), ptr(out), I(WARP_B), I(WARP_C), I(WARP_H), I(WARP_W),
-                                                LL(fl.stride(0)), LL(fl.stride(1)), I(0), sp), "warp")
-            for _ in range(5):
-                call()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(50):
-                call()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 50
-            kw[name] = {"launch_ms": ms, "achieved": fw_bytes / (ms * 1e-3) / 1e9, "frac": fw_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
-        line["flow_warp_roofline"] = {"kernel": "flow_warp_fwd_kernel", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
-                                      "bytes_per_launch": fw_bytes, "workload": "B=64, 3x352x352 fp32 (254 MB > L2)",
-                                      "flows": kw}
+        # ---------------- secondary: flow_warp (K3) HBM roofline at B=64, 3x352x352 (tools/k3_bench.py) ----------------
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import k3_bench
+        line["flow_warp_roofline"] = {"kernel": "flow_warp_fwd_kernel / flow_warp_bwd_kernel", "bound": "hbm", "unit": "GB/s",
+                                      "peak": pk["hbm"], "workload": "B=64, 3x352x352 fp32 (254 MB fwd / 317 MB bwd > L2)",
+                                      "flows": k3_bench.run(dev, pk["hbm"])}
         # ---------------- CPU baseline (oracle port) on this box's host cores ----------------
         if not args.no_cpu_baseline and world == 1:
             times, cores = cpu_reference_arm(10, B_PER_GPU)

@@ -74,11 +74,15 @@ __device__ __forceinline__ Tap make_tap(const Coord& c, int H, int W, float& wx,
   return t;
 }
 
-// Forward.  CTA = 32 x 8 output pixels of one sample; one thread per pixel, all C channels.
-// Consecutive lanes = consecutive pixels, so for the piecewise-smooth flows the model produces the four
-// tap requests of a warp touch 1-2 cache lines each (ncu r1a: the earlier 4-pixels-per-thread mapping made
-// every tap request span ~30 sectors and held the kernel to 19 % of HBM peak).  The 8-row tile lets the
-// bottom taps of row y and the top taps of row y+1 hit the same L1 lines.
+// Forward.  CTA = 256 threads = 32 x 8 lanes covering a 32 x 32 pixel tile of one sample: every thread owns
+// ROWS = 4 pixels (rows 8 apart), all C channels.  Consecutive lanes = consecutive pixels, so for the piecewise-smooth
+// flows the model produces the four tap requests of a warp touch 1-2 cache lines each (ncu r1a: a 4-consecutive-
+// pixels-per-thread mapping made every tap request span ~30 sectors and held the kernel to 19 % of HBM peak).
+// All 2*ROWS flow loads are issued first, then all 4*C*ROWS gathers, then the stores: ~50 independent loads in
+// flight per thread keep HBM busy at 16 resident warps per SM.  Vertically adjacent rows of the tile share tap lines
+// through L1 (taps come through the read-only path and are allowed to allocate in L1).
+constexpr int ROWS = 4;
+
 template <bool BORDER, int CT>
 __global__ void __launch_bounds__(256)
 flow_warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
@@ -89,32 +93,58 @@ flow_warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int px = tx * 32 + (threadIdx.x & 31);
-  const int py = ty * 8 + (threadIdx.x >> 5);
-  if (px >= W || py >= H) return;
-  const long long pix = (long long)py * W + px;
-  const float* fp = flow + (long long)b * fsb + pix;
-  const float fx = __ldcs(fp), fy = __ldcs(fp + fsc);          // streamed: read exactly once
-  Coord c = sample_point<BORDER>((float)px + fx, (float)py + fy, H, W);
-  float wx, wy;
-  const Tap tap = make_tap(c, H, W, wx, wy);
+  const int py0 = ty * (8 * ROWS) + (threadIdx.x >> 5);
+  if (px >= W) return;
+  const float* fb = flow + (long long)b * fsb + px;
   const float* xb = x + (long long)b * C * plane;
-  float* ob = out + (long long)b * C * plane + pix;
+  float* ob = out + (long long)b * C * plane + px;
+  float fx[ROWS], fy[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int py = py0 + 8 * r;
+    const bool ok = py < H;
+    fx[r] = ok ? __ldcs(fb + (long long)py * W) : 0.f;            // streamed: read exactly once
+    fy[r] = ok ? __ldcs(fb + fsc + (long long)py * W) : 0.f;
+  }
+  Tap tap[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int py = min(py0 + 8 * r, H - 1);
+    Coord c = sample_point<BORDER>((float)px + fx[r], (float)py + fy[r], H, W);
+    float wx, wy;
+    tap[r] = make_tap(c, H, W, wx, wy);
+  }
   if constexpr (CT > 0) {
-    float v[CT > 0 ? CT : 1][4];
+    float v[ROWS][CT > 0 ? CT : 1][4];
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch) {                           // all 4*C gathers in flight before any use
-      const float* xp = xb + ch * plane;
-      v[ch][0] = __ldg(xp + tap.o00); v[ch][1] = __ldg(xp + tap.o01);
-      v[ch][2] = __ldg(xp + tap.o10); v[ch][3] = __ldg(xp + tap.o11);
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) {                           // every gather in flight before any use
+        const float* xp = xb + ch * plane;
+        v[r][ch][0] = __ldg(xp + tap[r].o00); v[r][ch][1] = __ldg(xp + tap[r].o01);
+        v[r][ch][2] = __ldg(xp + tap[r].o10); v[r][ch][3] = __ldg(xp + tap[r].o11);
+      }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int py = py0 + 8 * r;
+      if (py < H) {
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch)
+          __stcs(ob + ch * plane + (long long)py * W, v[r][ch][0] * tap[r].w00 + v[r][ch][1] * tap[r].w01 +
+                                                          v[r][ch][2] * tap[r].w10 + v[r][ch][3] * tap[r].w11);
+      }
     }
-#pragma unroll
-    for (int ch = 0; ch < CT; ++ch)
-      __stcs(ob + ch * plane, v[ch][0] * tap.w00 + v[ch][1] * tap.w01 + v[ch][2] * tap.w10 + v[ch][3] * tap.w11);
   } else {
     for (int ch = 0; ch < C; ++ch) {
       const float* xp = xb + ch * plane;
-      float v00 = __ldg(xp + tap.o00), v01 = __ldg(xp + tap.o01), v10 = __ldg(xp + tap.o10), v11 = __ldg(xp + tap.o11);
-      __stcs(ob + ch * plane, v00 * tap.w00 + v01 * tap.w01 + v10 * tap.w10 + v11 * tap.w11);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int py = py0 + 8 * r;
+        float v00 = __ldg(xp + tap[r].o00), v01 = __ldg(xp + tap[r].o01), v10 = __ldg(xp + tap[r].o10),
+              v11 = __ldg(xp + tap[r].o11);
+        if (py < H)
+          __stcs(ob + ch * plane + (long long)py * W, v00 * tap[r].w00 + v01 * tap[r].w01 + v10 * tap[r].w10 + v11 * tap[r].w11);
+      }
     }
   }
 }
@@ -132,50 +162,262 @@ flow_warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ flow
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int px = tx * 32 + (threadIdx.x & 31);
-  const int py = ty * 8 + (threadIdx.x >> 5);
-  if (px >= W || py >= H) return;
-  const long long pix = (long long)py * W + px;
-  const float* fp = flow + (long long)b * fsb + pix;
-  const float fx = __ldcs(fp), fy = __ldcs(fp + fsc);
-  const Coord co = sample_point<BORDER>((float)px + fx, (float)py + fy, H, W);
-  float wx, wy;
-  const Tap tap = make_tap(co, H, W, wx, wy);
-  const float ex = 1.0f - wx, ey = 1.0f - wy;
+  const int py0 = ty * (8 * ROWS) + (threadIdx.x >> 5);
+  if (px >= W) return;
+  const float* fb = flow + (long long)b * fsb + px;
   const float* xb = x + (long long)b * C * plane;
-  const float* gb = dout + (long long)b * C * plane + pix;
-  float gx = 0.f, gy = 0.f;
-  auto one = [&](int ch) {
-    const float* xp = xb + ch * plane;
-    const float g = __ldcs(gb + ch * plane);
-    // a tap outside the image counts as value 0 (ATen within_bounds); offsets are always safe
-    float v00 = __ldg(xp + tap.o00), v01 = __ldg(xp + tap.o01), v10 = __ldg(xp + tap.o10), v11 = __ldg(xp + tap.o11);
-    v00 = (tap.valid & 1) ? v00 : 0.f;
-    v01 = (tap.valid & 2) ? v01 : 0.f;
-    v10 = (tap.valid & 4) ? v10 : 0.f;
-    v11 = (tap.valid & 8) ? v11 : 0.f;
-    gx += g * ((v01 - v00) * ey + (v11 - v10) * wy);
-    gy += g * ((v10 - v00) * ex + (v11 - v01) * wx);
-    if (WITH_DX) {
-      float* dp = dx + ((long long)b * C + ch) * plane;
-      if (tap.w00 != 0.0f) atomicAdd(dp + tap.o00, g * tap.w00);
-      if (tap.w01 != 0.0f) atomicAdd(dp + tap.o01, g * tap.w01);
-      if (tap.w10 != 0.0f) atomicAdd(dp + tap.o10, g * tap.w10);
-      if (tap.w11 != 0.0f) atomicAdd(dp + tap.o11, g * tap.w11);
-    }
-  };
-  if constexpr (CT > 0) {
+  const float* gb = dout + (long long)b * C * plane + px;
+  float fx[ROWS], fy[ROWS];
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch) one(ch);
-  } else {
-    for (int ch = 0; ch < C; ++ch) one(ch);
+  for (int r = 0; r < ROWS; ++r) {
+    const int py = py0 + 8 * r;
+    const bool ok = py < H;
+    fx[r] = ok ? __ldcs(fb + (long long)py * W) : 0.f;
+    fy[r] = ok ? __ldcs(fb + fsc + (long long)py * W) : 0.f;
   }
-  // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
-  float* dp = dflow + (long long)b * 2 * plane + pix;
-  __stcs(dp, __fdiv_rn(gx * (wm1 * 0.5f) * co.gmx, wm1) * 2.0f);
-  __stcs(dp + plane, __fdiv_rn(gy * (hm1 * 0.5f) * co.gmy, hm1) * 2.0f);
+  if constexpr (CT > 0 && !WITH_DX) {
+    // the photometric-loss case (images need no gradient): every load of the 4 rows in flight before any use
+    Tap tap[ROWS];
+    Coord co[ROWS];
+    float wxs[ROWS], wys[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int py = min(py0 + 8 * r, H - 1);
+      co[r] = sample_point<BORDER>((float)px + fx[r], (float)py + fy[r], H, W);
+      tap[r] = make_tap(co[r], H, W, wxs[r], wys[r]);
+    }
+    float g[ROWS][CT > 0 ? CT : 1], v[ROWS][CT > 0 ? CT : 1][4];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long pix = (long long)min(py0 + 8 * r, H - 1) * W;
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) {
+        const float* xp = xb + ch * plane;
+        g[r][ch] = __ldcs(gb + ch * plane + pix);
+        v[r][ch][0] = __ldg(xp + tap[r].o00); v[r][ch][1] = __ldg(xp + tap[r].o01);
+        v[r][ch][2] = __ldg(xp + tap[r].o10); v[r][ch][3] = __ldg(xp + tap[r].o11);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int py = py0 + 8 * r;
+      if (py >= H) continue;
+      const float wx = wxs[r], wy = wys[r], ex = 1.0f - wx, ey = 1.0f - wy;
+      float gx = 0.f, gy = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) {
+        // a tap outside the image counts as value 0 (ATen within_bounds); offsets are always safe
+        const float v00 = (tap[r].valid & 1) ? v[r][ch][0] : 0.f, v01 = (tap[r].valid & 2) ? v[r][ch][1] : 0.f;
+        const float v10 = (tap[r].valid & 4) ? v[r][ch][2] : 0.f, v11 = (tap[r].valid & 8) ? v[r][ch][3] : 0.f;
+        gx += g[r][ch] * ((v01 - v00) * ey + (v11 - v10) * wy);
+        gy += g[r][ch] * ((v10 - v00) * ex + (v11 - v01) * wx);
+      }
+      // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
+      float* dp = dflow + (long long)b * 2 * plane + (long long)py * W + px;
+      __stcs(dp, __fdiv_rn(gx * (wm1 * 0.5f) * co[r].gmx, wm1) * 2.0f);
+      __stcs(dp + plane, __fdiv_rn(gy * (hm1 * 0.5f) * co[r].gmy, hm1) * 2.0f);
+    }
+  } else {
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int py = py0 + 8 * r;
+    if (py >= H) continue;
+    const long long pix = (long long)py * W;
+    const Coord co = sample_point<BORDER>((float)px + fx[r], (float)py + fy[r], H, W);
+    float wx, wy;
+    const Tap tap = make_tap(co, H, W, wx, wy);
+    const float ex = 1.0f - wx, ey = 1.0f - wy;
+    float gx = 0.f, gy = 0.f;
+    auto one = [&](int ch) {
+      const float* xp = xb + ch * plane;
+      const float g = __ldcs(gb + ch * plane + pix);
+      // a tap outside the image counts as value 0 (ATen within_bounds); offsets are always safe
+      float v00 = __ldg(xp + tap.o00), v01 = __ldg(xp + tap.o01), v10 = __ldg(xp + tap.o10), v11 = __ldg(xp + tap.o11);
+      v00 = (tap.valid & 1) ? v00 : 0.f;
+      v01 = (tap.valid & 2) ? v01 : 0.f;
+      v10 = (tap.valid & 4) ? v10 : 0.f;
+      v11 = (tap.valid & 8) ? v11 : 0.f;
+      gx += g * ((v01 - v00) * ey + (v11 - v10) * wy);
+      gy += g * ((v10 - v00) * ex + (v11 - v01) * wx);
+      if (WITH_DX) {
+        float* dp = dx + ((long long)b * C + ch) * plane;
+        if (tap.w00 != 0.0f) atomicAdd(dp + tap.o00, g * tap.w00);
+        if (tap.w01 != 0.0f) atomicAdd(dp + tap.o01, g * tap.w01);
+        if (tap.w10 != 0.0f) atomicAdd(dp + tap.o10, g * tap.w10);
+        if (tap.w11 != 0.0f) atomicAdd(dp + tap.o11, g * tap.w11);
+      }
+    };
+    if constexpr (CT > 0) {
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) one(ch);
+    } else {
+      for (int ch = 0; ch < C; ++ch) one(ch);
+    }
+    // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
+    float* dp = dflow + (long long)b * 2 * plane + pix + px;
+    __stcs(dp, __fdiv_rn(gx * (wm1 * 0.5f) * co.gmx, wm1) * 2.0f);
+    __stcs(dp + plane, __fdiv_rn(gy * (hm1 * 0.5f) * co.gmy, hm1) * 2.0f);
+  }
+  }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path for what the photometric loss calls (loss_flow.py:90-91): pad='border', C = 3, no image gradient.
+// The generic kernels above cost ~225 SASS instructions per pixel (two IEEE divisions with slow-path branches,
+// tap-validity masks, 64-bit address arithmetic) and were issue-bound at 40 % of HBM peak; this path needs ~90:
+//  * a / (W-1) is computed as q = a*rc; q += fma(-q, W-1, a) * rc with rc = RN(1/(W-1)) -- the correctly rounded
+//    quotient (checked against IEEE division on 4M samples per size, incl. W-1 = 255/511/1023), so the reference's
+//    normalise -> un-normalise round trip is still reproduced;
+//  * after the border clamp every tap is inside the image except x1 = W (y1 = H), which only occurs with weight
+//    exactly 0: the index is clamped instead of masked;
+//  * in-plane offsets are 32-bit.
+struct FastCoord {
+  unsigned off;          // in-plane offset of the top-left tap (y0 * W + x0); the 2x2 block is off, off+1, off+W, off+W+1
+  float wx, wy, gmx, gmy;
+};
+
+__device__ __forceinline__ float div_rn(float a, float b, float rc) {
+  float q = a * rc;
+  return fmaf(fmaf(-q, b, a), rc, q);
+}
+
+// x0 is clamped to W-2 (y0 to H-2) so that the 2x2 tap block is always inside the image: at ix = W-1 this gives
+// (x0, wx) = (W-2, 1) instead of the reference's (W-1, 0) -- the same interpolated value and the same gradients.
+__device__ __forceinline__ FastCoord fast_coord(float u, float v, int H, int W, float wm1, float hm1, float rcw,
+                                                float rch) {
+  // warp_utils.py:21-22 then ATen grid_sampler_unnormalize (align_corners=True)
+  float ix = (((div_rn(2.0f * u, wm1, rcw) - 1.0f) + 1.0f) * 0.5f) * wm1;
+  float iy = (((div_rn(2.0f * v, hm1, rch) - 1.0f) + 1.0f) * 0.5f) * hm1;
+  FastCoord c;
+  c.gmx = (ix > 0.0f && ix < wm1) ? 1.0f : 0.0f;     // ATen clip_coordinates_set_grad
+  c.gmy = (iy > 0.0f && iy < hm1) ? 1.0f : 0.0f;
+  ix = fminf(fmaxf(ix, 0.0f), wm1);
+  iy = fminf(fmaxf(iy, 0.0f), hm1);
+  const int x0 = min(__float2int_rd(ix), W - 2), y0 = min(__float2int_rd(iy), H - 2);
+  c.wx = ix - (float)x0;
+  c.wy = iy - (float)y0;
+  c.off = (unsigned)(y0 * W + x0);
+  return c;
+}
+
+// Makes a per-sample base pointer opaque to the optimiser: otherwise nvcc folds the 64-bit batch offset into every
+// tap index and spends four instructions per address (IMAD.WIDE + IADD3 + LEA + LEA.HI.X) instead of one IMAD.WIDE.
+template <typename T>
+__device__ __forceinline__ T* opaque(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
+// LINEAR = false: CTA covers a 32 x 32 pixel tile (rows of a thread 8 apart; vertical tap reuse through L1).
+// LINEAR = true : CTA covers 1024 consecutive pixels of a plane (4 KB contiguous per stream; pixels of a thread
+//                 256 apart), which keeps every DRAM page access long.
+template <bool BWD, bool LINEAR>
+__global__ void __launch_bounds__(256)
+flow_warp_border3_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ dout,
+                         float* __restrict__ out, int H, int W, long long fsb, long long fsc, int tiles_x, int tiles_y,
+                         float rcw, float rch) {
+  const unsigned plane = (unsigned)(H * W);
+  int t = blockIdx.x;
+  int b, px, py0;
+  int lpx[ROWS], lpy[ROWS];
+  bool lok[ROWS];
+  if (LINEAR) {
+    b = t / tiles_x;                                   // tiles_x = CTAs per sample
+    const int p0 = (t - b * tiles_x) * (256 * ROWS) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int p = min(p0 + 256 * r, (int)plane - 1);
+      lok[r] = p0 + 256 * r < (int)plane;
+      lpy[r] = p / W;
+      lpx[r] = p - lpy[r] * W;
+    }
+    px = 0; py0 = 0;
+  } else {
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    b = t / tiles_y;
+    px = tx * 32 + (threadIdx.x & 31);
+    py0 = ty * (8 * ROWS) + (threadIdx.x >> 5);
+    if (px >= W) return;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      lok[r] = py0 + 8 * r < H;
+      lpy[r] = min(py0 + 8 * r, H - 1);               // rows past the end re-read the last row (stores masked)
+      lpx[r] = px;
+    }
+  }
+  const float* fb = opaque(flow + (long long)b * fsb);
+  const float* fb2 = opaque(fb + fsc);
+  const float* xb = opaque(x + (long long)b * 3 * plane);
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  unsigned pix[ROWS];
+  float fx[ROWS], fy[ROWS];
+  float g[ROWS][3];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    pix[r] = (unsigned)(lpy[r] * W + lpx[r]);
+    fx[r] = __ldcs(fb + pix[r]);
+    fy[r] = __ldcs(fb2 + pix[r]);
+    if (BWD) {
+      const float* gb = opaque(dout + (long long)b * 3 * plane);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) g[r][ch] = __ldcs(gb + (ch * plane + pix[r]));
+    }
+  }
+  FastCoord c[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+    c[r] = fast_coord((float)lpx[r] + fx[r], (float)lpy[r] + fy[r], H, W, wm1, hm1, rcw, rch);
+  float v[ROWS][3][4];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {                  // all 48 gathers in flight before any use
+      const float* p0 = xb + (c[r].off + ch * plane);
+      const float* p1 = xb + (c[r].off + ch * plane + (unsigned)W);
+      v[r][ch][0] = __ldg(p0); v[r][ch][1] = __ldg(p0 + 1);
+      v[r][ch][2] = __ldg(p1); v[r][ch][3] = __ldg(p1 + 1);
+    }
+  if (!BWD) {
+    float* ob = opaque(out + (long long)b * 3 * plane);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (lok[r]) {
+        const float wx = c[r].wx, wy = c[r].wy;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float top = fmaf(wx, v[r][ch][1] - v[r][ch][0], v[r][ch][0]);
+          const float bot = fmaf(wx, v[r][ch][3] - v[r][ch][2], v[r][ch][2]);
+          __stcs(ob + (ch * plane + pix[r]), fmaf(wy, bot - top, top));
+        }
+      }
+    }
+  } else {
+    float* db = opaque(out + (long long)b * 2 * plane);   // out = dflow [B,2,H,W]
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (lok[r]) {
+        const float wx = c[r].wx, wy = c[r].wy, ex = 1.0f - wx, ey = 1.0f - wy;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          gx = fmaf(g[r][ch], (v[r][ch][1] - v[r][ch][0]) * ey + (v[r][ch][3] - v[r][ch][2]) * wy, gx);
+          gy = fmaf(g[r][ch], (v[r][ch][2] - v[r][ch][0]) * ex + (v[r][ch][3] - v[r][ch][1]) * wx, gy);
+        }
+        // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
+        __stcs(db + pix[r], div_rn(gx * (wm1 * 0.5f) * c[r].gmx, wm1, rcw) * 2.0f);
+        __stcs(db + (plane + pix[r]), div_rn(gy * (hm1 * 0.5f) * c[r].gmy, hm1, rch) * 2.0f);
+      }
+    }
+  }
+}
+
+int g_k3_linear = 0;
 }  // namespace
+
+// Experiment switch (tools/k3_bench.py): 0 = 32x32 tiles, 1 = 1024-pixel linear segments.
+extern "C" void emip_debug_flow_warp_variant(int v) { g_k3_linear = v; }
 
 extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                                   long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream) {
@@ -184,13 +426,23 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_fwd: bad pad_mode %d", pad_mode);
   cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * ROWS - 1) / (8 * ROWS);
   const long long nblk = (long long)B * tiles_x * tiles_y;
   EMIP_CHECK_ARG(nblk < 0x7fffffffLL, "flow_warp_fwd: problem too large");
 #define LAUNCH(BD, CT) \
   flow_warp_fwd_kernel<BD, CT><<<(unsigned)nblk, 256, 0, st>>>(x, flow, out, C, H, W, flow_stride_b, flow_stride_c, tiles_x, tiles_y)
   const bool border = pad_mode == EMIP_PAD_BORDER;
-  if (C == 3) { if (border) LAUNCH(true, 3); else LAUNCH(false, 3); }
+  if (C == 3 && border && (long long)H * W * 4 < 0x7fffffffLL) {
+    const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
+    if (g_k3_linear) {
+      const int per = (H * W + 256 * ROWS - 1) / (256 * ROWS);
+      flow_warp_border3_kernel<false, true><<<(unsigned)(B * per), 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b,
+                                                                                  flow_stride_c, per, 1, rcw, rch);
+    } else {
+      flow_warp_border3_kernel<false, false><<<(unsigned)nblk, 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b,
+                                                                              flow_stride_c, tiles_x, tiles_y, rcw, rch);
+    }
+  } else if (C == 3) { if (border) LAUNCH(true, 3); else LAUNCH(false, 3); }
   else if (C == 2) { if (border) LAUNCH(true, 2); else LAUNCH(false, 2); }
   else { if (border) LAUNCH(true, 0); else LAUNCH(false, 0); }
 #undef LAUNCH
@@ -206,14 +458,24 @@ extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_bwd: bad pad_mode %d", pad_mode);
   cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * ROWS - 1) / (8 * ROWS);
   const long long nblk = (long long)B * tiles_x * tiles_y;
   EMIP_CHECK_ARG(nblk < 0x7fffffffLL, "flow_warp_bwd: problem too large");
 #define LAUNCH(BD, DX, CT)                                                                                      \
   flow_warp_bwd_kernel<BD, DX, CT><<<(unsigned)nblk, 256, 0, st>>>(x, flow, dout, dflow, dx, C, H, W, flow_stride_b, \
                                                                    flow_stride_c, tiles_x, tiles_y)
   const bool border = pad_mode == EMIP_PAD_BORDER;
-  if (C == 3) {
+  if (C == 3 && border && dx == nullptr && (long long)H * W * 4 < 0x7fffffffLL) {
+    const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
+    if (g_k3_linear) {
+      const int per = (H * W + 256 * ROWS - 1) / (256 * ROWS);
+      flow_warp_border3_kernel<true, true><<<(unsigned)(B * per), 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b,
+                                                                                 flow_stride_c, per, 1, rcw, rch);
+    } else {
+      flow_warp_border3_kernel<true, false><<<(unsigned)nblk, 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b,
+                                                                             flow_stride_c, tiles_x, tiles_y, rcw, rch);
+    }
+  } else if (C == 3) {
     if (border) { if (dx) LAUNCH(true, true, 3); else LAUNCH(true, false, 3); }
     else { if (dx) LAUNCH(false, true, 3); else LAUNCH(false, false, 3); }
   } else {
