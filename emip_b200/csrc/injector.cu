@@ -1,0 +1,898 @@
+// K4: prompt fusion (camouflaged feeder / motion collector) -- forward and backward.
+//
+// Replaces reference model/EMIP_short/motion/PromptInteract.py:452-464 (Injector) =
+// TransformerBlock_MDTA :436-450 = x + MDTA(LN1(x), LN2(x1)), then x + GDFN(LN3(x)) with
+// Attention_MDTA :390-432, FeedForward :367-385, WithBias_LayerNorm :333-349, and the autograd
+// graph torch derives for them.  dim 128, 2 heads x 64 channels, hidden 340, all convs bias-free.
+//
+// Everything is exact fp32 on the CUDA cores: the injector's inputs/outputs have to stay
+// fp32-accurate (bf16 I/O here costs 4.7e-2 end to end), and at ~1 MB per tensor
+// the block is launch/HBM bound, not FLOP bound.  What the reference runs as ~25 library
+// launches with three `rearrange` copies becomes 10 launches (forward):
+//   ln_stats x2 | gemm (LN fused on load) x2 | depthwise 3x3 (+ row sum-of-squares) x2 |
+//   64x64 Gram per (sample, head) | softmax + fold attn into project_out | gemm + residual |
+//   ln_stats | gemm (LN on load) | depthwise 3x3 + gelu gate | gemm + residual
+// Layout: activations stay [B, C, N] (NCHW, N = H*W contiguous): no permutes anywhere.
+// All reductions are deterministic (two-stage, no atomics).
+#include "common.cuh"
+#include "../../include/emip_b200.h"
+#include "gemm_simt.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int DIM = 128;
+constexpr int HEADS = 2;
+constexpr int HD = 64;          // channels per head
+constexpr int HID = 340;        // int(128 * 2.66)
+constexpr int HID2 = 680;
+constexpr float LN_EPS = 1e-5f;
+constexpr float NORM_EPS = 1e-12f;
+
+// ------------------------------------------------------------------ LayerNorm statistics
+// mean / rstd over the C channels of every pixel (PromptInteract.py:346-349: biased variance, eps 1e-5)
+__global__ void ln_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int C,
+                                int N) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* xp = x + (size_t)b * C * N + n;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += __ldg(xp + (size_t)c * N);
+  const float mu = s / (float)C;
+  float v = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = __ldg(xp + (size_t)c * N) - mu;
+    v = fmaf(d, d, v);
+  }
+  mean[(size_t)b * N + n] = mu;
+  rstd[(size_t)b * N + n] = 1.0f / sqrtf(v / (float)C + LN_EPS);
+}
+
+// ------------------------------------------------------------------ GEMM building blocks (gemm_simt.cuh)
+constexpr int GB = 64;   // block tile (both dims)
+constexpr int GK = 16;   // contraction step
+
+__device__ __forceinline__ float ln_apply(float v, int k, size_t bn, const GemmNN& a) {
+  return (v - __ldg(a.mean + bn)) * __ldg(a.rstd + bn) * __ldg(a.gamma + k) + __ldg(a.beta + k);
+}
+
+// Y[b][m][n] = sum_k W(b)[m][k] X'(b)[k][n] (+res) ; 256 threads, 64x64 tile, 4x4 outputs per thread
+__global__ void __launch_bounds__(256) gemm_nn_kernel(GemmNN a) {
+  __shared__ float Ws[GK][GB + 4];
+  __shared__ float Xs[GK][GB + 4];
+  const int b = blockIdx.z, m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* W = a.w + (size_t)b * a.w_stride_b;
+  const float* X = a.x + (size_t)b * a.x_stride_b;
+  const bool ln = a.mean != nullptr;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += GK) {
+    // W tile: element (m, k)
+    for (int i = threadIdx.x; i < GB * GK; i += 256) {
+      int m, k;
+      if (a.w_trans) { k = i / GB; m = i % GB; } else { m = i / GK; k = i % GK; }
+      float v = 0.f;
+      if (m0 + m < a.M && k0 + k < a.K)
+        v = __ldg(W + (a.w_trans ? (size_t)(k0 + k) * a.ldw + (m0 + m) : (size_t)(m0 + m) * a.ldw + (k0 + k)));
+      Ws[k][m] = v;
+    }
+    // X tile: element (k, n), n contiguous
+    for (int i = threadIdx.x; i < GK * GB; i += 256) {
+      const int k = i / GB, n = i % GB;
+      float v = 0.f;
+      if (k0 + k < a.K && n0 + n < a.N) {
+        v = __ldg(X + (size_t)(k0 + k) * a.ldx + (n0 + n));
+        if (ln) v = ln_apply(v, k0 + k, (size_t)b * a.N + n0 + n, a);
+      }
+      Xs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][ty * 4]);
+      const float4 xv = *reinterpret_cast<const float4*>(&Xs[k][tx * 4]);
+      const float wa[4] = {wv.x, wv.y, wv.z, wv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], xa[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Y = a.y + (size_t)b * a.y_stride_b;
+  const float* R = a.res ? a.res + (size_t)b * a.res_stride_b : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float v = acc[i][j];
+      if (R) v += __ldg(R + (size_t)m * a.ldr + n);
+      float* yp = Y + (size_t)m * a.ldy + n;
+      *yp = a.accumulate ? (*yp + v) : v;
+    }
+  }
+}
+
+// C[b*S+s][m][k] = sum_{n in split s} A(b)[m][n] B'(b)[k][n]
+struct GemmNTk {
+  GemmNT g;
+  int nsplit, chunk;
+};
+__global__ void __launch_bounds__(256) gemm_nt_kernel(GemmNTk p) {
+  const GemmNT& a = p.g;
+  __shared__ float As[32][GB + 4];
+  __shared__ float Bs[32][GB + 4];
+  const int bs = blockIdx.z, b = bs / p.nsplit, s = bs % p.nsplit;
+  const int m0 = blockIdx.y * GB, k0 = blockIdx.x * GB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* A = a.a + (size_t)b * a.a_stride_b;
+  const float* Bm = a.bm + (size_t)b * a.b_stride_b;
+  const bool ln = a.mean != nullptr;
+  const int nbeg = s * p.chunk, nend = min(a.N, nbeg + p.chunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int n0 = nbeg; n0 < nend; n0 += 32) {
+    for (int i = threadIdx.x; i < GB * 32; i += 256) {
+      const int r = i / 32, n = i % 32;          // 32 consecutive n per row: one 128-byte segment per warp
+      float va = 0.f, vb = 0.f;
+      if (n0 + n < nend) {
+        if (m0 + r < a.M) va = __ldg(A + (size_t)(m0 + r) * a.lda + n0 + n);
+        if (k0 + r < a.K) {
+          vb = __ldg(Bm + (size_t)(k0 + r) * a.ldb + n0 + n);
+          if (ln) {
+            const size_t bn = (size_t)b * a.N + n0 + n;
+            vb = (vb - __ldg(a.mean + bn)) * __ldg(a.rstd + bn) * __ldg(a.gamma + k0 + r) + __ldg(a.beta + k0 + r);
+          }
+        }
+      }
+      As[n][r] = va;
+      Bs[n][r] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < 32; ++n) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[n][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[n][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, ba[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], ba[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* C = a.c + (size_t)bs * a.c_stride_b;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < a.K) C[(size_t)m * a.ldc + k] = acc[i][j];
+    }
+  }
+}
+
+__global__ void reduce_batch_kernel(const float* __restrict__ in, long long stride, float* __restrict__ out, int B,
+                                    long long n, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += __ldg(in + (size_t)b * stride + i);   // fixed order: deterministic
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+// ------------------------------------------------------------------ depthwise 3x3, one (sample, channel) plane per CTA
+// The whole plane lives in shared memory with a zero halo, so forward, gelu gate, backward-data and
+// backward-weight are all CTA-local.
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+
+__device__ __forceinline__ void load_plane(float* s, const float* __restrict__ g, int H, int W) {
+  const int Wp = W + 2, tot = (H + 2) * Wp;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int y = i / Wp - 1, x = i % Wp - 1;
+    s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(g + y * W + x) : 0.f;
+  }
+}
+// cross-correlation with the 3x3 kernel k (nn.Conv2d semantics, padding 1)
+__device__ __forceinline__ float conv9(const float* s, int Wp, int y, int x, const float* k) {
+  const float* p = s + y * Wp + x;            // top-left of the window in the padded plane
+  return p[0] * k[0] + p[1] * k[1] + p[2] * k[2] + p[Wp] * k[3] + p[Wp + 1] * k[4] + p[Wp + 2] * k[5] +
+         p[2 * Wp] * k[6] + p[2 * Wp + 1] * k[7] + p[2 * Wp + 2] * k[8];
+}
+// transposed (backward-data) convolution: d_in(y,x) = sum_{ky,kx} d_out(y-ky+1, x-kx+1) k[ky][kx]
+__device__ __forceinline__ float conv9_flipped(const float* s, int Wp, int y, int x, const float* k) {
+  const float* p = s + y * Wp + x;
+  return p[0] * k[8] + p[1] * k[7] + p[2] * k[6] + p[Wp] * k[5] + p[Wp + 1] * k[4] + p[Wp + 2] * k[3] +
+         p[2 * Wp] * k[2] + p[2 * Wp + 1] * k[1] + p[2 * Wp + 2] * k[0];
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];   // fixed order
+  return s;
+}
+
+// out(c) = dw3x3(in(c)); channels >= split go to out2 (channel c - split): splits kv into k and v.
+// sumsq (optional): per (b, c) sum of squares of the output (for F.normalize over the pixels).
+__global__ void __launch_bounds__(256)
+dwconv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, float* __restrict__ out2,
+                  float* __restrict__ sumsq, int C, int split, int H, int W) {
+  extern __shared__ float sm[];
+  __shared__ float red[8];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, Wp = W + 2;
+  load_plane(sm, in + ((size_t)b * C + c) * N, H, W);
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  __syncthreads();
+  float* o = (c < split) ? out + ((size_t)b * split + c) * N : out2 + ((size_t)b * (C - split) + (c - split)) * N;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float v = conv9(sm, Wp, i / W, i % W, k);
+    o[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+  if (sumsq != nullptr) {
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) sumsq[(size_t)b * C + c] = ss;
+  }
+}
+
+// backward of the above: dout(c) comes from dout (c < split) or dout2; din = flipped conv; dw partial per (b, c)
+__global__ void __launch_bounds__(256)
+dwconv_bwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ dout,
+                  const float* __restrict__ dout2, float* __restrict__ din, float* __restrict__ dw_part, int C, int split,
+                  int H, int W) {
+  extern __shared__ float sm[];
+  __shared__ float red[8];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, Wp = W + 2, P = (H + 2) * Wp;
+  float* s_in = sm;
+  float* s_do = sm + P;
+  load_plane(s_in, in + ((size_t)b * C + c) * N, H, W);
+  const float* dg = (c < split) ? dout + ((size_t)b * split + c) * N : dout2 + ((size_t)b * (C - split) + (c - split)) * N;
+  load_plane(s_do, dg, H, W);
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  __syncthreads();
+  float dk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dk[i] = 0.f;
+  float* di = din + ((size_t)b * C + c) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int y = i / W, x = i % W;
+    di[i] = conv9_flipped(s_do, Wp, y, x, k);
+    const float g = s_do[(y + 1) * Wp + x + 1];
+    const float* p = s_in + y * Wp + x;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) dk[ky * 3 + kx] = fmaf(g, p[ky * Wp + kx], dk[ky * 3 + kx]);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float s = block_sum(dk[i], red);
+    if (threadIdx.x == 0) dw_part[((size_t)b * C + c) * 9 + i] = s;
+  }
+}
+
+// GDFN gate, forward: g(c) = gelu(dw(t_pre[c])) * dw(t_pre[c + HID])      (PromptInteract.py:382-383)
+__global__ void __launch_bounds__(256)
+gdfn_gate_fwd_kernel(const float* __restrict__ tpre, const float* __restrict__ w, float* __restrict__ g, int H, int W) {
+  extern __shared__ float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, Wp = W + 2, P = (H + 2) * Wp;
+  load_plane(sm, tpre + ((size_t)b * HID2 + c) * N, H, W);
+  load_plane(sm + P, tpre + ((size_t)b * HID2 + c + HID) * N, H, W);
+  float k1[9], k2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { k1[i] = __ldg(w + c * 9 + i); k2[i] = __ldg(w + (c + HID) * 9 + i); }
+  __syncthreads();
+  float* o = g + ((size_t)b * HID + c) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int y = i / W, x = i % W;
+    o[i] = gelu_erf(conv9(sm, Wp, y, x, k1)) * conv9(sm + P, Wp, y, x, k2);
+  }
+}
+
+// GDFN gate, backward: recomputes t1, t2 from t_pre, forms dt1 = dg t2 gelu'(t1), dt2 = dg gelu(t1), then the
+// depthwise backward (data + weight) for both channels.  Also re-emits g for the project_out weight gradient.
+__global__ void __launch_bounds__(256)
+gdfn_gate_bwd_kernel(const float* __restrict__ tpre, const float* __restrict__ w, const float* __restrict__ dg,
+                     float* __restrict__ dtpre, float* __restrict__ g_out, float* __restrict__ dw_part, int H, int W) {
+  extern __shared__ float sm[];
+  __shared__ float red[8];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, Wp = W + 2, P = (H + 2) * Wp;
+  float* s1 = sm;            // t_pre[c]
+  float* s2 = sm + P;        // t_pre[c + HID]
+  float* d1 = sm + 2 * P;    // dt1 (padded)
+  float* d2 = sm + 3 * P;    // dt2
+  load_plane(s1, tpre + ((size_t)b * HID2 + c) * N, H, W);
+  load_plane(s2, tpre + ((size_t)b * HID2 + c + HID) * N, H, W);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { d1[i] = 0.f; d2[i] = 0.f; }
+  float k1[9], k2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { k1[i] = __ldg(w + c * 9 + i); k2[i] = __ldg(w + (c + HID) * 9 + i); }
+  __syncthreads();
+  const float* dgp = dg + ((size_t)b * HID + c) * N;
+  float* go = g_out + ((size_t)b * HID + c) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int y = i / W, x = i % W;
+    const float t1 = conv9(s1, Wp, y, x, k1), t2 = conv9(s2, Wp, y, x, k2);
+    const float gg = gelu_erf(t1), d = __ldg(dgp + i);
+    go[i] = gg * t2;
+    d1[(y + 1) * Wp + x + 1] = d * t2 * gelu_erf_grad(t1);
+    d2[(y + 1) * Wp + x + 1] = d * gg;
+  }
+  __syncthreads();
+  float dk1[9], dk2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { dk1[i] = 0.f; dk2[i] = 0.f; }
+  float* o1 = dtpre + ((size_t)b * HID2 + c) * N;
+  float* o2 = dtpre + ((size_t)b * HID2 + c + HID) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int y = i / W, x = i % W;
+    o1[i] = conv9_flipped(d1, Wp, y, x, k1);
+    o2[i] = conv9_flipped(d2, Wp, y, x, k2);
+    const float g1 = d1[(y + 1) * Wp + x + 1], g2 = d2[(y + 1) * Wp + x + 1];
+    const float* p1 = s1 + y * Wp + x;
+    const float* p2 = s2 + y * Wp + x;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        dk1[ky * 3 + kx] = fmaf(g1, p1[ky * Wp + kx], dk1[ky * 3 + kx]);
+        dk2[ky * 3 + kx] = fmaf(g2, p2[ky * Wp + kx], dk2[ky * 3 + kx]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float a1 = block_sum(dk1[i], red);
+    const float a2 = block_sum(dk2[i], red);
+    if (threadIdx.x == 0) {
+      dw_part[((size_t)b * HID2 + c) * 9 + i] = a1;
+      dw_part[((size_t)b * HID2 + c + HID) * 9 + i] = a2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ MDTA channel attention, per (sample, head)
+// forward: attn = softmax_d( G[c][d] / (|q_c| |k_d|) * temperature )   (PromptInteract.py:421-425), then folds
+// it into project_out:  M[b][o][h*64+d] = sum_c Wo[o][h*64+c] attn[c][d], so that  z = M[b] v.
+__global__ void __launch_bounds__(256)
+mdta_attn_fwd_kernel(const float* __restrict__ G, const float* __restrict__ sq, const float* __restrict__ sk,
+                     const float* __restrict__ temperature, const float* __restrict__ wo, float* __restrict__ attn,
+                     float* __restrict__ M) {
+  __shared__ float sa[HD][HD + 1];
+  const int bh = blockIdx.x, b = bh / HEADS, h = bh % HEADS;
+  const float tau = __ldg(temperature + h);
+  const float* g = G + (size_t)bh * HD * HD;
+  // one warp per row c (8 warps -> 8 rows per pass); lane handles d and d + 32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < HD; c += 8) {
+    const float nq = fmaxf(sqrtf(__ldg(sq + (size_t)b * DIM + h * HD + c)), NORM_EPS);
+    float s0 = __ldg(g + c * HD + lane) / (nq * fmaxf(sqrtf(__ldg(sk + (size_t)b * DIM + h * HD + lane)), NORM_EPS)) * tau;
+    float s1 = __ldg(g + c * HD + lane + 32) /
+               (nq * fmaxf(sqrtf(__ldg(sk + (size_t)b * DIM + h * HD + lane + 32)), NORM_EPS)) * tau;
+    const float m = warp_max(fmaxf(s0, s1));
+    s0 = expf(s0 - m);
+    s1 = expf(s1 - m);
+    const float l = warp_sum(s0 + s1);
+    s0 /= l;
+    s1 /= l;
+    sa[c][lane] = s0;
+    sa[c][lane + 32] = s1;
+    attn[(size_t)bh * HD * HD + c * HD + lane] = s0;
+    attn[(size_t)bh * HD * HD + c * HD + lane + 32] = s1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DIM * HD; i += 256) {
+    const int o = i / HD, d = i % HD;
+    float acc = 0.f;
+    for (int c = 0; c < HD; ++c) acc = fmaf(__ldg(wo + (size_t)o * DIM + h * HD + c), sa[c][d], acc);
+    M[(size_t)b * DIM * DIM + (size_t)o * DIM + h * HD + d] = acc;
+  }
+}
+
+// backward: P[b][o][j] = sum_n dz[b][o][n] v[b][j][n]  (dz = gradient at project_out's output)
+//   dattn[c][d] = sum_o Wo[o][h64+c] P[o][h64+d]          dWo_part[b][o][h64+c] = sum_d P[o][h64+d] attn[c][d]
+//   dS = attn o (dattn - rowsum(dattn o attn))
+//   S = tau G / (nq nk)  =>  dG' = dS tau/(nq nk) ; dtau_part = sum dS G/(nq nk) ;
+//   d nq_c = -sum_d dS S / nq_c ; d nk_d = -sum_c dS S / nk_d ; a_q = d nq / |q| (0 when |q| <= eps), same for k
+__global__ void __launch_bounds__(256)
+mdta_attn_bwd_kernel(const float* __restrict__ P, const float* __restrict__ attn, const float* __restrict__ G,
+                     const float* __restrict__ sq, const float* __restrict__ sk, const float* __restrict__ temperature,
+                     const float* __restrict__ wo, float* __restrict__ dGs, float* __restrict__ aq, float* __restrict__ ak,
+                     float* __restrict__ dtau_part, float* __restrict__ dwo_part) {
+  __shared__ float sa[HD][HD + 1];    // attn
+  __shared__ float sd[HD][HD + 1];    // dattn, then dS
+  __shared__ float snq[HD], snk[HD];  // max(|q_c|, eps), max(|k_d|, eps)
+  __shared__ float red[8];
+  const int bh = blockIdx.x, b = bh / HEADS, h = bh % HEADS;
+  const float tau = __ldg(temperature + h);
+  const float* p = P + (size_t)b * DIM * DIM;
+  const float* Gb = G + (size_t)bh * HD * HD;
+  if (threadIdx.x < HD) snq[threadIdx.x] = fmaxf(sqrtf(__ldg(sq + (size_t)b * DIM + h * HD + threadIdx.x)), NORM_EPS);
+  else if (threadIdx.x < 2 * HD) snk[threadIdx.x - HD] = fmaxf(sqrtf(__ldg(sk + (size_t)b * DIM + h * HD + threadIdx.x - HD)), NORM_EPS);
+  __syncthreads();
+  auto sS = [&](int c, int d) { return __ldg(Gb + c * HD + d) / (snq[c] * snk[d]); };   // S / tau
+  for (int i = threadIdx.x; i < HD * HD; i += 256) {
+    const int c = i / HD, d = i % HD;
+    sa[c][d] = __ldg(attn + (size_t)bh * HD * HD + i);
+    float acc = 0.f;
+    for (int o = 0; o < DIM; ++o) acc = fmaf(__ldg(wo + (size_t)o * DIM + h * HD + c), __ldg(p + (size_t)o * DIM + h * HD + d), acc);
+    sd[c][d] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DIM * HD; i += 256) {
+    const int o = i / HD, c = i % HD;
+    float acc = 0.f;
+    for (int d = 0; d < HD; ++d) acc = fmaf(__ldg(p + (size_t)o * DIM + h * HD + d), sa[c][d], acc);
+    dwo_part[(size_t)b * DIM * DIM + (size_t)o * DIM + h * HD + c] = acc;
+  }
+  // softmax backward, one warp per row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < HD; c += 8) {
+    const float r = warp_sum(sd[c][lane] * sa[c][lane] + sd[c][lane + 32] * sa[c][lane + 32]);
+    sd[c][lane] = sa[c][lane] * (sd[c][lane] - r);
+    sd[c][lane + 32] = sa[c][lane + 32] * (sd[c][lane + 32] - r);
+  }
+  __syncthreads();
+  float tsum = 0.f;
+  for (int i = threadIdx.x; i < HD * HD; i += 256) {
+    const int c = i / HD, d = i % HD;
+    tsum = fmaf(sd[c][d], sS(c, d), tsum);
+    dGs[(size_t)bh * HD * HD + i] = sd[c][d] * tau / (snq[c] * snk[d]);
+  }
+  tsum = block_sum(tsum, red);
+  if (threadIdx.x == 0) dtau_part[bh] = tsum;
+  if (threadIdx.x < HD) {
+    const int c = threadIdx.x;
+    float s = 0.f;
+    for (int d = 0; d < HD; ++d) s = fmaf(sd[c][d], sS(c, d), s);
+    const float n2 = __ldg(sq + (size_t)b * DIM + h * HD + c), nq = sqrtf(n2);
+    // d|q_c| = -tau * s / nq ;  dq += d|q| * q / |q|
+    aq[(size_t)b * DIM + h * HD + c] = (nq > NORM_EPS) ? (-tau * s / (nq * nq)) : 0.f;
+  } else if (threadIdx.x < 2 * HD) {
+    const int d = threadIdx.x - HD;
+    float s = 0.f;
+    for (int c = 0; c < HD; ++c) s = fmaf(sd[c][d], sS(c, d), s);
+    const float n2 = __ldg(sk + (size_t)b * DIM + h * HD + d), nk = sqrtf(n2);
+    ak[(size_t)b * DIM + h * HD + d] = (nk > NORM_EPS) ? (-tau * s / (nk * nk)) : 0.f;
+  }
+}
+
+// y[b][c][n] += a[b][c] * x[b][c][n]
+__global__ void row_axpy_kernel(const float* __restrict__ a, const float* __restrict__ x, float* __restrict__ y, int N) {
+  const size_t row = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) y[row * N + n] = fmaf(__ldg(a + row), __ldg(x + row * N + n), y[row * N + n]);
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx = rstd (dn g - mean_c(dn g) - xhat mean_c(dn g xhat)) (+ add), dn = gradient at the LN output
+__global__ void ln_bwd_dx_kernel(const float* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ mean,
+                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                 const float* __restrict__ add, float* __restrict__ dx, int C, int N) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t base = (size_t)b * C * N + n;
+  const float mu = __ldg(mean + (size_t)b * N + n), rs = __ldg(rstd + (size_t)b * N + n);
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float g = __ldg(dn + base + (size_t)c * N) * __ldg(gamma + c);
+    const float xh = (__ldg(x + base + (size_t)c * N) - mu) * rs;
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+  }
+  s1 /= (float)C;
+  s2 /= (float)C;
+  for (int c = 0; c < C; ++c) {
+    const float g = __ldg(dn + base + (size_t)c * N) * __ldg(gamma + c);
+    const float xh = (__ldg(x + base + (size_t)c * N) - mu) * rs;
+    float v = rs * (g - s1 - xh * s2);
+    if (add != nullptr) v += __ldg(add + base + (size_t)c * N);
+    dx[base + (size_t)c * N] = v;
+  }
+}
+// per (b, c): dgamma_part = sum_n dn xhat, dbeta_part = sum_n dn
+__global__ void __launch_bounds__(256)
+ln_bwd_param_kernel(const float* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, float* __restrict__ dg_part, float* __restrict__ db_part, int C, int N) {
+  __shared__ float red[8];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const size_t row = ((size_t)b * C + c) * N;
+  float sg = 0.f, sb = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float d = __ldg(dn + row + n);
+    const float xh = (__ldg(x + row + n) - __ldg(mean + (size_t)b * N + n)) * __ldg(rstd + (size_t)b * N + n);
+    sg = fmaf(d, xh, sg);
+    sb += d;
+  }
+  sg = block_sum(sg, red);
+  sb = block_sum(sb, red);
+  if (threadIdx.x == 0) { dg_part[(size_t)b * C + c] = sg; db_part[(size_t)b * C + c] = sb; }
+}
+
+// ------------------------------------------------------------------ host-side launch helpers
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int N) {
+  __shared__ float red[8];
+  const size_t row = blockIdx.x;
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float v = __ldg(x + row * N + n);
+    s = fmaf(v, v, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[row] = s;
+}
+int launch_row_sumsq(const float* x, float* out, int rows, int N, cudaStream_t st) {
+  row_sumsq_kernel<<<rows, 256, 0, st>>>(x, out, N);
+  EMIP_CHECK_LAUNCH("row_sumsq");
+  return EMIP_OK;
+}
+
+int launch_ln_stats(const float* x, float* mean, float* rstd, int B, int C, int N, cudaStream_t st) {
+  ln_stats_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(x, mean, rstd, C, N);
+  EMIP_CHECK_LAUNCH("ln_stats");
+  return EMIP_OK;
+}
+size_t plane_smem(int H, int W, int planes) { return sizeof(float) * (size_t)planes * (H + 2) * (W + 2); }
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) EMIP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return EMIP_OK;
+}
+
+// carve helper
+struct Carver {
+  char* p;
+  size_t left;
+  bool ok;
+  float* take(size_t n_floats) {
+    size_t bytes = emip_align_up(n_floats * sizeof(float), 256);
+    if (bytes > left) { ok = false; return nullptr; }
+    float* r = reinterpret_cast<float*>(p);
+    p += bytes;
+    left -= bytes;
+    return r;
+  }
+};
+size_t al(size_t n_floats) { return emip_align_up(n_floats * sizeof(float), 256); }
+
+// parameter order = the order of the reference's state_dict (include/emip_b200.h)
+enum {
+  P_N1W, P_N1B, P_N2W, P_N2B, P_N3W, P_N3B, P_TEMP, P_QW, P_QDW, P_KVW, P_KVDW, P_POW, P_FIW, P_FDW, P_FOW, P_COUNT
+};
+
+struct Saved {          // activations kept for the backward pass (caller-owned buffer)
+  float *mean1, *rstd1, *mean2, *rstd2, *mean3, *rstd3;
+  float *qpre, *kvpre, *q, *k, *v, *sq, *sk, *G, *attn, *M, *y, *tpre;
+};
+size_t saved_bytes(int B, int N) {
+  size_t s = 6 * al((size_t)B * N);
+  s += al((size_t)B * DIM * N) * 5 + al((size_t)B * 2 * DIM * N);          // qpre q k v y + kvpre
+  s += 2 * al((size_t)B * DIM) + 2 * al((size_t)B * HEADS * HD * HD) + al((size_t)B * DIM * DIM);
+  s += al((size_t)B * HID2 * N);
+  return s;
+}
+bool carve_saved(void* buf, size_t bytes, int B, int N, Saved* s) {
+  Carver c{static_cast<char*>(buf), bytes, true};
+  s->mean1 = c.take((size_t)B * N); s->rstd1 = c.take((size_t)B * N);
+  s->mean2 = c.take((size_t)B * N); s->rstd2 = c.take((size_t)B * N);
+  s->mean3 = c.take((size_t)B * N); s->rstd3 = c.take((size_t)B * N);
+  s->qpre = c.take((size_t)B * DIM * N); s->kvpre = c.take((size_t)B * 2 * DIM * N);
+  s->q = c.take((size_t)B * DIM * N); s->k = c.take((size_t)B * DIM * N); s->v = c.take((size_t)B * DIM * N);
+  s->sq = c.take((size_t)B * DIM); s->sk = c.take((size_t)B * DIM);
+  s->G = c.take((size_t)B * HEADS * HD * HD); s->attn = c.take((size_t)B * HEADS * HD * HD);
+  s->M = c.take((size_t)B * DIM * DIM);
+  s->y = c.take((size_t)B * DIM * N); s->tpre = c.take((size_t)B * HID2 * N);
+  return c.ok;
+}
+constexpr int NT_SPLIT = 4;     // pixel-axis splits of the weight-gradient GEMMs (more CTAs at small batch)
+
+int check_common(const char* who, int B, int H, int W) {
+  EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "%s: bad shape B=%d H=%d W=%d", who, B, H, W);
+  if (plane_smem(H, W, 4) > 200 * 1024) {
+    emip_set_error("%s: %dx%d feature maps do not fit the plane-resident depthwise kernels", who, H, W);
+    return EMIP_ENOSYS;
+  }
+  return EMIP_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ public GEMM helpers (gemm_simt.cuh)
+int gemm_nn(const GemmNN& a, cudaStream_t st) {
+  if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
+  dim3 grid((a.N + GB - 1) / GB, (a.M + GB - 1) / GB, a.B);
+  gemm_nn_kernel<<<grid, 256, 0, st>>>(a);
+  EMIP_CHECK_LAUNCH("gemm_nn");
+  return EMIP_OK;
+}
+// nsplit partial results per batch entry: c must hold B*nsplit matrices (c_stride_b apart)
+static int gemm_nt_split(const GemmNT& a, int nsplit, cudaStream_t st) {
+  if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
+  GemmNTk p;
+  p.g = a;
+  p.nsplit = nsplit;
+  p.chunk = ((a.N + nsplit - 1) / nsplit + 31) / 32 * 32;
+  dim3 grid((a.K + GB - 1) / GB, (a.M + GB - 1) / GB, a.B * nsplit);
+  gemm_nt_kernel<<<grid, 256, 0, st>>>(p);
+  EMIP_CHECK_LAUNCH("gemm_nt");
+  return EMIP_OK;
+}
+int gemm_nt(const GemmNT& a, cudaStream_t st) { return gemm_nt_split(a, 1, st); }
+int reduce_batch(const float* in, long long stride, float* out, int B, long long n, int accumulate, cudaStream_t st) {
+  if (n == 0) return EMIP_OK;
+  reduce_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, stride, out, B, n, accumulate);
+  EMIP_CHECK_LAUNCH("reduce_batch");
+  return EMIP_OK;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" size_t emip_injector_saved_bytes(int B, int H, int W) {
+  if (B < 0 || H <= 0 || W <= 0) return 0;
+  return saved_bytes(B, H * W);
+}
+extern "C" size_t emip_injector_workspace(int B, int H, int W) {
+  if (B < 0 || H <= 0 || W <= 0) return 0;
+  const size_t N = (size_t)H * W;
+  // forward: g [B,340,N]; backward: g, dg, dtpre [B,680,N], 4 x [B,128,N], dkvpre [B,256,N], dn [B,128,N], partials
+  size_t s = 2 * al((size_t)B * HID * N) + al((size_t)B * HID2 * N) + 6 * al((size_t)B * DIM * N) +
+             al((size_t)B * 2 * DIM * N);
+  s += al((size_t)B * NT_SPLIT * HID2 * DIM);                      // largest weight-gradient partial
+  s += al((size_t)B * DIM * DIM) * 2 + al((size_t)B * HEADS * HD * HD) + 4 * al((size_t)B * DIM);
+  s += al((size_t)B * HID2 * 9) + 2 * al((size_t)B * DIM) + al((size_t)B * HEADS);
+  return s;
+}
+
+extern "C" int emip_injector_fwd(const float* x, const float* x1, const float* const* params, float* out, void* saved,
+                                 size_t saved_bytes_in, void* workspace, size_t ws_bytes, int B, int H, int W,
+                                 void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && x1 && params && out && saved && workspace, "injector_fwd: null pointer");
+  int rc = check_common("injector_fwd", B, H, W);
+  if (rc) return rc;
+  for (int i = 0; i < P_COUNT; ++i) EMIP_CHECK_ARG(params[i] != nullptr, "injector_fwd: parameter %d is NULL", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = H * W;
+  Saved s;
+  if (saved_bytes_in < saved_bytes(B, N) || !carve_saved(saved, saved_bytes_in, B, N, &s)) {
+    emip_set_error("injector_fwd: saved buffer too small (%zu < %zu)", saved_bytes_in, saved_bytes(B, N));
+    return EMIP_ENOMEM;
+  }
+  if (ws_bytes < emip_injector_workspace(B, H, W)) {
+    emip_set_error("injector_fwd: workspace too small");
+    return EMIP_ENOMEM;
+  }
+  Carver w{static_cast<char*>(workspace), ws_bytes, true};
+  float* g = w.take((size_t)B * HID * N);
+
+  // norm1 / norm2 statistics (PromptInteract.py:447, :346-349)
+  if ((rc = launch_ln_stats(x, s.mean1, s.rstd1, B, DIM, N, st))) return rc;
+  if ((rc = launch_ln_stats(x1, s.mean2, s.rstd2, B, DIM, N, st))) return rc;
+  // q = q_dwconv(q(LN1 x)), kv = kv_dwconv(kv(LN2 x1))      (:413-415)
+  GemmNN a = {};
+  a.B = B; a.N = N; a.K = DIM; a.ldx = N; a.x_stride_b = (long long)DIM * N; a.ldy = N;
+  a.w = params[P_QW]; a.ldw = DIM; a.M = DIM; a.x = x; a.mean = s.mean1; a.rstd = s.rstd1;
+  a.gamma = params[P_N1W]; a.beta = params[P_N1B]; a.y = s.qpre; a.y_stride_b = (long long)DIM * N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  a.w = params[P_KVW]; a.M = 2 * DIM; a.x = x1; a.mean = s.mean2; a.rstd = s.rstd2;
+  a.gamma = params[P_N2W]; a.beta = params[P_N2B]; a.y = s.kvpre; a.y_stride_b = (long long)2 * DIM * N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  const size_t sm1 = plane_smem(H, W, 1);
+  if ((rc = ensure_smem(dwconv_fwd_kernel, sm1))) return rc;
+  dwconv_fwd_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
+  EMIP_CHECK_LAUNCH("dwconv q");
+  // k = channels [0,128), v = [128,256) of kv (:415); only k is L2-normalised
+  dwconv_fwd_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
+  EMIP_CHECK_LAUNCH("dwconv kv");
+  // G[c][d] = sum_n q[c][n] k[d][n] per (sample, head)      (:421-424, normalisation folded in afterwards)
+  {
+    GemmNT t = {};
+    t.B = B * HEADS; t.M = HD; t.K = HD; t.N = N;
+    t.a = s.q; t.a_stride_b = (long long)HD * N; t.lda = N;
+    t.bm = s.k; t.b_stride_b = (long long)HD * N; t.ldb = N;
+    t.c = s.G; t.c_stride_b = HD * HD; t.ldc = HD;
+    if ((rc = gemm_nt(t, st))) return rc;
+  }
+  // |k_d|^2 over the pixels (F.normalize, :422); |q_c|^2 came out of the q depthwise kernel
+  if ((rc = launch_row_sumsq(s.k, s.sk, B * DIM, N, st))) return rc;
+  mdta_attn_fwd_kernel<<<B * HEADS, 256, 0, st>>>(s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], s.attn, s.M);
+  EMIP_CHECK_LAUNCH("mdta_attn_fwd");
+  // y = x + project_out(attn @ v) = x + M[b] v             (:427-431, :447)
+  a = {};
+  a.B = B; a.M = DIM; a.K = DIM; a.N = N; a.w = s.M; a.w_stride_b = DIM * DIM; a.ldw = DIM;
+  a.x = s.v; a.x_stride_b = (long long)DIM * N; a.ldx = N;
+  a.res = x; a.res_stride_b = (long long)DIM * N; a.ldr = N;
+  a.y = s.y; a.y_stride_b = (long long)DIM * N; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  // GDFN: out = y + project_out(gelu(t1) * t2), t = dwconv(project_in(LN3 y))     (:380-385, :448)
+  if ((rc = launch_ln_stats(s.y, s.mean3, s.rstd3, B, DIM, N, st))) return rc;
+  a = {};
+  a.B = B; a.M = HID2; a.K = DIM; a.N = N; a.w = params[P_FIW]; a.ldw = DIM;
+  a.x = s.y; a.x_stride_b = (long long)DIM * N; a.ldx = N; a.mean = s.mean3; a.rstd = s.rstd3;
+  a.gamma = params[P_N3W]; a.beta = params[P_N3B];
+  a.y = s.tpre; a.y_stride_b = (long long)HID2 * N; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  const size_t sm2 = plane_smem(H, W, 2);
+  if ((rc = ensure_smem(gdfn_gate_fwd_kernel, sm2))) return rc;
+  gdfn_gate_fwd_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
+  EMIP_CHECK_LAUNCH("gdfn_gate_fwd");
+  a = {};
+  a.B = B; a.M = DIM; a.K = HID; a.N = N; a.w = params[P_FOW]; a.ldw = HID;
+  a.x = g; a.x_stride_b = (long long)HID * N; a.ldx = N;
+  a.res = s.y; a.res_stride_b = (long long)DIM * N; a.ldr = N;
+  a.y = out; a.y_stride_b = (long long)DIM * N; a.ldy = N;
+  return gemm_nn(a, st);
+}
+
+extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* const* params, const void* saved,
+                                 size_t saved_bytes_in, const float* dout, float* dx, float* dx1, float* const* dparams,
+                                 void* workspace, size_t ws_bytes, int B, int H, int W, void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && x1 && params && saved && dout && dx && dx1 && dparams && workspace, "injector_bwd: null pointer");
+  int rc = check_common("injector_bwd", B, H, W);
+  if (rc) return rc;
+  for (int i = 0; i < P_COUNT; ++i)
+    EMIP_CHECK_ARG(params[i] != nullptr && dparams[i] != nullptr, "injector_bwd: parameter %d is NULL", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = H * W;
+  Saved s;
+  if (saved_bytes_in < saved_bytes(B, N) || !carve_saved(const_cast<void*>(saved), saved_bytes_in, B, N, &s)) {
+    emip_set_error("injector_bwd: saved buffer too small");
+    return EMIP_ENOMEM;
+  }
+  if (ws_bytes < emip_injector_workspace(B, H, W)) {
+    emip_set_error("injector_bwd: workspace too small");
+    return EMIP_ENOMEM;
+  }
+  Carver w{static_cast<char*>(workspace), ws_bytes, true};
+  float* g = w.take((size_t)B * HID * N);
+  float* dg = w.take((size_t)B * HID * N);
+  float* dtpre = w.take((size_t)B * HID2 * N);
+  float* t128a = w.take((size_t)B * DIM * N);     // dn (gradient at a LayerNorm output)
+  float* dy = w.take((size_t)B * DIM * N);
+  float* dq = w.take((size_t)B * DIM * N);
+  float* dk = w.take((size_t)B * DIM * N);
+  float* dv = w.take((size_t)B * DIM * N);
+  float* dqpre = w.take((size_t)B * DIM * N);
+  float* dkvpre = w.take((size_t)B * 2 * DIM * N);
+  float* wpart = w.take((size_t)B * NT_SPLIT * HID2 * DIM);
+  float* Pm = w.take((size_t)B * DIM * DIM);
+  float* dwo_part = w.take((size_t)B * DIM * DIM);
+  float* dGs = w.take((size_t)B * HEADS * HD * HD);
+  float* aq = w.take((size_t)B * DIM);
+  float* ak = w.take((size_t)B * DIM);
+  float* lg_part = w.take((size_t)B * DIM);
+  float* lb_part = w.take((size_t)B * DIM);
+  float* dwc_part = w.take((size_t)B * HID2 * 9);
+  float* dtau_part = w.take((size_t)B * HEADS);
+  if (!w.ok) { emip_set_error("injector_bwd: workspace carve failed"); return EMIP_ENOMEM; }
+  const long long sN = (long long)DIM * N;
+
+  // ---- GDFN: out = y + Wout g
+  GemmNN a = {};
+  a.B = B; a.M = HID; a.K = DIM; a.N = N; a.w = params[P_FOW]; a.ldw = HID; a.w_trans = 1;     // dg = Wout^T dout
+  a.x = dout; a.x_stride_b = sN; a.ldx = N; a.y = dg; a.y_stride_b = (long long)HID * N; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  const size_t sm4 = plane_smem(H, W, 4);
+  if ((rc = ensure_smem(gdfn_gate_bwd_kernel, sm4))) return rc;
+  gdfn_gate_bwd_kernel<<<dim3(HID, B), 256, sm4, st>>>(s.tpre, params[P_FDW], dg, dtpre, g, dwc_part, H, W);
+  EMIP_CHECK_LAUNCH("gdfn_gate_bwd");
+  if ((rc = reduce_batch(dwc_part, HID2 * 9, dparams[P_FDW], B, HID2 * 9, 0, st))) return rc;
+  GemmNT t = {};
+  t.B = B; t.M = DIM; t.K = HID; t.N = N;                                                        // dWout = dout g^T
+  t.a = dout; t.a_stride_b = sN; t.lda = N; t.bm = g; t.b_stride_b = (long long)HID * N; t.ldb = N;
+  t.c = wpart; t.c_stride_b = DIM * HID; t.ldc = HID;
+  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
+  if ((rc = reduce_batch(wpart, DIM * HID, dparams[P_FOW], B * NT_SPLIT, DIM * HID, 0, st))) return rc;
+  t = {};
+  t.B = B; t.M = HID2; t.K = DIM; t.N = N;                                                       // dWin = dtpre LN3(y)^T
+  t.a = dtpre; t.a_stride_b = (long long)HID2 * N; t.lda = N; t.bm = s.y; t.b_stride_b = sN; t.ldb = N;
+  t.mean = s.mean3; t.rstd = s.rstd3; t.gamma = params[P_N3W]; t.beta = params[P_N3B];
+  t.c = wpart; t.c_stride_b = HID2 * DIM; t.ldc = DIM;
+  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
+  if ((rc = reduce_batch(wpart, HID2 * DIM, dparams[P_FIW], B * NT_SPLIT, HID2 * DIM, 0, st))) return rc;
+  a = {};
+  a.B = B; a.M = DIM; a.K = HID2; a.N = N; a.w = params[P_FIW]; a.ldw = DIM; a.w_trans = 1;      // dn3 = Win^T dtpre
+  a.x = dtpre; a.x_stride_b = (long long)HID2 * N; a.ldx = N; a.y = t128a; a.y_stride_b = sN; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  ln_bwd_param_kernel<<<dim3(DIM, B), 256, 0, st>>>(t128a, s.y, s.mean3, s.rstd3, lg_part, lb_part, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_param 3");
+  if ((rc = reduce_batch(lg_part, DIM, dparams[P_N3W], B, DIM, 0, st))) return rc;
+  if ((rc = reduce_batch(lb_part, DIM, dparams[P_N3B], B, DIM, 0, st))) return rc;
+  // dy = dout (residual) + LN3 backward
+  ln_bwd_dx_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(t128a, s.y, s.mean3, s.rstd3, params[P_N3W], dout, dy, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_dx 3");
+
+  // ---- MDTA: y = x + M[b] v,  M = Wo blockdiag(attn)
+  t = {};
+  t.B = B; t.M = DIM; t.K = DIM; t.N = N;                                                        // P = dy v^T
+  t.a = dy; t.a_stride_b = sN; t.lda = N; t.bm = s.v; t.b_stride_b = sN; t.ldb = N;
+  t.c = Pm; t.c_stride_b = DIM * DIM; t.ldc = DIM;
+  if ((rc = gemm_nt(t, st))) return rc;
+  mdta_attn_bwd_kernel<<<B * HEADS, 256, 0, st>>>(Pm, s.attn, s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], dGs, aq, ak,
+                                                   dtau_part, dwo_part);
+  EMIP_CHECK_LAUNCH("mdta_attn_bwd");
+  if ((rc = reduce_batch(dwo_part, DIM * DIM, dparams[P_POW], B, DIM * DIM, 0, st))) return rc;
+  if ((rc = reduce_batch(dtau_part, HEADS, dparams[P_TEMP], B, HEADS, 0, st))) return rc;
+  a = {};
+  a.B = B; a.M = DIM; a.K = DIM; a.N = N; a.w = s.M; a.w_stride_b = DIM * DIM; a.ldw = DIM; a.w_trans = 1;   // dv = M^T dy
+  a.x = dy; a.x_stride_b = sN; a.ldx = N; a.y = dv; a.y_stride_b = sN; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  // dq = dG' k + a_q q ; dk = dG'^T q + a_k k      (per (sample, head): batch of 2B 64x64 problems)
+  a = {};
+  a.B = B * HEADS; a.M = HD; a.K = HD; a.N = N; a.w = dGs; a.w_stride_b = HD * HD; a.ldw = HD;
+  a.x = s.k; a.x_stride_b = (long long)HD * N; a.ldx = N; a.y = dq; a.y_stride_b = (long long)HD * N; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  a.w_trans = 1; a.x = s.q; a.y = dk;
+  if ((rc = gemm_nn(a, st))) return rc;
+  row_axpy_kernel<<<dim3((N + 255) / 256, B * DIM), 256, 0, st>>>(aq, s.q, dq, N);
+  row_axpy_kernel<<<dim3((N + 255) / 256, B * DIM), 256, 0, st>>>(ak, s.k, dk, N);
+  EMIP_CHECK_LAUNCH("row_axpy");
+  // depthwise backward
+  const size_t sm2 = plane_smem(H, W, 2);
+  if ((rc = ensure_smem(dwconv_bwd_kernel, sm2))) return rc;
+  dwconv_bwd_kernel<<<dim3(DIM, B), 256, sm2, st>>>(s.qpre, params[P_QDW], dq, nullptr, dqpre, dwc_part, DIM, DIM, H, W);
+  EMIP_CHECK_LAUNCH("dwconv_bwd q");
+  if ((rc = reduce_batch(dwc_part, DIM * 9, dparams[P_QDW], B, DIM * 9, 0, st))) return rc;
+  dwconv_bwd_kernel<<<dim3(2 * DIM, B), 256, sm2, st>>>(s.kvpre, params[P_KVDW], dk, dv, dkvpre, dwc_part, 2 * DIM, DIM, H, W);
+  EMIP_CHECK_LAUNCH("dwconv_bwd kv");
+  if ((rc = reduce_batch(dwc_part, 2 * DIM * 9, dparams[P_KVDW], B, 2 * DIM * 9, 0, st))) return rc;
+  // 1x1 convs + LayerNorms
+  t = {};
+  t.B = B; t.M = DIM; t.K = DIM; t.N = N;                                                        // dWq = dqpre LN1(x)^T
+  t.a = dqpre; t.a_stride_b = sN; t.lda = N; t.bm = x; t.b_stride_b = sN; t.ldb = N;
+  t.mean = s.mean1; t.rstd = s.rstd1; t.gamma = params[P_N1W]; t.beta = params[P_N1B];
+  t.c = wpart; t.c_stride_b = DIM * DIM; t.ldc = DIM;
+  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
+  if ((rc = reduce_batch(wpart, DIM * DIM, dparams[P_QW], B * NT_SPLIT, DIM * DIM, 0, st))) return rc;
+  t.M = 2 * DIM; t.a = dkvpre; t.a_stride_b = 2 * sN; t.bm = x1;                                  // dWkv = dkvpre LN2(x1)^T
+  t.mean = s.mean2; t.rstd = s.rstd2; t.gamma = params[P_N2W]; t.beta = params[P_N2B];
+  t.c_stride_b = 2 * DIM * DIM;
+  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
+  if ((rc = reduce_batch(wpart, 2 * DIM * DIM, dparams[P_KVW], B * NT_SPLIT, 2 * DIM * DIM, 0, st))) return rc;
+  a = {};
+  a.B = B; a.M = DIM; a.K = DIM; a.N = N; a.w = params[P_QW]; a.ldw = DIM; a.w_trans = 1;        // dn1 = Wq^T dqpre
+  a.x = dqpre; a.x_stride_b = sN; a.ldx = N; a.y = t128a; a.y_stride_b = sN; a.ldy = N;
+  if ((rc = gemm_nn(a, st))) return rc;
+  ln_bwd_param_kernel<<<dim3(DIM, B), 256, 0, st>>>(t128a, x, s.mean1, s.rstd1, lg_part, lb_part, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_param 1");
+  if ((rc = reduce_batch(lg_part, DIM, dparams[P_N1W], B, DIM, 0, st))) return rc;
+  if ((rc = reduce_batch(lb_part, DIM, dparams[P_N1B], B, DIM, 0, st))) return rc;
+  // dx = dy (residual x + ...) + LN1 backward
+  ln_bwd_dx_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(t128a, x, s.mean1, s.rstd1, params[P_N1W], dy, dx, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_dx 1");
+  a.K = 2 * DIM; a.w = params[P_KVW]; a.x = dkvpre; a.x_stride_b = 2 * sN;                         // dn2 = Wkv^T dkvpre
+  if ((rc = gemm_nn(a, st))) return rc;
+  ln_bwd_param_kernel<<<dim3(DIM, B), 256, 0, st>>>(t128a, x1, s.mean2, s.rstd2, lg_part, lb_part, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_param 2");
+  if ((rc = reduce_batch(lg_part, DIM, dparams[P_N2W], B, DIM, 0, st))) return rc;
+  if ((rc = reduce_batch(lb_part, DIM, dparams[P_N2B], B, DIM, 0, st))) return rc;
+  ln_bwd_dx_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(t128a, x1, s.mean2, s.rstd2, params[P_N2W], nullptr, dx1, DIM, N);
+  EMIP_CHECK_LAUNCH("ln_bwd_dx 2");
+  return EMIP_OK;
+}

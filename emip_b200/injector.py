@@ -1,0 +1,142 @@
+"""Injector (camouflaged feeder / motion collector): drop-in for reference PromptInteract.py:452-464 (K4).
+
+The module tree only exists to own the parameters under the reference's exact ``state_dict`` keys
+(``transformer.norm1.body.weight`` ... ``transformer.ffn.project_out.weight``) with the reference's
+initialisation; ``forward`` hands the 15 tensors to one fused C-ABI call (emip_injector_fwd/_bwd).
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import I, SZ, ptr, stream_ptr
+from ._ws import workspace
+
+DIM, HEADS, HIDDEN = 128, 2, int(128 * 2.66)
+
+# order of the C ABI's params[] = order of the reference's state_dict
+PARAM_KEYS = (
+    "norm1.body.weight", "norm1.body.bias", "norm2.body.weight", "norm2.body.bias",
+    "norm3.body.weight", "norm3.body.bias", "attn.temperature", "attn.q.weight",
+    "attn.q_dwconv.weight", "attn.kv.weight", "attn.kv_dwconv.weight",
+    "attn.project_out.weight", "ffn.project_in.weight", "ffn.dwconv.weight",
+    "ffn.project_out.weight",
+)
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _InjectorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, x1, *params):
+        B, C, H, W = x.shape
+        x = x.contiguous()
+        x1 = x1.contiguous()
+        params = [p.contiguous() for p in params]
+        L = _lib.lib()
+        L.emip_injector_saved_bytes.restype = ctypes.c_size_t
+        L.emip_injector_workspace.restype = ctypes.c_size_t
+        nsaved = L.emip_injector_saved_bytes(I(B), I(H), I(W))
+        saved, saved_ptr, _ = workspace(nsaved, x.device, align=256)
+        ws, ws_ptr, ws_n = workspace(L.emip_injector_workspace(I(B), I(H), I(W)), x.device, align=256)
+        out = torch.empty_like(x)
+        _lib.check(L.emip_injector_fwd(ptr(x), ptr(x1), _ptr_array(params), ptr(out), ctypes.c_void_p(saved_ptr),
+                                       SZ(nsaved), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(H), I(W), stream_ptr()),
+                   "emip_injector_fwd")
+        ctx.save_for_backward(x, x1, saved, *params)
+        ctx.saved_ptr, ctx.nsaved = saved_ptr, nsaved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, x1, saved, *params = ctx.saved_tensors
+        B, C, H, W = x.shape
+        L = _lib.lib()
+        L.emip_injector_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_injector_workspace(I(B), I(H), I(W)), x.device, align=256)
+        dout = dout.contiguous()
+        dx, dx1 = torch.empty_like(x), torch.empty_like(x1)
+        dparams = [torch.empty_like(p) for p in params]
+        _lib.check(L.emip_injector_bwd(ptr(x), ptr(x1), _ptr_array(params), ctypes.c_void_p(ctx.saved_ptr), SZ(ctx.nsaved),
+                                       ptr(dout), ptr(dx), ptr(dx1), _ptr_array(dparams), ctypes.c_void_p(ws_ptr),
+                                       SZ(ws_n), I(B), I(H), I(W), stream_ptr()), "emip_injector_bwd")
+        return (dx, dx1, *dparams)
+
+
+def injector_forward(x, x1, params):
+    """Functional form: ``params`` maps PARAM_KEYS (or is a sequence in that order) to tensors."""
+    if not (x.is_cuda and x1.is_cuda):
+        raise _lib.EmipError("emip_b200 injector needs CUDA tensors (no CPU fallback)")
+    if x.dtype != torch.float32 or x1.dtype != torch.float32:
+        raise TypeError("emip_b200 injector computes in fp32 (SURVEY.md F4: its I/O must stay fp32-accurate)")
+    if x.shape != x1.shape or x.dim() != 4 or x.shape[1] != DIM:
+        raise ValueError(f"injector expects two [B,{DIM},H,W] tensors, got {tuple(x.shape)} and {tuple(x1.shape)}")
+    plist = [params[k] for k in PARAM_KEYS] if isinstance(params, dict) else list(params)
+    return _InjectorFn.apply(x, x1, *plist)
+
+
+class _WithBiasLayerNorm(nn.Module):            # PromptInteract.py:333-349 (parameters only)
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class _LayerNorm(nn.Module):                    # PromptInteract.py:352-362
+    def __init__(self, dim):
+        super().__init__()
+        self.body = _WithBiasLayerNorm(dim)
+
+
+class _AttentionMDTA(nn.Module):                # PromptInteract.py:390-405
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.q = nn.Conv2d(dim, dim, kernel_size=1, bias=False)
+        self.q_dwconv = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim, bias=False)
+        self.kv = nn.Conv2d(dim, dim * 2, kernel_size=1, bias=False)
+        self.kv_dwconv = nn.Conv2d(dim * 2, dim * 2, kernel_size=3, stride=1, padding=1, groups=dim * 2, bias=False)
+        self.project_out = nn.Conv2d(dim, dim, kernel_size=1, bias=False)
+
+
+class _FeedForward(nn.Module):                  # PromptInteract.py:367-378
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.project_in = nn.Conv2d(dim, hidden * 2, kernel_size=1, bias=False)
+        self.dwconv = nn.Conv2d(hidden * 2, hidden * 2, kernel_size=3, stride=1, padding=1, groups=hidden * 2, bias=False)
+        self.project_out = nn.Conv2d(hidden, dim, kernel_size=1, bias=False)
+
+
+class TransformerBlock_MDTA(nn.Module):         # PromptInteract.py:436-450
+    def __init__(self, dim=DIM, num_heads=HEADS, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias"):
+        super().__init__()
+        if dim != DIM or num_heads != HEADS or int(dim * ffn_expansion_factor) != HIDDEN or bias or \
+                LayerNorm_type != "WithBias":
+            raise NotImplementedError("emip_b200 implements the configuration EMIP instantiates: dim 128, 2 heads, "
+                                      "expansion 2.66, bias-free convs, WithBias LayerNorm")
+        self.norm1 = _LayerNorm(dim)
+        self.attn = _AttentionMDTA(dim, num_heads)
+        self.norm2 = _LayerNorm(dim)
+        self.ffn = _FeedForward(dim, HIDDEN)
+        self.norm3 = _LayerNorm(dim)
+
+    def forward(self, x, x1):
+        p = dict(self.named_parameters())
+        return injector_forward(x, x1, [p[k] for k in PARAM_KEYS])
+
+
+class Injector(nn.Module):
+    """Same constructor, parameters and ``forward(image_embeddings, flow)`` as the reference (PromptInteract.py:452-464)."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.transformer = TransformerBlock_MDTA()
+
+    def forward(self, image_embeddings, flow):
+        return self.transformer(image_embeddings, flow)

@@ -111,6 +111,26 @@ int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const flo
                        const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes, int B, int N,
                        int C, void* stream);
 
+/* ---- a4: prompt fusion (camouflaged feeder / motion collector) ---------------------------------- */
+/* Replaces model/EMIP_short/motion/PromptInteract.py:452-464 Injector.forward(image_embeddings, flow)
+ * = TransformerBlock_MDTA :436-450 (LayerNorm :333-362, Attention_MDTA :390-432, FeedForward :367-385)
+ * and its autograd backward.  dim 128, 2 heads, hidden 340; exact fp32.
+ *   x, x1, out, dout, dx, dx1   [B,128,H,W] contiguous
+ *   params / dparams            15 device pointers in the order of the reference's state_dict:
+ *        transformer.{norm1.body.weight, norm1.body.bias, norm2.body.weight, norm2.body.bias, norm3.body.weight,
+ *        norm3.body.bias, attn.temperature, attn.q.weight, attn.q_dwconv.weight, attn.kv.weight,
+ *        attn.kv_dwconv.weight, attn.project_out.weight, ffn.project_in.weight, ffn.dwconv.weight,
+ *        ffn.project_out.weight}; dparams are overwritten (not accumulated).
+ *   saved      >= emip_injector_saved_bytes() : activations written by fwd, read by bwd (caller keeps it alive)
+ *   workspace  >= emip_injector_workspace()   : scratch, 256-byte aligned */
+size_t emip_injector_saved_bytes(int B, int H, int W);
+size_t emip_injector_workspace(int B, int H, int W);
+int emip_injector_fwd(const float* x, const float* x1, const float* const* params, float* out, void* saved,
+                      size_t saved_bytes, void* workspace, size_t ws_bytes, int B, int H, int W, void* stream);
+int emip_injector_bwd(const float* x, const float* x1, const float* const* params, const void* saved, size_t saved_bytes,
+                      const float* dout, float* dx, float* dx1, float* const* dparams, void* workspace, size_t ws_bytes,
+                      int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,14 @@ def test_ops_fail_loudly_without_cuda():
         flow_warp(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8))
     with pytest.raises(_lib.EmipError):
         global_correlation_softmax(torch.zeros(1, 128, 4, 4), torch.zeros(1, 128, 4, 4), True)
+
+
+def test_injector_state_dict_matches_reference_keys():
+    """checkpoints load by key filter, so names and shapes must be the reference's."""
+    import cases
+    from emip_b200.injector import Injector, PARAM_KEYS
+    sd = Injector().state_dict()
+    want = {"transformer." + k: shp for k, shp in cases.INJECTOR_SHAPES.items()}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    assert list(PARAM_KEYS) == list(cases.INJECTOR_SHAPES)
+    assert sum(v.numel() for v in sd.values()) == 206442      # SURVEY.md 8a: learnable params per injector

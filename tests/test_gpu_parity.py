@@ -225,3 +225,37 @@ def test_a2_insitu_c1(golden):
     out = m(torch.cat((dev(g["f0"]), dev(g["f1"])), 0), flow)
     e = cases.check_packed(out, g["ffa_out"], TOL_OUT, "ffa_out")
     print(f"c1 in-situ FFA: rel-L2 {e:.2e}")
+
+
+# ----------------------------------------------------------------------------- a4
+@pytest.mark.parametrize("name", list(cases.A4_CASES))
+def test_a4_injector_golden(golden, name):
+    """Prompt fusion (feeder / collector) forward + full backward vs the reference's recorded outputs."""
+    from emip_b200.injector import Injector
+    g = golden(name)
+    d = cases.a4_inputs(cases.A4_CASES[name])
+    m = Injector().cuda()
+    m.transformer.load_state_dict(d["params"])
+    x = dev(d["x"]).requires_grad_(True)
+    x1 = dev(d["x1"]).requires_grad_(True)
+    out = m(x, x1)
+    e = cases.check_packed(out, g["out"], 2e-5, "out")
+    (out * dev(d["wout"])).sum().backward()
+    e_dx = cases.check_packed(x.grad, g["dx"], 1e-4, "dx")
+    e_dx1 = cases.check_packed(x1.grad, g["dx1"], 2e-4, "dx1")
+    print(f"{name}: out {e:.2e} dx {e_dx:.2e} dx1 {e_dx1:.2e}")
+    for k, p in m.transformer.named_parameters():
+        cases.check_packed(p.grad, g["dparams"][k], 3e-4, "d" + k)
+
+
+def test_a4_injector_vs_oracle_batch():
+    """B=3 at full resolution vs the CPU oracle (forward), plus determinism of the two-stage reductions."""
+    from emip_b200.injector import Injector
+    s = dict(b=3, h=44, w=44, xs=2.2, x1s=1.0, seed=47)
+    d = cases.a4_inputs(s)
+    m = Injector().cuda()
+    m.transformer.load_state_dict(d["params"])
+    ref = O.injector(d["x"], d["x1"], d["params"])
+    out = m(dev(d["x"]), dev(d["x1"]))
+    assert rel(out, ref) < 2e-5
+    assert torch.equal(out, m(dev(d["x"]), dev(d["x1"])))
