@@ -20,77 +20,10 @@
 #include "common.cuh"
 #include "../../include/emip_b200.h"
 #include "pair_common.cuh"
+#include "simt_tiles.cuh"
 
 namespace {
-
-constexpr int KC = 128;          // feature channels (contraction length)
-constexpr int BM = 64;           // rows per CTA
-constexpr int BN = 64;           // columns per tile
-constexpr int LDX = KC + 4;      // padded smem row stride (floats) -> conflict-free LDS.128
-constexpr int LDW = BN + 4;
-constexpr int NT = 256;          // threads: 16 x 16, thread (tx,ty) owns rows ty+16a, cols tx+16b
-
-// Load a [64 tokens x 128 channels] tile into smem as T[token][channel].
-// layout 0: src is token-major [N][C]; layout 1: src is channel-major [C][N].
-// Tokens >= n_valid are zero-filled.
-__device__ __forceinline__ void load_tile(float* __restrict__ dst, const float* __restrict__ src, int layout,
-                                          int tok0, int n_valid, int n_total) {
-  const int tid = threadIdx.x;
-  if (layout == 0) {
-    // 64 rows x 32 float4; a warp reads one full 512 B row
-    for (int i = tid; i < BM * (KC / 4); i += NT) {
-      int r = i / (KC / 4), c4 = i % (KC / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tok0 + r < n_valid) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(tok0 + r) * KC) + c4);
-      *reinterpret_cast<float4*>(dst + r * LDX + c4 * 4) = v;
-    }
-  } else {
-    // channel-major: consecutive lanes read consecutive tokens of one channel
-    for (int i = tid; i < BM * KC; i += NT) {
-      int c = i / BM, r = i % BM;
-      float v = 0.f;
-      if (tok0 + r < n_valid) v = __ldg(src + (size_t)c * n_total + tok0 + r);
-      dst[r * LDX + c] = v;
-    }
-  }
-}
-
-// acc[a][b] = sum_c Xs[ty+16a][c] * Ys[tx+16b][c]
-__device__ __forceinline__ void s_tile(const float* __restrict__ Xs, const float* __restrict__ Ys, int tx, int ty,
-                                       float (&acc)[4][4]) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
-  for (int c4 = 0; c4 < KC / 4; ++c4) {
-    float4 xa[4], yb[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) xa[a] = *reinterpret_cast<const float4*>(Xs + (ty + 16 * a) * LDX + c4 * 4);
-#pragma unroll
-    for (int b = 0; b < 4; ++b) yb[b] = *reinterpret_cast<const float4*>(Ys + (tx + 16 * b) * LDX + c4 * 4);
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        acc[a][b] = fmaf(xa[a].x, yb[b].x, acc[a][b]);
-        acc[a][b] = fmaf(xa[a].y, yb[b].y, acc[a][b]);
-        acc[a][b] = fmaf(xa[a].z, yb[b].z, acc[a][b]);
-        acc[a][b] = fmaf(xa[a].w, yb[b].w, acc[a][b]);
-      }
-  }
-}
-
-__device__ __forceinline__ float group16_max(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float group16_sum(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+using namespace simt;
 
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(NT)

@@ -131,6 +131,22 @@ int emip_injector_bwd(const float* x, const float* x1, const float* const* param
                       const float* dout, float* dx, float* dx1, float* const* dparams, void* workspace, size_t ws_bytes,
                       int B, int H, int W, void* stream);
 
+/* ---- a5: EMIP_long memory read (historical-feature prompt) ------------------------------------ */
+/* Replaces model/EMIP_long/LTM.py:49-68 Memory.forward(m_in, m_out, q_in, q_out):
+ * p = softmax over the memory axis of m_in^T q_in / sqrt(De); mem = m_out p.  Exact fp32, flash-style (p, the
+ * reference's unused `viz` output, is never materialised).
+ *   m_in, m_out [B,128,M] (M = T*H*W memory slots, the reference's [B,128,T,H,W] viewed flat)   q_in [B,128,Q]
+ *   mem  element (b,o,q) at mem[b*mem_stride_b + o*Q + q]: pass the first half of the [B,256,H,W] output of the
+ *        reference's torch.cat([mem, q_out]) (LTM.py:66) with mem_stride_b = 256*Q, or a plain [B,128,Q] tensor
+ *   lse  [B,Q] log-sum-exp over the memory axis (NULL in inference; required by the backward)
+ * Backward: dmem uses the same addressing as mem; dm_in, dm_out [B,128,M] and dq_in [B,128,Q] are overwritten. */
+size_t emip_memory_read_workspace(int B, int De, int Do, int M, int Q);
+int emip_memory_read_fwd(const float* m_in, const float* m_out, const float* q_in, float* mem, long long mem_stride_b,
+                         float* lse, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
+int emip_memory_read_bwd(const float* m_in, const float* m_out, const float* q_in, const float* mem, long long mem_stride_b,
+                         const float* lse, const float* dmem, long long dmem_stride_b, float* dm_in, float* dm_out,
+                         float* dq_in, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -259,3 +259,29 @@ def test_a4_injector_vs_oracle_batch():
     out = m(dev(d["x"]), dev(d["x1"]))
     assert rel(out, ref) < 2e-5
     assert torch.equal(out, m(dev(d["x"]), dev(d["x1"])))
+
+
+# ----------------------------------------------------------------------------- a5
+@pytest.mark.parametrize("name", list(cases.A5_CASES))
+def test_a5_memory_read_golden(golden, name):
+    from emip_b200.memory import Memory
+    g = golden(name)
+    d = cases.a5_inputs(cases.A5_CASES[name])
+    t = {k: dev(d[k]).requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
+    out, p = Memory()(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
+    assert p is None
+    e = cases.check_packed(out, g["out"], TOL_EXACT, "out")
+    (out * dev(d["wout"])).sum().backward()
+    errs = {k: cases.check_packed(v.grad, g["d" + k], 2e-4, "d" + k) for k, v in t.items()}
+    print(f"{name}: out {e:.2e} grads {errs}")
+
+
+def test_a5_memory_read_t5_vs_oracle():
+    """The largest memory the model keeps (T = 5 frames, model_long.py:105-107), B = 1, inference path."""
+    from emip_b200.memory import Memory
+    s = dict(b=1, t=5, h=44, w=44, scale=1.5, seed=57)
+    d = cases.a5_inputs(s)
+    ref, _ = O.memory_read(d["m_in"], d["m_out"], d["q_in"], d["q_out"])
+    with torch.no_grad():
+        out, _ = Memory()(dev(d["m_in"]), dev(d["m_out"]), dev(d["q_in"]), dev(d["q_out"]))
+    assert rel(out, ref) < TOL_EXACT
