@@ -1,0 +1,69 @@
+"""Rebind the reference's hot-path symbols to the emip_b200 implementations (the reference-side "binding").
+
+The reference has no operator registry; its call sites import plain functions/classes.  ``install()`` patches
+exactly those names in an already importable reference tree, so ``train.py`` / ``test.py`` / ``train_long.py`` run
+unchanged (same signatures, same ``state_dict`` keys):
+
+    model.EMIP_short.motion.gmflow.matching.global_correlation_softmax     (called at gmflow.py:121)
+    model.EMIP_short.motion.gmflow.gmflow.global_correlation_softmax       (the name gmflow.py imported)
+    model.EMIP_short.motion.gmflow.transformer.FeatureFlowAttention        (constructed at gmflow.py:48)
+    model.EMIP_short.motion.PromptInteract.Injector                        (constructed at model.py:64-65, model_long.py:62)
+    model.EMIP_long.LTM.Memory                                             (constructed at LTM.py:90)
+    loss.warp_utils.flow_warp / loss.loss_flow.flow_warp                   (called at loss_flow.py:90-91)
+
+Call it after the reference root is on ``sys.path`` and before the model is constructed.  ``uninstall()`` restores
+the originals (used by the tests).
+"""
+import importlib
+import sys
+
+_PATCHES = (
+    # (module, attribute, our module, our attribute)
+    ("model.EMIP_short.motion.gmflow.matching", "global_correlation_softmax", "emip_b200.matching", "global_correlation_softmax"),
+    ("model.EMIP_short.motion.gmflow.gmflow", "global_correlation_softmax", "emip_b200.matching", "global_correlation_softmax"),
+    ("model.EMIP_short.motion.gmflow.transformer", "FeatureFlowAttention", "emip_b200.flow_attn", "FeatureFlowAttention"),
+    ("model.EMIP_short.motion.gmflow.gmflow", "FeatureFlowAttention", "emip_b200.flow_attn", "FeatureFlowAttention"),
+    ("model.EMIP_short.motion.PromptInteract", "Injector", "emip_b200.injector", "Injector"),
+    ("model.EMIP_short.model", "Injector", "emip_b200.injector", "Injector"),
+    ("model.EMIP_long.model_long", "Injector", "emip_b200.injector", "Injector"),
+    ("model.EMIP_long.LTM", "Memory", "emip_b200.memory", "Memory"),
+    ("loss.warp_utils", "flow_warp", "emip_b200.warp", "flow_warp"),
+    ("loss.loss_flow", "flow_warp", "emip_b200.warp", "flow_warp"),
+)
+_saved = {}
+
+
+def install(strict=False):
+    """Patch every reference module that is importable; returns the list of ``module.attr`` names rebound.
+
+    Modules that cannot be imported (e.g. ``model.EMIP_long`` without its optional dependencies) are skipped unless
+    ``strict``.  Modules that import a symbol by name are patched too, whether they were imported before or after
+    this call.
+    """
+    done = []
+    for mod_name, attr, our_mod, our_attr in _PATCHES:
+        try:
+            mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
+        except Exception:
+            if strict:
+                raise
+            continue
+        if not hasattr(mod, attr):
+            if strict:
+                raise AttributeError(f"{mod_name} has no attribute {attr}")
+            continue
+        ours = getattr(importlib.import_module(our_mod), our_attr)
+        key = (mod_name, attr)
+        if key not in _saved:
+            _saved[key] = getattr(mod, attr)
+        setattr(mod, attr, ours)
+        done.append(f"{mod_name}.{attr}")
+    return done
+
+
+def uninstall():
+    for (mod_name, attr), orig in list(_saved.items()):
+        mod = sys.modules.get(mod_name)
+        if mod is not None:
+            setattr(mod, attr, orig)
+        del _saved[(mod_name, attr)]

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """flow_warp (K3) micro-benchmark: achieved HBM GB/s, forward and backward-to-flow, three flow fields.
 
-    model_like : per-sample translation (sigma 10 px) + smooth x8-upsampled variation (sigma 2 px per 8-px cell),
-                 i.e. what a trained GMFlow emits after convex upsampling (piecewise smooth)
+    model_like : per-sample translation (sigma 10 px) + smooth x8-upsampled variation (sigma 0.5 px per 8-px cell,
+                 local flow gradient ~0.07 px/px = a few percent of zoom / rotation / deformation), i.e. what a
+                 trained GMFlow emits after convex upsampling (piecewise smooth)
+    warpy      : same with sigma 2 px per cell (gradient ~0.35 px/px: a 35 % local stretch; upper end of plausible)
     iid5px / iid20px : SURVEY.md 8(d) stress cases (independent per-pixel flow; gather-bound)
 """
 import ctypes, json, os, sys
@@ -19,10 +21,12 @@ B, C, H, W = 64, 3, 352, 352
 
 def flows(dev, g):
     base = 10.0 * torch.randn(B, 2, 1, 1, device=dev, generator=g)
-    sm = torch.cat([cases.smooth_flow(11, B, H, W, 2.0), cases.smooth_flow(12, B, H, W, 2.0)], 1).to(dev)
-    sm[:, :2] += base
-    sm[:, 2:] -= base
-    return {"model_like": sm, "iid5px": 5.0 * torch.randn(B, 4, H, W, device=dev, generator=g),
+    def smooth(mag):
+        sm = torch.cat([cases.smooth_flow(11, B, H, W, mag), cases.smooth_flow(12, B, H, W, mag)], 1).to(dev)
+        sm[:, :2] += base
+        sm[:, 2:] -= base
+        return sm
+    return {"model_like": smooth(0.5), "warpy": smooth(2.0), "iid5px": 5.0 * torch.randn(B, 4, H, W, device=dev, generator=g),
             "iid20px": 20.0 * torch.randn(B, 4, H, W, device=dev, generator=g)}
 
 
@@ -69,7 +73,7 @@ if __name__ == "__main__":
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         pk = json.load(open(p))["hbm_gbs"]
-    for variant in (0, 1):
+    for variant in (0,):
       _lib.lib().emip_debug_flow_warp_variant(variant)
       print("variant", variant, "(0 = 32x32 tiles, 1 = linear 1024-px segments)")
       r = run(torch.device("cuda", 0), pk)
