@@ -309,115 +309,130 @@ __device__ __forceinline__ T* opaque(T* p) {
   return p;
 }
 
-// LINEAR = false: CTA covers a 32 x 32 pixel tile (rows of a thread 8 apart; vertical tap reuse through L1).
-// LINEAR = true : CTA covers 1024 consecutive pixels of a plane (4 KB contiguous per stream; pixels of a thread
-//                 256 apart), which keeps every DRAM page access long.
-template <bool BWD, bool LINEAR>
+// Persistent CTAs loop over 32 x 32 pixel tiles (rows of a thread 8 apart, lanes on consecutive x).  The flow of the
+// NEXT tile is requested right after the gathers of the current tile have been issued, so the dependent chain
+// flow -> address -> gather of one tile overlaps the gather latency of the previous one (ncu r1h: the single-shot
+// version was latency-bound: long-scoreboard stalls 6.0 per issue, 21 resident warps per SM, DRAM 40 %).
+template <bool BWD>
 __global__ void __launch_bounds__(256)
 flow_warp_border3_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ dout,
                          float* __restrict__ out, int H, int W, long long fsb, long long fsc, int tiles_x, int tiles_y,
-                         float rcw, float rch) {
+                         int n_tiles, float rcw, float rch) {
   const unsigned plane = (unsigned)(H * W);
-  int t = blockIdx.x;
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  int tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+
   int b, px, py0;
-  int lpx[ROWS], lpy[ROWS];
-  bool lok[ROWS];
-  if (LINEAR) {
-    b = t / tiles_x;                                   // tiles_x = CTAs per sample
-    const int p0 = (t - b * tiles_x) * (256 * ROWS) + threadIdx.x;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const int p = min(p0 + 256 * r, (int)plane - 1);
-      lok[r] = p0 + 256 * r < (int)plane;
-      lpy[r] = p / W;
-      lpx[r] = p - lpy[r] * W;
-    }
-    px = 0; py0 = 0;
-  } else {
+  unsigned pix[ROWS];
+  float fx[ROWS], fy[ROWS];
+  auto load_flow = [&](int t) {
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     b = t / tiles_y;
-    px = tx * 32 + (threadIdx.x & 31);
-    py0 = ty * (8 * ROWS) + (threadIdx.x >> 5);
-    if (px >= W) return;
+    px = min(tx * 32 + lx, W - 1);                   // columns past the end re-read the last column (stores masked)
+    py0 = ty * (8 * ROWS) + ly;
+    const float* fb = opaque(flow + (long long)b * fsb);
+    const float* fb2 = opaque(fb + fsc);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      lok[r] = py0 + 8 * r < H;
-      lpy[r] = min(py0 + 8 * r, H - 1);               // rows past the end re-read the last row (stores masked)
-      lpx[r] = px;
+      pix[r] = (unsigned)(min(py0 + 8 * r, H - 1) * W + px);   // rows past the end re-read the last row
+      fx[r] = __ldcs(fb + pix[r]);
+      fy[r] = __ldcs(fb2 + pix[r]);
     }
-  }
-  const float* fb = opaque(flow + (long long)b * fsb);
-  const float* fb2 = opaque(fb + fsc);
-  const float* xb = opaque(x + (long long)b * 3 * plane);
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  unsigned pix[ROWS];
-  float fx[ROWS], fy[ROWS];
-  float g[ROWS][3];
+    return tx * 32 + lx < W;
+  };
+  bool col_ok = load_flow(tile);
+
+  while (true) {
+    const int cb = b, cpy0 = py0;
+    const bool c_ok = col_ok;
+    unsigned cpix[ROWS];
+    FastCoord c[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    pix[r] = (unsigned)(lpy[r] * W + lpx[r]);
-    fx[r] = __ldcs(fb + pix[r]);
-    fy[r] = __ldcs(fb2 + pix[r]);
+    for (int r = 0; r < ROWS; ++r) {
+      cpix[r] = pix[r];
+      c[r] = fast_coord((float)px + fx[r], (float)min(py0 + 8 * r, H - 1) + fy[r], H, W, wm1, hm1, rcw, rch);
+    }
+    // one opaque base pointer per channel plane: every tap pair is then a single IMAD.WIDE (offset * 4 + base)
+    const float* xc[3];
+    xc[0] = opaque(x + (long long)cb * 3 * plane);
+    xc[1] = opaque(xc[0] + plane);
+    xc[2] = opaque(xc[1] + plane);
+    float v[ROWS][3][4];
+    float g[ROWS][3];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const unsigned o0 = c[r].off, o1 = c[r].off + (unsigned)W;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {                // all 48 gathers in flight before any use
+        const float* p0 = xc[ch] + o0;
+        const float* p1 = xc[ch] + o1;
+        v[r][ch][0] = __ldg(p0); v[r][ch][1] = __ldg(p0 + 1);
+        v[r][ch][2] = __ldg(p1); v[r][ch][3] = __ldg(p1 + 1);
+      }
+    }
     if (BWD) {
-      const float* gb = opaque(dout + (long long)b * 3 * plane);
+      const float* gc[3];
+      gc[0] = opaque(dout + (long long)cb * 3 * plane);
+      gc[1] = opaque(gc[0] + plane);
+      gc[2] = opaque(gc[1] + plane);
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) g[r][ch] = __ldcs(gb + (ch * plane + pix[r]));
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) g[r][ch] = __ldcs(gc[ch] + cpix[r]);
     }
-  }
-  FastCoord c[ROWS];
+    const int next = tile + gridDim.x;
+    const bool has_next = next < n_tiles;
+    if (has_next) col_ok = load_flow(next);            // in flight while this tile is finished below
+
+    if (!BWD) {
+      float* oc[3];
+      oc[0] = opaque(out + (long long)cb * 3 * plane);
+      oc[1] = opaque(oc[0] + plane);
+      oc[2] = opaque(oc[1] + plane);
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r)
-    c[r] = fast_coord((float)lpx[r] + fx[r], (float)lpy[r] + fy[r], H, W, wm1, hm1, rcw, rch);
-  float v[ROWS][3][4];
+      for (int r = 0; r < ROWS; ++r) {
+        if (c_ok && cpy0 + 8 * r < H) {
+          const float wx = c[r].wx, wy = c[r].wy;
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r)
+          for (int ch = 0; ch < 3; ++ch) {
+            const float top = fmaf(wx, v[r][ch][1] - v[r][ch][0], v[r][ch][0]);
+            const float bot = fmaf(wx, v[r][ch][3] - v[r][ch][2], v[r][ch][2]);
+            __stcs(oc[ch] + cpix[r], fmaf(wy, bot - top, top));
+          }
+        }
+      }
+    } else {
+      float* db = opaque(out + (long long)cb * 2 * plane);   // out = dflow [B,2,H,W]
+      float* db2 = opaque(db + plane);
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {                  // all 48 gathers in flight before any use
-      const float* p0 = xb + (c[r].off + ch * plane);
-      const float* p1 = xb + (c[r].off + ch * plane + (unsigned)W);
-      v[r][ch][0] = __ldg(p0); v[r][ch][1] = __ldg(p0 + 1);
-      v[r][ch][2] = __ldg(p1); v[r][ch][3] = __ldg(p1 + 1);
-    }
-  if (!BWD) {
-    float* ob = opaque(out + (long long)b * 3 * plane);
+      for (int r = 0; r < ROWS; ++r) {
+        if (c_ok && cpy0 + 8 * r < H) {
+          const float wx = c[r].wx, wy = c[r].wy, ex = 1.0f - wx, ey = 1.0f - wy;
+          float gx = 0.f, gy = 0.f;
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      if (lok[r]) {
-        const float wx = c[r].wx, wy = c[r].wy;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float top = fmaf(wx, v[r][ch][1] - v[r][ch][0], v[r][ch][0]);
-          const float bot = fmaf(wx, v[r][ch][3] - v[r][ch][2], v[r][ch][2]);
-          __stcs(ob + (ch * plane + pix[r]), fmaf(wy, bot - top, top));
+          for (int ch = 0; ch < 3; ++ch) {
+            gx = fmaf(g[r][ch], (v[r][ch][1] - v[r][ch][0]) * ey + (v[r][ch][3] - v[r][ch][2]) * wy, gx);
+            gy = fmaf(g[r][ch], (v[r][ch][2] - v[r][ch][0]) * ex + (v[r][ch][3] - v[r][ch][1]) * wx, gy);
+          }
+          // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
+          __stcs(db + cpix[r], div_rn(gx * (wm1 * 0.5f) * c[r].gmx, wm1, rcw) * 2.0f);
+          __stcs(db2 + cpix[r], div_rn(gy * (hm1 * 0.5f) * c[r].gmy, hm1, rch) * 2.0f);
         }
       }
     }
-  } else {
-    float* db = opaque(out + (long long)b * 2 * plane);   // out = dflow [B,2,H,W]
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      if (lok[r]) {
-        const float wx = c[r].wx, wy = c[r].wy, ex = 1.0f - wx, ey = 1.0f - wy;
-        float gx = 0.f, gy = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          gx = fmaf(g[r][ch], (v[r][ch][1] - v[r][ch][0]) * ey + (v[r][ch][3] - v[r][ch][2]) * wy, gx);
-          gy = fmaf(g[r][ch], (v[r][ch][2] - v[r][ch][0]) * ex + (v[r][ch][3] - v[r][ch][1]) * wx, gy);
-        }
-        // ATen: grad_grid = gix * (W-1)/2 * clipmask ; norm_grid backward: / (W-1) * 2
-        __stcs(db + pix[r], div_rn(gx * (wm1 * 0.5f) * c[r].gmx, wm1, rcw) * 2.0f);
-        __stcs(db + (plane + pix[r]), div_rn(gy * (hm1 * 0.5f) * c[r].gmy, hm1, rch) * 2.0f);
-      }
-    }
+    if (!has_next) break;
+    tile = next;
   }
 }
 
-int g_k3_linear = 0;
+int g_k3_ctas_per_sm = 2;
 }  // namespace
 
-// Experiment switch (tools/k3_bench.py): 0 = 32x32 tiles, 1 = 1024-pixel linear segments.
-extern "C" void emip_debug_flow_warp_variant(int v) { g_k3_linear = v; }
+// Experiment switch (tools/k3_bench.py): persistent CTAs per SM of the border/C=3 fast path.
+extern "C" void emip_debug_flow_warp_variant(int v) { g_k3_ctas_per_sm = v > 0 ? v : 2; }
 
 extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                                   long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream) {
@@ -434,14 +449,9 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
   const bool border = pad_mode == EMIP_PAD_BORDER;
   if (C == 3 && border && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
-    if (g_k3_linear) {
-      const int per = (H * W + 256 * ROWS - 1) / (256 * ROWS);
-      flow_warp_border3_kernel<false, true><<<(unsigned)(B * per), 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b,
-                                                                                  flow_stride_c, per, 1, rcw, rch);
-    } else {
-      flow_warp_border3_kernel<false, false><<<(unsigned)nblk, 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b,
-                                                                              flow_stride_c, tiles_x, tiles_y, rcw, rch);
-    }
+    const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    flow_warp_border3_kernel<false><<<grid, 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b, flow_stride_c,
+                                                         tiles_x, tiles_y, (int)nblk, rcw, rch);
   } else if (C == 3) { if (border) LAUNCH(true, 3); else LAUNCH(false, 3); }
   else if (C == 2) { if (border) LAUNCH(true, 2); else LAUNCH(false, 2); }
   else { if (border) LAUNCH(true, 0); else LAUNCH(false, 0); }
@@ -467,14 +477,9 @@ extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float
   const bool border = pad_mode == EMIP_PAD_BORDER;
   if (C == 3 && border && dx == nullptr && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
-    if (g_k3_linear) {
-      const int per = (H * W + 256 * ROWS - 1) / (256 * ROWS);
-      flow_warp_border3_kernel<true, true><<<(unsigned)(B * per), 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b,
-                                                                                 flow_stride_c, per, 1, rcw, rch);
-    } else {
-      flow_warp_border3_kernel<true, false><<<(unsigned)nblk, 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b,
-                                                                             flow_stride_c, tiles_x, tiles_y, rcw, rch);
-    }
+    const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    flow_warp_border3_kernel<true><<<grid, 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b, flow_stride_c, tiles_x,
+                                                        tiles_y, (int)nblk, rcw, rch);
   } else if (C == 3) {
     if (border) { if (dx) LAUNCH(true, true, 3); else LAUNCH(true, false, 3); }
     else { if (dx) LAUNCH(false, true, 3); else LAUNCH(false, false, 3); }

@@ -11,15 +11,18 @@
 // flow rel-L2 ~1e-5 versus fp32 SGEMM.  terms=1 keeps only hi.hi (bf16 inference
 // mode, 2e-2 tolerance).  Softmax statistics are always fp32.
 //
-// CTA = 320 threads, persistent, one CTA per SM (225 KB smem, all 512 TMEM columns).
+// CTA = 576 threads, persistent, one CTA per SM (225 KB smem, all 512 TMEM columns).
 // A work item is (problem, PAIR of 128-row query tiles): every key chunk that TMA
 // brings in is used by both query tiles, which halves the L2->SM operand traffic
 // per MMA (1 MB per 256 rows; the first version of this kernel, one tile per CTA, asked
 // L2 for 11 TB/s at the MMA-bound rate).
-//   warps 0..3  softmax group 0  (query tile 0: thread <-> TMEM lane <-> one row; no shuffles)
-//   warps 4..7  softmax group 1  (query tile 1)
-//   warp 8      TMA producer   (2 x 64 KB query tiles per item; key chunks through a 4-stage ring)
-//   warp 9      UMMA issuer    (one elected lane; owns the TMEM allocation)
+//   warps 0..7   softmax, query tile 0: warp w <-> TMEM lane quarter w%4, column half (w/4)%2 of every key tile
+//   warps 8..15  softmax, query tile 1      (thread <-> TMEM lane <-> one row; no shuffles; the two column halves
+//                of a row keep independent online-softmax states that are merged once per work item)
+//   warp 16      TMA producer   (2 x 64 KB query tiles per item; key chunks through a 4-stage ring)
+//   warp 17      UMMA issuer    (one elected lane; owns the TMEM allocation)
+// 16 softmax warps = 4 per SM sub-partition: with 8 (one query tile per warp group, r1d) each warp ran at IPC 0.3
+// and a tile took 3500 cycles against 3072 of UMMA time per key step.
 // The two control warps have the HIGHEST warp ids on purpose: the SM sub-partition arbiter favours
 // high warp ids, and an issuer that shares its sub-partition with two busy softmax warps at low
 // priority could only issue one UMMA per ~128 cycles (ncu r1c: tensor pipe 42 % active, softmax
@@ -39,21 +42,29 @@ constexpr int TN = 128;                 // key columns per tile (UMMA N)
 constexpr int CH_ELEMS = 64;            // bf16 per 128-byte swizzle row
 constexpr int CHUNK_BYTES = TM * 128;   // one [128 rows x 128 B] SW128 box = 16 KB
 constexpr int NCHUNK = 4;               // hi[0:64] hi[64:128] lo[0:64] lo[64:128]
-constexpr int STAGES = 4;
 constexpr int MAXK = 2048;              // value table capacity (columns)
-constexpr int NTHREADS = 320;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STG_BYTES = 2048;         // per softmax warp: [32 rows][16 fp32], 64-byte swizzle
+constexpr int R_BYTES = 32768;          // region R, see below
 
+// Shared-memory layout.  (A TS-mode variant with the query tiles in TMEM was tried in r1m: tcgen05.cp.128x256b and
+// the TS-mode UMMA behave as expected -- tools/probe/ -- but the four 128-column accumulators already fill the 512
+// TMEM columns, so it would cost the accumulator double-buffering.)
+// Region R (32 KB) is the score-emission stage (16 x 2 KB) in matching mode, and the value table (16 KB) plus the
+// end-of-item merge slots in attention mode -- the two uses never coexist (attention emits no scores, matching
+// generates the pixel grid analytically and needs no table).
+constexpr int STAGES = 4;
 constexpr int OFF_Q = 0;                                        // [2 tiles][4 chunks][16 KB]
 constexpr int OFF_K = OFF_Q + 2 * NCHUNK * CHUNK_BYTES;         // ring
-constexpr int OFF_STG = OFF_K + STAGES * CHUNK_BYTES;
-constexpr int OFF_V = OFF_STG + 8 * STG_BYTES;
-constexpr int OFF_BAR = OFF_V + 2 * MAXK * 4;
+constexpr int OFF_R = OFF_K + STAGES * CHUNK_BYTES;
+constexpr int OFF_STG = OFF_R;
+constexpr int OFF_V = OFF_R;
+constexpr int OFF_MERGE = OFF_R + 2 * MAXK * 4;                 // attention mode: 16 x 512 B
+constexpr int OFF_BAR = OFF_R + R_BYTES;
 constexpr int NBAR = 3 + 2 * STAGES + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;                // + slack to align the base to 1024 B
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+static_assert(2 * MAXK * 4 + 16 * 512 <= R_BYTES, "region R too small");
 
 // ---- PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -233,35 +244,135 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], int nv, u
   m = m_new;
 }
 
-// Emit 32 score columns of 32 rows (one warp) as two [32 rows x 16 cols] TMA bulk stores.
+// Same update for the analytic pixel grid (geometry.py:5-21) when grid_w >= 32 and grid_w % 4 == 0: the 32 columns
+// start at grid position (x0, y0) and wrap to the next grid row at most once, at a multiple of four (brk4 * 4):
+//   x_i = x0 + i - W [i >= brk],  y_i = y0 + [i >= brk]
+//   sum e_i x_i = x0 L + sum i e_i - W H,   sum e_i y_i = y0 L + H,   L = sum e_i,  H = sum_{i >= brk} e_i
+// so the inner loop is one FFMA (scale), one MUFU, one FADD (groups of four -> H comes from 8 partial sums) and one
+// FFMA with an immediate -- no value table, no LDS.
+template <bool FULL>
+__device__ __forceinline__ void softmax_chunk_grid(const uint32_t (&r)[32], int nv, float x0, float y0, int brk4, float gw,
+                                                   float c2, float& m, float& l, float& sx, float& sy) {
+  float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float s = __uint_as_float(r[i]);
+    cm[i & 3] = (FULL || i < nv) ? fmaxf(cm[i & 3], s) : cm[i & 3];
+  }
+  const float m_new = fmaxf(fmaxf(m, fmaxf(cm[0], cm[1])), fmaxf(cm[2], cm[3]));
+  const float corr = ex2f((m - m_new) * c2);
+  const float mb = m_new * c2;
+  float g8[8], si[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = t * 4 + k;
+      float e = ex2f(fmaf(__uint_as_float(r[i]), c2, -mb));
+      if (!FULL) e = (i < nv) ? e : 0.f;
+      acc += e;
+      si[k] = fmaf(e, (float)i, si[k]);
+    }
+    g8[t] = acc;
+  }
+  float ls = 0.f, hs = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    ls += g8[t];
+    hs += (t >= brk4) ? g8[t] : 0.f;
+  }
+  const float sidx = (si[0] + si[1]) + (si[2] + si[3]);
+  l = fmaf(l, corr, ls);
+  sx = fmaf(sx, corr, fmaf(x0, ls, sidx) - gw * hs);
+  sy = fmaf(sy, corr, fmaf(y0, ls, hs));
+  m = m_new;
+}
+// Any grid width (small test grids): positions computed per element.
+template <bool FULL>
+__device__ __forceinline__ void softmax_chunk_grid_slow(const uint32_t (&r)[32], int nv, int col0, int gw, float c2, float& m,
+                                                        float& l, float& sx, float& sy) {
+  float cmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) cmax = (FULL || i < nv) ? fmaxf(cmax, __uint_as_float(r[i])) : cmax;
+  const float m_new = fmaxf(m, cmax);
+  const float corr = ex2f((m - m_new) * c2);
+  const float mb = m_new * c2;
+  float ls = 0.f, lx = 0.f, ly = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float e = ex2f(fmaf(__uint_as_float(r[i]), c2, -mb));
+    if (!FULL) e = (i < nv) ? e : 0.f;
+    const int c = col0 + i;
+    ls += e;
+    lx = fmaf(e, (float)(c % gw), lx);
+    ly = fmaf(e, (float)(c / gw), ly);
+  }
+  l = fmaf(l, corr, ls);
+  sx = fmaf(sx, corr, lx);
+  sy = fmaf(sy, corr, ly);
+  m = m_new;
+}
+
+// Emit 32 score columns of 32 rows (one warp) through the warp's smem stage and TMA bulk stores.
+// WIDE = false: 2 KB stage, two [32 rows x 16 cols] boxes (64-byte swizzle); WIDE = true: 4 KB stage, one
+// [32 rows x 32 cols] box (128-byte swizzle).  The swizzle is applied by hand so that the st.shared.v4 of the 32 rows
+// are bank-conflict free.
+template <bool WIDE>
 __device__ __forceinline__ void emit_chunk_tma(const uint32_t (&r)[32], float scale, uint32_t stg_u32,
                                                const CUtensorMap* map, int col, int row0, int slab, int lane, int nk) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  if constexpr (WIDE) {
     if (lane == 0) bulk_wait_read0();                 // the previous store has finished reading the stage
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       float4 v;
-      v.x = __uint_as_float(r[h * 16 + q * 4 + 0]) * scale;
-      v.y = __uint_as_float(r[h * 16 + q * 4 + 1]) * scale;
-      v.z = __uint_as_float(r[h * 16 + q * 4 + 2]) * scale;
-      v.w = __uint_as_float(r[h * 16 + q * 4 + 3]) * scale;
-      // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8] = (row >> 1) & 3
-      sts128(stg_u32 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), v);
+      v.x = __uint_as_float(r[q * 4 + 0]) * scale;
+      v.y = __uint_as_float(r[q * 4 + 1]) * scale;
+      v.z = __uint_as_float(r[q * 4 + 2]) * scale;
+      v.w = __uint_as_float(r[q * 4 + 3]) * scale;
+      // CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk index ^= address bits [7,9] = row & 7
+      sts128(stg_u32 + lane * 128 + ((q ^ (lane & 7)) << 4), v);
     }
     fence_async_smem();
     __syncwarp();
-    if (lane == 0 && col + h * 16 < nk) {             // columns past nk inside the box are clipped by TMA
-      tma_store_3d(map, stg_u32, col + h * 16, row0, slab);
+    if (lane == 0 && col < nk) {                      // columns past nk inside the box are clipped by TMA
+      tma_store_3d(map, stg_u32, col, row0, slab);
       bulk_commit();
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v;
+        v.x = __uint_as_float(r[h * 16 + q * 4 + 0]) * scale;
+        v.y = __uint_as_float(r[h * 16 + q * 4 + 1]) * scale;
+        v.z = __uint_as_float(r[h * 16 + q * 4 + 2]) * scale;
+        v.w = __uint_as_float(r[h * 16 + q * 4 + 3]) * scale;
+        // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8] = (row >> 1) & 3
+        sts128(stg_u32 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), v);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && col + h * 16 < nk) {
+        tma_store_3d(map, stg_u32, col + h * 16, row0, slab);
+        bulk_commit();
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int NSMX>
+__global__ void __launch_bounds__((NSMX + 2) * 32, 1)
 match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                     const __grid_constant__ CUtensorMap map_s, KParams p) {
+  constexpr int HALVES = NSMX / 8;                    // column halves of a key tile handled by different warps
+  constexpr int STG_BYTES = R_BYTES / NSMX;           // emission stage per softmax warp
+  constexpr int SMX_THREADS = NSMX * 32;
+  constexpr int COLS_MINE = TN / HALVES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -287,10 +398,10 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     mbar_init(q_empty, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     for (int g = 0; g < 2; ++g)
-      for (int b = 0; b < 2; ++b) { mbar_init(s_full(g, b), 1); mbar_init(s_empty(g, b), 128); }
+      for (int b = 0; b < 2; ++b) { mbar_init(s_full(g, b), 1); mbar_init(s_empty(g, b), 128 * HALVES); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == NSMX + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -301,7 +412,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == NSMX) {
     // ===================== TMA producer =====================
     {
       const bool leader = elect_one();
@@ -336,7 +447,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       if (p.prof && leader) { p.prof[blockIdx.x * 8 + 0] = w_qe; p.prof[blockIdx.x * 8 + 1] = w_ke; }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == NSMX + 1) {
     // ===================== UMMA issuer =====================
     {
       const bool leader = elect_one();
@@ -349,6 +460,12 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint32_t idesc_full = make_idesc(TN), idesc_tail = make_idesc(n_tail);
       // descriptor start-address units are 16 B: chunk = 1024 units, K16 step inside a swizzle row = 2 units
       const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
+      // Notes from the role profile (tools/k1_roles.py): (1) tcgen05.mma issue back-pressures, the issuer is busy for
+      // the whole UMMA time; (2) hoisting the mbarrier waits of the next chunk in front of the last UMMAs of the
+      // current one made the kernel SLOWER (r1n: 97 -> 112 us): a try_wait on a barrier that is not complete yet
+      // suspends the warp with a coarse wake-up and the tensor pipe drains meanwhile -- waits stay between chunks;
+      // (3) the UMMAs of the two query tiles are interleaved one by one so that consecutive instructions
+      // accumulate into different TMEM tiles.
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         for (int kt = 0; kt < nkt; ++kt, ++tile) {
           const int buf = tile & 1;
@@ -356,36 +473,47 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const uint32_t idesc = (kt == nkt - 1) ? idesc_tail : idesc_full;
           for (int c = 0; c < nch; ++c) {
             w_kf += mbar_wait(k_full(stage), kphase);
-            tc_fence_after();
-            const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_K + stage * CHUNK_BYTES);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (c == 0) {
-                // this group's accumulator must have been drained by its softmax warps (two tiles ago)
-                w_se += mbar_wait(s_empty(g, buf), (use & 1) ^ 1);
-                if (kt == 0) w_qf += mbar_wait(q_full(g), it & 1);
-                tc_fence_after();
-              }
-              const uint32_t d_tmem = tmem_base + (uint32_t)((g * 2 + buf) * TN);
-              // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
-              const uint64_t a_hi = qd + (uint64_t)((g * NCHUNK + (c & 1)) * (CHUNK_BYTES >> 4));
-              const uint64_t a_lo = qd + (uint64_t)((g * NCHUNK + 2 + (c & 1)) * (CHUNK_BYTES >> 4));
-              if (leader) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, kd + 2 * k, idesc, (c | k) ? 1u : 0u);
-                if (c < 2 && nch == NCHUNK) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, kd + 2 * k, idesc, 1u);
-                }
-                if (c == nch - 1) umma_commit(s_full(g, buf));   // this group's S tile is complete
+            if (c == 0) {
+              // the accumulators of this key step must have been drained by the softmax warps (two steps ago)
+              w_se += mbar_wait(s_empty(0, buf), (use & 1) ^ 1);
+              w_se += mbar_wait(s_empty(1, buf), (use & 1) ^ 1);
+              if (kt == 0) {
+                w_qf += mbar_wait(q_full(0), it & 1);
+                w_qf += mbar_wait(q_full(1), it & 1);
               }
             }
-            if (leader) umma_commit(k_empty(stage));   // frees the smem stage when these MMAs retire
+            tc_fence_after();
+            if (leader) {
+              const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_K + stage * CHUNK_BYTES);
+              const uint32_t d0 = tmem_base + (uint32_t)(buf * TN), d1 = d0 + 2 * TN;
+              // chunk 0/1 = Y.hi halves: pair with X.hi and X.lo ; chunk 2/3 = Y.lo halves: pair with X.hi
+              const uint64_t a_hi0 = qd + (uint64_t)((c & 1) * (CHUNK_BYTES >> 4));
+              const uint64_t a_hi1 = a_hi0 + (uint64_t)(NCHUNK * (CHUNK_BYTES >> 4));
+              const uint32_t acc0 = c ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d0, a_hi0 + 2 * k, kd + 2 * k, idesc, (k ? 1u : acc0));
+                umma_bf16(d1, a_hi1 + 2 * k, kd + 2 * k, idesc, (k ? 1u : acc0));
+              }
+              if (c < 2 && nch == NCHUNK) {
+                const uint64_t a_lo0 = a_hi0 + (uint64_t)(2 * (CHUNK_BYTES >> 4)), a_lo1 = a_hi1 + (uint64_t)(2 * (CHUNK_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d0, a_lo0 + 2 * k, kd + 2 * k, idesc, 1u);
+                  umma_bf16(d1, a_lo1 + 2 * k, kd + 2 * k, idesc, 1u);
+                }
+              }
+              umma_commit(k_empty(stage));       // frees the smem stage when these MMAs retire
+              if (c == nch - 1) {                // both S tiles complete -> softmax groups
+                umma_commit(s_full(0, buf));
+                umma_commit(s_full(1, buf));
+              }
+            }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; kphase ^= 1; }
           }
         }
-        if (leader) umma_commit(q_empty);      // query tiles no longer read -> producer may overwrite
+        if (leader) umma_commit(q_empty);        // query tiles no longer read -> producer may overwrite
         __syncwarp();
       }
       if (p.prof && leader) {
@@ -396,15 +524,23 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     __syncwarp();
   } else {
     // ===================== softmax warps =====================
-    const int g = warp >> 2;                             // softmax group = query tile of the pair
+    const int g = warp / (4 * HALVES);                   // query tile of the pair
+    const int half = (warp >> 2) & (HALVES - 1);         // column half of every key tile (HALVES == 2)
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int r_in_tile = quarter * 32 + lane;
-    const int st = threadIdx.x;                          // 0..255 within the softmax warps
+    const int st = threadIdx.x;                          // index within the softmax warps
+    const bool grid_mode = p.grid_w > 0;
+    const bool grid_fast = p.grid_w >= 32 && (p.grid_w & 3) == 0;
+    const float gwf = (float)p.grid_w;
     float* vtab = reinterpret_cast<float*>(smem + OFF_V);
     const uint32_t stg = sbase + OFF_STG + warp * STG_BYTES;
     const uint32_t vtab_u32 = sbase + OFF_V;
+    // end-of-item merge slot (16 B per row): the warp's own emission stage in matching mode, a dedicated slot otherwise
+    const uint32_t my_slot = grid_mode ? stg : sbase + OFF_MERGE + warp * 512;
+    const uint32_t partner_slot = grid_mode ? stg + 4 * STG_BYTES : sbase + OFF_MERGE + (warp + 4) * 512;
     const float c2 = 1.4426950408889634f * p.inv_sqrt_c;   // log2(e)/sqrt(C)
     const int nk_pad = (p.nk + 31) & ~31;
+    const int cbeg = half * COLS_MINE;
     uint32_t tile = 0;
     int cur_v = -1;
     long long w_sf = 0;
@@ -412,28 +548,25 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int prob = item / npair, qt = 2 * (item % npair) + g;
       const int row = qt * TM + r_in_tile;
-      const int v_id = (p.grid_w > 0 || p.v_stride_b == 0) ? 0 : prob;
-      if (v_id != cur_v) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone finished with the old table
-        if (p.grid_w > 0) {
-          for (int c = st; c < nk_pad; c += 256) {        // geometry.py:5-21: channel 0 = x, channel 1 = y
-            vtab[c] = (c < p.nk) ? (float)(c % p.grid_w) : 0.f;
-            vtab[MAXK + c] = (c < p.nk) ? (float)(c / p.grid_w) : 0.f;
-          }
-        } else {
+      if (!grid_mode) {
+        const int v_id = (p.v_stride_b == 0) ? 0 : prob;
+        if (v_id != cur_v) {
+          asm volatile("bar.sync 1, %0;" ::"n"(SMX_THREADS) : "memory");   // everyone finished with the old table
           const float* vg = p.v + (size_t)prob * p.v_stride_b;
           // masked tail columns are multiplied by p = 0: keep them finite
-          for (int c = st; c < nk_pad; c += 256) {
+          for (int c = st; c < nk_pad; c += SMX_THREADS) {
             vtab[c] = (c < p.nk) ? __ldg(vg + c) : 0.f;
             vtab[MAXK + c] = (c < p.nk) ? __ldg(vg + p.nk + c) : 0.f;
           }
+          asm volatile("bar.sync 1, %0;" ::"n"(SMX_THREADS) : "memory");
+          cur_v = v_id;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_v = v_id;
       }
       const int row0w = qt * TM + quarter * 32;          // first row of this warp's 32-row slab
       const bool emit = p.s_mode != 0 && prob >= p.s_first && prob < p.s_first + p.s_count && row0w < p.nq;
       const int slab = prob - p.s_first;
+      // grid position of this warp's first column of the current key tile (matching mode)
+      int gx = grid_mode ? cbeg % p.grid_w : 0, gy = grid_mode ? cbeg / p.grid_w : 0;
       float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;
       for (int kt = 0; kt < nkt; ++kt, ++tile) {
         const int buf = tile & 1;
@@ -442,58 +575,110 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         const int col_base = kt * TN;
         const int n_valid = min(TN, p.nk - col_base);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((g * 2 + buf) * TN);
-        auto work = [&](const uint32_t (&r)[32], int c0, int nv, bool full) {
+        const int n_mine = max(0, min(COLS_MINE, n_valid - cbeg));
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((g * 2 + buf) * TN + cbeg);
+        auto work = [&](const uint32_t (&r)[32], int c0, int nv, bool full) {      // c0 = column offset within my part
+          const int col0 = col_base + cbeg + c0;
           if (emit) {
             if (p.s_mode == 1) {
-              emit_chunk_tma(r, p.inv_sqrt_c, stg, &map_s, col_base + c0, row0w, slab, lane, p.nk);
+              emit_chunk_tma<HALVES == 1>(r, p.inv_sqrt_c, stg, &map_s, col0, row0w, slab, lane, p.nk);
             } else if (row < p.nq) {
-              float* sg = p.s_out + ((size_t)slab * p.nq + row) * p.nk + col_base + c0;
+              float* sg = p.s_out + ((size_t)slab * p.nq + row) * p.nk + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (i < nv) sg[i] = __uint_as_float(r[i]) * p.inv_sqrt_c;
             }
           }
-          const uint32_t vx = vtab_u32 + 4 * (col_base + c0);
-          if (full) softmax_chunk<true>(r, 32, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
-          else softmax_chunk<false>(r, nv, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
+          if (grid_fast) {
+            int x0 = gx + c0, y0 = gy;
+            while (x0 >= p.grid_w) { x0 -= p.grid_w; ++y0; }
+            const int rem = p.grid_w - x0;                 // columns left in this grid row
+            const int brk4 = rem < 32 ? (rem >> 2) : 8;
+            if (full) softmax_chunk_grid<true>(r, 32, (float)x0, (float)y0, brk4, gwf, c2, m, l, sx, sy);
+            else softmax_chunk_grid<false>(r, nv, (float)x0, (float)y0, brk4, gwf, c2, m, l, sx, sy);
+          } else if (grid_mode) {
+            if (full) softmax_chunk_grid_slow<true>(r, 32, col0, p.grid_w, c2, m, l, sx, sy);
+            else softmax_chunk_grid_slow<false>(r, nv, col0, p.grid_w, c2, m, l, sx, sy);
+          } else {
+            const uint32_t vx = vtab_u32 + 4 * col0;
+            if (full) softmax_chunk<true>(r, 32, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
+            else softmax_chunk<false>(r, nv, vx, vx + 4 * MAXK, c2, m, l, sx, sy);
+          }
         };
-        if (n_valid == TN) {
-          // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
-          uint32_t ra[32], rb[32];
-          tmem_ld32_async(taddr, ra);
-          tmem_wait(ra);
-          tmem_ld32_async(taddr + 32, rb);
-          work(ra, 0, 32, true);
-          tmem_wait(rb);
-          tmem_ld32_async(taddr + 64, ra);
-          work(rb, 32, 32, true);
-          tmem_wait(ra);
-          tmem_ld32_async(taddr + 96, rb);
-          work(ra, 64, 32, true);
-          tmem_wait(rb);
-          tc_fence_before();
-          mbar_arrive(s_empty(g, buf));                  // accumulator drained: the next MMAs may overwrite it
-          work(rb, 96, 32, true);
+        if (n_mine == COLS_MINE) {
+          if constexpr (HALVES == 1) {
+            // 8 softmax warps: software pipeline, the TMEM load of chunk c+1 is in flight while chunk c is processed
+            uint32_t ra[32], rb[32];
+            tmem_ld32_async(taddr, ra);
+            tmem_wait(ra);
+            tmem_ld32_async(taddr + 32, rb);
+            work(ra, 0, 32, true);
+            tmem_wait(rb);
+            tmem_ld32_async(taddr + 64, ra);
+            work(rb, 32, 32, true);
+            tmem_wait(ra);
+            tmem_ld32_async(taddr + 96, rb);
+            work(ra, 64, 32, true);
+            tmem_wait(rb);
+            tc_fence_before();
+            mbar_arrive(s_empty(g, buf));                // accumulator drained: the next MMAs may overwrite it
+            work(rb, 96, 32, true);
+          } else {
+            // 16 softmax warps leave 96 registers per thread: one buffer, the other warps hide the TMEM latency
+            uint32_t ra[32];
+            tmem_ld32_async(taddr, ra);
+            tmem_wait(ra);
+            work(ra, 0, 32, true);
+            tmem_ld32_async(taddr + 32, ra);
+            tmem_wait(ra);
+            tc_fence_before();
+            mbar_arrive(s_empty(g, buf));
+            work(ra, 32, 32, true);
+          }
         } else {
-          for (int c0 = 0; c0 < n_valid; c0 += 32) {
+          for (int c0 = 0; c0 < n_mine; c0 += 32) {
             uint32_t ra[32];
             tmem_ld32_async(taddr + c0, ra);
             tmem_wait(ra);
-            const int nv = min(32, n_valid - c0);
+            const int nv = min(32, n_mine - c0);
             work(ra, c0, nv, nv == 32);
           }
           tc_fence_before();
           mbar_arrive(s_empty(g, buf));
         }
+        if (grid_fast) {                                 // next key tile: + TN columns
+          gx += TN;
+          while (gx >= p.grid_w) { gx -= p.grid_w; ++gy; }
+        }
       }
-      if (row < p.nq) {
+      if constexpr (HALVES == 2) {
+        // merge the two column halves of every row: half 1 hands (m, l, sx, sy) to half 0 through shared memory
+        if (half == 1) {
+          if (p.s_mode == 1) {
+            if (lane == 0) bulk_wait_read0();            // my emission stage is free again
+            __syncwarp();
+          }
+          sts128(my_slot + lane * 16, make_float4(m, l, sx, sy));
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+        if (half == 0) {
+          const float4 o = lds128(partner_slot + lane * 16);
+          const float mm = fmaxf(m, o.x);
+          const float a = ex2f((m - mm) * c2), b = ex2f((o.x - mm) * c2);   // an empty half has m = -inf, l = 0
+          l = l * a + o.y * b;
+          sx = sx * a + o.z * b;
+          sy = sy * a + o.w * b;
+          m = mm;
+        }
+      }
+      if (half == 0 && row < p.nq) {
         float ex = sx / l, ey = sy / l;
         if (p.sub_grid) { ex -= (float)(row % p.grid_w); ey -= (float)(row / p.grid_w); }
         p.out[((size_t)prob * 2 + 0) * p.nq + row] = ex;
         p.out[((size_t)prob * 2 + 1) * p.nq + row] = ey;
         if (p.lse != nullptr) p.lse[(size_t)prob * p.nq + row] = m * p.inv_sqrt_c + logf(l);
       }
+      if constexpr (HALVES == 2) asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");   // merge slot reusable
     }
     if (p.prof && threadIdx.x == 0) { p.prof[blockIdx.x * 8 + 6] = w_sf; p.prof[blockIdx.x * 8 + 7] = clock64() - t_begin; }
     if (lane == 0) bulk_wait0();                         // all score stores of this warp have landed
@@ -501,7 +686,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == NSMX + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -515,26 +700,32 @@ __device__ __forceinline__ void split2(float a, float b, __nv_bfloat162& hi, __n
 }
 
 // src [nb][128][n] (channel-major; batches >= nb come from src2) -> dst [..][n][256]
-__global__ void __launch_bounds__(256)
+// One thread = one token x 32 channels: 32 coalesced 4-byte loads (lanes = consecutive tokens), then the token's
+// 64-byte hi and lo segments as 4 + 4 128-bit stores (full 32-byte sectors).  No shared memory, no barrier:
+// 62 MB of traffic at c2 in ~10 us instead of 22 us for the smem-transpose version.
+__global__ void __launch_bounds__(128)
 split_cn_kernel(const float* __restrict__ src, const float* __restrict__ src2, __nv_bfloat16* __restrict__ dst, int nb,
                 int n) {
-  __shared__ float t[128][65];
-  const int b = blockIdx.y, tok0 = blockIdx.x * 64;
-  const float* s = (b < nb ? src + (size_t)b * 128 * n : src2 + (size_t)(b - nb) * 128 * n);
-  for (int i = threadIdx.x; i < 128 * 64; i += 256) {
-    int c = i >> 6, r = i & 63;
-    t[c][r] = (tok0 + r < n) ? __ldg(s + (size_t)c * n + tok0 + r) : 0.f;
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= n) return;
+  const float* s = (b < nb ? src + (size_t)b * 128 * n : src2 + (size_t)(b - nb) * 128 * n) + (size_t)chunk * 32 * n + tok;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __ldg(s + (size_t)i * n);
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat162 h, l;
+    split2(v[2 * i], v[2 * i + 1], h, l);
+    hi[i] = *reinterpret_cast<uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<uint32_t*>(&l);
   }
-  __syncthreads();
-  __nv_bfloat16* d = dst + ((size_t)b * n + tok0) * 256;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    int r = i >> 6, cp = i & 63;
-    if (tok0 + r < n) {
-      __nv_bfloat162 hi, lo;
-      split2(t[2 * cp][r], t[2 * cp + 1][r], hi, lo);
-      *reinterpret_cast<__nv_bfloat162*>(d + (size_t)r * 256 + 2 * cp) = hi;
-      *reinterpret_cast<__nv_bfloat162*>(d + (size_t)r * 256 + 128 + 2 * cp) = lo;
-    }
+  uint4* d = reinterpret_cast<uint4*>(dst + ((size_t)b * n + tok) * 256 + chunk * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    d[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    d[16 + i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);     // + 128 bf16 = 256 bytes
   }
 }
 
@@ -591,22 +782,32 @@ int make_map(CUtensorMap* m, const void* base, int nb, int n) {
   return EMIP_OK;
 }
 
-// scores [slabs][nq][nk] fp32, box = 16 columns x 32 rows x 1 slab, 64-byte swizzle (store side: OOB is clipped)
-int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk) {
+// scores [slabs][nq][nk] fp32, box = 16 (64-byte swizzle) or 32 (128-byte swizzle) columns x 32 rows x 1 slab
+// (store side: OOB is clipped)
+int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk, bool wide) {
   EncodeTiledFn enc = get_encoder();
   if (enc == nullptr) return EMIP_ENOSYS;
   cuuint64_t dims[3] = {(cuuint64_t)nk, (cuuint64_t)nq, (cuuint64_t)slabs};
   cuuint64_t strides[2] = {(cuuint64_t)nk * 4, (cuuint64_t)nq * nk * 4};
-  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t box[3] = {wide ? 32u : 16u, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EMIP_OK : EMIP_EINVAL;
 }
 
 }  // namespace
 
 static unsigned long long* g_prof = nullptr;
+static int g_softmax_warps = 0;
+// Diagnostics: force 8 or 16 softmax warps per CTA (tools/k1_roles.py compares them); 0 = choose by mode:
+// 8 for the 3-term split (UMMA-bound: fewer warps = no spills, less smem/L1 traffic next to the operand reads),
+// 16 for single-pass bf16 (softmax-bound: r1p 70 vs 76 us).
+extern "C" void emip_match_tc_set_variant(int softmax_warps) {
+  g_softmax_warps = (softmax_warps == 16 || softmax_warps == 8) ? softmax_warps : 0;
+}
+
 // Diagnostics: device buffer of gridDim.x * 8 counters filled by the next launches (NULL switches it off).
 extern "C" void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf) { g_prof = dev_buf; }
 
@@ -620,8 +821,8 @@ int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n
   if (nb == 0 || n == 0) return EMIP_OK;
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst) + (size_t)dst_batch0 * n * 256;
   if (layout == EMIP_LAYOUT_CN) {
-    dim3 grid((n + 63) / 64, src2 ? 2 * nb : nb);
-    split_cn_kernel<<<grid, 256, 0, st>>>(src, src2, d, nb, n);
+    dim3 grid((n + 127) / 128, 4, src2 ? 2 * nb : nb);
+    split_cn_kernel<<<grid, 128, 0, st>>>(src, src2, d, nb, n);
   } else {
     long long rows = (long long)nb * n;
     split_nc_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(src, d, rows);
@@ -638,6 +839,7 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   if (a.sub_grid && a.grid_w <= 0) { emip_set_error("match_tc_fwd: sub_grid needs grid_w"); return EMIP_EINVAL; }
   CUtensorMap mx, my, ms;
   int rc;
+  const int nsmx = g_softmax_warps ? g_softmax_warps : (a.terms == 1 ? 16 : 8);
   if ((rc = make_map(&mx, a.x_split, a.nbx, a.nq))) return rc;
   if ((rc = make_map(&my, a.y_split, a.nby, a.nk))) return rc;
   ms = mx;
@@ -645,13 +847,14 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   if (a.s_out != nullptr && a.s_count > 0) {
     // TMA needs 16-byte aligned global rows; odd token counts fall back to plain stores
     const bool tma_ok = (a.nk % 4 == 0) && (reinterpret_cast<uintptr_t>(a.s_out) % 16 == 0) &&
-                        make_store_map(&ms, a.s_out, a.s_count, a.nq, a.nk) == EMIP_OK;
+                        make_store_map(&ms, a.s_out, a.s_count, a.nq, a.nk, nsmx == 8) == EMIP_OK;
     s_mode = tma_ok ? 1 : 2;
     if (!tma_ok) ms = mx;
   }
   static bool attr_done = false;
   if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   KParams p;
@@ -664,7 +867,8 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   const int nqt = (a.nq + TM - 1) / TM;
   int grid = a.nb * ((nqt + 1) / 2);
   if (grid > emip_num_sms()) grid = emip_num_sms();
-  match_tc_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, ms, p);
+  if (nsmx == 8) match_tc_fwd_kernel<8><<<grid, 10 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+  else match_tc_fwd_kernel<16><<<grid, 18 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
   EMIP_CHECK_LAUNCH("match_tc_fwd");
   return EMIP_OK;
 }

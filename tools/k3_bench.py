@@ -73,9 +73,11 @@ if __name__ == "__main__":
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         pk = json.load(open(p))["hbm_gbs"]
-    for variant in (0,):
+    import sys as _sys
+    variants = [int(a, 0) for a in _sys.argv[1:]] or [2]
+    for variant in variants:
       _lib.lib().emip_debug_flow_warp_variant(variant)
-      print("variant", variant, "(0 = 32x32 tiles, 1 = linear 1024-px segments)")
+      print("persistent CTAs per SM:", variant)
       r = run(torch.device("cuda", 0), pk)
       for k, v in r.items():
           print(f"{k:11s} fwd {v['fwd']['launch_ms']*1e3:7.1f} us {v['fwd']['achieved']:7.0f} GB/s ({100*v['fwd']['frac']:4.1f}%)   "
