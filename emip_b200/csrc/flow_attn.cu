@@ -7,6 +7,7 @@
 #include "../../include/emip_b200.h"
 #include "pair_common.cuh"
 #include "match_tc.cuh"
+#include "pair_bwd_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -15,7 +16,7 @@ size_t d_bytes(int B, int N) { return emip_align_up(sizeof(float) * (size_t)B * 
 
 extern "C" size_t emip_flow_attn_workspace(int B, int N, int C) {
   if (B < 0 || N <= 0 || C <= 0) return 0;
-  return d_bytes(B, N) + 2 * match_tc_split_bytes(B, N, C);
+  return d_bytes(B, N) + 2 * match_tc_split_bytes(B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N);
 }
 
 extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse,
@@ -59,7 +60,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
 
 extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
                                   const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes,
-                                  int B, int N, int C, void* stream) {
+                                  int B, int N, int C, int flags, void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(q && k && v && out && lse && dout && dq && dk, "flow_attn_bwd: null pointer");
   if (C != 128) {
@@ -75,6 +76,29 @@ extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v
   float* D = static_cast<float*>(workspace);      // D_i = dO_i . O_i
   int rc;
   if ((rc = launch_rowdot2(dout, out, nullptr, D, B, N, st))) return rc;
+  if (!(flags & EMIP_FLAG_EXACT_FP32) && pair_bwd_tc_supported(N, N, C) && N % 8 == 0) {
+    const size_t sb = match_tc_split_bytes(B, N, C);
+    if (ws_bytes < d_bytes(B, N) + 2 * sb + pair_bwd_tc_chn_bytes(2 * B, N) || reinterpret_cast<uintptr_t>(workspace) % 1024) {
+      emip_set_error("flow_attn_bwd: workspace too small or not 1024-byte aligned");
+      return EMIP_ENOMEM;
+    }
+    char* tok = static_cast<char*>(workspace) + d_bytes(B, N);        // [q batches | k batches] token-major
+    char* chn = tok + 2 * sb;
+    if ((rc = match_tc_split(q, k, tok, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    if ((rc = pair_bwd_tc_split_chn(q, k, chn, B, N, EMIP_LAYOUT_NC, st))) return rc;
+    PairBwdTcArgs t = {};
+    t.tok_split = tok; t.tok_split_y = tok; t.chn_split_y = chn; t.n_split = 2 * B;
+    t.nb = B; t.nr = N; t.nc = N; t.dx_layout = EMIP_LAYOUT_NC; t.sqrt_c = sqrtf((float)C);
+    // dq_i = sum_j P_ij (dO_i.v_j - D_i) k_j / sqrt(C)
+    t.x_base = 0; t.y_base = B; t.dx = dq;
+    t.l1 = lse; t.u = dout; t.u0 = D; t.t = v; t.t_stride_b = 2LL * N;
+    if ((rc = pair_bwd_tc(t, st))) return rc;
+    // dk_j = sum_i P_ij (dO_i.v_j - D_i) q_i / sqrt(C): rows j, softmax statistics live on the columns i
+    t.x_base = B; t.y_base = 0; t.dx = dk;
+    t.l1 = t.u = t.u0 = t.t = nullptr;
+    t.l2 = lse; t.w = dout; t.w0 = D; t.t2 = v; t.t2_stride_b = 2LL * N;
+    return pair_bwd_tc(t, st);
+  }
   PairBwdArgs a = {};
   a.nb = B; a.nr = N; a.nc = N;
   a.x_layout = a.y_layout = a.dx_layout = EMIP_LAYOUT_NC;

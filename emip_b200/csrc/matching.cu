@@ -5,20 +5,22 @@
 #include "../../include/emip_b200.h"
 #include "pair_common.cuh"
 #include "match_tc.cuh"
+#include "pair_bwd_tc.cuh"
 #include <math.h>
 
 namespace {
 struct MatchWs {
   float* grid;     // [2][N] pixel grid (geometry.py:5-21)
   float* u0;       // [nd*B][N]
-  void* split;     // bf16 hi/lo operands for the tensor-core path
+  void* split;     // bf16 hi/lo token-major operands for the tensor-core paths
   size_t split_bytes;
+  void* chn;       // bf16 hi/lo channel-major operands (tensor-core backward)
 };
 
 size_t simt_bytes(int B, int N, int nd) { return emip_align_up(sizeof(float) * ((size_t)2 * N + (size_t)nd * B * N), 1024); }
 
 int carve(void* ws, size_t ws_bytes, int B, int C, int N, int nd, MatchWs* out) {
-  size_t need = simt_bytes(B, N, nd) + match_tc_split_bytes(2 * B, N, C);
+  size_t need = simt_bytes(B, N, 2) + match_tc_split_bytes(2 * B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N);
   if (ws == nullptr || ws_bytes < need) {
     emip_set_error("global_matching: workspace too small (%zu < %zu bytes)", ws_bytes, need);
     return EMIP_ENOMEM;
@@ -30,15 +32,16 @@ int carve(void* ws, size_t ws_bytes, int B, int C, int N, int nd, MatchWs* out) 
   char* p = static_cast<char*>(ws);
   out->grid = reinterpret_cast<float*>(p);
   out->u0 = out->grid + 2 * (size_t)N;
-  out->split = p + simt_bytes(B, N, nd);
+  out->split = p + simt_bytes(B, N, 2);
   out->split_bytes = match_tc_split_bytes(2 * B, N, C);
+  out->chn = p + simt_bytes(B, N, 2) + out->split_bytes;
   return EMIP_OK;
 }
 }  // namespace
 
 extern "C" size_t emip_global_matching_workspace(int B, int C, int H, int W) {
   if (B < 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return simt_bytes(B, H * W, 2) + match_tc_split_bytes(2 * B, H * W, C);
+  return simt_bytes(B, H * W, 2) + match_tc_split_bytes(2 * B, H * W, C) + pair_bwd_tc_chn_bytes(2 * B, H * W);
 }
 
 extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float* flow, float* corr, float* lse,
@@ -99,7 +102,7 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
 extern "C" int emip_global_matching_bwd(const float* f0, const float* f1, const float* flow, const float* lse,
                                         const float* dflow, const float* dcorr, float* df0, float* df1,
                                         void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir,
-                                        void* stream) {
+                                        int flags, void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(f0 && f1 && flow && lse && df0 && df1, "global_matching_bwd: null pointer");
   EMIP_CHECK_ARG(dflow || dcorr, "global_matching_bwd: both dflow and dcorr are NULL");
@@ -119,6 +122,29 @@ extern "C" int emip_global_matching_bwd(const float* f0, const float* f1, const 
     if ((rc = launch_rowdot2(dflow, flow, ws.grid, ws.u0, nd * B, N, st))) return rc;
   }
   const size_t hb = (size_t)B * N;   // offset of the backward-direction half
+  if (!(flags & EMIP_FLAG_EXACT_FP32) && pair_bwd_tc_supported(N, N, C) && N % 8 == 0) {
+    // tensor-core path: operands split once (token-major for S, channel-major for dX), one launch per gradient
+    if ((rc = match_tc_split(f0, f1, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
+    if ((rc = pair_bwd_tc_split_chn(f0, f1, ws.chn, B, N, EMIP_LAYOUT_CN, st))) return rc;
+    PairBwdTcArgs t = {};
+    t.tok_split = ws.split; t.tok_split_y = ws.split; t.chn_split_y = ws.chn; t.n_split = 2 * B;
+    t.nb = B; t.nr = N; t.nc = N; t.dx_layout = EMIP_LAYOUT_CN; t.sqrt_c = sqrtf((float)C);
+    t.t = ws.grid; t.t_stride_b = 0; t.t2 = ws.grid; t.t2_stride_b = 0;
+    t.e = dcorr; t.e_stride_b = (long long)N * N;
+    // d f0 : rows i (f0), columns j (f1)
+    t.x_base = 0; t.y_base = B; t.dx = df0;
+    if (dflow) { t.l1 = lse; t.u = dflow; t.u0 = ws.u0; }
+    if (dflow && bidir) { t.l2 = lse + hb; t.w = dflow + 2 * hb; t.w0 = ws.u0 + hb; }
+    if (bidir) { t.e_stride_r = 1; t.e_stride_c = N; } else { t.e_stride_r = N; t.e_stride_c = 1; }
+    if ((rc = pair_bwd_tc(t, st))) return rc;
+    // d f1 : rows j (f1), columns i (f0) -- the same tile transposed
+    t.x_base = B; t.y_base = 0; t.dx = df1;
+    t.l1 = t.u = t.u0 = t.l2 = t.w = t.w0 = nullptr;
+    if (dflow && bidir) { t.l1 = lse + hb; t.u = dflow + 2 * hb; t.u0 = ws.u0 + hb; }
+    if (dflow) { t.l2 = lse; t.w = dflow; t.w0 = ws.u0; }
+    if (bidir) { t.e_stride_r = N; t.e_stride_c = 1; } else { t.e_stride_r = 1; t.e_stride_c = N; }
+    return pair_bwd_tc(t, st);
+  }
   PairBwdArgs a = {};
   a.nb = B; a.nr = N; a.nc = N;
   a.x_layout = a.y_layout = a.dx_layout = EMIP_LAYOUT_CN;

@@ -27,6 +27,7 @@ class _FlowAttnCore(torch.autograd.Function):
         _lib.check(L.emip_flow_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ctypes.c_void_p(ws_ptr), SZ(ws_n),
                                         I(B), I(N), I(C), I(flags), stream_ptr()), "emip_flow_attn_fwd")
         ctx.save_for_backward(q, k, v, out, lse)
+        ctx.flags = flags
         return out
 
     @staticmethod
@@ -42,7 +43,8 @@ class _FlowAttnCore(torch.autograd.Function):
         dq = torch.empty_like(q)
         dk = torch.empty_like(k)
         _lib.check(L.emip_flow_attn_bwd(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout.contiguous()), ptr(dq),
-                                        ptr(dk), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(N), I(C), stream_ptr()),
+                                        ptr(dk), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(N), I(C), I(ctx.flags & 1),
+                                        stream_ptr()),
                    "emip_flow_attn_bwd")
         return dq, dk, None, None
 

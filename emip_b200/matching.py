@@ -35,6 +35,7 @@ class _GlobalMatching(torch.autograd.Function):
                    "emip_global_matching_fwd")
         ctx.save_for_backward(f0, f1, flow, lse)
         ctx.bidir = bidir
+        ctx.flags = flags
         ctx.set_materialize_grads(False)
         return flow, smem
 
@@ -54,7 +55,8 @@ class _GlobalMatching(torch.autograd.Function):
         df1 = torch.empty_like(f1)
         _lib.check(L.emip_global_matching_bwd(ptr(f0), ptr(f1), ptr(flow), ptr(lse), ptr(dflow), ptr(dsmem), ptr(df0),
                                               ptr(df1), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C), I(H), I(W),
-                                              I(int(ctx.bidir)), stream_ptr()), "emip_global_matching_bwd")
+                                              I(int(ctx.bidir)), I(ctx.flags & EXACT_FP32), stream_ptr()),
+                   "emip_global_matching_bwd")
         return df0, df1, None, None, None
 
 

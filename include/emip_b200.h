@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EMIP_ABI_VERSION 1
+#define EMIP_ABI_VERSION 2
 
 #define EMIP_PAD_BORDER 0
 #define EMIP_PAD_ZEROS 1
@@ -92,10 +92,12 @@ int emip_global_matching_fwd(const float* f0, const float* f1, float* flow, floa
                              void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir, int flags,
                              void* stream);
 /* Backward of the above (what autograd derives for matching.py:16-39).  dflow [nd*B,2,H,W] and/or dcorr (same
- * layout as corr) may be NULL; flow and lse are the forward outputs.  df0, df1 [B,C,H,W] are overwritten. */
+ * layout as corr) may be NULL; flow and lse are the forward outputs.  df0, df1 [B,C,H,W] are overwritten.
+ * flags: 0 = tensor-core path (S recomputed and dX accumulated with bf16 hi/lo splits, H*W % 8 == 0),
+ *        EMIP_FLAG_EXACT_FP32 = CUDA-core fp32. */
 int emip_global_matching_bwd(const float* f0, const float* f1, const float* flow, const float* lse,
                              const float* dflow, const float* dcorr, float* df0, float* df1, void* workspace,
-                             size_t ws_bytes, int B, int C, int H, int W, int bidir, void* stream);
+                             size_t ws_bytes, int B, int C, int H, int W, int bidir, int flags, void* stream);
 
 /* ---- a2: flow-propagation attention -------------------------------------- */
 /* Replaces the attention core of FeatureFlowAttention.forward,
@@ -109,7 +111,7 @@ int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* ou
 /* Backward w.r.t. q and k only: the value is flow.detach() in the model (gmflow.py:137). */
 int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
                        const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes, int B, int N,
-                       int C, void* stream);
+                       int C, int flags, void* stream);
 
 /* ---- a4: prompt fusion (camouflaged feeder / motion collector) ---------------------------------- */
 /* Replaces model/EMIP_short/motion/PromptInteract.py:452-464 Injector.forward(image_embeddings, flow)

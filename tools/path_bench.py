@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Per-row benchmark of the hot path, forward and backward, on one B200.
+
+For every row: CUDA-event time of the public op (inputs resident in HBM, L2 defeated by rotating input sets where the
+footprint is small), algorithmic FLOPs / bytes, the fraction of the measured peak that bounds it, and the CPU oracle
+(the reference algorithm restated, torch CPU fp32, all host threads) timed on a bounded sample beside it.
+
+    python tools/path_bench.py [--no-cpu] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import torch  # noqa: E402
+import cases  # noqa: E402
+
+N, C, H, W = 1936, 128, 44, 44
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def gpu_time(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cpu_time(fn, budget_s=6.0):
+    fn()
+    t0, n = time.perf_counter(), 0
+    while True:
+        fn()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 5:
+            break
+    return (time.perf_counter() - t0) / n * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    from oracle import restate as O
+    from emip_b200.matching import global_correlation_softmax
+    from emip_b200.flow_attn import FeatureFlowAttention
+    from emip_b200.warp import flow_warp
+    from emip_b200.injector import Injector
+    from emip_b200.memory import Memory
+    hbm, tf, src = peaks()
+    dev = torch.device("cuda", 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rows = []
+
+    def add(name, unit_n, unit, ms_f, ms_b, flops_f, flops_b, bytes_f, bytes_b, bound, cpu_f=None, cpu_b=None, note=""):
+        r = {"row": name, "units": unit_n, "unit": unit, "fwd_ms": ms_f, "bwd_ms": ms_b,
+             "fwd_units_per_s": unit_n / (ms_f * 1e-3), "bound": bound, "note": note}
+        if bound == "tensor":
+            r["fwd_frac_of_peak"] = flops_f / (ms_f * 1e-3) / 1e12 / tf
+            r["fwd_alg_tflops"] = flops_f / (ms_f * 1e-3) / 1e12
+        else:
+            r["fwd_frac_of_peak"] = bytes_f / (ms_f * 1e-3) / 1e9 / hbm
+            r["fwd_alg_gbs"] = bytes_f / (ms_f * 1e-3) / 1e9
+        if ms_b is not None:
+            r["bwd_alg_tflops"] = flops_b / (ms_b * 1e-3) / 1e12
+            r["bwd_alg_gbs"] = bytes_b / (ms_b * 1e-3) / 1e9
+        if cpu_f is not None:
+            r["cpu_fwd_ms"] = cpu_f
+            r["cpu_bwd_ms"] = cpu_b
+            r["speedup_fwd"] = cpu_f / ms_f
+            if cpu_b and ms_b:
+                r["speedup_fwd_bwd"] = (cpu_f + cpu_b) / (ms_f + ms_b)
+        rows.append(r)
+        print(json.dumps(r))
+
+    # ---------------- a1: global matching, B = 16 (config c2) ----------------
+    B = 16
+    sets = [(4.1 * torch.randn(B, C, H, W, device=dev, generator=g), 4.1 * torch.randn(B, C, H, W, device=dev, generator=g))
+            for _ in range(4)]
+    wf = torch.randn(2 * B, 2, H, W, device=dev, generator=g)
+    wc = 0.05 * torch.randn(B, N, H, W, device=dev, generator=g)
+    it = [0]
+
+    def a1_fwd():
+        f0, f1 = sets[it[0] % 4]
+        it[0] += 1
+        with torch.no_grad():
+            return global_correlation_softmax(f0, f1, True)
+
+    def a1_fwd_bwd():
+        f0, f1 = sets[it[0] % 4]
+        it[0] += 1
+        a, b = f0.detach().requires_grad_(True), f1.detach().requires_grad_(True)
+        flow, _, corr = global_correlation_softmax(a, b, True)
+        torch.autograd.backward([flow, corr], [wf, wc])
+
+    ms_f = gpu_time(a1_fwd)
+    ms_fb = gpu_time(a1_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        c0, c1 = sets[0][0].cpu(), sets[0][1].cpu()
+        cw, cc = wf.cpu(), wc.cpu()
+
+        def c_f():
+            with torch.no_grad():
+                O.global_correlation_softmax(c0, c1, True)
+
+        def c_fb():
+            a, b = c0.clone().requires_grad_(True), c1.clone().requires_grad_(True)
+            flow, _, corr = O.global_correlation_softmax(a, b, True)
+            torch.autograd.backward([flow, corr], [cw, cc])
+        cf = cpu_time(c_f)
+        cb = cpu_time(c_fb) - cf
+    fl = B * (2.0 * N * N * C + 8.0 * N * N)
+    add("a1 global matching (bidir, corr emitted), B=16", B, "pairs", ms_f, ms_fb - ms_f, fl, 2 * fl + 2 * B * 2.0 * N * N * C * 2,
+        B * (2 * C * N * 4 + 4 * N * 2 * 4 + N * N * 4), B * (3 * N * N * 4), "tensor", cf, cb,
+        "bwd = exact-fp32 CUDA-core recompute (dflow and dcorr)")
+
+    # ---------------- a2: flow-propagation attention, 2B = 32 ----------------
+    B2 = 32
+    m = FeatureFlowAttention(C).to(dev)
+    xs = [4.1 * torch.randn(B2, C, H, W, device=dev, generator=g) for _ in range(4)]
+    fl2 = 12.0 * torch.randn(B2, 2, H, W, device=dev, generator=g)
+    wo = torch.randn(B2, 2, H, W, device=dev, generator=g)
+
+    def a2_fwd():
+        it[0] += 1
+        with torch.no_grad():
+            return m(xs[it[0] % 4], fl2)
+
+    def a2_fwd_bwd():
+        it[0] += 1
+        x = xs[it[0] % 4].detach().requires_grad_(True)
+        m(x, fl2).backward(wo)
+    ms_f = gpu_time(a2_fwd)
+    ms_fb = gpu_time(a2_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        prm = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        cx, cfl, cwo = xs[0].cpu(), fl2.cpu(), wo.cpu()
+
+        def c_f():
+            with torch.no_grad():
+                O.feature_flow_attention(cx, cfl, prm["q_proj.weight"], prm["q_proj.bias"], prm["k_proj.weight"], prm["k_proj.bias"])
+
+        def c_fb():
+            x = cx.clone().requires_grad_(True)
+            O.feature_flow_attention(x, cfl, prm["q_proj.weight"], prm["q_proj.bias"], prm["k_proj.weight"],
+                                     prm["k_proj.bias"]).backward(cwo)
+        cf = cpu_time(c_f)
+        cb = cpu_time(c_fb) - cf
+    fl = B2 * (2.0 * N * N * (C + 2) + 2 * 2.0 * N * C * C)
+    add("a2 flow-propagation attention (incl. q/k Linear), 2B=32", B2 // 2, "pairs", ms_f, ms_fb - ms_f, fl, 2.5 * fl,
+        B2 * (C * N * 4 + 4 * N * 4), B2 * (2 * C * N * 4), "tensor", cf, cb)
+
+    # ---------------- a3: flow_warp, B = 64, 3 x 352 x 352 ----------------
+    Bw, Cw, Hw, Ww = 64, 3, 352, 352
+    x = torch.randn(Bw, Cw, Hw, Ww, device=dev, generator=g)
+    base = 10.0 * torch.randn(Bw, 2, 1, 1, device=dev, generator=g)
+    fl4 = torch.cat([cases.smooth_flow(11, Bw, Hw, Ww, 0.5), cases.smooth_flow(12, Bw, Hw, Ww, 0.5)], 1).to(dev)
+    fl4[:, :2] += base
+    fl4[:, 2:] -= base
+    wout = torch.randn(Bw, Cw, Hw, Ww, device=dev, generator=g)
+
+    def a3_fwd():
+        with torch.no_grad():
+            return flow_warp(x, fl4[:, 2:])
+
+    def a3_fwd_bwd():
+        f = fl4.detach().requires_grad_(True)
+        flow_warp(x, f[:, 2:]).backward(wout)
+    ms_f = gpu_time(a3_fwd)
+    ms_fb = gpu_time(a3_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        sx, sf, sw = x[:8].cpu(), fl4[:8].cpu(), wout[:8].cpu()          # bounded sample: 8 of 64 images
+
+        def c_f():
+            with torch.no_grad():
+                O.flow_warp(sx, sf[:, 2:])
+
+        def c_fb():
+            f = sf.clone().requires_grad_(True)
+            O.flow_warp(sx, f[:, 2:]).backward(sw)
+        cf = cpu_time(c_f) * 8
+        cb = cpu_time(c_fb) * 8 - cf
+    add("a3 flow_warp (model-like smooth flow), B=64 3x352x352", Bw, "images", ms_f, ms_fb - ms_f, 0, 0,
+        Bw * Hw * Ww * (2 * Cw + 2) * 4, Bw * Hw * Ww * (2 * Cw + 4) * 4, "hbm", cf, cb,
+        "bwd through autograd: includes the zero-fill + slice scatter of the [B,4,H,W] flow gradient; CPU sample = 8 images x 8")
+
+    # ---------------- a4: injector, B = 16 ----------------
+    B4 = 16
+    inj = Injector().to(dev)
+    inj.transformer.load_state_dict({k: v for k, v in cases.injector_params(7).items()})
+    x4 = [2.2 * torch.randn(B4, C, H, W, device=dev, generator=g) for _ in range(4)]
+    y4 = [torch.randn(B4, C, H, W, device=dev, generator=g) for _ in range(4)]
+    w4 = torch.randn(B4, C, H, W, device=dev, generator=g)
+
+    def a4_fwd():
+        it[0] += 1
+        with torch.no_grad():
+            return inj(x4[it[0] % 4], y4[it[0] % 4])
+
+    def a4_fwd_bwd():
+        it[0] += 1
+        a, b = x4[it[0] % 4].detach().requires_grad_(True), y4[it[0] % 4].detach().requires_grad_(True)
+        inj(a, b).backward(w4)
+        inj.zero_grad(set_to_none=True)
+    ms_f = gpu_time(a4_fwd, iters=10)
+    ms_fb = gpu_time(a4_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        prm = cases.injector_params(7)
+        sx, sy, sw = x4[0][:4].cpu(), y4[0][:4].cpu(), w4[:4].cpu()    # bounded sample: 4 of 16
+
+        def c_f():
+            with torch.no_grad():
+                O.injector(sx, sy, prm)
+
+        def c_fb():
+            a, b = sx.clone().requires_grad_(True), sy.clone().requires_grad_(True)
+            pp = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+            O.injector(a, b, pp).backward(sw)
+        cf = cpu_time(c_f) * 4
+        cb = cpu_time(c_fb) * 4 - cf
+    fl = B4 * 0.86e9
+    add("a4 prompt fusion (Injector), B=16", B4, "calls", ms_f, ms_fb - ms_f, fl, 2 * fl, B4 * 3 * C * N * 4, B4 * 5 * C * N * 4,
+        "hbm", cf, cb, "exact fp32 CUDA cores; 0.86 GFLOP and 2.97 MB algorithmic per sample; CPU sample = 4 x 4")
+
+    # ---------------- a5: memory read, B = 1, T = 5 ----------------
+    d5 = cases.a5_inputs(dict(b=1, t=5, h=44, w=44, scale=1.5, seed=57))
+    t5 = {k: d5[k].to(dev) for k in ("m_in", "m_out", "q_in", "q_out")}
+    w5 = d5["wout"].to(dev)
+    mem = Memory()
+
+    def a5_fwd():
+        with torch.no_grad():
+            return mem(t5["m_in"], t5["m_out"], t5["q_in"], t5["q_out"])
+
+    def a5_fwd_bwd():
+        tt = {k: v.detach().requires_grad_(True) for k, v in t5.items()}
+        mem(tt["m_in"], tt["m_out"], tt["q_in"], tt["q_out"])[0].backward(w5)
+    ms_f = gpu_time(a5_fwd, iters=10)
+    ms_fb = gpu_time(a5_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        def c_f():
+            with torch.no_grad():
+                O.memory_read(d5["m_in"], d5["m_out"], d5["q_in"], d5["q_out"])
+
+        def c_fb():
+            tt = {k: d5[k].clone().requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
+            O.memory_read(tt["m_in"], tt["m_out"], tt["q_in"], tt["q_out"])[0].backward(d5["wout"])
+        cf = cpu_time(c_f)
+        cb = cpu_time(c_fb) - cf
+    M = 5 * N
+    fl = 2.0 * M * N * 256
+    add("a5 EMIP_long memory read, B=1 T=5 (9680 slots)", 1, "frames", ms_f, ms_fb - ms_f, fl, 2.5 * fl, (2 * M + 3 * N) * 128 * 4,
+        (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "exact fp32 CUDA cores (fraction shown against the bf16 tensor peak)")
+
+    out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "cpu_threads": os.cpu_count(), "rows": rows}
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
