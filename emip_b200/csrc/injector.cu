@@ -186,6 +186,228 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(GemmNTk p) {
   }
 }
 
+// ------------------------------------------------------------------ 128 x 128 tile SGEMM (fast paths)
+// 256 threads as 16 x 16; thread (tx, ty) owns rows {4ty..4ty+3, 64+4ty..} and columns {4tx.., 64+4tx..} (8 x 8
+// outputs), operands staged k-major in double-buffered shared memory with register prefetch of the next slab.
+// The first version of these GEMMs (64 x 64 tiles, 4 x 4 per thread, no prefetch) reached 16 TFLOP/s and was 60 %
+// of the injector's forward time.
+constexpr int FB = 128;   // tile (both dims)
+constexpr int FK = 8;     // contraction slab
+
+__device__ __forceinline__ void fma_slab(const float (*As)[FB], const float (*Bs)[FB], int tx, int ty, float (&acc)[8][8]) {
+#pragma unroll
+  for (int k = 0; k < FK; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+// Y[b][m][n] = sum_k W(b)[m][k] X'(b)[k][n] (+res): requires N % 4 == 0, ldx/ldy/ldr % 4 == 0, 16-byte aligned bases.
+__global__ void __launch_bounds__(256, 2) gemm_nn_fast_kernel(GemmNN a) {
+  __shared__ __align__(16) float As[2][FK][FB];
+  __shared__ __align__(16) float Bs[2][FK][FB];
+  const int b = blockIdx.z, m0 = blockIdx.y * FB, n0 = blockIdx.x * FB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* W = a.w + (size_t)b * a.w_stride_b;
+  const float* X = a.x + (size_t)b * a.x_stride_b;
+  const bool ln = a.mean != nullptr;
+  // B slab: 8 rows x 32 float4; this thread always loads row kb, columns nb4..nb4+3
+  const int kb = tid >> 5, nb4 = n0 + (tid & 31) * 4;
+  const bool n_ok = nb4 < a.N;
+  float4 mu4 = make_float4(0.f, 0.f, 0.f, 0.f), rs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (ln && n_ok) {
+    mu4 = __ldg(reinterpret_cast<const float4*>(a.mean + (size_t)b * a.N + nb4));
+    rs4 = __ldg(reinterpret_cast<const float4*>(a.rstd + (size_t)b * a.N + nb4));
+  }
+  // A slab: 128 rows x 8 k.  w_trans: 8 k-rows x 32 float4 along m; else thread -> (row tid/2, four k at (tid%2)*4)
+  const int am = a.w_trans ? (tid & 31) * 4 : (tid >> 1), ak = a.w_trans ? (tid >> 5) : (tid & 1) * 4;
+  float4 ra, rb;
+  auto load = [&](int k0) {
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.w_trans) {
+      if (k0 + ak < a.K && m0 + am < a.M) ra = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k0 + ak) * a.ldw + m0 + am));
+    } else {
+      if (m0 + am < a.M) {
+        const float* wp = W + (size_t)(m0 + am) * a.ldw + k0 + ak;
+        if (k0 + ak + 3 < a.K) ra = __ldg(reinterpret_cast<const float4*>(wp));
+        else {
+          if (k0 + ak < a.K) ra.x = __ldg(wp);
+          if (k0 + ak + 1 < a.K) ra.y = __ldg(wp + 1);
+          if (k0 + ak + 2 < a.K) ra.z = __ldg(wp + 2);
+        }
+      }
+    }
+    if (k0 + kb < a.K && n_ok) {
+      rb = __ldg(reinterpret_cast<const float4*>(X + (size_t)(k0 + kb) * a.ldx + nb4));
+      if (ln) {
+        const float gk = __ldg(a.gamma + k0 + kb), bk = __ldg(a.beta + k0 + kb);
+        rb.x = (rb.x - mu4.x) * rs4.x * gk + bk;
+        rb.y = (rb.y - mu4.y) * rs4.y * gk + bk;
+        rb.z = (rb.z - mu4.z) * rs4.z * gk + bk;
+        rb.w = (rb.w - mu4.w) * rs4.w * gk + bk;
+      }
+    }
+  };
+  auto store = [&](int s) {
+    if (a.w_trans) *reinterpret_cast<float4*>(&As[s][ak][am]) = ra;
+    else { As[s][ak][am] = ra.x; As[s][ak + 1][am] = ra.y; As[s][ak + 2][am] = ra.z; As[s][ak + 3][am] = ra.w; }
+    *reinterpret_cast<float4*>(&Bs[s][kb][(tid & 31) * 4]) = rb;
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load(0);
+  store(0);
+  __syncthreads();
+  int s = 0;
+  for (int k0 = 0; k0 < a.K; k0 += FK) {
+    const bool more = k0 + FK < a.K;
+    if (more) load(k0 + FK);                      // global loads of the next slab fly during the FMAs
+    fma_slab(As[s], Bs[s], tx, ty, acc);
+    if (more) store(s ^ 1);
+    __syncthreads();
+    s ^= 1;
+  }
+  float* Y = a.y + (size_t)b * a.y_stride_b;
+  const float* R = a.res ? a.res + (size_t)b * a.res_stride_b : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + h * 64 + tx * 4;
+      if (n >= a.N) continue;
+      float4 v = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      if (R) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(R + (size_t)m * a.ldr + n));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      float4* yp = reinterpret_cast<float4*>(Y + (size_t)m * a.ldy + n);
+      if (a.accumulate) { const float4 o = *yp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *yp = v;
+    }
+  }
+}
+
+// C[b*S+s][m][k] = sum_{n in split s} A(b)[m][n] B'(b)[k][n]: both operands contiguous along the contraction.
+// Requires lda/ldb % 4 == 0, N % 4 == 0, chunk % 4 == 0, 16-byte aligned bases.
+constexpr int TK = 16;    // contraction slab of the NT kernel (one float4 per thread and operand)
+__global__ void __launch_bounds__(256, 2) gemm_nt_fast_kernel(GemmNTk p) {
+  const GemmNT& a = p.g;
+  __shared__ __align__(16) float As[2][TK][FB + 4];
+  __shared__ __align__(16) float Bs[2][TK][FB + 4];
+  const int bs = blockIdx.z, b = bs / p.nsplit, sp = bs % p.nsplit;
+  const int m0 = blockIdx.y * FB, k0 = blockIdx.x * FB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* A = a.a + (size_t)b * a.a_stride_b;
+  const float* Bm = a.bm + (size_t)b * a.b_stride_b;
+  const bool ln = a.mean != nullptr;
+  const int nbeg = sp * p.chunk, nend = min(a.N, nbeg + p.chunk);
+  // slab: 128 rows x 16 n = 512 float4 per operand: thread -> rows r0 and r0 + 64, four n at n4
+  const int r0 = tid >> 2, n4 = (tid & 3) * 4;
+  float gam[2] = {0.f, 0.f}, bet[2] = {0.f, 0.f};
+  if (ln) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (k0 + r0 + 64 * h < a.K) { gam[h] = __ldg(a.gamma + k0 + r0 + 64 * h); bet[h] = __ldg(a.beta + k0 + r0 + 64 * h); }
+  }
+  float4 ra[2], rb[2];
+  auto load = [&](int n0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = n0 + n4;
+      if (n < nend) {
+        if (m0 + r0 + 64 * h < a.M) ra[h] = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + r0 + 64 * h) * a.lda + n));
+        if (k0 + r0 + 64 * h < a.K) {
+          rb[h] = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + r0 + 64 * h) * a.ldb + n));
+          if (ln) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean + (size_t)b * a.N + n));
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(a.rstd + (size_t)b * a.N + n));
+            rb[h].x = (rb[h].x - mu.x) * rs.x * gam[h] + bet[h];
+            rb[h].y = (rb[h].y - mu.y) * rs.y * gam[h] + bet[h];
+            rb[h].z = (rb[h].z - mu.z) * rs.z * gam[h] + bet[h];
+            rb[h].w = (rb[h].w - mu.w) * rs.w * gam[h] + bet[h];
+          }
+        }
+      }
+    }
+  };
+  auto store = [&](int s) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + 64 * h;
+      As[s][n4][r] = ra[h].x; As[s][n4 + 1][r] = ra[h].y; As[s][n4 + 2][r] = ra[h].z; As[s][n4 + 3][r] = ra[h].w;
+      Bs[s][n4][r] = rb[h].x; Bs[s][n4 + 1][r] = rb[h].y; Bs[s][n4 + 2][r] = rb[h].z; Bs[s][n4 + 3][r] = rb[h].w;
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (nbeg < nend) {
+    load(nbeg);
+    store(0);
+    __syncthreads();
+    int s = 0;
+    for (int n0 = nbeg; n0 < nend; n0 += TK) {
+      const bool more = n0 + TK < nend;
+      if (more) load(n0 + TK);
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[s][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[s][k][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[s][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[s][k][64 + tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (more) store(s ^ 1);
+      __syncthreads();
+      s ^= 1;
+    }
+  }
+  float* C = a.c + (size_t)bs * a.c_stride_b;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (k < a.K) C[(size_t)m * a.ldc + k] = acc[i][j];
+    }
+  }
+}
+
+// out[b][i] = sum_s part[(b*S + s)][i]
+__global__ void sum_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int nb, int S, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * n) return;
+  const int b = idx / n, i = idx % n;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += __ldg(part + ((size_t)b * S + s) * n + i);
+  out[idx] = acc;
+}
+
 __global__ void reduce_batch_kernel(const float* __restrict__ in, long long stride, float* __restrict__ out, int B,
                                     long long n, int accumulate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,7 +832,22 @@ bool carve_saved(void* buf, size_t bytes, int B, int N, Saved* s) {
   s->y = c.take((size_t)B * DIM * N); s->tpre = c.take((size_t)B * HID2 * N);
   return c.ok;
 }
-constexpr int NT_SPLIT = 4;     // pixel-axis splits of the weight-gradient GEMMs (more CTAs at small batch)
+// pixel-axis splits of the weight-gradient GEMMs: enough (batch x split x output tiles) CTAs for two per SM
+int nt_split(int B, int M, int K) {
+  const int tiles = ((M + 127) / 128) * ((K + 127) / 128);
+  int s = (2 * emip_num_sms() + B * tiles - 1) / (B * tiles);
+  return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+size_t nt_part_floats(int B) {       // largest partial buffer any of the backward's NT GEMMs needs
+  size_t m = 0;
+  const int shp[5][2] = {{DIM, HID}, {HID2, DIM}, {DIM, DIM}, {2 * DIM, DIM}, {DIM, DIM}};
+  for (auto& sh : shp) {
+    const size_t v = (size_t)B * nt_split(B, sh[0], sh[1]) * sh[0] * sh[1];
+    m = v > m ? v : m;
+  }
+  return m;
+}
+constexpr int G_SPLIT = 8;      // pixel-axis splits of the 64 x 64 Gram matrices
 
 int check_common(const char* who, int B, int H, int W) {
   EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "%s: bad shape B=%d H=%d W=%d", who, B, H, W);
@@ -626,8 +863,19 @@ int check_common(const char* who, int B, int H, int W) {
 // ------------------------------------------------------------------ public GEMM helpers (gemm_simt.cuh)
 int gemm_nn(const GemmNN& a, cudaStream_t st) {
   if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
-  dim3 grid((a.N + GB - 1) / GB, (a.M + GB - 1) / GB, a.B);
-  gemm_nn_kernel<<<grid, 256, 0, st>>>(a);
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const bool fast = a.N % 4 == 0 && a.ldx % 4 == 0 && a.ldy % 4 == 0 && a.x_stride_b % 4 == 0 && a.y_stride_b % 4 == 0 &&
+                    al16(a.x) && al16(a.y) && al16(a.w) && a.w_stride_b % 4 == 0 &&
+                    (a.w_trans ? a.ldw % 4 == 0 : a.ldw % 4 == 0) &&
+                    (!a.res || (a.ldr % 4 == 0 && a.res_stride_b % 4 == 0 && al16(a.res))) &&
+                    (!a.mean || (al16(a.mean) && al16(a.rstd))) && a.M >= 128 && a.M % 4 == 0;
+  if (fast) {
+    dim3 grid((a.N + FB - 1) / FB, (a.M + FB - 1) / FB, a.B);
+    gemm_nn_fast_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid((a.N + GB - 1) / GB, (a.M + GB - 1) / GB, a.B);
+    gemm_nn_kernel<<<grid, 256, 0, st>>>(a);
+  }
   EMIP_CHECK_LAUNCH("gemm_nn");
   return EMIP_OK;
 }
@@ -638,8 +886,16 @@ static int gemm_nt_split(const GemmNT& a, int nsplit, cudaStream_t st) {
   p.g = a;
   p.nsplit = nsplit;
   p.chunk = ((a.N + nsplit - 1) / nsplit + 31) / 32 * 32;
-  dim3 grid((a.K + GB - 1) / GB, (a.M + GB - 1) / GB, a.B * nsplit);
-  gemm_nt_kernel<<<grid, 256, 0, st>>>(p);
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool fast = a.N % 4 == 0 && a.lda % 4 == 0 && a.ldb % 4 == 0 && a.a_stride_b % 4 == 0 && a.b_stride_b % 4 == 0 &&
+                    al16(a.a) && al16(a.bm) && (!a.mean || (al16(a.mean) && al16(a.rstd))) && a.M >= 128 && a.K >= 128;
+  if (fast) {
+    dim3 grid((a.K + FB - 1) / FB, (a.M + FB - 1) / FB, a.B * nsplit);
+    gemm_nt_fast_kernel<<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((a.K + GB - 1) / GB, (a.M + GB - 1) / GB, a.B * nsplit);
+    gemm_nt_kernel<<<grid, 256, 0, st>>>(p);
+  }
   EMIP_CHECK_LAUNCH("gemm_nt");
   return EMIP_OK;
 }
@@ -662,9 +918,10 @@ extern "C" size_t emip_injector_workspace(int B, int H, int W) {
   // forward: g [B,340,N]; backward: g, dg, dtpre [B,680,N], 4 x [B,128,N], dkvpre [B,256,N], dn [B,128,N], partials
   size_t s = 2 * al((size_t)B * HID * N) + al((size_t)B * HID2 * N) + 6 * al((size_t)B * DIM * N) +
              al((size_t)B * 2 * DIM * N);
-  s += al((size_t)B * NT_SPLIT * HID2 * DIM);                      // largest weight-gradient partial
+  s += al(nt_part_floats(B));                                      // largest weight-gradient partial
   s += al((size_t)B * DIM * DIM) * 2 + al((size_t)B * HEADS * HD * HD) + 4 * al((size_t)B * DIM);
   s += al((size_t)B * HID2 * 9) + 2 * al((size_t)B * DIM) + al((size_t)B * HEADS);
+  s += al((size_t)B * HEADS * G_SPLIT * HD * HD);
   return s;
 }
 
@@ -715,8 +972,13 @@ extern "C" int emip_injector_fwd(const float* x, const float* x1, const float* c
     t.B = B * HEADS; t.M = HD; t.K = HD; t.N = N;
     t.a = s.q; t.a_stride_b = (long long)HD * N; t.lda = N;
     t.bm = s.k; t.b_stride_b = (long long)HD * N; t.ldb = N;
-    t.c = s.G; t.c_stride_b = HD * HD; t.ldc = HD;
-    if ((rc = gemm_nt(t, st))) return rc;
+    // 2B problems of 64 x 64 x N: split the pixel axis so that the launch fills the chip, then sum the partials
+    float* gpart = w.take((size_t)B * HEADS * G_SPLIT * HD * HD);
+    if (gpart == nullptr) { emip_set_error("injector_fwd: workspace carve failed"); return EMIP_ENOMEM; }
+    t.c = gpart; t.c_stride_b = HD * HD; t.ldc = HD;
+    if ((rc = gemm_nt_split(t, G_SPLIT, st))) return rc;
+    sum_splits_kernel<<<(B * HEADS * HD * HD + 255) / 256, 256, 0, st>>>(gpart, s.G, B * HEADS, G_SPLIT, HD * HD);
+    EMIP_CHECK_LAUNCH("sum_splits");
   }
   // |k_d|^2 over the pixels (F.normalize, :422); |q_c|^2 came out of the q depthwise kernel
   if ((rc = launch_row_sumsq(s.k, s.sk, B * DIM, N, st))) return rc;
@@ -780,7 +1042,7 @@ extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* c
   float* dv = w.take((size_t)B * DIM * N);
   float* dqpre = w.take((size_t)B * DIM * N);
   float* dkvpre = w.take((size_t)B * 2 * DIM * N);
-  float* wpart = w.take((size_t)B * NT_SPLIT * HID2 * DIM);
+  float* wpart = w.take(nt_part_floats(B));
   float* Pm = w.take((size_t)B * DIM * DIM);
   float* dwo_part = w.take((size_t)B * DIM * DIM);
   float* dGs = w.take((size_t)B * HEADS * HD * HD);
@@ -807,15 +1069,17 @@ extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* c
   t.B = B; t.M = DIM; t.K = HID; t.N = N;                                                        // dWout = dout g^T
   t.a = dout; t.a_stride_b = sN; t.lda = N; t.bm = g; t.b_stride_b = (long long)HID * N; t.ldb = N;
   t.c = wpart; t.c_stride_b = DIM * HID; t.ldc = HID;
-  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
-  if ((rc = reduce_batch(wpart, DIM * HID, dparams[P_FOW], B * NT_SPLIT, DIM * HID, 0, st))) return rc;
+  int ns = nt_split(B, DIM, HID);
+  if ((rc = gemm_nt_split(t, ns, st))) return rc;
+  if ((rc = reduce_batch(wpart, DIM * HID, dparams[P_FOW], B * ns, DIM * HID, 0, st))) return rc;
   t = {};
   t.B = B; t.M = HID2; t.K = DIM; t.N = N;                                                       // dWin = dtpre LN3(y)^T
   t.a = dtpre; t.a_stride_b = (long long)HID2 * N; t.lda = N; t.bm = s.y; t.b_stride_b = sN; t.ldb = N;
   t.mean = s.mean3; t.rstd = s.rstd3; t.gamma = params[P_N3W]; t.beta = params[P_N3B];
   t.c = wpart; t.c_stride_b = HID2 * DIM; t.ldc = DIM;
-  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
-  if ((rc = reduce_batch(wpart, HID2 * DIM, dparams[P_FIW], B * NT_SPLIT, HID2 * DIM, 0, st))) return rc;
+  ns = nt_split(B, HID2, DIM);
+  if ((rc = gemm_nt_split(t, ns, st))) return rc;
+  if ((rc = reduce_batch(wpart, HID2 * DIM, dparams[P_FIW], B * ns, HID2 * DIM, 0, st))) return rc;
   a = {};
   a.B = B; a.M = DIM; a.K = HID2; a.N = N; a.w = params[P_FIW]; a.ldw = DIM; a.w_trans = 1;      // dn3 = Win^T dtpre
   a.x = dtpre; a.x_stride_b = (long long)HID2 * N; a.ldx = N; a.y = t128a; a.y_stride_b = sN; a.ldy = N;
@@ -832,8 +1096,11 @@ extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* c
   t = {};
   t.B = B; t.M = DIM; t.K = DIM; t.N = N;                                                        // P = dy v^T
   t.a = dy; t.a_stride_b = sN; t.lda = N; t.bm = s.v; t.b_stride_b = sN; t.ldb = N;
-  t.c = Pm; t.c_stride_b = DIM * DIM; t.ldc = DIM;
-  if ((rc = gemm_nt(t, st))) return rc;
+  ns = nt_split(B, DIM, DIM);
+  t.c = wpart; t.c_stride_b = DIM * DIM; t.ldc = DIM;
+  if ((rc = gemm_nt_split(t, ns, st))) return rc;
+  sum_splits_kernel<<<(B * DIM * DIM + 255) / 256, 256, 0, st>>>(wpart, Pm, B, ns, DIM * DIM);
+  EMIP_CHECK_LAUNCH("sum_splits P");
   mdta_attn_bwd_kernel<<<B * HEADS, 256, 0, st>>>(Pm, s.attn, s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], dGs, aq, ak,
                                                    dtau_part, dwo_part);
   EMIP_CHECK_LAUNCH("mdta_attn_bwd");
@@ -868,13 +1135,15 @@ extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* c
   t.a = dqpre; t.a_stride_b = sN; t.lda = N; t.bm = x; t.b_stride_b = sN; t.ldb = N;
   t.mean = s.mean1; t.rstd = s.rstd1; t.gamma = params[P_N1W]; t.beta = params[P_N1B];
   t.c = wpart; t.c_stride_b = DIM * DIM; t.ldc = DIM;
-  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
-  if ((rc = reduce_batch(wpart, DIM * DIM, dparams[P_QW], B * NT_SPLIT, DIM * DIM, 0, st))) return rc;
+  ns = nt_split(B, DIM, DIM);
+  if ((rc = gemm_nt_split(t, ns, st))) return rc;
+  if ((rc = reduce_batch(wpart, DIM * DIM, dparams[P_QW], B * ns, DIM * DIM, 0, st))) return rc;
   t.M = 2 * DIM; t.a = dkvpre; t.a_stride_b = 2 * sN; t.bm = x1;                                  // dWkv = dkvpre LN2(x1)^T
   t.mean = s.mean2; t.rstd = s.rstd2; t.gamma = params[P_N2W]; t.beta = params[P_N2B];
   t.c_stride_b = 2 * DIM * DIM;
-  if ((rc = gemm_nt_split(t, NT_SPLIT, st))) return rc;
-  if ((rc = reduce_batch(wpart, 2 * DIM * DIM, dparams[P_KVW], B * NT_SPLIT, 2 * DIM * DIM, 0, st))) return rc;
+  ns = nt_split(B, 2 * DIM, DIM);
+  if ((rc = gemm_nt_split(t, ns, st))) return rc;
+  if ((rc = reduce_batch(wpart, 2 * DIM * DIM, dparams[P_KVW], B * ns, 2 * DIM * DIM, 0, st))) return rc;
   a = {};
   a.B = B; a.M = DIM; a.K = DIM; a.N = N; a.w = params[P_QW]; a.ldw = DIM; a.w_trans = 1;        // dn1 = Wq^T dqpre
   a.x = dqpre; a.x_stride_b = sN; a.ldx = N; a.y = t128a; a.y_stride_b = sN; a.ldy = N;
