@@ -30,6 +30,7 @@ FEATURE_STD = 4.1              # matches the feature scale seen inside the model
 N_INPUT_SETS = 8               # rotated so that the live footprint (8 x 32 MB in + 240 MB corr out) exceeds L2
 ALG_FLOP_PER_PAIR = 2.0 * N * N * C + 8.0 * N * N          # S counted once
 EXEC_MMA_FLOP_PER_PAIR = 2.0 * N * N * C * 3 * 2           # bf16 hi/lo split (x3), both directions (x2)
+NCU_DRAM_BYTES_PER_LAUNCH = 229.74e6                       # measured once per kernel change with ncu (profiles/)
 WARP_B, WARP_C, WARP_H, WARP_W = 64, 3, 352, 352
 
 
@@ -143,6 +144,8 @@ def workload_config(n_gpus):
                         "batch 16 pairs per GPU, corr emitted",
             "pairs_per_gpu": B_PER_GPU, "global_pairs": B_PER_GPU * n_gpus, "tokens": N, "channels": C,
             "l2_policy": f"inputs rotate over {N_INPUT_SETS} sets; live footprint > 126 MB L2",
+            "arithmetic": "fp32 in / fp32 out; S by three bf16 tcgen05 MMAs (hi.hi + lo.hi + hi.lo) accumulated in fp32, "
+                          "fp32 softmax",
             "sharding": f"batch-sharded x{n_gpus}, no data-path collective"}
 
 
@@ -295,7 +298,9 @@ def main():
         ach = alg / (k_ms * 1e-3) / 1e12
         line["roofline"] = {
             "kernel": "match_tc_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
-            "frac": ach / pk["tf"], "traffic": None, "peak_source": pk["src"] + " burst bf16 (cuBLAS)",
+            "frac": ach / pk["tf"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes",
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1s_k1_match_tc_fwd_full.txt",
+            "peak_source": pk["src"] + " burst bf16 (cuBLAS)",
             "launch_ms": k_ms, "launch_ms_flow_only": res["flow_only"],
             "launch_ms_bf16_mode": res["bf16_with_corr"], "launch_ms_bf16_mode_flow_only": res["bf16_flow_only"],
             "executed_mma_tflops": EXEC_MMA_FLOP_PER_PAIR * B_PER_GPU / (k_ms * 1e-3) / 1e12,
