@@ -10,6 +10,7 @@ unchanged (same signatures, same ``state_dict`` keys):
     model.EMIP_short.motion.PromptInteract.Injector                        (constructed at model.py:64-65, model_long.py:62)
     model.EMIP_long.LTM.Memory                                             (constructed at LTM.py:90)
     loss.warp_utils.flow_warp / loss.loss_flow.flow_warp                   (called at loss_flow.py:90-91)
+    model.EMIP_short.motion.gmflow.gmflow.GMFlow.upsample_flow             (method, called at gmflow.py:131,148)
 
 Call it after the reference root is on ``sys.path`` and before the model is constructed.  ``uninstall()`` restores
 the originals (used by the tests).
@@ -58,6 +59,19 @@ def install(strict=False):
             _saved[key] = getattr(mod, attr)
         setattr(mod, attr, ours)
         done.append(f"{mod_name}.{attr}")
+    # method patch: the convex x8 flow upsampling inside GMFlow
+    try:
+        gm = sys.modules.get("model.EMIP_short.motion.gmflow.gmflow") or importlib.import_module(
+            "model.EMIP_short.motion.gmflow.gmflow")
+        from .upsample import upsample_flow
+        key = ("model.EMIP_short.motion.gmflow.gmflow", "GMFlow.upsample_flow")
+        if key not in _saved:
+            _saved[key] = gm.GMFlow.upsample_flow
+        gm.GMFlow.upsample_flow = upsample_flow
+        done.append("model.EMIP_short.motion.gmflow.gmflow.GMFlow.upsample_flow")
+    except Exception:
+        if strict:
+            raise
     return done
 
 
@@ -65,5 +79,9 @@ def uninstall():
     for (mod_name, attr), orig in list(_saved.items()):
         mod = sys.modules.get(mod_name)
         if mod is not None:
-            setattr(mod, attr, orig)
+            if "." in attr:                                   # Class.method
+                cls_name, meth = attr.split(".")
+                setattr(getattr(mod, cls_name), meth, orig)
+            else:
+                setattr(mod, attr, orig)
         del _saved[(mod_name, attr)]

@@ -149,6 +149,16 @@ int emip_memory_read_bwd(const float* m_in, const float* m_out, const float* q_i
                          const float* lse, const float* dmem, long long dmem_stride_b, float* dm_in, float* dm_out,
                          float* dq_in, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
 
+/* ---- f4: convex x8 upsampling of the coarse flow -------------------------------- */
+/* Replaces model/EMIP_short/motion/gmflow/gmflow.py:64-77, the part of GMFlow.upsample_flow after
+ * `mask = self.upsampler(concat)`: softmax over the 9 taps, 3x3 unfold of k*flow, weighted sum, pixel shuffle.
+ *   flow [B,2,h,w]   mask [B,9*k*k,h,w] (channel = tap*k*k + ky*k + kx)   out, dout [B,2,k*h,k*w]   k must be 8
+ * Backward: dflow [B,2,h,w] and dmask [B,9*k*k,h,w] are overwritten; workspace >= emip_convex_upsample_workspace(). */
+size_t emip_convex_upsample_workspace(int B, int h, int w);
+int emip_convex_upsample_fwd(const float* flow, const float* mask, float* out, int B, int h, int w, int k, void* stream);
+int emip_convex_upsample_bwd(const float* flow, const float* mask, const float* dout, float* dflow, float* dmask,
+                             void* workspace, size_t ws_bytes, int B, int h, int w, int k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,3 +216,28 @@ def memory_read(m_in, m_out, q_in, q_out, return_prob=False):
     mem = torch.bmm(m_out.reshape(b, do, t * h * w), p).reshape(b, do, h, w)
     out = torch.cat([mem, q_out.reshape(b, do, h, w)], dim=1)         # LTM.py:66
     return out, (p if return_prob else None)
+
+
+# --------------------------------------------------------------------------- f4
+def upsample_flow_convex(flow, mask, upsample_factor=8):
+    """Convex upsampling of a coarse flow with a learned 9-way mask (RAFT-style).
+
+    flow [B,2,h,w]; mask [B,9*K*K,h,w] = the output of GMFlow.upsampler (channel = n*K*K + ky*K + kx, n = 3x3 tap,
+    row-major); returns [B,2,K*h,K*w]:  out[c, K*y+ky, K*x+kx] = sum_n softmax_n(mask)[n,ky,kx,y,x] * K*flow[c, y+dy_n, x+dx_n]
+    with zero padding (F.unfold(padding=1)).
+
+    Reference: model/EMIP_short/motion/gmflow/gmflow.py:64-77 (the part after ``mask = self.upsampler(concat)``).
+    """
+    b, c, h, w = flow.shape
+    k = upsample_factor
+    m = mask.reshape(b, 9, k, k, h, w)
+    m = m - m.max(dim=1, keepdim=True).values
+    p = torch.exp(m)
+    p = p / p.sum(dim=1, keepdim=True)                                # gmflow.py:69
+    fp = torch.zeros(b, c, h + 2, w + 2, dtype=flow.dtype, device=flow.device)
+    fp[:, :, 1:-1, 1:-1] = k * flow                                   # gmflow.py:71 (unfold of K*flow, padding 1)
+    out = torch.zeros(b, c, k, k, h, w, dtype=flow.dtype, device=flow.device)
+    for n in range(9):
+        dy, dx = n // 3, n % 3
+        out = out + p[:, n].unsqueeze(1) * fp[:, :, dy:dy + h, dx:dx + w].reshape(b, c, 1, 1, h, w)   # gmflow.py:74
+    return out.permute(0, 1, 4, 2, 5, 3).reshape(b, c, k * h, k * w)  # gmflow.py:75-77

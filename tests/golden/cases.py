@@ -91,6 +91,18 @@ A5_CASES = {
 }
 
 
+F4_CASES = {
+    "f4_small": dict(b=2, h=5, w=7, fscale=3.0, mscale=2.0, seed=61, full=False),
+    "f4_full": dict(b=1, h=44, w=44, fscale=12.0, mscale=1.5, seed=62, full=True),
+}
+
+
+def f4_inputs(s):
+    return dict(flow=randn(s["seed"], (s["b"], 2, s["h"], s["w"]), s["fscale"]),
+                mask=randn(s["seed"] + 1000, (s["b"], 576, s["h"], s["w"]), s["mscale"]),
+                wout=randn(s["seed"] + 2000, (s["b"], 2, 8 * s["h"], 8 * s["w"])))
+
+
 def a1_inputs(s):
     shp = (s["b"], s["c"], s["h"], s["w"])
     n = s["h"] * s["w"]

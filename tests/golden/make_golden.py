@@ -104,6 +104,26 @@ def gen_a5():
                         **{"d" + k: cases.pack(v.grad, s["full"]) for k, v in t.items()}))
 
 
+def gen_f4():
+    """Convex x8 upsampling: the reference method GMFlow.upsample_flow with the upsampler conv replaced by a stub
+    that returns the seeded mask (the conv itself is out of scope)."""
+    from model.EMIP_short.motion.gmflow.gmflow import GMFlow
+
+    class Stub:
+        upsample_factor = 8
+
+    for name, s in cases.F4_CASES.items():
+        d = cases.f4_inputs(s)
+        flow = d["flow"].clone().requires_grad_(True)
+        mask = d["mask"].clone().requires_grad_(True)
+        stub = Stub()
+        stub.upsampler = lambda concat, m=mask: m
+        out = GMFlow.upsample_flow(stub, flow, torch.zeros(s["b"], 128, s["h"], s["w"]))
+        (out * d["wout"]).sum().backward()
+        save(name, dict(spec=s, out=cases.pack(out, s["full"]), dflow=cases.pack(flow.grad, False),
+                        dmask=cases.pack(mask.grad, s["full"])))
+
+
 def gen_c1():
     """config c1: CoUpdater eval forward on one seeded 352x352 pair; capture the a1/a2 call in situ."""
     from model.EMIP_short.model import CoUpdater
@@ -144,6 +164,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

@@ -285,3 +285,38 @@ def test_a5_memory_read_t5_vs_oracle():
     with torch.no_grad():
         out, _ = Memory()(dev(d["m_in"]), dev(d["m_out"]), dev(d["q_in"]), dev(d["q_out"]))
     assert rel(out, ref) < TOL_EXACT
+
+
+# ----------------------------------------------------------------------------- f4 (convex x8 upsampling)
+@pytest.mark.parametrize("name", list(cases.F4_CASES))
+def test_f4_convex_upsample_golden(golden, name):
+    from emip_b200.upsample import upsample_flow_convex
+    g = golden(name)
+    d = cases.f4_inputs(cases.F4_CASES[name])
+    flow = dev(d["flow"]).requires_grad_(True)
+    mask = dev(d["mask"]).requires_grad_(True)
+    out = upsample_flow_convex(flow, mask)
+    e = cases.check_packed(out, g["out"], TOL_EXACT, "out")
+    (out * dev(d["wout"])).sum().backward()
+    e1 = cases.check_packed(flow.grad, g["dflow"], 1e-4, "dflow")
+    e2 = cases.check_packed(mask.grad, g["dmask"], 1e-4, "dmask")
+    print(f"{name}: out {e:.2e} dflow {e1:.2e} dmask {e2:.2e}")
+
+
+def test_f4_convex_upsample_properties_batch():
+    """B=32 (config c2's 2B): uniform mask = 3x3 box filter of 8*flow; deterministic backward."""
+    from emip_b200.upsample import upsample_flow_convex
+    B, h, w = 32, 44, 44
+    g = torch.Generator(device="cuda").manual_seed(9)
+    flow = 5 * torch.randn(B, 2, h, w, device="cuda", generator=g)
+    out = upsample_flow_convex(flow, torch.zeros(B, 576, h, w, device="cuda"))
+    box = torch.nn.functional.avg_pool2d(8 * flow, 3, 1, 1, count_include_pad=True)       # zero padding, /9
+    assert rel(out, box.repeat_interleave(8, 2).repeat_interleave(8, 3)) < 1e-6
+    mask = torch.randn(B, 576, h, w, device="cuda", generator=g).requires_grad_(True)
+    f2 = flow.clone().requires_grad_(True)
+    wout = torch.randn(B, 2, 8 * h, 8 * w, device="cuda", generator=g)
+    upsample_flow_convex(f2, mask).backward(wout)
+    g1 = (f2.grad.clone(), mask.grad.clone())
+    f2.grad = None; mask.grad = None
+    upsample_flow_convex(f2, mask).backward(wout)
+    assert torch.equal(g1[0], f2.grad) and torch.equal(g1[1], mask.grad)

@@ -127,3 +127,16 @@ def test_a5_memory_read(golden, name):
     (out * d["wout"]).sum().backward()
     for k, v in t.items():
         cases.check_packed(v.grad, g["d" + k], GTOL, "d" + k)
+
+
+@pytest.mark.parametrize("name", list(cases.F4_CASES))
+def test_f4_convex_upsample(golden, name):
+    g = golden(name)
+    d = cases.f4_inputs(cases.F4_CASES[name])
+    flow = d["flow"].clone().requires_grad_(True)
+    mask = d["mask"].clone().requires_grad_(True)
+    out = O.upsample_flow_convex(flow, mask)
+    cases.check_packed(out, g["out"], TOL, "out")
+    (out * d["wout"]).sum().backward()
+    cases.check_packed(flow.grad, g["dflow"], GTOL, "dflow")
+    cases.check_packed(mask.grad, g["dmask"], GTOL, "dmask")
