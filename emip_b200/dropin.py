@@ -30,6 +30,8 @@ _PATCHES = (
     ("model.EMIP_long.LTM", "Memory", "emip_b200.memory", "Memory"),
     ("loss.warp_utils", "flow_warp", "emip_b200.warp", "flow_warp"),
     ("loss.loss_flow", "flow_warp", "emip_b200.warp", "flow_warp"),
+    ("loss.warp_utils", "get_occu_mask_backward", "emip_b200.warp", "get_occu_mask_backward"),
+    ("loss.loss_flow", "get_occu_mask_backward", "emip_b200.warp", "get_occu_mask_backward"),
 )
 _saved = {}
 

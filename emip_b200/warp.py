@@ -2,7 +2,8 @@
 import torch
 
 from . import _lib
-from ._lib import I, LL, ptr, stream_ptr
+from ._lib import F as CF, I, LL, SZ, ptr, stream_ptr
+from ._ws import workspace
 
 _PAD = {"border": 0, "zeros": 1}
 
@@ -61,3 +62,27 @@ def flow_warp(x, flow12, pad="border", mode="bilinear"):
     if flow12.shape[0] != x.shape[0] or flow12.shape[1] != 2 or flow12.shape[2:] != x.shape[2:]:
         raise ValueError(f"flow12 {tuple(flow12.shape)} does not match x {tuple(x.shape)}")
     return _FlowWarp.apply(x, flow12, _PAD[pad])
+
+
+def get_occu_mask_backward(flow21, th=0.2):
+    """Occlusion mask from the backward flow: drop-in for reference loss/warp_utils.py:106-112.
+
+    Returns a float [B,1,H,W] tensor, 1 where the pixel receives less than ``th`` of splatted mass.  ``flow21`` may be
+    a channel slice of the [B,4,H,W] flow (loss_flow.py:95-96); no copy is made.  Not differentiable, as in the
+    reference.
+    """
+    import ctypes
+    if not flow21.is_cuda:
+        raise _lib.EmipError("emip_b200.get_occu_mask_backward needs CUDA tensors (no CPU fallback)")
+    if flow21.dtype != torch.float32 or flow21.dim() != 4 or flow21.shape[1] != 2:
+        raise TypeError("flow21 must be a float32 [B,2,H,W] tensor")
+    flow21 = flow21.detach()
+    B, _, H, W = flow21.shape
+    flow21, sb, sc = _flow_strides(flow21)
+    L = _lib.lib()
+    L.emip_occu_mask_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_occu_mask_workspace(I(B), I(H), I(W)), flow21.device, align=256)
+    mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=flow21.device)
+    _lib.check(L.emip_occu_mask_backward(ptr(flow21), ptr(mask), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(H), I(W), LL(sb),
+                                         LL(sc), CF(th), stream_ptr()), "emip_occu_mask_backward")
+    return mask

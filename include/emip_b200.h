@@ -159,6 +159,15 @@ int emip_convex_upsample_fwd(const float* flow, const float* mask, float* out, i
 int emip_convex_upsample_bwd(const float* flow, const float* mask, const float* dout, float* dflow, float* dmask,
                              void* workspace, size_t ws_bytes, int B, int h, int w, int k, void* stream);
 
+/* ---- f3: backward-flow occlusion mask of the photometric loss ----------------------- */
+/* Replaces loss/warp_utils.py:106-112 get_occu_mask_backward(flow21, th) (get_corresponding_map :26-80): forward
+ * splat of every pixel's bilinear weights along flow21, clamp to [0,1], compare with th.  Not differentiable.
+ *   flow21 addressed like flow in emip_flow_warp_fwd (channel-slice strides)   mask [B,1,H,W] (1 = occluded)
+ *   workspace >= emip_occu_mask_workspace() holds the splat accumulator. */
+size_t emip_occu_mask_workspace(int B, int H, int W);
+int emip_occu_mask_backward(const float* flow21, float* mask, void* workspace, size_t ws_bytes, int B, int H, int W,
+                            long long flow_stride_b, long long flow_stride_c, float th, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,3 +241,32 @@ def upsample_flow_convex(flow, mask, upsample_factor=8):
         dy, dx = n // 3, n % 3
         out = out + p[:, n].unsqueeze(1) * fp[:, :, dy:dy + h, dx:dx + w].reshape(b, c, 1, 1, h, w)   # gmflow.py:74
     return out.permute(0, 1, 4, 2, 5, 3).reshape(b, c, k * h, k * w)  # gmflow.py:75-77
+
+
+# --------------------------------------------------------------------------- f3
+def corresponding_map(flow21):
+    """Forward splat of unit mass along flow21: every source pixel (i, j) deposits its bilinear weights on the four
+    integer neighbours of (j + flow_x, i + flow_y); taps outside the image are dropped.  Returns [B,1,H,W].
+
+    Reference: loss/warp_utils.py:26-80 (get_corresponding_map on base_grid + flow21, :106-110).
+    """
+    b, _, h, w = flow21.shape
+    dt = flow21.dtype
+    x = torch.arange(w, dtype=dt).view(1, 1, w) + flow21[:, 0]
+    y = torch.arange(h, dtype=dt).view(1, h, 1) + flow21[:, 1]
+    x1, y1 = torch.floor(x), torch.floor(y)
+    out = torch.zeros(b, h * w, dtype=dt)
+    for xc, yc in ((x1 + 1, y1 + 1), (x1 + 1, y1), (x1, y1 + 1), (x1, y1)):      # warp_utils.py:58-66 order
+        ok = (xc >= 0) & (xc <= w - 1) & (yc >= 0) & (yc <= h - 1)
+        xcl, ycl = xc.clamp(0, w - 1), yc.clamp(0, h - 1)
+        val = (1 - (x - xcl).abs()) * (1 - (y - ycl).abs()) * ok.to(dt)
+        out.scatter_add_(1, (xcl + ycl * w).long().reshape(b, -1), val.reshape(b, -1))
+    return out.view(b, 1, h, w)
+
+
+def occu_mask_backward(flow21, th=0.2):
+    """1 where fewer than ``th`` of a pixel's mass is hit by the backward flow (occluded), else 0.
+
+    Reference: loss/warp_utils.py:106-112.
+    """
+    return (corresponding_map(flow21).clamp(0.0, 1.0) < th).to(flow21.dtype)

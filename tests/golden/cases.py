@@ -103,6 +103,16 @@ def f4_inputs(s):
                 wout=randn(s["seed"] + 2000, (s["b"], 2, 8 * s["h"], 8 * s["w"])))
 
 
+F3_CASES = {
+    "f3_small": dict(b=2, h=9, w=11, sigma=2.0, seed=71),
+    "f3_mid": dict(b=2, h=40, w=56, sigma=6.0, seed=72),
+}
+
+
+def f3_inputs(s):
+    return dict(flow4=randn(s["seed"], (s["b"], 4, s["h"], s["w"]), s["sigma"]))
+
+
 def a1_inputs(s):
     shp = (s["b"], s["c"], s["h"], s["w"])
     n = s["h"] * s["w"]

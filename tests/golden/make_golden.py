@@ -124,6 +124,15 @@ def gen_f4():
                         dmask=cases.pack(mask.grad, s["full"])))
 
 
+def gen_f3():
+    from loss.warp_utils import get_occu_mask_backward, get_corresponding_map, mesh_grid
+    for name, s in cases.F3_CASES.items():
+        fl = cases.f3_inputs(s)["flow4"][:, 2:]                     # the slice loss_flow.py:95 passes
+        base = mesh_grid(s["b"], s["h"], s["w"]).type_as(fl)
+        save(name, dict(spec=s, mask=cases.pack(get_occu_mask_backward(fl, th=0.2), False),
+                        corr_map=cases.pack(get_corresponding_map(base + fl), False)))
+
+
 def gen_c1():
     """config c1: CoUpdater eval forward on one seeded 352x352 pair; capture the a1/a2 call in situ."""
     from model.EMIP_short.model import CoUpdater
@@ -164,6 +173,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f3", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

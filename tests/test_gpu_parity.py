@@ -320,3 +320,28 @@ def test_f4_convex_upsample_properties_batch():
     f2.grad = None; mask.grad = None
     upsample_flow_convex(f2, mask).backward(wout)
     assert torch.equal(g1[0], f2.grad) and torch.equal(g1[1], mask.grad)
+
+
+# ----------------------------------------------------------------------------- f3 (occlusion mask)
+@pytest.mark.parametrize("name", list(cases.F3_CASES))
+def test_f3_occlusion_mask_golden(golden, name):
+    from emip_b200.warp import get_occu_mask_backward
+    g = golden(name)
+    fl4 = dev(cases.f3_inputs(cases.F3_CASES[name])["flow4"])
+    mask = get_occu_mask_backward(fl4[:, 2:], th=0.2).cpu()
+    ref, cm = g["mask"]["full"], g["corr_map"]["full"]
+    assert mask.shape == ref.shape
+    differ = (mask != ref) & ((cm - 0.2).abs() > 1e-5)              # only threshold ties may differ (atomic order)
+    assert not differ.any(), int(differ.sum())
+    assert 0.02 < mask.mean().item() < 0.9                          # the case exercises both classes
+
+
+def test_f3_occlusion_mask_properties_full():
+    """352x352, B=64: zero flow -> nothing occluded; a uniform shift occludes exactly the vacated border."""
+    from emip_b200.warp import get_occu_mask_backward
+    B, H, W = 64, 352, 352
+    z = torch.zeros(B, 2, H, W, device="cuda")
+    assert get_occu_mask_backward(z).sum().item() == 0
+    z[:, 0] = 3.0                                                   # everything moves 3 px to the right
+    m = get_occu_mask_backward(z)
+    assert m[..., :3].min().item() == 1.0 and m[..., 3:].sum().item() == 0

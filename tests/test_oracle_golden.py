@@ -140,3 +140,15 @@ def test_f4_convex_upsample(golden, name):
     (out * d["wout"]).sum().backward()
     cases.check_packed(flow.grad, g["dflow"], GTOL, "dflow")
     cases.check_packed(mask.grad, g["dmask"], GTOL, "dmask")
+
+
+@pytest.mark.parametrize("name", list(cases.F3_CASES))
+def test_f3_occlusion_mask(golden, name):
+    g = golden(name)
+    fl = cases.f3_inputs(cases.F3_CASES[name])["flow4"][:, 2:]
+    cm = O.corresponding_map(fl)
+    cases.check_packed(cm, g["corr_map"], TOL, "corr_map")
+    mask = O.occu_mask_backward(fl, 0.2)
+    ref = g["mask"]["full"]
+    differ = (mask != ref) & ((cm - 0.2).abs() > 1e-5)              # only threshold ties may differ (summation order)
+    assert not differ.any()
