@@ -11,6 +11,8 @@
 // The fp32 normalise -> un-normalise round trip of the reference
 // (nx = 2u/(W-1)-1 ; ix = ((nx+1)/2)(W-1)) is reproduced in the same order.
 #include "common.cuh"
+#include "flow_warp_common.cuh"
+#include "flow_warp_staged.cuh"
 #include "../../include/emip_b200.h"
 
 namespace {
@@ -81,7 +83,11 @@ __device__ __forceinline__ Tap make_tap(const Coord& c, int H, int W, float& wx,
 // All 2*ROWS flow loads are issued first, then all 4*C*ROWS gathers, then the stores: ~50 independent loads in
 // flight per thread keep HBM busy at 16 resident warps per SM.  Vertically adjacent rows of the tile share tap lines
 // through L1 (taps come through the read-only path and are allowed to allocate in L1).
-constexpr int ROWS = 4;
+using k3::ROWS;
+using k3::FastCoord;
+using k3::fast_coord;
+using k3::div_rn;
+using k3::opaque;
 
 template <bool BORDER, int CT>
 __global__ void __launch_bounds__(256)
@@ -272,43 +278,6 @@ flow_warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ flow
 //  * after the border clamp every tap is inside the image except x1 = W (y1 = H), which only occurs with weight
 //    exactly 0: the index is clamped instead of masked;
 //  * in-plane offsets are 32-bit.
-struct FastCoord {
-  unsigned off;          // in-plane offset of the top-left tap (y0 * W + x0); the 2x2 block is off, off+1, off+W, off+W+1
-  float wx, wy, gmx, gmy;
-};
-
-__device__ __forceinline__ float div_rn(float a, float b, float rc) {
-  float q = a * rc;
-  return fmaf(fmaf(-q, b, a), rc, q);
-}
-
-// x0 is clamped to W-2 (y0 to H-2) so that the 2x2 tap block is always inside the image: at ix = W-1 this gives
-// (x0, wx) = (W-2, 1) instead of the reference's (W-1, 0) -- the same interpolated value and the same gradients.
-__device__ __forceinline__ FastCoord fast_coord(float u, float v, int H, int W, float wm1, float hm1, float rcw,
-                                                float rch) {
-  // warp_utils.py:21-22 then ATen grid_sampler_unnormalize (align_corners=True)
-  float ix = (((div_rn(2.0f * u, wm1, rcw) - 1.0f) + 1.0f) * 0.5f) * wm1;
-  float iy = (((div_rn(2.0f * v, hm1, rch) - 1.0f) + 1.0f) * 0.5f) * hm1;
-  FastCoord c;
-  c.gmx = (ix > 0.0f && ix < wm1) ? 1.0f : 0.0f;     // ATen clip_coordinates_set_grad
-  c.gmy = (iy > 0.0f && iy < hm1) ? 1.0f : 0.0f;
-  ix = fminf(fmaxf(ix, 0.0f), wm1);
-  iy = fminf(fmaxf(iy, 0.0f), hm1);
-  const int x0 = min(__float2int_rd(ix), W - 2), y0 = min(__float2int_rd(iy), H - 2);
-  c.wx = ix - (float)x0;
-  c.wy = iy - (float)y0;
-  c.off = (unsigned)(y0 * W + x0);
-  return c;
-}
-
-// Makes a per-sample base pointer opaque to the optimiser: otherwise nvcc folds the 64-bit batch offset into every
-// tap index and spends four instructions per address (IMAD.WIDE + IADD3 + LEA + LEA.HI.X) instead of one IMAD.WIDE.
-template <typename T>
-__device__ __forceinline__ T* opaque(T* p) {
-  asm volatile("" : "+l"(p));
-  return p;
-}
-
 // Persistent CTAs loop over 32 x 32 pixel tiles (rows of a thread 8 apart, lanes on consecutive x).  The flow of the
 // NEXT tile is requested right after the gathers of the current tile have been issued, so the dependent chain
 // flow -> address -> gather of one tile overlaps the gather latency of the previous one (ncu r1h: the single-shot
@@ -429,10 +398,20 @@ flow_warp_border3_kernel(const float* __restrict__ x, const float* __restrict__ 
 }
 
 int g_k3_ctas_per_sm = 2;
+bool g_k3_staged = true;
 }  // namespace
 
-// Experiment switch (tools/k3_bench.py): persistent CTAs per SM of the border/C=3 fast path.
-extern "C" void emip_debug_flow_warp_variant(int v) { g_k3_ctas_per_sm = v > 0 ? v : 2; }
+extern "C" void emip_debug_flow_warp_staged_ctas(int v);
+extern "C" void emip_debug_flow_warp_staged_policy(int v);
+// Experiment switch (tools/k3_bench.py): v in 1..99 = direct-gather fast path with v persistent CTAs per SM;
+// 100 + v = shared-memory-staged fast path (flow_warp_staged.cu) with v persistent CTAs per SM and the adaptive
+// fallback to the direct kernel; 200 + v = staged kernel always; 0 = default (adaptive, 2 CTAs per SM).
+extern "C" void emip_debug_flow_warp_variant(int v) {
+  if (v >= 200) { g_k3_staged = true; emip_debug_flow_warp_staged_policy(1); emip_debug_flow_warp_staged_ctas(v - 200); }
+  else if (v >= 100) { g_k3_staged = true; emip_debug_flow_warp_staged_policy(0); emip_debug_flow_warp_staged_ctas(v - 100); }
+  else if (v > 0) { g_k3_staged = false; g_k3_ctas_per_sm = v; }
+  else { g_k3_staged = true; g_k3_ctas_per_sm = 2; emip_debug_flow_warp_staged_policy(0); emip_debug_flow_warp_staged_ctas(2); }
+}
 
 extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                                   long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream) {
@@ -450,6 +429,10 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
   if (C == 3 && border && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
     const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    int rc = EMIP_ENOSYS;
+    if (g_k3_staged) rc = flow_warp_staged_launch(false, x, flow, nullptr, out, B, H, W, flow_stride_b, flow_stride_c, st);
+    if (rc != EMIP_OK && rc != EMIP_ENOSYS) return rc;
+    if (rc == EMIP_ENOSYS)
     flow_warp_border3_kernel<false><<<grid, 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b, flow_stride_c,
                                                          tiles_x, tiles_y, (int)nblk, rcw, rch);
   } else if (C == 3) { if (border) LAUNCH(true, 3); else LAUNCH(false, 3); }
@@ -478,6 +461,10 @@ extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float
   if (C == 3 && border && dx == nullptr && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
     const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    int rc = EMIP_ENOSYS;
+    if (g_k3_staged) rc = flow_warp_staged_launch(true, x, flow, dout, dflow, B, H, W, flow_stride_b, flow_stride_c, st);
+    if (rc != EMIP_OK && rc != EMIP_ENOSYS) return rc;
+    if (rc == EMIP_ENOSYS)
     flow_warp_border3_kernel<true><<<grid, 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b, flow_stride_c, tiles_x,
                                                         tiles_y, (int)nblk, rcw, rch);
   } else if (C == 3) {

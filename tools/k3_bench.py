@@ -53,8 +53,9 @@ def run(dev, hbm_peak, iters=50):
                                             LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "bwd")
         r = {}
         for tag, fn, nbytes in (("fwd", fwd, fw_bytes), ("bwd", bwd, bw_bytes)):
-            for _ in range(5):
+            for _ in range(10):
                 fn()
+            torch.cuda.synchronize()      # lets the launcher's kernel-choice feedback land (see flow_warp_staged.cu)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(iters):
@@ -74,10 +75,10 @@ if __name__ == "__main__":
     if os.path.exists(p):
         pk = json.load(open(p))["hbm_gbs"]
     import sys as _sys
-    variants = [int(a, 0) for a in _sys.argv[1:]] or [2]
+    variants = [int(a, 0) for a in _sys.argv[1:]] or [0]
     for variant in variants:
       _lib.lib().emip_debug_flow_warp_variant(variant)
-      print("persistent CTAs per SM:", variant)
+      print("variant (0 = default: staged + adaptive; 1-99 direct, 1xx staged adaptive, 2xx staged always):", variant)
       r = run(torch.device("cuda", 0), pk)
       for k, v in r.items():
           print(f"{k:11s} fwd {v['fwd']['launch_ms']*1e3:7.1f} us {v['fwd']['achieved']:7.0f} GB/s ({100*v['fwd']['frac']:4.1f}%)   "
