@@ -16,7 +16,7 @@ size_t d_bytes(int B, int N) { return emip_align_up(sizeof(float) * (size_t)B * 
 
 extern "C" size_t emip_flow_attn_workspace(int B, int N, int C) {
   if (B < 0 || N <= 0 || C <= 0) return 0;
-  return d_bytes(B, N) + 2 * match_tc_split_bytes(B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N);
+  return d_bytes(B, N) + 2 * match_tc_split_bytes(B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N) + match_tc_streamk_bytes(B, N, N);
 }
 
 extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse,
@@ -32,7 +32,8 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
   cudaStream_t st = (cudaStream_t)stream;
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
     size_t sb = match_tc_split_bytes(B, N, C);
-    if (workspace == nullptr || ws_bytes < d_bytes(B, N) + 2 * sb || reinterpret_cast<uintptr_t>(workspace) % 1024) {
+    const size_t sk_off = d_bytes(B, N) + 2 * sb + pair_bwd_tc_chn_bytes(2 * B, N), sk_bytes = match_tc_streamk_bytes(B, N, N);
+    if (workspace == nullptr || ws_bytes < sk_off + sk_bytes || reinterpret_cast<uintptr_t>(workspace) % 1024) {
       emip_set_error("flow_attn_fwd: workspace too small or not 1024-byte aligned");
       return EMIP_ENOMEM;
     }
@@ -47,6 +48,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
     a.out = out; a.lse = lse; a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0; a.y_mod = B;
     a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
     a.sqrt_c = sqrtf((float)C);
+    a.sk_ws = static_cast<char*>(workspace) + sk_off; a.sk_bytes = sk_bytes;
     return match_tc_fwd(a, st);
   }
   PairFwdArgs a = {};

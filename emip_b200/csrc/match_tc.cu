@@ -12,7 +12,9 @@
 // mode, 2e-2 tolerance).  Softmax statistics are always fp32.
 //
 // CTA = 576 threads, persistent, one CTA per SM (225 KB smem, all 512 TMEM columns).
-// A work item is (problem, PAIR of 128-row query tiles): every key chunk that TMA
+// Scheduling is stream-K: the units (item, key tile) are dealt to the CTAs in equal contiguous spans, so every SM gets
+// the same amount of MMA work whatever the batch (r1s: item-granular scheduling left 13 % of the SM-time idle at c2,
+// 256 items on 148 SMs).  A work item is (problem, PAIR of 128-row query tiles): every key chunk that TMA
 // brings in is used by both query tiles, which halves the L2->SM operand traffic
 // per MMA (1 MB per 256 rows; the first version of this kernel, one tile per CTA, asked
 // L2 for 11 TB/s at the MMA-bound rate).
@@ -77,6 +79,11 @@ struct KParams {
   int grid_w, sub_grid, terms, s_mode;   // s_mode: 0 none, 1 TMA bulk store, 2 direct st.global
   float inv_sqrt_c;
   unsigned long long* prof;   // optional [gridDim.x][8] wait-cycle counters (emip_match_tc_set_profile_buffer)
+  // stream-K scheduling: the (item, key tile) units are dealt to the CTAs in equal contiguous spans; a row whose keys
+  // are covered by several CTAs leaves its online-softmax state in `part` and the last CTA to arrive merges them
+  float4* part;          // [n_items][pmax][2 tiles][128 rows] (m, l, sx, sy)
+  unsigned* cnt;         // [n_items] arrival counters, zero before the launch and left at zero
+  int pmax;
 };
 
 // Online-softmax update of one row with 32 score columns (raw accumulator values, scale folded into c2).
@@ -233,7 +240,7 @@ __device__ __forceinline__ void emit_chunk_tma(const uint32_t (&r)[32], float sc
   }
 }
 
-template <int NSMX>
+template <int NSMX, bool SK>
 __global__ void __launch_bounds__((NSMX + 2) * 32, 1)
 match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                     const __grid_constant__ CUtensorMap map_s, KParams p) {
@@ -259,6 +266,24 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int nkt = (p.nk + TN - 1) / TN;
   const int n_items = p.nb * npair;
   const int nch = (p.terms == 3) ? NCHUNK : 2;        // single-pass mode streams the hi halves only
+  // this CTA's span of (item, key tile) units, walked as visits (item, kt0, kt1)
+  // SK: `u` runs over this CTA's span of units; else `u` is the item index, grid-strided
+  const long long units = (long long)n_items * nkt;
+  const int u_begin = SK ? (int)(units * blockIdx.x / gridDim.x) : (int)blockIdx.x;
+  const int u_end = SK ? (int)(units * (blockIdx.x + 1) / gridDim.x) : n_items;
+  auto next_visit = [&](int& u, int& item, int& kt0, int& kt1) {
+    if constexpr (SK) {
+      item = u / nkt;
+      kt0 = u - item * nkt;
+      kt1 = min(nkt, kt0 + (u_end - u));
+      u += kt1 - kt0;
+    } else {
+      item = u;
+      kt0 = 0;
+      kt1 = nkt;
+      u += (int)gridDim.x;
+    }
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(q_full(0), 1);
@@ -288,7 +313,9 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       uint32_t kphase = 0;
       uint32_t it = 0;
       long long w_qe = 0, w_ke = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int u = u_begin; u < u_end; ++it) {
+        int item, kt0, kt1;
+        next_visit(u, item, kt0, kt1);
         const int prob = item / npair, qt0 = 2 * (item % npair);
         const int by = (prob + p.y_shift) % p.y_mod;
         w_qe += mbar_wait(q_empty, (it & 1) ^ 1);
@@ -301,7 +328,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                           (qt0 + g) * TM, prob);
           }
         }
-        for (int kt = 0; kt < nkt; ++kt) {
+        for (int kt = kt0; kt < kt1; ++kt) {
           for (int c = 0; c < nch; ++c) {
             w_ke += mbar_wait(k_empty(stage), kphase ^ 1);
             if (leader) {
@@ -334,8 +361,10 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       // suspends the warp with a coarse wake-up and the tensor pipe drains meanwhile -- waits stay between chunks;
       // (3) the UMMAs of the two query tiles are interleaved one by one so that consecutive instructions
       // accumulate into different TMEM tiles.
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        for (int kt = 0; kt < nkt; ++kt, ++tile) {
+      for (int u = u_begin; u < u_end; ++it) {
+        int item, kt0, kt1;
+        next_visit(u, item, kt0, kt1);
+        for (int kt = kt0; kt < kt1; ++kt, ++tile) {
           const int buf = tile & 1;
           const uint32_t use = tile >> 1;
           const uint32_t idesc = (kt == nkt - 1) ? idesc_tail : idesc_full;
@@ -345,7 +374,7 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
               // the accumulators of this key step must have been drained by the softmax warps (two steps ago)
               w_se += mbar_wait(s_empty(0, buf), (use & 1) ^ 1);
               w_se += mbar_wait(s_empty(1, buf), (use & 1) ^ 1);
-              if (kt == 0) {
+              if (kt == kt0) {
                 w_qf += mbar_wait(q_full(0), it & 1);
                 w_qf += mbar_wait(q_full(1), it & 1);
               }
@@ -413,7 +442,9 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     int cur_v = -1;
     long long w_sf = 0;
     const long long t_begin = clock64();
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int u = u_begin; u < u_end;) {
+      int item, kt0, kt1;
+      next_visit(u, item, kt0, kt1);
       const int prob = item / npair, qt = 2 * (item % npair) + g;
       const int row = qt * TM + r_in_tile;
       if (!grid_mode) {
@@ -434,9 +465,9 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const bool emit = p.s_mode != 0 && prob >= p.s_first && prob < p.s_first + p.s_count && row0w < p.nq;
       const int slab = prob - p.s_first;
       // grid position of this warp's first column of the current key tile (matching mode)
-      int gx = grid_mode ? cbeg % p.grid_w : 0, gy = grid_mode ? cbeg / p.grid_w : 0;
+      int gx = grid_mode ? (kt0 * TN + cbeg) % p.grid_w : 0, gy = grid_mode ? (kt0 * TN + cbeg) / p.grid_w : 0;
       float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;
-      for (int kt = 0; kt < nkt; ++kt, ++tile) {
+      for (int kt = kt0; kt < kt1; ++kt, ++tile) {
         const int buf = tile & 1;
         const uint32_t use = tile >> 1;
         w_sf += mbar_wait(s_full(g, buf), use & 1);
@@ -539,7 +570,42 @@ match_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           m = mm;
         }
       }
-      if (half == 0 && row < p.nq) {
+      if (SK && (kt0 != 0 || kt1 != nkt)) {
+        // This CTA saw only part of the item's keys.  The CTAs covering the item are consecutive: first .. last.
+        const long long ub = (long long)item * nkt;
+        const int first = (int)(((ub + 1) * gridDim.x + units - 1) / units) - 1;
+        const int last = (int)(((ub + nkt) * gridDim.x + units - 1) / units) - 1;
+        const int parts = last - first + 1;
+        float4* slab = p.part + (size_t)item * p.pmax * (2 * TM);
+        if (half == 0) slab[((int)blockIdx.x - first) * (2 * TM) + g * TM + r_in_tile] = make_float4(m, l, sx, sy);
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(SMX_THREADS) : "memory");
+        volatile uint32_t* flag = tmem_slot + 2;
+        if (st == 0) {
+          const bool is_last = atomicAdd(p.cnt + item, 1u) == (unsigned)(parts - 1);
+          if (is_last) p.cnt[item] = 0;                  // left at zero for the next launch
+          *flag = is_last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SMX_THREADS) : "memory");
+        if (*flag == 0u) {
+          l = 0.f;                                       // somebody else finishes these rows
+        } else {
+          __threadfence();
+          // merge in part order, whoever arrives last: the result does not depend on the schedule
+          m = -INFINITY; l = 0.f; sx = 0.f; sy = 0.f;
+          if (half == 0)
+            for (int q = 0; q < parts; ++q) {
+              const float4 o = __ldcg(slab + q * (2 * TM) + g * TM + r_in_tile);
+              const float mm = fmaxf(m, o.x);
+              const float a = ex2f((m - mm) * c2), b = ex2f((o.x - mm) * c2);
+              l = l * a + o.y * b;
+              sx = sx * a + o.z * b;
+              sy = sy * a + o.w * b;
+              m = mm;
+            }
+        }
+      }
+      if (half == 0 && row < p.nq && (!SK || l > 0.f)) {
         float ex = sx / l, ey = sy / l;
         if (p.sub_grid) { ex -= (float)(row % p.grid_w); ey -= (float)(row / p.grid_w); }
         p.out[((size_t)prob * 2 + 0) * p.nq + row] = ex;
@@ -652,6 +718,7 @@ int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk, bool 
 
 static unsigned long long* g_prof = nullptr;
 static int g_softmax_warps = 0;
+static int g_schedule = 0;   // 0 = choose, 1 = stream-K spans, 2 = grid-strided items
 // Diagnostics: force 8 or 16 softmax warps per CTA (tools/k1_roles.py compares them); 0 = choose by mode:
 // 8 for the 3-term split (UMMA-bound: fewer warps = no spills, less smem/L1 traffic next to the operand reads),
 // 16 for single-pass bf16 (softmax-bound: r1p 70 vs 76 us).
@@ -659,12 +726,28 @@ extern "C" void emip_match_tc_set_variant(int softmax_warps) {
   g_softmax_warps = (softmax_warps == 16 || softmax_warps == 8) ? softmax_warps : 0;
 }
 
+// Diagnostics: force the work schedule (0 = choose by batch size, 1 = stream-K spans, 2 = grid-strided whole items).
+extern "C" void emip_match_tc_set_schedule(int mode) { g_schedule = (mode == 1 || mode == 2) ? mode : 0; }
+
 // Diagnostics: device buffer of gridDim.x * 8 counters filled by the next launches (NULL switches it off).
 extern "C" void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf) { g_prof = dev_buf; }
 
 bool match_tc_supported(int nq, int nk, int c) { return c == 128 && nk <= MAXK && nk >= 16 && nq >= 1; }
 
 size_t match_tc_split_bytes(int nb, int n, int c) { return emip_align_up((size_t)nb * n * 2 * c * 2, 1024); }
+
+// Upper bound of the stream-K workspace of match_tc_fwd for nb problems: with G CTAs and T = items * key tiles units,
+// a span holds >= floor(T / G) units, so an item (nkt units) meets at most nkt / floor(T / G) + 2 spans, and never
+// more than nkt.
+size_t match_tc_streamk_bytes(int nb, int nq, int nk) {
+  const int nqt = (nq + TM - 1) / TM, nkt = (nk + TN - 1) / TN;
+  const long long n_items = (long long)nb * ((nqt + 1) / 2), units = n_items * nkt;
+  if (units == 0) return 0;
+  const long long g = units < emip_num_sms() ? units : emip_num_sms();
+  long long pmax = nkt / (units / g) + 2;
+  if (pmax > nkt) pmax = nkt;
+  return emip_align_up(emip_align_up((size_t)n_items * sizeof(unsigned), 256) + (size_t)n_items * pmax * 2 * TM * sizeof(float4), 1024);
+}
 
 int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n, int c, int layout, int dst_batch0,
                    cudaStream_t st) {
@@ -704,8 +787,10 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   KParams p;
@@ -715,11 +800,44 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   p.grid_w = a.grid_w; p.sub_grid = a.sub_grid; p.terms = a.terms; p.s_mode = s_mode;
   p.inv_sqrt_c = 1.0f / a.sqrt_c;
   p.prof = g_prof;
-  const int nqt = (a.nq + TM - 1) / TM;
-  int grid = a.nb * ((nqt + 1) / 2);
-  if (grid > emip_num_sms()) grid = emip_num_sms();
-  if (nsmx == 8) match_tc_fwd_kernel<8><<<grid, 10 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
-  else match_tc_fwd_kernel<16><<<grid, 18 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+  const int nqt = (a.nq + TM - 1) / TM, nkt = (a.nk + TN - 1) / TN;
+  const int n_items = a.nb * ((nqt + 1) / 2);
+  const long long units = (long long)n_items * nkt;
+  // Whole items grid-strided keep every SM busy when the batch is large; when the last wave would leave more than a
+  // fifth of the SM-time idle (small batches: B = 1 has 16 items for 148 SMs) the units are dealt in equal spans.
+  // (At c2, 256 items, both schedules take the same time: the kernel runs power-limited at ~1.5 GHz when all SMs work,
+  // and the score-emitting items -- the second half of the list -- unbalance contiguous spans.)
+  const int sms = emip_num_sms();
+  const int waves = (n_items + sms - 1) / sms;
+  const int stream_k = g_schedule == 1 ? 1 : g_schedule == 2 ? 0 : ((double)n_items < 0.8 * waves * sms ? 1 : 0);
+  const int grid = stream_k ? (int)(units < sms ? units : sms) : (n_items < sms ? n_items : sms);
+  p.cnt = nullptr; p.part = nullptr; p.pmax = 1;
+  if (stream_k) {
+    // bookkeeping (arrival counters + partial rows) carved from the caller's workspace
+    const size_t cnt_bytes = emip_align_up((size_t)n_items * sizeof(unsigned), 256);
+    int pmax = 1;
+    for (int i = 0; i < n_items; ++i) {
+      const long long ub = (long long)i * nkt;
+      const int first = (int)(((ub + 1) * grid + units - 1) / units) - 1, last = (int)(((ub + nkt) * grid + units - 1) / units) - 1;
+      if (last - first + 1 > pmax) pmax = last - first + 1;
+    }
+    const size_t need = cnt_bytes + (size_t)n_items * pmax * 2 * TM * sizeof(float4);
+    if (a.sk_ws == nullptr || a.sk_bytes < need || reinterpret_cast<uintptr_t>(a.sk_ws) % 16 != 0) {
+      emip_set_error("match_tc_fwd: stream-K workspace too small or misaligned (%zu < %zu bytes)", a.sk_bytes, need);
+      return EMIP_ENOMEM;
+    }
+    p.cnt = static_cast<unsigned*>(a.sk_ws);
+    p.part = reinterpret_cast<float4*>(static_cast<char*>(a.sk_ws) + cnt_bytes);
+    p.pmax = pmax;
+  }
+  if (stream_k) EMIP_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)n_items * sizeof(unsigned), st));
+  if (nsmx == 8) {
+    if (stream_k) match_tc_fwd_kernel<8, true><<<grid, 10 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+    else match_tc_fwd_kernel<8, false><<<grid, 10 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+  } else {
+    if (stream_k) match_tc_fwd_kernel<16, true><<<grid, 18 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+    else match_tc_fwd_kernel<16, false><<<grid, 18 * 32, SMEM_BYTES, st>>>(mx, my, ms, p);
+  }
   EMIP_CHECK_LAUNCH("match_tc_fwd");
   return EMIP_OK;
 }

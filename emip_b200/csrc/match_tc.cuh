@@ -20,10 +20,13 @@ struct MatchTcArgs {
   int s_first, s_count;
   float sqrt_c;
   int terms;               // 3 = bf16 hi/lo split (hi.hi + lo.hi + hi.lo, fp32-accurate); 1 = single-pass bf16
+  void* sk_ws;             // stream-K bookkeeping, match_tc_streamk_bytes(nb, nq, nk) bytes, 16-byte aligned
+  size_t sk_bytes;
 };
 
 bool match_tc_supported(int nq, int nk, int c);
 size_t match_tc_split_bytes(int nb, int n, int c);
+size_t match_tc_streamk_bytes(int nb, int nq, int nk);
 // fp32 -> (bf16 hi | bf16 lo) token-major operands; writes batches [dst_batch0, dst_batch0+nb) of dst.
 // src2 != NULL: a second source of nb batches is written right behind the first (one launch for f0 and f1).
 int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n, int c, int layout, int dst_batch0,

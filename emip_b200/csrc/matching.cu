@@ -15,12 +15,21 @@ struct MatchWs {
   void* split;     // bf16 hi/lo token-major operands for the tensor-core paths
   size_t split_bytes;
   void* chn;       // bf16 hi/lo channel-major operands (tensor-core backward)
+  void* sk;        // stream-K bookkeeping of the tensor-core forward
+  size_t sk_bytes;
 };
+
+// uni- and bidirectional calls share one workspace: take the larger stream-K need
+size_t sk_need(int B, int N) {
+  const size_t a = match_tc_streamk_bytes(B, N, N), b = match_tc_streamk_bytes(2 * B, N, N);
+  return a > b ? a : b;
+}
 
 size_t simt_bytes(int B, int N, int nd) { return emip_align_up(sizeof(float) * ((size_t)2 * N + (size_t)nd * B * N), 1024); }
 
 int carve(void* ws, size_t ws_bytes, int B, int C, int N, int nd, MatchWs* out) {
-  size_t need = simt_bytes(B, N, 2) + match_tc_split_bytes(2 * B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N);
+  size_t need = simt_bytes(B, N, 2) + match_tc_split_bytes(2 * B, N, C) + pair_bwd_tc_chn_bytes(2 * B, N) +
+                sk_need(B, N);
   if (ws == nullptr || ws_bytes < need) {
     emip_set_error("global_matching: workspace too small (%zu < %zu bytes)", ws_bytes, need);
     return EMIP_ENOMEM;
@@ -35,13 +44,16 @@ int carve(void* ws, size_t ws_bytes, int B, int C, int N, int nd, MatchWs* out) 
   out->split = p + simt_bytes(B, N, 2);
   out->split_bytes = match_tc_split_bytes(2 * B, N, C);
   out->chn = p + simt_bytes(B, N, 2) + out->split_bytes;
+  out->sk = static_cast<char*>(out->chn) + pair_bwd_tc_chn_bytes(2 * B, N);
+  out->sk_bytes = sk_need(B, N);
   return EMIP_OK;
 }
 }  // namespace
 
 extern "C" size_t emip_global_matching_workspace(int B, int C, int H, int W) {
   if (B < 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return simt_bytes(B, H * W, 2) + match_tc_split_bytes(2 * B, H * W, C) + pair_bwd_tc_chn_bytes(2 * B, H * W);
+  return simt_bytes(B, H * W, 2) + match_tc_split_bytes(2 * B, H * W, C) + pair_bwd_tc_chn_bytes(2 * B, H * W) +
+         sk_need(B, H * W);
 }
 
 extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float* flow, float* corr, float* lse,
@@ -73,6 +85,7 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
     a.s_out = corr; a.s_first = bidir ? B : 0; a.s_count = corr ? B : 0;
     a.sqrt_c = sqrtf((float)C);
     a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
+    a.sk_ws = ws.sk; a.sk_bytes = ws.sk_bytes;
     return match_tc_fwd(a, st);
   }
   if ((rc = launch_coords_grid(ws.grid, H, W, st))) return rc;

@@ -194,6 +194,42 @@ def test_a1_odd_tile_count_and_batches():
         assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
 
 
+@pytest.mark.parametrize("schedule", [1, 2], ids=["stream_k", "strided_items"])
+def test_a1_a2_work_schedules(schedule):
+    """Both work schedules of the fused tcgen05 kernel (equal spans of key tiles with a cross-CTA merge of the
+    online-softmax rows / whole items grid-strided) against the CPU restatement: small and c2-sized batches."""
+    from emip_b200 import _lib
+    from emip_b200.matching import global_correlation_softmax
+    from emip_b200.flow_attn import FeatureFlowAttention
+    L = _lib.lib()
+    L.emip_match_tc_set_schedule(schedule)
+    try:
+        for (b, h, w) in ((1, 44, 44), (3, 20, 16), (11, 24, 20)):
+            f0 = cases.randn(170 + b, (b, 128, h, w), 1.5)
+            f1 = cases.randn(180 + b, (b, 128, h, w), 1.5)
+            ref_flow, _, ref_corr = O.global_correlation_softmax(f0, f1, True)
+            flow, _, corr = global_correlation_softmax(dev(f0), dev(f1), True)
+            assert rel(flow, ref_flow) < TOL_OUT, (b, h, w)
+            assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
+        # c2 size: against the exact-fp32 CUDA-core path
+        f0 = dev(cases.randn(2, (16, 128, 44, 44), 4.1))
+        f1 = dev(cases.randn(3, (16, 128, 44, 44), 4.1))
+        flow_tc, _, corr_tc = global_correlation_softmax(f0, f1, True)
+        flow_ex, _, corr_ex = global_correlation_softmax(f0, f1, True, exact_fp32=True)
+        assert rel(flow_tc, flow_ex) < TOL_OUT and rel(corr_tc, corr_ex) < TOL_EXACT
+        # a2 (value table mode) against its golden vector
+        name = list(cases.A2_CASES)[0]
+        sp = cases.A2_CASES[name]
+        d = cases.a2_inputs(sp)
+        m = FeatureFlowAttention(sp["c"]).cuda()
+        m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
+        ref = O.feature_flow_attention(d["x"], d["flow"], d["q_proj.weight"], d["q_proj.bias"], d["k_proj.weight"],
+                                       d["k_proj.bias"])
+        assert rel(m(dev(d["x"]), dev(d["flow"])), ref) < TOL_OUT
+    finally:
+        L.emip_match_tc_set_schedule(0)
+
+
 # ----------------------------------------------------------------------------- a2
 @pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
 @pytest.mark.parametrize("name", list(cases.A2_CASES))
