@@ -311,7 +311,7 @@ def main():
         # ---------------- secondary: flow_warp (K3) HBM roofline at B=64, 3x352x352 (tools/k3_bench.py) ----------------
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import k3_bench
-        line["flow_warp_roofline"] = {"kernel": "flow_warp_fwd_kernel / flow_warp_bwd_kernel", "bound": "hbm", "unit": "GB/s",
+        line["flow_warp_roofline"] = {"kernel": "flow_warp_staged_kernel<fwd|bwd> (TMA-staged; smooth flow) / flow_warp_border3_kernel (direct gather; chosen by the launcher for noisy flow)", "bound": "hbm", "unit": "GB/s",
                                       "peak": pk["hbm"], "workload": "B=64, 3x352x352 fp32 (254 MB fwd / 317 MB bwd > L2)",
                                       "flows": k3_bench.run(dev, pk["hbm"])}
         # ---------------- CPU baseline (oracle port) on this box's host cores ----------------
