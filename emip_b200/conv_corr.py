@@ -1,0 +1,97 @@
+"""First layer of ``conv_corr`` on the never-materialised cost volume.
+
+Reference: model/EMIP_short/model.py:59 (``nn.Conv2d(44*44, 968, 3, 1, 1)``) applied at model.py:96 to the ``corr``
+tensor of matching.py:16-20.  ``conv_corr_first_layer(f0, f1, weight, bias)`` returns exactly what
+``F.conv2d(corr, weight, bias, padding=1)`` returns for ``corr = global_correlation_softmax(f0, f1)[2]`` without
+forming ``corr``: two per-sample tensor-core GEMMs on the feature maps (csrc/conv_corr.cu).
+
+Training: the backward pass re-derives the gradients from the same re-association with library matmuls
+(``_reassociated_torch``) -- the forward kernel is the product, the backward is plumbing for now.
+"""
+import ctypes
+import math
+import weakref
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import I, SZ, ptr, stream_ptr
+from ._ws import workspace
+
+_prepared = {}   # id(weight) -> (weakref, version, device, buffer, aligned pointer)
+
+
+def _prepared_weight(weight):
+    """bf16 hi|lo, (o,dy,dx)-major copy of the conv weight, rebuilt when the parameter changes (optimizer step, load)."""
+    L = _lib.lib()
+    key = id(weight)
+    ent = _prepared.get(key)
+    if ent is not None and ent[0]() is weight and ent[1] == weight._version and ent[2] == weight.device and \
+            ent[5] == weight.data_ptr():
+        return ent[3], ent[4]
+    O, N = weight.shape[0], weight.shape[1]
+    L.emip_conv_corr_weight_bytes.restype = ctypes.c_size_t
+    buf, p, _ = workspace(L.emip_conv_corr_weight_bytes(I(O), I(N)), weight.device)
+    w = weight.detach().contiguous()
+    _lib.check(L.emip_conv_corr_prepare_weight(ptr(w), ctypes.c_void_p(p), I(O), I(N), stream_ptr()),
+               "emip_conv_corr_prepare_weight")
+    _prepared[key] = (weakref.ref(weight, lambda _r, k=key: _prepared.pop(k, None)), weight._version, weight.device, buf, p,
+                      weight.data_ptr())
+    return buf, p
+
+
+def _reassociated_torch(f0, f1, weight, bias):
+    """The same re-association with library ops (autograd-capable): G = W . f1 / sqrt(C); out = conv3x3(f0; G_b)."""
+    B, C, H, W = f0.shape
+    O = weight.shape[0]
+    g = torch.einsum("ojt,bcj->botc", weight.reshape(O, H * W, 9), f1.reshape(B, C, H * W)) / math.sqrt(C)   # [B,O,9,C]
+    wb = g.permute(0, 1, 3, 2).reshape(B * O, C, 3, 3)
+    out = F.conv2d(f0.reshape(1, B * C, H, W), wb, None, padding=1, groups=B).reshape(B, O, H, W)
+    return out if bias is None else out + bias.view(1, O, 1, 1)
+
+
+class _ConvCorr(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f0, f1, weight, bias):
+        L = _lib.lib()
+        B, C, H, W = f0.shape
+        O = weight.shape[0]
+        f0c, f1c = f0.contiguous(), f1.contiguous()
+        wbuf, wp = _prepared_weight(weight)
+        L.emip_conv_corr_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_conv_corr_workspace(I(B), I(C), I(H), I(W), I(O)), f0.device)
+        out = torch.empty((B, O, H, W), dtype=torch.float32, device=f0.device)
+        b = bias.detach().contiguous() if bias is not None else None
+        _lib.check(L.emip_conv_corr_fwd(ptr(f0c), ptr(f1c), ctypes.c_void_p(wp), ptr(b) if b is not None else None, ptr(out),
+                                        ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C), I(H), I(W), I(O), stream_ptr()),
+                   "emip_conv_corr_fwd")
+        ctx.save_for_backward(f0, f1, weight, bias if bias is not None else torch.empty(0, device=f0.device))
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f0, f1, weight, bias = ctx.saved_tensors
+        bias = bias if ctx.has_bias else None
+        with torch.enable_grad():
+            ins = [t.detach().requires_grad_(True) for t in (f0, f1, weight)]
+            b = bias.detach().requires_grad_(True) if bias is not None else None
+            out = _reassociated_torch(ins[0], ins[1], ins[2], b)
+            grads = torch.autograd.grad(out, ins + ([b] if b is not None else []), dout)
+        return grads[0], grads[1], grads[2], (grads[3] if b is not None else None)
+
+
+def conv_corr_first_layer(f0, f1, weight, bias=None):
+    """``F.conv2d(corr, weight, bias, padding=1)`` for ``corr[b,j,y,x] = <f0[b,:,y,x], f1[b,:,j]> / sqrt(C)``."""
+    if not (f0.is_cuda and f1.is_cuda and weight.is_cuda):
+        raise _lib.EmipError("emip_b200 conv_corr needs CUDA tensors (no CPU fallback)")
+    if f0.dtype != torch.float32 or f1.dtype != torch.float32 or weight.dtype != torch.float32:
+        raise TypeError("emip_b200 conv_corr computes from fp32 features and weights")
+    B, C, H, W = f0.shape
+    if f1.shape != f0.shape or weight.dim() != 4 or tuple(weight.shape[1:]) != (H * W, 3, 3):
+        raise ValueError(f"expected f0, f1 [B,C,H,W] and weight [O,{H * W},3,3], got {tuple(f0.shape)}, {tuple(f1.shape)}, "
+                         f"{tuple(weight.shape)}")
+    if not _lib.lib().emip_conv_corr_supported(I(C), I(H), I(W)):
+        raise _lib.EmipError(f"emip_b200 conv_corr: unsupported shape C={C} H={H} W={W}")
+    return _ConvCorr.apply(f0, f1, weight, bias)

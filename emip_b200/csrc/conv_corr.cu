@@ -1,0 +1,389 @@
+// f1: first layer of conv_corr on the NEVER-MATERIALISED cost volume.
+//
+// Replaces reference model/EMIP_short/model.py:59 (`nn.Conv2d(44*44, 968, 3, 1, 1)`, first layer of `conv_corr`)
+// applied at model.py:96 to the `corr` tensor of matching.py:16-20, corr[b, j, y, x] = S[b, (y,x), j] =
+// sum_c f0[b,c,(y,x)] f1[b,c,j] / sqrt(C).  Re-associating the two contractions,
+//
+//   out[b,o,y,x] = bias[o] + sum_{j,dy,dx} Wt[o,j,dy,dx] corr[b,j,y+dy-1,x+dx-1]            (zero padding in (y,x))
+//                = bias[o] + sum_{dy,dx,c} f0[b,c,(y+dy-1,x+dx-1)] G[b][(o,dy,dx), c]
+//   G[b][(o,dy,dx), c] = (1/sqrt(C)) sum_j Wt[o,j,dy,dx] f1[b,c,j]
+//
+// turns a 65.3 GFLOP/sample convolution over a 15 MB/sample input into two 4.3 GFLOP GEMMs per sample on the 1 MB
+// feature maps, and removes the only consumer of the cost volume (the matching kernel can run flow-only).
+//
+// Both GEMMs run on the 5th-gen tensor cores in the same accuracy-preserving form as the matching kernel: operands
+// are bf16 hi + lo pairs, D += A.hi B.hi + A.lo B.hi + A.hi B.lo with fp32 accumulation in TMEM (SS-mode tcgen05.mma,
+// M = 128), operands staged by TMA into 128-byte-swizzled K-major tiles:
+//   GEMM 1 (G):    A = prepared weight [(o,dy,dx)][j] (emip_conv_corr_prepare_weight: permuted + split once per
+//                  weight version), B = f1 channel-major [c][j]; N = 128; the epilogue scales by 1/sqrt(C) and writes G
+//                  as bf16 hi | lo, row (o,dy,dx) x column c -- which IS the K-major A operand of GEMM 2;
+//   GEMM 2 (conv): A = G[b] [o][(dy,dx,c)], B = the token-major f0 read through a 4-D tensor map {c, x, y, b} with
+//                  the box origin shifted by the tap (dx-1, dy-1): out-of-image pixels are zero-filled by the TMA
+//                  unit, which is exactly the convolution's zero padding -- no im2col buffer; N = R image rows
+//                  (R*W a multiple of 16, <= 256; 4 x 44 = 176 for the model's grid); epilogue adds the bias.
+// One 128 x N output tile per CTA: 4 epilogue warps (TMEM -> registers -> global), 1 TMA producer warp, 1 MMA warp.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/emip_b200.h"
+#include "pair_common.cuh"
+#include "match_tc.cuh"
+#include "pair_bwd_tc.cuh"
+#include <math.h>
+
+namespace {
+using namespace tc;
+
+constexpr int KCH = 64;                       // bf16 per 128-byte swizzle row = K elements per chunk
+constexpr int A_BYTES = TM * 128;             // one [128 x 64] bf16 operand tile
+constexpr int NMAX = 256;
+constexpr int THREADS = 6 * 32;
+
+struct CcParams {
+  int mode;                 // 0: G = Wp f1^T (split-bf16 output)   1: out = conv3x3(f0; G) + bias (fp32 output)
+  int M;                    // rows of A / of the output (mode 0: O*9, mode 1: O)
+  int n_mtiles, n_ntiles;   // tiles per sample
+  int n_tile;               // UMMA N (mode 0: 128 channels, mode 1: R*W pixels)
+  int kchunks;              // K / 64 (rounded up; the TMA unit zero-fills the tail)
+  int stages, stage_bytes, b_bytes;
+  int W, H, R;              // mode 1: image geometry, rows per pixel tile
+  float scale;              // mode 0: 1/sqrt(C)
+  const float* bias;        // mode 1
+  __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, then lo
+  __nv_bfloat16* g_lo;
+  float* out;               // mode 1 output: [B][M][H*W]
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_corr_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b, const CcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + p.stages * p.stage_bytes;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 8 * (p.stages + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * p.stages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+  const int mt = t % p.n_mtiles;
+  const int b = t / p.n_mtiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32((const void*)tmem_slot))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kc = 0; kc < p.kchunks; ++kc) {
+      mbar_wait(empty(stage), phase ^ 1);
+      if (leader) {
+        const uint32_t sa = sbase + stage * p.stage_bytes;
+        mbar_expect_tx(full(stage), 2 * A_BYTES + 2 * p.b_bytes);
+        if (p.mode == 0) {
+          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, 0);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, 0);
+          // f1 channel-major [b][256 = hi c | lo c][ld]: rows 0..127 hi, 128..255 lo
+          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, 0, b);
+          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), kc * KCH, 128, b);
+        } else {
+          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
+          // K chunk kc = tap (dy,dx) = kc / 2, channel half kc % 2 of the token-major [.., 256 = hi 128 | lo 128] f0
+          const int tap = kc >> 1, dy = tap / 3, dx = tap - dy * 3, c0 = (kc & 1) * KCH;
+          tma_load_4d(sa + 2 * A_BYTES, &map_b, full(stage), c0, dx - 1, nt * p.R + dy - 1, b);
+          tma_load_4d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), 128 + c0, dx - 1, nt * p.R + dy - 1, b);
+        }
+      }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== UMMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(p.n_tile);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kc = 0; kc < p.kchunks; ++kc) {
+      mbar_wait(full(stage), phase);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t sa = sbase + stage * p.stage_bytes;
+        const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_BYTES);
+        const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_BYTES), b_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + p.b_bytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        umma_commit(empty(stage));
+        if (kc == p.kchunks - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps: thread <-> output row =====================
+    const int row = mt * TM + warp * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (p.mode == 0) {
+      __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
+      __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        if (row < p.M) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v0 = __uint_as_float(r[2 * i]) * p.scale, v1 = __uint_as_float(r[2 * i + 1]) * p.scale;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+            const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
+                                                         __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(gh + c0);
+          uint4* dl = reinterpret_cast<uint4*>(gl + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      }
+    } else {
+      const int npix = p.H * p.W;
+      const int px0 = nt * p.R * p.W;
+      const int nvalid = min(p.n_tile, npix - px0);          // the last tile may hang over the bottom edge
+      const float bias = (row < p.M && p.bias != nullptr) ? __ldg(p.bias + row) : 0.f;
+      float* o = p.out + ((size_t)b * p.M + row) * npix + px0;
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t r[32];
+        // n_tile is a multiple of 16: the last group may be a half group
+        if (c0 + 32 <= p.n_tile) {
+          tmem_ld32_async(taddr + c0, r);
+          tmem_wait(r);
+        } else {
+          uint32_t h[32];
+          tmem_ld32_async(taddr + p.n_tile - 32, h);          // overlapping read of the last 32 columns
+          tmem_wait(h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = h[16 + i];
+#pragma unroll
+          for (int i = 16; i < 32; ++i) r[i] = 0u;
+        }
+        if (row < p.M) {
+          const int n = min(32, min(p.n_tile, nvalid) - c0);
+          if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0)) {
+            float4* d = reinterpret_cast<float4*>(o + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              d[i] = make_float4(__uint_as_float(r[4 * i]) + bias, __uint_as_float(r[4 * i + 1]) + bias,
+                                 __uint_as_float(r[4 * i + 2]) + bias, __uint_as_float(r[4 * i + 3]) + bias);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + bias;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// [O][N][3][3] fp32 -> hi | lo bf16 [2][O*9][ld], row (o, dy, dx), K = j contiguous
+__global__ void __launch_bounds__(256)
+prepare_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int O, int N,
+                      long long ld) {
+  const int o = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    const float* s = w + ((size_t)o * N + j) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float v = __ldg(s + t);
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[((size_t)o * 9 + t) * ld + j] = h;
+      lo[((size_t)o * 9 + t) * ld + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+int make_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encoder();
+  if (enc == nullptr) {
+    emip_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return EMIP_ENOSYS;
+  }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    emip_set_error("conv_corr: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return EMIP_EINVAL;
+  }
+  return EMIP_OK;
+}
+
+long long weight_ld(int N) { return (N + 7) / 8 * 8; }      // 16-byte row pitch
+
+// image rows per pixel tile: R*W a multiple of 16 and <= 256 (0: unsupported grid)
+int rows_per_tile(int H, int W) {
+  int best = 0;
+  for (int r = 1; r * W <= NMAX && r <= H + 3; ++r)
+    if ((r * W) % 16 == 0) best = r;
+  return best;
+}
+
+struct Ws {
+  void* f0_tok;        // bf16 [B][N][256]
+  void* f1_chn;        // bf16 [B][256][ld]
+  __nv_bfloat16* g;    // bf16 [2][B][O*9][128]
+};
+size_t g_bytes(int B, int O) { return emip_align_up((size_t)2 * B * O * 9 * 128 * 2, 1024); }
+}  // namespace
+
+extern "C" int emip_conv_corr_supported(int C, int H, int W) {
+  return C == 128 && rows_per_tile(H, W) > 0 && H * W >= 16 ? 1 : 0;
+}
+
+extern "C" size_t emip_conv_corr_weight_bytes(int O, int N) {
+  if (O <= 0 || N <= 0) return 0;
+  return emip_align_up((size_t)2 * O * 9 * weight_ld(N) * 2, 1024);
+}
+
+extern "C" int emip_conv_corr_prepare_weight(const float* w, void* w_prep, int O, int N, void* stream) {
+  EMIP_CHECK_ARG(w && w_prep && O > 0 && N > 0, "conv_corr_prepare_weight: bad arguments");
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(w_prep) % 1024 == 0, "conv_corr_prepare_weight: w_prep must be 1024-byte aligned");
+  const long long ld = weight_ld(N);
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(w_prep);
+  __nv_bfloat16* lo = hi + (size_t)O * 9 * ld;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ld != N) EMIP_CUDA(cudaMemsetAsync(w_prep, 0, (size_t)2 * O * 9 * ld * 2, st));
+  dim3 grid((N + 255) / 256, O);
+  prepare_weight_kernel<<<grid, 256, 0, st>>>(w, hi, lo, O, N, ld);
+  EMIP_CHECK_LAUNCH("conv_corr_prepare_weight");
+  return EMIP_OK;
+}
+
+extern "C" size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O) {
+  if (B < 0 || C != 128 || H <= 0 || W <= 0 || O <= 0) return 0;
+  return match_tc_split_bytes(B, H * W, C) + pair_bwd_tc_chn_bytes(B, H * W) + g_bytes(B, O);
+}
+
+extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
+                                  void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(f0 && f1 && w_prep && out, "conv_corr_fwd: null pointer");
+  EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0 && O > 0, "conv_corr_fwd: bad shape B=%d H=%d W=%d O=%d", B, H, W, O);
+  if (!emip_conv_corr_supported(C, H, W)) {
+    emip_set_error("conv_corr_fwd: unsupported shape C=%d H=%d W=%d (needs C=128 and R*W %% 16 == 0 for some R*W <= 256)", C, H, W);
+    return EMIP_ENOSYS;
+  }
+  const int N = H * W;
+  const size_t need = emip_conv_corr_workspace(B, C, H, W, O);
+  if (workspace == nullptr || ws_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) {
+    emip_set_error("conv_corr_fwd: workspace too small or not 1024-byte aligned (%zu < %zu bytes)", ws_bytes, need);
+    return EMIP_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wsp = static_cast<char*>(workspace);
+  Ws ws;
+  ws.f0_tok = wsp;
+  ws.f1_chn = wsp + match_tc_split_bytes(B, N, C);
+  ws.g = reinterpret_cast<__nv_bfloat16*>(wsp + match_tc_split_bytes(B, N, C) + pair_bwd_tc_chn_bytes(B, N));
+  int rc;
+  if ((rc = match_tc_split(f0, nullptr, ws.f0_tok, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
+  if ((rc = pair_bwd_tc_split_chn(f1, nullptr, ws.f1_chn, B, N, EMIP_LAYOUT_CN, st))) return rc;
+
+  const int M1 = O * 9;
+  const long long wld = weight_ld(N), cld = pair_bwd_tc_chn_ld(N);
+  const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(w_prep);
+  const __nv_bfloat16* w_lo = w_hi + (size_t)M1 * wld;
+  __nv_bfloat16* g_hi = ws.g;
+  __nv_bfloat16* g_lo = ws.g + (size_t)B * M1 * 128;
+  static bool attr_done = false;
+  const int max_smem = 227 * 1024;
+  if (!attr_done) {
+    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_done = true;
+  }
+  auto smem_for = [](int stages, int stage_bytes) { return stages * stage_bytes + 8 * (2 * stages + 1) + 16 + 1024; };
+
+  // ---- GEMM 1: G[b] = Wp f1[b]^T / sqrt(C)
+  {
+    CUtensorMap ma_hi, ma_lo, mb;
+    const cuuint64_t adims[3] = {(cuuint64_t)N, (cuuint64_t)M1, 1}, astr[2] = {(cuuint64_t)wld * 2, (cuuint64_t)M1 * wld * 2};
+    const cuuint32_t abox[3] = {KCH, TM, 1};
+    if ((rc = make_map_bf16(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
+    if ((rc = make_map_bf16(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
+    const cuuint64_t bdims[3] = {(cuuint64_t)N, 256, (cuuint64_t)B}, bstr[2] = {(cuuint64_t)cld * 2, (cuuint64_t)cld * 2 * 256};
+    const cuuint32_t bbox[3] = {KCH, 128, 1};
+    if ((rc = make_map_bf16(&mb, ws.f1_chn, 3, bdims, bstr, bbox))) return rc;
+    CcParams p = {};
+    p.mode = 0; p.M = M1; p.n_mtiles = (M1 + TM - 1) / TM; p.n_ntiles = 1; p.n_tile = 128;
+    p.kchunks = (N + KCH - 1) / KCH;
+    p.b_bytes = 128 * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes; p.stages = 3;
+    p.scale = 1.0f / sqrtf((float)C);
+    p.g_hi = g_hi; p.g_lo = g_lo;
+    const long long grid = (long long)B * p.n_mtiles;
+    EMIP_CHECK_ARG(grid < 0x7fffffffLL, "conv_corr_fwd: problem too large");
+    conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem_for(p.stages, p.stage_bytes), st>>>(ma_hi, ma_lo, mb, p);
+    EMIP_CHECK_LAUNCH("conv_corr_fwd (G)");
+  }
+  // ---- GEMM 2: out[b] = conv3x3(f0[b]; G[b]) + bias
+  {
+    const int R = rows_per_tile(H, W);
+    CUtensorMap ma_hi, ma_lo, mb;
+    const cuuint64_t adims[3] = {9 * 128, (cuuint64_t)O, (cuuint64_t)B}, astr[2] = {9 * 128 * 2, (cuuint64_t)M1 * 128 * 2};
+    const cuuint32_t abox[3] = {KCH, TM, 1};
+    if ((rc = make_map_bf16(&ma_hi, g_hi, 3, adims, astr, abox))) return rc;
+    if ((rc = make_map_bf16(&ma_lo, g_lo, 3, adims, astr, abox))) return rc;
+    const cuuint64_t bdims[4] = {256, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t bstr[3] = {512, (cuuint64_t)W * 512, (cuuint64_t)N * 512};
+    const cuuint32_t bbox[4] = {KCH, (cuuint32_t)W, (cuuint32_t)R, 1};
+    if ((rc = make_map_bf16(&mb, ws.f0_tok, 4, bdims, bstr, bbox))) return rc;
+    CcParams p = {};
+    p.mode = 1; p.M = O; p.n_mtiles = (O + TM - 1) / TM; p.n_ntiles = (H + R - 1) / R; p.n_tile = R * W;
+    p.kchunks = 18;
+    p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024); p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
+    p.stages = (max_smem - 2048) / p.stage_bytes;
+    if (p.stages > 4) p.stages = 4;
+    p.W = W; p.H = H; p.R = R;
+    p.bias = bias; p.out = out;
+    const long long grid = (long long)B * p.n_mtiles * p.n_ntiles;
+    EMIP_CHECK_ARG(grid < 0x7fffffffLL, "conv_corr_fwd: problem too large");
+    conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem_for(p.stages, p.stage_bytes), st>>>(ma_hi, ma_lo, mb, p);
+    EMIP_CHECK_LAUNCH("conv_corr_fwd (conv)");
+  }
+  return EMIP_OK;
+}

@@ -168,6 +168,22 @@ size_t emip_occu_mask_workspace(int B, int H, int W);
 int emip_occu_mask_backward(const float* flow21, float* mask, void* workspace, size_t ws_bytes, int B, int H, int W,
                             long long flow_stride_b, long long flow_stride_c, float th, void* stream);
 
+/* ---- f1: first layer of conv_corr on the never-materialised cost volume --------------- */
+/* Replaces model/EMIP_short/model.py:59 (nn.Conv2d(H*W, O, 3, 1, 1), first layer of conv_corr) applied at model.py:96
+ * to corr = matching.py:16-20: out[b,o,y,x] = bias[o] + sum_{j,dy,dx} w[o,j,dy,dx] corr[b,j,y+dy-1,x+dx-1] with
+ * corr[b,j,y,x] = sum_c f0[b,c,(y,x)] f1[b,c,j] / sqrt(C), computed as two per-sample GEMMs on the feature maps
+ * (csrc/conv_corr.cu) so that corr is never formed.
+ *   f0, f1 [B,C,H,W] (the matching features)   w [O, H*W, 3, 3]   bias [O] or NULL   out [B,O,H,W]
+ * The weight is permuted and split into bf16 hi|lo once per weight version by emip_conv_corr_prepare_weight into a
+ * caller-owned buffer of emip_conv_corr_weight_bytes(O, H*W) bytes (1024-byte aligned).
+ * emip_conv_corr_supported: C == 128 and some R with R*W % 16 == 0, R*W <= 256 (44x44: R = 4). */
+int emip_conv_corr_supported(int C, int H, int W);
+size_t emip_conv_corr_weight_bytes(int O, int N);
+int emip_conv_corr_prepare_weight(const float* w, void* w_prep, int O, int N, void* stream);
+size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O);
+int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
+                       void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

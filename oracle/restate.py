@@ -270,3 +270,16 @@ def occu_mask_backward(flow21, th=0.2):
     Reference: loss/warp_utils.py:106-112.
     """
     return (corresponding_map(flow21).clamp(0.0, 1.0) < th).to(flow21.dtype)
+
+
+def conv_corr_first_layer(feature0, feature1, weight, bias=None):
+    """First layer of conv_corr on the cost volume of ``global_correlation_softmax``.
+
+    Reference: model/EMIP_short/model.py:59 (``nn.Conv2d(44*44, 968, 3, 1, 1)``) applied at model.py:96 to
+    ``corr`` = matching.py:16-20 (``corr[b, j, y, x] = S[b, (y,x), j]``).  Restated literally: materialise the cost
+    volume, then the 3x3 zero-padded convolution over its key-index channels.
+    """
+    b, c, h, w = feature0.shape
+    s = torch.matmul(feature0.reshape(b, c, h * w).transpose(1, 2), feature1.reshape(b, c, h * w)) / (c ** 0.5)   # [b, i, j]
+    corr = s.reshape(b, h, w, h * w).permute(0, 3, 1, 2)
+    return torch.nn.functional.conv2d(corr, weight, bias, stride=1, padding=1)

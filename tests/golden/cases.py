@@ -103,6 +103,21 @@ def f4_inputs(s):
                 wout=randn(s["seed"] + 2000, (s["b"], 2, 8 * s["h"], 8 * s["w"])))
 
 
+F1_CASES = {
+    "f1_small": dict(b=2, c=128, h=12, w=12, o=24, scale=1.5, seed=91),
+    "f1_ragged": dict(b=3, c=128, h=10, w=16, o=200, scale=4.1, seed=92),
+}
+
+
+def f1_inputs(s):
+    shp = (s["b"], s["c"], s["h"], s["w"])
+    n = s["h"] * s["w"]
+    return dict(f0=randn(s["seed"], shp, s["scale"]), f1=randn(s["seed"] + 1000, shp, s["scale"]),
+                weight=randn(s["seed"] + 2000, (s["o"], n, 3, 3), (9 * n) ** -0.5),
+                bias=randn(s["seed"] + 3000, (s["o"],), 0.1),
+                wout=randn(s["seed"] + 4000, (s["b"], s["o"], s["h"], s["w"])))
+
+
 F3_CASES = {
     "f3_small": dict(b=2, h=9, w=11, sigma=2.0, seed=71),
     "f3_mid": dict(b=2, h=40, w=56, sigma=6.0, seed=72),

@@ -124,6 +124,24 @@ def gen_f4():
                         dmask=cases.pack(mask.grad, s["full"])))
 
 
+def gen_f1():
+    """conv_corr[0] (model.py:59) on the corr tensor the reference's matching function returns."""
+    from model.EMIP_short.motion.gmflow.matching import global_correlation_softmax
+    for name, s in cases.F1_CASES.items():
+        d = cases.f1_inputs(s)
+        f0 = d["f0"].clone().requires_grad_(True)
+        f1 = d["f1"].clone().requires_grad_(True)
+        conv = torch.nn.Conv2d(s["h"] * s["w"], s["o"], 3, 1, 1)
+        with torch.no_grad():
+            conv.weight.copy_(d["weight"])
+            conv.bias.copy_(d["bias"])
+        corr = global_correlation_softmax(f0, f1, True)[2]
+        out = conv(corr)
+        (out * d["wout"]).sum().backward()
+        save(name, dict(spec=s, out=cases.pack(out.detach(), False), df0=cases.pack(f0.grad, False), df1=cases.pack(f1.grad, False),
+                        dw=cases.pack(conv.weight.grad, False), db=cases.pack(conv.bias.grad, False)))
+
+
 def gen_f3():
     from loss.warp_utils import get_occu_mask_backward, get_corresponding_map, mesh_grid
     for name, s in cases.F3_CASES.items():
@@ -173,6 +191,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f3", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f3", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

@@ -381,3 +381,43 @@ def test_f3_occlusion_mask_properties_full():
     z[:, 0] = 3.0                                                   # everything moves 3 px to the right
     m = get_occu_mask_backward(z)
     assert m[..., :3].min().item() == 1.0 and m[..., 3:].sum().item() == 0
+
+
+# ----------------------------------------------------------------------------- f1
+@pytest.mark.parametrize("name", list(cases.F1_CASES))
+def test_f1_conv_corr_golden(golden, name):
+    from emip_b200.conv_corr import conv_corr_first_layer
+    g = golden(name)
+    d = cases.f1_inputs(cases.F1_CASES[name])
+    f0 = dev(d["f0"]).requires_grad_(True)
+    f1 = dev(d["f1"]).requires_grad_(True)
+    w = dev(d["weight"]).requires_grad_(True)
+    b = dev(d["bias"]).requires_grad_(True)
+    out = conv_corr_first_layer(f0, f1, w, b)
+    e = cases.check_packed(out, g["out"], TOL_EXACT, "out")
+    print(f"{name}: out rel-L2 {e:.2e}")
+    (out * dev(d["wout"])).sum().backward()
+    cases.check_packed(f0.grad, g["df0"], TOL_GRAD, "df0")
+    cases.check_packed(f1.grad, g["df1"], TOL_GRAD, "df1")
+    cases.check_packed(w.grad, g["dw"], TOL_GRAD, "dw")
+    cases.check_packed(b.grad, g["db"], TOL_GRAD, "db")
+
+
+def test_f1_conv_corr_model_size_vs_materialised():
+    """The model's shape (44x44 tokens, 968 output channels): against F.conv2d on the cost volume our a1 kernel emits,
+    weight update invalidates the prepared copy."""
+    from emip_b200.conv_corr import conv_corr_first_layer
+    from emip_b200.matching import global_correlation_softmax
+    B, C, H, W, O = 2, 128, 44, 44, 968
+    f0 = dev(cases.randn(95, (B, C, H, W), 4.1))
+    f1 = dev(cases.randn(96, (B, C, H, W), 4.1))
+    w = dev(cases.randn(97, (O, H * W, 3, 3), (9 * H * W) ** -0.5))
+    b = dev(cases.randn(98, (O,), 0.1))
+    corr = global_correlation_softmax(f0, f1, True, exact_fp32=True)[2]
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(corr.double(), w.double(), b.double(), padding=1)
+    out = conv_corr_first_layer(f0, f1, w, b)
+    assert rel(out, ref) < TOL_EXACT
+    with torch.no_grad():
+        w.mul_(0.5)
+    assert rel(conv_corr_first_layer(f0, f1, w, b), (ref - b.double().view(1, -1, 1, 1)) * 0.5 + b.double().view(1, -1, 1, 1)) < TOL_EXACT

@@ -152,3 +152,23 @@ def test_f3_occlusion_mask(golden, name):
     ref = g["mask"]["full"]
     differ = (mask != ref) & ((cm - 0.2).abs() > 1e-5)              # only threshold ties may differ (summation order)
     assert not differ.any()
+
+
+@pytest.mark.parametrize("name", list(cases.F1_CASES))
+def test_f1_conv_corr_first_layer(golden, name):
+    """conv_corr[0] on the cost volume: the oracle restatement and the two-GEMM re-association the CUDA path uses."""
+    g = golden(name)
+    d = cases.f1_inputs(cases.F1_CASES[name])
+    cases.check_packed(O.conv_corr_first_layer(d["f0"], d["f1"], d["weight"], d["bias"]), g["out"], TOL, "out")
+    from emip_b200.conv_corr import _reassociated_torch
+    f0 = d["f0"].clone().requires_grad_(True)
+    f1 = d["f1"].clone().requires_grad_(True)
+    w = d["weight"].clone().requires_grad_(True)
+    b = d["bias"].clone().requires_grad_(True)
+    out = _reassociated_torch(f0, f1, w, b)
+    cases.check_packed(out, g["out"], 1e-5, "re-associated out")
+    (out * d["wout"]).sum().backward()
+    cases.check_packed(f0.grad, g["df0"], 1e-5, "df0")
+    cases.check_packed(f1.grad, g["df1"], 1e-5, "df1")
+    cases.check_packed(w.grad, g["dw"], 1e-5, "dw")
+    cases.check_packed(b.grad, g["db"], 1e-5, "db")
