@@ -95,3 +95,18 @@ def conv_corr_first_layer(f0, f1, weight, bias=None):
     if not _lib.lib().emip_conv_corr_supported(I(C), I(H), I(W)):
         raise _lib.EmipError(f"emip_b200 conv_corr: unsupported shape C={C} H={H} W={W}")
     return _ConvCorr.apply(f0, f1, weight, bias)
+
+
+class CorrConv2d(torch.nn.Conv2d):
+    """``conv_corr[0]`` (model.py:59) with the same parameters and ``state_dict`` keys.  Fed with the placeholder that
+    ``global_correlation_softmax`` returns inside a fused model (``dropin.fuse_conv_corr``) it runs on the feature maps;
+    fed with a real tensor it is the plain convolution."""
+
+    def forward(self, x):
+        pair = getattr(x, "_emip_pair", None)
+        if pair is None:
+            return super().forward(x)
+        if self.kernel_size != (3, 3) or self.stride != (1, 1) or self.padding != (1, 1) or self.dilation != (1, 1) or \
+                self.groups != 1:
+            raise _lib.EmipError("CorrConv2d: only the reference's 3x3 / stride 1 / padding 1 layer is supported")
+        return conv_corr_first_layer(pair[0], pair[1], self.weight, self.bias)

@@ -14,6 +14,12 @@ unchanged (same signatures, same ``state_dict`` keys):
 
 Call it after the reference root is on ``sys.path`` and before the model is constructed.  ``uninstall()`` restores
 the originals (used by the tests).
+
+``fuse_conv_corr(model)`` (optional, per constructed ``CoUpdater``) additionally removes the cost volume from HBM:
+``conv_corr[0]`` (model.py:59) becomes ``emip_b200.conv_corr.CorrConv2d`` -- same parameters, same ``state_dict``
+keys -- and while that model's ``forward`` runs, ``global_correlation_softmax`` hands it the two feature maps instead
+of ``corr``.  ``Model_long`` reshapes ``corr`` itself (model_long.py:80-84) and keeps the
+materialised tensor.
 """
 import importlib
 import sys
@@ -87,3 +93,32 @@ def uninstall():
             else:
                 setattr(mod, attr, orig)
         del _saved[(mod_name, attr)]
+
+
+def fuse_conv_corr(model):
+    """Fuse ``conv_corr[0]`` of a constructed ``CoUpdater`` with the matching kernel (cost volume never materialised).
+
+    Requires ``install()`` (the model must call our ``global_correlation_softmax``).  Returns ``model``.
+    """
+    import functools
+    from . import matching
+    from .conv_corr import CorrConv2d
+    conv = model.conv_corr[0]
+    if not isinstance(conv, CorrConv2d):
+        conv.__class__ = CorrConv2d              # same parameters, buffers and state_dict keys
+    if getattr(model, "_emip_fused_forward", False):
+        return model
+    inner = model.forward
+
+    @functools.wraps(inner)
+    def forward(*args, **kwargs):
+        prev = matching._lazy_corr[0]
+        matching._lazy_corr[0] = True
+        try:
+            return inner(*args, **kwargs)
+        finally:
+            matching._lazy_corr[0] = prev
+
+    model.forward = forward
+    model._emip_fused_forward = True
+    return model

@@ -60,6 +60,11 @@ class _GlobalMatching(torch.autograd.Function):
         return df0, df1, None, None, None
 
 
+# Set (only) by dropin.fuse_conv_corr while the fused model runs: `corr` then is an empty placeholder that carries the
+# two feature maps to emip_b200.conv_corr.CorrConv2d, and the H*W x H*W cost volume is never written.
+_lazy_corr = [False]
+
+
 def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return_corr=True, exact_fp32=False,
                                bf16=False):
     """GMFlow global matching: returns ``(flow, prob, corr)`` like the reference.
@@ -87,9 +92,15 @@ def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return
     B, C, H, W = feature0.shape
     if bf16 and exact_fp32:
         raise ValueError("exact_fp32 and bf16 are mutually exclusive")
+    lazy = bool(return_corr) and _lazy_corr[0]
+    if lazy:
+        return_corr = False
     flow, smem = _GlobalMatching.apply(feature0, feature1, bool(pred_bidir_flow), bool(return_corr),
                                        EXACT_FP32 if exact_fp32 else (BF16 if bf16 else 0))
     corr = None
     if smem is not None:
         corr = smem if pred_bidir_flow else smem.view(B, H, W, H * W).permute(0, 3, 1, 2)
+    if lazy:
+        corr = flow.new_empty(0)
+        corr._emip_pair = (feature0, feature1)
     return flow, None, corr

@@ -92,6 +92,14 @@ def test_dropin_rebinds_reference_symbols():
         assert isinstance(net.GMFlow.feature_flow_attn, FeatureFlowAttention)
         assert isinstance(net.injector, Injector) and isinstance(net.injector1, Injector)
         assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == ref_sd
+        # optional fusion of conv_corr[0] with the matching kernel: same keys, plain convolution on real tensors
+        from emip_b200.conv_corr import CorrConv2d
+        dropin.fuse_conv_corr(net)
+        assert isinstance(net.conv_corr[0], CorrConv2d)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == ref_sd
+        x = torch.randn(1, 44 * 44, 6, 5)
+        assert torch.equal(net.conv_corr[0](x), torch.nn.functional.conv2d(x, net.conv_corr[0].weight, net.conv_corr[0].bias,
+                                                                          padding=1))
     finally:
         dropin.uninstall()
     import model.EMIP_short.motion.gmflow.matching as ref_matching

@@ -421,3 +421,43 @@ def test_f1_conv_corr_model_size_vs_materialised():
     with torch.no_grad():
         w.mul_(0.5)
     assert rel(conv_corr_first_layer(f0, f1, w, b), (ref - b.double().view(1, -1, 1, 1)) * 0.5 + b.double().view(1, -1, 1, 1)) < TOL_EXACT
+
+
+def test_f1_fused_model_slice():
+    """dropin.fuse_conv_corr on a stand-in with the reference's structure (model.py:59-62,95-96): the fused forward and
+    backward equal the unfused ones."""
+    from emip_b200 import dropin
+    from emip_b200.matching import global_correlation_softmax
+
+    class Slice(torch.nn.Module):
+        def __init__(self, n, o):
+            super().__init__()
+            self.conv_corr = torch.nn.Sequential(torch.nn.Conv2d(n, o, 3, 1, 1), torch.nn.BatchNorm2d(o),
+                                                 torch.nn.ReLU(inplace=True), torch.nn.Conv2d(o, 16, 3, 1, 1))
+
+        def forward(self, a, b):
+            flow, _, corr = global_correlation_softmax(a, b, True)
+            return flow, self.conv_corr(corr)
+
+    B, C, H, W, O = 2, 128, 16, 16, 40
+    torch.manual_seed(5)
+    net = Slice(H * W, O).cuda()
+    a = dev(cases.randn(31, (B, C, H, W), 1.5)).requires_grad_(True)
+    b = dev(cases.randn(32, (B, C, H, W), 1.5)).requires_grad_(True)
+    wf, wc = dev(cases.randn(33, (2 * B, 2, H, W))), dev(cases.randn(34, (B, 16, H, W)))
+
+    def run():
+        for t in (a, b):
+            t.grad = None
+        net.zero_grad()
+        flow, y = net(a, b)
+        ((flow * wf).sum() + (y * wc).sum()).backward()
+        return flow.detach(), y.detach(), a.grad.clone(), b.grad.clone(), net.conv_corr[0].weight.grad.clone()
+
+    ref = run()
+    keys = list(net.state_dict())
+    dropin.fuse_conv_corr(net)
+    assert list(net.state_dict()) == keys
+    got = run()
+    for name, r, g in zip(("flow", "y", "da", "db", "dw"), ref, got):
+        assert rel(g, r) < TOL_GRAD, name
