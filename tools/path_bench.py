@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-row benchmark of the hot path, forward and backward, on one B200.
+"""Per-row benchmark of the hot path (SURVEY.md section 8a rows a1..a5 and the 8f rows built so far), forward and
+backward, on one B200.
 
 For every row: CUDA-event time of the public op (inputs resident in HBM, L2 defeated by rotating input sets where the
 footprint is small), algorithmic FLOPs / bytes, the fraction of the measured peak that bounds it, and the CPU oracle
@@ -276,6 +277,75 @@ def main():
     fl = 2.0 * M * N * 256
     add("a5 EMIP_long memory read, B=1 T=5 (9680 slots)", 1, "frames", ms_f, ms_fb - ms_f, fl, 2.5 * fl, (2 * M + 3 * N) * 128 * 4,
         (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "exact fp32 CUDA cores (fraction shown against the bf16 tensor peak)")
+
+    # ---------------- f1: conv_corr[0] on the never-materialised cost volume, B = 16 ----------------
+    from emip_b200.conv_corr import conv_corr_first_layer
+    Of = 968
+    wq = torch.randn(Of, N, 3, 3, device=dev, generator=g) * (9 * N) ** -0.5
+    bq = 0.1 * torch.randn(Of, device=dev, generator=g)
+
+    def f1_fwd():
+        f0, f1 = sets[it[0] % 4]
+        it[0] += 1
+        with torch.no_grad():
+            return conv_corr_first_layer(f0, f1, wq, bq)
+    ms_f = gpu_time(f1_fwd, iters=10)
+    cf = None
+    if not args.no_cpu:
+        c0, c1, cwq, cbq = sets[0][0][:1].cpu(), sets[0][1][:1].cpu(), wq.cpu(), bq.cpu()     # bounded sample: 1 of 16
+
+        def c_f():
+            with torch.no_grad():
+                O.conv_corr_first_layer(c0, c1, cwq, cbq)
+        cf = cpu_time(c_f) * 16
+    fl = 16 * 2.0 * (Of * 9 * N * C + Of * N * 9 * C)
+    add("f1 conv_corr[0] on the never-materialised cost volume, B=16 (968 out channels)", 16, "pairs", ms_f, None, fl, 0,
+        16 * (2 * C * N * 4 + Of * N * 4), 0, "tensor", cf, None,
+        "two split-bf16 tcgen05 GEMMs (8.6 GFLOP/sample) instead of a 65.3 GFLOP/sample convolution over corr; "
+        "CPU = the reference composition (matmul + conv2d on corr), sample = 1 pair x 16; backward = library matmuls")
+
+    # ---------------- f3: occlusion mask, f4: convex upsampling ----------------
+    from emip_b200.warp import get_occu_mask_backward
+    from emip_b200.upsample import upsample_flow_convex
+
+    def f3_fwd():
+        return get_occu_mask_backward(fl4[:, 2:])
+    ms_f = gpu_time(f3_fwd)
+    cf = None
+    if not args.no_cpu:
+        sf = fl4[:8, 2:].cpu()
+        cf = cpu_time(lambda: O.occu_mask_backward(sf, 0.2)) * 8
+    add("f3 backward-flow occlusion mask, B=64 352x352", Bw, "images", ms_f, None, 0, 0, Bw * Hw * Ww * 3 * 4, 0, "hbm", cf, None,
+        "bilinear splat (4 atomicAdd per pixel) + threshold; CPU sample = 8 images x 8")
+    Bu = 32
+    cfl = 12.0 * torch.randn(Bu, 2, H, W, device=dev, generator=g)
+    cmask = torch.randn(Bu, 576, H, W, device=dev, generator=g)
+    wup = torch.randn(Bu, 2, 8 * H, 8 * W, device=dev, generator=g)
+
+    def f4_fwd():
+        with torch.no_grad():
+            return upsample_flow_convex(cfl, cmask)
+
+    def f4_fwd_bwd():
+        a, b = cfl.detach().requires_grad_(True), cmask.detach().requires_grad_(True)
+        upsample_flow_convex(a, b).backward(wup)
+    ms_f = gpu_time(f4_fwd)
+    ms_fb = gpu_time(f4_fwd_bwd, iters=5)
+    cf = cb = None
+    if not args.no_cpu:
+        sfl, smk, swu = cfl[:4].cpu(), cmask[:4].cpu(), wup[:4].cpu()
+
+        def c_f():
+            with torch.no_grad():
+                O.upsample_flow_convex(sfl, smk)
+
+        def c_fb():
+            a, b = sfl.clone().requires_grad_(True), smk.clone().requires_grad_(True)
+            O.upsample_flow_convex(a, b).backward(swu)
+        cf = cpu_time(c_f) * 8
+        cb = cpu_time(c_fb) * 8 - cf
+    add("f4 convex x8 flow upsampling, 2B=32", Bu, "flows", ms_f, ms_fb - ms_f, 0, 0, Bu * (576 * N + 2 * N + 2 * 64 * N) * 4,
+        Bu * (2 * 576 * N + 2 * N + 2 * 64 * N) * 4, "hbm", cf, cb, "CPU sample = 4 flows x 8")
 
     out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "cpu_threads": os.cpu_count(), "rows": rows}
     if args.json:
