@@ -768,7 +768,8 @@ int match_tc_split(const float* src, const float* src2, void* dst, int nb, int n
 
 int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   if (a.nb == 0) return EMIP_OK;
-  if (!match_tc_supported(a.nq, a.nk, 128)) { emip_set_error("match_tc_fwd: unsupported shape"); return EMIP_ENOSYS; }
+  // the value table (attention mode) holds MAXK columns; the analytic grid (matching mode) has no such limit
+  if (a.nq < 1 || a.nk < 16 || (a.grid_w <= 0 && a.nk > MAXK)) { emip_set_error("match_tc_fwd: unsupported shape"); return EMIP_ENOSYS; }
   if (a.terms != 1 && a.terms != 3) { emip_set_error("match_tc_fwd: terms must be 1 or 3"); return EMIP_EINVAL; }
   if (a.sub_grid && a.grid_w <= 0) { emip_set_error("match_tc_fwd: sub_grid needs grid_w"); return EMIP_EINVAL; }
   CUtensorMap mx, my, ms;

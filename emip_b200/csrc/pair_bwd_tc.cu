@@ -74,7 +74,10 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrt = (p.nr + TM - 1) / TM;
   const int nkt = (p.nc + TN - 1) / TN;
-  const int n_items = p.nb * nrt;
+  // an item is (problem, row tile, key split): split ks covers key tiles [ks*nkt/ns, (ks+1)*nkt/ns) and writes its own
+  // partial dX (stacked by split index; summed by the caller) -- used when nb * nrt alone cannot fill the SMs
+  const int ns = p.ksplit > 1 ? p.ksplit : 1;
+  const int n_items = p.nb * nrt * ns;
 
   if (threadIdx.x == 0) {
     mbar_init(x_full, 1);
@@ -112,7 +115,8 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int prob = item / nrt, rt = item % nrt;
+      const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
+      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
       const int xb = p.x_base + prob, yb = p.y_base + prob;
       mbar_wait(x_empty, (it & 1) ^ 1);
       if (leader) {
@@ -120,9 +124,9 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int c = 0; c < 4; ++c) tma_load_3d(sbase + OFF_X + c * CHUNK_BYTES, &map_x, x_full, c * CH_ELEMS, rt * TM, xb);
       }
       // ring order = consumption order of the issuer: Y1(0), then per tile { Y1(t+1), Y2(t) }
-      for (int c = 0; c < 4; ++c) push(&map_y1, c * CH_ELEMS, 0, yb);
-      for (int t = 0; t < nkt; ++t) {
-        if (t + 1 < nkt)
+      for (int c = 0; c < 4; ++c) push(&map_y1, c * CH_ELEMS, kb * TN, yb);
+      for (int t = kb; t < ke; ++t) {
+        if (t + 1 < ke)
           for (int c = 0; c < 4; ++c) push(&map_y1, c * CH_ELEMS, (t + 1) * TN, yb);
         for (int c = 0; c < 4; ++c)       // hi keys[0:64], hi keys[64:128], lo keys[0:64], lo keys[64:128]
           push(&map_y2, t * TN + (c & 1) * CH_ELEMS, (c >> 1) * 128, yb);
@@ -189,14 +193,16 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int ks = item % ns;
+      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
       mbar_wait(x_full, it & 1);
       tc_fence_after();
-      mma1(tile, nkt == 1);
-      for (int t = 0; t < nkt; ++t) {
-        if (t + 1 < nkt) mma1(tile + t + 1, t + 1 == nkt - 1);
-        mma2(tile + t, t == 0, t == nkt - 1);
+      mma1(tile, kb == nkt - 1);
+      for (int t = kb; t < ke; ++t) {
+        if (t + 1 < ke) mma1(tile + (t - kb) + 1, t + 1 == nkt - 1);
+        mma2(tile + (t - kb), t == kb, t == ke - 1);
       }
-      tile += nkt;
+      tile += ke - kb;
       if (leader) umma_commit(x_empty);
       __syncwarp();
     }
@@ -217,7 +223,8 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                        (reinterpret_cast<uintptr_t>(p.e) % 16) == 0;
     uint32_t tile = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int prob = item / nrt, rt = item % nrt;
+      const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
+      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
       const int row = rt * TM + quarter * 32 + lane;
       const bool row_ok = row < p.nr;
       float rL1 = 0.f, rux = 0.f, ruy = 0.f, ru0 = 0.f, rtx = 0.f, rty = 0.f;
@@ -232,7 +239,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         rty = __ldg(p.t2 + (size_t)prob * p.t2_stride_b + p.nr + row);
       }
       const float* E = extra ? p.e + (size_t)prob * p.e_stride_b + (size_t)row * p.e_stride_r : nullptr;
-      for (int kt = 0; kt < nkt; ++kt, ++tile) {
+      for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int buf = tile & 1;
         const int col_base = kt * TN;
         // per-column terms of this key tile -> smem (double-buffered; one barrier per tile orders writes and reads)
@@ -315,7 +322,7 @@ pair_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       // ---- epilogue: dX tile -> global (scaled by 1/sqrt(C): the chain through S = X Y^T / sqrt(C))
       mbar_wait(dx_full, it & 1);
       tc_fence_after();
-      float* DX = p.dx + (size_t)prob * p.nr * 128;
+      float* DX = p.dx + ((size_t)ks * p.nb + prob) * p.nr * 128;
       {
         uint32_t r[32];
         tmem_ld32_async(tmem_base + lane_base + COL_DX + (uint32_t)cb, r);
@@ -424,7 +431,7 @@ int pair_bwd_tc(const PairBwdTcArgs& a, cudaStream_t st) {
   bp.a = a;
   bp.inv_sqrt_c = 1.0f / a.sqrt_c;
   const int nrt = (a.nr + TM - 1) / TM;
-  int grid = a.nb * nrt;
+  int grid = a.nb * nrt * (a.ksplit > 1 ? a.ksplit : 1);
   if (grid > emip_num_sms()) grid = emip_num_sms();
   pair_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, my1, my2, bp);
   EMIP_CHECK_LAUNCH("pair_bwd_tc");

@@ -16,6 +16,7 @@ struct PairBwdTcArgs {
   float* dx;                 // [nb][nr*128] in dx_layout
   int nb, nr, nc, dx_layout;
   float sqrt_c;
+  int ksplit;                // > 1: split the key tiles over ksplit CTAs per row tile; dx then is [ksplit][nb][nr*128] partials
 };
 
 bool pair_bwd_tc_supported(int nr, int nc, int c);

@@ -13,21 +13,28 @@ class _MemoryRead(torch.autograd.Function):
     """out[:, :Do] = m_out softmax_m(m_in^T q_in / sqrt(De)); out[:, Do:] = q_out  (one [B,2*Do,H,W] tensor)."""
 
     @staticmethod
-    def forward(ctx, m_in, m_out, q_in, q_out):
+    def forward(ctx, m_in, m_out, q_in, q_out, exact_fp32):
         B, De, T, H, W = m_in.shape
         Do = m_out.shape[1]
         M, Q = T * H * W, H * W
         m_in, m_out, q_in = m_in.contiguous(), m_out.contiguous(), q_in.contiguous()
         L = _lib.lib()
-        L.emip_memory_read_workspace.restype = ctypes.c_size_t
-        ws, ws_ptr, ws_n = workspace(L.emip_memory_read_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device, align=256)
         out = torch.empty((B, 2 * Do, H, W), dtype=torch.float32, device=m_in.device)
         out[:, Do:] = q_out.reshape(B, Do, H, W)                      # LTM.py:66 torch.cat([mem, q_out.squeeze(2)])
         need_grad = any(ctx.needs_input_grad[:3])
         lse = torch.empty((B, Q), dtype=torch.float32, device=m_in.device) if need_grad else None
-        _lib.check(L.emip_memory_read_fwd(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse),
-                                          ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()),
-                   "emip_memory_read_fwd")
+        if exact_fp32 or M < 16:
+            L.emip_memory_read_workspace.restype = ctypes.c_size_t
+            ws, ws_ptr, ws_n = workspace(L.emip_memory_read_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device, align=256)
+            _lib.check(L.emip_memory_read_fwd(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse),
+                                              ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()),
+                       "emip_memory_read_fwd")
+        else:                                                         # tensor-core path (split-bf16, fp32 accumulate)
+            L.emip_memory_read_tc_workspace.restype = ctypes.c_size_t
+            ws, ws_ptr, ws_n = workspace(L.emip_memory_read_tc_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device)
+            _lib.check(L.emip_memory_read_fwd_tc(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse),
+                                                 ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q),
+                                                 stream_ptr()), "emip_memory_read_fwd_tc")
         ctx.save_for_backward(m_in, m_out, q_in, out, lse)
         ctx.q_out_shape = q_out.shape
         return out
@@ -46,7 +53,7 @@ class _MemoryRead(torch.autograd.Function):
         _lib.check(L.emip_memory_read_bwd(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse), ptr(dout),
                                           LL(2 * Do * Q), ptr(dm_in), ptr(dm_out), ptr(dq_in), ctypes.c_void_p(ws_ptr),
                                           SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()), "emip_memory_read_bwd")
-        return dm_in, dm_out, dq_in, dout[:, Do:].reshape(ctx.q_out_shape)
+        return dm_in, dm_out, dq_in, dout[:, Do:].reshape(ctx.q_out_shape), None
 
 
 class Memory(nn.Module):
@@ -58,6 +65,9 @@ class Memory(nn.Module):
     is not produced.
     """
 
+    #: True selects the exact-fp32 CUDA-core forward instead of the tcgen05 one (bf16 hi/lo split, fp32 accumulation)
+    exact_fp32 = False
+
     def forward(self, m_in, m_out, q_in, q_out):
         if not m_in.is_cuda:
             raise _lib.EmipError("emip_b200 memory read needs CUDA tensors (no CPU fallback)")
@@ -66,4 +76,4 @@ class Memory(nn.Module):
                 raise TypeError("emip_b200 memory read computes in fp32")
         if m_in.dim() != 5 or m_out.shape[2:] != m_in.shape[2:] or q_in.shape != (m_in.shape[0], m_in.shape[1]) + m_in.shape[3:]:
             raise ValueError("shapes must be m_in [B,De,T,H,W], m_out [B,Do,T,H,W], q_in [B,De,H,W]")
-        return _MemoryRead.apply(m_in, m_out, q_in, q_out), None
+        return _MemoryRead.apply(m_in, m_out, q_in, q_out, bool(self.exact_fp32)), None

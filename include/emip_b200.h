@@ -149,6 +149,13 @@ int emip_memory_read_bwd(const float* m_in, const float* m_out, const float* q_i
                          const float* lse, const float* dmem, long long dmem_stride_b, float* dm_in, float* dm_out,
                          float* dq_in, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
 
+/* a5 forward on the tensor cores (csrc/memory_read_tc.cu): same arguments and results as emip_memory_read_fwd
+ * (3-term split-bf16 operands, fp32 accumulation: rel-L2 ~1e-5 instead of ~1e-7); M >= 16; workspace of
+ * emip_memory_read_tc_workspace() bytes, 1024-byte aligned.  lse (optional) is what emip_memory_read_bwd takes. */
+size_t emip_memory_read_tc_workspace(int B, int De, int Do, int M, int Q);
+int emip_memory_read_fwd_tc(const float* m_in, const float* m_out, const float* q_in, float* mem, long long mem_stride_b,
+                            float* lse, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
+
 /* ---- f4: convex x8 upsampling of the coarse flow -------------------------------- */
 /* Replaces model/EMIP_short/motion/gmflow/gmflow.py:64-77, the part of GMFlow.upsample_flow after
  * `mask = self.upsampler(concat)`: softmax over the 9 taps, 3x3 unfold of k*flow, weighted sum, pixel shuffle.

@@ -298,13 +298,16 @@ def test_a4_injector_vs_oracle_batch():
 
 
 # ----------------------------------------------------------------------------- a5
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
 @pytest.mark.parametrize("name", list(cases.A5_CASES))
-def test_a5_memory_read_golden(golden, name):
+def test_a5_memory_read_golden(golden, name, exact):
     from emip_b200.memory import Memory
     g = golden(name)
     d = cases.a5_inputs(cases.A5_CASES[name])
     t = {k: dev(d[k]).requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
-    out, p = Memory()(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
+    mod = Memory()
+    mod.exact_fp32 = exact
+    out, p = mod(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
     assert p is None
     e = cases.check_packed(out, g["out"], TOL_EXACT, "out")
     (out * dev(d["wout"])).sum().backward()
@@ -312,15 +315,20 @@ def test_a5_memory_read_golden(golden, name):
     print(f"{name}: out {e:.2e} grads {errs}")
 
 
-def test_a5_memory_read_t5_vs_oracle():
-    """The largest memory the model keeps (T = 5 frames, model_long.py:105-107), B = 1, inference path."""
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
+def test_a5_memory_read_t5_vs_oracle(exact):
+    """The largest memory the model keeps (T = 5 frames, model_long.py:105-107), B = 1, inference path; and B = 3."""
     from emip_b200.memory import Memory
-    s = dict(b=1, t=5, h=44, w=44, scale=1.5, seed=57)
-    d = cases.a5_inputs(s)
-    ref, _ = O.memory_read(d["m_in"], d["m_out"], d["q_in"], d["q_out"])
-    with torch.no_grad():
-        out, _ = Memory()(dev(d["m_in"]), dev(d["m_out"]), dev(d["q_in"]), dev(d["q_out"]))
-    assert rel(out, ref) < TOL_EXACT
+    mod = Memory()
+    mod.exact_fp32 = exact
+    for s in (dict(b=1, t=5, h=44, w=44, scale=1.5, seed=57), dict(b=3, t=2, h=20, w=28, scale=4.0, seed=58)):
+        d = cases.a5_inputs(s)
+        ref, _ = O.memory_read(d["m_in"], d["m_out"], d["q_in"], d["q_out"])
+        with torch.no_grad():
+            out, _ = mod(dev(d["m_in"]), dev(d["m_out"]), dev(d["q_in"]), dev(d["q_out"]))
+        e = rel(out, ref)
+        print(f"a5 exact={exact} {s}: rel-L2 {e:.2e}")
+        assert e < TOL_EXACT
 
 
 # ----------------------------------------------------------------------------- f4 (SURVEY 8f: convex x8 upsampling)
