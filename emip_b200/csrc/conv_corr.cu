@@ -28,6 +28,7 @@
 #include "pair_common.cuh"
 #include "match_tc.cuh"
 #include "pair_bwd_tc.cuh"
+#include "gemm_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -39,7 +40,7 @@ constexpr int NMAX = 256;
 constexpr int THREADS = 6 * 32;
 
 struct CcParams {
-  int mode;                 // 0: G = Wp f1^T (split-bf16 output)   1: out = conv3x3(f0; G) + bias (fp32 output)
+  int mode;                 // 0: G = Wp f1^T (split-bf16 output)   1: out = conv3x3(f0; G) + bias (fp32 output)   2: gemm_nn
   int M;                    // rows of A / of the output (mode 0: O*9, mode 1: O)
   int n_mtiles, n_ntiles;   // tiles per sample
   int n_tile;               // UMMA N (mode 0: 128 channels, mode 1: R*W pixels)
@@ -51,6 +52,11 @@ struct CcParams {
   __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, then lo
   __nv_bfloat16* g_lo;
   float* out;               // mode 1 output: [B][M][H*W]
+  // mode 2: y[b][m][n] = sum_k A(b)[m][k] Bt[b][n][k] (+ res): A = weights (shared: a_batched = 0), Bt = token-major
+  // activations [B][N][2*Kp] (hi | lo); y / res rows are ldy / ldr floats apart
+  int a_batched, Kp, N;
+  float* y; long long y_stride_b; int ldy;
+  const float* res; long long res_stride_b; int ldr;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -102,6 +108,12 @@ conv_corr_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           // f1 channel-major [b][256 = hi c | lo c][ld]: rows 0..127 hi, 128..255 lo
           tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, 0, b);
           tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), kc * KCH, 128, b);
+        } else if (p.mode == 2) {
+          const int ab = p.a_batched ? b : 0;
+          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, ab);
+          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, nt * TM, b);
+          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + kc * KCH, nt * TM, b);
         } else {
           tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
           tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
@@ -170,6 +182,35 @@ conv_corr_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           for (int i = 0; i < 4; ++i) {
             dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
             dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      }
+    } else if (p.mode == 2) {
+      const int n0 = nt * TM;
+      float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
+      const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
+      for (int c0 = 0; c0 < TM; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        const int n = min(32, p.N - n0 - c0);
+        if (row < p.M && n > 0) {
+          if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs + c0) & 15) == 0)) {
+            float4* d = reinterpret_cast<float4*>(o + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                     __uint_as_float(r[4 * i + 3]));
+              if (rs) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+              }
+              d[i] = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + (rs ? __ldg(rs + c0 + i) : 0.f);
           }
         }
       }
@@ -263,6 +304,63 @@ int rows_per_tile(int H, int W) {
     if ((r * W) % 16 == 0) best = r;
   return best;
 }
+
+// ---- gemm_nn on the tensor cores (the Injector's 1x1 convolutions) ------------------------------------------
+// weights W(b)[m][k] fp32 -> hi, lo bf16 [nbw][M][Kp] (zero padded to Kp)
+__global__ void __launch_bounds__(256)
+split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, __nv_bfloat16* __restrict__ hi,
+               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)M * Kp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / Kp), k = (int)(i % Kp);
+    const float v = k < K ? __ldg(w + (size_t)b * w_stride_b + (size_t)m * ldw + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[(size_t)b * n + i] = h;
+    lo[(size_t)b * n + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// activations x[b][k][n] fp32 (rows ldx apart), optional LayerNorm over k -> token-major bf16 [b][n][2*Kp] (hi | lo)
+// One thread = one token x 32 channels (lanes = consecutive tokens: coalesced reads; 64-byte hi and lo segments out).
+__global__ void __launch_bounds__(128)
+split_act_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ dst, int K, int Kp, int N) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= N) return;
+  const float* s = x + (size_t)b * x_stride_b + (size_t)chunk * 32 * ldx + tok;
+  float mu = 0.f, rs = 1.f;
+  if (mean != nullptr) { mu = __ldg(mean + (size_t)b * N + tok); rs = __ldg(rstd + (size_t)b * N + tok); }
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = chunk * 32 + i;
+    float t = k < K ? __ldg(s + (size_t)i * ldx) : 0.f;
+    if (mean != nullptr && k < K) t = (t - mu) * rs * __ldg(gamma + k) + __ldg(beta + k);
+    v[i] = t;
+  }
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
+                                                 __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + chunk * 32);
+  uint4* dl = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + Kp + chunk * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+  }
+}
+
+int kpad(int K) { return (K + KCH - 1) / KCH * KCH; }
 
 struct Ws {
   void* f0_tok;        // bf16 [B][N][256]
@@ -385,5 +483,66 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
     conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem_for(p.stages, p.stage_bytes), st>>>(ma_hi, ma_lo, mb, p);
     EMIP_CHECK_LAUNCH("conv_corr_fwd (conv)");
   }
+  return EMIP_OK;
+}
+
+bool gemm_nn_tc_supported(const GemmNN& a) {
+  return !a.w_trans && !a.accumulate && a.K >= 1 && a.K <= 384 && a.M >= 1 && a.N >= 1 && a.ldy % 4 == 0 &&
+         reinterpret_cast<uintptr_t>(a.y) % 16 == 0 && a.y_stride_b % 4 == 0;
+}
+
+size_t gemm_nn_tc_scratch_bytes(int B, int M, int K, int N, bool per_sample_w) {
+  const size_t Kp = (size_t)kpad(K);
+  return emip_align_up((size_t)(per_sample_w ? B : 1) * M * Kp * 2 * 2, 1024) + emip_align_up((size_t)B * N * 2 * Kp * 2, 1024) + 1024;
+}
+
+int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
+  if (!gemm_nn_tc_supported(a)) { emip_set_error("gemm_nn_tc: unsupported arguments"); return EMIP_ENOSYS; }
+  const bool per_sample = a.w_stride_b != 0;
+  const int Kp = kpad(a.K), nbw = per_sample ? a.B : 1;
+  if (scratch == nullptr || scratch_bytes < gemm_nn_tc_scratch_bytes(a.B, a.M, a.K, a.N, per_sample)) {
+    emip_set_error("gemm_nn_tc: scratch too small");
+    return EMIP_ENOMEM;
+  }
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* w_lo = w_hi + (size_t)nbw * a.M * Kp;
+  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)nbw * a.M * Kp * 2 * 2, 1024));
+  split_w_kernel<<<dim3((unsigned)(((size_t)a.M * Kp + 255) / 256), nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, w_hi, w_lo, a.M,
+                                                                                    a.K, Kp);
+  EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
+  split_act_kernel<<<dim3((a.N + 127) / 128, Kp / 32, a.B), 128, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta,
+                                                                        bt, a.K, Kp, a.N);
+  EMIP_CHECK_LAUNCH("gemm_nn_tc (activations)");
+  CUtensorMap ma_hi, ma_lo, mb;
+  int rc;
+  const cuuint64_t adims[3] = {(cuuint64_t)Kp, (cuuint64_t)a.M, (cuuint64_t)nbw};
+  const cuuint64_t astr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)a.M * Kp * 2};
+  const cuuint32_t abox[3] = {KCH, TM, 1};
+  if ((rc = make_map_bf16(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
+  if ((rc = make_map_bf16(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
+  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)a.N, (cuuint64_t)a.B};
+  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)a.N * 2 * Kp * 2};
+  const cuuint32_t bbox[3] = {KCH, TM, 1};
+  if ((rc = make_map_bf16(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  CcParams p = {};
+  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.N + TM - 1) / TM; p.n_tile = TM;
+  p.kchunks = Kp / KCH;
+  p.b_bytes = TM * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
+  p.stages = p.kchunks < 3 ? p.kchunks : 3;
+  p.a_batched = per_sample ? 1 : 0; p.Kp = Kp; p.N = a.N;
+  p.y = a.y; p.y_stride_b = a.y_stride_b; p.ldy = a.ldy;
+  p.res = a.res; p.res_stride_b = a.res_stride_b; p.ldr = a.ldr;
+  const long long grid = (long long)a.B * p.n_mtiles * p.n_ntiles;
+  EMIP_CHECK_ARG(grid < 0x7fffffffLL, "gemm_nn_tc: problem too large");
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+  conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem, st>>>(ma_hi, ma_lo, mb, p);
+  EMIP_CHECK_LAUNCH("gemm_nn_tc");
   return EMIP_OK;
 }

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "../../include/emip_b200.h"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -861,8 +862,18 @@ int check_common(const char* who, int B, int H, int W) {
 }  // namespace
 
 // ------------------------------------------------------------------ public GEMM helpers (gemm_simt.cuh)
+// Set by emip_injector_fwd_ex for the duration of a forward call on this thread: scratch for the tensor-core GEMMs.
+struct TcScope {
+  void* ws = nullptr;
+  size_t bytes = 0;
+};
+static thread_local TcScope g_tc;
+
 int gemm_nn(const GemmNN& a, cudaStream_t st) {
   if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
+  if (g_tc.ws != nullptr && gemm_nn_tc_supported(a) &&
+      g_tc.bytes >= gemm_nn_tc_scratch_bytes(a.B, a.M, a.K, a.N, a.w_stride_b != 0))
+    return gemm_nn_tc(a, g_tc.ws, g_tc.bytes, st);
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   const bool fast = a.N % 4 == 0 && a.ldx % 4 == 0 && a.ldy % 4 == 0 && a.x_stride_b % 4 == 0 && a.y_stride_b % 4 == 0 &&
                     al16(a.x) && al16(a.y) && al16(a.w) && a.w_stride_b % 4 == 0 &&
@@ -907,6 +918,17 @@ int reduce_batch(const float* in, long long stride, float* out, int B, long long
   return EMIP_OK;
 }
 
+// largest scratch any of the five forward GEMMs needs (they run one after the other)
+static size_t tc_scratch_bytes(int B, int N) {
+  size_t m = 0;
+  const int shapes[5][3] = {{DIM, DIM, 0}, {2 * DIM, DIM, 0}, {DIM, DIM, 1}, {HID2, DIM, 0}, {DIM, HID, 0}};   // M, K, per-sample W
+  for (auto& sh : shapes) {
+    const size_t b = gemm_nn_tc_scratch_bytes(B, sh[0], sh[1], N, sh[2] != 0);
+    if (b > m) m = b;
+  }
+  return emip_align_up(m, 256);
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" size_t emip_injector_saved_bytes(int B, int H, int W) {
   if (B < 0 || H <= 0 || W <= 0) return 0;
@@ -922,12 +944,19 @@ extern "C" size_t emip_injector_workspace(int B, int H, int W) {
   s += al((size_t)B * DIM * DIM) * 2 + al((size_t)B * HEADS * HD * HD) + 4 * al((size_t)B * DIM);
   s += al((size_t)B * HID2 * 9) + 2 * al((size_t)B * DIM) + al((size_t)B * HEADS);
   s += al((size_t)B * HEADS * G_SPLIT * HD * HD);
+  s += tc_scratch_bytes(B, (int)N);                                // bf16 hi|lo operands of the tensor-core forward GEMMs
   return s;
 }
 
 extern "C" int emip_injector_fwd(const float* x, const float* x1, const float* const* params, float* out, void* saved,
                                  size_t saved_bytes_in, void* workspace, size_t ws_bytes, int B, int H, int W,
                                  void* stream) {
+  return emip_injector_fwd_ex(x, x1, params, out, saved, saved_bytes_in, workspace, ws_bytes, B, H, W, 0, stream);
+}
+
+extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float* const* params, float* out, void* saved,
+                                    size_t saved_bytes_in, void* workspace, size_t ws_bytes, int B, int H, int W, int flags,
+                                    void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && x1 && params && out && saved && workspace, "injector_fwd: null pointer");
   int rc = check_common("injector_fwd", B, H, W);
@@ -946,6 +975,15 @@ extern "C" int emip_injector_fwd(const float* x, const float* x1, const float* c
   }
   Carver w{static_cast<char*>(workspace), ws_bytes, true};
   float* g = w.take((size_t)B * HID * N);
+  // The five 1x1 convolutions run on the tensor cores (3-term split-bf16, fp32 accumulate; gemm_tc.cuh) unless the
+  // caller asks for the exact-fp32 CUDA-core GEMMs.  LayerNorm is applied while the activations are re-laid out.
+  struct Scope {
+    ~Scope() { g_tc = TcScope(); }
+  } scope;
+  if (!(flags & EMIP_FLAG_EXACT_FP32)) {
+    g_tc.bytes = tc_scratch_bytes(B, N);
+    g_tc.ws = reinterpret_cast<char*>(workspace) + (ws_bytes - g_tc.bytes) / 256 * 256;   // the tail of the workspace
+  }
 
   // norm1 / norm2 statistics (PromptInteract.py:447, :346-349)
   if ((rc = launch_ln_stats(x, s.mean1, s.rstd1, B, DIM, N, st))) return rc;

@@ -34,7 +34,7 @@ def _ptr_array(tensors):
 
 class _InjectorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, x1, *params):
+    def forward(ctx, x, x1, flags, *params):
         B, C, H, W = x.shape
         x = x.contiguous()
         x1 = x1.contiguous()
@@ -46,9 +46,9 @@ class _InjectorFn(torch.autograd.Function):
         saved, saved_ptr, _ = workspace(nsaved, x.device, align=256)
         ws, ws_ptr, ws_n = workspace(L.emip_injector_workspace(I(B), I(H), I(W)), x.device, align=256)
         out = torch.empty_like(x)
-        _lib.check(L.emip_injector_fwd(ptr(x), ptr(x1), _ptr_array(params), ptr(out), ctypes.c_void_p(saved_ptr),
-                                       SZ(nsaved), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(H), I(W), stream_ptr()),
-                   "emip_injector_fwd")
+        _lib.check(L.emip_injector_fwd_ex(ptr(x), ptr(x1), _ptr_array(params), ptr(out), ctypes.c_void_p(saved_ptr),
+                                          SZ(nsaved), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(H), I(W), I(flags),
+                                          stream_ptr()), "emip_injector_fwd_ex")
         ctx.save_for_backward(x, x1, saved, *params)
         ctx.saved_ptr, ctx.nsaved = saved_ptr, nsaved
         return out
@@ -66,11 +66,14 @@ class _InjectorFn(torch.autograd.Function):
         _lib.check(L.emip_injector_bwd(ptr(x), ptr(x1), _ptr_array(params), ctypes.c_void_p(ctx.saved_ptr), SZ(ctx.nsaved),
                                        ptr(dout), ptr(dx), ptr(dx1), _ptr_array(dparams), ctypes.c_void_p(ws_ptr),
                                        SZ(ws_n), I(B), I(H), I(W), stream_ptr()), "emip_injector_bwd")
-        return (dx, dx1, *dparams)
+        return (dx, dx1, None, *dparams)
 
 
-def injector_forward(x, x1, params):
-    """Functional form: ``params`` maps PARAM_KEYS (or is a sequence in that order) to tensors."""
+def injector_forward(x, x1, params, exact_fp32=False):
+    """Functional form: ``params`` maps PARAM_KEYS (or is a sequence in that order) to tensors.
+
+    ``exact_fp32=True`` runs the five 1x1 convolutions of the forward as exact-fp32 CUDA-core GEMMs instead of tcgen05
+    GEMMs on bf16 hi/lo split operands with fp32 accumulation (rel-L2 ~1e-5).  The backward is exact fp32 either way."""
     if not (x.is_cuda and x1.is_cuda):
         raise _lib.EmipError("emip_b200 injector needs CUDA tensors (no CPU fallback)")
     if x.dtype != torch.float32 or x1.dtype != torch.float32:
@@ -78,7 +81,7 @@ def injector_forward(x, x1, params):
     if x.shape != x1.shape or x.dim() != 4 or x.shape[1] != DIM:
         raise ValueError(f"injector expects two [B,{DIM},H,W] tensors, got {tuple(x.shape)} and {tuple(x1.shape)}")
     plist = [params[k] for k in PARAM_KEYS] if isinstance(params, dict) else list(params)
-    return _InjectorFn.apply(x, x1, *plist)
+    return _InjectorFn.apply(x, x1, 1 if exact_fp32 else 0, *plist)
 
 
 class _WithBiasLayerNorm(nn.Module):            # PromptInteract.py:333-349 (parameters only)
@@ -126,9 +129,12 @@ class TransformerBlock_MDTA(nn.Module):         # PromptInteract.py:436-450
         self.ffn = _FeedForward(dim, HIDDEN)
         self.norm3 = _LayerNorm(dim)
 
+    #: True selects the exact-fp32 CUDA-core GEMMs in the forward (see injector_forward)
+    exact_fp32 = False
+
     def forward(self, x, x1):
         p = dict(self.named_parameters())
-        return injector_forward(x, x1, [p[k] for k in PARAM_KEYS])
+        return injector_forward(x, x1, [p[k] for k in PARAM_KEYS], self.exact_fp32)
 
 
 class Injector(nn.Module):

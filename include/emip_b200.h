@@ -129,6 +129,10 @@ size_t emip_injector_saved_bytes(int B, int H, int W);
 size_t emip_injector_workspace(int B, int H, int W);
 int emip_injector_fwd(const float* x, const float* x1, const float* const* params, float* out, void* saved,
                       size_t saved_bytes, void* workspace, size_t ws_bytes, int B, int H, int W, void* stream);
+/* Same with flags: 0 = the five 1x1 convolutions on the tensor cores (3-term split-bf16 operands, fp32 accumulation,
+ * rel-L2 ~1e-5), EMIP_FLAG_EXACT_FP32 = exact-fp32 CUDA-core GEMMs.  emip_injector_fwd == flags 0. */
+int emip_injector_fwd_ex(const float* x, const float* x1, const float* const* params, float* out, void* saved,
+                         size_t saved_bytes, void* workspace, size_t ws_bytes, int B, int H, int W, int flags, void* stream);
 int emip_injector_bwd(const float* x, const float* x1, const float* const* params, const void* saved, size_t saved_bytes,
                       const float* dout, float* dx, float* dx1, float* const* dparams, void* workspace, size_t ws_bytes,
                       int B, int H, int W, void* stream);
