@@ -306,19 +306,45 @@ int rows_per_tile(int H, int W) {
 }
 
 // ---- gemm_nn on the tensor cores (the Injector's 1x1 convolutions) ------------------------------------------
-// weights W(b)[m][k] fp32 -> hi, lo bf16 [nbw][M][Kp] (zero padded to Kp)
-__global__ void __launch_bounds__(256)
-split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, __nv_bfloat16* __restrict__ hi,
-               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp) {
-  const int b = blockIdx.y;
-  const size_t n = (size_t)M * Kp;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / Kp), k = (int)(i % Kp);
-    const float v = k < K ? __ldg(w + (size_t)b * w_stride_b + (size_t)m * ldw + k) : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[(size_t)b * n + i] = h;
-    lo[(size_t)b * n + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+// 8 fp32 -> 8 bf16 hi + 8 bf16 lo (two 16-byte stores)
+__device__ __forceinline__ void split8_store(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
+                                                  __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// weights / row operands W(b)[m][k] fp32 -> hi, lo bf16 [nbw][M][Kp] (zero padded to Kp; Kp % 64 == 0).
+// grid (ceil(Kp / 2048), M, nbw): one row per blockIdx.y, 8 consecutive k per thread.
+__global__ void __launch_bounds__(256)
+split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int trans, __nv_bfloat16* __restrict__ hi,
+               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp) {
+  const int b = blockIdx.z, m = blockIdx.y;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (k0 >= Kp) return;
+  const float* src = w + (size_t)b * w_stride_b;
+  float v[8];
+  if (!trans && k0 + 8 <= K && (ldw & 3) == 0 && (w_stride_b & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)m * ldw + k0));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(src + (size_t)m * ldw + k0 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      v[i] = k < K ? __ldg(src + (trans ? (size_t)k * ldw + m : (size_t)m * ldw + k)) : 0.f;
+    }
+  }
+  const size_t o = ((size_t)b * M + m) * Kp + k0;
+  split8_store(v, hi + o, lo + o);
 }
 
 // activations x[b][k][n] fp32 (rows ldx apart), optional LayerNorm over k -> token-major bf16 [b][n][2*Kp] (hi | lo)
@@ -358,6 +384,35 @@ split_act_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, con
     dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
     dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
   }
+}
+
+// B'(b)[k][n] fp32 (rows ldb apart), optional LayerNorm over k -> bf16 [b][k][2*Np] (hi | lo), zero padded to Np.
+// grid (ceil(Np / 2048), K, B): 8 consecutive n per thread.
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  __nv_bfloat16* __restrict__ dst, int K, int N, int Np) {
+  const int b = blockIdx.z, k = blockIdx.y;
+  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (n0 >= Np) return;
+  const float ga = mean != nullptr ? __ldg(gamma + k) : 1.f, be = mean != nullptr ? __ldg(beta + k) : 0.f;
+  const float* src = x + (size_t)b * x_stride_b + (size_t)k * ldx;
+  float v[8];
+  const bool vec = n0 + 8 <= N && (ldx & 3) == 0 && (x_stride_b & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (N & 3) == 0;
+  if (vec) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + n0)), c = __ldg(reinterpret_cast<const float4*>(src + n0 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = n0 + i < N ? __ldg(src + n0 + i) : 0.f;
+  }
+  if (mean != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (n0 + i < N) v[i] = (v[i] - __ldg(mean + (size_t)b * N + n0 + i)) * __ldg(rstd + (size_t)b * N + n0 + i) * ga + be;
+  }
+  __nv_bfloat16* d = dst + ((size_t)b * K + k) * 2 * Np + n0;
+  split8_store(v, d, d + Np);
 }
 
 int kpad(int K) { return (K + KCH - 1) / KCH * KCH; }
@@ -487,7 +542,7 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
 }
 
 bool gemm_nn_tc_supported(const GemmNN& a) {
-  return !a.w_trans && !a.accumulate && a.K >= 1 && a.K <= 384 && a.M >= 1 && a.N >= 1 && a.ldy % 4 == 0 &&
+  return !a.accumulate && a.K >= 1 && a.K <= 1024 && a.M >= 1 && a.N >= 1 && a.ldy % 4 == 0 &&
          reinterpret_cast<uintptr_t>(a.y) % 16 == 0 && a.y_stride_b % 4 == 0;
 }
 
@@ -509,8 +564,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* w_lo = w_hi + (size_t)nbw * a.M * Kp;
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)nbw * a.M * Kp * 2 * 2, 1024));
-  split_w_kernel<<<dim3((unsigned)(((size_t)a.M * Kp + 255) / 256), nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, w_hi, w_lo, a.M,
-                                                                                    a.K, Kp);
+  split_w_kernel<<<dim3((Kp + 2047) / 2048, a.M, nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, a.w_trans, w_hi, w_lo, a.M, a.K, Kp);
   EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
   split_act_kernel<<<dim3((a.N + 127) / 128, Kp / 32, a.B), 128, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta,
                                                                         bt, a.K, Kp, a.N);
@@ -544,5 +598,64 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
   conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem, st>>>(ma_hi, ma_lo, mb, p);
   EMIP_CHECK_LAUNCH("gemm_nn_tc");
+  return EMIP_OK;
+}
+
+// C[b][m][k] = sum_n A(b)[m][n] B'(b)[k][n]: the weight-gradient GEMMs (contraction over the contiguous pixel axis, so
+// both operands are K-major as they lie in memory and only need the elementwise hi|lo split)
+bool gemm_nt_tc_supported(const GemmNT& a) {
+  return a.M >= 1 && a.K >= 1 && a.N >= 16 && a.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(a.c) % 16 == 0 && a.c_stride_b % 4 == 0;
+}
+
+size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N) {
+  const size_t Np = (size_t)kpad(N);
+  return emip_align_up((size_t)B * M * Np * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
+}
+
+int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
+  if (!gemm_nt_tc_supported(a)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
+  if (scratch == nullptr || scratch_bytes < gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N)) {
+    emip_set_error("gemm_nt_tc: scratch too small");
+    return EMIP_ENOMEM;
+  }
+  const int Np = kpad(a.N);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* a_lo = a_hi + (size_t)a.B * a.M * Np;
+  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)a.B * a.M * Np * 2 * 2, 1024));
+  split_w_kernel<<<dim3((Np + 2047) / 2048, a.M, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np);
+  EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
+  split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,
+                                                                    a.K, a.N, Np);
+  EMIP_CHECK_LAUNCH("gemm_nt_tc (B)");
+  CUtensorMap ma_hi, ma_lo, mb;
+  int rc;
+  const cuuint64_t adims[3] = {(cuuint64_t)Np, (cuuint64_t)a.M, (cuuint64_t)a.B};
+  const cuuint64_t astr[2] = {(cuuint64_t)Np * 2, (cuuint64_t)a.M * Np * 2};
+  const cuuint32_t abox[3] = {KCH, TM, 1};
+  if ((rc = make_map_bf16(&ma_hi, a_hi, 3, adims, astr, abox))) return rc;
+  if ((rc = make_map_bf16(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
+  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Np, (cuuint64_t)a.K, (cuuint64_t)a.B};
+  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)a.K * 2 * Np * 2};
+  const cuuint32_t bbox[3] = {KCH, TM, 1};
+  if ((rc = make_map_bf16(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  CcParams p = {};
+  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.K + TM - 1) / TM; p.n_tile = TM;
+  p.kchunks = Np / KCH;
+  p.b_bytes = TM * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
+  p.stages = p.kchunks < 3 ? p.kchunks : 3;
+  p.a_batched = 1; p.Kp = Np; p.N = a.K;
+  p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
+  const long long grid = (long long)a.B * p.n_mtiles * p.n_ntiles;
+  EMIP_CHECK_ARG(grid < 0x7fffffffLL, "gemm_nt_tc: problem too large");
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+  conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem, st>>>(ma_hi, ma_lo, mb, p);
+  EMIP_CHECK_LAUNCH("gemm_nt_tc");
   return EMIP_OK;
 }

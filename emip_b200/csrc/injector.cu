@@ -834,16 +834,16 @@ bool carve_saved(void* buf, size_t bytes, int B, int N, Saved* s) {
   return c.ok;
 }
 // pixel-axis splits of the weight-gradient GEMMs: enough (batch x split x output tiles) CTAs for two per SM
-int nt_split(int B, int M, int K) {
+int nt_split_simt(int B, int M, int K) {
   const int tiles = ((M + 127) / 128) * ((K + 127) / 128);
   int s = (2 * emip_num_sms() + B * tiles - 1) / (B * tiles);
   return s < 1 ? 1 : (s > 16 ? 16 : s);
 }
-size_t nt_part_floats(int B) {       // largest partial buffer any of the backward's NT GEMMs needs
+size_t nt_part_floats(int B) {       // largest partial buffer any of the backward's NT GEMMs needs (CUDA-core path)
   size_t m = 0;
   const int shp[5][2] = {{DIM, HID}, {HID2, DIM}, {DIM, DIM}, {2 * DIM, DIM}, {DIM, DIM}};
   for (auto& sh : shp) {
-    const size_t v = (size_t)B * nt_split(B, sh[0], sh[1]) * sh[0] * sh[1];
+    const size_t v = (size_t)B * nt_split_simt(B, sh[0], sh[1]) * sh[0] * sh[1];
     m = v > m ? v : m;
   }
   return m;
@@ -891,8 +891,13 @@ int gemm_nn(const GemmNN& a, cudaStream_t st) {
   return EMIP_OK;
 }
 // nsplit partial results per batch entry: c must hold B*nsplit matrices (c_stride_b apart)
+// pixel-axis splits of a weight-gradient GEMM: the tensor-core path produces one partial per batch entry
+static int nt_split(int B, int M, int K) { return g_tc.ws != nullptr ? 1 : nt_split_simt(B, M, K); }
+
 static int gemm_nt_split(const GemmNT& a, int nsplit, cudaStream_t st) {
   if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
+  if (nsplit == 1 && g_tc.ws != nullptr && gemm_nt_tc_supported(a) && g_tc.bytes >= gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N))
+    return gemm_nt_tc(a, g_tc.ws, g_tc.bytes, st);
   GemmNTk p;
   p.g = a;
   p.nsplit = nsplit;
@@ -918,12 +923,20 @@ int reduce_batch(const float* in, long long stride, float* out, int B, long long
   return EMIP_OK;
 }
 
-// largest scratch any of the five forward GEMMs needs (they run one after the other)
+// largest scratch any of the forward / backward tensor-core GEMMs needs (they run one after the other)
 static size_t tc_scratch_bytes(int B, int N) {
   size_t m = 0;
-  const int shapes[5][3] = {{DIM, DIM, 0}, {2 * DIM, DIM, 0}, {DIM, DIM, 1}, {HID2, DIM, 0}, {DIM, HID, 0}};   // M, K, per-sample W
-  for (auto& sh : shapes) {
-    const size_t b = gemm_nn_tc_scratch_bytes(B, sh[0], sh[1], N, sh[2] != 0);
+  // gemm_nn: batch factor, M, K, per-sample W
+  const int nn[9][4] = {{1, DIM, DIM, 0}, {1, 2 * DIM, DIM, 0}, {1, DIM, DIM, 1}, {1, HID2, DIM, 0}, {1, DIM, HID, 0},
+                        {1, HID, DIM, 0}, {1, DIM, HID2, 0}, {1, DIM, 2 * DIM, 0}, {HEADS, HD, HD, 1}};
+  for (auto& sh : nn) {
+    const size_t b = gemm_nn_tc_scratch_bytes(B * sh[0], sh[1], sh[2], N, sh[3] != 0);
+    if (b > m) m = b;
+  }
+  // gemm_nt: M, K
+  const int nt[5][2] = {{DIM, HID}, {HID2, DIM}, {DIM, DIM}, {2 * DIM, DIM}, {DIM, DIM}};
+  for (auto& sh : nt) {
+    const size_t b = gemm_nt_tc_scratch_bytes(B, sh[0], sh[1], N);
     if (b > m) m = b;
   }
   return emip_align_up(m, 256);
@@ -1052,6 +1065,13 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
 extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* const* params, const void* saved,
                                  size_t saved_bytes_in, const float* dout, float* dx, float* dx1, float* const* dparams,
                                  void* workspace, size_t ws_bytes, int B, int H, int W, void* stream) {
+  return emip_injector_bwd_ex(x, x1, params, saved, saved_bytes_in, dout, dx, dx1, dparams, workspace, ws_bytes, B, H, W, 0,
+                              stream);
+}
+
+extern "C" int emip_injector_bwd_ex(const float* x, const float* x1, const float* const* params, const void* saved,
+                                    size_t saved_bytes_in, const float* dout, float* dx, float* dx1, float* const* dparams,
+                                    void* workspace, size_t ws_bytes, int B, int H, int W, int flags, void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && x1 && params && saved && dout && dx && dx1 && dparams && workspace, "injector_bwd: null pointer");
   int rc = check_common("injector_bwd", B, H, W);
@@ -1070,6 +1090,14 @@ extern "C" int emip_injector_bwd(const float* x, const float* x1, const float* c
     return EMIP_ENOMEM;
   }
   Carver w{static_cast<char*>(workspace), ws_bytes, true};
+  // input- and weight-gradient GEMMs on the tensor cores unless the caller asks for exact fp32 (see emip_injector_fwd_ex)
+  struct Scope {
+    ~Scope() { g_tc = TcScope(); }
+  } scope;
+  if (!(flags & EMIP_FLAG_EXACT_FP32)) {
+    g_tc.bytes = tc_scratch_bytes(B, N);
+    g_tc.ws = reinterpret_cast<char*>(workspace) + (ws_bytes - g_tc.bytes) / 256 * 256;   // the tail of the workspace
+  }
   float* g = w.take((size_t)B * HID * N);
   float* dg = w.take((size_t)B * HID * N);
   float* dtpre = w.take((size_t)B * HID2 * N);

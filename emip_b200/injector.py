@@ -51,6 +51,7 @@ class _InjectorFn(torch.autograd.Function):
                                           stream_ptr()), "emip_injector_fwd_ex")
         ctx.save_for_backward(x, x1, saved, *params)
         ctx.saved_ptr, ctx.nsaved = saved_ptr, nsaved
+        ctx.flags = flags
         return out
 
     @staticmethod
@@ -63,9 +64,9 @@ class _InjectorFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx, dx1 = torch.empty_like(x), torch.empty_like(x1)
         dparams = [torch.empty_like(p) for p in params]
-        _lib.check(L.emip_injector_bwd(ptr(x), ptr(x1), _ptr_array(params), ctypes.c_void_p(ctx.saved_ptr), SZ(ctx.nsaved),
-                                       ptr(dout), ptr(dx), ptr(dx1), _ptr_array(dparams), ctypes.c_void_p(ws_ptr),
-                                       SZ(ws_n), I(B), I(H), I(W), stream_ptr()), "emip_injector_bwd")
+        _lib.check(L.emip_injector_bwd_ex(ptr(x), ptr(x1), _ptr_array(params), ctypes.c_void_p(ctx.saved_ptr), SZ(ctx.nsaved),
+                                          ptr(dout), ptr(dx), ptr(dx1), _ptr_array(dparams), ctypes.c_void_p(ws_ptr),
+                                          SZ(ws_n), I(B), I(H), I(W), I(ctx.flags), stream_ptr()), "emip_injector_bwd_ex")
         return (dx, dx1, None, *dparams)
 
 
@@ -73,7 +74,7 @@ def injector_forward(x, x1, params, exact_fp32=False):
     """Functional form: ``params`` maps PARAM_KEYS (or is a sequence in that order) to tensors.
 
     ``exact_fp32=True`` runs the five 1x1 convolutions of the forward as exact-fp32 CUDA-core GEMMs instead of tcgen05
-    GEMMs on bf16 hi/lo split operands with fp32 accumulation (rel-L2 ~1e-5).  The backward is exact fp32 either way."""
+    GEMMs on bf16 hi/lo split operands with fp32 accumulation (rel-L2 ~1e-5), in the forward and in the backward."""
     if not (x.is_cuda and x1.is_cuda):
         raise _lib.EmipError("emip_b200 injector needs CUDA tensors (no CPU fallback)")
     if x.dtype != torch.float32 or x1.dtype != torch.float32:

@@ -136,6 +136,10 @@ int emip_injector_fwd_ex(const float* x, const float* x1, const float* const* pa
 int emip_injector_bwd(const float* x, const float* x1, const float* const* params, const void* saved, size_t saved_bytes,
                       const float* dout, float* dx, float* dx1, float* const* dparams, void* workspace, size_t ws_bytes,
                       int B, int H, int W, void* stream);
+/* Same with flags (0 = input- and weight-gradient GEMMs on the tensor cores, EMIP_FLAG_EXACT_FP32 = CUDA cores). */
+int emip_injector_bwd_ex(const float* x, const float* x1, const float* const* params, const void* saved, size_t saved_bytes,
+                         const float* dout, float* dx, float* dx1, float* const* dparams, void* workspace, size_t ws_bytes,
+                         int B, int H, int W, int flags, void* stream);
 
 /* ---- a5: EMIP_long memory read (historical-feature prompt) ------------------------------------ */
 /* Replaces model/EMIP_long/LTM.py:49-68 Memory.forward(m_in, m_out, q_in, q_out):

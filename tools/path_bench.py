@@ -245,7 +245,7 @@ def main():
         cb = cpu_time(c_fb) * 4 - cf
     fl = B4 * 0.86e9
     add("a4 prompt fusion (Injector), B=16", B4, "calls", ms_f, ms_fb - ms_f, fl, 2 * fl, B4 * 3 * C * N * 4, B4 * 5 * C * N * 4,
-        "hbm", cf, cb, "exact fp32 CUDA cores; 0.86 GFLOP and 2.97 MB algorithmic per sample; CPU sample = 4 x 4")
+        "hbm", cf, cb, "1x1-conv GEMMs on tcgen05 (split-bf16, fp32 accumulate), the rest exact fp32 CUDA cores; 0.86 GFLOP and 2.97 MB algorithmic per sample; CPU sample = 4 x 4")
 
     # ---------------- a5: memory read, B = 1, T = 5 ----------------
     d5 = cases.a5_inputs(dict(b=1, t=5, h=44, w=44, scale=1.5, seed=57))
@@ -276,7 +276,7 @@ def main():
     M = 5 * N
     fl = 2.0 * M * N * 256
     add("a5 EMIP_long memory read, B=1 T=5 (9680 slots)", 1, "frames", ms_f, ms_fb - ms_f, fl, 2.5 * fl, (2 * M + 3 * N) * 128 * 4,
-        (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "exact fp32 CUDA cores (fraction shown against the bf16 tensor peak)")
+        (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "forward on tcgen05 (lse pass + e^(S-L) V pass, split-bf16), backward exact fp32 CUDA cores")
 
     # ---------------- f1: conv_corr[0] on the never-materialised cost volume, B = 16 ----------------
     from emip_b200.conv_corr import conv_corr_first_layer
