@@ -80,6 +80,18 @@ def install(strict=False):
     except Exception:
         if strict:
             raise
+    # method patch: the fused photometric loss term
+    try:
+        lf = sys.modules.get("loss.loss_flow") or importlib.import_module("loss.loss_flow")
+        from .photometric import loss_photomatric
+        key = ("loss.loss_flow", "unFlowLoss.loss_photomatric")
+        if key not in _saved:
+            _saved[key] = lf.unFlowLoss.loss_photomatric
+        lf.unFlowLoss.loss_photomatric = loss_photomatric
+        done.append("loss.loss_flow.unFlowLoss.loss_photomatric")
+    except Exception:
+        if strict:
+            raise
     return done
 
 

@@ -199,6 +199,19 @@ size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O);
 int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
                        void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream);
 
+/* ---- f3, second half: photometric term of the unsupervised flow loss, fused -------- */
+/* Replaces loss/loss_flow.py:35-49 unFlowLoss.loss_photomatric(im1_scaled, im1_recons, occu_mask1) with
+ * loss/loss_blocks.py:46-65 SSIM (3x3, no padding), w_ternary = 0:
+ *   loss = (w_l1 mean(|im - rec| m) + w_ssim mean(clamp((1 - SSIM(rec m, im m)) / 2, 0, 1))) / mean(m)
+ *   im, rec, drec [B,C,H,W]   mask [B,1,H,W]   loss: device scalar (may be NULL)   sums: device float[4]
+ *   (sum |im - rec| m, sum dist, sum m, loss) written by fwd and read by bwd   gloss: device scalar dL/dloss
+ * Only rec carries a gradient (loss_flow.py:90-91).  H, W >= 3. */
+size_t emip_photometric_workspace(int B, int H, int W);
+int emip_photometric_fwd(const float* im, const float* rec, const float* mask, float* loss, float* sums, void* workspace,
+                         size_t ws_bytes, int B, int C, int H, int W, float w_l1, float w_ssim, void* stream);
+int emip_photometric_bwd(const float* im, const float* rec, const float* mask, const float* sums, const float* gloss,
+                         float* drec, int B, int C, int H, int W, float w_l1, float w_ssim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,3 +283,22 @@ def conv_corr_first_layer(feature0, feature1, weight, bias=None):
     s = torch.matmul(feature0.reshape(b, c, h * w).transpose(1, 2), feature1.reshape(b, c, h * w)) / (c ** 0.5)   # [b, i, j]
     corr = s.reshape(b, h, w, h * w).permute(0, 3, 1, 2)
     return torch.nn.functional.conv2d(corr, weight, bias, stride=1, padding=1)
+
+
+def ssim_distance(x, y):
+    """clamp((1 - SSIM) / 2, 0, 1) with 3x3 mean filters and no padding.  Reference: loss/loss_blocks.py:46-65 (md = 1)."""
+    pool = lambda t: torch.nn.functional.avg_pool2d(t, 3, 1, 0)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    mu_x, mu_y = pool(x), pool(y)
+    sigma_x = pool(x * x) - mu_x * mu_x
+    sigma_y = pool(y * y) - mu_y * mu_y
+    sigma_xy = pool(x * y) - mu_x * mu_y
+    ssim = ((2 * mu_x * mu_y + c1) * (2 * sigma_xy + c2)) / ((mu_x * mu_x + mu_y * mu_y + c1) * (sigma_x + sigma_y + c2))
+    return torch.clamp((1 - ssim) / 2, 0, 1)
+
+
+def photometric_loss(im, rec, mask, w_l1=0.15, w_ssim=0.85):
+    """Photometric term of the unsupervised flow loss.  Reference: loss/loss_flow.py:35-49 (w_ternary = 0)."""
+    l1 = (w_l1 * (im - rec).abs() * mask).mean()
+    ss = (w_ssim * ssim_distance(rec * mask, im * mask)).mean()
+    return (l1 + ss) / mask.mean()

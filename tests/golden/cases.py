@@ -118,6 +118,20 @@ def f1_inputs(s):
                 wout=randn(s["seed"] + 4000, (s["b"], s["o"], s["h"], s["w"])))
 
 
+F3B_CASES = {
+    "f3b_small": dict(b=2, c=3, h=13, w=37, seed=111),
+    "f3b_mid": dict(b=3, c=3, h=64, w=96, seed=112),
+}
+
+
+def f3b_inputs(s):
+    shp = (s["b"], s["c"], s["h"], s["w"])
+    im = randn(s["seed"], shp, 0.5)
+    rec = im + randn(s["seed"] + 1000, shp, 0.2)
+    mask = (randn(s["seed"] + 2000, (s["b"], 1, s["h"], s["w"])) > -0.8).float()
+    return dict(im=im, rec=rec, mask=mask)
+
+
 F3_CASES = {
     "f3_small": dict(b=2, h=9, w=11, sigma=2.0, seed=71),
     "f3_mid": dict(b=2, h=40, w=56, sigma=6.0, seed=72),

@@ -142,6 +142,18 @@ def gen_f1():
                         dw=cases.pack(conv.weight.grad, False), db=cases.pack(conv.bias.grad, False)))
 
 
+def gen_f3b():
+    """unFlowLoss.loss_photomatric (loss_flow.py:35-49) with gradients to the reconstruction."""
+    from loss.loss_flow import unFlowLoss
+    crit = unFlowLoss()
+    for name, s in cases.F3B_CASES.items():
+        d = cases.f3b_inputs(s)
+        rec = d["rec"].clone().requires_grad_(True)
+        loss = crit.loss_photomatric(d["im"], rec, d["mask"])
+        loss.backward()
+        save(name, dict(spec=s, loss=float(loss), drec=cases.pack(rec.grad, False)))
+
+
 def gen_f3():
     from loss.warp_utils import get_occu_mask_backward, get_corresponding_map, mesh_grid
     for name, s in cases.F3_CASES.items():
@@ -191,6 +203,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f3", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f3", "f3b", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

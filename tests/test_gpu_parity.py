@@ -475,3 +475,37 @@ def test_f1_fused_model_slice():
     got = run()
     for name, r, g in zip(("flow", "y", "da", "db", "dw"), ref, got):
         assert rel(g, r) < TOL_GRAD, name
+
+
+# ----------------------------------------------------------------------------- f3b (photometric loss)
+@pytest.mark.parametrize("name", list(cases.F3B_CASES))
+def test_f3b_photometric_loss_golden(golden, name):
+    from emip_b200.photometric import photometric_loss
+    g = golden(name)
+    d = cases.f3b_inputs(cases.F3B_CASES[name])
+    rec = dev(d["rec"]).requires_grad_(True)
+    loss = photometric_loss(dev(d["im"]), rec, dev(d["mask"]))
+    assert abs(float(loss) - g["loss"]) <= 2e-6 * abs(g["loss"]), (float(loss), g["loss"])
+    (3.0 * loss).backward()
+    e = cases.check_packed(rec.grad / 3.0, g["drec"], 2e-5, "drec")
+    print(f"{name}: loss {float(loss):.6f} vs {g['loss']:.6f}, drec rel-L2 {e:.2e}")
+
+
+def test_f3b_photometric_loss_fullsize_with_warp():
+    """The training call chain at full size (B reduced): flow_warp -> loss -> backward to the flow, vs the CPU oracle."""
+    from emip_b200.photometric import photometric_loss
+    from emip_b200.warp import flow_warp, get_occu_mask_backward
+    B, H, W = 2, 352, 352
+    im1, im2 = cases.randn(121, (B, 3, H, W), 0.5), cases.randn(122, (B, 3, H, W), 0.5)
+    fl4 = torch.cat([cases.smooth_flow(123, B, H, W, 3.0), cases.smooth_flow(124, B, H, W, 3.0)], 1)
+    f_ref = fl4.clone().requires_grad_(True)
+    mask_ref = 1 - O.occu_mask_backward(fl4[:, 2:], 0.2)
+    l_ref = O.photometric_loss(im1, O.flow_warp(im2, f_ref[:, :2]), mask_ref)
+    l_ref.backward()
+    f = dev(fl4).requires_grad_(True)
+    mask = 1 - get_occu_mask_backward(f.detach()[:, 2:], th=0.2)
+    loss = photometric_loss(dev(im1), flow_warp(dev(im2), f[:, :2]), mask)
+    loss.backward()
+    assert (mask.cpu() != mask_ref).float().mean() < 1e-4              # threshold ties only
+    assert abs(float(loss) - float(l_ref)) < 1e-4 * abs(float(l_ref))
+    assert rel(f.grad[:, :2], f_ref.grad[:, :2]) < 2e-3

@@ -172,3 +172,14 @@ def test_f1_conv_corr_first_layer(golden, name):
     cases.check_packed(f1.grad, g["df1"], 1e-5, "df1")
     cases.check_packed(w.grad, g["dw"], 1e-5, "dw")
     cases.check_packed(b.grad, g["db"], 1e-5, "db")
+
+
+@pytest.mark.parametrize("name", list(cases.F3B_CASES))
+def test_f3b_photometric_loss(golden, name):
+    g = golden(name)
+    d = cases.f3b_inputs(cases.F3B_CASES[name])
+    rec = d["rec"].clone().requires_grad_(True)
+    loss = O.photometric_loss(d["im"], rec, d["mask"])
+    assert abs(float(loss) - g["loss"]) <= 1e-6 * abs(g["loss"])
+    loss.backward()
+    cases.check_packed(rec.grad, g["drec"], 1e-5, "drec")

@@ -347,6 +347,42 @@ def main():
     add("f4 convex x8 flow upsampling, 2B=32", Bu, "flows", ms_f, ms_fb - ms_f, 0, 0, Bu * (576 * N + 2 * N + 2 * 64 * N) * 4,
         Bu * (2 * 576 * N + 2 * N + 2 * 64 * N) * 4, "hbm", cf, cb, "CPU sample = 4 flows x 8")
 
+    # ---------------- f3b: photometric loss term (L1 + SSIM 3x3, masked), B = 64 ----------------
+    from emip_b200.photometric import photometric_loss
+    rec0 = x + 0.2 * torch.randn(Bw, Cw, Hw, Ww, device=dev, generator=g)
+    occ = (torch.rand(Bw, 1, Hw, Ww, device=dev, generator=g) > 0.2).float()
+
+    def f3b_fwd():
+        with torch.no_grad():
+            return photometric_loss(x, rec0, occ)
+
+    def f3b_fwd_bwd():
+        r = rec0.detach().requires_grad_(True)
+        photometric_loss(x, r, occ).backward()
+
+    def torch_fwd_bwd():                                  # the reference's op sequence on the same GPU (library kernels)
+        r = rec0.detach().requires_grad_(True)
+        O.photometric_loss(x, r, occ).backward()
+    ms_f = gpu_time(f3b_fwd)
+    ms_fb = gpu_time(f3b_fwd_bwd, iters=5)
+    ms_torch = gpu_time(torch_fwd_bwd, iters=3, warm=1)
+    cf = cb = None
+    if not args.no_cpu:
+        sx, sr, so = x[:8].cpu(), rec0[:8].cpu(), occ[:8].cpu()
+
+        def c_f():
+            with torch.no_grad():
+                O.photometric_loss(sx, sr, so)
+
+        def c_fb():
+            r = sr.clone().requires_grad_(True)
+            O.photometric_loss(sx, r, so).backward()
+        cf = cpu_time(c_f) * 8
+        cb = cpu_time(c_fb) * 8 - cf
+    add("f3b photometric loss term (L1 + SSIM), B=64 3x352x352", Bw, "images", ms_f, ms_fb - ms_f, 0, 0,
+        Bw * Hw * Ww * (2 * Cw + 1) * 4, Bw * Hw * Ww * (3 * Cw + 1) * 4, "hbm", cf, cb,
+        f"the same formula as eager torch ops on this GPU (what the reference launches): fwd+bwd {ms_torch:.2f} ms; CPU sample = 8 x 8")
+
     out = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": src}, "cpu_threads": os.cpu_count(), "rows": rows}
     if args.json:
         with open(args.json, "w") as f:
