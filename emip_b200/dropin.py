@@ -34,6 +34,10 @@ _PATCHES = (
     ("model.EMIP_short.model", "Injector", "emip_b200.injector", "Injector"),
     ("model.EMIP_long.model_long", "Injector", "emip_b200.injector", "Injector"),
     ("model.EMIP_long.LTM", "Memory", "emip_b200.memory", "Memory"),
+    ("model.EMIP_short.motion.gmflow.transformer", "single_head_split_window_attention", "emip_b200.window_attn",
+     "single_head_split_window_attention"),
+    ("model.EMIP_short.motion.gmflow.transformer", "single_head_full_attention", "emip_b200.window_attn",
+     "single_head_full_attention"),
     ("loss.warp_utils", "flow_warp", "emip_b200.warp", "flow_warp"),
     ("loss.loss_flow", "flow_warp", "emip_b200.warp", "flow_warp"),
     ("loss.warp_utils", "get_occu_mask_backward", "emip_b200.warp", "get_occu_mask_backward"),

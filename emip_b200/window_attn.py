@@ -1,0 +1,109 @@
+"""Attention core of the GMFlow FeatureTransformer.
+
+Reference: model/EMIP_short/motion/gmflow/transformer.py:8-16 ``single_head_full_attention`` and :46-105
+``single_head_split_window_attention`` (swin-style split windows with an optional half-window shift).  Both functions
+below keep the reference's names and signatures (``dropin.install`` binds them); the projections, LayerNorms and MLPs of
+the transformer layers stay library code.
+
+The forward runs on the tensor cores (``emip_attention_fwd_tc``: row log-sum-exp pass + ``e^{S-L} V`` pass, bf16 hi/lo
+split operands, fp32 accumulation).  The shifted-window mask of the reference (0 / -100, transformer.py:19-43) only
+separates rectangular blocks of tokens -- in un-rolled coordinates the cuts are at ``shift`` and ``h - window + shift``
+-- and ``exp(-100)`` relative weight is below fp32 resolution, so a shifted layer is computed as plain attention inside
+each block: no roll, no mask tensor, no masked score entries.
+The GMFlow weights are frozen in training (train.py:340-342) but gradients still flow through this attention to the
+prompt-fusion outputs; the backward re-derives them with library matmuls (plumbing for now).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import I, SZ, ptr, stream_ptr
+from ._ws import workspace
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v):
+        nb, n, c = q.shape
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        L = _lib.lib()
+        L.emip_attention_tc_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_attention_tc_workspace(I(nb), I(n), I(c)), q.device)
+        out = torch.empty_like(q)
+        _lib.check(L.emip_attention_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(out), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(nb), I(n), I(c),
+                                           stream_ptr()), "emip_attention_fwd_tc")
+        ctx.save_for_backward(q, k, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v = ctx.saved_tensors
+        scale = q.shape[-1] ** -0.5
+        p = torch.softmax(torch.matmul(q, k.transpose(1, 2)) * scale, dim=-1)
+        dv = torch.matmul(p.transpose(1, 2), dout)
+        dp = torch.matmul(dout, v.transpose(1, 2))
+        ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
+        return torch.matmul(ds, k), torch.matmul(ds.transpose(1, 2), q), dv
+
+
+def attention(q, k, v):
+    """softmax(q k^T / sqrt(C)) v for [nb, n, C] token-major tensors, C = 128, n >= 16."""
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise _lib.EmipError("emip_b200 attention needs CUDA tensors (no CPU fallback)")
+    if q.dtype != torch.float32 or k.dtype != torch.float32 or v.dtype != torch.float32:
+        raise TypeError("emip_b200 attention computes from fp32 tensors")
+    if q.dim() != 3 or q.shape != k.shape or q.shape != v.shape:
+        raise ValueError(f"expected q, k, v of one shape [nb, n, C], got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    return _Attention.apply(q, k, v)
+
+
+def single_head_full_attention(q, k, v):
+    """Reference transformer.py:8-16."""
+    assert q.dim() == k.dim() == v.dim() == 3
+    return attention(q, k, v)
+
+
+def _axis_groups(size, num_splits, shift):
+    """Ranges (in un-rolled coordinates) of one axis inside which the reference lets tokens attend to each other."""
+    win = size // num_splits
+    if shift == 0:
+        return [(i * win, (i + 1) * win) for i in range(num_splits)]
+    # rolled coordinate r = (orig - shift) mod size; windows [i*win, (i+1)*win) in rolled coordinates; the last window is
+    # cut at size - shift by the mask labels of generate_shift_window_attn_mask (transformer.py:25-30)
+    rolled = [(i * win, (i + 1) * win) for i in range(num_splits - 1)] + [(size - win, size - shift), (size - shift, size)]
+    out = []
+    for a, b in rolled:
+        a0, b0 = (a + shift) % size, (b + shift - 1) % size + 1
+        assert a0 < b0
+        out.append((a0, b0))
+    return out
+
+
+def single_head_split_window_attention(q, k, v, num_splits=1, with_shift=False, h=None, w=None, attn_mask=None):
+    """Reference transformer.py:46-105: q, k, v [B, h*w, C] -> [B, h*w, C]."""
+    assert q.dim() == k.dim() == v.dim() == 3
+    assert h is not None and w is not None
+    assert q.size(1) == h * w
+    b, _, c = q.shape
+    assert h % num_splits == 0 and w % num_splits == 0
+    if with_shift:
+        assert attn_mask is not None                         # the reference computes it once; its content is implied here
+    sh, sw = ((h // num_splits) // 2, (w // num_splits) // 2) if with_shift else (0, 0)
+    rows, cols = _axis_groups(h, num_splits, sh), _axis_groups(w, num_splits, sw)
+    q4, k4, v4 = q.view(b, h, w, c), k.view(b, h, w, c), v.view(b, h, w, c)
+    out = torch.empty_like(q4)
+    # batch the blocks of equal shape into one launch
+    by_shape = {}
+    for (r0, r1) in rows:
+        for (c0, c1) in cols:
+            by_shape.setdefault((r1 - r0, c1 - c0), []).append((r0, c0))
+    for (bh, bw), origins in by_shape.items():
+        n = bh * bw
+
+        def gather(t):
+            return torch.stack([t[:, r0:r0 + bh, c0:c0 + bw] for (r0, c0) in origins], 0).reshape(len(origins) * b, n, c)
+        o = attention(gather(q4), gather(k4), gather(v4)).view(len(origins), b, bh, bw, c)
+        for i, (r0, c0) in enumerate(origins):
+            out[:, r0:r0 + bh, c0:c0 + bw] = o[i]
+    return out.view(b, h * w, c)

@@ -212,6 +212,15 @@ int emip_photometric_fwd(const float* im, const float* rec, const float* mask, f
 int emip_photometric_bwd(const float* im, const float* rec, const float* mask, const float* sums, const float* gloss,
                          float* drec, int B, int C, int H, int W, float w_l1, float w_ssim, void* stream);
 
+/* ---- f2: attention core of the GMFlow FeatureTransformer ----------------------------- */
+/* Replaces model/EMIP_short/motion/gmflow/transformer.py:8-16 single_head_full_attention and the per-window attention
+ * of :46-105 single_head_split_window_attention: out = softmax(q k^T / sqrt(C)) v for nb independent problems of n
+ * tokens (the shifted-window mask is handled by the host side: it only separates rectangular token blocks, each of
+ * which is a plain attention problem).  q, k, v, out token-major [nb][n][C], C = 128, n >= 16.  Forward only. */
+size_t emip_attention_tc_workspace(int nb, int n, int C);
+int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace, size_t ws_bytes,
+                          int nb, int n, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

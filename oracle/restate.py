@@ -302,3 +302,39 @@ def photometric_loss(im, rec, mask, w_l1=0.15, w_ssim=0.85):
     l1 = (w_l1 * (im - rec).abs() * mask).mean()
     ss = (w_ssim * ssim_distance(rec * mask, im * mask)).mean()
     return (l1 + ss) / mask.mean()
+
+
+def shift_window_attn_mask(h, w, win_h, win_w, shift_h, shift_w):
+    """0 / -100 mask of the shifted split windows.  Reference: .../gmflow/transformer.py:19-43."""
+    img = torch.zeros(1, h, w, 1)
+    cnt = 0
+    for hs in (slice(0, -win_h), slice(-win_h, -shift_h), slice(-shift_h, None)):
+        for ws in (slice(0, -win_w), slice(-win_w, -shift_w), slice(-shift_w, None)):
+            img[:, hs, ws, :] = cnt
+            cnt += 1
+    k = w // win_w
+    mw = img.view(1, k, h // k, k, w // k, 1).permute(0, 1, 3, 2, 4, 5).reshape(k * k, win_h * win_w)
+    d = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return torch.where(d != 0, torch.full_like(d, -100.0), torch.zeros_like(d))
+
+
+def split_window_attention(q, k, v, num_splits, with_shift, h, w):
+    """Swin-style single-head attention in split windows.  Reference: .../gmflow/transformer.py:46-105 with
+    utils.py:5-58 (split_feature / merge_splits); q, k, v [B, h*w, C]."""
+    b, _, c = q.shape
+    K = num_splits
+    wh, ww = h // K, w // K
+    q, k, v = (t.view(b, h, w, c) for t in (q, k, v))
+    if with_shift:
+        sh, sw = wh // 2, ww // 2
+        q, k, v = (torch.roll(t, shifts=(-sh, -sw), dims=(1, 2)) for t in (q, k, v))
+    split = lambda t: t.reshape(b, K, wh, K, ww, c).permute(0, 1, 3, 2, 4, 5).reshape(b * K * K, wh * ww, c)
+    qs, ks, vs = split(q), split(k), split(v)
+    scores = torch.matmul(qs, ks.transpose(1, 2)) / (c ** 0.5)
+    if with_shift:
+        scores = scores + shift_window_attn_mask(h, w, wh, ww, sh, sw).to(scores).repeat(b, 1, 1)
+    out = torch.matmul(torch.softmax(scores, dim=-1), vs)
+    out = out.view(b, K, K, wh, ww, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+    if with_shift:
+        out = torch.roll(out, shifts=(sh, sw), dims=(1, 2))
+    return out.reshape(b, h * w, c)

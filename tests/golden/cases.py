@@ -132,6 +132,18 @@ def f3b_inputs(s):
     return dict(im=im, rec=rec, mask=mask)
 
 
+F2_CASES = {
+    "f2_small": dict(b=1, c=128, h=16, w=24, k=2, scale=1.5, seed=131),
+    "f2_full": dict(b=2, c=128, h=44, w=44, k=2, scale=2.0, seed=132),
+}
+
+
+def f2_inputs(s):
+    shp = (s["b"], s["h"] * s["w"], s["c"])
+    return dict(q=randn(s["seed"], shp, s["scale"]), k=randn(s["seed"] + 1000, shp, s["scale"]), v=randn(s["seed"] + 2000, shp),
+                wout=randn(s["seed"] + 3000, shp))
+
+
 F3_CASES = {
     "f3_small": dict(b=2, h=9, w=11, sigma=2.0, seed=71),
     "f3_mid": dict(b=2, h=40, w=56, sigma=6.0, seed=72),

@@ -142,6 +142,28 @@ def gen_f1():
                         dw=cases.pack(conv.weight.grad, False), db=cases.pack(conv.bias.grad, False)))
 
 
+def gen_f2():
+    """single_head_split_window_attention (transformer.py:46-105) with and without the half-window shift."""
+    import model.EMIP_short.motion.gmflow.transformer as T
+    for name, s in cases.F2_CASES.items():
+        d = cases.f2_inputs(s)
+        full = name.endswith("full")
+        rec = dict(spec=s)
+        for shift in (False, True):
+            q, k, v = (d[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+            mask = None
+            if shift:
+                wh, ww = s["h"] // s["k"], s["w"] // s["k"]
+                mask = T.generate_shift_window_attn_mask((s["h"], s["w"]), wh, ww, wh // 2, ww // 2, device=torch.device("cpu"))
+            out = T.single_head_split_window_attention(q, k, v, num_splits=s["k"], with_shift=shift, h=s["h"], w=s["w"],
+                                                       attn_mask=mask)
+            (out * d["wout"]).sum().backward()
+            tag = "shift" if shift else "plain"
+            rec[tag] = dict(out=cases.pack(out.detach(), full), dq=cases.pack(q.grad, True), dk=cases.pack(k.grad, True),
+                            dv=cases.pack(v.grad, True))
+        save(name, rec)
+
+
 def gen_f3b():
     """unFlowLoss.loss_photomatric (loss_flow.py:35-49) with gradients to the reconstruction."""
     from loss.loss_flow import unFlowLoss
@@ -203,6 +225,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f3", "f3b", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f3", "f3b", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

@@ -509,3 +509,30 @@ def test_f3b_photometric_loss_fullsize_with_warp():
     assert (mask.cpu() != mask_ref).float().mean() < 1e-4              # threshold ties only
     assert abs(float(loss) - float(l_ref)) < 1e-4 * abs(float(l_ref))
     assert rel(f.grad[:, :2], f_ref.grad[:, :2]) < 2e-3
+
+
+# ----------------------------------------------------------------------------- f2 (split-window attention)
+@pytest.mark.parametrize("name", list(cases.F2_CASES))
+def test_f2_split_window_attention_golden(golden, name):
+    from emip_b200.window_attn import single_head_split_window_attention
+    g = golden(name)
+    s = cases.F2_CASES[name]
+    d = cases.f2_inputs(s)
+    for shift in (False, True):
+        tag = "shift" if shift else "plain"
+        q, k, v = (dev(d[n]).requires_grad_(True) for n in ("q", "k", "v"))
+        mask = torch.zeros(1, device="cuda") if shift else None      # content implied by the geometry
+        out = single_head_split_window_attention(q, k, v, num_splits=s["k"], with_shift=shift, h=s["h"], w=s["w"], attn_mask=mask)
+        e = cases.check_packed(out, g[tag]["out"], TOL_EXACT, tag + " out")
+        (out * dev(d["wout"])).sum().backward()
+        cases.check_packed(q.grad, g[tag]["dq"], TOL_GRAD, tag + " dq")
+        cases.check_packed(k.grad, g[tag]["dk"], TOL_GRAD, tag + " dk")
+        cases.check_packed(v.grad, g[tag]["dv"], TOL_GRAD, tag + " dv")
+        print(f"{name} {tag}: out rel-L2 {e:.2e}")
+
+
+def test_f2_full_attention_vs_oracle():
+    from emip_b200.window_attn import single_head_full_attention
+    q, k, v = (cases.randn(140 + i, (3, 300, 128), 1.5) for i in range(3))
+    ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / 128 ** 0.5, -1) @ v.double()
+    assert rel(single_head_full_attention(dev(q), dev(k), dev(v)), ref) < TOL_EXACT

@@ -183,3 +183,28 @@ def test_f3b_photometric_loss(golden, name):
     assert abs(float(loss) - g["loss"]) <= 1e-6 * abs(g["loss"])
     loss.backward()
     cases.check_packed(rec.grad, g["drec"], 1e-5, "drec")
+
+
+@pytest.mark.parametrize("name", list(cases.F2_CASES))
+def test_f2_split_window_attention(golden, name):
+    """The oracle restatement of the swin split-window attention, and the block decomposition the CUDA path uses for
+    the shifted layers (plain attention inside the rectangles the 0 / -100 mask separates)."""
+    from emip_b200.window_attn import _axis_groups
+    g = golden(name)
+    s = cases.F2_CASES[name]
+    d = cases.f2_inputs(s)
+    for shift in (False, True):
+        tag = "shift" if shift else "plain"
+        out = O.split_window_attention(d["q"], d["k"], d["v"], s["k"], shift, s["h"], s["w"])
+        cases.check_packed(out, g[tag]["out"], TOL, tag)
+        # block decomposition with exact fp64 attention per block
+        b, c, h, w = s["b"], s["c"], s["h"], s["w"]
+        sh, sw = ((h // s["k"]) // 2, (w // s["k"]) // 2) if shift else (0, 0)
+        q4, k4, v4 = (d[n].double().view(b, h, w, c) for n in ("q", "k", "v"))
+        dec = torch.empty_like(q4)
+        for (r0, r1) in _axis_groups(h, s["k"], sh):
+            for (c0, c1) in _axis_groups(w, s["k"], sw):
+                qb, kb, vb = (t[:, r0:r1, c0:c1].reshape(b, -1, c) for t in (q4, k4, v4))
+                p = torch.softmax(qb @ kb.transpose(1, 2) / c ** 0.5, -1)
+                dec[:, r0:r1, c0:c1] = (p @ vb).view(b, r1 - r0, c1 - c0, c)
+        cases.check_packed(dec.view(b, h * w, c).float(), g[tag]["out"], TOL, tag + " blocks")

@@ -347,6 +347,30 @@ def main():
     add("f4 convex x8 flow upsampling, 2B=32", Bu, "flows", ms_f, ms_fb - ms_f, 0, 0, Bu * (576 * N + 2 * N + 2 * 64 * N) * 4,
         Bu * (2 * 576 * N + 2 * N + 2 * 64 * N) * 4, "hbm", cf, cb, "CPU sample = 4 flows x 8")
 
+    # ---------------- f2: split-window attention of the FeatureTransformer, 2B = 32 ----------------
+    from emip_b200.window_attn import single_head_split_window_attention
+    qw, kw, vw = (2.0 * torch.randn(32, N, C, device=dev, generator=g) for _ in range(3))
+    amask = O.shift_window_attn_mask(H, W, 22, 22, 11, 11).to(dev)
+    res2 = {}
+    for shift in (False, True):
+        def f2_fwd():
+            with torch.no_grad():
+                return single_head_split_window_attention(qw, kw, vw, 2, shift, H, W, amask if shift else None)
+
+        def f2_torch():                                   # the reference's op sequence on the same GPU (library kernels)
+            with torch.no_grad():
+                return O.split_window_attention(qw, kw, vw, 2, shift, H, W)
+        res2[shift] = (gpu_time(f2_fwd, iters=10), gpu_time(f2_torch, iters=5, warm=2))
+    cf = None
+    if not args.no_cpu:
+        cq, ck, cv = qw[:4].cpu(), kw[:4].cpu(), vw[:4].cpu()
+        cf = cpu_time(lambda: O.split_window_attention(cq, ck, cv, 2, True, H, W)) * 8
+    fl = 32 * 4 * 2.0 * 484 * 484 * (C + C)
+    add("f2 split-window attention (one shifted layer), 2B=32, 4 windows of 484 tokens", 16, "pairs", res2[True][0], None, fl, 0,
+        32 * 4 * N * C * 4, 0, "tensor", cf, None,
+        f"unshifted layer {res2[False][0]:.3f} ms; the same formula as eager torch ops on this GPU: shifted {res2[True][1]:.3f} ms, "
+        f"unshifted {res2[False][1]:.3f} ms; 12 such layers per pair of feature maps; CPU sample = 4 x 8")
+
     # ---------------- f3b: photometric loss term (L1 + SSIM 3x3, masked), B = 64 ----------------
     from emip_b200.photometric import photometric_loss
     rec0 = x + 0.2 * torch.randn(Bw, Cw, Hw, Ww, device=dev, generator=g)
