@@ -485,10 +485,10 @@ def test_f3b_photometric_loss_golden(golden, name):
     d = cases.f3b_inputs(cases.F3B_CASES[name])
     rec = dev(d["rec"]).requires_grad_(True)
     loss = photometric_loss(dev(d["im"]), rec, dev(d["mask"]))
-    assert abs(float(loss) - g["loss"]) <= 2e-6 * abs(g["loss"]), (float(loss), g["loss"])
+    assert abs(float(loss.detach()) - g["loss"]) <= 2e-6 * abs(g["loss"]), (float(loss.detach()), g["loss"])
     (3.0 * loss).backward()
     e = cases.check_packed(rec.grad / 3.0, g["drec"], 2e-5, "drec")
-    print(f"{name}: loss {float(loss):.6f} vs {g['loss']:.6f}, drec rel-L2 {e:.2e}")
+    print(f"{name}: loss {float(loss.detach()):.6f} vs {g['loss']:.6f}, drec rel-L2 {e:.2e}")
 
 
 def test_f3b_photometric_loss_fullsize_with_warp():
@@ -507,7 +507,7 @@ def test_f3b_photometric_loss_fullsize_with_warp():
     loss = photometric_loss(dev(im1), flow_warp(dev(im2), f[:, :2]), mask)
     loss.backward()
     assert (mask.cpu() != mask_ref).float().mean() < 1e-4              # threshold ties only
-    assert abs(float(loss) - float(l_ref)) < 1e-4 * abs(float(l_ref))
+    assert abs(float(loss.detach()) - float(l_ref.detach())) < 1e-4 * abs(float(l_ref.detach()))
     assert rel(f.grad[:, :2], f_ref.grad[:, :2]) < 2e-3
 
 
