@@ -21,7 +21,7 @@
 //                  the box origin shifted by the tap (dx-1, dy-1): out-of-image pixels are zero-filled by the TMA
 //                  unit, which is exactly the convolution's zero padding -- no im2col buffer; N = R image rows
 //                  (R*W a multiple of 16, <= 256; 4 x 44 = 176 for the model's grid); epilogue adds the bias.
-// One 128 x N output tile per CTA: 4 epilogue warps (TMEM -> registers -> global), 1 TMA producer warp, 1 MMA warp.
+// The GEMM kernel itself is gemm_tc.cu (modes 0 and 1); this file is the C-ABI front end.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/emip_b200.h"
@@ -32,233 +32,9 @@
 #include <math.h>
 
 namespace {
-using namespace tc;
-
-constexpr int KCH = 64;                       // bf16 per 128-byte swizzle row = K elements per chunk
-constexpr int A_BYTES = TM * 128;             // one [128 x 64] bf16 operand tile
+using tc::TM;
+constexpr int KCH = GEMM_TC_KCH;
 constexpr int NMAX = 256;
-constexpr int THREADS = 6 * 32;
-
-struct CcParams {
-  int mode;                 // 0: G = Wp f1^T (split-bf16 output)   1: out = conv3x3(f0; G) + bias (fp32 output)   2: gemm_nn
-  int M;                    // rows of A / of the output (mode 0: O*9, mode 1: O)
-  int n_mtiles, n_ntiles;   // tiles per sample
-  int n_tile;               // UMMA N (mode 0: 128 channels, mode 1: R*W pixels)
-  int kchunks;              // K / 64 (rounded up; the TMA unit zero-fills the tail)
-  int stages, stage_bytes, b_bytes;
-  int W, H, R;              // mode 1: image geometry, rows per pixel tile
-  float scale;              // mode 0: 1/sqrt(C)
-  const float* bias;        // mode 1
-  __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, then lo
-  __nv_bfloat16* g_lo;
-  float* out;               // mode 1 output: [B][M][H*W]
-  // mode 2: y[b][m][n] = sum_k A(b)[m][k] Bt[b][n][k] (+ res): A = weights (shared: a_batched = 0), Bt = token-major
-  // activations [B][N][2*Kp] (hi | lo); y / res rows are ldy / ldr floats apart
-  int a_batched, Kp, N;
-  float* y; long long y_stride_b; int ldy;
-  const float* res; long long res_stride_b; int ldr;
-};
-
-__global__ void __launch_bounds__(THREADS, 1)
-conv_corr_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                      const __grid_constant__ CUtensorMap map_b, const CcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + p.stages * p.stage_bytes;
-  auto full = [&](int s) { return bar0 + 8 * s; };
-  auto empty = [&](int s) { return bar0 + 8 * (p.stages + s); };
-  const uint32_t acc_full = bar0 + 8 * (2 * p.stages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 1));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int nt = t % p.n_ntiles; t /= p.n_ntiles;
-  const int mt = t % p.n_mtiles;
-  const int b = t / p.n_mtiles;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32((const void*)tmem_slot))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    const bool leader = elect_one();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kc = 0; kc < p.kchunks; ++kc) {
-      mbar_wait(empty(stage), phase ^ 1);
-      if (leader) {
-        const uint32_t sa = sbase + stage * p.stage_bytes;
-        mbar_expect_tx(full(stage), 2 * A_BYTES + 2 * p.b_bytes);
-        if (p.mode == 0) {
-          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, 0);
-          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, 0);
-          // f1 channel-major [b][256 = hi c | lo c][ld]: rows 0..127 hi, 128..255 lo
-          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, 0, b);
-          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), kc * KCH, 128, b);
-        } else if (p.mode == 2) {
-          const int ab = p.a_batched ? b : 0;
-          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
-          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, ab);
-          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, nt * TM, b);
-          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + kc * KCH, nt * TM, b);
-        } else {
-          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
-          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
-          // K chunk kc = tap (dy,dx) = kc / 2, channel half kc % 2 of the token-major [.., 256 = hi 128 | lo 128] f0
-          const int tap = kc >> 1, dy = tap / 3, dx = tap - dy * 3, c0 = (kc & 1) * KCH;
-          tma_load_4d(sa + 2 * A_BYTES, &map_b, full(stage), c0, dx - 1, nt * p.R + dy - 1, b);
-          tma_load_4d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), 128 + c0, dx - 1, nt * p.R + dy - 1, b);
-        }
-      }
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    // ===================== UMMA issuer =====================
-    const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(p.n_tile);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kc = 0; kc < p.kchunks; ++kc) {
-      mbar_wait(full(stage), phase);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t sa = sbase + stage * p.stage_bytes;
-        const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_BYTES);
-        const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_BYTES), b_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + p.b_bytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-        umma_commit(empty(stage));
-        if (kc == p.kchunks - 1) umma_commit(acc_full);
-      }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
-    }
-  } else {
-    // ===================== epilogue warps: thread <-> output row =====================
-    const int row = mt * TM + warp * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    if (p.mode == 0) {
-      __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
-      __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32_async(taddr + c0, r);
-        tmem_wait(r);
-        if (row < p.M) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float v0 = __uint_as_float(r[2 * i]) * p.scale, v1 = __uint_as_float(r[2 * i + 1]) * p.scale;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
-            const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
-                                                         __float2bfloat16_rn(v1 - __bfloat162float(h1)));
-            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-          }
-          uint4* dh = reinterpret_cast<uint4*>(gh + c0);
-          uint4* dl = reinterpret_cast<uint4*>(gl + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-          }
-        }
-      }
-    } else if (p.mode == 2) {
-      const int n0 = nt * TM;
-      float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
-      const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
-      for (int c0 = 0; c0 < TM; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32_async(taddr + c0, r);
-        tmem_wait(r);
-        const int n = min(32, p.N - n0 - c0);
-        if (row < p.M && n > 0) {
-          if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs + c0) & 15) == 0)) {
-            float4* d = reinterpret_cast<float4*>(o + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                     __uint_as_float(r[4 * i + 3]));
-              if (rs) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-              }
-              d[i] = v;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + (rs ? __ldg(rs + c0 + i) : 0.f);
-          }
-        }
-      }
-    } else {
-      const int npix = p.H * p.W;
-      const int px0 = nt * p.R * p.W;
-      const int nvalid = min(p.n_tile, npix - px0);          // the last tile may hang over the bottom edge
-      const float bias = (row < p.M && p.bias != nullptr) ? __ldg(p.bias + row) : 0.f;
-      float* o = p.out + ((size_t)b * p.M + row) * npix + px0;
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        uint32_t r[32];
-        // n_tile is a multiple of 16: the last group may be a half group
-        if (c0 + 32 <= p.n_tile) {
-          tmem_ld32_async(taddr + c0, r);
-          tmem_wait(r);
-        } else {
-          uint32_t h[32];
-          tmem_ld32_async(taddr + p.n_tile - 32, h);          // overlapping read of the last 32 columns
-          tmem_wait(h);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = h[16 + i];
-#pragma unroll
-          for (int i = 16; i < 32; ++i) r[i] = 0u;
-        }
-        if (row < p.M) {
-          const int n = min(32, min(p.n_tile, nvalid) - c0);
-          if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0)) {
-            float4* d = reinterpret_cast<float4*>(o + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              d[i] = make_float4(__uint_as_float(r[4 * i]) + bias, __uint_as_float(r[4 * i + 1]) + bias,
-                                 __uint_as_float(r[4 * i + 2]) + bias, __uint_as_float(r[4 * i + 3]) + bias);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + bias;
-          }
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
-  }
-}
 
 // [O][N][3][3] fp32 -> hi | lo bf16 [2][O*9][ld], row (o, dy, dx), K = j contiguous
 __global__ void __launch_bounds__(256)
@@ -277,24 +53,6 @@ prepare_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ h
   }
 }
 
-int make_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
-  EncodeTiledFn enc = get_encoder();
-  if (enc == nullptr) {
-    emip_set_error("cuTensorMapEncodeTiled not available from the driver");
-    return EMIP_ENOSYS;
-  }
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    emip_set_error("conv_corr: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return EMIP_EINVAL;
-  }
-  return EMIP_OK;
-}
-
 long long weight_ld(int N) { return (N + 7) / 8 * 8; }      // 16-byte row pitch
 
 // image rows per pixel tile: R*W a multiple of 16 and <= 256 (0: unsupported grid)
@@ -304,118 +62,6 @@ int rows_per_tile(int H, int W) {
     if ((r * W) % 16 == 0) best = r;
   return best;
 }
-
-// ---- gemm_nn on the tensor cores (the Injector's 1x1 convolutions) ------------------------------------------
-// 8 fp32 -> 8 bf16 hi + 8 bf16 lo (two 16-byte stores)
-__device__ __forceinline__ void split8_store(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
-    const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
-                                                  __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// weights / row operands W(b)[m][k] fp32 -> hi, lo bf16 [nbw][M][Kp] (zero padded to Kp; Kp % 64 == 0).
-// grid (ceil(Kp / 2048), M, nbw): one row per blockIdx.y, 8 consecutive k per thread.
-__global__ void __launch_bounds__(256)
-split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int trans, __nv_bfloat16* __restrict__ hi,
-               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp) {
-  const int b = blockIdx.z, m = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (k0 >= Kp) return;
-  const float* src = w + (size_t)b * w_stride_b;
-  float v[8];
-  if (!trans && k0 + 8 <= K && (ldw & 3) == 0 && (w_stride_b & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)m * ldw + k0));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(src + (size_t)m * ldw + k0 + 4));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = k0 + i;
-      v[i] = k < K ? __ldg(src + (trans ? (size_t)k * ldw + m : (size_t)m * ldw + k)) : 0.f;
-    }
-  }
-  const size_t o = ((size_t)b * M + m) * Kp + k0;
-  split8_store(v, hi + o, lo + o);
-}
-
-// activations x[b][k][n] fp32 (rows ldx apart), optional LayerNorm over k -> token-major bf16 [b][n][2*Kp] (hi | lo)
-// One thread = one token x 32 channels (lanes = consecutive tokens: coalesced reads; 64-byte hi and lo segments out).
-__global__ void __launch_bounds__(128)
-split_act_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, const float* __restrict__ mean,
-                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ dst, int K, int Kp, int N) {
-  const int b = blockIdx.z, chunk = blockIdx.y;
-  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= N) return;
-  const float* s = x + (size_t)b * x_stride_b + (size_t)chunk * 32 * ldx + tok;
-  float mu = 0.f, rs = 1.f;
-  if (mean != nullptr) { mu = __ldg(mean + (size_t)b * N + tok); rs = __ldg(rstd + (size_t)b * N + tok); }
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int k = chunk * 32 + i;
-    float t = k < K ? __ldg(s + (size_t)i * ldx) : 0.f;
-    if (mean != nullptr && k < K) t = (t - mu) * rs * __ldg(gamma + k) + __ldg(beta + k);
-    v[i] = t;
-  }
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
-    const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
-                                                 __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-  }
-  uint4* dh = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + chunk * 32);
-  uint4* dl = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + Kp + chunk * 32);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-    dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-  }
-}
-
-// B'(b)[k][n] fp32 (rows ldb apart), optional LayerNorm over k -> bf16 [b][k][2*Np] (hi | lo), zero padded to Np.
-// grid (ceil(Np / 2048), K, B): 8 consecutive n per thread.
-__global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, const float* __restrict__ mean,
-                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  __nv_bfloat16* __restrict__ dst, int K, int N, int Np) {
-  const int b = blockIdx.z, k = blockIdx.y;
-  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (n0 >= Np) return;
-  const float ga = mean != nullptr ? __ldg(gamma + k) : 1.f, be = mean != nullptr ? __ldg(beta + k) : 0.f;
-  const float* src = x + (size_t)b * x_stride_b + (size_t)k * ldx;
-  float v[8];
-  const bool vec = n0 + 8 <= N && (ldx & 3) == 0 && (x_stride_b & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (N & 3) == 0;
-  if (vec) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + n0)), c = __ldg(reinterpret_cast<const float4*>(src + n0 + 4));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = n0 + i < N ? __ldg(src + n0 + i) : 0.f;
-  }
-  if (mean != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (n0 + i < N) v[i] = (v[i] - __ldg(mean + (size_t)b * N + n0 + i)) * __ldg(rstd + (size_t)b * N + n0 + i) * ga + be;
-  }
-  __nv_bfloat16* d = dst + ((size_t)b * K + k) * 2 * Np + n0;
-  split8_store(v, d, d + Np);
-}
-
-int kpad(int K) { return (K + KCH - 1) / KCH * KCH; }
 
 struct Ws {
   void* f0_tok;        // bf16 [B][N][256]
@@ -484,34 +130,23 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
   const __nv_bfloat16* w_lo = w_hi + (size_t)M1 * wld;
   __nv_bfloat16* g_hi = ws.g;
   __nv_bfloat16* g_lo = ws.g + (size_t)B * M1 * 128;
-  static bool attr_done = false;
-  const int max_smem = 227 * 1024;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_done = true;
-  }
-  auto smem_for = [](int stages, int stage_bytes) { return stages * stage_bytes + 8 * (2 * stages + 1) + 16 + 1024; };
 
   // ---- GEMM 1: G[b] = Wp f1[b]^T / sqrt(C)
   {
     CUtensorMap ma_hi, ma_lo, mb;
     const cuuint64_t adims[3] = {(cuuint64_t)N, (cuuint64_t)M1, 1}, astr[2] = {(cuuint64_t)wld * 2, (cuuint64_t)M1 * wld * 2};
     const cuuint32_t abox[3] = {KCH, TM, 1};
-    if ((rc = make_map_bf16(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
-    if ((rc = make_map_bf16(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
+    if ((rc = gemm_tc_make_map(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
+    if ((rc = gemm_tc_make_map(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
     const cuuint64_t bdims[3] = {(cuuint64_t)N, 256, (cuuint64_t)B}, bstr[2] = {(cuuint64_t)cld * 2, (cuuint64_t)cld * 2 * 256};
     const cuuint32_t bbox[3] = {KCH, 128, 1};
-    if ((rc = make_map_bf16(&mb, ws.f1_chn, 3, bdims, bstr, bbox))) return rc;
-    CcParams p = {};
+    if ((rc = gemm_tc_make_map(&mb, ws.f1_chn, 3, bdims, bstr, bbox))) return rc;
+    GemmTcParams p = {};
     p.mode = 0; p.M = M1; p.n_mtiles = (M1 + TM - 1) / TM; p.n_ntiles = 1; p.n_tile = 128;
     p.kchunks = (N + KCH - 1) / KCH;
-    p.b_bytes = 128 * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes; p.stages = 3;
     p.scale = 1.0f / sqrtf((float)C);
     p.g_hi = g_hi; p.g_lo = g_lo;
-    const long long grid = (long long)B * p.n_mtiles;
-    EMIP_CHECK_ARG(grid < 0x7fffffffLL, "conv_corr_fwd: problem too large");
-    conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem_for(p.stages, p.stage_bytes), st>>>(ma_hi, ma_lo, mb, p);
-    EMIP_CHECK_LAUNCH("conv_corr_fwd (G)");
+    if ((rc = gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st))) return rc;
   }
   // ---- GEMM 2: out[b] = conv3x3(f0[b]; G[b]) + bias
   {
@@ -519,143 +154,18 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
     CUtensorMap ma_hi, ma_lo, mb;
     const cuuint64_t adims[3] = {9 * 128, (cuuint64_t)O, (cuuint64_t)B}, astr[2] = {9 * 128 * 2, (cuuint64_t)M1 * 128 * 2};
     const cuuint32_t abox[3] = {KCH, TM, 1};
-    if ((rc = make_map_bf16(&ma_hi, g_hi, 3, adims, astr, abox))) return rc;
-    if ((rc = make_map_bf16(&ma_lo, g_lo, 3, adims, astr, abox))) return rc;
+    if ((rc = gemm_tc_make_map(&ma_hi, g_hi, 3, adims, astr, abox))) return rc;
+    if ((rc = gemm_tc_make_map(&ma_lo, g_lo, 3, adims, astr, abox))) return rc;
     const cuuint64_t bdims[4] = {256, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t bstr[3] = {512, (cuuint64_t)W * 512, (cuuint64_t)N * 512};
     const cuuint32_t bbox[4] = {KCH, (cuuint32_t)W, (cuuint32_t)R, 1};
-    if ((rc = make_map_bf16(&mb, ws.f0_tok, 4, bdims, bstr, bbox))) return rc;
-    CcParams p = {};
+    if ((rc = gemm_tc_make_map(&mb, ws.f0_tok, 4, bdims, bstr, bbox))) return rc;
+    GemmTcParams p = {};
     p.mode = 1; p.M = O; p.n_mtiles = (O + TM - 1) / TM; p.n_ntiles = (H + R - 1) / R; p.n_tile = R * W;
     p.kchunks = 18;
-    p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024); p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
-    p.stages = (max_smem - 2048) / p.stage_bytes;
-    if (p.stages > 4) p.stages = 4;
     p.W = W; p.H = H; p.R = R;
     p.bias = bias; p.out = out;
-    const long long grid = (long long)B * p.n_mtiles * p.n_ntiles;
-    EMIP_CHECK_ARG(grid < 0x7fffffffLL, "conv_corr_fwd: problem too large");
-    conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem_for(p.stages, p.stage_bytes), st>>>(ma_hi, ma_lo, mb, p);
-    EMIP_CHECK_LAUNCH("conv_corr_fwd (conv)");
+    if ((rc = gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st))) return rc;
   }
-  return EMIP_OK;
-}
-
-bool gemm_nn_tc_supported(const GemmNN& a) {
-  return !a.accumulate && a.K >= 1 && a.K <= 1024 && a.M >= 1 && a.N >= 1 && a.ldy % 4 == 0 &&
-         reinterpret_cast<uintptr_t>(a.y) % 16 == 0 && a.y_stride_b % 4 == 0;
-}
-
-size_t gemm_nn_tc_scratch_bytes(int B, int M, int K, int N, bool per_sample_w) {
-  const size_t Kp = (size_t)kpad(K);
-  return emip_align_up((size_t)(per_sample_w ? B : 1) * M * Kp * 2 * 2, 1024) + emip_align_up((size_t)B * N * 2 * Kp * 2, 1024) + 1024;
-}
-
-int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-  if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
-  if (!gemm_nn_tc_supported(a)) { emip_set_error("gemm_nn_tc: unsupported arguments"); return EMIP_ENOSYS; }
-  const bool per_sample = a.w_stride_b != 0;
-  const int Kp = kpad(a.K), nbw = per_sample ? a.B : 1;
-  if (scratch == nullptr || scratch_bytes < gemm_nn_tc_scratch_bytes(a.B, a.M, a.K, a.N, per_sample)) {
-    emip_set_error("gemm_nn_tc: scratch too small");
-    return EMIP_ENOMEM;
-  }
-  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
-  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* w_lo = w_hi + (size_t)nbw * a.M * Kp;
-  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)nbw * a.M * Kp * 2 * 2, 1024));
-  split_w_kernel<<<dim3((Kp + 2047) / 2048, a.M, nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, a.w_trans, w_hi, w_lo, a.M, a.K, Kp);
-  EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
-  split_act_kernel<<<dim3((a.N + 127) / 128, Kp / 32, a.B), 128, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta,
-                                                                        bt, a.K, Kp, a.N);
-  EMIP_CHECK_LAUNCH("gemm_nn_tc (activations)");
-  CUtensorMap ma_hi, ma_lo, mb;
-  int rc;
-  const cuuint64_t adims[3] = {(cuuint64_t)Kp, (cuuint64_t)a.M, (cuuint64_t)nbw};
-  const cuuint64_t astr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)a.M * Kp * 2};
-  const cuuint32_t abox[3] = {KCH, TM, 1};
-  if ((rc = make_map_bf16(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
-  if ((rc = make_map_bf16(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
-  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)a.N, (cuuint64_t)a.B};
-  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)a.N * 2 * Kp * 2};
-  const cuuint32_t bbox[3] = {KCH, TM, 1};
-  if ((rc = make_map_bf16(&mb, bt, 3, bdims, bstr, bbox))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
-  CcParams p = {};
-  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.N + TM - 1) / TM; p.n_tile = TM;
-  p.kchunks = Kp / KCH;
-  p.b_bytes = TM * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
-  p.stages = p.kchunks < 3 ? p.kchunks : 3;
-  p.a_batched = per_sample ? 1 : 0; p.Kp = Kp; p.N = a.N;
-  p.y = a.y; p.y_stride_b = a.y_stride_b; p.ldy = a.ldy;
-  p.res = a.res; p.res_stride_b = a.res_stride_b; p.ldr = a.ldr;
-  const long long grid = (long long)a.B * p.n_mtiles * p.n_ntiles;
-  EMIP_CHECK_ARG(grid < 0x7fffffffLL, "gemm_nn_tc: problem too large");
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
-  conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem, st>>>(ma_hi, ma_lo, mb, p);
-  EMIP_CHECK_LAUNCH("gemm_nn_tc");
-  return EMIP_OK;
-}
-
-// C[b][m][k] = sum_n A(b)[m][n] B'(b)[k][n]: the weight-gradient GEMMs (contraction over the contiguous pixel axis, so
-// both operands are K-major as they lie in memory and only need the elementwise hi|lo split)
-bool gemm_nt_tc_supported(const GemmNT& a) {
-  return a.M >= 1 && a.K >= 1 && a.N >= 16 && a.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(a.c) % 16 == 0 && a.c_stride_b % 4 == 0;
-}
-
-size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N) {
-  const size_t Np = (size_t)kpad(N);
-  return emip_align_up((size_t)B * M * Np * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
-}
-
-int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-  if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
-  if (!gemm_nt_tc_supported(a)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
-  if (scratch == nullptr || scratch_bytes < gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N)) {
-    emip_set_error("gemm_nt_tc: scratch too small");
-    return EMIP_ENOMEM;
-  }
-  const int Np = kpad(a.N);
-  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
-  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* a_lo = a_hi + (size_t)a.B * a.M * Np;
-  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)a.B * a.M * Np * 2 * 2, 1024));
-  split_w_kernel<<<dim3((Np + 2047) / 2048, a.M, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np);
-  EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
-  split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,
-                                                                    a.K, a.N, Np);
-  EMIP_CHECK_LAUNCH("gemm_nt_tc (B)");
-  CUtensorMap ma_hi, ma_lo, mb;
-  int rc;
-  const cuuint64_t adims[3] = {(cuuint64_t)Np, (cuuint64_t)a.M, (cuuint64_t)a.B};
-  const cuuint64_t astr[2] = {(cuuint64_t)Np * 2, (cuuint64_t)a.M * Np * 2};
-  const cuuint32_t abox[3] = {KCH, TM, 1};
-  if ((rc = make_map_bf16(&ma_hi, a_hi, 3, adims, astr, abox))) return rc;
-  if ((rc = make_map_bf16(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
-  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Np, (cuuint64_t)a.K, (cuuint64_t)a.B};
-  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)a.K * 2 * Np * 2};
-  const cuuint32_t bbox[3] = {KCH, TM, 1};
-  if ((rc = make_map_bf16(&mb, bt, 3, bdims, bstr, bbox))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(conv_corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
-  CcParams p = {};
-  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.K + TM - 1) / TM; p.n_tile = TM;
-  p.kchunks = Np / KCH;
-  p.b_bytes = TM * 128; p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
-  p.stages = p.kchunks < 3 ? p.kchunks : 3;
-  p.a_batched = 1; p.Kp = Np; p.N = a.K;
-  p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
-  const long long grid = (long long)a.B * p.n_mtiles * p.n_ntiles;
-  EMIP_CHECK_ARG(grid < 0x7fffffffLL, "gemm_nt_tc: problem too large");
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
-  conv_corr_gemm_kernel<<<(unsigned)grid, THREADS, smem, st>>>(ma_hi, ma_lo, mb, p);
-  EMIP_CHECK_LAUNCH("gemm_nt_tc");
   return EMIP_OK;
 }

@@ -1,8 +1,44 @@
-// Tensor-core (tcgen05, 3-term split-bf16, fp32 accumulate) version of gemm_nn (gemm_simt.cuh); see conv_corr.cu.
+// Tensor-core GEMMs on bf16 hi|lo split operands (tcgen05 SS-mode UMMA, fp32 accumulation in TMEM, TMA-fed 128-byte-swizzled
+// K-major tiles): D = A.hi B.hi + A.lo B.hi + A.hi B.lo.  One kernel, three operand / epilogue modes (gemm_tc.cu):
+//   mode 0  G = A B^T * scale, written as bf16 hi | lo                       (conv_corr: weight x features)
+//   mode 1  out = conv3x3 as a GEMM whose B tiles are shifted 4-D TMA boxes   (conv_corr: taps of f0, zero fill = padding)
+//   mode 2  y = A Bt^T (+ residual), fp32 row-major                            (gemm_nn_tc / gemm_nt_tc: the Injector)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stddef.h>
 #include "gemm_simt.cuh"
+
+struct GemmTcParams {
+  int mode;                 // see above
+  int M;                    // rows of A / of the output
+  int n_mtiles, n_ntiles;   // tiles per batch entry
+  int n_tile;               // UMMA N (multiple of 16, <= 256)
+  int kchunks;              // K / 64 (rounded up; the TMA unit zero-fills the tail)
+  int stages, stage_bytes, b_bytes;
+  int W, H, R;              // mode 1: image geometry, image rows per pixel tile
+  float scale;              // mode 0
+  const float* bias;        // mode 1
+  __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, lo
+  __nv_bfloat16* g_lo;
+  float* out;               // mode 1 output: [B][M][H*W]
+  // mode 2: y[b][m][n] = sum_k A(b)[m][k] Bt[b][n][k] (+ res): A = weights (shared: a_batched = 0), Bt = token-major
+  // activations [B][N][2*Kp] (hi | lo); y / res rows are ldy / ldr floats apart
+  int a_batched, Kp, N;
+  float* y; long long y_stride_b; int ldy;
+  const float* res; long long res_stride_b; int ldr;
+};
+
+constexpr int GEMM_TC_KCH = 64;                    // K elements per chunk (one 128-byte swizzle row of bf16)
+constexpr int GEMM_TC_A_BYTES = 128 * 128;         // one [128 x 64] bf16 operand tile
+
+// bf16 tiled tensor map with 128-byte swizzle (rank 3 or 4), out-of-bounds elements read as zero
+int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box);
+// launches grid = batch * n_mtiles * n_ntiles CTAs; fills stages / stage_bytes from n_tile when stages == 0
+int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b, GemmTcParams p, int batch,
+                   cudaStream_t st);
 
 // y[b][m][n] = sum_k W(b)[m][k] * X'(b)[k][n] (+ res), X' = optional LayerNorm of x over k -- the arguments of gemm_nn.
 // Supported: no accumulate, K <= 1024, 16-byte aligned output rows.
