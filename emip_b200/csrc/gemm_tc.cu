@@ -2,9 +2,10 @@
 // front ends (see gemm_tc.cuh).  Used by conv_corr.cu (f1: conv_corr[0] on the never-materialised cost volume) and by
 // injector.cu (a4: the 1x1 convolutions of the prompt fusion, forward and backward).
 //
-// One 128 x N output tile per CTA: 4 epilogue warps (thread <-> TMEM lane <-> output row), 1 TMA producer warp, 1 UMMA
-// issuer warp; operands stream through a 2-3 stage ring of (A.hi, A.lo, B.hi, B.lo) tiles; per K chunk of 64 the issuer
-// runs 4 + 4 + 4 UMMAs (hi.hi, lo.hi, hi.lo) into one fp32 accumulator tile in TMEM.
+// Persistent CTAs (one per SM) walk the 128 x N output tiles: 4 epilogue warps (thread <-> TMEM lane <-> output row),
+// 1 TMA producer warp, 1 UMMA issuer warp; operands stream through a 2-3 stage ring of (A.hi, A.lo, B.hi, B.lo) tiles;
+// per K chunk of 64 the issuer runs 4 + 4 + 4 UMMAs (hi.hi, lo.hi, hi.lo) into one of two fp32 accumulator tiles in
+// TMEM, so the epilogue of a tile overlaps the main loop of the next one.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/emip_b200.h"
@@ -27,22 +28,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t bar0 = sbase + p.stages * p.stage_bytes;
   auto full = [&](int s) { return bar0 + 8 * s; };
   auto empty = [&](int s) { return bar0 + 8 * (p.stages + s); };
-  const uint32_t acc_full = bar0 + 8 * (2 * p.stages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 1));
+  // two accumulator tiles of <= 256 TMEM columns: the epilogue of tile i overlaps the main loop of tile i + 1
+  auto acc_full = [&](int a) { return bar0 + 8 * (2 * p.stages + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8 * (2 * p.stages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int nt = t % p.n_ntiles; t /= p.n_ntiles;
-  const int mt = t % p.n_mtiles;
-  const int b = t / p.n_mtiles;
+  // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the (batch, m tile, n tile) list
+  auto decode = [&](int t, int& nt, int& mt, int& b) {
+    nt = t % p.n_ntiles; t /= p.n_ntiles;
+    mt = t % p.n_mtiles;
+    b = t / p.n_mtiles;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32((const void*)tmem_slot))
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -56,6 +61,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int nt, mt, b;
+    decode(tile, nt, mt, b);
     for (int kc = 0; kc < p.kchunks; ++kc) {
       mbar_wait(empty(stage), phase ^ 1);
       if (leader) {
@@ -84,13 +92,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    }
     __syncwarp();
   } else if (warp == 5) {
     // ===================== UMMA issuer =====================
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(p.n_tile);
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const int acc = it & 1;
+    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+    mbar_wait(acc_empty(acc), ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (two tiles ago)
+    tc_fence_after();
     for (int kc = 0; kc < p.kchunks; ++kc) {
       mbar_wait(full(stage), phase);
       tc_fence_after();
@@ -99,23 +113,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_BYTES);
         const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_BYTES), b_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + p.b_bytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
         umma_commit(empty(stage));
-        if (kc == p.kchunks - 1) umma_commit(acc_full);
+        if (kc == p.kchunks - 1) umma_commit(acc_full(acc));
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    }
   } else {
     // ===================== epilogue warps: thread <-> output row =====================
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int nt, mt, b;
+    decode(tile, nt, mt, b);
+    const int acc = it & 1;
     const int row = mt * TM + warp * 32 + lane;
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full(acc), (it >> 1) & 1);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
     if (p.mode == 0) {
       __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
       __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
@@ -211,11 +231,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
     tc_fence_before();
+    mbar_arrive(acc_empty(acc));                          // every TMEM read of this tile has completed
+    }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -372,10 +395,12 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
     if (p.stages > 3) p.stages = 3;
     if (p.stages > p.kchunks) p.stages = p.kchunks;
   }
-  const long long grid = (long long)batch * p.n_mtiles * p.n_ntiles;
-  EMIP_CHECK_ARG(grid > 0 && grid < 0x7fffffffLL, "gemm_tc: bad grid");
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
-  gemm_tc_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a_hi, a_lo, b, p);
+  const long long tiles = (long long)batch * p.n_mtiles * p.n_ntiles;
+  EMIP_CHECK_ARG(tiles > 0 && tiles < 0x7fffffffLL, "gemm_tc: bad tile count");
+  p.total_tiles = (int)tiles;
+  const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
+  gemm_tc_kernel<<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p);
   EMIP_CHECK_LAUNCH("gemm_tc");
   return EMIP_OK;
 }

@@ -14,6 +14,7 @@ struct GemmTcParams {
   int mode;                 // see above
   int M;                    // rows of A / of the output
   int n_mtiles, n_ntiles;   // tiles per batch entry
+  int total_tiles;          // batch * n_mtiles * n_ntiles (set by gemm_tc_launch)
   int n_tile;               // UMMA N (multiple of 16, <= 256)
   int kchunks;              // K / 64 (rounded up; the TMA unit zero-fills the tail)
   int stages, stage_bytes, b_bytes;
