@@ -1,0 +1,24 @@
+// Fused single-pass attention forward on the tensor cores (tcgen05 / TMEM / TMA); see attn_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+// out[b][r][:] = softmax_c(Q[b][r] . K[b][c] / sqrt(128)) V[b][c][:]   for nb independent problems.
+struct AttnTcArgs {
+  const void* q_split;       // bf16 [nb][nq][256] token-major hi|lo (match_tc_split)
+  const void* k_split;       // bf16 [nb][nk][256] token-major hi|lo
+  const void* v_chn;         // bf16 [nb][256][ld] channel-major values: rows 0..127 hi, 128..255 lo (pair_bwd_tc_split_chn)
+  float* out;                // ksplit == 1: [nb] x (nq * 128) in out_layout, batch stride out_stride_b (floats)
+  long long out_stride_b;
+  float* lse;                // optional [nb][nq]: log-sum-exp of the scaled scores (natural log)
+  float* part_o;             // ksplit > 1: [ksplit][nb][nq * 128] un-normalised partial outputs (out_layout)
+  float2* part_ml;           // ksplit > 1: [ksplit][nb][nq] (reference exponent in log2 units, partial row sum)
+  int nb, nq, nk, out_layout;
+  float sqrt_c;
+  int ksplit;                // > 1: the key tiles of a row tile are dealt to ksplit CTAs (few row tiles, many keys)
+};
+
+bool attn_tc_supported(int nq, int nk, int c);
+int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st);
+// out / lse from the ksplit partials of attn_tc_fwd
+int attn_tc_merge(const AttnTcArgs& a, cudaStream_t st);

@@ -1,19 +1,17 @@
 // a5 forward on the tensor cores: EMIP_long space-time memory read, reference model/EMIP_long/LTM.py:49-68
 //   p = softmax over the memory axis of (m_in^T q_in / sqrt(De));  mem = m_out p
-// as two passes over the score matrix with kernels this library already has (both 3-term split-bf16, fp32 accumulate):
-//   pass 1  match_tc_fwd (stream-K schedule, analytic-grid mode = no value table, any number of keys): the row
-//           log-sum-exp L[q] of S = Q K^T / sqrt(De);
-//   pass 2  pair_bwd_tc_kernel with its row term reduced to W = e^{S - L} (u = 0, u0 = -1) and the VALUES as the
-//           channel-major column operand: out = W V -- S is recomputed, W goes to TMEM as bf16 hi|lo and feeds a
-//           TS-mode UMMA.  Because W is already normalised by the final L, key splits simply add: the key tiles are
-//           dealt to `ksplit` CTAs per row tile (the model calls this with B = 1: 16 row tiles for 148 SMs) and a
-//           small kernel sums the partial outputs.
+// and f2, the attention core of the GMFlow FeatureTransformer -- both are  out = softmax(Q K^T / sqrt(128)) V  and run
+// as ONE fused flash-style kernel (attn_tc.cu: S in TMEM, online softmax with a lazy reference, P back to TMEM as the
+// A operand of a TS-mode UMMA; 3-term split-bf16 operands, fp32 accumulation) after three operand-split passes.
+// The model calls the memory read with B = 1 (16 row tiles for 148 SMs): the key tiles are then dealt to `ksplit` CTAs
+// per row tile and a small kernel merges the partial (O, m, l) states.
 // The exact-fp32 CUDA-core path (memory_read.cu) stays as the reference path and does the backward.
 #include "common.cuh"
 #include "../../include/emip_b200.h"
 #include "pair_common.cuh"
 #include "match_tc.cuh"
 #include "pair_bwd_tc.cuh"
+#include "attn_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -28,44 +26,22 @@ int pick_ksplit(int B, int Q, int M) {
   return ks < 1 ? 1 : ks;
 }
 
-__global__ void fill_kernel(float* __restrict__ p, size_t n, float v) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// mem[b][c][q] = scale * sum_s part[s][b][c][q]
-__global__ void __launch_bounds__(256)
-sum_parts_kernel(const float* __restrict__ part, float* __restrict__ mem, long long mem_stride_b, int ns, int B, int Q, float scale) {
-  const int b = blockIdx.y;
-  const size_t per = (size_t)KC * Q;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < ns; ++s) acc += __ldcs(part + ((size_t)s * B + b) * per + i);
-    mem[(size_t)b * mem_stride_b + i] = acc * scale;
-  }
-}
-
 struct Ws {
-  char *qs, *ks, *vs, *sk;
-  float *lse, *dummy, *zeros, *ones, *part;
-  size_t sk_bytes;
+  char *qs, *ks, *vs;
+  float* part;
+  float2* ml;
 };
 
 size_t carve(char* base, int B, int M, int Q, Ws* w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += emip_align_up(bytes, 1024); return p; };
-  const size_t zeros_n = (size_t)2 * (M > (size_t)B * Q ? M : (size_t)B * Q);
+  const int ksp = pick_ksplit(B, Q, M);
   char* qs = take(match_tc_split_bytes(B, Q, KC));
   char* ks = take(match_tc_split_bytes(B, M, KC));
   char* vs = take(pair_bwd_tc_chn_bytes(B, M));
-  float* lse = reinterpret_cast<float*>(take(alf((size_t)B * Q)));
-  float* dummy = reinterpret_cast<float*>(take(alf((size_t)B * 2 * Q)));
-  float* zeros = reinterpret_cast<float*>(take(alf(zeros_n)));
-  float* ones = reinterpret_cast<float*>(take(alf((size_t)B * Q)));
-  float* part = reinterpret_cast<float*>(take(alf((size_t)pick_ksplit(B, Q, M) * B * KC * Q)));
-  const size_t skb = match_tc_streamk_bytes(B, Q, M);
-  char* sk = take(skb);
-  if (w) { w->qs = qs; w->ks = ks; w->vs = vs; w->lse = lse; w->dummy = dummy; w->zeros = zeros; w->ones = ones; w->part = part;
-           w->sk = sk; w->sk_bytes = skb; }
+  float* part = reinterpret_cast<float*>(take(ksp > 1 ? alf((size_t)ksp * B * KC * Q) : 0));
+  float2* ml = reinterpret_cast<float2*>(take(ksp > 1 ? alf((size_t)2 * ksp * B * Q) : 0));
+  if (w) { w->qs = qs; w->ks = ks; w->vs = vs; w->part = part; w->ml = ml; }
   return off;
 }
 }  // namespace
@@ -81,37 +57,15 @@ static int attention_tc_core(const float* q_in, const float* m_in, const float* 
   if ((rc = match_tc_split(q_in, nullptr, w.qs, B, Q, KC, layout, 0, st))) return rc;
   if ((rc = match_tc_split(m_in, nullptr, w.ks, B, M, KC, layout, 0, st))) return rc;
   if ((rc = pair_bwd_tc_split_chn(m_out, nullptr, w.vs, B, M, layout, st))) return rc;
-  const size_t zeros_n = (size_t)2 * (M > (size_t)B * Q ? M : (size_t)B * Q);
-  EMIP_CUDA(cudaMemsetAsync(w.zeros, 0, zeros_n * sizeof(float), st));
-  fill_kernel<<<64, 256, 0, st>>>(w.ones, (size_t)B * Q, -1.0f);
-  EMIP_CHECK_LAUNCH("attention_tc (fill)");
-
-  // pass 1: row log-sum-exp
-  MatchTcArgs a = {};
-  a.x_split = w.qs; a.y_split = w.ks; a.nbx = B; a.nby = B;
-  a.v = nullptr; a.v_stride_b = 0; a.grid_w = 64; a.sub_grid = 0;     // analytic-grid mode: only the lse is used
-  a.out = w.dummy; a.lse = w.lse;
-  a.nb = B; a.nq = Q; a.nk = M; a.y_shift = 0; a.y_mod = B;
-  a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
+  AttnTcArgs a = {};
+  a.q_split = w.qs; a.k_split = w.ks; a.v_chn = w.vs;
+  a.out = mem; a.out_stride_b = mem_stride_b; a.lse = lse;
+  a.part_o = w.part; a.part_ml = w.ml;
+  a.nb = B; a.nq = Q; a.nk = M; a.out_layout = out_layout;
   a.sqrt_c = sqrtf((float)KC);
-  a.terms = 3;
-  a.sk_ws = w.sk; a.sk_bytes = w.sk_bytes;
-  if ((rc = match_tc_fwd(a, st))) return rc;
-
-  // pass 2: out = e^{S - L} V, key tiles split over CTAs when the row tiles alone cannot fill the SMs
-  const int ks = pick_ksplit(B, Q, M);
-  PairBwdTcArgs t = {};
-  t.tok_split = w.qs; t.tok_split_y = w.ks; t.chn_split_y = w.vs;
-  t.n_split = B; t.x_base = 0; t.y_base = 0;
-  t.l1 = w.lse; t.u = w.zeros; t.u0 = w.ones; t.t = w.zeros; t.t_stride_b = 0;
-  t.dx = w.part; t.nb = B; t.nr = Q; t.nc = M; t.dx_layout = out_layout;
-  t.sqrt_c = sqrtf((float)KC);
-  t.ksplit = ks;
-  if ((rc = pair_bwd_tc(t, st))) return rc;
-  sum_parts_kernel<<<dim3(128, B), 256, 0, st>>>(w.part, mem, mem_stride_b, ks, B, Q, sqrtf((float)KC));
-  EMIP_CHECK_LAUNCH("attention_tc (sum)");
-  if (lse != nullptr) EMIP_CUDA(cudaMemcpyAsync(lse, w.lse, (size_t)B * Q * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return EMIP_OK;
+  a.ksplit = pick_ksplit(B, Q, M);
+  if ((rc = attn_tc_fwd(a, st))) return rc;
+  return attn_tc_merge(a, st);
 }
 
 extern "C" size_t emip_memory_read_tc_workspace(int B, int De, int Do, int M, int Q) {

@@ -146,6 +146,17 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 
+// fp32 pair -> packed bf16 hi (round to nearest, ties away from zero) + packed bf16 lo (truncated residual) on the
+// integer / FMA pipes only.  cvt.rn.bf16x2.f32 (F2FP) shares the 16-lanes-per-clock XU pipe with MUFU.EX2: in the
+// softmax loops, which need that pipe for the exponentials, two conversions per pair doubled the time per element
+// (attn_tc role profile r2b: 17 cycles per warp-element with F2FP, MUFU alone is 8).  |a - (hi + lo)| <= 2^-16 |a|.
+__device__ __forceinline__ void split_bf16x2_alu(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ha = (__float_as_uint(a) + 0x8000u) & 0xffff0000u, hb = (__float_as_uint(b) + 0x8000u) & 0xffff0000u;
+  const float la = a - __uint_as_float(ha), lb = b - __uint_as_float(hb);
+  hi = __byte_perm(ha, hb, 0x7632);                                  // (a.hi16, b.hi16): first element in the low half
+  lo = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+}
+
 // 16 packed 32-bit columns of this thread's TMEM lane (tcgen05.st, 32x32b shape)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
