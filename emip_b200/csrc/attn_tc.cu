@@ -12,11 +12,13 @@
 //   warps 0..15 softmax + epilogue (thread <-> TMEM lane <-> query row; warp w: lane quarter w%4, 32-column part w/4 of
 //               every key tile; the four threads of a row exchange their tile maxima through shared memory)
 //   warp 16     TMA producer: Q tile (token-major hi|lo) once per item, then per 128-key tile four token-major chunks
-//               of K (for S) and four channel-major chunks of V (for P V) through one 8-stage ring
+//               of K (for S) and four token-major chunks of V (for P V) through one 8-stage ring
 //   warp 17     UMMA issuer
 // TMEM (512 columns): S double-buffered [0,256) | P as bf16 hi [256,320) + lo [320,384) | O accumulator [384,512).
 //   UMMA-1 (SS): S  = Q.hi K.hi^T + Q.lo K.hi^T + Q.hi K.lo^T        (3-term bf16 split: fp32-grade scores)
-//   UMMA-2 (TS): O += P.hi V.hi + P.lo V.hi + P.hi V.lo              (A = P read from TMEM, B = channel-major V chunks)
+//   UMMA-2 (TS): O += P.hi V.hi + P.lo V.hi + P.hi V.lo              (A = P read from TMEM, B = V tiles as they lie in
+//                memory: token-major V through an MN-major shared-memory descriptor, channel-major V (the memory read)
+//                through the K-major one -- either way the operand-split pass of V is elementwise, no transposed copy)
 // Online softmax with a lazy reference: P = 2^{(S - ref)} with ref = the running row maximum as of the last time it
 // grew by more than 2^TAU; only then is the O accumulator rescaled (tcgen05.ld / multiply / tcgen05.st between two
 // UMMA-2 groups).  Any ref gives the same out = O / l in exact arithmetic; bf16 hi|lo and the fp32 accumulators have the
@@ -33,6 +35,7 @@ constexpr int TN = 128;                 // key columns per tile
 constexpr int CH_ELEMS = 64;
 constexpr int CHUNK_BYTES = TM * 128;   // 16 KB
 constexpr int STAGES = 8;
+static_assert(STAGES % 4 == 0, "the MN-major V operand needs its two 64-channel chunks in adjacent ring stages");
 constexpr int NMATH = 16;               // softmax warps
 constexpr int NTHREADS = (NMATH + 2) * 32;
 constexpr uint32_t TMEM_COLS = 512;
@@ -77,7 +80,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, AParams ap) {
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AParams ap) {
   const AttnTcArgs& p = ap.a;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -146,8 +149,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int t = kb; t < ke; ++t) {
         if (t + 1 < ke)
           for (int c = 0; c < 4; ++c) push(&map_k, c * CH_ELEMS, (t + 1) * TN, prob);
-        for (int c = 0; c < 4; ++c)       // hi keys[0:64], hi keys[64:128], lo keys[0:64], lo keys[64:128]
-          push(&map_v, t * TN + (c & 1) * CH_ELEMS, (c >> 1) * 128, prob);
+        if (p.v_chn)
+          for (int c = 0; c < 4; ++c)     // channel-major V: hi keys[0:64], hi keys[64:128], lo keys[0:64], lo keys[64:128]
+            push(&map_v, t * TN + (c & 1) * CH_ELEMS, (c >> 1) * 128, prob);
+        else
+          for (int c = 0; c < 4; ++c)     // token-major V like K: hi ch[0:64], hi ch[64:128], lo ch[0:64], lo ch[64:128]
+            push(&map_v, c * CH_ELEMS, t * TN, prob);
       }
     }
     __syncwarp();
@@ -187,29 +194,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     };
+    // UMMA-2 reads V as an MN-major B operand straight from the token-major tile (keys = rows of 128 B, 64 channels each):
+    // the two 64-channel chunks of a half are adjacent ring stages (the ring advances in groups of four chunks and
+    // STAGES is a multiple of four), LBO = one chunk; a K16 step = two 8-key groups = 2 KB further down.
+    const uint32_t idesc_mn = idesc_full | (1u << 16);    // b_major = MN
     auto mma2 = [&](uint32_t T, bool first, bool last) {  // O += P(T) V(T)
       w_pf += mbar_wait(p_full, T & 1);
       if (first) w_oe += mbar_wait(o_empty, (it & 1) ^ 1);        // the epilogue of the previous item has drained O
-      for (int c = 0; c < 4; ++c) {
-        w_rf += mbar_wait(r_full(stage), phase);
+      for (int half = 0; half < 2; ++half) {              // V.hi chunks, then V.lo chunks
+        const int s0 = stage;
+        w_rf += mbar_wait(r_full(s0), phase);
+        w_rf += mbar_wait(r_full(s0 + 1), phase);
         tc_fence_after();
         if (leader) {
-          const uint64_t bd = make_kmajor_sw128_desc(sbase + OFF_RING + stage * CHUNK_BYTES);
-          const int j = c & 1;                            // which 64 keys of the tile
+          if (p.v_chn) {
+            // channel-major V (the memory read gets it that way): the classic K-major operand, 64 keys per chunk
+            const uint64_t bd = make_kmajor_sw128_desc(sbase + OFF_RING + s0 * CHUNK_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ko = (uint32_t)(8 * (4 * j + k));
-            umma_bf16_ts(t_o, t_p + ko, bd + 2 * k, idesc_full, (first && c == 0 && k == 0) ? 0u : 1u);   // P.hi V.(hi|lo)
-            if (c < 2) umma_bf16_ts(t_o, t_p + 64 + ko, bd + 2 * k, idesc_full, 1u);                      // P.lo V.hi
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t b = bd + (uint64_t)((kk >> 2) * (CHUNK_BYTES >> 4) + 2 * (kk & 3));
+              umma_bf16_ts(t_o, t_p + (uint32_t)(8 * kk), b, idesc_full, (first && half == 0 && kk == 0) ? 0u : 1u);
+              if (half == 0) umma_bf16_ts(t_o, t_p + 64 + (uint32_t)(8 * kk), b, idesc_full, 1u);
+            }
+          } else {
+            const uint64_t bd = make_mnmajor_sw128_desc(sbase + OFF_RING + s0 * CHUNK_BYTES, CHUNK_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t b = bd + (uint64_t)(kk * (2048 >> 4));
+              umma_bf16_ts(t_o, t_p + (uint32_t)(8 * kk), b, idesc_mn, (first && half == 0 && kk == 0) ? 0u : 1u);   // P.hi V.(hi|lo)
+              if (half == 0) umma_bf16_ts(t_o, t_p + 64 + (uint32_t)(8 * kk), b, idesc_mn, 1u);                     // P.lo V.hi
+            }
           }
-          umma_commit(r_empty(stage));
-          if (c == 3) {
+          umma_commit(r_empty(s0));
+          umma_commit(r_empty(s0 + 1));
+          if (half == 1) {
             umma_commit(p_empty);
             if (last) umma_commit(o_full);
           }
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        stage += 2;
+        if (stage == STAGES) { stage = 0; phase ^= 1; }
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -345,7 +370,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         if (row_ok) {
           if (p.out_layout == EMIP_LAYOUT_NC) {
-            float4* dst = reinterpret_cast<float4*>(OUT + (size_t)row * 128 + cb);
+            size_t orow = (size_t)row;
+            if (p.win.enabled) {                          // scatter: token `row` of block (prob / B) of image (prob % B)
+              const int blk = prob / p.win.B, img = prob - blk * p.win.B;
+              const int bw = p.win.bw[blk];
+              const int ty = row / bw, tx = row - ty * bw;
+              OUT = p.out;
+              orow = ((size_t)img * p.win.h + p.win.r0[blk] + ty) * p.win.w + p.win.c0[blk] + tx;
+            }
+            float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               dst[q] = make_float4(__uint_as_float(r[4 * q]) * sc, __uint_as_float(r[4 * q + 1]) * sc,
@@ -406,13 +439,16 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   if (!attn_tc_supported(a.nq, a.nk, 128)) { emip_set_error("attn_tc_fwd: unsupported shape"); return EMIP_ENOSYS; }
   const int nkt = (a.nk + TN - 1) / TN;
   if (a.ksplit > nkt) { emip_set_error("attn_tc_fwd: ksplit %d exceeds the %d key tiles", a.ksplit, nkt); return EMIP_EINVAL; }
+  if (a.win.enabled && (a.ksplit > 1 || a.out_layout != EMIP_LAYOUT_NC)) { emip_set_error("attn_tc_fwd: the window scatter needs ksplit == 1 and the NC layout"); return EMIP_EINVAL; }
   if (a.ksplit > 1 && (a.part_o == nullptr || a.part_ml == nullptr)) { emip_set_error("attn_tc_fwd: ksplit needs partial buffers"); return EMIP_EINVAL; }
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_bf16_map(&mq, a.q_split, 256, (uint64_t)a.nq, (uint64_t)a.nb, 512, (uint64_t)a.nq * 512))) return rc;
   if ((rc = make_bf16_map(&mk, a.k_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
-  const uint64_t ld = ((uint64_t)a.nk + 7) / 8 * 8;       // = pair_bwd_tc_chn_ld
-  if ((rc = make_bf16_map(&mv, a.v_chn, (uint64_t)a.nk, 256, (uint64_t)a.nb, ld * 2, ld * 2 * 256))) return rc;
+  if (a.v_chn) {
+    const uint64_t ld = ((uint64_t)a.nk + 7) / 8 * 8;     // = pair_bwd_tc_chn_ld
+    if ((rc = make_bf16_map(&mv, a.v_split, (uint64_t)a.nk, 256, (uint64_t)a.nb, ld * 2, ld * 2 * 256))) return rc;
+  } else if ((rc = make_bf16_map(&mv, a.v_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
     EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -3,11 +3,20 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+// Optional output scatter for window attention (window_attn.cu): problem p = block (p / B) of image (p % B), token t of
+// a block of width bw is pixel (r0 + t / bw, c0 + t % bw) of the [B][h][w][128] output.
+struct AttnWinMap {
+  int enabled, B, h, w;
+  int r0[16], c0[16], bw[16];
+};
+
 // out[b][r][:] = softmax_c(Q[b][r] . K[b][c] / sqrt(128)) V[b][c][:]   for nb independent problems.
 struct AttnTcArgs {
   const void* q_split;       // bf16 [nb][nq][256] token-major hi|lo (match_tc_split)
   const void* k_split;       // bf16 [nb][nk][256] token-major hi|lo
-  const void* v_chn;         // bf16 [nb][256][ld] channel-major values: rows 0..127 hi, 128..255 lo (pair_bwd_tc_split_chn)
+  const void* v_split;       // v_chn == 0: bf16 [nb][nk][256] token-major hi|lo values (read as an MN-major UMMA operand)
+                             // v_chn == 1: bf16 [nb][256][ld] channel-major: rows 0..127 hi, 128..255 lo (pair_bwd_tc_split_chn)
+  int v_chn;
   float* out;                // ksplit == 1: [nb] x (nq * 128) in out_layout, batch stride out_stride_b (floats)
   long long out_stride_b;
   float* lse;                // optional [nb][nq]: log-sum-exp of the scaled scores (natural log)
@@ -16,6 +25,7 @@ struct AttnTcArgs {
   int nb, nq, nk, out_layout;
   float sqrt_c;
   int ksplit;                // > 1: the key tiles of a row tile are dealt to ksplit CTAs (few row tiles, many keys)
+  AttnWinMap win;            // enabled: out is the [B][h][w][128] image, rows are scattered (needs ksplit == 1, NC layout)
 };
 
 bool attn_tc_supported(int nq, int nk, int c);

@@ -32,13 +32,15 @@ struct Ws {
   float2* ml;
 };
 
-size_t carve(char* base, int B, int M, int Q, Ws* w) {
+// the values are split without a transpose either way: channel-major sources feed the K-major operand form,
+// token-major sources the MN-major one
+size_t carve(char* base, int B, int M, int Q, int layout, Ws* w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += emip_align_up(bytes, 1024); return p; };
   const int ksp = pick_ksplit(B, Q, M);
   char* qs = take(match_tc_split_bytes(B, Q, KC));
   char* ks = take(match_tc_split_bytes(B, M, KC));
-  char* vs = take(pair_bwd_tc_chn_bytes(B, M));
+  char* vs = take(layout == EMIP_LAYOUT_CN ? pair_bwd_tc_chn_bytes(B, M) : match_tc_split_bytes(B, M, KC));
   float* part = reinterpret_cast<float*>(take(ksp > 1 ? alf((size_t)ksp * B * KC * Q) : 0));
   float2* ml = reinterpret_cast<float2*>(take(ksp > 1 ? alf((size_t)2 * ksp * B * Q) : 0));
   if (w) { w->qs = qs; w->ks = ks; w->vs = vs; w->part = part; w->ml = ml; }
@@ -52,13 +54,15 @@ static int attention_tc_core(const float* q_in, const float* m_in, const float* 
                              long long mem_stride_b, int out_layout, float* lse, void* workspace, int B, int M, int Q,
                              cudaStream_t st) {
   Ws w;
-  carve(static_cast<char*>(workspace), B, M, Q, &w);
+  carve(static_cast<char*>(workspace), B, M, Q, layout, &w);
   int rc;
   if ((rc = match_tc_split(q_in, nullptr, w.qs, B, Q, KC, layout, 0, st))) return rc;
   if ((rc = match_tc_split(m_in, nullptr, w.ks, B, M, KC, layout, 0, st))) return rc;
-  if ((rc = pair_bwd_tc_split_chn(m_out, nullptr, w.vs, B, M, layout, st))) return rc;
+  if (layout == EMIP_LAYOUT_CN) rc = pair_bwd_tc_split_chn(m_out, nullptr, w.vs, B, M, layout, st);
+  else rc = match_tc_split(m_out, nullptr, w.vs, B, M, KC, layout, 0, st);
+  if (rc) return rc;
   AttnTcArgs a = {};
-  a.q_split = w.qs; a.k_split = w.ks; a.v_chn = w.vs;
+  a.q_split = w.qs; a.k_split = w.ks; a.v_split = w.vs; a.v_chn = layout == EMIP_LAYOUT_CN;
   a.out = mem; a.out_stride_b = mem_stride_b; a.lse = lse;
   a.part_o = w.part; a.part_ml = w.ml;
   a.nb = B; a.nq = Q; a.nk = M; a.out_layout = out_layout;
@@ -70,7 +74,7 @@ static int attention_tc_core(const float* q_in, const float* m_in, const float* 
 
 extern "C" size_t emip_memory_read_tc_workspace(int B, int De, int Do, int M, int Q) {
   if (B < 0 || M <= 0 || Q <= 0 || De != KC || Do != KC) return 0;
-  return carve(nullptr, B, M, Q, nullptr);
+  return carve(nullptr, B, M, Q, EMIP_LAYOUT_CN, nullptr);
 }
 
 extern "C" int emip_memory_read_fwd_tc(const float* m_in, const float* m_out, const float* q_in, float* mem,
@@ -97,7 +101,7 @@ extern "C" int emip_memory_read_fwd_tc(const float* m_in, const float* m_out, co
 // q, k, v, out token-major [nb][n][128].
 extern "C" size_t emip_attention_tc_workspace(int nb, int n, int C) {
   if (nb < 0 || n <= 0 || C != KC) return 0;
-  return carve(nullptr, nb, n, n, nullptr);
+  return carve(nullptr, nb, n, n, EMIP_LAYOUT_NC, nullptr);
 }
 
 extern "C" int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace,

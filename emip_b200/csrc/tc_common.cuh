@@ -101,6 +101,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;              // SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte swizzle (cute::UMMA make_umma_desc<Major::MN>, LayoutType::B128): rows of 128 B hold 64 consecutive
+// M/N elements of one K index, 8 K-rows form a 1 KB swizzle atom (stride byte offset between atoms along K), the next
+// 64 M/N elements start `lbo_bytes` further (leading byte offset).  This is what a {64 elements x rows} SWIZZLE_128B
+// TMA box of a row-major [K][MN] tensor leaves in shared memory.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);

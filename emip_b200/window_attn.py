@@ -5,8 +5,9 @@ Reference: model/EMIP_short/motion/gmflow/transformer.py:8-16 ``single_head_full
 below keep the reference's names and signatures (``dropin.install`` binds them); the projections, LayerNorms and MLPs of
 the transformer layers stay library code.
 
-The forward runs on the tensor cores (``emip_attention_fwd_tc``: row log-sum-exp pass + ``e^{S-L} V`` pass, bf16 hi/lo
-split operands, fp32 accumulation).  The shifted-window mask of the reference (0 / -100, transformer.py:19-43) only
+The forward runs on the tensor cores as one fused flash-style kernel (csrc/attn_tc.cu: bf16 hi/lo split operands, fp32
+accumulation, online softmax); a whole layer is ONE C-ABI call (``emip_window_attention_fwd_tc``) whose operand-split
+pass and epilogue do the window gather / scatter as address arithmetic.  The shifted-window mask of the reference (0 / -100, transformer.py:19-43) only
 separates rectangular blocks of tokens -- in un-rolled coordinates the cuts are at ``shift`` and ``h - window + shift``
 -- and ``exp(-100)`` relative weight is below fp32 resolution, so a shifted layer is computed as plain attention inside
 each block: no roll, no mask tensor, no masked score entries.
@@ -80,30 +81,75 @@ def _axis_groups(size, num_splits, shift):
     return out
 
 
+def _block_groups(h, w, num_splits, with_shift):
+    """{(bh, bw): [(r0, c0), ...]}: the rectangular token blocks of one layer, grouped by shape."""
+    sh, sw = ((h // num_splits) // 2, (w // num_splits) // 2) if with_shift else (0, 0)
+    by_shape = {}
+    for (r0, r1) in _axis_groups(h, num_splits, sh):
+        for (c0, c1) in _axis_groups(w, num_splits, sw):
+            by_shape.setdefault((r1 - r0, c1 - c0), []).append((r0, c0))
+    return by_shape
+
+
+class _WindowAttention(torch.autograd.Function):
+    """One C-ABI call per layer: the window partition is address arithmetic inside the kernels (csrc/window_attn.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, num_splits, with_shift, h, w):
+        b, _, c = q.shape
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        L = _lib.lib()
+        L.emip_window_attention_tc_workspace.restype = ctypes.c_size_t
+        need = L.emip_window_attention_tc_workspace(I(b), I(h), I(w), I(c), I(num_splits), I(int(with_shift)))
+        if need == 0 and b > 0:
+            raise _lib.EmipError(f"emip_b200 window attention: unsupported geometry h={h} w={w} C={c} num_splits={num_splits}")
+        ws, ws_ptr, ws_n = workspace(need, q.device)
+        out = torch.empty_like(q)
+        _lib.check(L.emip_window_attention_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(out), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(b), I(h),
+                                                  I(w), I(c), I(num_splits), I(int(with_shift)), stream_ptr()),
+                   "emip_window_attention_fwd_tc")
+        ctx.save_for_backward(q, k, v)
+        ctx.geom = (num_splits, with_shift, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        # plumbing (DESIGN.md 7): the same block decomposition with library matmuls
+        q, k, v = ctx.saved_tensors
+        num_splits, with_shift, h, w = ctx.geom
+        b, _, c = q.shape
+        scale = c ** -0.5
+        q4, k4, v4, d4 = (t.reshape(b, h, w, c) for t in (q, k, v, dout))
+        dq, dk, dv = (torch.empty_like(q4) for _ in range(3))
+        for (bh, bw), origins in _block_groups(h, w, num_splits, with_shift).items():
+            n = bh * bw
+
+            def gather(t):
+                return torch.stack([t[:, r0:r0 + bh, c0:c0 + bw] for (r0, c0) in origins], 0).reshape(len(origins) * b, n, c)
+            qg, kg, vg, dg = gather(q4), gather(k4), gather(v4), gather(d4)
+            p = torch.softmax(torch.matmul(qg, kg.transpose(1, 2)) * scale, dim=-1)
+            dp = torch.matmul(dg, vg.transpose(1, 2))
+            ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
+            parts = (torch.matmul(ds, kg), torch.matmul(ds.transpose(1, 2), qg), torch.matmul(p.transpose(1, 2), dg))
+            for dst, src in zip((dq, dk, dv), parts):
+                src = src.view(len(origins), b, bh, bw, c)
+                for i, (r0, c0) in enumerate(origins):
+                    dst[:, r0:r0 + bh, c0:c0 + bw] = src[i]
+        return dq.view(b, h * w, c), dk.view(b, h * w, c), dv.view(b, h * w, c), None, None, None, None
+
+
 def single_head_split_window_attention(q, k, v, num_splits=1, with_shift=False, h=None, w=None, attn_mask=None):
     """Reference transformer.py:46-105: q, k, v [B, h*w, C] -> [B, h*w, C]."""
     assert q.dim() == k.dim() == v.dim() == 3
     assert h is not None and w is not None
     assert q.size(1) == h * w
-    b, _, c = q.shape
     assert h % num_splits == 0 and w % num_splits == 0
     if with_shift:
         assert attn_mask is not None                         # the reference computes it once; its content is implied here
-    sh, sw = ((h // num_splits) // 2, (w // num_splits) // 2) if with_shift else (0, 0)
-    rows, cols = _axis_groups(h, num_splits, sh), _axis_groups(w, num_splits, sw)
-    q4, k4, v4 = q.view(b, h, w, c), k.view(b, h, w, c), v.view(b, h, w, c)
-    out = torch.empty_like(q4)
-    # batch the blocks of equal shape into one launch
-    by_shape = {}
-    for (r0, r1) in rows:
-        for (c0, c1) in cols:
-            by_shape.setdefault((r1 - r0, c1 - c0), []).append((r0, c0))
-    for (bh, bw), origins in by_shape.items():
-        n = bh * bw
-
-        def gather(t):
-            return torch.stack([t[:, r0:r0 + bh, c0:c0 + bw] for (r0, c0) in origins], 0).reshape(len(origins) * b, n, c)
-        o = attention(gather(q4), gather(k4), gather(v4)).view(len(origins), b, bh, bw, c)
-        for i, (r0, c0) in enumerate(origins):
-            out[:, r0:r0 + bh, c0:c0 + bw] = o[i]
-    return out.view(b, h * w, c)
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise _lib.EmipError("emip_b200 attention needs CUDA tensors (no CPU fallback)")
+    if q.dtype != torch.float32 or k.dtype != torch.float32 or v.dtype != torch.float32:
+        raise TypeError("emip_b200 attention computes from fp32 tensors")
+    if q.shape != k.shape or q.shape != v.shape:
+        raise ValueError(f"expected q, k, v of one shape [B, h*w, C], got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    return _WindowAttention.apply(q, k, v, num_splits, bool(with_shift), h, w)

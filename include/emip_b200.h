@@ -221,6 +221,18 @@ size_t emip_attention_tc_workspace(int nb, int n, int C);
 int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace, size_t ws_bytes,
                           int nb, int n, int C, void* stream);
 
+/* One call per FeatureTransformer attention layer (csrc/window_attn.cu): q, k, v, out [B][h*w][C] as the reference's
+ * single_head_split_window_attention(q, k, v, num_splits, with_shift, h, w, attn_mask) takes and returns them.  The
+ * window partition (and, when shifted, the block structure its 0 / -100 mask implies) is address arithmetic inside the
+ * operand-split pass and the attention epilogue: no gather / scatter / roll copies, no mask tensor.  C = 128, every
+ * block >= 16 tokens, at most 16 blocks of one shape.  Forward only. */
+size_t emip_window_attention_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift);
+int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace,
+                                 size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift, void* stream);
+
+/* Diagnostics: device buffer of (CTAs x 16) cycle counters filled by the next fused-attention launches (NULL = off). */
+void emip_attn_tc_set_profile_buffer(unsigned long long* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif
