@@ -432,7 +432,7 @@ static unsigned long long* g_attn_prof = nullptr;
 // Diagnostics: device buffer of gridDim.x * 16 counters filled by the next launches (NULL switches it off).
 extern "C" void emip_attn_tc_set_profile_buffer(unsigned long long* dev_buf) { g_attn_prof = dev_buf; }
 
-bool attn_tc_supported(int nq, int nk, int c) { return c == 128 && nq >= 1 && nk >= 16; }
+bool attn_tc_supported(int nq, int nk, int c) { return c == 128 && nq >= 1 && nk >= 1; }
 
 int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   if (a.nb == 0 || a.nq == 0) return EMIP_OK;

@@ -20,6 +20,7 @@ size_t alf(size_t n_floats) { return emip_align_up(n_floats * sizeof(float), 102
 
 int pick_ksplit(int B, int Q, int M) {
   const int nrt = (Q + 127) / 128, nkt = (M + 127) / 128;
+  if (B <= 0 || nrt <= 0) return 1;
   int ks = (emip_num_sms() + B * nrt - 1) / (B * nrt);
   if (ks > nkt) ks = nkt;
   if (ks > 16) ks = 16;
@@ -108,7 +109,7 @@ extern "C" int emip_attention_fwd_tc(const float* q, const float* k, const float
                                      size_t ws_bytes, int nb, int n, int C, void* stream) {
   if (nb == 0) return EMIP_OK;
   EMIP_CHECK_ARG(q && k && v && out && workspace, "attention_fwd_tc: null pointer");
-  EMIP_CHECK_ARG(nb > 0 && n >= 16, "attention_fwd_tc: bad shape nb=%d n=%d (n >= 16)", nb, n);
+  EMIP_CHECK_ARG(nb > 0 && n >= 1, "attention_fwd_tc: bad shape nb=%d n=%d", nb, n);
   if (C != KC) {
     emip_set_error("attention_fwd_tc: C=%d unsupported (kernels are built for the model's C=128)", C);
     return EMIP_ENOSYS;

@@ -152,11 +152,6 @@ extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, cons
     emip_set_error("window_attention_fwd_tc: unsupported window geometry h=%d w=%d num_splits=%d", h, w, num_splits);
     return EMIP_ENOSYS;
   }
-  for (int i = 0; i < ng; ++i)
-    if (g[i].n < 16) {
-      emip_set_error("window_attention_fwd_tc: block of %d tokens is below the 16-token minimum", g[i].n);
-      return EMIP_ENOSYS;
-    }
   if (ws_bytes < emip_window_attention_tc_workspace(B, h, w, C, num_splits, with_shift) ||
       reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) {
     emip_set_error("window_attention_fwd_tc: workspace too small or not 1024-byte aligned");

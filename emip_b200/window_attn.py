@@ -49,7 +49,7 @@ class _Attention(torch.autograd.Function):
 
 
 def attention(q, k, v):
-    """softmax(q k^T / sqrt(C)) v for [nb, n, C] token-major tensors, C = 128, n >= 16."""
+    """softmax(q k^T / sqrt(C)) v for [nb, n, C] token-major tensors, C = 128."""
     if not (q.is_cuda and k.is_cuda and v.is_cuda):
         raise _lib.EmipError("emip_b200 attention needs CUDA tensors (no CPU fallback)")
     if q.dtype != torch.float32 or k.dtype != torch.float32 or v.dtype != torch.float32:

@@ -216,7 +216,7 @@ int emip_photometric_bwd(const float* im, const float* rec, const float* mask, c
 /* Replaces model/EMIP_short/motion/gmflow/transformer.py:8-16 single_head_full_attention and the per-window attention
  * of :46-105 single_head_split_window_attention: out = softmax(q k^T / sqrt(C)) v for nb independent problems of n
  * tokens (the shifted-window mask is handled by the host side: it only separates rectangular token blocks, each of
- * which is a plain attention problem).  q, k, v, out token-major [nb][n][C], C = 128, n >= 16.  Forward only. */
+ * which is a plain attention problem).  q, k, v, out token-major [nb][n][C], C = 128.  Forward only. */
 size_t emip_attention_tc_workspace(int nb, int n, int C);
 int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace, size_t ws_bytes,
                           int nb, int n, int C, void* stream);
@@ -224,8 +224,8 @@ int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float*
 /* One call per FeatureTransformer attention layer (csrc/window_attn.cu): q, k, v, out [B][h*w][C] as the reference's
  * single_head_split_window_attention(q, k, v, num_splits, with_shift, h, w, attn_mask) takes and returns them.  The
  * window partition (and, when shifted, the block structure its 0 / -100 mask implies) is address arithmetic inside the
- * operand-split pass and the attention epilogue: no gather / scatter / roll copies, no mask tensor.  C = 128, every
- * block >= 16 tokens, at most 16 blocks of one shape.  Forward only. */
+ * operand-split pass and the attention epilogue: no gather / scatter / roll copies, no mask tensor.  C = 128, at most
+ * 16 blocks with the same token count (num_splits <= 3).  Forward only. */
 size_t emip_window_attention_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift);
 int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace,
                                  size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift, void* stream);

@@ -536,3 +536,44 @@ def test_f2_full_attention_vs_oracle():
     q, k, v = (cases.randn(140 + i, (3, 300, 128), 1.5) for i in range(3))
     ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / 128 ** 0.5, -1) @ v.double()
     assert rel(single_head_full_attention(dev(q), dev(k), dev(v)), ref) < TOL_EXACT
+
+
+@pytest.mark.parametrize("b,h,w,k", [(3, 44, 44, 2), (1, 24, 40, 2), (5, 12, 18, 3), (2, 16, 16, 1)])
+def test_f2_window_geometries_vs_oracle(b, h, w, k):
+    """The fused per-layer call against the oracle's roll + mask formulation on other batch sizes / grids / splits."""
+    from emip_b200.window_attn import single_head_split_window_attention
+    q, k_, v = (cases.randn(150 + i, (b, h * w, 128), 1.5 if i < 2 else 1.0) for i in range(3))
+    for shift in (False, True):
+        if shift and k == 1:
+            continue                                                   # the reference never shifts a single window
+        ref = O.split_window_attention(q.double(), k_.double(), v.double(), k, shift, h, w)
+        out = single_head_split_window_attention(dev(q), dev(k_), dev(v), k, shift, h, w, torch.zeros(1) if shift else None)
+        assert rel(out, ref) < TOL_EXACT, (shift, rel(out, ref))
+
+
+def test_f2_attention_lazy_rescale_and_peaked_rows():
+    """Row maxima that grow by > 2^16 from key tile to key tile (forces the O-accumulator rescale of attn_tc.cu on every
+    tile) and near-one-hot rows with scores in [-80, 70]."""
+    from emip_b200.window_attn import attention
+    n = 700
+    q = cases.randn(160, (2, n, 128))
+    sgn = torch.sign(q[:, :1, :])
+    k = cases.randn(161, (2, n, 128), 0.05) + torch.arange(n, dtype=torch.float32).view(1, n, 1) * 0.02 * sgn
+    q = q.abs() * sgn
+    v = cases.randn(162, (2, n, 128))
+    s = q.double() @ k.double().transpose(1, 2) / 128 ** 0.5
+    assert (s[:, :, 128:].amax(-1) - s[:, :, :128].amax(-1)).min() > 16 * 0.6931 * 3   # the ramp really crosses the threshold
+    ref = torch.softmax(s, -1) @ v.double()
+    assert rel(attention(dev(q), dev(k), dev(v)), ref) < 2e-4          # |S| ~ 160: S itself carries ~4e-6 * 160 of error
+    q, k, v = (cases.randn(163 + i, (3, 200, 128), 4.0 if i < 2 else 1.0) for i in range(3))
+    ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / 128 ** 0.5, -1) @ v.double()
+    assert rel(attention(dev(q), dev(k), dev(v)), ref) < TOL_EXACT
+
+
+def test_f2_attention_empty_and_minimum():
+    from emip_b200.window_attn import attention
+    z = torch.zeros(0, 64, 128, device="cuda")
+    assert attention(z, z, z).shape == (0, 64, 128)
+    q, k, v = (cases.randn(170 + i, (2, 6, 128)) for i in range(3))     # a handful of tokens: one partial tile
+    ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / 128 ** 0.5, -1) @ v.double()
+    assert rel(attention(dev(q), dev(k), dev(v)), ref) < TOL_EXACT
