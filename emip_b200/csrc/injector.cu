@@ -598,9 +598,238 @@ gdfn_gate_bwd_kernel(const float* __restrict__ tpre, const float* __restrict__ w
   }
 }
 
+// ------------------------------------------------------------------ 4-wide variants of the plane kernels (W % 4 == 0)
+// Same arithmetic per output as the kernels above; one thread = four consecutive pixels of a row.  The padded plane has
+// pitch W + 8 with the interior at column 4, so every row is 16-byte aligned: 128-bit global loads / stores, and a
+// 3x3 window row for four outputs is one LDS.128 + two LDS.32 (2.25 shared loads per output and tap row instead of 9,
+// one integer division per four outputs).  r1: gdfn_gate_fwd 92 us, dwconv 57 us at B = 16, 3-5x off their HBM floors.
+__device__ __forceinline__ void load_plane4(float* s, const float* __restrict__ g, int H, int W) {
+  const int PW = W + 8, W4 = W >> 2;
+  for (int i = threadIdx.x; i < PW; i += blockDim.x) { s[i] = 0.f; s[(H + 1) * PW + i] = 0.f; }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { s[(i + 1) * PW + 3] = 0.f; s[(i + 1) * PW + 4 + W] = 0.f; }
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, xq = i - y * W4;
+    *reinterpret_cast<float4*>(s + (y + 1) * PW + 4 + 4 * xq) = __ldg(g4 + i);
+  }
+}
+__device__ __forceinline__ void zero_plane4(float* s, int H, int W) {
+  const int tot4 = ((H + 2) * (W + 8)) >> 2;
+  for (int i = threadIdx.x; i < tot4; i += blockDim.x) reinterpret_cast<float4*>(s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// the 3 x 6 input window of the four outputs (y, x0 .. x0 + 3)
+__device__ __forceinline__ void window4(const float* s, int PW, int y, int x0, float (&v)[3][6]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* p = s + (y + r) * PW + 4 + x0;
+    const float4 m = *reinterpret_cast<const float4*>(p);
+    v[r][0] = p[-1]; v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w; v[r][5] = p[4];
+  }
+}
+__device__ __forceinline__ void conv9x4(const float (&v)[3][6], const float* k, float (&o)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = v[0][j] * k[0] + v[0][j + 1] * k[1] + v[0][j + 2] * k[2] + v[1][j] * k[3] + v[1][j + 1] * k[4] + v[1][j + 2] * k[5] +
+           v[2][j] * k[6] + v[2][j + 1] * k[7] + v[2][j + 2] * k[8];
+}
+__device__ __forceinline__ void conv9x4_flipped(const float (&v)[3][6], const float* k, float (&o)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = v[0][j] * k[8] + v[0][j + 1] * k[7] + v[0][j + 2] * k[6] + v[1][j] * k[5] + v[1][j + 1] * k[4] + v[1][j + 2] * k[3] +
+           v[2][j] * k[2] + v[2][j + 1] * k[1] + v[2][j + 2] * k[0];
+}
+
+// N block-wide sums with one barrier pair: warp shuffles, one smem slot per (warp, value), then thread i < N adds the
+// warp partials in a fixed order.  Returns the total of value `threadIdx.x` to threads < N (0 elsewhere).
+template <int N>
+__device__ __forceinline__ float block_sums(const float (&v)[N], float* red /* [8][N] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float t = warp_sum(v[i]);
+    if (lane == 0) red[warp * N + i] = t;
+  }
+  __syncthreads();
+  float tot = 0.f;
+  if (threadIdx.x < N)
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) tot += red[wi * N + threadIdx.x];
+  return tot;
+}
+
+__global__ void __launch_bounds__(256)
+dwconv_fwd_v4_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, float* __restrict__ out2,
+                     float* __restrict__ sumsq, int C, int split, int H, int W) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float red[8];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, W4 = W >> 2;
+  load_plane4(sm, in + ((size_t)b * C + c) * N, H, W);
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  __syncthreads();
+  float* o = (c < split) ? out + ((size_t)b * split + c) * N : out2 + ((size_t)b * (C - split) + (c - split)) * N;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, x0 = 4 * (i - y * W4);
+    float v[3][6], r[4];
+    window4(sm, PW, y, x0, v);
+    conv9x4(v, k, r);
+    reinterpret_cast<float4*>(o)[i] = make_float4(r[0], r[1], r[2], r[3]);
+    ss = fmaf(r[0], r[0], fmaf(r[1], r[1], fmaf(r[2], r[2], fmaf(r[3], r[3], ss))));
+  }
+  if (sumsq != nullptr) {
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) sumsq[(size_t)b * C + c] = ss;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dwconv_bwd_v4_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ dout,
+                     const float* __restrict__ dout2, float* __restrict__ din, float* __restrict__ dw_part, int C, int split,
+                     int H, int W) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float red9[8 * 9];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, P = (H + 2) * PW, W4 = W >> 2;
+  float* s_in = sm;
+  float* s_do = sm + P;
+  load_plane4(s_in, in + ((size_t)b * C + c) * N, H, W);
+  const float* dg = (c < split) ? dout + ((size_t)b * split + c) * N : dout2 + ((size_t)b * (C - split) + (c - split)) * N;
+  load_plane4(s_do, dg, H, W);
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  __syncthreads();
+  float dk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dk[i] = 0.f;
+  float* di = din + ((size_t)b * C + c) * N;
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, x0 = 4 * (i - y * W4);
+    float vd[3][6], vi[3][6], r[4];
+    window4(s_do, PW, y, x0, vd);
+    conv9x4_flipped(vd, k, r);
+    reinterpret_cast<float4*>(di)[i] = make_float4(r[0], r[1], r[2], r[3]);
+    window4(s_in, PW, y, x0, vi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = vd[1][j + 1];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) dk[ky * 3 + kx] = fmaf(g, vi[ky][j + kx], dk[ky * 3 + kx]);
+    }
+  }
+  const float t = block_sums<9>(dk, red9);
+  if (threadIdx.x < 9) dw_part[((size_t)b * C + c) * 9 + threadIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(256)
+gdfn_gate_fwd_v4_kernel(const float* __restrict__ tpre, const float* __restrict__ w, float* __restrict__ g, int H, int W) {
+  extern __shared__ __align__(16) float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, P = (H + 2) * PW, W4 = W >> 2;
+  load_plane4(sm, tpre + ((size_t)b * HID2 + c) * N, H, W);
+  load_plane4(sm + P, tpre + ((size_t)b * HID2 + c + HID) * N, H, W);
+  float k1[9], k2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { k1[i] = __ldg(w + c * 9 + i); k2[i] = __ldg(w + (c + HID) * 9 + i); }
+  __syncthreads();
+  float4* o = reinterpret_cast<float4*>(g + ((size_t)b * HID + c) * N);
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, x0 = 4 * (i - y * W4);
+    float v[3][6], t1[4], t2[4];
+    window4(sm, PW, y, x0, v);
+    conv9x4(v, k1, t1);
+    window4(sm + P, PW, y, x0, v);
+    conv9x4(v, k2, t2);
+    o[i] = make_float4(gelu_erf(t1[0]) * t2[0], gelu_erf(t1[1]) * t2[1], gelu_erf(t1[2]) * t2[2], gelu_erf(t1[3]) * t2[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gdfn_gate_bwd_v4_kernel(const float* __restrict__ tpre, const float* __restrict__ w, const float* __restrict__ dg,
+                        float* __restrict__ dtpre, float* __restrict__ g_out, float* __restrict__ dw_part, int H, int W) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float red18[8 * 18];
+  const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, P = (H + 2) * PW, W4 = W >> 2;
+  float* s1 = sm;            // t_pre[c]
+  float* s2 = sm + P;        // t_pre[c + HID]
+  float* d1 = sm + 2 * P;    // dt1 (padded)
+  float* d2 = sm + 3 * P;    // dt2
+  load_plane4(s1, tpre + ((size_t)b * HID2 + c) * N, H, W);
+  load_plane4(s2, tpre + ((size_t)b * HID2 + c + HID) * N, H, W);
+  zero_plane4(d1, H, W);
+  zero_plane4(d2, H, W);
+  float k1[9], k2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { k1[i] = __ldg(w + c * 9 + i); k2[i] = __ldg(w + (c + HID) * 9 + i); }
+  __syncthreads();
+  const float4* dgp = reinterpret_cast<const float4*>(dg + ((size_t)b * HID + c) * N);
+  float4* go = reinterpret_cast<float4*>(g_out + ((size_t)b * HID + c) * N);
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, x0 = 4 * (i - y * W4);
+    float v[3][6], t1[4], t2[4];
+    window4(s1, PW, y, x0, v);
+    conv9x4(v, k1, t1);
+    window4(s2, PW, y, x0, v);
+    conv9x4(v, k2, t2);
+    const float4 d4 = __ldg(dgp + i);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    float gg[4], a1[4], a2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gg[j] = gelu_erf(t1[j]);
+      a1[j] = d[j] * t2[j] * gelu_erf_grad(t1[j]);
+      a2[j] = d[j] * gg[j];
+    }
+    go[i] = make_float4(gg[0] * t2[0], gg[1] * t2[1], gg[2] * t2[2], gg[3] * t2[3]);
+    *reinterpret_cast<float4*>(d1 + (y + 1) * PW + 4 + x0) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+    *reinterpret_cast<float4*>(d2 + (y + 1) * PW + 4 + x0) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+  }
+  __syncthreads();
+  float dkk[18];             // [0,9) channel c, [9,18) channel c + HID
+#pragma unroll
+  for (int i = 0; i < 18; ++i) dkk[i] = 0.f;
+  float4* o1 = reinterpret_cast<float4*>(dtpre + ((size_t)b * HID2 + c) * N);
+  float4* o2 = reinterpret_cast<float4*>(dtpre + ((size_t)b * HID2 + c + HID) * N);
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int y = i / W4, x0 = 4 * (i - y * W4);
+    float vd[3][6], vi[3][6], r[4];
+    window4(d1, PW, y, x0, vd);
+    conv9x4_flipped(vd, k1, r);
+    o1[i] = make_float4(r[0], r[1], r[2], r[3]);
+    window4(s1, PW, y, x0, vi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gq = vd[1][j + 1];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) dkk[ky * 3 + kx] = fmaf(gq, vi[ky][j + kx], dkk[ky * 3 + kx]);
+    }
+    window4(d2, PW, y, x0, vd);
+    conv9x4_flipped(vd, k2, r);
+    o2[i] = make_float4(r[0], r[1], r[2], r[3]);
+    window4(s2, PW, y, x0, vi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gq = vd[1][j + 1];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) dkk[9 + ky * 3 + kx] = fmaf(gq, vi[ky][j + kx], dkk[9 + ky * 3 + kx]);
+    }
+  }
+  const float tot = block_sums<18>(dkk, red18);
+  if (threadIdx.x < 9) dw_part[((size_t)b * HID2 + c) * 9 + threadIdx.x] = tot;
+  else if (threadIdx.x < 18) dw_part[((size_t)b * HID2 + c + HID) * 9 + threadIdx.x - 9] = tot;
+}
+
 // ------------------------------------------------------------------ MDTA channel attention, per (sample, head)
 // forward: attn = softmax_d( G[c][d] / (|q_c| |k_d|) * temperature )   (PromptInteract.py:421-425), then folds
 // it into project_out:  M[b][o][h*64+d] = sum_c Wo[o][h*64+c] attn[c][d], so that  z = M[b] v.
+// Grid (B * HEADS, 4): every CTA redoes the (tiny) softmax, CTA y folds it into output rows o in [32 y, 32 y + 32);
+// one thread = one column d x eight rows o, weights read as warp-uniform 128-bit loads (r1: one CTA per (sample, head)
+// with a 64-deep dependent global-load loop per output took 43 us on 32 SMs).
 __global__ void __launch_bounds__(256)
 mdta_attn_fwd_kernel(const float* __restrict__ G, const float* __restrict__ sq, const float* __restrict__ sk,
                      const float* __restrict__ temperature, const float* __restrict__ wo, float* __restrict__ attn,
@@ -624,16 +853,27 @@ mdta_attn_fwd_kernel(const float* __restrict__ G, const float* __restrict__ sq, 
     s1 /= l;
     sa[c][lane] = s0;
     sa[c][lane + 32] = s1;
-    attn[(size_t)bh * HD * HD + c * HD + lane] = s0;
-    attn[(size_t)bh * HD * HD + c * HD + lane + 32] = s1;
+    if (blockIdx.y == 0) {
+      attn[(size_t)bh * HD * HD + c * HD + lane] = s0;
+      attn[(size_t)bh * HD * HD + c * HD + lane + 32] = s1;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < DIM * HD; i += 256) {
-    const int o = i / HD, d = i % HD;
-    float acc = 0.f;
-    for (int c = 0; c < HD; ++c) acc = fmaf(__ldg(wo + (size_t)o * DIM + h * HD + c), sa[c][d], acc);
-    M[(size_t)b * DIM * DIM + (size_t)o * DIM + h * HD + d] = acc;
+  const int d = threadIdx.x & 63, o0 = 32 * blockIdx.y + 8 * (threadIdx.x >> 6);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 2
+  for (int c = 0; c < HD; c += 4) {
+    const float a0 = sa[c][d], a1 = sa[c + 1][d], a2 = sa[c + 2][d], a3 = sa[c + 3][d];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wo + (size_t)(o0 + k) * DIM + h * HD + c));
+      acc[k] = fmaf(w4.x, a0, fmaf(w4.y, a1, fmaf(w4.z, a2, fmaf(w4.w, a3, acc[k]))));
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) M[(size_t)b * DIM * DIM + (size_t)(o0 + k) * DIM + h * HD + d] = acc[k];
 }
 
 // backward: P[b][o][j] = sum_n dz[b][o][n] v[b][j][n]  (dz = gradient at project_out's output)
@@ -658,20 +898,73 @@ mdta_attn_bwd_kernel(const float* __restrict__ P, const float* __restrict__ attn
   else if (threadIdx.x < 2 * HD) snk[threadIdx.x - HD] = fmaxf(sqrtf(__ldg(sk + (size_t)b * DIM + h * HD + threadIdx.x - HD)), NORM_EPS);
   __syncthreads();
   auto sS = [&](int c, int d) { return __ldg(Gb + c * HD + d) / (snq[c] * snk[d]); };   // S / tau
-  for (int i = threadIdx.x; i < HD * HD; i += 256) {
-    const int c = i / HD, d = i % HD;
-    sa[c][d] = __ldg(attn + (size_t)bh * HD * HD + i);
-    float acc = 0.f;
-    for (int o = 0; o < DIM; ++o) acc = fmaf(__ldg(wo + (size_t)o * DIM + h * HD + c), __ldg(p + (size_t)o * DIM + h * HD + d), acc);
-    sd[c][d] = acc;
+  {
+    float4 t[4];                                         // all loads in flight before the first use
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(attn + (size_t)bh * HD * HD) + threadIdx.x + 256 * j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = 4 * (threadIdx.x + 256 * j), c = i / HD, d = i % HD;
+      sa[c][d] = t[j].x; sa[c][d + 1] = t[j].y; sa[c][d + 2] = t[j].z; sa[c][d + 3] = t[j].w;
+    }
+  }
+  if (blockIdx.y > 0) {
+    // CTAs 1..4: the project_out weight-gradient partial for output rows o in [32 (y - 1), 32 y): one thread = one
+    // column c x eight rows o, P read as warp-uniform 128-bit loads
+    __syncthreads();
+    const int c = threadIdx.x & 63, o0 = 32 * (blockIdx.y - 1) + 8 * (threadIdx.x >> 6);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 2
+    for (int d = 0; d < HD; d += 4) {
+      const float a0 = sa[c][d], a1 = sa[c][d + 1], a2 = sa[c][d + 2], a3 = sa[c][d + 3];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(o0 + k) * DIM + h * HD + d));
+        acc[k] = fmaf(p4.x, a0, fmaf(p4.y, a1, fmaf(p4.z, a2, fmaf(p4.w, a3, acc[k]))));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dwo_part[(size_t)b * DIM * DIM + (size_t)(o0 + k) * DIM + h * HD + c] = acc[k];
+    return;
+  }
+  {
+    // CTA 0: dattn[c][d] = sum_o Wo[o][h64+c] P[o][h64+d]: one thread = one column d x sixteen rows c.  The two
+    // [128][64] operand slices are staged in shared memory with every load in flight at once (a 128-deep loop of
+    // dependent L2 round trips was 40 % of this kernel's 84 us)
+    extern __shared__ __align__(16) float dyn[];
+    float4* swo4 = reinterpret_cast<float4*>(dyn);
+    float4* sp4 = swo4 + DIM * HD / 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = threadIdx.x + 256 * j, o = i >> 4, q = i & 15;
+      swo4[i] = __ldg(reinterpret_cast<const float4*>(wo + (size_t)o * DIM + h * HD) + q);
+      sp4[i] = __ldg(reinterpret_cast<const float4*>(p + (size_t)o * DIM + h * HD) + q);
+    }
+    __syncthreads();
+    const float* sp = reinterpret_cast<const float*>(sp4);
+    const int d = threadIdx.x & 63, c0 = 16 * (threadIdx.x >> 6);
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+#pragma unroll 4
+    for (int o = 0; o < DIM; ++o) {
+      const float pv = sp[o * HD + d];
+      const float4* w4 = swo4 + (o * HD + c0) / 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = w4[q];
+        acc[4 * q] = fmaf(w.x, pv, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(w.y, pv, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w.z, pv, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(w.w, pv, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sd[c0 + k][d] = acc[k];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < DIM * HD; i += 256) {
-    const int o = i / HD, c = i % HD;
-    float acc = 0.f;
-    for (int d = 0; d < HD; ++d) acc = fmaf(__ldg(p + (size_t)o * DIM + h * HD + d), sa[c][d], acc);
-    dwo_part[(size_t)b * DIM * DIM + (size_t)o * DIM + h * HD + c] = acc;
-  }
   // softmax backward, one warp per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = warp; c < HD; c += 8) {
@@ -780,7 +1073,8 @@ int launch_ln_stats(const float* x, float* mean, float* rstd, int B, int C, int 
   EMIP_CHECK_LAUNCH("ln_stats");
   return EMIP_OK;
 }
-size_t plane_smem(int H, int W, int planes) { return sizeof(float) * (size_t)planes * (H + 2) * (W + 2); }
+// W % 4 == 0 selects the 4-wide plane kernels (pitch W + 8), anything else the scalar ones (pitch W + 2)
+size_t plane_smem(int H, int W, int planes) { return sizeof(float) * (size_t)planes * (H + 2) * (W + ((W & 3) ? 2 : 8)); }
 
 template <typename K>
 int ensure_smem(K kernel, size_t bytes) {
@@ -1011,11 +1305,14 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   a.gamma = params[P_N2W]; a.beta = params[P_N2B]; a.y = s.kvpre; a.y_stride_b = (long long)2 * DIM * N;
   if ((rc = gemm_nn(a, st))) return rc;
   const size_t sm1 = plane_smem(H, W, 1);
-  if ((rc = ensure_smem(dwconv_fwd_kernel, sm1))) return rc;
-  dwconv_fwd_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
+  const bool v4 = (W & 3) == 0;
+  if ((rc = v4 ? ensure_smem(dwconv_fwd_v4_kernel, sm1) : ensure_smem(dwconv_fwd_kernel, sm1))) return rc;
+  if (v4) dwconv_fwd_v4_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
+  else dwconv_fwd_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
   EMIP_CHECK_LAUNCH("dwconv q");
   // k = channels [0,128), v = [128,256) of kv (:415); only k is L2-normalised
-  dwconv_fwd_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
+  if (v4) dwconv_fwd_v4_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
+  else dwconv_fwd_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
   EMIP_CHECK_LAUNCH("dwconv kv");
   // G[c][d] = sum_n q[c][n] k[d][n] per (sample, head)      (:421-424, normalisation folded in afterwards)
   {
@@ -1033,7 +1330,7 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   }
   // |k_d|^2 over the pixels (F.normalize, :422); |q_c|^2 came out of the q depthwise kernel
   if ((rc = launch_row_sumsq(s.k, s.sk, B * DIM, N, st))) return rc;
-  mdta_attn_fwd_kernel<<<B * HEADS, 256, 0, st>>>(s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], s.attn, s.M);
+  mdta_attn_fwd_kernel<<<dim3(B * HEADS, 4), 256, 0, st>>>(s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], s.attn, s.M);
   EMIP_CHECK_LAUNCH("mdta_attn_fwd");
   // y = x + project_out(attn @ v) = x + M[b] v             (:427-431, :447)
   a = {};
@@ -1051,8 +1348,9 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   a.y = s.tpre; a.y_stride_b = (long long)HID2 * N; a.ldy = N;
   if ((rc = gemm_nn(a, st))) return rc;
   const size_t sm2 = plane_smem(H, W, 2);
-  if ((rc = ensure_smem(gdfn_gate_fwd_kernel, sm2))) return rc;
-  gdfn_gate_fwd_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
+  if ((rc = v4 ? ensure_smem(gdfn_gate_fwd_v4_kernel, sm2) : ensure_smem(gdfn_gate_fwd_kernel, sm2))) return rc;
+  if (v4) gdfn_gate_fwd_v4_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
+  else gdfn_gate_fwd_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
   EMIP_CHECK_LAUNCH("gdfn_gate_fwd");
   a = {};
   a.B = B; a.M = DIM; a.K = HID; a.N = N; a.w = params[P_FOW]; a.ldw = HID;
@@ -1127,8 +1425,10 @@ extern "C" int emip_injector_bwd_ex(const float* x, const float* x1, const float
   a.x = dout; a.x_stride_b = sN; a.ldx = N; a.y = dg; a.y_stride_b = (long long)HID * N; a.ldy = N;
   if ((rc = gemm_nn(a, st))) return rc;
   const size_t sm4 = plane_smem(H, W, 4);
-  if ((rc = ensure_smem(gdfn_gate_bwd_kernel, sm4))) return rc;
-  gdfn_gate_bwd_kernel<<<dim3(HID, B), 256, sm4, st>>>(s.tpre, params[P_FDW], dg, dtpre, g, dwc_part, H, W);
+  const bool v4 = (W & 3) == 0;
+  if ((rc = v4 ? ensure_smem(gdfn_gate_bwd_v4_kernel, sm4) : ensure_smem(gdfn_gate_bwd_kernel, sm4))) return rc;
+  if (v4) gdfn_gate_bwd_v4_kernel<<<dim3(HID, B), 256, sm4, st>>>(s.tpre, params[P_FDW], dg, dtpre, g, dwc_part, H, W);
+  else gdfn_gate_bwd_kernel<<<dim3(HID, B), 256, sm4, st>>>(s.tpre, params[P_FDW], dg, dtpre, g, dwc_part, H, W);
   EMIP_CHECK_LAUNCH("gdfn_gate_bwd");
   if ((rc = reduce_batch(dwc_part, HID2 * 9, dparams[P_FDW], B, HID2 * 9, 0, st))) return rc;
   GemmNT t = {};
@@ -1167,7 +1467,8 @@ extern "C" int emip_injector_bwd_ex(const float* x, const float* x1, const float
   if ((rc = gemm_nt_split(t, ns, st))) return rc;
   sum_splits_kernel<<<(B * DIM * DIM + 255) / 256, 256, 0, st>>>(wpart, Pm, B, ns, DIM * DIM);
   EMIP_CHECK_LAUNCH("sum_splits P");
-  mdta_attn_bwd_kernel<<<B * HEADS, 256, 0, st>>>(Pm, s.attn, s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], dGs, aq, ak,
+  if ((rc = ensure_smem(mdta_attn_bwd_kernel, (size_t)2 * DIM * HD * sizeof(float)))) return rc;
+  mdta_attn_bwd_kernel<<<dim3(B * HEADS, 5), 256, 2 * DIM * HD * sizeof(float), st>>>(Pm, s.attn, s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], dGs, aq, ak,
                                                    dtau_part, dwo_part);
   EMIP_CHECK_LAUNCH("mdta_attn_bwd");
   if ((rc = reduce_batch(dwo_part, DIM * DIM, dparams[P_POW], B, DIM * DIM, 0, st))) return rc;
@@ -1188,11 +1489,13 @@ extern "C" int emip_injector_bwd_ex(const float* x, const float* x1, const float
   EMIP_CHECK_LAUNCH("row_axpy");
   // depthwise backward
   const size_t sm2 = plane_smem(H, W, 2);
-  if ((rc = ensure_smem(dwconv_bwd_kernel, sm2))) return rc;
-  dwconv_bwd_kernel<<<dim3(DIM, B), 256, sm2, st>>>(s.qpre, params[P_QDW], dq, nullptr, dqpre, dwc_part, DIM, DIM, H, W);
+  if ((rc = v4 ? ensure_smem(dwconv_bwd_v4_kernel, sm2) : ensure_smem(dwconv_bwd_kernel, sm2))) return rc;
+  if (v4) dwconv_bwd_v4_kernel<<<dim3(DIM, B), 256, sm2, st>>>(s.qpre, params[P_QDW], dq, nullptr, dqpre, dwc_part, DIM, DIM, H, W);
+  else dwconv_bwd_kernel<<<dim3(DIM, B), 256, sm2, st>>>(s.qpre, params[P_QDW], dq, nullptr, dqpre, dwc_part, DIM, DIM, H, W);
   EMIP_CHECK_LAUNCH("dwconv_bwd q");
   if ((rc = reduce_batch(dwc_part, DIM * 9, dparams[P_QDW], B, DIM * 9, 0, st))) return rc;
-  dwconv_bwd_kernel<<<dim3(2 * DIM, B), 256, sm2, st>>>(s.kvpre, params[P_KVDW], dk, dv, dkvpre, dwc_part, 2 * DIM, DIM, H, W);
+  if (v4) dwconv_bwd_v4_kernel<<<dim3(2 * DIM, B), 256, sm2, st>>>(s.kvpre, params[P_KVDW], dk, dv, dkvpre, dwc_part, 2 * DIM, DIM, H, W);
+  else dwconv_bwd_kernel<<<dim3(2 * DIM, B), 256, sm2, st>>>(s.kvpre, params[P_KVDW], dk, dv, dkvpre, dwc_part, 2 * DIM, DIM, H, W);
   EMIP_CHECK_LAUNCH("dwconv_bwd kv");
   if ((rc = reduce_batch(dwc_part, 2 * DIM * 9, dparams[P_KVDW], B, 2 * DIM * 9, 0, st))) return rc;
   // 1x1 convs + LayerNorms

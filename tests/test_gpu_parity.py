@@ -577,3 +577,23 @@ def test_f2_attention_empty_and_minimum():
     q, k, v = (cases.randn(170 + i, (2, 6, 128)) for i in range(3))     # a handful of tokens: one partial tile
     ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / 128 ** 0.5, -1) @ v.double()
     assert rel(attention(dev(q), dev(k), dev(v)), ref) < TOL_EXACT
+
+
+def test_a4_injector_odd_width_vs_oracle():
+    """W % 4 != 0 takes the scalar depthwise / gate kernels (W % 4 == 0, every model size, takes the 4-wide ones):
+    forward and all gradients against the CPU oracle."""
+    from emip_b200.injector import Injector
+    d = cases.a4_inputs(dict(b=2, h=9, w=10, xs=2.2, x1s=1.0, seed=49))
+    m = Injector().cuda()
+    m.transformer.load_state_dict(d["params"])
+    x, x1 = d["x"].clone().requires_grad_(True), d["x1"].clone().requires_grad_(True)
+    prm = {k: v.clone().requires_grad_(True) for k, v in d["params"].items()}
+    ref = O.injector(x, x1, prm)
+    (ref * d["wout"]).sum().backward()
+    gx, gx1 = dev(d["x"]).requires_grad_(True), dev(d["x1"]).requires_grad_(True)
+    out = m(gx, gx1)
+    (out * dev(d["wout"])).sum().backward()
+    assert rel(out, ref) < 2e-5
+    assert rel(gx.grad, x.grad) < 3e-4 and rel(gx1.grad, x1.grad) < 3e-4
+    for k, p in m.transformer.named_parameters():
+        assert rel(p.grad, prm[k].grad) < 3e-4, k
