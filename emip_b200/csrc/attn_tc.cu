@@ -431,6 +431,7 @@ attn_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ p
 static unsigned long long* g_attn_prof = nullptr;
 // Diagnostics: device buffer of gridDim.x * 16 counters filled by the next launches (NULL switches it off).
 extern "C" void emip_attn_tc_set_profile_buffer(unsigned long long* dev_buf) { g_attn_prof = dev_buf; }
+unsigned long long* attn_tc_profile_buffer() { return g_attn_prof; }
 
 bool attn_tc_supported(int nq, int nk, int c) { return c == 128 && nq >= 1 && nk >= 1; }
 

@@ -29,6 +29,8 @@ struct AttnTcArgs {
 };
 
 bool attn_tc_supported(int nq, int nk, int c);
+// diagnostics: the buffer set through emip_attn_tc_set_profile_buffer (NULL = off); shared with attn_bwd_tc.cu
+unsigned long long* attn_tc_profile_buffer();
 int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st);
 // out / lse from the ksplit partials of attn_tc_fwd
 int attn_tc_merge(const AttnTcArgs& a, cudaStream_t st);

@@ -37,6 +37,7 @@ class _MemoryRead(torch.autograd.Function):
                                                  stream_ptr()), "emip_memory_read_fwd_tc")
         ctx.save_for_backward(m_in, m_out, q_in, out, lse)
         ctx.q_out_shape = q_out.shape
+        ctx.exact_fp32 = bool(exact_fp32 or M < 16)
         return out
 
     @staticmethod
@@ -47,12 +48,20 @@ class _MemoryRead(torch.autograd.Function):
         M, Q = T * H * W, H * W
         dout = dout.contiguous()
         L = _lib.lib()
-        L.emip_memory_read_workspace.restype = ctypes.c_size_t
-        ws, ws_ptr, ws_n = workspace(L.emip_memory_read_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device, align=256)
         dm_in, dm_out, dq_in = torch.empty_like(m_in), torch.empty_like(m_out), torch.empty_like(q_in)
-        _lib.check(L.emip_memory_read_bwd(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse), ptr(dout),
-                                          LL(2 * Do * Q), ptr(dm_in), ptr(dm_out), ptr(dq_in), ctypes.c_void_p(ws_ptr),
-                                          SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()), "emip_memory_read_bwd")
+        if ctx.exact_fp32:
+            L.emip_memory_read_workspace.restype = ctypes.c_size_t
+            ws, ws_ptr, ws_n = workspace(L.emip_memory_read_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device, align=256)
+            _lib.check(L.emip_memory_read_bwd(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse), ptr(dout),
+                                              LL(2 * Do * Q), ptr(dm_in), ptr(dm_out), ptr(dq_in), ctypes.c_void_p(ws_ptr),
+                                              SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()), "emip_memory_read_bwd")
+        else:                                                         # tensor-core path (csrc/attn_bwd_tc.cu)
+            L.emip_memory_read_bwd_tc_workspace.restype = ctypes.c_size_t
+            ws, ws_ptr, ws_n = workspace(L.emip_memory_read_bwd_tc_workspace(I(B), I(De), I(Do), I(M), I(Q)), m_in.device)
+            _lib.check(L.emip_memory_read_bwd_tc(ptr(m_in), ptr(m_out), ptr(q_in), ptr(out), LL(2 * Do * Q), ptr(lse), ptr(dout),
+                                                 LL(2 * Do * Q), ptr(dm_in), ptr(dm_out), ptr(dq_in), ctypes.c_void_p(ws_ptr),
+                                                 SZ(ws_n), I(B), I(De), I(Do), I(M), I(Q), stream_ptr()),
+                       "emip_memory_read_bwd_tc")
         return dm_in, dm_out, dq_in, dout[:, Do:].reshape(ctx.q_out_shape), None
 
 
@@ -65,7 +74,7 @@ class Memory(nn.Module):
     is not produced.
     """
 
-    #: True selects the exact-fp32 CUDA-core forward instead of the tcgen05 one (bf16 hi/lo split, fp32 accumulation)
+    #: True selects the exact-fp32 CUDA-core forward / backward instead of the tcgen05 ones (bf16 hi/lo split, fp32 accumulation)
     exact_fp32 = False
 
     def forward(self, m_in, m_out, q_in, q_out):

@@ -12,7 +12,8 @@ separates rectangular blocks of tokens -- in un-rolled coordinates the cuts are 
 -- and ``exp(-100)`` relative weight is below fp32 resolution, so a shifted layer is computed as plain attention inside
 each block: no roll, no mask tensor, no masked score entries.
 The GMFlow weights are frozen in training (train.py:340-342) but gradients still flow through this attention to the
-prompt-fusion outputs; the backward re-derives them with library matmuls (plumbing for now).
+prompt-fusion outputs: the backward (dq, dk, dv) runs on the tensor cores too (``emip_attention_bwd_tc``,
+csrc/attn_bwd_tc.cu), per block group.
 """
 import ctypes
 
@@ -40,12 +41,19 @@ class _Attention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v = ctx.saved_tensors
-        scale = q.shape[-1] ** -0.5
-        p = torch.softmax(torch.matmul(q, k.transpose(1, 2)) * scale, dim=-1)
-        dv = torch.matmul(p.transpose(1, 2), dout)
-        dp = torch.matmul(dout, v.transpose(1, 2))
-        ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
-        return torch.matmul(ds, k), torch.matmul(ds.transpose(1, 2), q), dv
+        return _attention_bwd(q, k, v, dout.contiguous())
+
+
+def _attention_bwd(q, k, v, dout):
+    """dq, dk, dv on the tensor cores (csrc/attn_bwd_tc.cu); the call re-runs the fused forward for O and the lse."""
+    nb, n, c = q.shape
+    L = _lib.lib()
+    L.emip_attention_bwd_tc_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_attention_bwd_tc_workspace(I(nb), I(n), I(c)), q.device)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    _lib.check(L.emip_attention_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ctypes.c_void_p(ws_ptr),
+                                       SZ(ws_n), I(nb), I(n), I(c), stream_ptr()), "emip_attention_bwd_tc")
+    return dq, dk, dv
 
 
 def attention(q, k, v):
@@ -114,11 +122,10 @@ class _WindowAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        # plumbing: the same block decomposition with library matmuls
+        # the same block decomposition; the gathers / scatters are torch copies, the gradients run on the tensor cores
         q, k, v = ctx.saved_tensors
         num_splits, with_shift, h, w = ctx.geom
         b, _, c = q.shape
-        scale = c ** -0.5
         q4, k4, v4, d4 = (t.reshape(b, h, w, c) for t in (q, k, v, dout))
         dq, dk, dv = (torch.empty_like(q4) for _ in range(3))
         for (bh, bw), origins in _block_groups(h, w, num_splits, with_shift).items():
@@ -126,11 +133,7 @@ class _WindowAttention(torch.autograd.Function):
 
             def gather(t):
                 return torch.stack([t[:, r0:r0 + bh, c0:c0 + bw] for (r0, c0) in origins], 0).reshape(len(origins) * b, n, c)
-            qg, kg, vg, dg = gather(q4), gather(k4), gather(v4), gather(d4)
-            p = torch.softmax(torch.matmul(qg, kg.transpose(1, 2)) * scale, dim=-1)
-            dp = torch.matmul(dg, vg.transpose(1, 2))
-            ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
-            parts = (torch.matmul(ds, kg), torch.matmul(ds.transpose(1, 2), qg), torch.matmul(p.transpose(1, 2), dg))
+            parts = _attention_bwd(gather(q4), gather(k4), gather(v4), gather(d4))
             for dst, src in zip((dq, dk, dv), parts):
                 src = src.view(len(origins), b, bh, bw, c)
                 for i, (r0, c0) in enumerate(origins):

@@ -164,6 +164,15 @@ size_t emip_memory_read_tc_workspace(int B, int De, int Do, int M, int Q);
 int emip_memory_read_fwd_tc(const float* m_in, const float* m_out, const float* q_in, float* mem, long long mem_stride_b,
                             float* lse, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
 
+/* a5 backward on the tensor cores (csrc/attn_bwd_tc.cu: one kernel, three launches -- dq_in with rows = queries,
+ * dm_in and dm_out with rows = memory slots and the score tile recomputed transposed; 3-term split-bf16 operands, fp32
+ * accumulation).  Same arguments and results as emip_memory_read_bwd; workspace of
+ * emip_memory_read_bwd_tc_workspace() bytes, 1024-byte aligned. */
+size_t emip_memory_read_bwd_tc_workspace(int B, int De, int Do, int M, int Q);
+int emip_memory_read_bwd_tc(const float* m_in, const float* m_out, const float* q_in, const float* mem, long long mem_stride_b,
+                            const float* lse, const float* dmem, long long dmem_stride_b, float* dm_in, float* dm_out,
+                            float* dq_in, void* workspace, size_t ws_bytes, int B, int De, int Do, int M, int Q, void* stream);
+
 /* ---- f4: convex x8 upsampling of the coarse flow -------------------------------- */
 /* Replaces model/EMIP_short/motion/gmflow/gmflow.py:64-77, the part of GMFlow.upsample_flow after
  * `mask = self.upsampler(concat)`: softmax over the 9 taps, 3x3 unfold of k*flow, weighted sum, pixel shuffle.
@@ -216,10 +225,16 @@ int emip_photometric_bwd(const float* im, const float* rec, const float* mask, c
 /* Replaces model/EMIP_short/motion/gmflow/transformer.py:8-16 single_head_full_attention and the per-window attention
  * of :46-105 single_head_split_window_attention: out = softmax(q k^T / sqrt(C)) v for nb independent problems of n
  * tokens (the shifted-window mask is handled by the host side: it only separates rectangular token blocks, each of
- * which is a plain attention problem).  q, k, v, out token-major [nb][n][C], C = 128.  Forward only. */
+ * which is a plain attention problem).  q, k, v, out token-major [nb][n][C], C = 128. */
 size_t emip_attention_tc_workspace(int nb, int n, int C);
 int emip_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace, size_t ws_bytes,
                           int nb, int n, int C, void* stream);
+
+/* Backward of emip_attention_fwd_tc on the tensor cores: dq, dk, dv [nb][n][C] from q, k, v and dout (self-contained: the
+ * fused forward is re-run inside for the output and the row log-sum-exp, nothing has to be saved). */
+size_t emip_attention_bwd_tc_workspace(int nb, int n, int C);
+int emip_attention_bwd_tc(const float* q, const float* k, const float* v, const float* dout, float* dq, float* dk, float* dv,
+                          void* workspace, size_t ws_bytes, int nb, int n, int C, void* stream);
 
 /* One call per FeatureTransformer attention layer (csrc/window_attn.cu): q, k, v, out [B][h*w][C] as the reference's
  * single_head_split_window_attention(q, k, v, num_splits, with_shift, h, w, attn_mask) takes and returns them.  The

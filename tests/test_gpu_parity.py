@@ -597,3 +597,33 @@ def test_a4_injector_odd_width_vs_oracle():
     assert rel(gx.grad, x.grad) < 3e-4 and rel(gx1.grad, x1.grad) < 3e-4
     for k, p in m.transformer.named_parameters():
         assert rel(p.grad, prm[k].grad) < 3e-4, k
+
+
+@pytest.mark.parametrize("nb,n,scale", [(2, 100, 1.0), (3, 300, 1.5), (2, 700, 1.0), (5, 16, 2.0)])
+def test_f2_attention_backward_tc_vs_fp64(nb, n, scale):
+    """dq, dk, dv of the tensor-core backward (attn_bwd_tc.cu: three launches of one kernel) against fp64 autograd,
+    incl. partial row / column tiles and several column tiles per row tile."""
+    from emip_b200.window_attn import attention
+    q, k, v, w = (cases.randn(180 + i, (nb, n, 128), scale if i < 2 else 1.0) for i in range(4))
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    (torch.softmax(qd @ kd.transpose(1, 2) / 128 ** 0.5, -1) @ vd).backward(w.double())
+    qq, kk, vv = (dev(t).requires_grad_(True) for t in (q, k, v))
+    attention(qq, kk, vv).backward(dev(w))
+    for name, a, b in (("dq", qq.grad, qd.grad), ("dk", kk.grad, kd.grad), ("dv", vv.grad, vd.grad)):
+        assert rel(a, b) < 1e-4, (name, rel(a, b))
+
+
+def test_a5_memory_read_backward_tc_vs_exact():
+    """a5 backward on the tensor cores (key-split row launch, CN layouts, strided dmem) against the exact-fp32 kernels."""
+    from emip_b200.memory import Memory
+    d = cases.a5_inputs(dict(b=2, t=3, h=20, w=24, scale=1.5, seed=59))
+    grads = {}
+    for exact in (True, False):
+        t = {k: dev(d[k]).requires_grad_(True) for k in ("m_in", "m_out", "q_in", "q_out")}
+        m = Memory()
+        m.exact_fp32 = exact
+        out, _ = m(t["m_in"], t["m_out"], t["q_in"], t["q_out"])
+        (out * dev(d["wout"])).sum().backward()
+        grads[exact] = {k: v.grad.clone() for k, v in t.items()}
+    for k in ("m_in", "m_out", "q_in", "q_out"):
+        assert rel(grads[False][k], grads[True][k]) < 1e-4, (k, rel(grads[False][k], grads[True][k]))
