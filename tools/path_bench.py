@@ -276,7 +276,7 @@ def main():
     M = 5 * N
     fl = 2.0 * M * N * 256
     add("a5 EMIP_long memory read, B=1 T=5 (9680 slots)", 1, "frames", ms_f, ms_fb - ms_f, fl, 2.5 * fl, (2 * M + 3 * N) * 128 * 4,
-        (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "forward on tcgen05 (lse pass + e^(S-L) V pass, split-bf16), backward exact fp32 CUDA cores")
+        (4 * M + 4 * N) * 128 * 4, "tensor", cf, cb, "forward: one fused flash-style tcgen05 kernel; backward: three launches of the tcgen05 gradient kernel (dQ; dK; dV); split-bf16, fp32 accumulate")
 
     # ---------------- f1: conv_corr[0] on the never-materialised cost volume, B = 16 ----------------
     from emip_b200.conv_corr import conv_corr_first_layer
@@ -351,6 +351,7 @@ def main():
     from emip_b200.window_attn import single_head_split_window_attention
     qw, kw, vw = (2.0 * torch.randn(32, N, C, device=dev, generator=g) for _ in range(3))
     amask = O.shift_window_attn_mask(H, W, 22, 22, 11, 11).to(dev)
+    wf2 = torch.randn(32, N, C, device=dev, generator=g)
     res2 = {}
     for shift in (False, True):
         def f2_fwd():
@@ -360,16 +361,21 @@ def main():
         def f2_torch():                                   # the reference's op sequence on the same GPU (library kernels)
             with torch.no_grad():
                 return O.split_window_attention(qw, kw, vw, 2, shift, H, W)
-        res2[shift] = (gpu_time(f2_fwd, iters=10), gpu_time(f2_torch, iters=5, warm=2))
+        def f2_fwd_bwd():
+            a, b, c = (t.detach().requires_grad_(True) for t in (qw, kw, vw))
+            single_head_split_window_attention(a, b, c, 2, shift, H, W, amask if shift else None).backward(wf2)
+        res2[shift] = (gpu_time(f2_fwd, iters=10), gpu_time(f2_torch, iters=5, warm=2), gpu_time(f2_fwd_bwd, iters=5))
     cf = None
     if not args.no_cpu:
         cq, ck, cv = qw[:4].cpu(), kw[:4].cpu(), vw[:4].cpu()
         cf = cpu_time(lambda: O.split_window_attention(cq, ck, cv, 2, True, H, W)) * 8
     fl = 32 * 4 * 2.0 * 484 * 484 * (C + C)
-    add("f2 split-window attention (one shifted layer), 2B=32, 4 windows of 484 tokens", 16, "pairs", res2[True][0], None, fl, 0,
+    add("f2 split-window attention (one shifted layer), 2B=32", 16, "pairs", res2[True][0], res2[True][2] - res2[True][0], fl, 2.5 * fl,
         32 * 4 * N * C * 4, 0, "tensor", cf, None,
-        f"unshifted layer {res2[False][0]:.3f} ms; the same formula as eager torch ops on this GPU: shifted {res2[True][1]:.3f} ms, "
-        f"unshifted {res2[False][1]:.3f} ms; 12 such layers per pair of feature maps; CPU sample = 4 x 8")
+        f"one C-ABI call per layer (fused flash kernel, window gather / scatter inside); unshifted layer {res2[False][0]:.3f} ms fwd, "
+        f"{res2[False][2] - res2[False][0]:.3f} ms bwd; backward = tcgen05 gradient kernel per block group (+ torch gather / scatter "
+        f"copies); the same formula as eager torch ops on this GPU: shifted {res2[True][1]:.3f} ms, unshifted {res2[False][1]:.3f} ms "
+        f"forward; 12 such layers per pair of feature maps; CPU sample = 4 x 8")
 
     # ---------------- f3b: photometric loss term (L1 + SSIM 3x3, masked), B = 64 ----------------
     from emip_b200.photometric import photometric_loss
