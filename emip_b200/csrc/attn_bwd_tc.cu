@@ -373,7 +373,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         float* OUT = ns == 1 ? p.out + (size_t)prob * p.out_stride_b : p.part + ((size_t)ks * p.nb + prob) * p.nr * 128;
         if (row_ok) {
           if (p.out_layout == EMIP_LAYOUT_NC) {
-            float4* dst = reinterpret_cast<float4*>(OUT + (size_t)row * 128 + cb);
+            size_t orow = (size_t)row;
+            if (p.win.enabled) {                          // scatter: token `row` of block (prob / B) of image (prob % B)
+              const int blk = prob / p.win.B, img = prob - blk * p.win.B;
+              const int bw = p.win.bw[blk];
+              const int ty = row / bw, tx = row - ty * bw;
+              OUT = p.out;
+              orow = ((size_t)img * p.win.h + p.win.r0[blk] + ty) * p.win.w + p.win.c0[blk] + tx;
+            }
+            float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               dst[q] = make_float4(__uint_as_float(r[4 * q]) * sc, __uint_as_float(r[4 * q + 1]) * sc,
@@ -421,6 +429,20 @@ dsum_nc_kernel(const float* __restrict__ d_o, long long do_stride_b, const float
   const float s = warp_sum(a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w);
   if (lane == 0) dsum[(size_t)b * n + r] = s;
 }
+__global__ void __launch_bounds__(256)
+dsum_split_kernel(const __nv_bfloat16* __restrict__ dos, const float* __restrict__ o, float* __restrict__ dsum, long long rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(dos + r * 256) + lane), l = __ldg(reinterpret_cast<const uint2*>(dos + r * 256 + 128) + lane);
+  const float4 c = __ldg(reinterpret_cast<const float4*>(o + r * 128) + lane);
+  const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+  const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
+  const float a0 = __low2float(h0) + __low2float(l0), a1 = __high2float(h0) + __high2float(l0);
+  const float a2 = __low2float(h1) + __low2float(l1), a3 = __high2float(h1) + __high2float(l1);
+  const float s = warp_sum(a0 * c.x + a1 * c.y + a2 * c.z + a3 * c.w);
+  if (lane == 0) dsum[r] = s;
+}
 __global__ void __launch_bounds__(128)
 dsum_cn_kernel(const float* __restrict__ d_o, long long do_stride_b, const float* __restrict__ o, long long o_stride_b,
                float* __restrict__ dsum, int n) {
@@ -441,6 +463,7 @@ int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st) {
   if (a.nc < 1 || a.mode < 0 || a.mode > 2) { emip_set_error("attn_bwd_tc: bad arguments"); return EMIP_EINVAL; }
   const int nkt = (a.nc + TN - 1) / TN;
   if (a.ksplit > nkt) { emip_set_error("attn_bwd_tc: ksplit %d exceeds the %d column tiles", a.ksplit, nkt); return EMIP_EINVAL; }
+  if (a.win.enabled && (a.ksplit > 1 || a.out_layout != EMIP_LAYOUT_NC)) { emip_set_error("attn_bwd_tc: the window scatter needs ksplit == 1 and the NC layout"); return EMIP_EINVAL; }
   if (a.ksplit > 1 && a.part == nullptr) { emip_set_error("attn_bwd_tc: ksplit needs the partial buffer"); return EMIP_EINVAL; }
   CUtensorMap mx, my, mg, mz;
   int rc;
@@ -472,6 +495,14 @@ int attn_bwd_tc_sum(const AttnBwdTcArgs& a, cudaStream_t st) {
   if (a.nb == 0 || a.nr == 0 || a.ksplit <= 1) return EMIP_OK;
   sum_parts_kernel<<<dim3(128, a.nb), 256, 0, st>>>(a.part, a.out, a.out_stride_b, a.ksplit, a.nb, (size_t)a.nr * 128);
   EMIP_CHECK_LAUNCH("attn_bwd_tc_sum");
+  return EMIP_OK;
+}
+
+int attn_dsum_split(const void* do_split, const float* o, float* dsum, int nb, int n, cudaStream_t st) {
+  const long long rows = (long long)nb * n;
+  if (rows == 0) return EMIP_OK;
+  dsum_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(do_split), o, dsum, rows);
+  EMIP_CHECK_LAUNCH("attn_dsum_split");
   return EMIP_OK;
 }
 

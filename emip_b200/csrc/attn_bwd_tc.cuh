@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include "attn_tc.cuh"
 
 enum { ATTN_BWD_ROW = 0, ATTN_BWD_COL = 1, ATTN_BWD_PV = 2 };
 
@@ -23,10 +24,13 @@ struct AttnBwdTcArgs {
   int mode, nb, nr, nc, out_layout;
   float sqrt_c;
   int ksplit;                // > 1: the column tiles of a row tile are dealt to ksplit CTAs
+  AttnWinMap win;            // enabled: out is the [B][h][w][128] image, rows are scattered (needs ksplit == 1, NC layout)
 };
 
 int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st);
 int attn_bwd_tc_sum(const AttnBwdTcArgs& a, cudaStream_t st);
-// D[b][r] = sum_c dO[b][r][c] O[b][r][c]; layout NC: [n][128] rows, CN: [128][n]; explicit batch strides (floats)
+// D[b][r] = sum_c dO[b][r][c] O[b][r][c] from the bf16 hi|lo split of dO ([nb][n][256]) and a packed fp32 O ([nb][n][128])
+int attn_dsum_split(const void* do_split, const float* o, float* dsum, int nb, int n, cudaStream_t st);
+// the same from fp32 dO; layout NC: [n][128] rows, CN: [128][n]; explicit batch strides (floats)
 int attn_dsum(const float* d_o, long long do_stride_b, const float* o, long long o_stride_b, float* dsum, int nb, int n, int layout,
               cudaStream_t st);

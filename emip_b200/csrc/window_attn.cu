@@ -16,6 +16,7 @@
 #include "match_tc.cuh"
 #include "pair_bwd_tc.cuh"
 #include "attn_tc.cuh"
+#include "attn_bwd_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -76,8 +77,8 @@ int make_groups(int h, int w, int splits, int with_shift, Group* g, int max_grou
 }
 
 struct SplitParams {
-  const float* src[3];       // q, k, v: [B][h*w][128]
-  __nv_bfloat16* dst[3];     // [nprob][n][256] token-major hi|lo
+  const float* src[4];       // q, k, v (, dout): [B][h*w][128]
+  __nv_bfloat16* dst[4];     // [nprob][n][256] token-major hi|lo
   int B, h, w, n;
   int r0[MAXBLK], c0[MAXBLK], bw[MAXBLK];
 };
@@ -120,6 +121,12 @@ win_split_kernel(const __grid_constant__ SplitParams sp) {
 
 size_t group_bytes(int B, const Group& g) {
   return 3 * match_tc_split_bytes(g.nblk * B, g.n, KC);
+}
+size_t alf(size_t n_floats) { return emip_align_up(n_floats * sizeof(float), 1024); }
+// backward: four operand splits, the packed output of the re-run forward, lse and D
+size_t group_bytes_bwd(int B, const Group& g) {
+  const size_t np = (size_t)g.nblk * B;
+  return 4 * match_tc_split_bytes(g.nblk * B, g.n, KC) + alf(np * g.n * KC) + 2 * alf(np * g.n);
 }
 }  // namespace
 
@@ -184,6 +191,84 @@ extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, cons
     a.ksplit = 1;
     int rc;
     if ((rc = attn_tc_fwd(a, st))) return rc;
+  }
+  return EMIP_OK;
+}
+
+extern "C" size_t emip_window_attention_bwd_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift) {
+  Group g[16];
+  if (B < 0 || C != KC || h <= 0 || w <= 0) return 0;
+  const int ng = make_groups(h, w, num_splits, with_shift, g, 16);
+  if (ng < 0) return 0;
+  size_t need = 0;
+  for (int i = 0; i < ng; ++i) {
+    const size_t b = group_bytes_bwd(B, g[i]);
+    need = b > need ? b : need;
+  }
+  return need;
+}
+
+// Backward of emip_window_attention_fwd_tc: dq, dk, dv [B][h*w][C] from q, k, v and dout.  Per block group: one split
+// launch (window gather of all four tensors), the fused forward again for O and the row log-sum-exp (packed, in the
+// workspace), D = rowsum(dO o O), and the three gradient launches whose epilogues scatter the rows to their pixels.
+extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* dout, float* dq,
+                                            float* dk, float* dv, void* workspace, size_t ws_bytes, int B, int h, int w, int C,
+                                            int num_splits, int with_shift, void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(q && k && v && dout && dq && dk && dv && workspace, "window_attention_bwd_tc: null pointer");
+  EMIP_CHECK_ARG(B > 0 && h > 0 && w > 0, "window_attention_bwd_tc: bad shape B=%d h=%d w=%d", B, h, w);
+  if (C != KC) {
+    emip_set_error("window_attention_bwd_tc: C=%d unsupported (kernels are built for the model's C=128)", C);
+    return EMIP_ENOSYS;
+  }
+  Group g[16];
+  const int ng = make_groups(h, w, num_splits, with_shift, g, 16);
+  if (ng < 0) {
+    emip_set_error("window_attention_bwd_tc: unsupported window geometry h=%d w=%d num_splits=%d", h, w, num_splits);
+    return EMIP_ENOSYS;
+  }
+  if (ws_bytes < emip_window_attention_bwd_tc_workspace(B, h, w, C, num_splits, with_shift) ||
+      reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) {
+    emip_set_error("window_attention_bwd_tc: workspace too small or not 1024-byte aligned");
+    return EMIP_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < ng; ++i) {
+    const int n = g[i].n, nprob = g[i].nblk * B;
+    char* base = static_cast<char*>(workspace);
+    const size_t tok_bytes = match_tc_split_bytes(nprob, n, KC);
+    SplitParams sp;
+    sp.src[0] = q; sp.src[1] = k; sp.src[2] = v; sp.src[3] = dout;
+    for (int j = 0; j < 4; ++j) sp.dst[j] = reinterpret_cast<__nv_bfloat16*>(base + j * tok_bytes);
+    float* o = reinterpret_cast<float*>(base + 4 * tok_bytes);
+    float* lse = reinterpret_cast<float*>(base + 4 * tok_bytes + alf((size_t)nprob * n * KC));
+    float* dsum = lse + alf((size_t)nprob * n) / sizeof(float);
+    sp.B = B; sp.h = h; sp.w = w; sp.n = n;
+    AttnWinMap wm = {};
+    wm.enabled = 1; wm.B = B; wm.h = h; wm.w = w;
+    for (int j = 0; j < MAXBLK; ++j) {
+      sp.r0[j] = wm.r0[j] = j < g[i].nblk ? g[i].r0[j] : 0;
+      sp.c0[j] = wm.c0[j] = j < g[i].nblk ? g[i].c0[j] : 0;
+      sp.bw[j] = wm.bw[j] = j < g[i].nblk ? g[i].bw[j] : 1;
+    }
+    win_split_kernel<<<dim3((n + TOK - 1) / TOK, nprob, 4), 256, 0, st>>>(sp);
+    EMIP_CHECK_LAUNCH("window_attention_bwd (split)");
+    int rc;
+    AttnTcArgs f = {};
+    f.q_split = sp.dst[0]; f.k_split = sp.dst[1]; f.v_split = sp.dst[2]; f.v_chn = 0;
+    f.out = o; f.out_stride_b = (long long)n * KC; f.lse = lse;
+    f.nb = nprob; f.nq = n; f.nk = n; f.out_layout = EMIP_LAYOUT_NC; f.sqrt_c = sqrtf((float)KC); f.ksplit = 1;
+    if ((rc = attn_tc_fwd(f, st))) return rc;
+    if ((rc = attn_dsum_split(sp.dst[3], o, dsum, nprob, n, st))) return rc;
+    AttnBwdTcArgs a = {};
+    a.lse = lse; a.dsum = dsum; a.nb = nprob; a.nr = n; a.nc = n; a.out_layout = EMIP_LAYOUT_NC; a.out_stride_b = 0;
+    a.sqrt_c = sqrtf((float)KC); a.ksplit = 1; a.win = wm;
+    a.mode = ATTN_BWD_ROW; a.x_split = sp.dst[0]; a.y_split = sp.dst[1]; a.g_split = sp.dst[3]; a.z_split = sp.dst[2]; a.out = dq;
+    if ((rc = attn_bwd_tc(a, st))) return rc;
+    a.mode = ATTN_BWD_COL; a.x_split = sp.dst[1]; a.y_split = sp.dst[0]; a.g_split = sp.dst[2]; a.z_split = sp.dst[3]; a.out = dk;
+    if ((rc = attn_bwd_tc(a, st))) return rc;
+    a.mode = ATTN_BWD_PV; a.g_split = nullptr; a.out = dv;
+    if ((rc = attn_bwd_tc(a, st))) return rc;
   }
   return EMIP_OK;
 }

@@ -13,7 +13,7 @@ separates rectangular blocks of tokens -- in un-rolled coordinates the cuts are 
 each block: no roll, no mask tensor, no masked score entries.
 The GMFlow weights are frozen in training (train.py:340-342) but gradients still flow through this attention to the
 prompt-fusion outputs: the backward (dq, dk, dv) runs on the tensor cores too (``emip_attention_bwd_tc``,
-csrc/attn_bwd_tc.cu), per block group.
+csrc/attn_bwd_tc.cu), one C-ABI call per layer (``emip_window_attention_bwd_tc``) as well.
 """
 import ctypes
 
@@ -122,23 +122,19 @@ class _WindowAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        # the same block decomposition; the gathers / scatters are torch copies, the gradients run on the tensor cores
         q, k, v = ctx.saved_tensors
         num_splits, with_shift, h, w = ctx.geom
         b, _, c = q.shape
-        q4, k4, v4, d4 = (t.reshape(b, h, w, c) for t in (q, k, v, dout))
-        dq, dk, dv = (torch.empty_like(q4) for _ in range(3))
-        for (bh, bw), origins in _block_groups(h, w, num_splits, with_shift).items():
-            n = bh * bw
-
-            def gather(t):
-                return torch.stack([t[:, r0:r0 + bh, c0:c0 + bw] for (r0, c0) in origins], 0).reshape(len(origins) * b, n, c)
-            parts = _attention_bwd(gather(q4), gather(k4), gather(v4), gather(d4))
-            for dst, src in zip((dq, dk, dv), parts):
-                src = src.view(len(origins), b, bh, bw, c)
-                for i, (r0, c0) in enumerate(origins):
-                    dst[:, r0:r0 + bh, c0:c0 + bw] = src[i]
-        return dq.view(b, h * w, c), dk.view(b, h * w, c), dv.view(b, h * w, c), None, None, None, None
+        dout = dout.contiguous()
+        L = _lib.lib()
+        L.emip_window_attention_bwd_tc_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_window_attention_bwd_tc_workspace(I(b), I(h), I(w), I(c), I(num_splits),
+                                                                              I(int(with_shift))), q.device)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _lib.check(L.emip_window_attention_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+                                                  ctypes.c_void_p(ws_ptr), SZ(ws_n), I(b), I(h), I(w), I(c), I(num_splits),
+                                                  I(int(with_shift)), stream_ptr()), "emip_window_attention_bwd_tc")
+        return dq, dk, dv, None, None, None, None
 
 
 def single_head_split_window_attention(q, k, v, num_splits=1, with_shift=False, h=None, w=None, attn_mask=None):
