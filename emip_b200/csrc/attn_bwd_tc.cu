@@ -278,8 +278,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const bool row_ok = row < p.nr;
       float rL = 0.f, rD = 0.f;
       if (row_stats && row_ok) {
-        rL = __ldg(p.lse + (size_t)prob * p.nr + row) * LOG2E;
-        rD = __ldg(p.dsum + (size_t)prob * p.nr + row);
+        const size_t si = p.win.enabled ? p.win.pixel(prob, row) : (size_t)prob * p.nr + row;
+        rL = __ldg(p.lse + si) * LOG2E;
+        rD = __ldg(p.dsum + si);
       }
       for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int col_base = kt * TN;
@@ -291,8 +292,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int k = threadIdx.x / TN, c = threadIdx.x % TN, col = col_base + c;
             float v = 0.f;
             if (col < p.nc) {
-              if (k == 0) v = __ldg(p.lse + (size_t)prob * p.nc + col) * LOG2E;
-              else if (has_dp) v = __ldg(p.dsum + (size_t)prob * p.nc + col);
+              const size_t si = p.win.enabled ? p.win.pixel(prob, col) : (size_t)prob * p.nc + col;
+              if (k == 0) v = __ldg(p.lse + si) * LOG2E;
+              else if (has_dp) v = __ldg(p.dsum + si);
             }
             tab[threadIdx.x] = v;
           }
@@ -375,11 +377,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (p.out_layout == EMIP_LAYOUT_NC) {
             size_t orow = (size_t)row;
             if (p.win.enabled) {                          // scatter: token `row` of block (prob / B) of image (prob % B)
-              const int blk = prob / p.win.B, img = prob - blk * p.win.B;
-              const int bw = p.win.bw[blk];
-              const int ty = row / bw, tx = row - ty * bw;
               OUT = p.out;
-              orow = ((size_t)img * p.win.h + p.win.r0[blk] + ty) * p.win.w + p.win.c0[blk] + tx;
+              orow = p.win.pixel(prob, row);
             }
             float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
 #pragma unroll
@@ -428,20 +427,6 @@ dsum_nc_kernel(const float* __restrict__ d_o, long long do_stride_b, const float
   const float4 c = __ldg(reinterpret_cast<const float4*>(o + (size_t)b * o_stride_b + (size_t)r * 128) + lane);
   const float s = warp_sum(a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w);
   if (lane == 0) dsum[(size_t)b * n + r] = s;
-}
-__global__ void __launch_bounds__(256)
-dsum_split_kernel(const __nv_bfloat16* __restrict__ dos, const float* __restrict__ o, float* __restrict__ dsum, long long rows) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r = (long long)blockIdx.x * 8 + warp;
-  if (r >= rows) return;
-  const uint2 h = __ldg(reinterpret_cast<const uint2*>(dos + r * 256) + lane), l = __ldg(reinterpret_cast<const uint2*>(dos + r * 256 + 128) + lane);
-  const float4 c = __ldg(reinterpret_cast<const float4*>(o + r * 128) + lane);
-  const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
-  const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
-  const float a0 = __low2float(h0) + __low2float(l0), a1 = __high2float(h0) + __high2float(l0);
-  const float a2 = __low2float(h1) + __low2float(l1), a3 = __high2float(h1) + __high2float(l1);
-  const float s = warp_sum(a0 * c.x + a1 * c.y + a2 * c.z + a3 * c.w);
-  if (lane == 0) dsum[r] = s;
 }
 __global__ void __launch_bounds__(128)
 dsum_cn_kernel(const float* __restrict__ d_o, long long do_stride_b, const float* __restrict__ o, long long o_stride_b,
@@ -495,14 +480,6 @@ int attn_bwd_tc_sum(const AttnBwdTcArgs& a, cudaStream_t st) {
   if (a.nb == 0 || a.nr == 0 || a.ksplit <= 1) return EMIP_OK;
   sum_parts_kernel<<<dim3(128, a.nb), 256, 0, st>>>(a.part, a.out, a.out_stride_b, a.ksplit, a.nb, (size_t)a.nr * 128);
   EMIP_CHECK_LAUNCH("attn_bwd_tc_sum");
-  return EMIP_OK;
-}
-
-int attn_dsum_split(const void* do_split, const float* o, float* dsum, int nb, int n, cudaStream_t st) {
-  const long long rows = (long long)nb * n;
-  if (rows == 0) return EMIP_OK;
-  dsum_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(do_split), o, dsum, rows);
-  EMIP_CHECK_LAUNCH("attn_dsum_split");
   return EMIP_OK;
 }
 

@@ -16,7 +16,7 @@ struct AttnBwdTcArgs {
   const void* y_split;       // bf16 [nb][nc][256]
   const void* g_split;       // bf16 [nb][nr][256] (ROW, COL)
   const void* z_split;       // bf16 [nb][nc][256]
-  const float* lse;          // [nb][n]: n = nr (ROW) or nc (COL, PV)
+  const float* lse;          // [nb][n]: n = nr (ROW) or nc (COL, PV); with win.enabled both statistics are [B][h * w]
   const float* dsum;         // [nb][n]  (ROW, COL)
   float* out;                // ksplit == 1: [nb] x (nr * 128) in out_layout, batch stride out_stride_b
   long long out_stride_b;
@@ -29,8 +29,6 @@ struct AttnBwdTcArgs {
 
 int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st);
 int attn_bwd_tc_sum(const AttnBwdTcArgs& a, cudaStream_t st);
-// D[b][r] = sum_c dO[b][r][c] O[b][r][c] from the bf16 hi|lo split of dO ([nb][n][256]) and a packed fp32 O ([nb][n][128])
-int attn_dsum_split(const void* do_split, const float* o, float* dsum, int nb, int n, cudaStream_t st);
-// the same from fp32 dO; layout NC: [n][128] rows, CN: [128][n]; explicit batch strides (floats)
+// D[b][r] = sum_c dO[b][r][c] O[b][r][c]; layout NC: [n][128] rows, CN: [128][n]; explicit batch strides (floats)
 int attn_dsum(const float* d_o, long long do_stride_b, const float* o, long long o_stride_b, float* dsum, int nb, int n, int layout,
               cudaStream_t st);

@@ -362,7 +362,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (ns == 1) {
           OUT = p.out + (size_t)prob * p.out_stride_b;
           sc = 1.0f / l_row;
-          if (part == 0 && row_ok && p.lse != nullptr) p.lse[(size_t)prob * p.nq + row] = mref * LN2 + logf(l_row);
+          if (part == 0 && row_ok && p.lse != nullptr)
+            p.lse[p.win.enabled ? p.win.pixel(prob, row) : (size_t)prob * p.nq + row] = mref * LN2 + logf(l_row);
         } else {
           OUT = p.part_o + ((size_t)ks * p.nb + prob) * p.nq * 128;
           sc = 1.0f;
@@ -372,11 +373,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           if (p.out_layout == EMIP_LAYOUT_NC) {
             size_t orow = (size_t)row;
             if (p.win.enabled) {                          // scatter: token `row` of block (prob / B) of image (prob % B)
-              const int blk = prob / p.win.B, img = prob - blk * p.win.B;
-              const int bw = p.win.bw[blk];
-              const int ty = row / bw, tx = row - ty * bw;
               OUT = p.out;
-              orow = ((size_t)img * p.win.h + p.win.r0[blk] + ty) * p.win.w + p.win.c0[blk] + tx;
+              orow = p.win.pixel(prob, row);
             }
             float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
 #pragma unroll

@@ -8,6 +8,15 @@
 struct AttnWinMap {
   int enabled, B, h, w;
   int r0[16], c0[16], bw[16];
+#ifdef __CUDACC__
+  // index of token t of problem `prob` in the [B][h * w] pixel order (per-row statistics live in that order too)
+  __device__ __forceinline__ size_t pixel(int prob, int t) const {
+    const int blk = prob / B, img = prob - blk * B;
+    const int wd = bw[blk];
+    const int ty = t / wd, tx = t - ty * wd;
+    return ((size_t)img * h + r0[blk] + ty) * w + c0[blk] + tx;
+  }
+#endif
 };
 
 // out[b][r][:] = softmax_c(Q[b][r] . K[b][c] / sqrt(128)) V[b][c][:]   for nb independent problems.
@@ -19,7 +28,7 @@ struct AttnTcArgs {
   int v_chn;
   float* out;                // ksplit == 1: [nb] x (nq * 128) in out_layout, batch stride out_stride_b (floats)
   long long out_stride_b;
-  float* lse;                // optional [nb][nq]: log-sum-exp of the scaled scores (natural log)
+  float* lse;                // optional [nb][nq]: log-sum-exp of the scaled scores (natural log); [B][h * w] with win.enabled
   float* part_o;             // ksplit > 1: [ksplit][nb][nq * 128] un-normalised partial outputs (out_layout)
   float2* part_ml;           // ksplit > 1: [ksplit][nb][nq] (reference exponent in log2 units, partial row sum)
   int nb, nq, nk, out_layout;

@@ -123,11 +123,17 @@ size_t group_bytes(int B, const Group& g) {
   return 3 * match_tc_split_bytes(g.nblk * B, g.n, KC);
 }
 size_t alf(size_t n_floats) { return emip_align_up(n_floats * sizeof(float), 1024); }
-// backward: four operand splits, the packed output of the re-run forward, lse and D
-size_t group_bytes_bwd(int B, const Group& g) {
-  const size_t np = (size_t)g.nblk * B;
-  return 4 * match_tc_split_bytes(g.nblk * B, g.n, KC) + alf(np * g.n * KC) + 2 * alf(np * g.n);
+size_t group_bytes_bwd(int B, const Group& g);
+size_t ws_bytes_groups(int B, const Group* g, int ng) {
+  size_t need = 0;
+  for (int i = 0; i < ng; ++i) {
+    const size_t b = group_bytes_bwd(B, g[i]);
+    need = b > need ? b : need;
+  }
+  return need;
 }
+// backward: four operand splits
+size_t group_bytes_bwd(int B, const Group& g) { return 4 * match_tc_split_bytes(g.nblk * B, g.n, KC); }
 }  // namespace
 
 extern "C" size_t emip_window_attention_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift) {
@@ -143,9 +149,9 @@ extern "C" size_t emip_window_attention_tc_workspace(int B, int h, int w, int C,
   return need;
 }
 
-extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace,
-                                            size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift,
-                                            void* stream) {
+extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, float* lse,
+                                            void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
+                                            int with_shift, void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(q && k && v && out && workspace, "window_attention_fwd_tc: null pointer");
   EMIP_CHECK_ARG(B > 0 && h > 0 && w > 0, "window_attention_fwd_tc: bad shape B=%d h=%d w=%d", B, h, w);
@@ -185,7 +191,7 @@ extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, cons
     win_split_kernel<<<dim3((n + TOK - 1) / TOK, nprob, 3), 256, 0, st>>>(sp);
     EMIP_CHECK_LAUNCH("window_attention (split)");
     a.q_split = sp.dst[0]; a.k_split = sp.dst[1]; a.v_split = sp.dst[2];
-    a.out = out; a.out_stride_b = 0; a.lse = nullptr;
+    a.out = out; a.out_stride_b = 0; a.lse = lse;
     a.nb = nprob; a.nq = n; a.nk = n; a.out_layout = EMIP_LAYOUT_NC;
     a.sqrt_c = sqrtf((float)KC);
     a.ksplit = 1;
@@ -200,22 +206,19 @@ extern "C" size_t emip_window_attention_bwd_tc_workspace(int B, int h, int w, in
   if (B < 0 || C != KC || h <= 0 || w <= 0) return 0;
   const int ng = make_groups(h, w, num_splits, with_shift, g, 16);
   if (ng < 0) return 0;
-  size_t need = 0;
-  for (int i = 0; i < ng; ++i) {
-    const size_t b = group_bytes_bwd(B, g[i]);
-    need = b > need ? b : need;
-  }
-  return need;
+  return ws_bytes_groups(B, g, ng) + alf((size_t)B * h * w);      // + D in pixel order
 }
 
-// Backward of emip_window_attention_fwd_tc: dq, dk, dv [B][h*w][C] from q, k, v and dout.  Per block group: one split
-// launch (window gather of all four tensors), the fused forward again for O and the row log-sum-exp (packed, in the
-// workspace), D = rowsum(dO o O), and the three gradient launches whose epilogues scatter the rows to their pixels.
-extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* dout, float* dq,
-                                            float* dk, float* dv, void* workspace, size_t ws_bytes, int B, int h, int w, int C,
-                                            int num_splits, int with_shift, void* stream) {
+// Backward of emip_window_attention_fwd_tc: dq, dk, dv [B][h*w][C] from q, k, v, the forward's out and lse ([B][h*w], as
+// the forward wrote it) and dout.  D = rowsum(dO o O) is formed once in pixel order; per block group one split launch
+// (window gather of q, k, v, dout) and the three gradient launches, whose statistics loads and epilogues use the same
+// pixel map.
+extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* out, const float* lse,
+                                            const float* dout, float* dq, float* dk, float* dv, void* workspace,
+                                            size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift,
+                                            void* stream) {
   if (B == 0) return EMIP_OK;
-  EMIP_CHECK_ARG(q && k && v && dout && dq && dk && dv && workspace, "window_attention_bwd_tc: null pointer");
+  EMIP_CHECK_ARG(q && k && v && out && lse && dout && dq && dk && dv && workspace, "window_attention_bwd_tc: null pointer");
   EMIP_CHECK_ARG(B > 0 && h > 0 && w > 0, "window_attention_bwd_tc: bad shape B=%d h=%d w=%d", B, h, w);
   if (C != KC) {
     emip_set_error("window_attention_bwd_tc: C=%d unsupported (kernels are built for the model's C=128)", C);
@@ -233,6 +236,9 @@ extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, cons
     return EMIP_ENOMEM;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  float* dsum = reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_bytes_groups(B, g, ng));
+  if ((rc = attn_dsum(dout, (long long)h * w * KC, out, (long long)h * w * KC, dsum, B, h * w, EMIP_LAYOUT_NC, st))) return rc;
   for (int i = 0; i < ng; ++i) {
     const int n = g[i].n, nprob = g[i].nblk * B;
     char* base = static_cast<char*>(workspace);
@@ -240,9 +246,6 @@ extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, cons
     SplitParams sp;
     sp.src[0] = q; sp.src[1] = k; sp.src[2] = v; sp.src[3] = dout;
     for (int j = 0; j < 4; ++j) sp.dst[j] = reinterpret_cast<__nv_bfloat16*>(base + j * tok_bytes);
-    float* o = reinterpret_cast<float*>(base + 4 * tok_bytes);
-    float* lse = reinterpret_cast<float*>(base + 4 * tok_bytes + alf((size_t)nprob * n * KC));
-    float* dsum = lse + alf((size_t)nprob * n) / sizeof(float);
     sp.B = B; sp.h = h; sp.w = w; sp.n = n;
     AttnWinMap wm = {};
     wm.enabled = 1; wm.B = B; wm.h = h; wm.w = w;
@@ -253,13 +256,6 @@ extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, cons
     }
     win_split_kernel<<<dim3((n + TOK - 1) / TOK, nprob, 4), 256, 0, st>>>(sp);
     EMIP_CHECK_LAUNCH("window_attention_bwd (split)");
-    int rc;
-    AttnTcArgs f = {};
-    f.q_split = sp.dst[0]; f.k_split = sp.dst[1]; f.v_split = sp.dst[2]; f.v_chn = 0;
-    f.out = o; f.out_stride_b = (long long)n * KC; f.lse = lse;
-    f.nb = nprob; f.nq = n; f.nk = n; f.out_layout = EMIP_LAYOUT_NC; f.sqrt_c = sqrtf((float)KC); f.ksplit = 1;
-    if ((rc = attn_tc_fwd(f, st))) return rc;
-    if ((rc = attn_dsum_split(sp.dst[3], o, dsum, nprob, n, st))) return rc;
     AttnBwdTcArgs a = {};
     a.lse = lse; a.dsum = dsum; a.nb = nprob; a.nr = n; a.nc = n; a.out_layout = EMIP_LAYOUT_NC; a.out_stride_b = 0;
     a.sqrt_c = sqrtf((float)KC); a.ksplit = 1; a.win = wm;

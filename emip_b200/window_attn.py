@@ -113,16 +113,18 @@ class _WindowAttention(torch.autograd.Function):
             raise _lib.EmipError(f"emip_b200 window attention: unsupported geometry h={h} w={w} C={c} num_splits={num_splits}")
         ws, ws_ptr, ws_n = workspace(need, q.device)
         out = torch.empty_like(q)
-        _lib.check(L.emip_window_attention_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(out), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(b), I(h),
-                                                  I(w), I(c), I(num_splits), I(int(with_shift)), stream_ptr()),
+        need_grad = any(ctx.needs_input_grad[:3])
+        lse = torch.empty((b, h * w), dtype=torch.float32, device=q.device) if need_grad else None
+        _lib.check(L.emip_window_attention_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ctypes.c_void_p(ws_ptr), SZ(ws_n),
+                                                  I(b), I(h), I(w), I(c), I(num_splits), I(int(with_shift)), stream_ptr()),
                    "emip_window_attention_fwd_tc")
-        ctx.save_for_backward(q, k, v)
+        ctx.save_for_backward(q, k, v, out, lse)
         ctx.geom = (num_splits, with_shift, h, w)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v = ctx.saved_tensors
+        q, k, v, out, lse = ctx.saved_tensors
         num_splits, with_shift, h, w = ctx.geom
         b, _, c = q.shape
         dout = dout.contiguous()
@@ -131,7 +133,7 @@ class _WindowAttention(torch.autograd.Function):
         ws, ws_ptr, ws_n = workspace(L.emip_window_attention_bwd_tc_workspace(I(b), I(h), I(w), I(c), I(num_splits),
                                                                               I(int(with_shift))), q.device)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        _lib.check(L.emip_window_attention_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+        _lib.check(L.emip_window_attention_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
                                                   ctypes.c_void_p(ws_ptr), SZ(ws_n), I(b), I(h), I(w), I(c), I(num_splits),
                                                   I(int(with_shift)), stream_ptr()), "emip_window_attention_bwd_tc")
         return dq, dk, dv, None, None, None, None

@@ -242,15 +242,16 @@ int emip_attention_bwd_tc(const float* q, const float* k, const float* v, const 
  * operand-split pass and the attention epilogue: no gather / scatter / roll copies, no mask tensor.  C = 128, at most
  * 16 blocks with the same token count (num_splits <= 3). */
 size_t emip_window_attention_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift);
-int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, void* workspace,
+int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, float* lse, void* workspace,
                                  size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift, void* stream);
 
-/* Backward of the call above: dq, dk, dv [B][h*w][C] (every element is written) from q, k, v and dout; self-contained like
- * emip_attention_bwd_tc, window gather in the operand-split pass, scatter in the gradient kernels' epilogues. */
+/* Backward of the call above: dq, dk, dv [B][h*w][C] (every element is written) from q, k, v, the forward's out and lse
+ * ([B][h*w] row log-sum-exp in pixel order; pass a buffer as `lse` to the forward, NULL in inference) and dout.  Window
+ * gather in the operand-split pass, scatter in the gradient kernels' epilogues. */
 size_t emip_window_attention_bwd_tc_workspace(int B, int h, int w, int C, int num_splits, int with_shift);
-int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* dout, float* dq, float* dk,
-                                 float* dv, void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
-                                 int with_shift, void* stream);
+int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* out, const float* lse,
+                                 const float* dout, float* dq, float* dk, float* dv, void* workspace, size_t ws_bytes, int B,
+                                 int h, int w, int C, int num_splits, int with_shift, void* stream);
 
 /* Diagnostics: device buffer of (CTAs x 16) cycle counters filled by the next fused-attention launches (NULL = off). */
 void emip_attn_tc_set_profile_buffer(unsigned long long* dev_buf);
