@@ -19,9 +19,11 @@
 //   math:         W  = 2^{S c2 - L} (dP - D), split into bf16 hi + lo, back to TMEM
 //   UMMA-2  (TS): acc += W.hi B.hi + W.lo B.hi + W.hi B.lo,  B = the y tile (ROW, COL: it stays in its ring stages from
 //                 UMMA-1a to UMMA-2) or the z tile (PV), read as an MN-major operand straight from the token-major tile
-// All operands are 3-term split bf16 with fp32 accumulation, as in the forward.  The MMAs of a tile run strictly in
-// sequence with its math (UMMA-1, math, UMMA-2; S, dP and W are single-buffered in TMEM), only the operand loads of the
-// next tile overlap: the tensor pipe idles during the math.
+// All operands are 3-term split bf16 with fp32 accumulation, as in the forward.  In ROW / COL mode the MMAs of a tile
+// run strictly in sequence with its math (UMMA-1, math, UMMA-2; S, dP and W are single-buffered in TMEM and the y tile
+// occupies 4 of the 10 ring stages until UMMA-2, so the 12 chunks of the next tile cannot all be staged), only the
+// operand loads overlap: the tensor pipe idles during the math.  PV mode issues S(t + 1) ahead of
+// UMMA-2(t) like the forward kernel.
 #include "common.cuh"
 #include "pair_common.cuh"
 #include "tc_common.cuh"
@@ -129,9 +131,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           for (int c = 0; c < 4; ++c) push(&map_g, c * CH_ELEMS, rt * TM, prob);
           for (int c = 0; c < 4; ++c) push(&map_z, c * CH_ELEMS, t * TN, prob);
         }
-        for (int c = 0; c < 4; ++c) push(&map_y, c * CH_ELEMS, t * TN, prob);
-        if (!has_dp)
+        if (has_dp || t == kb)
+          for (int c = 0; c < 4; ++c) push(&map_y, c * CH_ELEMS, t * TN, prob);
+        if (!has_dp) {                    // PV is pipelined like the forward: y(t + 1) is consumed before z(t)
+          if (t + 1 < ke)
+            for (int c = 0; c < 4; ++c) push(&map_y, c * CH_ELEMS, (t + 1) * TN, prob);
           for (int c = 0; c < 4; ++c) push(&map_z, c * CH_ELEMS, t * TN, prob);
+        }
       }
     }
     __syncwarp();
@@ -227,26 +233,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
       w_xf += mbar_wait(x_full, it & 1);
       tc_fence_after();
+      if (!has_dp) {
+        // PV (dV) has no dP: S(t + 1) is issued ahead of UMMA-2(t), as in the forward kernel, so the tensor pipe works
+        // on the next score tile while the math warps turn the current one into W.  (Measured gain is small, 8970 ->
+        // 8460 cycles per tile: the math phase itself, ~3700 cycles per tile next to a running UMMA, bounds this mode.)
+        auto issue_s = [&](int t, uint32_t T) {
+          w_se += mbar_wait(s_empty, (T & 1) ^ 1);
+          tc_fence_after();
+          mma1(OFF_X, COL_S, (t == nkt - 1) ? idesc_tail : idesc_full, true);
+          if (leader) {
+            umma_commit(s_full);
+            if (t == ke - 1) umma_commit(x_empty);
+          }
+          __syncwarp();
+        };
+        issue_s(kb, tile);
+        for (int t = kb; t < ke; ++t, ++tile) {
+          if (t + 1 < ke) issue_s(t + 1, tile + 1);
+          const int bs = stage;
+          for (int c = 0; c < 4; ++c) {
+            w_rf += mbar_wait(r_full(stage), phase);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          w_wf += mbar_wait(w_full, tile & 1);
+          if (t == kb) w_ae += mbar_wait(acc_empty, (it & 1) ^ 1);
+          tc_fence_after();
+          mma2(bs, t == kb, t == ke - 1);
+        }
+        continue;
+      }
       for (int t = kb; t < ke; ++t, ++tile) {
         const uint32_t idesc = (t == nkt - 1) ? idesc_tail : idesc_full;
         w_se += mbar_wait(s_empty, (tile & 1) ^ 1);       // the math warps hold the previous S / dP tiles in registers
         tc_fence_after();
-        if (has_dp) mma_dp(idesc);
+        mma_dp(idesc);
         const int ys = stage;                             // first ring stage of the y tile
-        mma1(OFF_X, COL_S, idesc, !has_dp);
+        mma1(OFF_X, COL_S, idesc, false);
         if (leader) {
           umma_commit(s_full);
           if (t == ke - 1) umma_commit(x_empty);          // x and g are read by UMMA-1 only
         }
         __syncwarp();
-        int bs = ys;
-        if (!has_dp) {                                    // PV: the z tile follows in the ring
-          bs = stage;
-          for (int c = 0; c < 4; ++c) {
-            w_rf += mbar_wait(r_full(stage), phase);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
+        const int bs = ys;
         w_wf += mbar_wait(w_full, tile & 1);
         if (t == kb) w_ae += mbar_wait(acc_empty, (it & 1) ^ 1);  // the epilogue of the previous item has drained the accumulator
         tc_fence_after();
@@ -304,8 +332,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         w_sf += mbar_wait(s_full, tile & 1);
         long long c0 = clock64();
         tc_fence_after();
-        w_we += mbar_wait(w_empty, (tile & 1) ^ 1);         // UMMA-2 of the previous tile has retired (long ago)
-        tc_fence_after();
         const int nv = p.nc - (col_base + cb);              // valid columns of my part (warp-uniform)
         // two halves of 16 columns: 32 + 16 live registers instead of 64 + 32 (the first version spilled 250 bytes per
         // thread into an L1 that the 227 KB shared-memory carve-out leaves almost empty)
@@ -350,6 +376,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               if (!(row_ok && cq + e < nv)) w4[e] = 0.f;
             split_bf16x2_alu(w4[0], w4[1], whi[2 * q], wlo[2 * q]);
             split_bf16x2_alu(w4[2], w4[3], whi[2 * q + 1], wlo[2 * q + 1]);
+          }
+          if (hf == 0) {
+            w_we += mbar_wait(w_empty, (tile & 1) ^ 1);     // UMMA-2 of the previous tile has retired: W may be overwritten
+            tc_fence_after();
           }
           const uint32_t t_whi = tmem_base + lane_base + COL_W + (uint32_t)(part * 16 + 8 * hf);
           tmem_st8(t_whi, whi);
