@@ -58,6 +58,7 @@ struct BParams {
   unsigned long long* prof;   // optional [gridDim.x][16] cycle counters (emip_attn_tc_set_profile_buffer)
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                    const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_z,
@@ -151,13 +152,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t idesc_mn = idesc_full | (1u << 16);    // b_major = MN
     const uint32_t t_w = tmem_base + COL_W, t_acc = tmem_base + COL_ACC;
     long long w_rf = 0, w_se = 0, w_wf = 0, w_ae = 0, w_xf = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = PROF ? clock64() : 0;
     // D[128 x n] = A.hi B.hi^T + A.lo B.hi^T + A.hi B.lo^T with A resident at a_off and B in the next four ring stages;
     // `release` hands the stages back to the producer (the y tile of ROW / COL mode is kept for UMMA-2)
     auto mma1 = [&](int a_off, uint32_t d_col, uint32_t idesc, bool release) {
       const uint64_t ad = make_kmajor_sw128_desc(sbase + a_off);
       for (int c = 0; c < 4; ++c) {
-        w_rf += mbar_wait(r_full(stage), phase);
+        prof_add<PROF>(w_rf, mbar_wait(r_full(stage), phase));
         tc_fence_after();
         if (leader) {
           const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_RING + stage * CHUNK_BYTES);
@@ -179,7 +180,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     auto mma_dp = [&](uint32_t idesc) {
       int sg[4], sz[4];
       for (int c = 0; c < 8; ++c) {
-        w_rf += mbar_wait(r_full(stage), phase);
+        prof_add<PROF>(w_rf, mbar_wait(r_full(stage), phase));
         if (c < 4) sg[c] = stage; else sz[c - 4] = stage;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -231,14 +232,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int ks = item % ns;
       const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
-      w_xf += mbar_wait(x_full, it & 1);
+      prof_add<PROF>(w_xf, mbar_wait(x_full, it & 1));
       tc_fence_after();
       if (!has_dp) {
         // PV (dV) has no dP: S(t + 1) is issued ahead of UMMA-2(t), as in the forward kernel, so the tensor pipe works
         // on the next score tile while the math warps turn the current one into W.  (Measured gain is small, 8970 ->
         // 8460 cycles per tile: the math phase itself, ~3700 cycles per tile next to a running UMMA, bounds this mode.)
         auto issue_s = [&](int t, uint32_t T) {
-          w_se += mbar_wait(s_empty, (T & 1) ^ 1);
+          prof_add<PROF>(w_se, mbar_wait(s_empty, (T & 1) ^ 1));
           tc_fence_after();
           mma1(OFF_X, COL_S, (t == nkt - 1) ? idesc_tail : idesc_full, true);
           if (leader) {
@@ -252,11 +253,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (t + 1 < ke) issue_s(t + 1, tile + 1);
           const int bs = stage;
           for (int c = 0; c < 4; ++c) {
-            w_rf += mbar_wait(r_full(stage), phase);
+            prof_add<PROF>(w_rf, mbar_wait(r_full(stage), phase));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          w_wf += mbar_wait(w_full, tile & 1);
-          if (t == kb) w_ae += mbar_wait(acc_empty, (it & 1) ^ 1);
+          prof_add<PROF>(w_wf, mbar_wait(w_full, tile & 1));
+          if (t == kb) prof_add<PROF>(w_ae, mbar_wait(acc_empty, (it & 1) ^ 1));
           tc_fence_after();
           mma2(bs, t == kb, t == ke - 1);
         }
@@ -264,7 +265,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       for (int t = kb; t < ke; ++t, ++tile) {
         const uint32_t idesc = (t == nkt - 1) ? idesc_tail : idesc_full;
-        w_se += mbar_wait(s_empty, (tile & 1) ^ 1);       // the math warps hold the previous S / dP tiles in registers
+        prof_add<PROF>(w_se, mbar_wait(s_empty, (tile & 1) ^ 1));       // the math warps hold the previous S / dP tiles in registers
         tc_fence_after();
         mma_dp(idesc);
         const int ys = stage;                             // first ring stage of the y tile
@@ -275,13 +276,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         __syncwarp();
         const int bs = ys;
-        w_wf += mbar_wait(w_full, tile & 1);
-        if (t == kb) w_ae += mbar_wait(acc_empty, (it & 1) ^ 1);  // the epilogue of the previous item has drained the accumulator
+        prof_add<PROF>(w_wf, mbar_wait(w_full, tile & 1));
+        if (t == kb) prof_add<PROF>(w_ae, mbar_wait(acc_empty, (it & 1) ^ 1));  // the epilogue of the previous item has drained the accumulator
         tc_fence_after();
         mma2(bs, t == kb, t == ke - 1);
       }
     }
-    if (bp.prof && leader) {
+    if (PROF && bp.prof && leader) {
       unsigned long long* o = bp.prof + blockIdx.x * 16;
       o[8] = w_se; o[9] = w_rf; o[10] = w_wf; o[11] = w_ae; o[12] = w_xf; o[13] = clock64() - t_begin;
     }
@@ -298,7 +299,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const bool row_stats = p.mode == ATTN_BWD_ROW;
     uint32_t tile = 0, it = 0;
     long long w_sf = 0, t_tab = 0, t_ld = 0, t_m = 0, w_we = 0, t_st = 0, w_af = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = PROF ? clock64() : 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
       const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
@@ -312,7 +313,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int col_base = kt * TN;
-        const long long cA = clock64();
+        const long long cA = PROF ? clock64() : 0;
         if (!row_stats) {
           // per-column L log2(e) and D of this tile -> smem (single buffer: every warp has finished the previous tile)
           asm volatile("bar.sync 1, %0;" ::"n"(NMATH * 32) : "memory");
@@ -328,9 +329,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           }
           asm volatile("bar.sync 1, %0;" ::"n"(NMATH * 32) : "memory");
         }
-        t_tab += clock64() - cA;
-        w_sf += mbar_wait(s_full, tile & 1);
-        long long c0 = clock64();
+        if (PROF) t_tab += clock64() - cA;
+        prof_add<PROF>(w_sf, mbar_wait(s_full, tile & 1));
+        long long c0 = PROF ? clock64() : 0;
         tc_fence_after();
         const int nv = p.nc - (col_base + cb);              // valid columns of my part (warp-uniform)
         // two halves of 16 columns: 32 + 16 live registers instead of 64 + 32 (the first version spilled 250 bytes per
@@ -378,22 +379,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             split_bf16x2_alu(w4[2], w4[3], whi[2 * q + 1], wlo[2 * q + 1]);
           }
           if (hf == 0) {
-            w_we += mbar_wait(w_empty, (tile & 1) ^ 1);     // UMMA-2 of the previous tile has retired: W may be overwritten
+            prof_add<PROF>(w_we, mbar_wait(w_empty, (tile & 1) ^ 1));     // UMMA-2 of the previous tile has retired: W may be overwritten
             tc_fence_after();
           }
           const uint32_t t_whi = tmem_base + lane_base + COL_W + (uint32_t)(part * 16 + 8 * hf);
           tmem_st8(t_whi, whi);
           tmem_st8(t_whi + 64, wlo);
         }
-        t_m += clock64() - c0;
-        c0 = clock64();
+        if (PROF) t_m += clock64() - c0;
+        if (PROF) c0 = clock64();
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(w_full);
-        t_st += clock64() - c0;
+        if (PROF) t_st += clock64() - c0;
       }
       // ---- epilogue: accumulator -> global
-      w_af += mbar_wait(acc_full, it & 1);
+      prof_add<PROF>(w_af, mbar_wait(acc_full, it & 1));
       tc_fence_after();
       {
         uint32_t r[32];
@@ -422,7 +423,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       }
     }
-    if (bp.prof && threadIdx.x == 0) {
+    if (PROF && bp.prof && threadIdx.x == 0) {
       unsigned long long* o = bp.prof + blockIdx.x * 16;
       o[0] = w_sf; o[1] = t_tab; o[2] = t_ld; o[3] = t_m; o[4] = w_we; o[5] = t_st; o[6] = w_af; o[7] = clock64() - t_begin;
     }
@@ -491,7 +492,8 @@ int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st) {
     return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   BParams bp;
@@ -501,7 +503,8 @@ int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st) {
   const int nrt = (a.nr + TM - 1) / TM;
   long long grid = (long long)a.nb * nrt * (a.ksplit > 1 ? a.ksplit : 1);
   if (grid > emip_num_sms()) grid = emip_num_sms();
-  attn_bwd_tc_kernel<<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, mg, mz, bp);
+  if (bp.prof) attn_bwd_tc_kernel<true><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, mg, mz, bp);   // diagnostics build
+  else attn_bwd_tc_kernel<false><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mx, my, mg, mz, bp);
   EMIP_CHECK_LAUNCH("attn_bwd_tc");
   return EMIP_OK;
 }

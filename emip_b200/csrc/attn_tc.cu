@@ -78,6 +78,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AParams ap) {
@@ -168,14 +169,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
     const uint32_t t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
     long long w_se = 0, w_rf = 0, w_pf = 0, w_oe = 0, w_qf = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = PROF ? clock64() : 0;
     auto mma1 = [&](uint32_t T, bool tail) {              // S tile T -> TMEM buffer T & 1
       const int buf = T & 1;
-      w_se += mbar_wait(s_empty(buf), ((T >> 1) & 1) ^ 1);
+      prof_add<PROF>(w_se, mbar_wait(s_empty(buf), ((T >> 1) & 1) ^ 1));
       const uint32_t idesc = tail ? idesc_tail : idesc_full;
       const uint32_t d = tmem_base + (uint32_t)(buf * TN);
       for (int c = 0; c < 4; ++c) {
-        w_rf += mbar_wait(r_full(stage), phase);
+        prof_add<PROF>(w_rf, mbar_wait(r_full(stage), phase));
         tc_fence_after();
         if (leader) {
           const uint64_t kd = make_kmajor_sw128_desc(sbase + OFF_RING + stage * CHUNK_BYTES);
@@ -199,12 +200,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // STAGES is a multiple of four), LBO = one chunk; a K16 step = two 8-key groups = 2 KB further down.
     const uint32_t idesc_mn = idesc_full | (1u << 16);    // b_major = MN
     auto mma2 = [&](uint32_t T, bool first, bool last) {  // O += P(T) V(T)
-      w_pf += mbar_wait(p_full, T & 1);
-      if (first) w_oe += mbar_wait(o_empty, (it & 1) ^ 1);        // the epilogue of the previous item has drained O
+      prof_add<PROF>(w_pf, mbar_wait(p_full, T & 1));
+      if (first) prof_add<PROF>(w_oe, mbar_wait(o_empty, (it & 1) ^ 1));        // the epilogue of the previous item has drained O
       for (int half = 0; half < 2; ++half) {              // V.hi chunks, then V.lo chunks
         const int s0 = stage;
-        w_rf += mbar_wait(r_full(s0), phase);
-        w_rf += mbar_wait(r_full(s0 + 1), phase);
+        prof_add<PROF>(w_rf, mbar_wait(r_full(s0), phase));
+        prof_add<PROF>(w_rf, mbar_wait(r_full(s0 + 1), phase));
         tc_fence_after();
         if (leader) {
           if (p.v_chn) {
@@ -240,7 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int ks = item % ns;
       const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
-      w_qf += mbar_wait(q_full, it & 1);
+      prof_add<PROF>(w_qf, mbar_wait(q_full, it & 1));
       tc_fence_after();
       // Q is read by UMMA-1 only: it is handed back as soon as the LAST S tile of the item has been issued, so the
       // producer brings in the next item's Q tile and first K chunks under the last two UMMA-2 groups
@@ -257,7 +258,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       tile += ke - kb;
     }
-    if (ap.prof && leader) {
+    if (PROF && ap.prof && leader) {
       unsigned long long* o = ap.prof + blockIdx.x * 16;
       o[8] = w_se; o[9] = w_rf; o[10] = w_pf; o[11] = w_oe; o[12] = w_qf; o[13] = clock64() - t_begin;
     }
@@ -272,7 +273,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int cb = part * 32;                              // first column (within the tile) of my chunk
     uint32_t tile = 0, it = 0;
     long long w_sf = 0, t_ld = 0, t_x = 0, t_e = 0, w_pe = 0, t_st = 0, w_of = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = PROF ? clock64() : 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
       const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
@@ -281,15 +282,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       float mref = -INFINITY, l = 0.f;                     // reference exponent (log2 units), my part of the row sum
       for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int buf = tile & 1;
-        w_sf += mbar_wait(s_full(buf), (tile >> 1) & 1);
-        long long c0 = clock64();
+        prof_add<PROF>(w_sf, mbar_wait(s_full(buf), (tile >> 1) & 1));
+        long long c0 = PROF ? clock64() : 0;
         tc_fence_after();
         uint32_t r[32];
         tmem_ld32_async(tmem_base + lane_base + (uint32_t)(buf * TN + cb), r);
         tmem_wait(r);
         tc_fence_before();
         mbar_arrive(s_empty(buf));                          // my part of the S tile is in registers
-        { const long long c1 = clock64(); t_ld += c1 - c0; c0 = c1; }
+        if (PROF) { const long long c1 = clock64(); t_ld += c1 - c0; c0 = c1; }
         const int nv = p.nk - (kt * TN + cb);               // valid columns of my part (warp-uniform)
         if (nv < 32) {                                      // key tail: masked scores = -inf -> max ignores them, P = 0
 #pragma unroll
@@ -305,7 +306,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
         const uint32_t sq = slot + (uint32_t)((quarter * 32 + lane) * 4);
         const float m_tile = fmaxf(fmaxf(lds32(sq), lds32(sq + 4 * 128)), fmaxf(lds32(sq + 8 * 128), lds32(sq + 12 * 128)));
-        { const long long c1 = clock64(); t_x += c1 - c0; c0 = c1; }
+        if (PROF) { const long long c1 = clock64(); t_x += c1 - c0; c0 = c1; }
         float f = 1.f;
         const bool grow = m_tile > mref + TAU;              // first tile: mref = -inf
         if (grow) {
@@ -324,9 +325,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         // the P buffer is free, and O is quiescent, once UMMA-2 of the previous tile has retired
-        { const long long c1 = clock64(); t_e += c1 - c0; }
-        w_pe += mbar_wait(p_empty, (tile & 1) ^ 1);
-        c0 = clock64();
+        if (PROF) { const long long c1 = clock64(); t_e += c1 - c0; }
+        prof_add<PROF>(w_pe, mbar_wait(p_empty, (tile & 1) ^ 1));
+        if (PROF) c0 = clock64();
         tc_fence_after();
         if (kt != kb && __any_sync(0xffffffffu, grow)) {    // rare: rescale my 32 columns of the O accumulator
           uint32_t o[32];
@@ -342,14 +343,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);
-        t_st += clock64() - c0;
+        if (PROF) t_st += clock64() - c0;
       }
       // ---- epilogue: row sum across the four parts, O / l -> global
       sts32(xl_u32 + (uint32_t)((warp * 32 + lane) * 4), l);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       const uint32_t lq = xl_u32 + (uint32_t)((quarter * 32 + lane) * 4);
       const float l_row = (lds32(lq) + lds32(lq + 4 * 128)) + (lds32(lq + 8 * 128) + lds32(lq + 12 * 128));
-      w_of += mbar_wait(o_full, it & 1);
+      prof_add<PROF>(w_of, mbar_wait(o_full, it & 1));
       tc_fence_after();
       {
         uint32_t r[32];
@@ -388,7 +389,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
     }
-    if (ap.prof && threadIdx.x == 0) {
+    if (PROF && ap.prof && threadIdx.x == 0) {
       unsigned long long* o = ap.prof + blockIdx.x * 16;
       o[0] = w_sf; o[1] = t_ld; o[2] = t_x; o[3] = t_e; o[4] = w_pe; o[5] = t_st; o[6] = w_of; o[7] = clock64() - t_begin;
     }
@@ -450,7 +451,8 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   } else if ((rc = make_bf16_map(&mv, a.v_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   AParams ap;
@@ -460,7 +462,8 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   const int nrt = (a.nq + TM - 1) / TM;
   long long grid = (long long)a.nb * nrt * (a.ksplit > 1 ? a.ksplit : 1);
   if (grid > emip_num_sms()) grid = emip_num_sms();
-  attn_fwd_tc_kernel<<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, ap);
+  if (ap.prof) attn_fwd_tc_kernel<true><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, ap);   // diagnostics build
+  else attn_fwd_tc_kernel<false><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, ap);
   EMIP_CHECK_LAUNCH("attn_tc_fwd");
   return EMIP_OK;
 }

@@ -44,6 +44,11 @@ __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return clock64() - t0;
 }
+// role-profile accumulation that compiles away in the production instantiation of a kernel
+template <bool PROF>
+__device__ __forceinline__ void prof_add(long long& acc, long long v) {
+  if constexpr (PROF) acc += v;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
