@@ -5,8 +5,8 @@ tensor of matching.py:16-20.  ``conv_corr_first_layer(f0, f1, weight, bias)`` re
 ``F.conv2d(corr, weight, bias, padding=1)`` returns for ``corr = global_correlation_softmax(f0, f1)[2]`` without
 forming ``corr``: two per-sample tensor-core GEMMs on the feature maps (csrc/conv_corr.cu).
 
-Training: the backward pass re-derives the gradients from the same re-association with library matmuls
-(``_reassociated_torch``) -- the forward kernel is the product, the backward is plumbing for now.
+Training: the backward pass runs on the tensor cores too (``emip_conv_corr_bwd``: five split-bf16 GEMMs on the same
+re-association; ``_reassociated_torch`` states it with library ops and is what the tests compare the gradients with).
 """
 import ctypes
 import math
@@ -72,14 +72,21 @@ class _ConvCorr(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        # five split-bf16 tensor-core GEMMs (csrc/gemm_tc.cu, conv_corr_bwd_tc): G recomputed, dG, dX9 -> df0, dW, df1
         f0, f1, weight, bias = ctx.saved_tensors
-        bias = bias if ctx.has_bias else None
-        with torch.enable_grad():
-            ins = [t.detach().requires_grad_(True) for t in (f0, f1, weight)]
-            b = bias.detach().requires_grad_(True) if bias is not None else None
-            out = _reassociated_torch(ins[0], ins[1], ins[2], b)
-            grads = torch.autograd.grad(out, ins + ([b] if b is not None else []), dout)
-        return grads[0], grads[1], grads[2], (grads[3] if b is not None else None)
+        L = _lib.lib()
+        B, C, H, W = f0.shape
+        O = weight.shape[0]
+        f0c, f1c, w, d = f0.contiguous(), f1.contiguous(), weight.detach().contiguous(), dout.contiguous()
+        wbuf, wp = _prepared_weight(weight)
+        L.emip_conv_corr_bwd_workspace.restype = ctypes.c_size_t
+        ws, ws_ptr, ws_n = workspace(L.emip_conv_corr_bwd_workspace(I(B), I(C), I(H), I(W), I(O)), f0.device)
+        df0, df1, dw = torch.empty_like(f0c), torch.empty_like(f1c), torch.empty_like(w)
+        db = torch.empty(O, dtype=torch.float32, device=f0.device) if ctx.has_bias else None
+        _lib.check(L.emip_conv_corr_bwd(ptr(f0c), ptr(f1c), ptr(w), ctypes.c_void_p(wp), ptr(d), ptr(df0), ptr(df1), ptr(dw), ptr(db),
+                                        ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C), I(H), I(W), I(O), stream_ptr()),
+                   "emip_conv_corr_bwd")
+        return df0, df1, dw, db
 
 
 def conv_corr_first_layer(f0, f1, weight, bias=None):

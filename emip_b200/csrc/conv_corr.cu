@@ -169,3 +169,24 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
   }
   return EMIP_OK;
 }
+
+// Backward of emip_conv_corr_fwd on the tensor cores (five mode-2 GEMMs, gemm_tc.cu): df0, df1 [B,C,H,W],
+// dweight [O,H*W,3,3], dbias [O] (NULL: not wanted) from dout [B,O,H,W].  weight = the fp32 parameter, w_prep = its
+// prepared copy (emip_conv_corr_prepare_weight).
+extern "C" size_t emip_conv_corr_bwd_workspace(int B, int C, int H, int W, int O) {
+  if (B < 0 || C != 128 || H <= 0 || W <= 0 || O <= 0) return 0;
+  return conv_corr_bwd_scratch_bytes(B, O, H * W);
+}
+
+extern "C" int emip_conv_corr_bwd(const float* f0, const float* f1, const float* weight, const void* w_prep, const float* dout,
+                                  float* df0, float* df1, float* dweight, float* dbias, void* workspace, size_t ws_bytes, int B,
+                                  int C, int H, int W, int O, void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(f0 && f1 && weight && w_prep && dout && df0 && df1 && dweight && workspace, "conv_corr_bwd: null pointer");
+  if (!emip_conv_corr_supported(C, H, W)) {
+    emip_set_error("conv_corr_bwd: unsupported shape C=%d H=%d W=%d", C, H, W);
+    return EMIP_ENOSYS;
+  }
+  return conv_corr_bwd_tc(f0, f1, weight, w_prep, weight_ld(H * W), dout, df0, df1, dweight, dbias, workspace, ws_bytes, B, H, W, O,
+                          (cudaStream_t)stream);
+}

@@ -499,3 +499,264 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
   return gemm_tc_launch(ma_hi, ma_lo, mb, p, a.B, st);
 }
+
+// =====================================================================================================================
+// f1 backward: the gradients of  out[b,o,p] = bias[o] + sum_{t,c} G[b][(o,t)][c] f0[b,c,p + d_t],
+//                                G[b][(o,t)][c] = s sum_j Wp[(o,t)][j] f1[b,c,j],  s = 1/sqrt(C)      (conv_corr.cu)
+// as five mode-2 launches of the tensor-core GEMM on K-major bf16 hi|lo operands (X9[b][(t,c)][p] = f0[b,c,p + d_t], the
+// nine zero-padded shifts of f0, exists only as the split operand of GEMM (i)):
+//   G / s      = Wp f1^T                   M = 9 O, N = 128,     K = HW      (recomputed: the forward keeps it in bf16 only)
+//   (i)   dG   = dout X9^T                 M = O,   N = 9 * 128, K = HW      per sample
+//   (ii)  dX9  = G^T dout                  M = 9 * 128, N = HW,  K = O       per sample; df0 = col2im(dX9)
+//   (iii) dWp  = s sum_(b,c) dG f1         M = 9 O, N = HW,      K = 128 B   (batch folded into K)
+//   (iv)  df1  = s sum_(o,t) dG^T Wp       M = 128 B, N = HW,    K = 9 O     (batch folded into M)
+// r1 re-derived these with library ops (three fp32 SIMT sgemms + 16 cuDNN wgrad calls: 5.6 ms at B = 16).
+namespace {
+
+// dbias[o] = sum_{b,p} dout[b][o][p]
+__global__ void __launch_bounds__(256)
+f1_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int O, int P) {
+  __shared__ float red[8];
+  const int o = blockIdx.x, P4 = P >> 2;                 // P % 4 == 0 (checked by the caller)
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B * P4; i += blockDim.x) {
+    const int b = i / P4, q = i - b * P4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dout + ((size_t)b * O + o) * P) + q);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    dbias[o] = t;
+  }
+}
+// Bt[b][(t,c)][hi | lo over p] = f0[b][c][p + d_t] (0 outside the image): the B operand of (i).
+// grid (ceil(Pp / 2048), 9 * 128, B): 8 consecutive pixels per thread.
+__global__ void __launch_bounds__(256)
+f1_im2col_split_kernel(const float* __restrict__ f0, __nv_bfloat16* __restrict__ dst, int H, int W, int Pp) {
+  const int b = blockIdx.z, tc_ = blockIdx.y, t = tc_ >> 7, c = tc_ & 127;
+  const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (p0 >= Pp) return;
+  const int dy = t / 3 - 1, dx = t % 3 - 1, P = H * W;
+  const float* src = f0 + ((size_t)b * 128 + c) * P;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = p0 + i, y = p / W + dy, x = p % W + dx;
+    v[i] = (p < P && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + y * W + x) : 0.f;
+  }
+  __nv_bfloat16* d = dst + ((size_t)b * 9 * 128 + tc_) * 2 * Pp + p0;
+  split8_store(v, d, d + Pp);
+}
+// df0[b][c][q] = s sum_t dX9[b][(t,c)][q - d_t]   (s: G is kept unscaled, the 1/sqrt(C) of (ii) is applied here)
+__global__ void __launch_bounds__(256)
+f1_col2im_kernel(const float* __restrict__ dx9, float* __restrict__ df0, int H, int W, float s_) {
+  const int b = blockIdx.z, c = blockIdx.y, P = H * W;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P) return;
+  const int qy = q / W, qx = q % W;
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int y = qy - (t / 3 - 1), x = qx - (t % 3 - 1);
+    if (y >= 0 && y < H && x >= 0 && x < W) s += __ldg(dx9 + (((size_t)b * 9 + t) * 128 + c) * P + y * W + x);
+  }
+  df0[((size_t)b * 128 + c) * P + q] = s * s_;
+}
+// A of (iii): hi, lo [M1][Kp = 128 B] with A[m][b * 128 + c] = s dG[b][m][c]
+__global__ void __launch_bounds__(128)
+f1_gather_split_kernel(const float* __restrict__ dg, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B, int M1,
+                       float s) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 4), b = blockIdx.y;
+  const int c0 = (threadIdx.x & 15) * 8;
+  if (m >= M1) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(dg + ((size_t)b * M1 + m) * 128 + c0));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(dg + ((size_t)b * M1 + m) * 128 + c0 + 4));
+  const float v[8] = {a.x * s, a.y * s, a.z * s, a.w * s, c.x * s, c.y * s, c.z * s, c.w * s};
+  const size_t o = (size_t)m * (128 * B) + (size_t)b * 128 + c0;
+  split8_store(v, hi + o, lo + o);
+}
+// Bt of (iv): [j][hi | lo over k = (o,t)] = s w[o][j][t], zero padded to Kp
+__global__ void __launch_bounds__(256)
+f1_weight_t_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O, int N, int Kp, float s) {
+  const int j = blockIdx.y;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (k0 >= Kp) return;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + i, o = k / 9, t = k - o * 9;
+    v[i] = o < O ? __ldg(w + ((size_t)o * N + j) * 9 + t) * s : 0.f;
+  }
+  __nv_bfloat16* d = dst + (size_t)j * 2 * Kp + k0;
+  split8_store(v, d, d + Kp);
+}
+// dweight[o][j][t] = dWp[(o,t)][j]
+__global__ void __launch_bounds__(256)
+f1_dweight_permute_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int O, int N) {
+  const int o = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    float* d = dw + ((size_t)o * N + j) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) d[t] = __ldg(dwp + ((size_t)o * 9 + t) * N + j);
+  }
+}
+
+struct F1Bufs {
+  float *g, *dg, *dx9, *dwp;
+  char* ops;        // operand scratch, reused by every GEMM
+  size_t ops_bytes;
+};
+size_t f1_ops_bytes(int B, int O, int P) {
+  const size_t Pp = kpad(P), M1 = (size_t)O * 9, Ko = kpad(O), Kb = (size_t)128 * B, Km = kpad((int)M1);
+  auto al = [](size_t x) { return emip_align_up(x, 1024); };
+  size_t need = 0, t;
+  t = al((size_t)B * 128 * 2 * Pp * 2);                                              // G: Bt = f1 rows
+  need = t > need ? t : need;
+  t = al((size_t)B * O * Pp * 2 * 2) + al((size_t)B * 9 * 128 * 2 * Pp * 2);         // (i): A = dout, Bt = X9
+  need = t > need ? t : need;
+  t = al((size_t)B * 9 * 128 * Ko * 2 * 2) + al((size_t)B * P * 2 * Ko * 2);         // (ii): A = G^T, Bt = dout token-major
+  need = t > need ? t : need;
+  t = al(M1 * Kb * 2 * 2) + al((size_t)P * 2 * Kb * 2);                              // (iii)
+  need = t > need ? t : need;
+  t = al(Kb * Km * 2 * 2) + al((size_t)P * 2 * Km * 2);                              // (iv)
+  need = t > need ? t : need;
+  return need;
+}
+size_t f1_carve(char* base, int B, int O, int P, F1Bufs* f) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += emip_align_up(bytes, 1024); return p; };
+  const size_t M1 = (size_t)O * 9;
+  F1Bufs t;
+  t.g = reinterpret_cast<float*>(take((size_t)B * M1 * 128 * 4));
+  t.dg = reinterpret_cast<float*>(take((size_t)B * M1 * 128 * 4));
+  t.dx9 = reinterpret_cast<float*>(take((size_t)B * 9 * 128 * P * 4));
+  t.dwp = reinterpret_cast<float*>(take(M1 * P * 4));
+  t.ops_bytes = f1_ops_bytes(B, O, P);
+  t.ops = take(t.ops_bytes);
+  if (f) *f = t;
+  return off;
+}
+
+// y[b][m][n] = sum_k A(b or shared)[m][k] Bt[b][n][k] on already split operands
+int f1_gemm(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, size_t a_ld, int a_batched, const __nv_bfloat16* bt, int M, int N,
+            int Kp, int batch, float* y, long long y_stride_b, int ldy, cudaStream_t st) {
+  CUtensorMap ma_hi, ma_lo, mb;
+  int rc;
+  const cuuint64_t adims[3] = {(cuuint64_t)Kp, (cuuint64_t)M, (cuuint64_t)(a_batched ? batch : 1)};
+  const cuuint64_t astr[2] = {(cuuint64_t)a_ld * 2, (cuuint64_t)M * a_ld * 2};
+  const cuuint32_t abox[3] = {KCH, TM, 1};
+  if ((rc = gemm_tc_make_map(&ma_hi, a_hi, 3, adims, astr, abox))) return rc;
+  if ((rc = gemm_tc_make_map(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
+  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)N, (cuuint64_t)batch};
+  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)N * 2 * Kp * 2};
+  const cuuint32_t bbox[3] = {KCH, TM, 1};
+  if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  GemmTcParams p = {};
+  p.mode = 2; p.M = M; p.n_mtiles = (M + TM - 1) / TM; p.n_ntiles = (N + TM - 1) / TM; p.n_tile = TM;
+  p.kchunks = Kp / KCH;
+  p.a_batched = a_batched; p.Kp = Kp; p.N = N;
+  p.y = y; p.y_stride_b = y_stride_b; p.ldy = ldy;
+  return gemm_tc_launch(ma_hi, ma_lo, mb, p, batch, st);
+}
+}  // namespace
+
+size_t conv_corr_bwd_scratch_bytes(int B, int O, int P) { return f1_carve(nullptr, B, O, P, nullptr); }
+
+int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, const void* w_prep, long long w_prep_ld,
+                     const float* dout, float* df0, float* df1, float* dweight, float* dbias, void* scratch, size_t scratch_bytes,
+                     int B, int H, int W, int O, cudaStream_t st) {
+  const int P = H * W, M1 = O * 9, Pp = kpad(P), Ko = kpad(O), Kb = 128 * B, Km = kpad(M1);
+  const float s = 1.0f / sqrtf(128.0f);
+  if (scratch == nullptr || scratch_bytes < conv_corr_bwd_scratch_bytes(B, O, P) || reinterpret_cast<uintptr_t>(scratch) % 1024 != 0) {
+    emip_set_error("conv_corr_bwd: scratch too small or not 1024-byte aligned");
+    return EMIP_ENOMEM;
+  }
+  if (P % 4 != 0) { emip_set_error("conv_corr_bwd: H * W must be a multiple of 4"); return EMIP_ENOSYS; }
+  F1Bufs f;
+  f1_carve(static_cast<char*>(scratch), B, O, P, &f);
+  auto al = [](size_t x) { return emip_align_up(x, 1024); };
+  int rc;
+  if (dbias != nullptr) {
+    f1_dbias_kernel<<<O, 256, 0, st>>>(dout, dbias, B, O, P);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dbias)");
+  }
+  // ---- G = s Wp f1^T  (A = the prepared weight of the forward, K-major over j)
+  {
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    split_rows_kernel<<<dim3((Pp + 2047) / 2048, 128, B), 256, 0, st>>>(f1, (long long)128 * P, P, nullptr, nullptr, nullptr, nullptr, bt,
+                                                                        128, P, Pp);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (f1 rows)");
+    const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(w_prep);
+    const __nv_bfloat16* w_lo = w_hi + (size_t)M1 * w_prep_ld;
+    // the prepared weight has P valid columns per row (pitch w_prep_ld): columns >= P of the last K chunk are zero-filled
+    // by TMA only if the map says so -- describe exactly P columns
+    CUtensorMap ma_hi, ma_lo, mb;
+    const cuuint64_t adims[3] = {(cuuint64_t)P, (cuuint64_t)M1, 1}, astr[2] = {(cuuint64_t)w_prep_ld * 2, (cuuint64_t)M1 * w_prep_ld * 2};
+    const cuuint32_t abox[3] = {KCH, TM, 1};
+    if ((rc = gemm_tc_make_map(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
+    if ((rc = gemm_tc_make_map(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
+    const cuuint64_t bdims[3] = {(cuuint64_t)2 * Pp, 128, (cuuint64_t)B}, bstr[2] = {(cuuint64_t)2 * Pp * 2, (cuuint64_t)128 * 2 * Pp * 2};
+    const cuuint32_t bbox[3] = {KCH, TM, 1};
+    if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+    GemmTcParams p = {};
+    p.mode = 2; p.M = M1; p.n_mtiles = (M1 + TM - 1) / TM; p.n_ntiles = 1; p.n_tile = TM;
+    p.kchunks = Pp / KCH;
+    p.a_batched = 0; p.Kp = Pp; p.N = 128;
+    p.y = f.g; p.y_stride_b = (long long)M1 * 128; p.ldy = 128;
+    if ((rc = gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st))) return rc;      // G / s: the scale is applied by its consumer
+  }
+  // ---- (i) dG[b] = dout[b] X9[b]^T
+  {
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    __nv_bfloat16* a_lo = a_hi + (size_t)B * O * Pp;
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)B * O * Pp * 2 * 2));
+    split_w_kernel<<<dim3((Pp + 2047) / 2048, O, B), 256, 0, st>>>(dout, (long long)O * P, P, 0, a_hi, a_lo, O, P, Pp);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dout rows)");
+    f1_im2col_split_kernel<<<dim3((Pp + 2047) / 2048, 9 * 128, B), 256, 0, st>>>(f0, bt, H, W, Pp);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (im2col)");
+    if ((rc = f1_gemm(a_hi, a_lo, Pp, 1, bt, O, 9 * 128, Pp, B, f.dg, (long long)M1 * 128, 9 * 128, st))) return rc;
+  }
+  // ---- (ii) dX9[b] = G[b]^T dout[b];  df0 = col2im
+  {
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    __nv_bfloat16* a_lo = a_hi + (size_t)B * 9 * 128 * Ko;
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)B * 9 * 128 * Ko * 2 * 2));
+    split_w_kernel<<<dim3((Ko + 2047) / 2048, 9 * 128, B), 256, 0, st>>>(f.g, (long long)M1 * 128, 9 * 128, 1, a_hi, a_lo, 9 * 128, O, Ko);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (G^T)");
+    split_act_kernel<<<dim3((P + 127) / 128, Ko / 32, B), 128, 0, st>>>(dout, (long long)O * P, P, nullptr, nullptr, nullptr, nullptr, bt, O,
+                                                                        Ko, P);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dout tokens)");
+    if ((rc = f1_gemm(a_hi, a_lo, Ko, 1, bt, 9 * 128, P, Ko, B, f.dx9, (long long)9 * 128 * P, P, st))) return rc;
+    f1_col2im_kernel<<<dim3((P + 255) / 256, 128, B), 256, 0, st>>>(f.dx9, df0, H, W, s);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (col2im)");
+  }
+  // ---- (iii) dWp = s sum_(b,c) dG f1
+  {
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    __nv_bfloat16* a_lo = a_hi + (size_t)M1 * Kb;
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)M1 * Kb * 2 * 2));
+    f1_gather_split_kernel<<<dim3((M1 + 7) / 8, B), 128, 0, st>>>(f.dg, a_hi, a_lo, B, M1, s);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dG gather)");
+    split_act_kernel<<<dim3((P + 127) / 128, Kb / 32, 1), 128, 0, st>>>(f1, 0, P, nullptr, nullptr, nullptr, nullptr, bt, Kb, Kb, P);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (f1 tokens)");
+    if ((rc = f1_gemm(a_hi, a_lo, Kb, 0, bt, M1, P, Kb, 1, f.dwp, 0, P, st))) return rc;
+    f1_dweight_permute_kernel<<<dim3((P + 255) / 256, O), 256, 0, st>>>(f.dwp, dweight, O, P);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dweight)");
+  }
+  // ---- (iv) df1 = s sum_(o,t) dG^T Wp
+  {
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    __nv_bfloat16* a_lo = a_hi + (size_t)Kb * Km;
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)Kb * Km * 2 * 2));
+    split_w_kernel<<<dim3((Km + 2047) / 2048, 128, B), 256, 0, st>>>(f.dg, (long long)M1 * 128, 128, 1, a_hi, a_lo, 128, M1, Km);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dG^T)");
+    f1_weight_t_split_kernel<<<dim3((Km + 2047) / 2048, P), 256, 0, st>>>(weight, bt, O, P, Km, s);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (weight^T)");
+    if ((rc = f1_gemm(a_hi, a_lo, Km, 0, bt, Kb, P, Km, 1, df1, 0, P, st))) return rc;
+  }
+  return EMIP_OK;
+}

@@ -52,3 +52,10 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 bool gemm_nt_tc_supported(const GemmNT& a);
 size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N);
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// f1 backward (gemm_tc.cu): df0, df1 [B][128][H*W], dweight [O][H*W][3][3], dbias [O] (may be NULL) from dout [B][O][H*W];
+// w_prep = the forward's prepared weight (hi | lo rows of pitch w_prep_ld); scratch 1024-byte aligned
+size_t conv_corr_bwd_scratch_bytes(int B, int O, int P);
+int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, const void* w_prep, long long w_prep_ld,
+                     const float* dout, float* df0, float* df1, float* dweight, float* dbias, void* scratch, size_t scratch_bytes,
+                     int B, int H, int W, int O, cudaStream_t st);

@@ -208,6 +208,14 @@ size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O);
 int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
                        void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream);
 
+/* Backward of emip_conv_corr_fwd on the tensor cores: df0, df1 [B,C,H,W], dweight [O,H*W,3,3], dbias [O] (NULL = not
+ * wanted) from dout [B,O,H,W]; weight = the fp32 parameter, w_prep = its prepared copy.  Five split-bf16 GEMMs
+ * (csrc/gemm_tc.cu); workspace of emip_conv_corr_bwd_workspace() bytes, 1024-byte aligned. */
+size_t emip_conv_corr_bwd_workspace(int B, int C, int H, int W, int O);
+int emip_conv_corr_bwd(const float* f0, const float* f1, const float* weight, const void* w_prep, const float* dout, float* df0,
+                       float* df1, float* dweight, float* dbias, void* workspace, size_t ws_bytes, int B, int C, int H, int W,
+                       int O, void* stream);
+
 /* ---- f3, second half: photometric term of the unsupervised flow loss, fused -------- */
 /* Replaces loss/loss_flow.py:35-49 unFlowLoss.loss_photomatric(im1_scaled, im1_recons, occu_mask1) with
  * loss/loss_blocks.py:46-65 SSIM (3x3, no padding), w_ternary = 0:

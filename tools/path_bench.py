@@ -290,6 +290,17 @@ def main():
         with torch.no_grad():
             return conv_corr_first_layer(f0, f1, wq, bq)
     ms_f = gpu_time(f1_fwd, iters=10)
+    wqg, bqg = wq.clone().requires_grad_(True), bq.clone().requires_grad_(True)
+    wof = torch.randn(16, Of, H, W, device=dev, generator=g)
+
+    def f1_fwd_bwd():
+        f0, f1 = sets[it[0] % 4]
+        it[0] += 1
+        a, b = f0.detach().requires_grad_(True), f1.detach().requires_grad_(True)
+        conv_corr_first_layer(a, b, wqg, bqg).backward(wof)
+        wqg.grad = None
+        bqg.grad = None
+    ms_f1fb = gpu_time(f1_fwd_bwd, iters=5)
     cf = None
     if not args.no_cpu:
         c0, c1, cwq, cbq = sets[0][0][:1].cpu(), sets[0][1][:1].cpu(), wq.cpu(), bq.cpu()     # bounded sample: 1 of 16
@@ -299,10 +310,10 @@ def main():
                 O.conv_corr_first_layer(c0, c1, cwq, cbq)
         cf = cpu_time(c_f) * 16
     fl = 16 * 2.0 * (Of * 9 * N * C + Of * N * 9 * C)
-    add("f1 conv_corr[0] on the never-materialised cost volume, B=16 (968 out channels)", 16, "pairs", ms_f, None, fl, 0,
+    add("f1 conv_corr[0] on the never-materialised cost volume, B=16 (968 out channels)", 16, "pairs", ms_f, ms_f1fb - ms_f, fl, 2.5 * fl,
         16 * (2 * C * N * 4 + Of * N * 4), 0, "tensor", cf, None,
         "two split-bf16 tcgen05 GEMMs (8.6 GFLOP/sample) instead of a 65.3 GFLOP/sample convolution over corr; "
-        "CPU = the reference composition (matmul + conv2d on corr), sample = 1 pair x 16; backward = library matmuls")
+        "CPU = the reference composition (matmul + conv2d on corr), sample = 1 pair x 16; backward = five split-bf16 tcgen05 GEMMs (tools/f1_bwd_time.py)")
 
     # ---------------- f3: occlusion mask, f4: convex upsampling ----------------
     from emip_b200.warp import get_occu_mask_backward
