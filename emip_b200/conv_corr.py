@@ -6,10 +6,9 @@ tensor of matching.py:16-20.  ``conv_corr_first_layer(f0, f1, weight, bias)`` re
 forming ``corr``: two per-sample tensor-core GEMMs on the feature maps (csrc/conv_corr.cu).
 
 Training: the backward pass runs on the tensor cores too (``emip_conv_corr_bwd``: five split-bf16 GEMMs on the same
-re-association; ``_reassociated_torch`` states it with library ops and is what the tests compare the gradients with).
+re-association; ``oracle.restate.conv_corr_reassociated`` states it with library ops for the tests).
 """
 import ctypes
-import math
 import weakref
 
 import torch
@@ -39,16 +38,6 @@ def _prepared_weight(weight):
     _prepared[key] = (weakref.ref(weight, lambda _r, k=key: _prepared.pop(k, None)), weight._version, weight.device, buf, p,
                       weight.data_ptr())
     return buf, p
-
-
-def _reassociated_torch(f0, f1, weight, bias):
-    """The same re-association with library ops (autograd-capable): G = W . f1 / sqrt(C); out = conv3x3(f0; G_b)."""
-    B, C, H, W = f0.shape
-    O = weight.shape[0]
-    g = torch.einsum("ojt,bcj->botc", weight.reshape(O, H * W, 9), f1.reshape(B, C, H * W)) / math.sqrt(C)   # [B,O,9,C]
-    wb = g.permute(0, 1, 3, 2).reshape(B * O, C, 3, 3)
-    out = F.conv2d(f0.reshape(1, B * C, H, W), wb, None, padding=1, groups=B).reshape(B, O, H, W)
-    return out if bias is None else out + bias.view(1, O, 1, 1)
 
 
 class _ConvCorr(torch.autograd.Function):

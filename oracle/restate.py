@@ -285,6 +285,17 @@ def conv_corr_first_layer(feature0, feature1, weight, bias=None):
     return torch.nn.functional.conv2d(corr, weight, bias, stride=1, padding=1)
 
 
+def conv_corr_reassociated(f0, f1, weight, bias):
+    """The re-association the CUDA path (csrc/conv_corr.cu, csrc/gemm_tc.cu) computes, stated with library ops:
+    G[b][(o,t)][c] = sum_j W[o,j,t] f1[b,c,j] / sqrt(C);  out = conv3x3(f0[b]; G[b]) -- equal to conv_corr_first_layer."""
+    B, C, H, W = f0.shape
+    O = weight.shape[0]
+    g = torch.einsum("ojt,bcj->botc", weight.reshape(O, H * W, 9), f1.reshape(B, C, H * W)) / (C ** 0.5)   # [B,O,9,C]
+    wb = g.permute(0, 1, 3, 2).reshape(B * O, C, 3, 3)
+    out = torch.nn.functional.conv2d(f0.reshape(1, B * C, H, W), wb, None, padding=1, groups=B).reshape(B, O, H, W)
+    return out if bias is None else out + bias.view(1, O, 1, 1)
+
+
 def ssim_distance(x, y):
     """clamp((1 - SSIM) / 2, 0, 1) with 3x3 mean filters and no padding.  Reference: loss/loss_blocks.py:46-65 (md = 1)."""
     pool = lambda t: torch.nn.functional.avg_pool2d(t, 3, 1, 0)

@@ -160,12 +160,11 @@ def test_f1_conv_corr_first_layer(golden, name):
     g = golden(name)
     d = cases.f1_inputs(cases.F1_CASES[name])
     cases.check_packed(O.conv_corr_first_layer(d["f0"], d["f1"], d["weight"], d["bias"]), g["out"], TOL, "out")
-    from emip_b200.conv_corr import _reassociated_torch
     f0 = d["f0"].clone().requires_grad_(True)
     f1 = d["f1"].clone().requires_grad_(True)
     w = d["weight"].clone().requires_grad_(True)
     b = d["bias"].clone().requires_grad_(True)
-    out = _reassociated_torch(f0, f1, w, b)
+    out = O.conv_corr_reassociated(f0, f1, w, b)
     cases.check_packed(out, g["out"], 1e-5, "re-associated out")
     (out * d["wout"]).sum().backward()
     cases.check_packed(f0.grad, g["df0"], 1e-5, "df0")
