@@ -6,7 +6,7 @@ tensor of matching.py:16-20.  ``conv_corr_first_layer(f0, f1, weight, bias)`` re
 forming ``corr``: two per-sample tensor-core GEMMs on the feature maps (csrc/conv_corr.cu).
 
 Training: the backward pass runs on the tensor cores too (``emip_conv_corr_bwd``: five split-bf16 GEMMs on the same
-re-association; ``oracle.restate.conv_corr_reassociated`` states it with library ops for the tests).
+re-association, csrc/gemm_tc.cu ``conv_corr_bwd_tc``).
 """
 import ctypes
 import weakref
