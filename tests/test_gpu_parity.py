@@ -627,3 +627,19 @@ def test_a5_memory_read_backward_tc_vs_exact():
         grads[exact] = {k: v.grad.clone() for k, v in t.items()}
     for k in ("m_in", "m_out", "q_in", "q_out"):
         assert rel(grads[False][k], grads[True][k]) < 1e-4, (k, rel(grads[False][k], grads[True][k]))
+
+
+def test_f1_backward_tc_no_bias_single_sample_vs_fp64():
+    """f1 backward (five tensor-core GEMMs) without a bias and with B = 1, against fp64 autograd through the
+    materialised cost volume (the reference's formulation)."""
+    from emip_b200.conv_corr import conv_corr_first_layer
+    B, C, H, W, Oc = 1, 128, 12, 20, 72
+    f0, f1 = cases.randn(201, (B, C, H, W), 2.0), cases.randn(202, (B, C, H, W), 2.0)
+    w = cases.randn(203, (Oc, H * W, 3, 3), (9 * H * W) ** -0.5)
+    wo = cases.randn(204, (B, Oc, H, W))
+    a, b_, c = (t.double().requires_grad_(True) for t in (f0, f1, w))
+    O.conv_corr_first_layer(a, b_, c, None).backward(wo.double())
+    ga, gb, gc = (dev(t).requires_grad_(True) for t in (f0, f1, w))
+    conv_corr_first_layer(ga, gb, gc, None).backward(dev(wo))
+    for name, x, y in (("df0", ga.grad, a.grad), ("df1", gb.grad, b_.grad), ("dw", gc.grad, c.grad)):
+        assert rel(x, y) < 1e-4, (name, rel(x, y))
