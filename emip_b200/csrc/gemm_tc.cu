@@ -75,6 +75,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // f1 channel-major [b][256 = hi c | lo c][ld]: rows 0..127 hi, 128..255 lo
           tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, 0, b);
           tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), kc * KCH, 128, b);
+        } else if (p.mode == 2 && p.b_mn) {
+          // B as it lies in memory, [k rows][n contiguous] (hi | lo per row, lo at column Np): two {64 n x 64 k} boxes
+          // per operand half = the MN-major SW128 layout (tc_common.cuh), no token-major copy of the activations
+          const int ab = p.a_batched ? b : 0;
+          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, ab);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_load_3d(sa + 2 * A_BYTES + h * 8192, &map_b, full(stage), nt * TM + h * 64, kc * KCH, b);
+            tma_load_3d(sa + 2 * A_BYTES + p.b_bytes + h * 8192, &map_b, full(stage), p.Np + nt * TM + h * 64, kc * KCH, b);
+          }
         } else if (p.mode == 2) {
           const int ab = p.a_batched ? b : 0;
           tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
@@ -111,6 +122,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (leader) {
         const uint32_t sa = sbase + stage * p.stage_bytes;
         const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_BYTES);
+        if (p.b_mn) {
+          // MN-major B: a K16 step = two 8-row groups = 2 KB down the box; the second 64 columns 8 KB further (LBO)
+          const uint64_t b_hi = make_mnmajor_sw128_desc(sa + 2 * A_BYTES, 8192), b_lo = make_mnmajor_sw128_desc(sa + 2 * A_BYTES + p.b_bytes, 8192);
+          const uint32_t idesc_mn = idesc | (1u << 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 128 * k, idesc_mn, (kc | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 128 * k, idesc_mn, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 128 * k, idesc_mn, 1u);
+        } else {
         const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_BYTES), b_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + p.b_bytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc | k) ? 1u : 0u);
@@ -118,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        }
         umma_commit(empty(stage));
         if (kc == p.kchunks - 1) umma_commit(acc_full(acc));
       }
@@ -411,8 +434,8 @@ bool gemm_nn_tc_supported(const GemmNN& a) {
 }
 
 size_t gemm_nn_tc_scratch_bytes(int B, int M, int K, int N, bool per_sample_w) {
-  const size_t Kp = (size_t)kpad(K);
-  return emip_align_up((size_t)(per_sample_w ? B : 1) * M * Kp * 2 * 2, 1024) + emip_align_up((size_t)B * N * 2 * Kp * 2, 1024) + 1024;
+  const size_t Kp = (size_t)kpad(K), Np = (size_t)kpad(N);
+  return emip_align_up((size_t)(per_sample_w ? B : 1) * M * Kp * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
 }
 
 int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -430,8 +453,12 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)nbw * a.M * Kp * 2 * 2, 1024));
   split_w_kernel<<<dim3((Kp + 2047) / 2048, a.M, nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, a.w_trans, w_hi, w_lo, a.M, a.K, Kp);
   EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
-  split_act_kernel<<<dim3((a.N + 127) / 128, Kp / 32, a.B), 128, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta,
-                                                                        bt, a.K, Kp, a.N);
+  // the activations keep their channel-major layout ([k][n], hi | lo per row): elementwise split (with the LayerNorm
+  // applied on the way), read by the GEMM as an MN-major operand.  (r1 / r2a re-laid them out token-major with
+  // split_act_kernel: 64-byte store segments, 200 us of the Injector's forward + backward.)
+  const int Np = kpad(a.N);
+  split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta, bt,
+                                                                    a.K, a.N, Np);
   EMIP_CHECK_LAUNCH("gemm_nn_tc (activations)");
   CUtensorMap ma_hi, ma_lo, mb;
   int rc;
@@ -440,13 +467,14 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   const cuuint32_t abox[3] = {KCH, TM, 1};
   if ((rc = gemm_tc_make_map(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
   if ((rc = gemm_tc_make_map(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
-  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)a.N, (cuuint64_t)a.B};
-  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)a.N * 2 * Kp * 2};
-  const cuuint32_t bbox[3] = {KCH, TM, 1};
+  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Np, (cuuint64_t)a.K, (cuuint64_t)a.B};
+  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)a.K * 2 * Np * 2};
+  const cuuint32_t bbox[3] = {64, 64, 1};
   if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
   GemmTcParams p = {};
   p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.N + TM - 1) / TM; p.n_tile = TM;
   p.kchunks = Kp / KCH;
+  p.b_mn = 1; p.Np = Np;
   p.a_batched = per_sample ? 1 : 0; p.Kp = Kp; p.N = a.N;
   p.y = a.y; p.y_stride_b = a.y_stride_b; p.ldy = a.ldy;
   p.res = a.res; p.res_stride_b = a.res_stride_b; p.ldr = a.ldr;

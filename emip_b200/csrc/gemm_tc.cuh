@@ -27,6 +27,7 @@ struct GemmTcParams {
   // mode 2: y[b][m][n] = sum_k A(b)[m][k] Bt[b][n][k] (+ res): A = weights (shared: a_batched = 0), Bt = token-major
   // activations [B][N][2*Kp] (hi | lo); y / res rows are ldy / ldr floats apart
   int a_batched, Kp, N;
+  int b_mn, Np;             // b_mn: Bt is [B][K][2*Np] (k rows, n contiguous, hi | lo) and is read as an MN-major operand
   float* y; long long y_stride_b; int ldy;
   const float* res; long long res_stride_b; int ldr;
 };
