@@ -326,45 +326,6 @@ split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int t
   split8_store(v, hi + o, lo + o);
 }
 
-// activations x[b][k][n] fp32 (rows ldx apart), optional LayerNorm over k -> token-major bf16 [b][n][2*Kp] (hi | lo)
-// One thread = one token x 32 channels (lanes = consecutive tokens: coalesced reads; 64-byte hi and lo segments out).
-__global__ void __launch_bounds__(128)
-split_act_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, const float* __restrict__ mean,
-                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ dst, int K, int Kp, int N) {
-  const int b = blockIdx.z, chunk = blockIdx.y;
-  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= N) return;
-  const float* s = x + (size_t)b * x_stride_b + (size_t)chunk * 32 * ldx + tok;
-  float mu = 0.f, rs = 1.f;
-  if (mean != nullptr) { mu = __ldg(mean + (size_t)b * N + tok); rs = __ldg(rstd + (size_t)b * N + tok); }
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int k = chunk * 32 + i;
-    float t = k < K ? __ldg(s + (size_t)i * ldx) : 0.f;
-    if (mean != nullptr && k < K) t = (t - mu) * rs * __ldg(gamma + k) + __ldg(beta + k);
-    v[i] = t;
-  }
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
-    const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
-                                                 __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-  }
-  uint4* dh = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + chunk * 32);
-  uint4* dl = reinterpret_cast<uint4*>(dst + ((size_t)b * N + tok) * 2 * Kp + Kp + chunk * 32);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-    dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-  }
-}
-
 // B'(b)[k][n] fp32 (rows ldb apart), optional LayerNorm over k -> bf16 [b][k][2*Np] (hi | lo), zero padded to Np.
 // grid (ceil(Np / 2048), K, B): 8 consecutive n per thread.
 __global__ void __launch_bounds__(256)
@@ -455,7 +416,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
   // the activations keep their channel-major layout ([k][n], hi | lo per row): elementwise split (with the LayerNorm
   // applied on the way), read by the GEMM as an MN-major operand.  (r1 / r2a re-laid them out token-major with
-  // split_act_kernel: 64-byte store segments, 200 us of the Injector's forward + backward.)
+  // a transposing kernel: 64-byte store segments, 200 us of the Injector's forward + backward.)
   const int Np = kpad(a.N);
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta, bt,
                                                                     a.K, a.N, Np);
@@ -635,6 +596,7 @@ f1_dweight_permute_kernel(const float* __restrict__ dwp, float* __restrict__ dw,
 
 struct F1Bufs {
   float *g, *dg, *dx9, *dwp;
+  __nv_bfloat16 *dsp, *fsp;   // dout and f1 split once as rows [.][row][hi | lo over the pixel axis] (pitch 2 Pp)
   char* ops;        // operand scratch, reused by every GEMM
   size_t ops_bytes;
 };
@@ -663,6 +625,8 @@ size_t f1_carve(char* base, int B, int O, int P, F1Bufs* f) {
   t.dg = reinterpret_cast<float*>(take((size_t)B * M1 * 128 * 4));
   t.dx9 = reinterpret_cast<float*>(take((size_t)B * 9 * 128 * P * 4));
   t.dwp = reinterpret_cast<float*>(take(M1 * P * 4));
+  t.dsp = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * O * 2 * kpad(P) * 2));
+  t.fsp = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 128 * 2 * kpad(P) * 2));
   t.ops_bytes = f1_ops_bytes(B, O, P);
   t.ops = take(t.ops_bytes);
   if (f) *f = t;
@@ -670,8 +634,9 @@ size_t f1_carve(char* base, int B, int O, int P, F1Bufs* f) {
 }
 
 // y[b][m][n] = sum_k A(b or shared)[m][k] Bt[b][n][k] on already split operands
+// b_mn: bt is [batch][K rows][2 * Np] (n contiguous) and is read as an MN-major operand; else [batch][N][2 * Kp]
 int f1_gemm(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, size_t a_ld, int a_batched, const __nv_bfloat16* bt, int M, int N,
-            int Kp, int batch, float* y, long long y_stride_b, int ldy, cudaStream_t st) {
+            int Kp, int batch, float* y, long long y_stride_b, int ldy, cudaStream_t st, int b_mn = 0, int Krows = 0, int Np = 0) {
   CUtensorMap ma_hi, ma_lo, mb;
   int rc;
   const cuuint64_t adims[3] = {(cuuint64_t)Kp, (cuuint64_t)M, (cuuint64_t)(a_batched ? batch : 1)};
@@ -679,14 +644,22 @@ int f1_gemm(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, size_t a_ld, i
   const cuuint32_t abox[3] = {KCH, TM, 1};
   if ((rc = gemm_tc_make_map(&ma_hi, a_hi, 3, adims, astr, abox))) return rc;
   if ((rc = gemm_tc_make_map(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
-  const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)N, (cuuint64_t)batch};
-  const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)N * 2 * Kp * 2};
-  const cuuint32_t bbox[3] = {KCH, TM, 1};
-  if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  if (b_mn) {
+    const cuuint64_t bdims[3] = {(cuuint64_t)2 * Np, (cuuint64_t)Krows, (cuuint64_t)batch};
+    const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)Krows * 2 * Np * 2};
+    const cuuint32_t bbox[3] = {64, 64, 1};
+    if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  } else {
+    const cuuint64_t bdims[3] = {(cuuint64_t)2 * Kp, (cuuint64_t)N, (cuuint64_t)batch};
+    const cuuint64_t bstr[2] = {(cuuint64_t)2 * Kp * 2, (cuuint64_t)N * 2 * Kp * 2};
+    const cuuint32_t bbox[3] = {KCH, TM, 1};
+    if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
+  }
   GemmTcParams p = {};
   p.mode = 2; p.M = M; p.n_mtiles = (M + TM - 1) / TM; p.n_ntiles = (N + TM - 1) / TM; p.n_tile = TM;
   p.kchunks = Kp / KCH;
   p.a_batched = a_batched; p.Kp = Kp; p.N = N;
+  p.b_mn = b_mn; p.Np = Np;
   p.y = y; p.y_stride_b = y_stride_b; p.ldy = ldy;
   return gemm_tc_launch(ma_hi, ma_lo, mb, p, batch, st);
 }
@@ -714,10 +687,15 @@ int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, cons
   }
   // ---- G = s Wp f1^T  (A = the prepared weight of the forward, K-major over j)
   {
-    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops);
+    // f1 and dout are split ONCE, as rows over the pixel axis: f1 rows are the K-major B operand of G and the MN-major B
+    // operand of (iii); dout rows are the K-major A operand of (i) and the MN-major B operand of (ii)
+    __nv_bfloat16* bt = f.fsp;
     split_rows_kernel<<<dim3((Pp + 2047) / 2048, 128, B), 256, 0, st>>>(f1, (long long)128 * P, P, nullptr, nullptr, nullptr, nullptr, bt,
                                                                         128, P, Pp);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (f1 rows)");
+    split_rows_kernel<<<dim3((Pp + 2047) / 2048, O, B), 256, 0, st>>>(dout, (long long)O * P, P, nullptr, nullptr, nullptr, nullptr, f.dsp,
+                                                                      O, P, Pp);
+    EMIP_CHECK_LAUNCH("conv_corr_bwd (dout rows)");
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(w_prep);
     const __nv_bfloat16* w_lo = w_hi + (size_t)M1 * w_prep_ld;
     // the prepared weight has P valid columns per row (pitch w_prep_ld): columns >= P of the last K chunk are zero-filled
@@ -739,26 +717,18 @@ int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, cons
   }
   // ---- (i) dG[b] = dout[b] X9[b]^T
   {
-    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
-    __nv_bfloat16* a_lo = a_hi + (size_t)B * O * Pp;
-    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)B * O * Pp * 2 * 2));
-    split_w_kernel<<<dim3((Pp + 2047) / 2048, O, B), 256, 0, st>>>(dout, (long long)O * P, P, 0, a_hi, a_lo, O, P, Pp);
-    EMIP_CHECK_LAUNCH("conv_corr_bwd (dout rows)");
+    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops);
     f1_im2col_split_kernel<<<dim3((Pp + 2047) / 2048, 9 * 128, B), 256, 0, st>>>(f0, bt, H, W, Pp);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (im2col)");
-    if ((rc = f1_gemm(a_hi, a_lo, Pp, 1, bt, O, 9 * 128, Pp, B, f.dg, (long long)M1 * 128, 9 * 128, st))) return rc;
+    if ((rc = f1_gemm(f.dsp, f.dsp + Pp, 2 * (size_t)Pp, 1, bt, O, 9 * 128, Pp, B, f.dg, (long long)M1 * 128, 9 * 128, st))) return rc;
   }
   // ---- (ii) dX9[b] = G[b]^T dout[b];  df0 = col2im
   {
     __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
     __nv_bfloat16* a_lo = a_hi + (size_t)B * 9 * 128 * Ko;
-    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)B * 9 * 128 * Ko * 2 * 2));
     split_w_kernel<<<dim3((Ko + 2047) / 2048, 9 * 128, B), 256, 0, st>>>(f.g, (long long)M1 * 128, 9 * 128, 1, a_hi, a_lo, 9 * 128, O, Ko);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (G^T)");
-    split_act_kernel<<<dim3((P + 127) / 128, Ko / 32, B), 128, 0, st>>>(dout, (long long)O * P, P, nullptr, nullptr, nullptr, nullptr, bt, O,
-                                                                        Ko, P);
-    EMIP_CHECK_LAUNCH("conv_corr_bwd (dout tokens)");
-    if ((rc = f1_gemm(a_hi, a_lo, Ko, 1, bt, 9 * 128, P, Ko, B, f.dx9, (long long)9 * 128 * P, P, st))) return rc;
+    if ((rc = f1_gemm(a_hi, a_lo, Ko, 1, f.dsp, 9 * 128, P, Ko, B, f.dx9, (long long)9 * 128 * P, P, st, 1, O, Pp))) return rc;
     f1_col2im_kernel<<<dim3((P + 255) / 256, 128, B), 256, 0, st>>>(f.dx9, df0, H, W, s);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (col2im)");
   }
@@ -766,12 +736,9 @@ int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, cons
   {
     __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
     __nv_bfloat16* a_lo = a_hi + (size_t)M1 * Kb;
-    __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)M1 * Kb * 2 * 2));
     f1_gather_split_kernel<<<dim3((M1 + 7) / 8, B), 128, 0, st>>>(f.dg, a_hi, a_lo, B, M1, s);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (dG gather)");
-    split_act_kernel<<<dim3((P + 127) / 128, Kb / 32, 1), 128, 0, st>>>(f1, 0, P, nullptr, nullptr, nullptr, nullptr, bt, Kb, Kb, P);
-    EMIP_CHECK_LAUNCH("conv_corr_bwd (f1 tokens)");
-    if ((rc = f1_gemm(a_hi, a_lo, Kb, 0, bt, M1, P, Kb, 1, f.dwp, 0, P, st))) return rc;
+    if ((rc = f1_gemm(a_hi, a_lo, Kb, 0, f.fsp, M1, P, Kb, 1, f.dwp, 0, P, st, 1, Kb, Pp))) return rc;
     f1_dweight_permute_kernel<<<dim3((P + 255) / 256, O), 256, 0, st>>>(f.dwp, dweight, O, P);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (dweight)");
   }
