@@ -87,11 +87,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_3d(sa + 2 * A_BYTES + p.b_bytes + h * 8192, &map_b, full(stage), p.Np + nt * TM + h * 64, kc * KCH, b);
           }
         } else if (p.mode == 2) {
-          const int ab = p.a_batched ? b : 0;
-          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
-          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, ab);
-          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), kc * KCH, nt * TM, b);
-          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + kc * KCH, nt * TM, b);
+          // ksplit > 1: batch entry b = (sample, K split): the split walks its own kchunks chunks of the contraction
+          // axis and writes its own partial (K chunks past the operands are zero-filled by TMA on the A side)
+          const int ks = p.ksplit > 1 ? p.ksplit : 1, bs = b / ks, k0 = (b - bs * ks) * p.kchunks + kc;
+          const int ab = p.a_batched ? bs : 0;
+          tma_load_3d(sa, &map_a_hi, full(stage), k0 * KCH, mt * TM, ab);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), k0 * KCH, mt * TM, ab);
+          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), k0 * KCH, nt * TM, bs);
+          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + k0 * KCH, nt * TM, bs);
         } else {
           tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
           tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
@@ -453,7 +456,7 @@ size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N) {
   return emip_align_up((size_t)B * M * Np * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
 }
 
-int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit) {
   if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
   if (!gemm_nt_tc_supported(a)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
   if (scratch == nullptr || scratch_bytes < gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N)) {
@@ -483,10 +486,12 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
   GemmTcParams p = {};
   p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.K + TM - 1) / TM; p.n_tile = TM;
-  p.kchunks = Np / KCH;
+  const int ns = nsplit > 1 ? nsplit : 1;
+  p.kchunks = (Np / KCH + ns - 1) / ns;                  // per split; partial (b, s) is matrix b * ns + s of c
+  p.ksplit = ns;
   p.a_batched = 1; p.Kp = Np; p.N = a.K;
   p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
-  return gemm_tc_launch(ma_hi, ma_lo, mb, p, a.B, st);
+  return gemm_tc_launch(ma_hi, ma_lo, mb, p, a.B * ns, st);
 }
 
 // =====================================================================================================================

@@ -27,6 +27,7 @@ struct GemmTcParams {
   // mode 2: y[b][m][n] = sum_k A(b)[m][k] Bt[b][n][k] (+ res): A = weights (shared: a_batched = 0), Bt = token-major
   // activations [B][N][2*Kp] (hi | lo); y / res rows are ldy / ldr floats apart
   int a_batched, Kp, N;
+  int ksplit;               // mode 2, K-major B: > 1 = the batch index is (sample, K split), kchunks = chunks per split
   int b_mn, Np;             // b_mn: Bt is [B][K][2*Np] (k rows, n contiguous, hi | lo) and is read as an MN-major operand
   float* y; long long y_stride_b; int ldy;
   const float* res; long long res_stride_b; int ldr;
@@ -52,7 +53,9 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 // c[b][m][k] = sum_n A(b)[m][n] * B'(b)[k][n] -- the arguments of gemm_nt (one result per batch entry, no N split).
 bool gemm_nt_tc_supported(const GemmNT& a);
 size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N);
-int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
+// nsplit > 1: the contraction axis is dealt to nsplit CTAs per tile; c then holds B * nsplit partial matrices
+// (c_stride_b apart, partial (b, s) at index b * nsplit + s) for the caller's batch reduction
+int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit = 1);
 
 // f1 backward (gemm_tc.cu): df0, df1 [B][128][H*W], dweight [O][H*W][3][3], dbias [O] (may be NULL) from dout [B][O][H*W];
 // w_prep = the forward's prepared weight (hi | lo rows of pitch w_prep_ld); scratch 1024-byte aligned

@@ -1224,12 +1224,21 @@ int gemm_nn(const GemmNN& a, cudaStream_t st) {
 }
 // nsplit partial results per batch entry: c must hold B*nsplit matrices (c_stride_b apart)
 // pixel-axis splits of a weight-gradient GEMM: the tensor-core path produces one partial per batch entry
-static int nt_split(int B, int M, int K) { return g_tc.ws != nullptr ? 1 : nt_split_simt(B, M, K); }
+// tensor-core path: enough K splits to give every SM a tile (r2d: one partial per sample left the weight-gradient
+// GEMMs on 16-96 CTAs for 27-30 us each); never more than the CUDA-core path's count, which sizes the partial buffer
+static int nt_split(int B, int M, int K) {
+  const int simt = nt_split_simt(B, M, K);
+  if (g_tc.ws == nullptr) return simt;
+  const int tiles = B * ((M + 127) / 128) * ((K + 127) / 128);
+  int s = emip_num_sms() / tiles;
+  s = s < 1 ? 1 : (s > 8 ? 8 : s);
+  return s < simt ? s : simt;
+}
 
 static int gemm_nt_split(const GemmNT& a, int nsplit, cudaStream_t st) {
   if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
-  if (nsplit == 1 && g_tc.ws != nullptr && gemm_nt_tc_supported(a) && g_tc.bytes >= gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N))
-    return gemm_nt_tc(a, g_tc.ws, g_tc.bytes, st);
+  if (g_tc.ws != nullptr && gemm_nt_tc_supported(a) && g_tc.bytes >= gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N))
+    return gemm_nt_tc(a, g_tc.ws, g_tc.bytes, st, nsplit);
   GemmNTk p;
   p.g = a;
   p.nsplit = nsplit;
