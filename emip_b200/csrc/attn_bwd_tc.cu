@@ -311,23 +311,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         rL = __ldg(p.lse + si) * LOG2E;
         rD = __ldg(p.dsum + si);
       }
+      // per-column L log2(e) / D of key tile kt, one value per thread (threads 0..255); fetched one tile ahead so that
+      // the global-load latency is not paid between the two barriers below
+      auto col_stat = [&](int kt) -> float {
+        float v = 0.f;
+        if (!row_stats && threadIdx.x < 2 * TN && kt < ke) {
+          const int k = threadIdx.x / TN, col = kt * TN + threadIdx.x % TN;
+          if (col < p.nc) {
+            const size_t si = p.win.enabled ? p.win.pixel(prob, col) : (size_t)prob * p.nc + col;
+            if (k == 0) v = __ldg(p.lse + si) * LOG2E;
+            else if (has_dp) v = __ldg(p.dsum + si);
+          }
+        }
+        return v;
+      };
+      float stat_next = col_stat(kb);
       for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int col_base = kt * TN;
         const long long cA = PROF ? clock64() : 0;
         if (!row_stats) {
-          // per-column L log2(e) and D of this tile -> smem (single buffer: every warp has finished the previous tile)
+          // this tile's table -> smem (single buffer: every warp has finished the previous tile)
           asm volatile("bar.sync 1, %0;" ::"n"(NMATH * 32) : "memory");
-          if (threadIdx.x < 2 * TN) {
-            const int k = threadIdx.x / TN, c = threadIdx.x % TN, col = col_base + c;
-            float v = 0.f;
-            if (col < p.nc) {
-              const size_t si = p.win.enabled ? p.win.pixel(prob, col) : (size_t)prob * p.nc + col;
-              if (k == 0) v = __ldg(p.lse + si) * LOG2E;
-              else if (has_dp) v = __ldg(p.dsum + si);
-            }
-            tab[threadIdx.x] = v;
-          }
+          if (threadIdx.x < 2 * TN) tab[threadIdx.x] = stat_next;
           asm volatile("bar.sync 1, %0;" ::"n"(NMATH * 32) : "memory");
+          stat_next = col_stat(kt + 1);
         }
         if (PROF) t_tab += clock64() - cA;
         prof_add<PROF>(w_sf, mbar_wait(s_full, tile & 1));
