@@ -2,7 +2,7 @@
 // Replaces reference model/EMIP_short/motion/gmflow/transformer.py:526-532
 // (scores = q k^T / sqrt(C); softmax; prob @ flow) and its autograd backward
 // (value = flow.detach(), gmflow.py:137, so only dq and dk exist).  The two
-// nn.Linear projections (transformer.py:523-524) stay library GEMMs on the host side.
+// projections (transformer.py:523-524) are linear_cn.cu; q and k then arrive channel-major (EMIP_FLAG_CHANNEL_MAJOR).
 #include "common.cuh"
 #include "../../include/emip_b200.h"
 #include "pair_common.cuh"
@@ -30,6 +30,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
   }
   if (B == 0) return EMIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const int lay = (flags & EMIP_FLAG_CHANNEL_MAJOR) ? EMIP_LAYOUT_CN : EMIP_LAYOUT_NC;      // layout of q and k
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
     size_t sb = match_tc_split_bytes(B, N, C);
     const size_t sk_off = d_bytes(B, N) + 2 * sb + pair_bwd_tc_chn_bytes(2 * B, N), sk_bytes = match_tc_streamk_bytes(B, N, N);
@@ -39,8 +40,8 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
     }
     char* p = static_cast<char*>(workspace) + d_bytes(B, N);
     int rc;
-    if ((rc = match_tc_split(q, nullptr, p, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
-    if ((rc = match_tc_split(k, nullptr, p + sb, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
+    if ((rc = match_tc_split(q, nullptr, p, B, N, C, lay, 0, st))) return rc;
+    if ((rc = match_tc_split(k, nullptr, p + sb, B, N, C, lay, 0, st))) return rc;
     MatchTcArgs a = {};
     a.x_split = p; a.y_split = p + sb; a.nbx = B; a.nby = B;
     a.v = v; a.v_stride_b = 2LL * N; a.grid_w = 0; a.sub_grid = 0;
@@ -55,7 +56,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
   a.x = q; a.y = k; a.v = v; a.v_stride_b = 2LL * N; a.sub = nullptr;
   a.out = out; a.lse = lse; a.s_out = nullptr;
   a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0;
-  a.x_layout = a.y_layout = EMIP_LAYOUT_NC;
+  a.x_layout = a.y_layout = lay;
   a.sqrt_c = sqrtf((float)C);                       // transformer.py:528
   return pair_fwd_simt(a, st);
 }
@@ -75,6 +76,7 @@ extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v
     return EMIP_ENOMEM;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int lay = (flags & EMIP_FLAG_CHANNEL_MAJOR) ? EMIP_LAYOUT_CN : EMIP_LAYOUT_NC;      // layout of q, k, dq, dk
   float* D = static_cast<float*>(workspace);      // D_i = dO_i . O_i
   int rc;
   if ((rc = launch_rowdot2(dout, out, nullptr, D, B, N, st))) return rc;
@@ -86,11 +88,11 @@ extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v
     }
     char* tok = static_cast<char*>(workspace) + d_bytes(B, N);        // [q batches | k batches] token-major
     char* chn = tok + 2 * sb;
-    if ((rc = match_tc_split(q, k, tok, B, N, C, EMIP_LAYOUT_NC, 0, st))) return rc;
-    if ((rc = pair_bwd_tc_split_chn(q, k, chn, B, N, EMIP_LAYOUT_NC, st))) return rc;
+    if ((rc = match_tc_split(q, k, tok, B, N, C, lay, 0, st))) return rc;
+    if ((rc = pair_bwd_tc_split_chn(q, k, chn, B, N, lay, st))) return rc;
     PairBwdTcArgs t = {};
     t.tok_split = tok; t.tok_split_y = tok; t.chn_split_y = chn; t.n_split = 2 * B;
-    t.nb = B; t.nr = N; t.nc = N; t.dx_layout = EMIP_LAYOUT_NC; t.sqrt_c = sqrtf((float)C);
+    t.nb = B; t.nr = N; t.nc = N; t.dx_layout = lay; t.sqrt_c = sqrtf((float)C);
     // dq_i = sum_j P_ij (dO_i.v_j - D_i) k_j / sqrt(C)
     t.x_base = 0; t.y_base = B; t.dx = dq;
     t.l1 = lse; t.u = dout; t.u0 = D; t.t = v; t.t_stride_b = 2LL * N;
@@ -103,7 +105,7 @@ extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v
   }
   PairBwdArgs a = {};
   a.nb = B; a.nr = N; a.nc = N;
-  a.x_layout = a.y_layout = a.dx_layout = EMIP_LAYOUT_NC;
+  a.x_layout = a.y_layout = a.dx_layout = lay;
   a.sqrt_c = sqrtf((float)C);
   // dq_i = sum_j P_ij (dO_i.v_j - D_i) k_j / sqrt(C)
   a.x = q; a.y = k; a.dx = dq;

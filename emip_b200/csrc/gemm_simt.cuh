@@ -17,6 +17,7 @@ struct GemmNN {
   float* y; long long y_stride_b; int ldy;
   int B, M, K, N;
   int accumulate;                                                                  // y += instead of y =
+  const float* bias;                                                               // NULL or [M]: added per output row (tensor-core path only)
 };
 int gemm_nn(const GemmNN& a, cudaStream_t st);
 

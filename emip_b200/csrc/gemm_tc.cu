@@ -194,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int n0 = nt * TM;
       float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
       const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
+      const float rb = (p.bias != nullptr && row < p.M) ? __ldg(p.bias + row) : 0.f;      // per-row bias (linear layers)
       for (int c0 = 0; c0 < TM; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
@@ -204,8 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float4* d = reinterpret_cast<float4*>(o + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                     __uint_as_float(r[4 * i + 3]));
+              float4 v = make_float4(__uint_as_float(r[4 * i]) + rb, __uint_as_float(r[4 * i + 1]) + rb, __uint_as_float(r[4 * i + 2]) + rb,
+                                     __uint_as_float(r[4 * i + 3]) + rb);
               if (rs) {
                 const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
                 v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
@@ -215,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + (rs ? __ldg(rs + c0 + i) : 0.f);
+              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + rb + (rs ? __ldg(rs + c0 + i) : 0.f);
           }
         }
       }
@@ -439,6 +440,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.N + TM - 1) / TM; p.n_tile = TM;
   p.kchunks = Kp / KCH;
   p.b_mn = 1; p.Np = Np;
+  p.bias = a.bias;
   p.a_batched = per_sample ? 1 : 0; p.Kp = Kp; p.N = a.N;
   p.y = a.y; p.y_stride_b = a.y_stride_b; p.ldy = a.ldy;
   p.res = a.res; p.res_stride_b = a.res_stride_b; p.ldr = a.ldr;

@@ -44,6 +44,7 @@ extern "C" {
 
 #define EMIP_FLAG_BF16 4            /* bf16 inference mode: single-pass bf16 operands (no hi/lo split), fp32 accumulate and
                                        fp32 softmax; results within the 2e-2 tolerance instead of 1e-3 */
+#define EMIP_FLAG_CHANNEL_MAJOR 8  /* flow_attn_fwd / _bwd: q, k (and dq, dk) are channel-major [B,C,N] instead of [B,N,C] */
 
 /* ---- plumbing ------------------------------------------------------------ */
 const char* emip_last_error(void);
@@ -102,7 +103,7 @@ int emip_global_matching_bwd(const float* f0, const float* f1, const float* flow
 /* ---- a2: flow-propagation attention -------------------------------------- */
 /* Replaces the attention core of FeatureFlowAttention.forward,
  * model/EMIP_short/motion/gmflow/transformer.py:526-532: out = softmax(q k^T / sqrt(C)) v.
- *   q, k  [B,N,C] token-major, already projected (transformer.py:523-524 stay library GEMMs)
+ *   q, k  [B,N,C] token-major ([B,C,N] with EMIP_FLAG_CHANNEL_MAJOR), already projected (emip_linear_cn_fwd)
  *   v     [B,2,N]  (the flow viewed as [B,2,H*W])      out [B,2,N]
  *   lse   NULL or [B,N] (needed by the backward) */
 size_t emip_flow_attn_workspace(int B, int N, int C);
@@ -112,6 +113,15 @@ int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* ou
 int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
                        const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes, int B, int N,
                        int C, int flags, void* stream);
+
+/* The two projections of FeatureFlowAttention (transformer.py:523-524) on the feature map as it lies in memory:
+ * y[b][m][n] = sum_k w[m][k] x[b][k][n] + bias[m], x [B,K,N], y [B,M,N] (channel-major), w [M,K] as nn.Linear stores it.
+ * Forward and backward are split-bf16 tensor-core GEMMs; dw / db may be NULL (frozen weights).  M, K <= 1024, N % 4 == 0. */
+size_t emip_linear_cn_workspace(int B, int M, int K, int N);
+int emip_linear_cn_fwd(const float* x, const float* w, const float* bias, float* y, void* workspace, size_t ws_bytes, int B, int M,
+                       int K, int N, void* stream);
+int emip_linear_cn_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, void* workspace,
+                       size_t ws_bytes, int B, int M, int K, int N, void* stream);
 
 /* ---- a4: prompt fusion (camouflaged feeder / motion collector) ---------------------------------- */
 /* Replaces model/EMIP_short/motion/PromptInteract.py:452-464 Injector.forward(image_embeddings, flow)
