@@ -242,11 +242,16 @@ def main():
         for ev in step_done:
             ev.record(stream)
         e2e_loop(4)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_loop(Ke)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        # the loop is paced by the host (PCIe copies + one host read per step): a single pass of Ke steps swings by
+        # +-25 % with other activity on the box, so three passes are timed and the MEDIAN is reported
+        reps = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            e2e_loop(Ke)
+            torch.cuda.synchronize()
+            reps.append(time.perf_counter() - t0)
+        e2e_s = sorted(reps)[1]
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -259,7 +264,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(world), "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke},
+                "steps": Ke, "passes": 3, "stat": "median of the passes"},
         "gpu_launches": 2 * K,     # per step: operand split pre-pass + fused tcgen05 matching kernel
     }
 
