@@ -363,6 +363,28 @@ split_chn_kernel(const float* __restrict__ src, const float* __restrict__ src2, 
   __nv_bfloat16* d = dst + (size_t)b * 256 * ld;
   if (layout == EMIP_LAYOUT_CN) {
     const int c = blockIdx.y;
+    if ((n & 7) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+      // eight consecutive keys per thread: two 128-bit loads, one 128-bit store each for the hi and the lo row
+      // (the scalar loop below wrote 2-byte elements: 61 us for the 63 MB of an a2 backward)
+      for (int k = (blockIdx.x * blockDim.x + threadIdx.x) * 8; k < n; k += gridDim.x * blockDim.x * 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(s + (size_t)c * n + k));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(s + (size_t)c * n + k + 4));
+        const float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+          const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+          const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
+                                                        __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
+          h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(d + (size_t)c * ld + k) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + (size_t)(128 + c) * ld + k) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      return;
+    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
       const float v = __ldg(s + (size_t)c * n + k);
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
