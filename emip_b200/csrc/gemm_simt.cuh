@@ -29,6 +29,7 @@ struct GemmNT {
   const float* mean; const float* rstd; const float* gamma; const float* beta;
   float* c; long long c_stride_b; int ldc;
   int B, M, K, N;
+  int a_act;                                                                       // 1: exact GELU applied to A on load (tensor-core path only)
 };
 int gemm_nt(const GemmNT& a, cudaStream_t st);
 

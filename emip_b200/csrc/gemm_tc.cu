@@ -309,7 +309,7 @@ __device__ __forceinline__ void split8_store(const float (&v)[8], __nv_bfloat16*
 // grid (ceil(Kp / 2048), M, nbw): one row per blockIdx.y, 8 consecutive k per thread.
 __global__ void __launch_bounds__(256)
 split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int trans, __nv_bfloat16* __restrict__ hi,
-               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp) {
+               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp, int act = 0) {
   const int b = blockIdx.z, m = blockIdx.y;
   const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (k0 >= Kp) return;
@@ -325,6 +325,10 @@ split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int t
       const int k = k0 + i;
       v[i] = k < K ? __ldg(src + (trans ? (size_t)k * ldw + m : (size_t)m * ldw + k)) : 0.f;
     }
+  }
+  if (act == 1) {                                   // exact GELU (nn.GELU default): 0.5 x (1 + erf(x / sqrt 2))
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752440f));
   }
   const size_t o = ((size_t)b * M + m) * Kp + k0;
   split8_store(v, hi + o, lo + o);
@@ -470,7 +474,7 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* a_lo = a_hi + (size_t)a.B * a.M * Np;
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)a.B * a.M * Np * 2 * 2, 1024));
-  split_w_kernel<<<dim3((Np + 2047) / 2048, a.M, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np);
+  split_w_kernel<<<dim3((Np + 2047) / 2048, a.M, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act);
   EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,
                                                                     a.K, a.N, Np);

@@ -1,0 +1,139 @@
+// Token-major layers of the GMFlow FeatureTransformer blocks on the tensor cores (the part that is not
+// the attention core): reference model/EMIP_short/motion/gmflow/transformer.py:108-196, TransformerLayer.
+//   * the six bias-free nn.Linear layers of a block (q / k / v / merge: 128 -> 128, mlp: 256 -> 1024 -> 128) applied to
+//     [L, K] token rows (L = 2B * 1936):  y[l][m] = sum_k act(x[l][k]) w[m][k].  Both operands are K-major as they lie
+//     in memory (tokens x channels; nn.Linear stores [out][in]), so the GEMM only needs the elementwise bf16 hi | lo
+//     split (gemm_tc.cu, mode 2: three UMMAs per tile, fp32 accumulation in TMEM).  The exact GELU between the two MLP
+//     layers (transformer.py:145) is applied inside the operand split of the second layer: the activated [L, 1024]
+//     tensor never exists in fp32.
+//   * EMIP_LINEAR_W_TRANS: the same contraction against w^T -- the gradient with respect to the input rows (the GMFlow
+//     weights are frozen, train.py:340-342, but gradients pass through to the prompt-fusion outputs).
+//   * LayerNorm(128) over the channel axis with the residual add of transformer.py:176 folded in, one warp per token
+//     row (values stay in registers: one 16-byte load per lane), forward and backward.
+#include "common.cuh"
+#include "../../include/emip_b200.h"
+#include "gemm_tc.cuh"
+
+namespace {
+// wt[k][m] = w[m][k]  (the weights are at most 1 MB: 32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wt, int M, int K) {
+  __shared__ float t[32][33];
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (m0 + r < M && k0 + tx < K) t[r][tx] = __ldg(w + (size_t)(m0 + r) * K + k0 + tx);
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (k0 + r < K && m0 + tx < M) wt[(size_t)(k0 + r) * M + m0 + tx] = t[tx][r];
+}
+
+size_t wt_bytes(int M, int K) { return emip_align_up((size_t)M * K * sizeof(float), 1024); }
+bool shape_ok(int L, int M, int K) { return L >= 0 && M >= 1 && M % 4 == 0 && K >= 16 && K % 4 == 0 && M <= 4096 && K <= 4096; }
+
+// y[l][:] = (res ? res[l][:] : 0) + LN(x[l][:]) * gamma + beta, 128 channels: one warp per row, 8 rows per block
+__global__ void __launch_bounds__(256)
+ln128_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ res, float* __restrict__ y, int L, float eps) {
+  const int lane = threadIdx.x & 31;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane), be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  for (int l = blockIdx.x * 8 + (threadIdx.x >> 5); l < L; l += gridDim.x * 8) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)l * 128) + lane);
+    const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
+    const float rstd = rsqrtf(var + eps);
+    float4 o = make_float4(a * rstd * g.x + be.x, b * rstd * g.y + be.y, c * rstd * g.z + be.z, d * rstd * g.w + be.w);
+    if (res != nullptr) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(res + (size_t)l * 128) + lane);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    reinterpret_cast<float4*>(y + (size_t)l * 128)[lane] = o;
+  }
+}
+
+// dx[l][:] = rstd (g - mean(g) - xhat mean(g xhat)),  g = dy gamma  (statistics recomputed from x: 512 B per row)
+__global__ void __launch_bounds__(256)
+ln128_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy,
+                 float* __restrict__ dx, int L, float eps) {
+  const int lane = threadIdx.x & 31;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  for (int l = blockIdx.x * 8 + (threadIdx.x >> 5); l < L; l += gridDim.x * 8) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)l * 128) + lane);
+    const float4 u = __ldg(reinterpret_cast<const float4*>(dy + (size_t)l * 128) + lane);
+    const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+    float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
+    const float rstd = rsqrtf(var + eps);
+    a *= rstd; b *= rstd; c *= rstd; d *= rstd;
+    const float ga = u.x * g.x, gb = u.y * g.y, gc = u.z * g.z, gd = u.w * g.w;
+    const float m1 = warp_sum((ga + gb) + (gc + gd)) * (1.f / 128.f);
+    const float m2 = warp_sum((ga * a + gb * b) + (gc * c + gd * d)) * (1.f / 128.f);
+    reinterpret_cast<float4*>(dx + (size_t)l * 128)[lane] =
+        make_float4(rstd * (ga - m1 - a * m2), rstd * (gb - m1 - b * m2), rstd * (gc - m1 - c * m2), rstd * (gd - m1 - d * m2));
+  }
+}
+}  // namespace
+
+extern "C" size_t emip_linear_tm_workspace(int L, int M, int K) {
+  if (!shape_ok(L, M, K)) return 0;
+  const size_t a = gemm_nt_tc_scratch_bytes(1, L, M, K), b = gemm_nt_tc_scratch_bytes(1, L, K, M);
+  return emip_align_up(a > b ? a : b, 1024) + wt_bytes(M, K);
+}
+
+// y [L][M] = act(x [L][K]) w^T, w [M][K];   EMIP_LINEAR_W_TRANS: y [L][K] = act(x [L][M]) w
+extern "C" int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K,
+                                  int flags, void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && w && y && workspace, "linear_tm_fwd: null pointer");
+  EMIP_CHECK_ARG((flags & ~(EMIP_LINEAR_GELU_IN | EMIP_LINEAR_W_TRANS)) == 0, "linear_tm_fwd: unknown flag");
+  if (!shape_ok(L, M, K)) { emip_set_error("linear_tm_fwd: unsupported shape L=%d M=%d K=%d", L, M, K); return EMIP_ENOSYS; }
+  if (ws_bytes < emip_linear_tm_workspace(L, M, K)) { emip_set_error("linear_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "linear_tm_fwd: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t scratch_bytes = ws_bytes - wt_bytes(M, K);
+  const bool trans = (flags & EMIP_LINEAR_W_TRANS) != 0;
+  const float* wb = w;
+  if (trans) {
+    float* wt = reinterpret_cast<float*>(static_cast<char*>(workspace) + scratch_bytes);
+    transpose_w_kernel<<<dim3((K + 31) / 32, (M + 31) / 32), 256, 0, st>>>(w, wt, M, K);
+    EMIP_CHECK_LAUNCH("linear_tm_fwd (transpose)");
+    wb = wt;
+  }
+  const int out = trans ? K : M, in = trans ? M : K;
+  GemmNT t = {};
+  t.B = 1; t.M = L; t.K = out; t.N = in;
+  t.a = x; t.a_stride_b = 0; t.lda = in;
+  t.bm = wb; t.b_stride_b = 0; t.ldb = in;
+  t.c = y; t.c_stride_b = 0; t.ldc = out;
+  t.a_act = (flags & EMIP_LINEAR_GELU_IN) ? 1 : 0;
+  if (!gemm_nt_tc_supported(t)) { emip_set_error("linear_tm_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
+  return gemm_nt_tc(t, workspace, scratch_bytes, st, 1);
+}
+
+extern "C" int emip_layernorm_tm_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int L,
+                                     int C, float eps, void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && gamma && beta && y && L > 0, "layernorm_tm_fwd: null pointer");
+  if (C != 128) { emip_set_error("layernorm_tm_fwd: C=%d (only the FeatureTransformer width 128 is built)", C); return EMIP_ENOSYS; }
+  EMIP_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res) |
+                   reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+                 "layernorm_tm_fwd: pointers must be 16-byte aligned");
+  const int blocks = (L + 7) / 8, cap = emip_num_sms() * 8;
+  ln128_fwd_kernel<<<blocks < cap ? blocks : cap, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, res, y, L, eps);
+  EMIP_CHECK_LAUNCH("layernorm_tm_fwd");
+  return EMIP_OK;
+}
+
+extern "C" int emip_layernorm_tm_bwd(const float* x, const float* gamma, const float* dy, float* dx, int L, int C, float eps,
+                                     void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && gamma && dy && dx && L > 0, "layernorm_tm_bwd: null pointer");
+  if (C != 128) { emip_set_error("layernorm_tm_bwd: C=%d (only the FeatureTransformer width 128 is built)", C); return EMIP_ENOSYS; }
+  EMIP_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                   reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, "layernorm_tm_bwd: pointers must be 16-byte aligned");
+  const int blocks = (L + 7) / 8, cap = emip_num_sms() * 8;
+  ln128_bwd_kernel<<<blocks < cap ? blocks : cap, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, dx, L, eps);
+  EMIP_CHECK_LAUNCH("layernorm_tm_bwd");
+  return EMIP_OK;
+}

@@ -1,0 +1,136 @@
+"""Token-major layers of the GMFlow FeatureTransformer blocks (the part around the attention core).
+
+Reference: model/EMIP_short/motion/gmflow/transformer.py:108-196 ``TransformerLayer``.  ``transformer_layer_forward``
+has the signature of ``TransformerLayer.forward`` (:151-158) and reads the reference module's own parameters
+(``q_proj / k_proj / v_proj / merge / norm1 / mlp / norm2``, same ``state_dict`` keys); ``dropin.install`` binds it as
+that method.  Per block it issues
+
+    q / k / v / merge / mlp[0] / mlp[2]   ``emip_linear_tm_fwd``: split-bf16 tensor-core GEMMs on the token rows, the
+                                          exact GELU of mlp[1] applied inside the operand split of mlp[2]
+    attention                             ``emip_window_attention_fwd_tc`` / ``emip_attention_fwd_tc`` (window_attn.py)
+    norm1 / norm2 (+ ``source + ...``)    ``emip_layernorm_tm_fwd``: one warp per token row, residual folded in
+
+The GMFlow weights are frozen (train.py:340-342): the backward returns the gradient of the token rows only and raises
+for a weight that requires a gradient.  There is no CPU or library fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import I, SZ, F, ptr, stream_ptr
+from ._ws import workspace
+from .window_attn import single_head_full_attention, single_head_split_window_attention
+
+GELU_IN = 1
+W_TRANS = 2
+
+
+def _linear_call(x2, w, flags):
+    """x2 [L, in] contiguous fp32 CUDA, w [M, K] -> [L, M] (or [L, K] with W_TRANS)."""
+    L_, M, K = x2.shape[0], w.shape[0], w.shape[1]
+    lib = _lib.lib()
+    lib.emip_linear_tm_workspace.restype = ctypes.c_size_t
+    need = lib.emip_linear_tm_workspace(I(L_), I(M), I(K))
+    if need == 0:
+        raise _lib.EmipError(f"emip_b200 linear_tm: unsupported shape L={L_} M={M} K={K}")
+    ws, ws_ptr, ws_n = workspace(need, x2.device)
+    y = torch.empty((L_, K if flags & W_TRANS else M), dtype=torch.float32, device=x2.device)
+    _lib.check(lib.emip_linear_tm_fwd(ptr(x2), ptr(w), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K), I(flags),
+                                      stream_ptr()), "emip_linear_tm_fwd")
+    return y
+
+
+class _LinearTM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, gelu_in):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("emip_b200 linear_tm: weight gradients are not built (the GMFlow weights are frozen, "
+                                      "train.py:340-342)")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w = w.contiguous()
+        y = _linear_call(x2, w, GELU_IN if gelu_in else 0)
+        ctx.save_for_backward(x2 if gelu_in else None, w)
+        ctx.gelu_in, ctx.in_shape = gelu_in, x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dx = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w, W_TRANS)
+        if ctx.gelu_in:
+            dx = torch.ops.aten.gelu_backward(dx, x2)               # elementwise d GELU(x) / dx on the pre-activation
+        return dx.view(ctx.in_shape), None, None
+
+
+def _check(x, what):
+    if not x.is_cuda:
+        raise _lib.EmipError(f"emip_b200 {what} needs CUDA tensors (no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise TypeError(f"emip_b200 {what} computes from fp32 tensors")
+
+
+def linear_tm(x, weight, gelu_in=False):
+    """``F.linear(gelu(x) if gelu_in else x, weight)`` for [..., K] token rows, bias-free."""
+    _check(x, "linear_tm")
+    _check(weight, "linear_tm")
+    if weight.dim() != 2 or x.shape[-1] != weight.shape[1]:
+        raise ValueError(f"linear_tm: x {tuple(x.shape)} against weight {tuple(weight.shape)}")
+    return _LinearTM.apply(x, weight, bool(gelu_in))
+
+
+class _LayerNormTM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, res):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("emip_b200 layer_norm_tm: affine-parameter gradients are not built (frozen GMFlow)")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        r2 = None if res is None else res.reshape(-1, x.shape[-1]).contiguous()
+        y = torch.empty_like(x2)
+        lib = _lib.lib()
+        _lib.check(lib.emip_layernorm_tm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(r2), ptr(y), I(x2.shape[0]), I(x2.shape[1]),
+                                             F(eps), stream_ptr()), "emip_layernorm_tm_fwd")
+        ctx.save_for_backward(x2, gamma)
+        ctx.eps, ctx.in_shape, ctx.has_res = eps, x.shape, res is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = torch.empty_like(x2)
+        lib = _lib.lib()
+        _lib.check(lib.emip_layernorm_tm_bwd(ptr(x2), ptr(gamma), ptr(dy2), ptr(dx), I(x2.shape[0]), I(x2.shape[1]), F(ctx.eps),
+                                             stream_ptr()), "emip_layernorm_tm_bwd")
+        return dx.view(ctx.in_shape), None, None, None, (dy if ctx.has_res else None)
+
+
+def layer_norm_tm(x, weight, bias, eps=1e-5, residual=None):
+    """``residual + F.layer_norm(x, (C,), weight, bias, eps)`` over the last axis (C = 128)."""
+    _check(x, "layer_norm_tm")
+    if residual is not None and residual.shape != x.shape:
+        raise ValueError("layer_norm_tm: residual shape differs from x")
+    return _LayerNormTM.apply(x, weight.contiguous(), bias.contiguous(), float(eps), residual)
+
+
+def transformer_layer_forward(self, source, target, height=None, width=None, shifted_window_attn_mask=None,
+                              attn_num_splits=None, **kwargs):
+    """``TransformerLayer.forward`` (transformer.py:151-180): source, target [B, L, C] -> [B, L, C]."""
+    query = linear_tm(source, self.q_proj.weight)                          # :163
+    key = linear_tm(target, self.k_proj.weight)                            # :164
+    value = linear_tm(target, self.v_proj.weight)                          # :165
+    if self.attention_type == 'swin' and attn_num_splits > 1:
+        if self.nhead > 1:
+            raise NotImplementedError                                      # as the reference (:168-171)
+        message = single_head_split_window_attention(query, key, value, num_splits=attn_num_splits,
+                                                     with_shift=self.with_shift, h=height, w=width,
+                                                     attn_mask=shifted_window_attn_mask)
+    else:
+        message = single_head_full_attention(query, key, value)
+    message = linear_tm(message, self.merge.weight)                        # :171
+    if self.no_ffn:
+        return layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=source)   # :172, :180
+    message = layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+    hidden = linear_tm(torch.cat([source, message], dim=-1), self.mlp[0].weight)                           # :175
+    message = linear_tm(hidden, self.mlp[2].weight, gelu_in=True)
+    return layer_norm_tm(message, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=source)     # :176, :180

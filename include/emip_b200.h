@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EMIP_ABI_VERSION 2
+#define EMIP_ABI_VERSION 3
 
 #define EMIP_PAD_BORDER 0
 #define EMIP_PAD_ZEROS 1
@@ -122,6 +122,25 @@ int emip_linear_cn_fwd(const float* x, const float* w, const float* bias, float*
                        int K, int N, void* stream);
 int emip_linear_cn_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, void* workspace,
                        size_t ws_bytes, int B, int M, int K, int N, void* stream);
+
+/* ---- f2b: token-major layers of the FeatureTransformer blocks ------------------------------------ */
+/* Replaces the nn.Linear / nn.GELU / nn.LayerNorm calls of TransformerLayer.forward,
+ * model/EMIP_short/motion/gmflow/transformer.py:163-176 (q_proj, k_proj, v_proj :163-165, merge :171, norm1 :172,
+ * mlp = Linear(256,1024) - GELU - Linear(1024,128) :175 (defined :140-146), norm2 :176, residual :180); all six linear
+ * layers are bias-free (:126-131, :143-147).  Rows are tokens: x [L,K], y [L,M], w [M,K] as nn.Linear stores it.
+ *   y[l][m] = sum_k act(x[l][k]) w[m][k]          act = exact GELU with EMIP_LINEAR_GELU_IN, else identity
+ *   EMIP_LINEAR_W_TRANS: x [L,M], y [L,K] = act(x) w  (the input gradient of the layer)
+ * Split-bf16 tensor-core GEMM (three UMMAs, fp32 accumulation).  M % 4 == 0, K % 4 == 0, K >= 16; workspace 1024-byte aligned. */
+#define EMIP_LINEAR_GELU_IN 1
+#define EMIP_LINEAR_W_TRANS 2
+size_t emip_linear_tm_workspace(int L, int M, int K);
+int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K, int flags,
+                       void* stream);
+/* y = (res ? res : 0) + LayerNorm_C(x) * gamma + beta over the channel axis of [L,C] rows (C = 128), biased variance, eps as
+ * nn.LayerNorm; the backward returns dx only (frozen affine parameters), statistics are recomputed from x. */
+int emip_layernorm_tm_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int L, int C,
+                          float eps, void* stream);
+int emip_layernorm_tm_bwd(const float* x, const float* gamma, const float* dy, float* dx, int L, int C, float eps, void* stream);
 
 /* ---- a4: prompt fusion (camouflaged feeder / motion collector) ---------------------------------- */
 /* Replaces model/EMIP_short/motion/PromptInteract.py:452-464 Injector.forward(image_embeddings, flow)

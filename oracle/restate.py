@@ -349,3 +349,24 @@ def split_window_attention(q, k, v, num_splits, with_shift, h, w):
     if with_shift:
         out = torch.roll(out, shifts=(sh, sw), dims=(1, 2))
     return out.reshape(b, h * w, c)
+
+
+def transformer_layer(source, target, p, no_ffn, num_splits, with_shift, h, w, eps=1e-5):
+    """One FeatureTransformer block.  Reference: .../gmflow/transformer.py:151-180 (TransformerLayer.forward) with the
+    layers defined at :126-148: bias-free q / k / v / merge projections, LayerNorm over the 128 channels, and (cross
+    layers) mlp = Linear(256, 1024) - exact GELU - Linear(1024, 128) on cat([source, message]).  source, target [B, L, C];
+    p maps the reference's state_dict keys to tensors."""
+    def ln(x, g, b):
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        return (x - mu) / torch.sqrt(var + eps) * g + b
+
+    q = source @ p["q_proj.weight"].T
+    k = target @ p["k_proj.weight"].T
+    v = target @ p["v_proj.weight"].T
+    msg = split_window_attention(q, k, v, num_splits, with_shift, h, w) @ p["merge.weight"].T
+    msg = ln(msg, p["norm1.weight"], p["norm1.bias"])
+    if not no_ffn:
+        hid = torch.cat([source, msg], -1) @ p["mlp.0.weight"].T
+        msg = ln(_gelu_erf(hid) @ p["mlp.2.weight"].T, p["norm2.weight"], p["norm2.bias"])
+    return source + msg

@@ -144,6 +144,25 @@ def f2_inputs(s):
                 wout=randn(s["seed"] + 3000, shp))
 
 
+# f2b: whole TransformerLayer blocks (transformer.py:108-196): self-attention layer (no_ffn) and cross-attention + FFN layer
+F2B_CASES = {
+    "f2b_small": dict(b=1, c=128, h=16, w=24, k=2, scale=1.0, seed=141),
+    "f2b_full": dict(b=2, c=128, h=44, w=44, k=2, scale=1.0, seed=142),
+}
+
+
+def f2b_inputs(s):
+    c = s["c"]
+    shp = (s["b"], s["h"] * s["w"], c)
+    sd = s["seed"]
+    w = lambda i, o, k: randn(sd + 10 * i, (o, k), k ** -0.5)
+    return dict(source=randn(sd, shp, s["scale"]), target=randn(sd + 1, shp, s["scale"]), wout=randn(sd + 2, shp),
+                params={"q_proj.weight": w(1, c, c) * 2.0, "k_proj.weight": w(2, c, c) * 2.0, "v_proj.weight": w(3, c, c),
+                        "merge.weight": w(4, c, c), "norm1.weight": 1 + 0.1 * randn(sd + 50, (c,)), "norm1.bias": 0.1 * randn(sd + 51, (c,)),
+                        "mlp.0.weight": w(5, 8 * c, 2 * c), "mlp.2.weight": w(6, c, 8 * c),
+                        "norm2.weight": 1 + 0.1 * randn(sd + 52, (c,)), "norm2.bias": 0.1 * randn(sd + 53, (c,))})
+
+
 F3_CASES = {
     "f3_small": dict(b=2, h=9, w=11, sigma=2.0, seed=71),
     "f3_mid": dict(b=2, h=40, w=56, sigma=6.0, seed=72),

@@ -164,6 +164,30 @@ def gen_f2():
         save(name, rec)
 
 
+def gen_f2b():
+    """TransformerLayer.forward (transformer.py:151-180): self-attention layer (no_ffn) and cross-attention + FFN layer, plain and
+    shifted windows, with the gradients of the two token tensors."""
+    import model.EMIP_short.motion.gmflow.transformer as T
+    for name, s in cases.F2B_CASES.items():
+        d = cases.f2b_inputs(s)
+        full = name.endswith("full")
+        rec = dict(spec=s)
+        wh, ww = s["h"] // s["k"], s["w"] // s["k"]
+        mask = T.generate_shift_window_attn_mask((s["h"], s["w"]), wh, ww, wh // 2, ww // 2, device=torch.device("cpu"))
+        for no_ffn in (True, False):
+            for shift in (False, True):
+                m = T.TransformerLayer(d_model=s["c"], nhead=1, attention_type="swin", no_ffn=no_ffn, ffn_dim_expansion=4,
+                                       with_shift=shift)
+                m.load_state_dict({k: v for k, v in d["params"].items() if not (no_ffn and (k.startswith("mlp") or k.startswith("norm2")))},
+                                  strict=False)
+                src, tgt = d["source"].clone().requires_grad_(True), d["target"].clone().requires_grad_(True)
+                out = m(src, tgt, height=s["h"], width=s["w"], shifted_window_attn_mask=mask, attn_num_splits=s["k"])
+                (out * d["wout"]).sum().backward()
+                tag = ("self" if no_ffn else "cross") + ("_shift" if shift else "_plain")
+                rec[tag] = dict(out=cases.pack(out.detach(), full), dsource=cases.pack(src.grad, full), dtarget=cases.pack(tgt.grad, full))
+        save(name, rec)
+
+
 def gen_f3b():
     """unFlowLoss.loss_photomatric (loss_flow.py:35-49) with gradients to the reconstruction."""
     from loss.loss_flow import unFlowLoss
@@ -225,6 +249,6 @@ def gen_c1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f3", "f3b", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f2b", "f3", "f3b", "f4", "c1"]
     for w in which:
         globals()["gen_" + w]()

@@ -643,3 +643,79 @@ def test_f1_backward_tc_no_bias_single_sample_vs_fp64():
     conv_corr_first_layer(ga, gb, gc, None).backward(dev(wo))
     for name, x, y in (("df0", ga.grad, a.grad), ("df1", gb.grad, b_.grad), ("dw", gc.grad, c.grad)):
         assert rel(x, y) < 1e-4, (name, rel(x, y))
+
+
+# ----------------------------------------------------------------------------- f2b (token-major layers of the blocks)
+class _Layer(torch.nn.Module):
+    """Same submodules / state_dict keys as the reference TransformerLayer (transformer.py:126-148), frozen as train.py:340-342."""
+
+    def __init__(self, params, no_ffn, with_shift, c=128):
+        super().__init__()
+        nn = torch.nn
+        self.attention_type, self.nhead, self.no_ffn, self.with_shift = "swin", 1, no_ffn, with_shift
+        self.q_proj, self.k_proj, self.v_proj, self.merge = (nn.Linear(c, c, bias=False) for _ in range(4))
+        self.norm1 = nn.LayerNorm(c)
+        if not no_ffn:
+            self.mlp = nn.Sequential(nn.Linear(2 * c, 8 * c, bias=False), nn.GELU(), nn.Linear(8 * c, c, bias=False))
+            self.norm2 = nn.LayerNorm(c)
+        self.load_state_dict({k: v for k, v in params.items() if k in self.state_dict()})
+        self.requires_grad_(False).cuda()
+
+
+@pytest.mark.parametrize("name", list(cases.F2B_CASES))
+def test_f2b_transformer_layer_golden(golden, name):
+    from emip_b200.transformer_layer import transformer_layer_forward
+    g = golden(name)
+    s = cases.F2B_CASES[name]
+    d = cases.f2b_inputs(s)
+    mask = torch.zeros(1, device="cuda")
+    for no_ffn in (True, False):
+        for shift in (False, True):
+            tag = ("self" if no_ffn else "cross") + ("_shift" if shift else "_plain")
+            layer = _Layer(d["params"], no_ffn, shift)
+            src, tgt = dev(d["source"]).requires_grad_(True), dev(d["target"]).requires_grad_(True)
+            out = transformer_layer_forward(layer, src, tgt, height=s["h"], width=s["w"], shifted_window_attn_mask=mask,
+                                            attn_num_splits=s["k"])
+            e = cases.check_packed(out, g[tag]["out"], TOL_EXACT, tag + " out")
+            (out * dev(d["wout"])).sum().backward()
+            cases.check_packed(src.grad, g[tag]["dsource"], TOL_GRAD, tag + " dsource")
+            cases.check_packed(tgt.grad, g[tag]["dtarget"], TOL_GRAD, tag + " dtarget")
+            print(f"{name} {tag}: out rel-L2 {e:.2e}")
+
+
+@pytest.mark.parametrize("L,M,K,gelu", [(1936, 128, 128, False), (777, 1024, 256, False), (1000, 128, 1024, True), (5, 36, 20, True)])
+def test_f2b_linear_tm_vs_fp64(L, M, K, gelu):
+    """Token-major bias-free linear layer (ragged row counts, non-multiple-of-64 widths, GELU on load), forward and
+    input gradient, against fp64."""
+    from emip_b200.transformer_layer import linear_tm
+    x, w, wo = cases.randn(301, (L, K), 1.5), cases.randn(302, (M, K), K ** -0.5), cases.randn(303, (L, M))
+    xd = x.double().requires_grad_(True)
+    ref = (O._gelu_erf(xd) if gelu else xd) @ w.double().T
+    ref.backward(wo.double())
+    xg = dev(x).requires_grad_(True)
+    out = linear_tm(xg, dev(w), gelu_in=gelu)
+    out.backward(dev(wo))
+    assert rel(out, ref) < TOL_EXACT, rel(out, ref)
+    assert rel(xg.grad, xd.grad) < TOL_EXACT, rel(xg.grad, xd.grad)
+
+
+def test_f2b_layer_norm_tm_vs_fp64_and_errors():
+    from emip_b200.transformer_layer import layer_norm_tm, linear_tm
+    from emip_b200._lib import EmipError
+    L = 1001
+    x, r, g, b, wo = (cases.randn(311 + i, shp) for i, shp in enumerate(((L, 128), (L, 128), (128,), (128,), (L, 128))))
+    x = x * 3 + 0.5
+    xd, rd = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    ref = rd + torch.nn.functional.layer_norm(xd, (128,), g.double(), b.double(), 1e-5)
+    ref.backward(wo.double())
+    xg, rg = dev(x).requires_grad_(True), dev(r).requires_grad_(True)
+    out = layer_norm_tm(xg, dev(g), dev(b), 1e-5, residual=rg)
+    out.backward(dev(wo))
+    assert rel(out, ref) < 1e-6 and rel(xg.grad, xd.grad) < 1e-5 and torch.equal(rg.grad.cpu(), wo)
+    assert layer_norm_tm(dev(x)[:0], dev(g), dev(b)).shape == (0, 128)
+    with pytest.raises(EmipError):
+        layer_norm_tm(dev(x)[:, :64].contiguous(), dev(g)[:64], dev(b)[:64])         # only C = 128 is built
+    with pytest.raises(EmipError):
+        linear_tm(x, g.view(1, 128))                                                  # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        linear_tm(dev(x), dev(r)[:128].clone().requires_grad_(True))                  # frozen weights only

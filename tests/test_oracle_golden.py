@@ -207,3 +207,21 @@ def test_f2_split_window_attention(golden, name):
                 p = torch.softmax(qb @ kb.transpose(1, 2) / c ** 0.5, -1)
                 dec[:, r0:r1, c0:c1] = (p @ vb).view(b, r1 - r0, c1 - c0, c)
         cases.check_packed(dec.view(b, h * w, c).float(), g[tag]["out"], TOL, tag + " blocks")
+
+
+@pytest.mark.parametrize("name", list(cases.F2B_CASES))
+def test_f2b_transformer_layer(golden, name):
+    """The oracle restatement of TransformerLayer.forward (self-attention and cross-attention + FFN blocks, plain and
+    shifted windows) against vectors recorded from the reference, with the gradients of the token rows."""
+    g = golden(name)
+    s = cases.F2B_CASES[name]
+    d = cases.f2b_inputs(s)
+    for no_ffn in (True, False):
+        for shift in (False, True):
+            tag = ("self" if no_ffn else "cross") + ("_shift" if shift else "_plain")
+            src, tgt = d["source"].clone().requires_grad_(True), d["target"].clone().requires_grad_(True)
+            out = O.transformer_layer(src, tgt, d["params"], no_ffn, s["k"], shift, s["h"], s["w"])
+            cases.check_packed(out, g[tag]["out"], TOL, tag)
+            (out * d["wout"]).sum().backward()
+            cases.check_packed(src.grad, g[tag]["dsource"], GTOL, tag + " dsource")
+            cases.check_packed(tgt.grad, g[tag]["dtarget"], GTOL, tag + " dtarget")
