@@ -11,6 +11,7 @@ unchanged (same signatures, same ``state_dict`` keys):
     model.EMIP_long.LTM.Memory                                             (constructed at LTM.py:90)
     loss.warp_utils.flow_warp / loss.loss_flow.flow_warp                   (called at loss_flow.py:90-91)
     model.EMIP_short.motion.gmflow.gmflow.GMFlow.upsample_flow             (method, called at gmflow.py:131,148)
+    model.EMIP_short.motion.gmflow.transformer.TransformerLayer.forward    (method, called at transformer.py:205-209, 476-480)
 
 Call it after the reference root is on ``sys.path`` and before the model is constructed.  ``uninstall()`` restores
 the originals (used by the tests).
@@ -81,6 +82,19 @@ def install(strict=False):
             _saved[key] = gm.GMFlow.upsample_flow
         gm.GMFlow.upsample_flow = upsample_flow
         done.append("model.EMIP_short.motion.gmflow.gmflow.GMFlow.upsample_flow")
+    except Exception:
+        if strict:
+            raise
+    # method patch: the token-major layers of the FeatureTransformer blocks
+    try:
+        tr = sys.modules.get("model.EMIP_short.motion.gmflow.transformer") or importlib.import_module(
+            "model.EMIP_short.motion.gmflow.transformer")
+        from .transformer_layer import transformer_layer_forward
+        key = ("model.EMIP_short.motion.gmflow.transformer", "TransformerLayer.forward")
+        if key not in _saved:
+            _saved[key] = tr.TransformerLayer.forward
+        tr.TransformerLayer.forward = transformer_layer_forward
+        done.append("model.EMIP_short.motion.gmflow.transformer.TransformerLayer.forward")
     except Exception:
         if strict:
             raise

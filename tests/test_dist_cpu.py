@@ -85,6 +85,9 @@ def test_dropin_rebinds_reference_symbols():
         assert gm.global_correlation_softmax is M.global_correlation_softmax
         assert lf.flow_warp is Wp.flow_warp
         assert any(d.endswith("PromptInteract.Injector") for d in done)
+        import model.EMIP_short.motion.gmflow.transformer as tr
+        from emip_b200.transformer_layer import transformer_layer_forward
+        assert tr.TransformerLayer.forward is transformer_layer_forward
         # the reference's own CoUpdater constructor now builds OUR modules under the reference's parameter names:
         # checkpoints (loaded by key filter, test.py:85-89) keep working
         torch.manual_seed(123)
@@ -104,3 +107,4 @@ def test_dropin_rebinds_reference_symbols():
         dropin.uninstall()
     import model.EMIP_short.motion.gmflow.matching as ref_matching
     assert gm.global_correlation_softmax is ref_matching.global_correlation_softmax
+    assert tr.TransformerLayer.forward is not transformer_layer_forward
