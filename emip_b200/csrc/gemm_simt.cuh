@@ -30,6 +30,10 @@ struct GemmNT {
   float* c; long long c_stride_b; int ldc;
   int B, M, K, N;
   int a_act;                                                                       // 1: exact GELU applied to A on load (tensor-core path only)
+  // tensor-core path only, B == 1: A already split (bf16 hi, lo rows of pitch kpad(N)); C written as bf16 hi | lo rows of
+  // pitch ldc_split (c_act 1: exact GELU first) instead of fp32 c -- the MLP of the FeatureTransformer blocks
+  const void* a_hi_pre; const void* a_lo_pre;
+  void* c_hi; void* c_lo; int ldc_split; int c_act;
 };
 int gemm_nt(const GemmNT& a, cudaStream_t st);
 

@@ -190,6 +190,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+    } else if (p.mode == 2 && p.out_split != 0) {
+      // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
+      const int n0 = nt * TM;
+      __nv_bfloat16* gh = p.g_hi + (size_t)row * p.ldg + n0;
+      __nv_bfloat16* gl = p.g_lo + (size_t)row * p.ldg + n0;
+      for (int c0 = 0; c0 < TM; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        if (row < p.M && n0 + c0 < p.N) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+            if (p.out_split == 2) {
+              v0 = 0.5f * v0 * (1.f + erff(v0 * 0.70710678118654752440f));
+              v1 = 0.5f * v1 * (1.f + erff(v1 * 0.70710678118654752440f));
+            }
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+            const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
+                                                         __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(gh + c0);
+          uint4* dl = reinterpret_cast<uint4*>(gl + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      }
     } else if (p.mode == 2) {
       const int n0 = nt * TM;
       float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
@@ -306,13 +340,16 @@ __device__ __forceinline__ void split8_store(const float (&v)[8], __nv_bfloat16*
 }
 
 // weights / row operands W(b)[m][k] fp32 -> hi, lo bf16 [nbw][M][Kp] (zero padded to Kp; Kp % 64 == 0).
-// grid (ceil(Kp / 2048), M, nbw): one row per blockIdx.y, 8 consecutive k per thread.
+// grid (split_w_blocks(M, Kp), 1, nbw): 8 consecutive k per thread, the (row, k group) pairs dealt to threads as one
+// flat list (r3: one block per row left 240 of 256 threads idle on the 128-wide token rows -- 36 us for 32 MB).
 __global__ void __launch_bounds__(256)
 split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int trans, __nv_bfloat16* __restrict__ hi,
                __nv_bfloat16* __restrict__ lo, int M, int K, int Kp, int act = 0) {
-  const int b = blockIdx.z, m = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (k0 >= Kp) return;
+  const int b = blockIdx.z;
+  const int kg = Kp >> 3;                                                   // k groups per row
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * kg) return;
+  const int m = (int)(idx / kg), k0 = (int)(idx % kg) * 8;
   const float* src = w + (size_t)b * w_stride_b;
   float v[8];
   if (!trans && k0 + 8 <= K && (ldw & 3) == 0 && (w_stride_b & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
@@ -364,6 +401,7 @@ split_rows_kernel(const float* __restrict__ x, long long x_stride_b, int ldx, co
 }
 
 int kpad(int K) { return (K + KCH - 1) / KCH * KCH; }
+unsigned split_w_blocks(int M, int Kp) { return (unsigned)(((long long)M * (Kp >> 3) + 255) / 256); }
 
 }  // namespace
 
@@ -420,7 +458,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* w_lo = w_hi + (size_t)nbw * a.M * Kp;
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)nbw * a.M * Kp * 2 * 2, 1024));
-  split_w_kernel<<<dim3((Kp + 2047) / 2048, a.M, nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, a.w_trans, w_hi, w_lo, a.M, a.K, Kp);
+  split_w_kernel<<<dim3(split_w_blocks(a.M, Kp), 1, nbw), 256, 0, st>>>(a.w, a.w_stride_b, a.ldw, a.w_trans, w_hi, w_lo, a.M, a.K, Kp);
   EMIP_CHECK_LAUNCH("gemm_nn_tc (weights)");
   // the activations keep their channel-major layout ([k][n], hi | lo per row): elementwise split (with the LayerNorm
   // applied on the way), read by the GEMM as an MN-major operand.  (r1 / r2a re-laid them out token-major with
@@ -454,6 +492,16 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 // C[b][m][k] = sum_n A(b)[m][n] B'(b)[k][n]: the weight-gradient GEMMs (contraction over the contiguous pixel axis, so
 // both operands are K-major as they lie in memory and only need the elementwise hi|lo split)
 bool gemm_nt_tc_supported(const GemmNT& a) {
+  if (a.c_hi != nullptr || a.a_hi_pre != nullptr) {
+    if (a.B != 1) return false;
+    if (a.c_hi != nullptr && (a.c_lo == nullptr || a.K % 32 != 0 || a.ldc_split % 8 != 0 || a.ldc_split < a.K ||
+                              (reinterpret_cast<uintptr_t>(a.c_hi) | reinterpret_cast<uintptr_t>(a.c_lo)) % 16 != 0))
+      return false;
+    if (a.a_hi_pre != nullptr && (a.a_lo_pre == nullptr || a.N % 64 != 0 || a.a_act != 0 ||
+                                  (reinterpret_cast<uintptr_t>(a.a_hi_pre) | reinterpret_cast<uintptr_t>(a.a_lo_pre)) % 128 != 0))
+      return false;
+    if (a.c_hi != nullptr) return a.M >= 1 && a.K >= 1 && a.N >= 16;
+  }
   return a.M >= 1 && a.K >= 1 && a.N >= 16 && a.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(a.c) % 16 == 0 && a.c_stride_b % 4 == 0;
 }
 
@@ -461,11 +509,15 @@ size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N) {
   const size_t Np = (size_t)kpad(N);
   return emip_align_up((size_t)B * M * Np * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
 }
+// with a pre-split A operand only the B operand needs scratch
+size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N) { return emip_align_up((size_t)K * 2 * kpad(N) * 2, 1024) + 1024; }
 
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit) {
   if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
-  if (!gemm_nt_tc_supported(a)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
-  if (scratch == nullptr || scratch_bytes < gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N)) {
+  if (!gemm_nt_tc_supported(a) || (a.c_hi != nullptr && nsplit > 1)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
+  const bool pre = a.a_hi_pre != nullptr;
+  if (scratch == nullptr ||
+      scratch_bytes < (pre ? gemm_nt_tc_scratch_bytes_presplit(a.K, a.N) : gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N))) {
     emip_set_error("gemm_nt_tc: scratch too small");
     return EMIP_ENOMEM;
   }
@@ -473,9 +525,14 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* a_lo = a_hi + (size_t)a.B * a.M * Np;
-  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + emip_align_up((size_t)a.B * a.M * Np * 2 * 2, 1024));
-  split_w_kernel<<<dim3((Np + 2047) / 2048, a.M, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act);
-  EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
+  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(base + (pre ? 0 : emip_align_up((size_t)a.B * a.M * Np * 2 * 2, 1024)));
+  if (pre) {
+    a_hi = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a.a_hi_pre));
+    a_lo = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a.a_lo_pre));
+  } else {
+    split_w_kernel<<<dim3(split_w_blocks(a.M, Np), 1, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act);
+    EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
+  }
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,
                                                                     a.K, a.N, Np);
   EMIP_CHECK_LAUNCH("gemm_nt_tc (B)");
@@ -497,6 +554,10 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   p.ksplit = ns;
   p.a_batched = 1; p.Kp = Np; p.N = a.K;
   p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
+  if (a.c_hi != nullptr) {
+    p.g_hi = static_cast<__nv_bfloat16*>(a.c_hi); p.g_lo = static_cast<__nv_bfloat16*>(a.c_lo);
+    p.out_split = a.c_act ? 2 : 1; p.ldg = a.ldc_split;
+  }
   return gemm_tc_launch(ma_hi, ma_lo, mb, p, a.B * ns, st);
 }
 
@@ -737,7 +798,7 @@ int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, cons
   {
     __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
     __nv_bfloat16* a_lo = a_hi + (size_t)B * 9 * 128 * Ko;
-    split_w_kernel<<<dim3((Ko + 2047) / 2048, 9 * 128, B), 256, 0, st>>>(f.g, (long long)M1 * 128, 9 * 128, 1, a_hi, a_lo, 9 * 128, O, Ko);
+    split_w_kernel<<<dim3(split_w_blocks(9 * 128, Ko), 1, B), 256, 0, st>>>(f.g, (long long)M1 * 128, 9 * 128, 1, a_hi, a_lo, 9 * 128, O, Ko);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (G^T)");
     if ((rc = f1_gemm(a_hi, a_lo, Ko, 1, f.dsp, 9 * 128, P, Ko, B, f.dx9, (long long)9 * 128 * P, P, st, 1, O, Pp))) return rc;
     f1_col2im_kernel<<<dim3((P + 255) / 256, 128, B), 256, 0, st>>>(f.dx9, df0, H, W, s);
@@ -758,7 +819,7 @@ int conv_corr_bwd_tc(const float* f0, const float* f1, const float* weight, cons
     __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(f.ops);
     __nv_bfloat16* a_lo = a_hi + (size_t)Kb * Km;
     __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(f.ops + al((size_t)Kb * Km * 2 * 2));
-    split_w_kernel<<<dim3((Km + 2047) / 2048, 128, B), 256, 0, st>>>(f.dg, (long long)M1 * 128, 128, 1, a_hi, a_lo, 128, M1, Km);
+    split_w_kernel<<<dim3(split_w_blocks(128, Km), 1, B), 256, 0, st>>>(f.dg, (long long)M1 * 128, 128, 1, a_hi, a_lo, 128, M1, Km);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (dG^T)");
     f1_weight_t_split_kernel<<<dim3((Km + 2047) / 2048, P), 256, 0, st>>>(weight, bt, O, P, Km, s);
     EMIP_CHECK_LAUNCH("conv_corr_bwd (weight^T)");

@@ -31,6 +31,9 @@ struct GemmTcParams {
   int b_mn, Np;             // b_mn: Bt is [B][K][2*Np] (k rows, n contiguous, hi | lo) and is read as an MN-major operand
   float* y; long long y_stride_b; int ldy;
   const float* res; long long res_stride_b; int ldr;
+  // mode 2, out_split != 0: the tile is written as bf16 hi | lo rows of pitch ldg into g_hi / g_lo (the A operand of a
+  // following GEMM) instead of fp32 y; out_split == 2 applies the exact GELU first.  Batch 1, N % 32 == 0.
+  int out_split, ldg;
 };
 
 constexpr int GEMM_TC_KCH = 64;                    // K elements per chunk (one 128-byte swizzle row of bf16)
@@ -53,6 +56,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 // c[b][m][k] = sum_n A(b)[m][n] * B'(b)[k][n] -- the arguments of gemm_nt (one result per batch entry, no N split).
 bool gemm_nt_tc_supported(const GemmNT& a);
 size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N);
+size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N);    // GemmNT::a_hi_pre set: only the B operand is split
 // nsplit > 1: the contraction axis is dealt to nsplit CTAs per tile; c then holds B * nsplit partial matrices
 // (c_stride_b apart, partial (b, s) at index b * nsplit + s) for the caller's batch reduction
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit = 1);

@@ -111,6 +111,51 @@ extern "C" int emip_linear_tm_fwd(const float* x, const float* w, float* y, void
   return gemm_nt_tc(t, workspace, scratch_bytes, st, 1);
 }
 
+namespace {
+size_t hid_bytes(int L, int Hd) { return emip_align_up((size_t)L * Hd * 2 * 2, 1024); }      // bf16 hi + lo
+bool mlp_shape_ok(int L, int K1, int Hd, int M) {
+  return L >= 0 && K1 >= 16 && K1 % 4 == 0 && K1 <= 4096 && Hd >= 64 && Hd % 64 == 0 && Hd <= 8192 && M >= 1 && M % 4 == 0 && M <= 4096;
+}
+}  // namespace
+
+extern "C" size_t emip_mlp_tm_workspace(int L, int K1, int Hd, int M) {
+  if (!mlp_shape_ok(L, K1, Hd, M)) return 0;
+  const size_t s1 = gemm_nt_tc_scratch_bytes(1, L, Hd, K1), s2 = gemm_nt_tc_scratch_bytes_presplit(M, Hd);
+  return hid_bytes(L, Hd) + emip_align_up(s1 > s2 ? s1 : s2, 1024);
+}
+
+// y [L][M] = GELU(x [L][K1] w1^T) w2^T,  w1 [Hd][K1], w2 [M][Hd]: the epilogue of the first GEMM writes the activated
+// hidden rows as the bf16 hi | lo A operand of the second one (no fp32 hidden tensor, no separate split pass)
+extern "C" int emip_mlp_tm_fwd(const float* x, const float* w1, const float* w2, float* y, void* workspace, size_t ws_bytes, int L,
+                               int K1, int Hd, int M, void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && w1 && w2 && y && workspace, "mlp_tm_fwd: null pointer");
+  if (!mlp_shape_ok(L, K1, Hd, M)) { emip_set_error("mlp_tm_fwd: unsupported shape L=%d K1=%d H=%d M=%d", L, K1, Hd, M); return EMIP_ENOSYS; }
+  if (ws_bytes < emip_mlp_tm_workspace(L, K1, Hd, M)) { emip_set_error("mlp_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "mlp_tm_fwd: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* h_hi = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* h_lo = h_hi + (size_t)L * Hd;
+  void* scratch = static_cast<char*>(workspace) + hid_bytes(L, Hd);
+  const size_t scratch_bytes = ws_bytes - hid_bytes(L, Hd);
+  int rc;
+  GemmNT t = {};
+  t.B = 1; t.M = L; t.K = Hd; t.N = K1;
+  t.a = x; t.lda = K1;
+  t.bm = w1; t.ldb = K1;
+  t.ldc = Hd;
+  t.c_hi = h_hi; t.c_lo = h_lo; t.ldc_split = Hd; t.c_act = 1;
+  if (!gemm_nt_tc_supported(t)) { emip_set_error("mlp_tm_fwd: unsupported first layer"); return EMIP_ENOSYS; }
+  if ((rc = gemm_nt_tc(t, scratch, scratch_bytes, st, 1))) return rc;
+  GemmNT u = {};
+  u.B = 1; u.M = L; u.K = M; u.N = Hd;
+  u.a_hi_pre = h_hi; u.a_lo_pre = h_lo;
+  u.bm = w2; u.ldb = Hd;
+  u.c = y; u.ldc = M;
+  if (!gemm_nt_tc_supported(u)) { emip_set_error("mlp_tm_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
+  return gemm_nt_tc(u, scratch, scratch_bytes, st, 1);
+}
+
 extern "C" int emip_layernorm_tm_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int L,
                                      int C, float eps, void* stream) {
   if (L == 0) return EMIP_OK;

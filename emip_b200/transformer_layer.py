@@ -63,6 +63,26 @@ class _LinearTM(torch.autograd.Function):
         return dx.view(ctx.in_shape), None, None
 
 
+def mlp_tm(x, w1, w2):
+    """``F.linear(F.gelu(F.linear(x, w1)), w2)`` in one C-ABI call (no autograd graph: inference / no-grad path)."""
+    _check(x, "mlp_tm")
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    w1, w2 = w1.detach().contiguous(), w2.detach().contiguous()
+    L_, K1, Hd, M = x2.shape[0], w1.shape[1], w1.shape[0], w2.shape[0]
+    if x2.shape[1] != K1 or w2.shape[1] != Hd:
+        raise ValueError(f"mlp_tm: x {tuple(x.shape)} against weights {tuple(w1.shape)}, {tuple(w2.shape)}")
+    lib = _lib.lib()
+    lib.emip_mlp_tm_workspace.restype = ctypes.c_size_t
+    need = lib.emip_mlp_tm_workspace(I(L_), I(K1), I(Hd), I(M))
+    if need == 0:
+        raise _lib.EmipError(f"emip_b200 mlp_tm: unsupported shape L={L_} K1={K1} H={Hd} M={M}")
+    ws, ws_ptr, ws_n = workspace(need, x2.device)
+    y = torch.empty((L_, M), dtype=torch.float32, device=x2.device)
+    _lib.check(lib.emip_mlp_tm_fwd(ptr(x2), ptr(w1), ptr(w2), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(K1), I(Hd), I(M),
+                                   stream_ptr()), "emip_mlp_tm_fwd")
+    return y.view(*x.shape[:-1], M)
+
+
 def _check(x, what):
     if not x.is_cuda:
         raise _lib.EmipError(f"emip_b200 {what} needs CUDA tensors (no CPU fallback)")
@@ -131,6 +151,9 @@ def transformer_layer_forward(self, source, target, height=None, width=None, shi
     if self.no_ffn:
         return layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=source)   # :172, :180
     message = layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-    hidden = linear_tm(torch.cat([source, message], dim=-1), self.mlp[0].weight)                           # :175
-    message = linear_tm(hidden, self.mlp[2].weight, gelu_in=True)
+    cat = torch.cat([source, message], dim=-1)                                                             # :175
+    if torch.is_grad_enabled() and cat.requires_grad:
+        message = linear_tm(linear_tm(cat, self.mlp[0].weight), self.mlp[2].weight, gelu_in=True)
+    else:                                                    # inference: GELU + operand split in the first GEMM's epilogue
+        message = mlp_tm(cat, self.mlp[0].weight, self.mlp[2].weight)
     return layer_norm_tm(message, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=source)     # :176, :180

@@ -136,6 +136,13 @@ int emip_linear_cn_bwd(const float* x, const float* w, const float* dy, float* d
 size_t emip_linear_tm_workspace(int L, int M, int K);
 int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K, int flags,
                        void* stream);
+/* The MLP of a cross-attention block in one call (transformer.py:140-146, :175): y [L,M] = GELU(x [L,K1] w1^T) w2^T with
+ * w1 [Hd,K1], w2 [M,Hd].  The first GEMM's epilogue applies the exact GELU and writes the hidden rows as the bf16 hi | lo
+ * operand of the second GEMM: no fp32 hidden tensor, no separate split pass (inference / no-grad path; with autograd the
+ * host mirror issues two emip_linear_tm_fwd calls and keeps the pre-activation).  Hd % 64 == 0. */
+size_t emip_mlp_tm_workspace(int L, int K1, int Hd, int M);
+int emip_mlp_tm_fwd(const float* x, const float* w1, const float* w2, float* y, void* workspace, size_t ws_bytes, int L, int K1,
+                    int Hd, int M, void* stream);
 /* y = (res ? res : 0) + LayerNorm_C(x) * gamma + beta over the channel axis of [L,C] rows (C = 128), biased variance, eps as
  * nn.LayerNorm; the backward returns dx only (frozen affine parameters), statistics are recomputed from x. */
 int emip_layernorm_tm_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int L, int C,

@@ -719,3 +719,18 @@ def test_f2b_layer_norm_tm_vs_fp64_and_errors():
         linear_tm(x, g.view(1, 128))                                                  # CPU tensors: no fallback
     with pytest.raises(NotImplementedError):
         linear_tm(dev(x), dev(r)[:128].clone().requires_grad_(True))                  # frozen weights only
+
+
+@pytest.mark.parametrize("L,K1,Hd,M", [(1936, 256, 1024, 128), (333, 40, 192, 36)])
+def test_f2b_mlp_tm_fused_vs_fp64(L, K1, Hd, M):
+    """The no-grad MLP call (GELU + hi | lo split in the first GEMM's epilogue, pre-split A operand of the second)
+    against fp64 and against the two-call path."""
+    from emip_b200.transformer_layer import mlp_tm, linear_tm
+    x, w1, w2 = cases.randn(321, (L, K1), 1.5), cases.randn(322, (Hd, K1), K1 ** -0.5), cases.randn(323, (M, Hd), Hd ** -0.5)
+    ref = O._gelu_erf(x.double() @ w1.double().T) @ w2.double().T
+    with torch.no_grad():
+        out = mlp_tm(dev(x), dev(w1), dev(w2))
+        two = linear_tm(linear_tm(dev(x), dev(w1)), dev(w2), gelu_in=True)
+    assert rel(out, ref) < TOL_EXACT, rel(out, ref)
+    assert rel(out, two) < TOL_EXACT, rel(out, two)
+    assert mlp_tm(dev(x)[:0], dev(w1), dev(w2)).shape == (0, M)

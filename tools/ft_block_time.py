@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from emip_b200.transformer_layer import transformer_layer_forward, linear_tm, layer_norm_tm   # noqa: E402
+from emip_b200.transformer_layer import transformer_layer_forward, linear_tm, layer_norm_tm, mlp_tm   # noqa: E402
 from emip_b200 import window_attn                                                                # noqa: E402
 
 B2, H, W, C = 32, 44, 44, 128
@@ -78,6 +78,8 @@ with torch.no_grad():
     res["linear_256_1024_us"] = {"ours": t(lambda: linear_tm(xc, w2)), "eager": t(lambda: xc @ w2.T)}
     res["gelu_linear_1024_128_us"] = {"ours": t(lambda: linear_tm(h, w3, gelu_in=True)),
                                       "eager": t(lambda: torch.nn.functional.gelu(h) @ w3.T)}
+    res["mlp_256_1024_128_fused_us"] = {"ours": t(lambda: mlp_tm(xc, w2, w3)),
+                                        "eager": t(lambda: torch.nn.functional.gelu(xc @ w2.T) @ w3.T)}
     res["ln_residual_us"] = {"ours": t(lambda: layer_norm_tm(x2, g, b, 1e-5, residual=x2)),
                              "eager": t(lambda: x2 + torch.nn.functional.layer_norm(x2, (C,), g, b))}
 print(json.dumps(res, indent=1))
