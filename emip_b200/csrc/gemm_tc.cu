@@ -17,7 +17,7 @@ using namespace tc;
 
 constexpr int KCH = GEMM_TC_KCH;
 constexpr int A_BYTES = GEMM_TC_A_BYTES;
-constexpr int THREADS = 6 * 32;
+constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA producer; 5: UMMA issuer
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -93,8 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int ab = p.a_batched ? bs : 0;
           tma_load_3d(sa, &map_a_hi, full(stage), k0 * KCH, mt * TM, ab);
           tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), k0 * KCH, mt * TM, ab);
-          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), k0 * KCH, nt * TM, bs);
-          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + k0 * KCH, nt * TM, bs);
+          tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), k0 * KCH, nt * p.n_tile, bs);
+          tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + k0 * KCH, nt * p.n_tile, bs);
         } else {
           tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
           tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
@@ -153,15 +153,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else {
     // ===================== epilogue warps: thread <-> output row =====================
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    // two groups of four warps (0-3 and 6-9), one per accumulator: group g drains the CTA's tiles g, g + 2, ... so two
+    // epilogues run side by side (r3: with K <= 256 the epilogue, not the MMA loop, bounds a tile).  A warp reads the TMEM
+    // lane quarter warp % 4.
+    const int grp = warp >= 6 ? 1 : 0, qw = warp & 3;
+    uint32_t it = grp;
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     int nt, mt, b;
     decode(tile, nt, mt, b);
     const int acc = it & 1;
-    const int row = mt * TM + warp * 32 + lane;
+    const int row = mt * TM + qw * 32 + lane;
     mbar_wait(acc_full(acc), (it >> 1) & 1);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
+    const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 256);
     if (p.mode == 0) {
       __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
       __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
@@ -192,10 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     } else if (p.mode == 2 && p.out_split != 0) {
       // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
-      const int n0 = nt * TM;
+      const int n0 = nt * p.n_tile;
       __nv_bfloat16* gh = p.g_hi + (size_t)row * p.ldg + n0;
       __nv_bfloat16* gl = p.g_lo + (size_t)row * p.ldg + n0;
-      for (int c0 = 0; c0 < TM; c0 += 32) {
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
@@ -225,11 +229,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     } else if (p.mode == 2) {
-      const int n0 = nt * TM;
+      const int n0 = nt * p.n_tile;
       float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
       const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
       const float rb = (p.bias != nullptr && row < p.M) ? __ldg(p.bias + row) : 0.f;      // per-row bias (linear layers)
-      for (int c0 = 0; c0 < TM; c0 += 32) {
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
@@ -545,10 +549,13 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   if ((rc = gemm_tc_make_map(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
   const cuuint64_t bdims[3] = {(cuuint64_t)2 * Np, (cuuint64_t)a.K, (cuuint64_t)a.B};
   const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)a.K * 2 * Np * 2};
-  const cuuint32_t bbox[3] = {KCH, TM, 1};
+  // wide outputs (the 256 -> 1024 MLP layer): 256-column tiles -- the A tile (hi + lo) is fetched once per 256 instead
+  // of once per 128 output columns (r3: that GEMM was bound by the L2 -> shared-memory operand stream, 991 MB per call)
+  const int ntile = (a.K % 256 == 0 && a.K >= 512 && nsplit <= 1) ? 256 : TM;
+  const cuuint32_t bbox[3] = {KCH, (cuuint32_t)ntile, 1};
   if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
   GemmTcParams p = {};
-  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.K + TM - 1) / TM; p.n_tile = TM;
+  p.mode = 2; p.M = a.M; p.n_mtiles = (a.M + TM - 1) / TM; p.n_ntiles = (a.K + ntile - 1) / ntile; p.n_tile = ntile;
   const int ns = nsplit > 1 ? nsplit : 1;
   p.kchunks = (Np / KCH + ns - 1) / ns;                  // per split; partial (b, s) is matrix b * ns + s of c
   p.ksplit = ns;

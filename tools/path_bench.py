@@ -388,6 +388,49 @@ def main():
         f"copies); the same formula as eager torch ops on this GPU: shifted {res2[True][1]:.3f} ms, unshifted {res2[False][1]:.3f} ms "
         f"forward; 12 such layers per pair of feature maps; CPU sample = 4 x 8")
 
+    # ---------------- f2b: one whole FeatureTransformer block pair (self layer + cross / FFN layer), 2B = 32 ----------------
+    from types import SimpleNamespace as NS
+    from emip_b200.transformer_layer import transformer_layer_forward
+    pb = {k: v.to(dev) for k, v in cases.f2b_inputs(cases.F2B_CASES["f2b_full"])["params"].items()}
+    lin = lambda n: NS(weight=pb[n + ".weight"])
+    lnm = lambda n: NS(weight=pb[n + ".weight"], bias=pb[n + ".bias"], eps=1e-5)
+    mk = lambda no_ffn: NS(attention_type="swin", nhead=1, no_ffn=no_ffn, with_shift=True, q_proj=lin("q_proj"), k_proj=lin("k_proj"),
+                           v_proj=lin("v_proj"), merge=lin("merge"), norm1=lnm("norm1"), norm2=lnm("norm2"),
+                           mlp=[lin("mlp.0"), None, lin("mlp.2")])
+    l_self, l_cross = mk(True), mk(False)
+    src_b, tgt_b = torch.randn(32, N, C, device=dev, generator=g), torch.randn(32, N, C, device=dev, generator=g)
+
+    def block(s_, t_):
+        s_ = transformer_layer_forward(l_self, s_, s_, height=H, width=W, shifted_window_attn_mask=amask, attn_num_splits=2)
+        return transformer_layer_forward(l_cross, s_, t_, height=H, width=W, shifted_window_attn_mask=amask, attn_num_splits=2)
+
+    def f2b_fwd():
+        with torch.no_grad():
+            return block(src_b, tgt_b)
+
+    def f2b_fwd_bwd():
+        a, b = src_b.detach().requires_grad_(True), tgt_b.detach().requires_grad_(True)
+        block(a, b).backward(wf2)
+
+    def f2b_torch():                                      # the reference's op sequence on the same GPU (library kernels)
+        with torch.no_grad():
+            s_ = O.transformer_layer(src_b, src_b, pb, True, 2, True, H, W)
+            return O.transformer_layer(s_, tgt_b, pb, False, 2, True, H, W)
+    tb_f, tb_fb, tb_t = gpu_time(f2b_fwd, iters=10), gpu_time(f2b_fwd_bwd, iters=5), gpu_time(f2b_torch, iters=3, warm=1)
+    cf = None
+    if not args.no_cpu:
+        cs_, ct_ = src_b[:2].cpu(), tgt_b[:2].cpu()
+        pc = {k: v.cpu() for k, v in pb.items()}
+        cf = cpu_time(lambda: O.transformer_layer(O.transformer_layer(cs_, cs_, pc, True, 2, True, H, W), ct_, pc, False, 2, True, H, W)) * 16
+    ntok = 32 * N
+    fl = 2.0 * ntok * (8 * C * C + 2 * C * 8 * C + 8 * C * C) + 2 * 32 * 4 * 2.0 * 484 * 484 * (C + C)
+    add("f2b FeatureTransformer block pair (self + cross / FFN layer, shifted), 2B=32", 16, "pairs", tb_f, tb_fb - tb_f, fl, 2.0 * fl,
+        ntok * C * 4 * 3, 0, "tensor", cf, None,
+        f"TransformerLayer.forward as the drop-in: ten split-bf16 tcgen05 linear layers (executed MMA FLOPs = 3 x algorithmic), "
+        f"fused MLP call (GELU + operand split in the first GEMM's epilogue), two window-attention calls, three LayerNorm + residual "
+        f"launches; the reference's op sequence in eager torch on this GPU (cuBLAS fp32, library attention): {tb_t:.3f} ms forward; "
+        f"six block pairs per forward; CPU sample = 2 maps x 16")
+
     # ---------------- f3b: photometric loss term (L1 + SSIM 3x3, masked), B = 64 ----------------
     from emip_b200.photometric import photometric_loss
     rec0 = x + 0.2 * torch.randn(Bw, Cw, Hw, Ww, device=dev, generator=g)
