@@ -30,6 +30,7 @@ struct GemmNT {
   float* c; long long c_stride_b; int ldc;
   int B, M, K, N;
   int a_act;                                                                       // 1: exact GELU applied to A on load (tensor-core path only)
+  const float* a_aux;                                                              // a_act 2: A * GELU'(a_aux) on load, a_aux laid out like a
   // tensor-core path only, B == 1: A already split (bf16 hi, lo rows of pitch kpad(N)); C written as bf16 hi | lo rows of
   // pitch ldc_split (c_act 1: exact GELU first) instead of fp32 c -- the MLP of the FeatureTransformer blocks
   const void* a_hi_pre; const void* a_lo_pre;

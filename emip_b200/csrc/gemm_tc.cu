@@ -19,6 +19,21 @@ constexpr int KCH = GEMM_TC_KCH;
 constexpr int A_BYTES = GEMM_TC_A_BYTES;
 constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA producer; 5: UMMA issuer
 
+// exact-GELU x Phi(x) for the epilogue (where the instruction count is the critical path): Phi through the rational
+// erfc form of Abramowitz & Stegun 7.1.26, erfc(z) = poly5(t) e^{-z^2}, t = 1 / (1 + 0.3275911 z), |error| <= 1.5e-7 --
+// below the 2^-17 relative resolution of the bf16 hi | lo pair the value is stored as.  One MUFU.RCP + one MUFU.EX2 and
+// ~12 FP32 instructions instead of erff's two-branch polynomial; no 1 + erf cancellation for negative x.
+__device__ __forceinline__ float gelu_epi(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float g = 0.5f * p * t * __expf(-z * z);               // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
+  return x * (x >= 0.f ? 1.f - g : g);
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b, const GemmTcParams p) {
@@ -209,8 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int i = 0; i < 16; ++i) {
             float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
             if (p.out_split == 2) {
-              v0 = 0.5f * v0 * (1.f + erff(v0 * 0.70710678118654752440f));
-              v1 = 0.5f * v1 * (1.f + erff(v1 * 0.70710678118654752440f));
+              v0 = gelu_epi(v0);
+              v1 = gelu_epi(v1);
             }
             const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
             const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
@@ -348,7 +363,7 @@ __device__ __forceinline__ void split8_store(const float (&v)[8], __nv_bfloat16*
 // flat list (r3: one block per row left 240 of 256 threads idle on the 128-wide token rows -- 36 us for 32 MB).
 __global__ void __launch_bounds__(256)
 split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int trans, __nv_bfloat16* __restrict__ hi,
-               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp, int act = 0) {
+               __nv_bfloat16* __restrict__ lo, int M, int K, int Kp, int act = 0, const float* __restrict__ aux = nullptr) {
   const int b = blockIdx.z;
   const int kg = Kp >> 3;                                                   // k groups per row
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,6 +385,14 @@ split_w_kernel(const float* __restrict__ w, long long w_stride_b, int ldw, int t
   if (act == 1) {                                   // exact GELU (nn.GELU default): 0.5 x (1 + erf(x / sqrt 2))
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752440f));
+  }
+  if (act == 2) {                                   // v * GELU'(aux), aux laid out like w (not transposed): Phi(h) + h phi(h)
+    const float* ax = aux + (size_t)b * w_stride_b + (size_t)m * ldw;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float h = k0 + i < K ? __ldg(ax + k0 + i) : 0.f;
+      v[i] *= 0.5f * (1.f + erff(h * 0.70710678118654752440f)) + h * 0.39894228040143267794f * __expf(-0.5f * h * h);
+    }
   }
   const size_t o = ((size_t)b * M + m) * Kp + k0;
   split8_store(v, hi + o, lo + o);
@@ -501,6 +524,7 @@ bool gemm_nt_tc_supported(const GemmNT& a) {
     if (a.c_hi != nullptr && (a.c_lo == nullptr || a.K % 32 != 0 || a.ldc_split % 8 != 0 || a.ldc_split < a.K ||
                               (reinterpret_cast<uintptr_t>(a.c_hi) | reinterpret_cast<uintptr_t>(a.c_lo)) % 16 != 0))
       return false;
+    if (a.a_act == 2 && a.a_aux == nullptr) return false;
     if (a.a_hi_pre != nullptr && (a.a_lo_pre == nullptr || a.N % 64 != 0 || a.a_act != 0 ||
                                   (reinterpret_cast<uintptr_t>(a.a_hi_pre) | reinterpret_cast<uintptr_t>(a.a_lo_pre)) % 128 != 0))
       return false;
@@ -534,7 +558,7 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
     a_hi = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a.a_hi_pre));
     a_lo = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a.a_lo_pre));
   } else {
-    split_w_kernel<<<dim3(split_w_blocks(a.M, Np), 1, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act);
+    split_w_kernel<<<dim3(split_w_blocks(a.M, Np), 1, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act, a.a_aux);
     EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
   }
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,

@@ -84,9 +84,17 @@ extern "C" size_t emip_linear_tm_workspace(int L, int M, int K) {
 // y [L][M] = act(x [L][K]) w^T, w [M][K];   EMIP_LINEAR_W_TRANS: y [L][K] = act(x [L][M]) w
 extern "C" int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K,
                                   int flags, void* stream) {
+  return emip_linear_tm_fwd_ex(x, nullptr, w, y, workspace, ws_bytes, L, M, K, flags, stream);
+}
+
+// EMIP_LINEAR_GELU_BWD_IN: the rows are x * GELU'(aux) (aux laid out like x) -- the gradient entering the first MLP layer
+extern "C" int emip_linear_tm_fwd_ex(const float* x, const float* aux, const float* w, float* y, void* workspace, size_t ws_bytes,
+                                     int L, int M, int K, int flags, void* stream) {
   if (L == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && w && y && workspace, "linear_tm_fwd: null pointer");
-  EMIP_CHECK_ARG((flags & ~(EMIP_LINEAR_GELU_IN | EMIP_LINEAR_W_TRANS)) == 0, "linear_tm_fwd: unknown flag");
+  EMIP_CHECK_ARG((flags & ~(EMIP_LINEAR_GELU_IN | EMIP_LINEAR_W_TRANS | EMIP_LINEAR_GELU_BWD_IN)) == 0, "linear_tm_fwd: unknown flag");
+  EMIP_CHECK_ARG(!(flags & EMIP_LINEAR_GELU_BWD_IN) || (aux != nullptr && !(flags & EMIP_LINEAR_GELU_IN)),
+                 "linear_tm_fwd: EMIP_LINEAR_GELU_BWD_IN needs aux and excludes EMIP_LINEAR_GELU_IN");
   if (!shape_ok(L, M, K)) { emip_set_error("linear_tm_fwd: unsupported shape L=%d M=%d K=%d", L, M, K); return EMIP_ENOSYS; }
   if (ws_bytes < emip_linear_tm_workspace(L, M, K)) { emip_set_error("linear_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
   EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "linear_tm_fwd: workspace must be 1024-byte aligned");
@@ -106,7 +114,8 @@ extern "C" int emip_linear_tm_fwd(const float* x, const float* w, float* y, void
   t.a = x; t.a_stride_b = 0; t.lda = in;
   t.bm = wb; t.b_stride_b = 0; t.ldb = in;
   t.c = y; t.c_stride_b = 0; t.ldc = out;
-  t.a_act = (flags & EMIP_LINEAR_GELU_IN) ? 1 : 0;
+  t.a_act = (flags & EMIP_LINEAR_GELU_IN) ? 1 : (flags & EMIP_LINEAR_GELU_BWD_IN) ? 2 : 0;
+  t.a_aux = aux;
   if (!gemm_nt_tc_supported(t)) { emip_set_error("linear_tm_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
   return gemm_nt_tc(t, workspace, scratch_bytes, st, 1);
 }

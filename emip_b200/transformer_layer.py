@@ -24,10 +24,11 @@ from .window_attn import single_head_full_attention, single_head_split_window_at
 
 GELU_IN = 1
 W_TRANS = 2
+GELU_BWD_IN = 4
 
 
-def _linear_call(x2, w, flags):
-    """x2 [L, in] contiguous fp32 CUDA, w [M, K] -> [L, M] (or [L, K] with W_TRANS)."""
+def _linear_call(x2, w, flags, aux=None):
+    """x2 [L, in] contiguous fp32 CUDA, w [M, K] -> [L, M] (or [L, K] with W_TRANS); aux: rows for GELU_BWD_IN."""
     L_, M, K = x2.shape[0], w.shape[0], w.shape[1]
     lib = _lib.lib()
     lib.emip_linear_tm_workspace.restype = ctypes.c_size_t
@@ -36,8 +37,8 @@ def _linear_call(x2, w, flags):
         raise _lib.EmipError(f"emip_b200 linear_tm: unsupported shape L={L_} M={M} K={K}")
     ws, ws_ptr, ws_n = workspace(need, x2.device)
     y = torch.empty((L_, K if flags & W_TRANS else M), dtype=torch.float32, device=x2.device)
-    _lib.check(lib.emip_linear_tm_fwd(ptr(x2), ptr(w), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K), I(flags),
-                                      stream_ptr()), "emip_linear_tm_fwd")
+    _lib.check(lib.emip_linear_tm_fwd_ex(ptr(x2), ptr(aux), ptr(w), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K),
+                                         I(flags), stream_ptr()), "emip_linear_tm_fwd_ex")
     return y
 
 
@@ -60,6 +61,30 @@ class _LinearTM(torch.autograd.Function):
         dx = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w, W_TRANS)
         if ctx.gelu_in:
             dx = torch.ops.aten.gelu_backward(dx, x2)               # elementwise d GELU(x) / dx on the pre-activation
+        return dx.view(ctx.in_shape), None, None
+
+
+class _MlpTM(torch.autograd.Function):
+    """mlp[2](GELU(mlp[0](x))) with autograd: the forward keeps the fp32 pre-activation, the backward applies GELU' inside the
+    operand split of the mlp[0] input-gradient GEMM (no elementwise pass over the [L, 1024] tensors)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("emip_b200 mlp: weight gradients are not built (the GMFlow weights are frozen, train.py:340-342)")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w1, w2 = w1.contiguous(), w2.contiguous()
+        h = _linear_call(x2, w1, 0)
+        y = _linear_call(h, w2, GELU_IN)
+        ctx.save_for_backward(h, w1, w2)
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w1, w2 = ctx.saved_tensors
+        dh = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w2, W_TRANS)
+        dx = _linear_call(dh, w1, W_TRANS | GELU_BWD_IN, aux=h)
         return dx.view(ctx.in_shape), None, None
 
 
@@ -153,7 +178,7 @@ def transformer_layer_forward(self, source, target, height=None, width=None, shi
     message = layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)
     cat = torch.cat([source, message], dim=-1)                                                             # :175
     if torch.is_grad_enabled() and cat.requires_grad:
-        message = linear_tm(linear_tm(cat, self.mlp[0].weight), self.mlp[2].weight, gelu_in=True)
+        message = _MlpTM.apply(cat, self.mlp[0].weight, self.mlp[2].weight)
     else:                                                    # inference: GELU + operand split in the first GEMM's epilogue
         message = mlp_tm(cat, self.mlp[0].weight, self.mlp[2].weight)
     return layer_norm_tm(message, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=source)     # :176, :180

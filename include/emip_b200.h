@@ -136,6 +136,11 @@ int emip_linear_cn_bwd(const float* x, const float* w, const float* dy, float* d
 size_t emip_linear_tm_workspace(int L, int M, int K);
 int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K, int flags,
                        void* stream);
+/* EMIP_LINEAR_GELU_BWD_IN: the rows are x * GELU'(aux), aux laid out like x (the pre-activation the forward kept) -- with
+ * EMIP_LINEAR_W_TRANS this is the input gradient of mlp[0] with the derivative of mlp[1] applied on load. */
+#define EMIP_LINEAR_GELU_BWD_IN 4
+int emip_linear_tm_fwd_ex(const float* x, const float* aux, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M,
+                          int K, int flags, void* stream);
 /* The MLP of a cross-attention block in one call (transformer.py:140-146, :175): y [L,M] = GELU(x [L,K1] w1^T) w2^T with
  * w1 [Hd,K1], w2 [M,Hd].  The first GEMM's epilogue applies the exact GELU and writes the hidden rows as the bf16 hi | lo
  * operand of the second GEMM: no fp32 hidden tensor, no separate split pass (inference / no-grad path; with autograd the

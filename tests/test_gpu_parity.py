@@ -734,3 +734,12 @@ def test_f2b_mlp_tm_fused_vs_fp64(L, K1, Hd, M):
     assert rel(out, ref) < TOL_EXACT, rel(out, ref)
     assert rel(out, two) < TOL_EXACT, rel(out, two)
     assert mlp_tm(dev(x)[:0], dev(w1), dev(w2)).shape == (0, M)
+    # autograd path: pre-activation kept, GELU' applied inside the operand split of the input-gradient GEMM
+    from emip_b200.transformer_layer import _MlpTM
+    wo = cases.randn(324, (L, M))
+    xd = x.double().requires_grad_(True)
+    (O._gelu_erf(xd @ w1.double().T) @ w2.double().T).backward(wo.double())
+    xg = dev(x).requires_grad_(True)
+    og = _MlpTM.apply(xg, dev(w1), dev(w2))
+    og.backward(dev(wo))
+    assert rel(og, ref) < TOL_EXACT and rel(xg.grad, xd.grad) < TOL_EXACT, (rel(og, ref), rel(xg.grad, xd.grad))
