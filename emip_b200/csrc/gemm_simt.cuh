@@ -35,6 +35,8 @@ struct GemmNT {
   // pitch ldc_split (c_act 1: exact GELU first) instead of fp32 c -- the MLP of the FeatureTransformer blocks
   const void* a_hi_pre; const void* a_lo_pre;
   void* c_hi; void* c_lo; int ldc_split; int c_act;
+  // tensor-core path only, K == 128: c = c_res + LayerNorm over the K outputs of a row (gamma, beta [K]; c_res rows ldc apart or NULL)
+  const float* ln_gamma; const float* ln_beta; float ln_eps; const float* c_res;
 };
 int gemm_nt(const GemmNT& a, cudaStream_t st);
 

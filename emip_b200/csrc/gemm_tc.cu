@@ -209,6 +209,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+    } else if (p.mode == 2 && p.ln_gamma != nullptr) {
+      // the whole 128-wide output row lives in this thread's TMEM lane: LayerNorm over it (+ residual) before the store --
+      // three passes over TMEM (mean, centred variance, write), no fp32 round trip of the pre-norm tensor through HBM
+      float* o = p.y + (size_t)row * p.ldy;
+      const float* rs = p.res ? p.res + (size_t)row * p.ldr : nullptr;
+      float sum = 0.f;
+      for (int c0 = 0; c0 < TM; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]);
+      }
+      const float mean = sum * (1.f / 128.f);
+      float sq = 0.f;
+      for (int c0 = 0; c0 < TM; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mean; sq = fmaf(d, d, sq); }
+      }
+      const float rstd = rsqrtf(sq * (1.f / 128.f) + p.ln_eps);
+      for (int c0 = 0; c0 < TM; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        if (row < p.M) {
+          float4* d = reinterpret_cast<float4*>(o + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0) + i);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0) + i);
+            float4 v = make_float4((__uint_as_float(r[4 * i]) - mean) * rstd * g.x + be.x,
+                                   (__uint_as_float(r[4 * i + 1]) - mean) * rstd * g.y + be.y,
+                                   (__uint_as_float(r[4 * i + 2]) - mean) * rstd * g.z + be.z,
+                                   (__uint_as_float(r[4 * i + 3]) - mean) * rstd * g.w + be.w);
+            if (rs) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
+              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            d[i] = v;
+          }
+        }
+      }
     } else if (p.mode == 2 && p.out_split != 0) {
       // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
       const int n0 = nt * p.n_tile;
@@ -585,6 +630,15 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   p.ksplit = ns;
   p.a_batched = 1; p.Kp = Np; p.N = a.K;
   p.y = a.c; p.y_stride_b = a.c_stride_b; p.ldy = a.ldc;
+  if (a.ln_gamma != nullptr) {
+    if (a.K != TM || a.B != 1 || ns != 1 || a.c_hi != nullptr || a.ln_beta == nullptr || a.ldc % 4 != 0 ||
+        ((reinterpret_cast<uintptr_t>(a.ln_gamma) | reinterpret_cast<uintptr_t>(a.ln_beta) | reinterpret_cast<uintptr_t>(a.c_res)) & 15) != 0) {
+      emip_set_error("gemm_nt_tc: the LayerNorm epilogue needs 128 output columns and 16-byte aligned gamma / beta / residual");
+      return EMIP_ENOSYS;
+    }
+    p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+    p.res = a.c_res; p.res_stride_b = 0; p.ldr = a.ldc;
+  }
   if (a.c_hi != nullptr) {
     p.g_hi = static_cast<__nv_bfloat16*>(a.c_hi); p.g_lo = static_cast<__nv_bfloat16*>(a.c_lo);
     p.out_split = a.c_act ? 2 : 1; p.ldg = a.ldc_split;

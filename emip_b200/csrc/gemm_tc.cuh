@@ -34,6 +34,8 @@ struct GemmTcParams {
   // mode 2, out_split != 0: the tile is written as bf16 hi | lo rows of pitch ldg into g_hi / g_lo (the A operand of a
   // following GEMM) instead of fp32 y; out_split == 2 applies the exact GELU first.  Batch 1, N % 32 == 0.
   int out_split, ldg;
+  // mode 2, ln_gamma != NULL (N == n_tile == 128, one output row per thread): y = res + LayerNorm_N(tile) * gamma + beta
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 };
 
 constexpr int GEMM_TC_KCH = 64;                    // K elements per chunk (one 128-byte swizzle row of bf16)

@@ -87,6 +87,27 @@ extern "C" int emip_linear_tm_fwd(const float* x, const float* w, float* y, void
   return emip_linear_tm_fwd_ex(x, nullptr, w, y, workspace, ws_bytes, L, M, K, flags, stream);
 }
 
+// y [L][128] = (res ? res : 0) + LayerNorm_128(act(x) w^T) * gamma + beta: merge + norm1 (+ source) and, with
+// EMIP_LINEAR_GELU_IN off and the rows pre-activated by emip_mlp_ln_tm_fwd, mlp[2] + norm2 + source
+extern "C" int emip_linear_ln_tm_fwd(const float* x, const float* w, const float* gamma, const float* beta, const float* res,
+                                     float* y, void* workspace, size_t ws_bytes, int L, int M, int K, float eps, int flags,
+                                     void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && w && y && gamma && beta && workspace, "linear_ln_tm_fwd: null pointer");
+  EMIP_CHECK_ARG((flags & ~EMIP_LINEAR_GELU_IN) == 0, "linear_ln_tm_fwd: unknown flag");
+  if (M != 128 || !shape_ok(L, M, K)) { emip_set_error("linear_ln_tm_fwd: unsupported shape L=%d M=%d K=%d (M must be 128)", L, M, K); return EMIP_ENOSYS; }
+  if (ws_bytes < emip_linear_tm_workspace(L, M, K)) { emip_set_error("linear_ln_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
+  GemmNT t = {};
+  t.B = 1; t.M = L; t.K = M; t.N = K;
+  t.a = x; t.lda = K;
+  t.bm = w; t.ldb = K;
+  t.c = y; t.ldc = M;
+  t.a_act = (flags & EMIP_LINEAR_GELU_IN) ? 1 : 0;
+  t.ln_gamma = gamma; t.ln_beta = beta; t.ln_eps = eps; t.c_res = res;
+  if (!gemm_nt_tc_supported(t)) { emip_set_error("linear_ln_tm_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
+  return gemm_nt_tc(t, workspace, ws_bytes - wt_bytes(M, K), (cudaStream_t)stream, 1);
+}
+
 // EMIP_LINEAR_GELU_BWD_IN: the rows are x * GELU'(aux) (aux laid out like x) -- the gradient entering the first MLP layer
 extern "C" int emip_linear_tm_fwd_ex(const float* x, const float* aux, const float* w, float* y, void* workspace, size_t ws_bytes,
                                      int L, int M, int K, int flags, void* stream) {
@@ -137,7 +158,15 @@ extern "C" size_t emip_mlp_tm_workspace(int L, int K1, int Hd, int M) {
 // hidden rows as the bf16 hi | lo A operand of the second one (no fp32 hidden tensor, no separate split pass)
 extern "C" int emip_mlp_tm_fwd(const float* x, const float* w1, const float* w2, float* y, void* workspace, size_t ws_bytes, int L,
                                int K1, int Hd, int M, void* stream) {
+  return emip_mlp_ln_tm_fwd(x, w1, w2, nullptr, nullptr, nullptr, y, workspace, ws_bytes, L, K1, Hd, M, 0.f, stream);
+}
+
+// gamma != NULL (M == 128): y = (res ? res : 0) + LayerNorm_128(GELU(x w1^T) w2^T) * gamma + beta -- mlp + norm2 + source
+extern "C" int emip_mlp_ln_tm_fwd(const float* x, const float* w1, const float* w2, const float* gamma, const float* beta,
+                                  const float* res, float* y, void* workspace, size_t ws_bytes, int L, int K1, int Hd, int M,
+                                  float eps, void* stream) {
   if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(gamma == nullptr || (beta != nullptr && M == 128), "mlp_ln_tm_fwd: the LayerNorm epilogue needs beta and M = 128");
   EMIP_CHECK_ARG(x && w1 && w2 && y && workspace, "mlp_tm_fwd: null pointer");
   if (!mlp_shape_ok(L, K1, Hd, M)) { emip_set_error("mlp_tm_fwd: unsupported shape L=%d K1=%d H=%d M=%d", L, K1, Hd, M); return EMIP_ENOSYS; }
   if (ws_bytes < emip_mlp_tm_workspace(L, K1, Hd, M)) { emip_set_error("mlp_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
@@ -161,6 +190,7 @@ extern "C" int emip_mlp_tm_fwd(const float* x, const float* w1, const float* w2,
   u.a_hi_pre = h_hi; u.a_lo_pre = h_lo;
   u.bm = w2; u.ldb = Hd;
   u.c = y; u.ldc = M;
+  u.ln_gamma = gamma; u.ln_beta = beta; u.ln_eps = eps; u.c_res = gamma ? res : nullptr;
   if (!gemm_nt_tc_supported(u)) { emip_set_error("mlp_tm_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
   return gemm_nt_tc(u, scratch, scratch_bytes, st, 1);
 }

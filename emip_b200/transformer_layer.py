@@ -88,8 +88,30 @@ class _MlpTM(torch.autograd.Function):
         return dx.view(ctx.in_shape), None, None
 
 
-def mlp_tm(x, w1, w2):
-    """``F.linear(F.gelu(F.linear(x, w1)), w2)`` in one C-ABI call (no autograd graph: inference / no-grad path)."""
+def linear_ln_tm(x, weight, ln_weight, ln_bias, eps=1e-5, residual=None):
+    """``residual + F.layer_norm(F.linear(x, weight), (128,), ln_weight, ln_bias, eps)`` in one C-ABI call: the LayerNorm runs in
+    the GEMM epilogue (no autograd graph: inference / no-grad path)."""
+    _check(x, "linear_ln_tm")
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    w = weight.detach().contiguous()
+    L_, M, K = x2.shape[0], w.shape[0], w.shape[1]
+    r2 = None if residual is None else residual.detach().reshape(-1, M).contiguous()
+    lib = _lib.lib()
+    lib.emip_linear_tm_workspace.restype = ctypes.c_size_t
+    need = lib.emip_linear_tm_workspace(I(L_), I(M), I(K))
+    if need == 0 or M != 128:
+        raise _lib.EmipError(f"emip_b200 linear_ln_tm: unsupported shape L={L_} M={M} K={K}")
+    ws, ws_ptr, ws_n = workspace(need, x2.device)
+    y = torch.empty((L_, M), dtype=torch.float32, device=x2.device)
+    _lib.check(lib.emip_linear_ln_tm_fwd(ptr(x2), ptr(w), ptr(ln_weight.detach().contiguous()), ptr(ln_bias.detach().contiguous()),
+                                         ptr(r2), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K), F(eps), I(0),
+                                         stream_ptr()), "emip_linear_ln_tm_fwd")
+    return y.view(*x.shape[:-1], M)
+
+
+def mlp_tm(x, w1, w2, ln_weight=None, ln_bias=None, eps=1e-5, residual=None):
+    """``F.linear(F.gelu(F.linear(x, w1)), w2)`` in one C-ABI call (no autograd graph: inference / no-grad path); with
+    ``ln_weight`` the result is ``residual + F.layer_norm(..., ln_weight, ln_bias, eps)`` (LayerNorm in the last epilogue)."""
     _check(x, "mlp_tm")
     x2 = x.reshape(-1, x.shape[-1]).contiguous()
     w1, w2 = w1.detach().contiguous(), w2.detach().contiguous()
@@ -103,8 +125,11 @@ def mlp_tm(x, w1, w2):
         raise _lib.EmipError(f"emip_b200 mlp_tm: unsupported shape L={L_} K1={K1} H={Hd} M={M}")
     ws, ws_ptr, ws_n = workspace(need, x2.device)
     y = torch.empty((L_, M), dtype=torch.float32, device=x2.device)
-    _lib.check(lib.emip_mlp_tm_fwd(ptr(x2), ptr(w1), ptr(w2), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(K1), I(Hd), I(M),
-                                   stream_ptr()), "emip_mlp_tm_fwd")
+    g2 = None if ln_weight is None else ln_weight.detach().contiguous()
+    b2 = None if ln_weight is None else ln_bias.detach().contiguous()
+    r2 = None if (ln_weight is None or residual is None) else residual.detach().reshape(-1, M).contiguous()
+    _lib.check(lib.emip_mlp_ln_tm_fwd(ptr(x2), ptr(w1), ptr(w2), ptr(g2), ptr(b2), ptr(r2), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n),
+                                      I(L_), I(K1), I(Hd), I(M), F(eps), stream_ptr()), "emip_mlp_ln_tm_fwd")
     return y.view(*x.shape[:-1], M)
 
 
@@ -172,13 +197,19 @@ def transformer_layer_forward(self, source, target, height=None, width=None, shi
                                                      attn_mask=shifted_window_attn_mask)
     else:
         message = single_head_full_attention(query, key, value)
+    if not (torch.is_grad_enabled() and (source.requires_grad or target.requires_grad)):
+        # inference: norm1 / norm2 (+ source) inside the epilogues of merge / mlp[2], GELU + operand split inside mlp[0]'s
+        n1 = self.norm1
+        if self.no_ffn:
+            return linear_ln_tm(message, self.merge.weight, n1.weight, n1.bias, n1.eps, residual=source)      # :171-172, :180
+        message = linear_ln_tm(message, self.merge.weight, n1.weight, n1.bias, n1.eps)
+        cat = torch.cat([source, message], dim=-1)                                                             # :175
+        return mlp_tm(cat, self.mlp[0].weight, self.mlp[2].weight, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                      residual=source)                                                                         # :175-176, :180
     message = linear_tm(message, self.merge.weight)                        # :171
     if self.no_ffn:
         return layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=source)   # :172, :180
     message = layer_norm_tm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)
     cat = torch.cat([source, message], dim=-1)                                                             # :175
-    if torch.is_grad_enabled() and cat.requires_grad:
-        message = _MlpTM.apply(cat, self.mlp[0].weight, self.mlp[2].weight)
-    else:                                                    # inference: GELU + operand split in the first GEMM's epilogue
-        message = mlp_tm(cat, self.mlp[0].weight, self.mlp[2].weight)
+    message = _MlpTM.apply(cat, self.mlp[0].weight, self.mlp[2].weight)
     return layer_norm_tm(message, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=source)     # :176, :180

@@ -148,6 +148,15 @@ int emip_linear_tm_fwd_ex(const float* x, const float* aux, const float* w, floa
 size_t emip_mlp_tm_workspace(int L, int K1, int Hd, int M);
 int emip_mlp_tm_fwd(const float* x, const float* w1, const float* w2, float* y, void* workspace, size_t ws_bytes, int L, int K1,
                     int Hd, int M, void* stream);
+/* No-grad fast paths with the LayerNorm (+ residual) of transformer.py:172 / :176 / :180 inside the GEMM epilogue (M = 128: one
+ * output row per thread, the statistics never leave the registers; the pre-norm tensor never reaches HBM):
+ *   emip_linear_ln_tm_fwd: y = res + LN(act(x) w^T) * gamma + beta                    (merge + norm1 [+ source])
+ *   emip_mlp_ln_tm_fwd:    y = res + LN(GELU(x w1^T) w2^T) * gamma + beta; gamma NULL = emip_mlp_tm_fwd   (mlp + norm2 + source)
+ * res may be NULL; workspaces as emip_linear_tm_workspace / emip_mlp_tm_workspace. */
+int emip_linear_ln_tm_fwd(const float* x, const float* w, const float* gamma, const float* beta, const float* res, float* y,
+                          void* workspace, size_t ws_bytes, int L, int M, int K, float eps, int flags, void* stream);
+int emip_mlp_ln_tm_fwd(const float* x, const float* w1, const float* w2, const float* gamma, const float* beta, const float* res,
+                       float* y, void* workspace, size_t ws_bytes, int L, int K1, int Hd, int M, float eps, void* stream);
 /* y = (res ? res : 0) + LayerNorm_C(x) * gamma + beta over the channel axis of [L,C] rows (C = 128), biased variance, eps as
  * nn.LayerNorm; the backward returns dx only (frozen affine parameters), statistics are recomputed from x. */
 int emip_layernorm_tm_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int L, int C,

@@ -743,3 +743,32 @@ def test_f2b_mlp_tm_fused_vs_fp64(L, K1, Hd, M):
     og = _MlpTM.apply(xg, dev(w1), dev(w2))
     og.backward(dev(wo))
     assert rel(og, ref) < TOL_EXACT and rel(xg.grad, xd.grad) < TOL_EXACT, (rel(og, ref), rel(xg.grad, xd.grad))
+
+
+@pytest.mark.parametrize("name", list(cases.F2B_CASES))
+def test_f2b_transformer_layer_inference_path_golden(golden, name):
+    """The no-grad path (LayerNorm + residual in the GEMM epilogues, fused MLP call) against the reference's vectors, and
+    against the autograd path of the same layer."""
+    from emip_b200.transformer_layer import transformer_layer_forward, linear_ln_tm, linear_tm, layer_norm_tm
+    g = golden(name)
+    s = cases.F2B_CASES[name]
+    d = cases.f2b_inputs(s)
+    mask = torch.zeros(1, device="cuda")
+    kw = dict(height=s["h"], width=s["w"], shifted_window_attn_mask=mask, attn_num_splits=s["k"])
+    for no_ffn in (True, False):
+        for shift in (False, True):
+            tag = ("self" if no_ffn else "cross") + ("_shift" if shift else "_plain")
+            layer = _Layer(d["params"], no_ffn, shift)
+            with torch.no_grad():
+                out = transformer_layer_forward(layer, dev(d["source"]), dev(d["target"]), **kw)
+            cases.check_packed(out, g[tag]["out"], TOL_EXACT, tag + " out (no-grad path)")
+            ref = transformer_layer_forward(layer, dev(d["source"]).requires_grad_(True), dev(d["target"]), **kw)
+            assert rel(out, ref) < 1e-5, (tag, rel(out, ref))
+    # ragged row count, offset mean, no residual
+    x, w = cases.randn(331, (777, 128), 2.0) + 0.7, cases.randn(332, (128, 128), 128 ** -0.5)
+    gm, bt = 1 + 0.2 * cases.randn(333, (128,)), 0.3 * cases.randn(334, (128,))
+    with torch.no_grad():
+        a = linear_ln_tm(dev(x), dev(w), dev(gm), dev(bt), 1e-5)
+        b = layer_norm_tm(linear_tm(dev(x), dev(w)), dev(gm), dev(bt), 1e-5)
+    refd = torch.nn.functional.layer_norm(x.double() @ w.double().T, (128,), gm.double(), bt.double(), 1e-5)
+    assert rel(a, refd) < TOL_EXACT and rel(a, b) < 1e-5, (rel(a, refd), rel(a, b))
