@@ -583,6 +583,14 @@ size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N) {
   return emip_align_up((size_t)B * M * Np * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
 }
 // with a pre-split A operand only the B operand needs scratch
+// rows [M][K] fp32 -> hi, lo bf16 [M][kpad(K)] (the A operand GemmNT::a_hi_pre takes): one split shared by several GEMMs
+int gemm_tc_split_rows(const float* x, int M, int K, void* hi, void* lo, cudaStream_t st) {
+  const int Kp = kpad(K);
+  split_w_kernel<<<dim3(split_w_blocks(M, Kp), 1, 1), 256, 0, st>>>(x, 0, K, 0, static_cast<__nv_bfloat16*>(hi),
+                                                                    static_cast<__nv_bfloat16*>(lo), M, K, Kp);
+  EMIP_CHECK_LAUNCH("gemm_tc_split_rows");
+  return EMIP_OK;
+}
 size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N) { return emip_align_up((size_t)K * 2 * kpad(N) * 2, 1024) + 1024; }
 
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit) {

@@ -58,6 +58,7 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 // c[b][m][k] = sum_n A(b)[m][n] * B'(b)[k][n] -- the arguments of gemm_nt (one result per batch entry, no N split).
 bool gemm_nt_tc_supported(const GemmNT& a);
 size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N);
+int gemm_tc_split_rows(const float* x, int M, int K, void* hi, void* lo, cudaStream_t st);   // fp32 rows -> bf16 hi, lo [M][kpad(K)]
 size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N);    // GemmNT::a_hi_pre set: only the B operand is split
 // nsplit > 1: the contraction axis is dealt to nsplit CTAs per tile; c then holds B * nsplit partial matrices
 // (c_stride_b apart, partial (b, s) at index b * nsplit + s) for the caller's batch reduction

@@ -141,6 +141,39 @@ extern "C" int emip_linear_tm_fwd_ex(const float* x, const float* aux, const flo
   return gemm_nt_tc(t, workspace, scratch_bytes, st, 1);
 }
 
+// y_i [L][M] = x [L][K] w_i^T for n weights of one shape: the rows are split once (q / k / v of a self-attention layer read the
+// same tokens, k / v of a cross-attention layer too)
+extern "C" size_t emip_linear_tm_multi_workspace(int L, int M, int K) {
+  if (!shape_ok(L, M, K) || K % 64 != 0) return 0;
+  return emip_align_up((size_t)L * K * 2 * 2, 1024) + gemm_nt_tc_scratch_bytes_presplit(M, K);
+}
+
+extern "C" int emip_linear_tm_multi_fwd(const float* x, const float* const* w, float* const* y, int n, void* workspace, size_t ws_bytes,
+                                        int L, int M, int K, void* stream) {
+  if (L == 0 || n == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && w && y && workspace && n > 0, "linear_tm_multi_fwd: null pointer");
+  if (!shape_ok(L, M, K) || K % 64 != 0) { emip_set_error("linear_tm_multi_fwd: unsupported shape L=%d M=%d K=%d (K %% 64 == 0)", L, M, K); return EMIP_ENOSYS; }
+  if (ws_bytes < emip_linear_tm_multi_workspace(L, M, K)) { emip_set_error("linear_tm_multi_fwd: workspace too small"); return EMIP_ENOMEM; }
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "linear_tm_multi_fwd: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* lo = hi + (size_t)L * K;
+  const size_t split_bytes = emip_align_up((size_t)L * K * 2 * 2, 1024);
+  int rc;
+  if ((rc = gemm_tc_split_rows(x, L, K, hi, lo, st))) return rc;
+  for (int i = 0; i < n; ++i) {
+    EMIP_CHECK_ARG(w[i] && y[i], "linear_tm_multi_fwd: null weight / output pointer");
+    GemmNT t = {};
+    t.B = 1; t.M = L; t.K = M; t.N = K;
+    t.a_hi_pre = hi; t.a_lo_pre = lo;
+    t.bm = w[i]; t.ldb = K;
+    t.c = y[i]; t.ldc = M;
+    if (!gemm_nt_tc_supported(t)) { emip_set_error("linear_tm_multi_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
+    if ((rc = gemm_nt_tc(t, static_cast<char*>(workspace) + split_bytes, ws_bytes - split_bytes, st, 1))) return rc;
+  }
+  return EMIP_OK;
+}
+
 namespace {
 size_t hid_bytes(int L, int Hd) { return emip_align_up((size_t)L * Hd * 2 * 2, 1024); }      // bf16 hi + lo
 bool mlp_shape_ok(int L, int K1, int Hd, int M) {

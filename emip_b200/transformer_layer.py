@@ -64,6 +64,51 @@ class _LinearTM(torch.autograd.Function):
         return dx.view(ctx.in_shape), None, None
 
 
+class _LinearMultiTM(torch.autograd.Function):
+    """Several bias-free layers of one shape on the same rows: one operand split, n GEMMs (``emip_linear_tm_multi_fwd``)."""
+
+    @staticmethod
+    def forward(ctx, x, *ws):
+        if any(ctx.needs_input_grad[1:]):
+            raise NotImplementedError("emip_b200 linear_tm: weight gradients are not built (the GMFlow weights are frozen, "
+                                      "train.py:340-342)")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        ws = [w.contiguous() for w in ws]
+        n, L_, M, K = len(ws), x2.shape[0], ws[0].shape[0], ws[0].shape[1]
+        lib = _lib.lib()
+        lib.emip_linear_tm_multi_workspace.restype = ctypes.c_size_t
+        need = lib.emip_linear_tm_multi_workspace(I(L_), I(M), I(K))
+        if need == 0:
+            raise _lib.EmipError(f"emip_b200 linear_tm_multi: unsupported shape L={L_} M={M} K={K}")
+        buf, ws_ptr, ws_n = workspace(need, x2.device)
+        ys = [torch.empty((L_, M), dtype=torch.float32, device=x2.device) for _ in ws]
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+        yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+        _lib.check(lib.emip_linear_tm_multi_fwd(ptr(x2), wp, yp, I(n), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K),
+                                                stream_ptr()), "emip_linear_tm_multi_fwd")
+        ctx.save_for_backward(*ws)
+        ctx.in_shape = x.shape
+        return tuple(y.view(*x.shape[:-1], M) for y in ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        dx = None
+        for w, dy in zip(ctx.saved_tensors, dys):
+            d = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w, W_TRANS)
+            dx = d if dx is None else dx.add_(d)
+        return (dx.view(ctx.in_shape),) + (None,) * len(dys)
+
+
+def linear_tm_multi(x, weights):
+    """``[F.linear(x, w) for w in weights]`` for weights of one shape."""
+    _check(x, "linear_tm_multi")
+    for w in weights:
+        _check(w, "linear_tm_multi")
+        if w.shape != weights[0].shape or w.dim() != 2 or w.shape[1] != x.shape[-1]:
+            raise ValueError("linear_tm_multi: weights must share one [M, K] shape with K = x.shape[-1]")
+    return _LinearMultiTM.apply(x, *weights)
+
+
 class _MlpTM(torch.autograd.Function):
     """mlp[2](GELU(mlp[0](x))) with autograd: the forward keeps the fp32 pre-activation, the backward applies GELU' inside the
     operand split of the mlp[0] input-gradient GEMM (no elementwise pass over the [L, 1024] tensors)."""
@@ -186,9 +231,11 @@ def layer_norm_tm(x, weight, bias, eps=1e-5, residual=None):
 def transformer_layer_forward(self, source, target, height=None, width=None, shifted_window_attn_mask=None,
                               attn_num_splits=None, **kwargs):
     """``TransformerLayer.forward`` (transformer.py:151-180): source, target [B, L, C] -> [B, L, C]."""
-    query = linear_tm(source, self.q_proj.weight)                          # :163
-    key = linear_tm(target, self.k_proj.weight)                            # :164
-    value = linear_tm(target, self.v_proj.weight)                          # :165
+    if source is target:                                                   # self-attention layer: q, k, v read the same rows
+        query, key, value = linear_tm_multi(source, [self.q_proj.weight, self.k_proj.weight, self.v_proj.weight])   # :163-165
+    else:
+        query = linear_tm(source, self.q_proj.weight)                      # :163
+        key, value = linear_tm_multi(target, [self.k_proj.weight, self.v_proj.weight])                              # :164-165
     if self.attention_type == 'swin' and attn_num_splits > 1:
         if self.nhead > 1:
             raise NotImplementedError                                      # as the reference (:168-171)

@@ -136,6 +136,11 @@ int emip_linear_cn_bwd(const float* x, const float* w, const float* dy, float* d
 size_t emip_linear_tm_workspace(int L, int M, int K);
 int emip_linear_tm_fwd(const float* x, const float* w, float* y, void* workspace, size_t ws_bytes, int L, int M, int K, int flags,
                        void* stream);
+/* n layers of one shape on the same rows (q / k / v of a self-attention layer, k / v of a cross-attention layer,
+ * transformer.py:163-165): y[i] = x w[i]^T with the rows split once.  w, y: host arrays of n device pointers.  K % 64 == 0. */
+size_t emip_linear_tm_multi_workspace(int L, int M, int K);
+int emip_linear_tm_multi_fwd(const float* x, const float* const* w, float* const* y, int n, void* workspace, size_t ws_bytes, int L,
+                             int M, int K, void* stream);
 /* EMIP_LINEAR_GELU_BWD_IN: the rows are x * GELU'(aux), aux laid out like x (the pre-activation the forward kept) -- with
  * EMIP_LINEAR_W_TRANS this is the input gradient of mlp[0] with the derivative of mlp[1] applied on load. */
 #define EMIP_LINEAR_GELU_BWD_IN 4

@@ -772,3 +772,26 @@ def test_f2b_transformer_layer_inference_path_golden(golden, name):
         b = layer_norm_tm(linear_tm(dev(x), dev(w)), dev(gm), dev(bt), 1e-5)
     refd = torch.nn.functional.layer_norm(x.double() @ w.double().T, (128,), gm.double(), bt.double(), 1e-5)
     assert rel(a, refd) < TOL_EXACT and rel(a, b) < 1e-5, (rel(a, refd), rel(a, b))
+
+
+def test_f2b_self_layer_shared_split_vs_separate_calls():
+    """source is target (how TransformerBlock calls the self-attention layer, transformer.py:383-389): q / k / v come from one
+    operand split (emip_linear_tm_multi_fwd); same outputs and gradients as the three separate calls, and as fp64."""
+    from emip_b200.transformer_layer import transformer_layer_forward, linear_tm_multi
+    s = cases.F2B_CASES["f2b_small"]
+    d = cases.f2b_inputs(s)
+    layer = _Layer(d["params"], True, True)
+    kw = dict(height=s["h"], width=s["w"], shifted_window_attn_mask=torch.zeros(1, device="cuda"), attn_num_splits=s["k"])
+    x = dev(d["source"]).requires_grad_(True)
+    a = transformer_layer_forward(layer, x, x, **kw)
+    a.backward(dev(d["wout"]))
+    x1, x2 = dev(d["source"]).requires_grad_(True), dev(d["source"]).requires_grad_(True)
+    b = transformer_layer_forward(layer, x1, x2, **kw)
+    b.backward(dev(d["wout"]))
+    assert rel(a, b) < 1e-6 and rel(x.grad, x1.grad + x2.grad) < 1e-5, (rel(a, b), rel(x.grad, x1.grad + x2.grad))
+    with torch.no_grad():
+        assert rel(transformer_layer_forward(layer, x.detach(), x.detach(), **kw), b) < 1e-5
+    xs, ws = cases.randn(341, (301, 192), 1.3), [cases.randn(342 + i, (40, 192), 192 ** -0.5) for i in range(3)]
+    ys = linear_tm_multi(dev(xs), [dev(w) for w in ws])
+    for y, w in zip(ys, ws):
+        assert rel(y, xs.double() @ w.double().T) < TOL_EXACT
