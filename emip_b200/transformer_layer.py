@@ -5,10 +5,12 @@ has the signature of ``TransformerLayer.forward`` (:151-158) and reads the refer
 (``q_proj / k_proj / v_proj / merge / norm1 / mlp / norm2``, same ``state_dict`` keys); ``dropin.install`` binds it as
 that method.  Per block it issues
 
-    q / k / v / merge / mlp[0] / mlp[2]   ``emip_linear_tm_fwd``: split-bf16 tensor-core GEMMs on the token rows, the
-                                          exact GELU of mlp[1] applied inside the operand split of mlp[2]
-    attention                             ``emip_window_attention_fwd_tc`` / ``emip_attention_fwd_tc`` (window_attn.py)
-    norm1 / norm2 (+ ``source + ...``)    ``emip_layernorm_tm_fwd``: one warp per token row, residual folded in
+    q / k / v                 ``emip_linear_tm_multi_fwd``: one bf16 hi | lo split of the token rows, three (two) tcgen05 GEMMs
+    attention                 ``emip_window_attention_fwd_tc`` / ``emip_attention_fwd_tc`` (window_attn.py)
+    no-grad path              ``emip_linear_ln_tm_fwd`` (merge + norm1 [+ source]) and ``emip_mlp_ln_tm_fwd`` (mlp + norm2 + source):
+                              GELU + operand split in the first MLP GEMM's epilogue, LayerNorm + residual in the N = 128 epilogues
+    autograd path             ``emip_linear_tm_fwd`` per layer (GELU inside the operand split of mlp[2], GELU' inside the split
+                              of the mlp[0] input-gradient GEMM) and ``emip_layernorm_tm_fwd / _bwd`` (one warp per token row)
 
 The GMFlow weights are frozen (train.py:340-342): the backward returns the gradient of the token rows only and raises
 for a weight that requires a gradient.  There is no CPU or library fallback.
