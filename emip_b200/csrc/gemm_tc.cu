@@ -17,6 +17,7 @@ using namespace tc;
 
 constexpr int KCH = GEMM_TC_KCH;
 constexpr int A_BYTES = GEMM_TC_A_BYTES;
+constexpr int EPI_STAGE_BYTES = 8 * 32 * 33 * 4;   // eight epilogue warps x [32 rows][33 words]
 constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA producer; 5: UMMA issuer
 
 // exact-GELU x Phi(x) for the epilogue (where the instruction count is the critical path): Phi through the rational
@@ -172,6 +173,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // epilogues run side by side (r3: with K <= 256 the epilogue, not the MMA loop, bounds a tile).  A warp reads the TMEM
     // lane quarter warp % 4.
     const int grp = warp >= 6 ? 1 : 0, qw = warp & 3;
+    // warp-private staging tile [32 rows][33 words] behind the barriers: a thread's 32 accumulator columns go in as a row,
+    // come out as 4 rows x 128 B per warp store (r3h: the row-per-thread stores touched 32 lines per instruction)
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 15) & ~15)) +
+                    (grp * 4 + qw) * (32 * 33);
     uint32_t it = grp;
     for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     int nt, mt, b;
@@ -279,13 +284,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             hi[i] = *reinterpret_cast<const uint32_t*>(&h);
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
           }
-          uint4* dh = reinterpret_cast<uint4*>(gh + c0);
-          uint4* dl = reinterpret_cast<uint4*>(gl + c0);
+          if (p.epi_stage) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            for (int i = 0; i < 16; ++i) { stg[lane * 33 + i] = hi[i]; stg[lane * 33 + 16 + i] = lo[i]; }
+          } else {
+            uint4* dh = reinterpret_cast<uint4*>(gh + c0);
+            uint4* dl = reinterpret_cast<uint4*>(gl + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
           }
+        }
+        if (p.epi_stage && n0 + c0 < p.N) {                 // warp-uniform
+          __syncwarp();
+#pragma unroll
+          for (int it2 = 0; it2 < 4; ++it2) {
+            const int rr = it2 * 8 + (lane >> 2), w0 = (lane & 3) * 4;
+            const int grow = mt * TM + qw * 32 + rr;
+            const uint32_t* sp = stg + rr * 33 + w0;
+            const uint4 vh = make_uint4(sp[0], sp[1], sp[2], sp[3]), vl = make_uint4(sp[16], sp[17], sp[18], sp[19]);
+            if (grow < p.M) {
+              const size_t off = (size_t)grow * p.ldg + n0 + c0 + w0 * 2;
+              *reinterpret_cast<uint4*>(p.g_hi + off) = vh;
+              *reinterpret_cast<uint4*>(p.g_lo + off) = vl;
+            }
+          }
+          __syncwarp();
         }
       }
     } else if (p.mode == 2) {
@@ -298,7 +324,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
         const int n = min(32, p.N - n0 - c0);
-        if (row < p.M && n > 0) {
+        const float* yb = p.y + (size_t)b * p.y_stride_b + n0 + c0;
+        const float* rb0 = p.res ? p.res + (size_t)b * p.res_stride_b + n0 + c0 : nullptr;
+        if (p.epi_stage && n == 32 && (p.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yb) & 15) == 0 &&
+            (!rb0 || ((p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(rb0) & 15) == 0))) {       // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __float_as_uint(__uint_as_float(r[i]) + rb);
+          __syncwarp();
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const int rr = it2 * 4 + (lane >> 3), cc = (lane & 7) * 4;
+            const int grow = mt * TM + qw * 32 + rr;
+            const uint32_t* sp = stg + rr * 33 + cc;
+            float4 v = make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
+            if (grow < p.M) {
+              if (rb0) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rb0 + (size_t)grow * p.ldr + cc));
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+              }
+              *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)grow * p.ldy + cc) = v;
+            }
+          }
+          __syncwarp();
+        } else if (row < p.M && n > 0) {
           if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs + c0) & 15) == 0)) {
             float4* d = reinterpret_cast<float4*>(o + c0);
 #pragma unroll
@@ -493,7 +541,8 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   if (p.stages == 0) {
     p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024);
     p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
-    p.stages = (max_smem - 2048) / p.stage_bytes;
+    p.epi_stage = p.mode == 2 ? 1 : 0;
+    p.stages = (max_smem - 2048 - (p.epi_stage ? EPI_STAGE_BYTES : 0)) / p.stage_bytes;
     if (p.stages > 3) p.stages = 3;
     if (p.stages > p.kchunks) p.stages = p.kchunks;
   }
@@ -501,7 +550,7 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   EMIP_CHECK_ARG(tiles > 0 && tiles < 0x7fffffffLL, "gemm_tc: bad tile count");
   p.total_tiles = (int)tiles;
   const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0);
   gemm_tc_kernel<<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p);
   EMIP_CHECK_LAUNCH("gemm_tc");
   return EMIP_OK;

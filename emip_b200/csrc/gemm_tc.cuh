@@ -36,6 +36,7 @@ struct GemmTcParams {
   int out_split, ldg;
   // mode 2, ln_gamma != NULL (N == n_tile == 128, one output row per thread): y = res + LayerNorm_N(tile) * gamma + beta
   const float* ln_gamma; const float* ln_beta; float ln_eps;
+  int epi_stage;            // mode 2: per-warp shared-memory staging of the epilogue (set by gemm_tc_launch): coalesced row stores
 };
 
 constexpr int GEMM_TC_KCH = 64;                    // K elements per chunk (one 128-byte swizzle row of bf16)
