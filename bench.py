@@ -136,7 +136,7 @@ def run_reference(args):
                          "sample": f"{len(times)} full passes of the c2 batch ({B_PER_GPU} pairs) on host cores"},
         "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -149,8 +149,28 @@ def workload_config(n_gpus):
             "sharding": f"batch-sharded x{n_gpus}, no data-path collective"}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep fd 1 for the ONE JSON line: everything else that writes to stdout from here on -- including C-level prints such as
+    NCCL's version banner under torchrun -- goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(1 if _JSON_FD is None else _JSON_FD, data)
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -325,7 +345,7 @@ def main():
             cv = B_PER_GPU / (sum(times) / len(times))
             line["cpu_baseline"] = {"value": cv, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"{len(times)} full passes of the c2 batch ({B_PER_GPU} pairs), torch CPU fp32"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
