@@ -108,3 +108,23 @@ def test_dropin_rebinds_reference_symbols():
     import model.EMIP_short.motion.gmflow.matching as ref_matching
     assert gm.global_correlation_softmax is ref_matching.global_correlation_softmax
     assert tr.TransformerLayer.forward is not transformer_layer_forward
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py reserves fd 1 for the JSON line (C-level prints such as NCCL's banner go to stderr); rank != 0 of the
+    reference arm exits 0 without output."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frame-pairs/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    env = dict(os.environ, WORLD_SIZE="2", RANK="1", LOCAL_RANK="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
