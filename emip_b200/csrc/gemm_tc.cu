@@ -25,13 +25,16 @@ constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA 
 // below the 2^-17 relative resolution of the bf16 hi | lo pair the value is stored as.  One MUFU.RCP + one MUFU.EX2 and
 // ~12 FP32 instructions instead of erff's two-branch polynomial; no 1 + erf cancellation for negative x.
 __device__ __forceinline__ float gelu_epi(float x) {
+  // 0.5 folded into the polynomial; rcp / ex2 as single MUFU instructions (.ftz: t is in (0, 1], e^{-z^2} may flush to 0)
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float g = 0.5f * p * t * __expf(-z * z);               // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.44269504088896340736f * z));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float g = p * t * e;                                   // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
   return x * (x >= 0.f ? 1.f - g : g);
 }
 
@@ -270,18 +273,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_wait(r);
         if (row < p.M && n0 + c0 < p.N) {
           uint32_t hi[16], lo[16];
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.out_split == 2) {                             // one uniform branch per chunk, not per element
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_epi(v[i]);
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
-            if (p.out_split == 2) {
-              v0 = gelu_epi(v0);
-              v1 = gelu_epi(v1);
-            }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
-            const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
-                                                         __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);            // one packed conversion
             hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - __uint_as_float(hi[i] << 16),
+                                                           v[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
           }
           if (p.epi_stage) {
