@@ -1,0 +1,434 @@
+"""The chained motion-stream hot path of ``CoUpdater.forward`` between the backbones and the decoder, on our own kernels.
+
+Reference: model/EMIP_short/model.py:92-97
+
+    a = self.injector(fea_1_gm[0], fea_1[0]);  b = self.injector(fea_2_gm[0], fea_2[0])      # camouflaged feeder x2
+    flow_fw, flow_bw, corr = self.GMFlow([a], [b])                                            # gmflow.py:81-162
+    corr = self.conv_corr(corr);  fea_new = self.injector1(fea_1[0], corr)                    # motion collector
+
+with ``GMFlow.forward`` (num_scales 1, pred_bidir_flow, eval) = position add (utils.py:66-86) -> FeatureTransformer
+(transformer.py:433-482) -> global matching (matching.py:8-41) -> flow propagation (transformer.py:503-533) -> convex x8
+upsampling (gmflow.py:56-79).  ``MotionChain`` runs exactly that sequence, inference only, with the data kept in the layout
+the next kernel wants:
+
+  * both frames go through the camouflaged feeder as ONE call (same weights, batch 2B);
+  * the feeder's output is transposed to token rows with the window position embedding added on the way
+    (``emip_tokens_from_cn``) and stays token-major through the twelve transformer layers; the batch-swapped copy
+    ``concat1`` (transformer.py:462, :473) is never made -- the cross-attention kernels read the keys / values of the other half
+    of the block's input rows (``EMIP_WINATTN_KV_SWAP_HALVES``);
+  * matching (lazy ``corr``), the flow-propagation projections, the upsampler convolution and the re-associated
+    ``conv_corr[0]`` all take the token rows directly (no ``permute(0, 3, 1, 2).contiguous()`` of transformer.py:479-480);
+  * ``conv_corr[1:3]`` (eval BatchNorm + ReLU) live in the epilogue of the ``conv_corr[0]`` GEMM, ``conv_corr[3]`` and
+    ``upsampler[0]`` are tensor-core 3x3 convolutions whose im2col is a shifted TMA box (csrc/conv_tm.cu).
+
+The module owns (or borrows, ``MotionChain.wrap``) parameters under the reference's ``state_dict`` keys, so a reference
+checkpoint loads with ``strict=False`` key filtering exactly as test.py:85-89 does.  There is no CPU / library fallback.
+"""
+import ctypes
+import math
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import I, SZ, ptr, stream_ptr
+from ._ws import workspace
+from .conv_corr import CorrConv2d, _prepared_weight as _prepared_corr_weight
+from .flow_attn import FeatureFlowAttention, flow_attention_core
+from .injector import Injector
+from .transformer_layer import linear_ln_tm, linear_tm_multi, mlp_tm
+from .upsample import upsample_flow_convex
+
+LAYOUT_NC, LAYOUT_CN = 0, 1
+TOKEN_MAJOR = 16
+KV_SWAP = 1
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class _TransformerLayer(nn.Module):             # transformer.py:108-149 (parameters only; the adaptor layers are unused)
+    def __init__(self, d_model=128, no_ffn=False, with_shift=False, ffn_dim_expansion=4):
+        super().__init__()
+        self.no_ffn, self.with_shift = no_ffn, with_shift
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.norm1 = nn.LayerNorm(d_model)
+        if not no_ffn:
+            self.mlp = nn.Sequential(nn.Linear(2 * d_model, 2 * d_model * ffn_dim_expansion, bias=False), nn.GELU(),
+                                     nn.Linear(2 * d_model * ffn_dim_expansion, d_model, bias=False))
+            self.norm2 = nn.LayerNorm(d_model)
+
+
+class _TransformerBlock(nn.Module):             # transformer.py:349-375
+    def __init__(self, with_shift):
+        super().__init__()
+        self.self_attn = _TransformerLayer(no_ffn=True, with_shift=with_shift)
+        self.cross_attn_ffn = _TransformerLayer(no_ffn=False, with_shift=with_shift)
+
+
+class _FeatureTransformer(nn.Module):           # transformer.py:404-430
+    def __init__(self, num_layers=6):
+        super().__init__()
+        self.layers = nn.ModuleList([_TransformerBlock(with_shift=(i % 2 == 1)) for i in range(num_layers)])
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class _GMFlowPath(nn.Module):                   # gmflow.py:33-46 without the CNN encoder (out of scope)
+    def __init__(self):
+        super().__init__()
+        self.transformer = _FeatureTransformer()
+        self.feature_flow_attn = FeatureFlowAttention(128)
+        self.upsampler = nn.Sequential(nn.Conv2d(2 + 128, 256, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv2d(256, 8 ** 2 * 9, 1, 1, 0))
+
+
+# ------------------------------------------------------------------------------------------------ prepared operands
+class _VersionCache:
+    """Derived tensors (prepared weights, folded BatchNorm) rebuilt when any source parameter changes (optimizer step, load)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, name, sources, make):
+        sig = tuple((id(t), t._version, t.data_ptr(), t.device) for t in sources)
+        ent = self._d.get(name)
+        if ent is None or ent[0] != sig:
+            ent = (sig, make())
+            self._d[name] = ent
+        return ent[1]
+
+
+_pos_cache = {}
+
+
+def window_position(h, w, splits, channels, device):
+    """[C, h*w] sine embedding of one (h/splits x w/splits) window, tiled over the map: what feature_add_position
+    (utils.py:66-86) adds to both feature maps; PositionEmbeddingSine(num_pos_feats = C/2), position.py:24-46."""
+    key = (h, w, splits, channels, str(device))
+    pos = _pos_cache.get(key)
+    if pos is None:
+        K = splits if splits > 1 else 1
+        hh, ww, F = h // K, w // K, channels // 2
+        eps, scale = 1e-6, 2 * math.pi
+        y = torch.arange(1, hh + 1, dtype=torch.float32)
+        x = torch.arange(1, ww + 1, dtype=torch.float32)
+        y = y / (y[-1] + eps) * scale
+        x = x / (x[-1] + eps) * scale
+        i = torch.arange(F, dtype=torch.float32)
+        dim_t = 10000.0 ** (2 * torch.div(i, 2, rounding_mode="floor") / F)
+        px, py = x[:, None] / dim_t, y[:, None] / dim_t
+        px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)
+        py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)
+        p = torch.cat((py[:, None, :].expand(hh, ww, F), px[None, :, :].expand(hh, ww, F)), dim=2).permute(2, 0, 1)
+        pos = p.repeat(1, K, K).reshape(channels, h * w).contiguous().to(device)
+        _pos_cache[key] = pos
+    return pos
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI calls
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.EmipError(f"emip_b200 {what} needs CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"emip_b200 {what} computes from fp32 tensors")
+
+
+def tokens_from_cn(x, pos=None):
+    """[B,C,H,W] (+ pos [C,H*W]) -> token rows [B,H*W,C]."""
+    _need_cuda(x, "tokens_from_cn")
+    B, C = x.shape[0], x.shape[1]
+    N = x.numel() // (B * C)
+    x = x.contiguous()
+    out = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().emip_tokens_from_cn(ptr(x), ptr(pos), ptr(out), I(B), I(C), I(N), stream_ptr()), "emip_tokens_from_cn")
+    return out
+
+
+def linear_tm_bias(x, weight, bias):
+    """``F.linear(x, weight, bias)`` on [..., K] token rows (forward only)."""
+    _need_cuda(x, "linear_tm_bias")
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    w, b = weight.detach().contiguous(), bias.detach().contiguous()
+    L_, M, K = x2.shape[0], w.shape[0], w.shape[1]
+    lib = _lib.lib()
+    lib.emip_linear_tm_workspace.restype = ctypes.c_size_t
+    need = lib.emip_linear_tm_workspace(I(L_), I(M), I(K))
+    if need == 0:
+        raise _lib.EmipError(f"emip_b200 linear_tm_bias: unsupported shape L={L_} M={M} K={K}")
+    ws, ws_ptr, ws_n = workspace(need, x2.device)
+    y = torch.empty((L_, M), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.emip_linear_tm_bias_fwd(ptr(x2), ptr(w), ptr(b), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(L_), I(M), I(K),
+                                               stream_ptr()), "emip_linear_tm_bias_fwd")
+    return y.view(*x.shape[:-1], M)
+
+
+def window_attention(q, k, v, num_splits, with_shift, h, w, kv_swap_halves=False):
+    """Forward of one FeatureTransformer attention layer on [B, h*w, C] token rows (no autograd graph);
+    ``kv_swap_halves``: image i reads the keys / values of image (i + B/2) % B."""
+    _need_cuda(q, "window_attention")
+    b, _, c = q.shape
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    L = _lib.lib()
+    L.emip_window_attention_tc_workspace.restype = ctypes.c_size_t
+    need = L.emip_window_attention_tc_workspace(I(b), I(h), I(w), I(c), I(num_splits), I(int(with_shift)))
+    if need == 0 and b > 0:
+        raise _lib.EmipError(f"emip_b200 window attention: unsupported geometry h={h} w={w} C={c} num_splits={num_splits}")
+    ws, ws_ptr, ws_n = workspace(need, q.device)
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        _lib.check(L.emip_window_attention_fwd_tc_ex(ptr(q), ptr(k), ptr(v), ptr(out), None, ctypes.c_void_p(ws_ptr), SZ(ws_n), I(b),
+                                                     I(h), I(w), I(c), I(num_splits), I(int(with_shift)),
+                                                     I(KV_SWAP if kv_swap_halves else 0), stream_ptr()),
+                   "emip_window_attention_fwd_tc_ex")
+    return out
+
+
+def conv3x3(x0, layout0, x1, layout1, w_prep, out_channels, h, w, scale=None, shift=None, relu=False):
+    """3x3 / stride 1 / zero-pad 1 convolution of cat(x0, x1) (channel axis) -> [B, O, h, w]; sources are [B,C,h,w]
+    (``LAYOUT_CN``) or token rows [B,h*w,C] (``LAYOUT_NC``); ``w_prep`` from ``prepare_conv3x3``."""
+    _need_cuda(x0, "conv3x3")
+    B = x0.shape[0]
+    c0 = x0.shape[1] if layout0 == LAYOUT_CN else x0.shape[-1]
+    c1 = 0 if x1 is None else (x1.shape[1] if layout1 == LAYOUT_CN else x1.shape[-1])
+    x0 = x0.contiguous()
+    x1 = None if x1 is None else x1.contiguous()
+    L = _lib.lib()
+    if not L.emip_conv3x3_supported(I(c0 + c1), I(h), I(w)):
+        raise _lib.EmipError(f"emip_b200 conv3x3: unsupported shape Cin={c0 + c1} h={h} w={w}")
+    L.emip_conv3x3_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_conv3x3_workspace(I(B), I(c0 + c1), I(h), I(w)), x0.device)
+    out = torch.empty((B, out_channels, h, w), dtype=torch.float32, device=x0.device)
+    with torch.cuda.device(x0.device):
+        _lib.check(L.emip_conv3x3_fwd(ptr(x0), I(c0), I(layout0), ptr(x1), I(c1), I(layout1), ctypes.c_void_p(w_prep[1]), ptr(scale),
+                                      ptr(shift), I(int(relu)), ptr(out), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(h), I(w),
+                                      I(out_channels), stream_ptr()), "emip_conv3x3_fwd")
+    return out
+
+
+def prepare_conv3x3(weight):
+    """bf16 hi | lo, (o; tap, c)-major copy of a [O, Cin, 3, 3] weight: (buffer, aligned pointer)."""
+    L = _lib.lib()
+    O, Cin = weight.shape[0], weight.shape[1]
+    L.emip_conv3x3_weight_bytes.restype = ctypes.c_size_t
+    buf, p, _ = workspace(L.emip_conv3x3_weight_bytes(I(O), I(Cin)), weight.device)
+    w = weight.detach().contiguous()
+    with torch.cuda.device(weight.device):
+        _lib.check(L.emip_conv3x3_prepare_weight(ptr(w), ctypes.c_void_p(p), I(O), I(Cin), stream_ptr()), "emip_conv3x3_prepare_weight")
+    return buf, p
+
+
+def conv1x1_cn(x, weight, bias):
+    """1x1 convolution with bias on a channel-major map [B,K,h,w] -> [B,M,h,w] (``emip_linear_cn_fwd``, tensor cores)."""
+    _need_cuda(x, "conv1x1")
+    B, K, h, w = x.shape
+    N = h * w
+    wt = weight.detach().reshape(weight.shape[0], K).contiguous()
+    M = wt.shape[0]
+    L = _lib.lib()
+    L.emip_linear_cn_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_linear_cn_workspace(I(B), I(M), I(K), I(N)), x.device)
+    y = torch.empty((B, M, h, w), dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.detach().contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.emip_linear_cn_fwd(ptr(x.contiguous()), ptr(wt), ptr(b), ptr(y), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(M),
+                                        I(K), I(N), stream_ptr()), "emip_linear_cn_fwd")
+    return y
+
+
+def global_matching_tokens(tok, B, h, w, bf16=False):
+    """Bidirectional global matching on the transformer's token rows: tok [2B, h*w, 128] (frame 1 | frame 2) ->
+    flow [2B, 2, h, w] (forward flows, then backward flows); the cost volume is not written (matching.py:8-41)."""
+    L = _lib.lib()
+    C = tok.shape[-1]
+    L.emip_global_matching_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_global_matching_workspace(I(B), I(C), I(h), I(w)), tok.device)
+    flow = torch.empty((2 * B, 2, h, w), dtype=torch.float32, device=tok.device)
+    f0, f1 = tok[:B], tok[B:]
+    with torch.cuda.device(tok.device):
+        _lib.check(L.emip_global_matching_fwd(ptr(f0), ptr(f1), ptr(flow), None, None, ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C),
+                                              I(h), I(w), I(1), I(TOKEN_MAJOR | (4 if bf16 else 0)), stream_ptr()),
+                   "emip_global_matching_fwd")
+    return flow
+
+
+def conv_corr_head(tok, B, h, w, conv0, w_prep, scale, shift):
+    """conv_corr[0:3] on the never-materialised cost volume of the token rows: relu(bn(conv(corr))) -> [B, O, h, w]."""
+    L = _lib.lib()
+    C, O = tok.shape[-1], conv0.weight.shape[0]
+    if not L.emip_conv_corr_supported(I(C), I(h), I(w)):
+        raise _lib.EmipError(f"emip_b200 conv_corr: unsupported shape C={C} H={h} W={w}")
+    L.emip_conv_corr_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_conv_corr_workspace(I(B), I(C), I(h), I(w), I(O)), tok.device)
+    out = torch.empty((B, O, h, w), dtype=torch.float32, device=tok.device)
+    with torch.cuda.device(tok.device):
+        _lib.check(L.emip_conv_corr_fwd_ex(ptr(tok[:B]), ptr(tok[B:]), ctypes.c_void_p(w_prep), None, ptr(scale), ptr(shift), I(1),
+                                           I(LAYOUT_NC), ptr(out), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C), I(h), I(w), I(O),
+                                           stream_ptr()), "emip_conv_corr_fwd_ex")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ the chain
+def transformer_block(blk, x, h, w, num_splits):
+    """One FeatureTransformer block (transformer.py:377-401) on token rows x [2B, h*w, C] = (frame 1 | frame 2), inference:
+    self-attention layer, then cross-attention + FFN layer whose keys / values come from the block's INPUT rows of the other
+    frame (``concat1`` is refreshed once per block, transformer.py:464-473)."""
+    if num_splits <= 1:
+        raise NotImplementedError("MotionChain runs the configured split-window attention (attn_splits_list: [2])")
+    x_in = x
+    lay = blk.self_attn
+    q, k, v = linear_tm_multi(x, [lay.q_proj.weight.detach(), lay.k_proj.weight.detach(), lay.v_proj.weight.detach()])   # :163-165
+    msg = window_attention(q, k, v, num_splits, lay.with_shift, h, w)                                   # :167-176
+    n1 = lay.norm1
+    x = linear_ln_tm(msg, lay.merge.weight, n1.weight, n1.bias, n1.eps, residual=x)                     # :171-172, :180
+    lay = blk.cross_attn_ffn
+    (q,) = linear_tm_multi(x, [lay.q_proj.weight.detach()])                                             # :163
+    k, v = linear_tm_multi(x_in, [lay.k_proj.weight.detach(), lay.v_proj.weight.detach()])              # :164-165 (target rows, un-swapped)
+    msg = window_attention(q, k, v, num_splits, lay.with_shift, h, w, kv_swap_halves=True)
+    n1 = lay.norm1
+    msg = linear_ln_tm(msg, lay.merge.weight, n1.weight, n1.bias, n1.eps)
+    return mlp_tm(torch.cat([x, msg], dim=-1), lay.mlp[0].weight, lay.mlp[2].weight, lay.norm2.weight, lay.norm2.bias,
+                  lay.norm2.eps, residual=x)                                                            # :175-176, :180
+
+
+class MotionChain(nn.Module):
+    """``forward(gm, seg)``: gm, seg [2B, 128, H, W] = GMFlow-encoder / segmentation-backbone features of (frame 1 | frame 2)
+    -> ``(flow_fw [B,2,8H,8W], flow_bw, corr [B,128,H,W], fea_new [B,128,H,W])`` = what model.py:92-97 computes in eval mode
+    (``corr`` = conv_corr output, ``fea_new`` = motion-collector output that feeds ``dr1`` + the decoder)."""
+
+    def __init__(self, hw=44 * 44, corr_mid=968, attn_splits=2, _borrow=None):
+        super().__init__()
+        if _borrow is None:
+            self.injector = Injector()
+            self.injector1 = Injector()
+            self.GMFlow = _GMFlowPath()
+            self.conv_corr = nn.Sequential(CorrConv2d(hw, corr_mid, 3, 1, 1), nn.BatchNorm2d(corr_mid), nn.ReLU(inplace=True),
+                                           nn.Conv2d(corr_mid, 128, 3, 1, 1))
+        else:
+            self.injector, self.injector1, self.GMFlow, self.conv_corr = _borrow
+        self.attn_splits = attn_splits
+        self._cache = _VersionCache()
+
+    @classmethod
+    def wrap(cls, model):
+        """A chain over the submodules of a constructed ``CoUpdater`` (parameters shared, nothing copied)."""
+        return cls(attn_splits=model.GMFlow.attn_splits_list[0] if hasattr(model.GMFlow, "attn_splits_list") else 2,
+                   _borrow=(model.injector, model.injector1, model.GMFlow, model.conv_corr))
+
+    def _prepared(self):
+        up0, cc = self.GMFlow.upsampler[0], self.conv_corr
+        c = self._cache
+        w_up = c.get("up0", [up0.weight], lambda: prepare_conv3x3(up0.weight))
+        w_c3 = c.get("cc3", [cc[3].weight], lambda: prepare_conv3x3(cc[3].weight))
+        bn = cc[1]
+
+        def fold():
+            scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+            b0 = cc[0].bias.detach() if cc[0].bias is not None else torch.zeros_like(scale)
+            return scale.contiguous(), ((b0 - bn.running_mean) * scale + bn.bias.detach()).contiguous()
+        srcs = [bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([cc[0].bias] if cc[0].bias is not None else [])
+        scale, shift = c.get("bn", srcs, fold)
+        return w_up, w_c3, scale, shift
+
+    def forward(self, gm, seg, want=()):
+        if torch.is_grad_enabled() and (gm.requires_grad or seg.requires_grad or any(p.requires_grad for p in self.injector.parameters())):
+            raise _lib.EmipError("MotionChain is the inference path (call it under torch.no_grad()); training goes through "
+                                 "the per-op drop-ins with their backward kernels")
+        if self.conv_corr[1].training:
+            raise _lib.EmipError("MotionChain folds conv_corr's BatchNorm with its running statistics: call .eval() first")
+        _need_cuda(gm, "MotionChain")
+        _need_cuda(seg, "MotionChain")
+        if gm.shape != seg.shape or gm.dim() != 4 or gm.shape[0] % 2 or gm.shape[1] != 128:
+            raise ValueError(f"expected gm, seg [2B,128,H,W] (frame 1 | frame 2), got {tuple(gm.shape)}, {tuple(seg.shape)}")
+        B2, C, H, W = gm.shape
+        B, N = B2 // 2, H * W
+        dev = gm.device
+        w_up, w_c3, bn_scale, bn_shift = self._prepared()
+        gmf = self.GMFlow
+        with torch.cuda.device(dev):
+            ab = self.injector(gm, seg)                                                          # model.py:92-93, one call
+            x = tokens_from_cn(ab, window_position(H, W, self.attn_splits, C, dev))              # gmflow.py:114 + transformer.py:439-462
+            for blk in gmf.transformer.layers:                                                   # transformer.py:464-473
+                x = transformer_block(blk, x, H, W, self.attn_splits)
+            flow_pred = global_matching_tokens(x, B, H, W)              # gmflow.py:121
+            ffa = gmf.feature_flow_attn
+            q = linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)                            # transformer.py:523
+            k = linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)                            # transformer.py:524
+            flow = flow_attention_core(q, k, flow_pred.view(B2, 2, N)).view(B2, 2, H, W)   # gmflow.py:137
+            up = gmf.upsampler
+            hid = conv3x3(flow, LAYOUT_CN, x, LAYOUT_NC, w_up, up[0].weight.shape[0], H, W, shift=up[0].bias.detach(), relu=True)
+            mask = conv1x1_cn(hid, up[2].weight, up[2].bias)                                     # gmflow.py:64
+            flow_up = upsample_flow_convex(flow, mask, 8)                                        # gmflow.py:66-77
+            cc = self.conv_corr
+            c1 = conv_corr_head(x, B, H, W, cc[0], _prepared_corr_weight(cc[0].weight)[1], bn_scale, bn_shift)      # model.py:59-61, :96
+            corr = conv3x3(c1, LAYOUT_CN, None, LAYOUT_CN, w_c3, cc[3].weight.shape[0], H, W, shift=cc[3].bias.detach())
+            fea_new = self.injector1(seg[:B], corr)                                              # model.py:97
+        if want:
+            loc = dict(ab=ab, feat_tok=x, flow_pred=flow_pred, flow_prop=flow, mask=mask, corr1=c1)
+            return flow_up[:B], flow_up[B:], corr, fea_new, {k: loc[k] for k in want}
+        return flow_up[:B], flow_up[B:], corr, fea_new                                           # gmflow.py:152-155
+
+
+class GraphedChain:
+    """One ``MotionChain.forward`` on fixed device buffers captured into a CUDA graph: ``replay()`` re-runs the ~150 kernel
+    launches of a step as one graph launch (the per-GPU shards of c3 are launch-latency sized: 8 pairs at 8 GPUs).
+
+    ``gm`` / ``seg`` are the static input buffers (copy new features into them, e.g. with ``copy_(host, non_blocking=True)``);
+    ``outputs`` = ``(flow_fw, flow_bw, corr, fea_new)`` static output tensors.  Every kernel of the chain launches on the
+    stream it is handed and takes caller-owned workspaces, so the capture contains no allocation and no host sync.
+    """
+
+    def __init__(self, chain, gm, seg, pool=None):
+        self.chain, self.gm, self.seg = chain, gm, seg
+        dev = gm.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                        # warm-up off the capture: function attributes, prepared weights, caches
+                chain(gm, seg)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        try:
+            self.graph = torch.cuda.CUDAGraph(keep_graph=True)
+        except TypeError:
+            self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool):
+            self.outputs = chain(gm, seg)
+        self.kernel_nodes = _count_kernel_nodes(self.graph)
+        self.graph.replay()                           # instantiate now, not inside somebody's timed region
+        torch.cuda.synchronize(dev)
+
+    def pool(self):
+        return self.graph.pool()
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def __call__(self, gm, seg):
+        self.gm.copy_(gm, non_blocking=True)
+        self.seg.copy_(seg, non_blocking=True)
+        return self.replay()
+
+
+def _count_kernel_nodes(graph):
+    """Number of kernel nodes in a captured graph (None when the raw graph is not reachable)."""
+    try:
+        from cuda.bindings import runtime as rt
+        raw = graph.raw_cuda_graph()
+        err, _, n = rt.cudaGraphGetNodes(raw, 0)
+        if int(err) != 0:
+            return None
+        err, nodes, n = rt.cudaGraphGetNodes(raw, n)
+        cnt = 0
+        for nd in nodes[:n]:
+            err, ty = rt.cudaGraphNodeGetType(nd)
+            if int(err) == 0 and ty == rt.cudaGraphNodeType.cudaGraphNodeTypeKernel:
+                cnt += 1
+        return cnt
+    except Exception:
+        return None

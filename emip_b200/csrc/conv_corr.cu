@@ -101,7 +101,17 @@ extern "C" size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O) {
 
 extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
                                   void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream) {
+  return emip_conv_corr_fwd_ex(f0, f1, w_prep, bias, nullptr, nullptr, 0, EMIP_LAYOUT_CN, out, workspace, ws_bytes, B, C, H, W, O, stream);
+}
+
+// ep_scale != NULL: out = act(conv * ep_scale[o] + ep_shift[o]) -- the eval-mode BatchNorm2d + ReLU behind conv_corr[0]
+// (model.py:60-61) folded into the epilogue, with the convolution's bias inside ep_shift (bias is then ignored)
+extern "C" int emip_conv_corr_fwd_ex(const float* f0, const float* f1, const void* w_prep, const float* bias, const float* ep_scale,
+                                     const float* ep_shift, int relu, int layout, float* out, void* workspace, size_t ws_bytes,
+                                     int B, int C, int H, int W, int O, void* stream) {
   if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG((ep_scale == nullptr) == (ep_shift == nullptr), "conv_corr_fwd: ep_scale and ep_shift come together");
+  EMIP_CHECK_ARG(layout == EMIP_LAYOUT_NC || layout == EMIP_LAYOUT_CN, "conv_corr_fwd: layout must be 0 (token-major) or 1 (channel-major)");
   EMIP_CHECK_ARG(f0 && f1 && w_prep && out, "conv_corr_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0 && O > 0, "conv_corr_fwd: bad shape B=%d H=%d W=%d O=%d", B, H, W, O);
   if (!emip_conv_corr_supported(C, H, W)) {
@@ -121,8 +131,8 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
   ws.f1_chn = wsp + match_tc_split_bytes(B, N, C);
   ws.g = reinterpret_cast<__nv_bfloat16*>(wsp + match_tc_split_bytes(B, N, C) + pair_bwd_tc_chn_bytes(B, N));
   int rc;
-  if ((rc = match_tc_split(f0, nullptr, ws.f0_tok, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
-  if ((rc = pair_bwd_tc_split_chn(f1, nullptr, ws.f1_chn, B, N, EMIP_LAYOUT_CN, st))) return rc;
+  if ((rc = match_tc_split(f0, nullptr, ws.f0_tok, B, N, C, layout, 0, st))) return rc;
+  if ((rc = pair_bwd_tc_split_chn(f1, nullptr, ws.f1_chn, B, N, layout, st))) return rc;
 
   const int M1 = O * 9;
   const long long wld = weight_ld(N), cld = pair_bwd_tc_chn_ld(N);
@@ -162,9 +172,9 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
     if ((rc = gemm_tc_make_map(&mb, ws.f0_tok, 4, bdims, bstr, bbox))) return rc;
     GemmTcParams p = {};
     p.mode = 1; p.M = O; p.n_mtiles = (O + TM - 1) / TM; p.n_ntiles = (H + R - 1) / R; p.n_tile = R * W;
-    p.kchunks = 18;
+    p.kchunks = 18; p.cpt = 2; p.lo_off = 128;
     p.W = W; p.H = H; p.R = R;
-    p.bias = bias; p.out = out;
+    p.bias = ep_scale ? ep_shift : bias; p.ep_scale = ep_scale; p.ep_relu = relu; p.out = out;
     if ((rc = gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st))) return rc;
   }
   return EMIP_OK;

@@ -37,6 +37,7 @@ struct GemmNT {
   void* c_hi; void* c_lo; int ldc_split; int c_act;
   // tensor-core path only, K == 128: c = c_res + LayerNorm over the K outputs of a row (gamma, beta [K]; c_res rows ldc apart or NULL)
   const float* ln_gamma; const float* ln_beta; float ln_eps; const float* c_res;
+  const float* c_bias;                                                             // tensor-core path only: [K] added per output column
 };
 int gemm_nt(const GemmNT& a, cudaStream_t st);
 

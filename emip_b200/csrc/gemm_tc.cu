@@ -115,12 +115,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tma_load_3d(sa + 2 * A_BYTES, &map_b, full(stage), k0 * KCH, nt * p.n_tile, bs);
           tma_load_3d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.Kp + k0 * KCH, nt * p.n_tile, bs);
         } else {
-          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, b);
-          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, b);
-          // K chunk kc = tap (dy,dx) = kc / 2, channel half kc % 2 of the token-major [.., 256 = hi 128 | lo 128] f0
-          const int tap = kc >> 1, dy = tap / 3, dx = tap - dy * 3, c0 = (kc & 1) * KCH;
+          const int ab = p.a_shared ? 0 : b;                   // conv_corr: per-sample G; generic conv: one weight
+          tma_load_3d(sa, &map_a_hi, full(stage), kc * KCH, mt * TM, ab);
+          tma_load_3d(sa + A_BYTES, &map_a_lo, full(stage), kc * KCH, mt * TM, ab);
+          // K chunk kc = tap (dy,dx) = kc / cpt, channel chunk kc % cpt of the token-major [.., hi Cp | lo Cp] input
+          const int tap = kc / p.cpt, dy = tap / 3, dx = tap - dy * 3, c0 = (kc - tap * p.cpt) * KCH;
           tma_load_4d(sa + 2 * A_BYTES, &map_b, full(stage), c0, dx - 1, nt * p.R + dy - 1, b);
-          tma_load_4d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), 128 + c0, dx - 1, nt * p.R + dy - 1, b);
+          tma_load_4d(sa + 2 * A_BYTES + p.b_bytes, &map_b, full(stage), p.lo_off + c0, dx - 1, nt * p.R + dy - 1, b);
         }
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -332,6 +333,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const float* rb0 = p.res ? p.res + (size_t)b * p.res_stride_b + n0 + c0 : nullptr;
         if (p.epi_stage && n == 32 && (p.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yb) & 15) == 0 &&
             (!rb0 || ((p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(rb0) & 15) == 0))) {       // warp-uniform
+          if (p.bias_n != nullptr) {                         // per-column bias (nn.Linear on token rows), warp-uniform branch
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias_n + n0 + c0 + i));
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __float_as_uint(__uint_as_float(r[i]) + rb);
           __syncwarp();
@@ -351,6 +356,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           __syncwarp();
         } else if (row < p.M && n > 0) {
+          if (p.bias_n != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < n) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias_n + n0 + c0 + i));
+          }
           if (n == 32 && ((reinterpret_cast<uintptr_t>(o + c0) & 15) == 0) && (!rs || (reinterpret_cast<uintptr_t>(rs + c0) & 15) == 0)) {
             float4* d = reinterpret_cast<float4*>(o + c0);
 #pragma unroll
@@ -374,7 +384,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int npix = p.H * p.W;
       const int px0 = nt * p.R * p.W;
       const int nvalid = min(p.n_tile, npix - px0);          // the last tile may hang over the bottom edge
+      // per-output-channel affine + ReLU: bias alone, or a folded eval-mode BatchNorm (scale, shift) of the layer behind
       const float bias = (row < p.M && p.bias != nullptr) ? __ldg(p.bias + row) : 0.f;
+      const float esc = (row < p.M && p.ep_scale != nullptr) ? __ldg(p.ep_scale + row) : 1.f;
+      const float efl = p.ep_relu ? 0.f : -INFINITY;
       float* o = p.out + ((size_t)b * p.M + row) * npix + px0;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t r[32];
@@ -397,12 +410,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float4* d = reinterpret_cast<float4*>(o + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              d[i] = make_float4(__uint_as_float(r[4 * i]) + bias, __uint_as_float(r[4 * i + 1]) + bias,
-                                 __uint_as_float(r[4 * i + 2]) + bias, __uint_as_float(r[4 * i + 3]) + bias);
+              d[i] = make_float4(fmaxf(fmaf(__uint_as_float(r[4 * i]), esc, bias), efl), fmaxf(fmaf(__uint_as_float(r[4 * i + 1]), esc, bias), efl),
+                                 fmaxf(fmaf(__uint_as_float(r[4 * i + 2]), esc, bias), efl), fmaxf(fmaf(__uint_as_float(r[4 * i + 3]), esc, bias), efl));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i < n) o[c0 + i] = __uint_as_float(r[i]) + bias;
+              if (i < n) o[c0 + i] = fmaxf(fmaf(__uint_as_float(r[i]), esc, bias), efl);
           }
         }
       }
@@ -699,6 +712,10 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
     }
     p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
     p.res = a.c_res; p.res_stride_b = 0; p.ldr = a.ldc;
+  }
+  if (a.c_bias != nullptr) {
+    if (a.ln_gamma != nullptr || a.c_hi != nullptr || ns != 1) { emip_set_error("gemm_nt_tc: c_bias needs the plain fp32 epilogue"); return EMIP_ENOSYS; }
+    p.bias_n = a.c_bias;
   }
   if (a.c_hi != nullptr) {
     p.g_hi = static_cast<__nv_bfloat16*>(a.c_hi); p.g_lo = static_cast<__nv_bfloat16*>(a.c_lo);

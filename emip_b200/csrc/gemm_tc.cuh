@@ -19,8 +19,12 @@ struct GemmTcParams {
   int kchunks;              // K / 64 (rounded up; the TMA unit zero-fills the tail)
   int stages, stage_bytes, b_bytes;
   int W, H, R;              // mode 1: image geometry, image rows per pixel tile
+  int cpt, lo_off;          // mode 1: K chunks per tap (input channels / 64, rounded up) and offset of the lo half in a token row
+  int a_shared;             // mode 1: A is one weight matrix for every batch entry (0: one per sample, conv_corr's G[b])
   float scale;              // mode 0
-  const float* bias;        // mode 1
+  const float* bias;        // mode 1 (and per-row bias of mode 2)
+  const float* ep_scale;    // mode 1: out = act(acc * ep_scale[row] + bias[row]) (NULL: scale 1)
+  int ep_relu;              // mode 1: act = ReLU
   __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, lo
   __nv_bfloat16* g_lo;
   float* out;               // mode 1 output: [B][M][H*W]
@@ -36,6 +40,7 @@ struct GemmTcParams {
   int out_split, ldg;
   // mode 2, ln_gamma != NULL (N == n_tile == 128, one output row per thread): y = res + LayerNorm_N(tile) * gamma + beta
   const float* ln_gamma; const float* ln_beta; float ln_eps;
+  const float* bias_n;      // mode 2, plain fp32 epilogue: per-column bias [N] (NULL: none)
   int epi_stage;            // mode 2: per-warp shared-memory staging of the epilogue (set by gemm_tc_launch): coalesced row stores
 };
 

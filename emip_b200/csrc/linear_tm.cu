@@ -141,6 +141,25 @@ extern "C" int emip_linear_tm_fwd_ex(const float* x, const float* aux, const flo
   return gemm_nt_tc(t, workspace, scratch_bytes, st, 1);
 }
 
+// y [L][M] = x [L][K] w^T + bias [M]: nn.Linear with bias on token rows (FeatureFlowAttention.q_proj / k_proj on the
+// transformer's token-major output, transformer.py:523-524); forward only
+extern "C" int emip_linear_tm_bias_fwd(const float* x, const float* w, const float* bias, float* y, void* workspace, size_t ws_bytes,
+                                       int L, int M, int K, void* stream) {
+  if (L == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x && w && y && workspace, "linear_tm_bias_fwd: null pointer");
+  if (!shape_ok(L, M, K)) { emip_set_error("linear_tm_bias_fwd: unsupported shape L=%d M=%d K=%d", L, M, K); return EMIP_ENOSYS; }
+  if (ws_bytes < emip_linear_tm_workspace(L, M, K)) { emip_set_error("linear_tm_bias_fwd: workspace too small"); return EMIP_ENOMEM; }
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "linear_tm_bias_fwd: workspace must be 1024-byte aligned");
+  GemmNT t = {};
+  t.B = 1; t.M = L; t.K = M; t.N = K;
+  t.a = x; t.lda = K;
+  t.bm = w; t.ldb = K;
+  t.c = y; t.ldc = M;
+  t.c_bias = bias;
+  if (!gemm_nt_tc_supported(t)) { emip_set_error("linear_tm_bias_fwd: output must be 16-byte aligned"); return EMIP_EINVAL; }
+  return gemm_nt_tc(t, workspace, ws_bytes - wt_bytes(M, K), (cudaStream_t)stream, 1);
+}
+
 // y_i [L][M] = x [L][K] w_i^T for n weights of one shape: the rows are split once (q / k / v of a self-attention layer read the
 // same tokens, k / v of a cross-attention layer too)
 extern "C" size_t emip_linear_tm_multi_workspace(int L, int M, int K) {

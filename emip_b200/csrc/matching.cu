@@ -76,7 +76,8 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
 
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
     // tensor-core path: one operand-split launch + one fused launch covering both directions
-    if (!reuse && (rc = match_tc_split(f0, f1, ws.split, B, N, C, EMIP_LAYOUT_CN, 0, st))) return rc;
+    const int layout = (flags & EMIP_FLAG_TOKEN_MAJOR) ? EMIP_LAYOUT_NC : EMIP_LAYOUT_CN;
+    if (!reuse && (rc = match_tc_split(f0, f1, ws.split, B, N, C, layout, 0, st))) return rc;
     MatchTcArgs a = {};
     a.x_split = ws.split; a.y_split = ws.split; a.nbx = 2 * B; a.nby = 2 * B;
     a.v = nullptr; a.v_stride_b = 0; a.grid_w = W; a.sub_grid = 1;   // analytic pixel grid (geometry.py:5-21)
@@ -87,6 +88,10 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
     a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
     a.sk_ws = ws.sk; a.sk_bytes = ws.sk_bytes;
     return match_tc_fwd(a, st);
+  }
+  if (flags & EMIP_FLAG_TOKEN_MAJOR) {
+    emip_set_error("global_matching_fwd: EMIP_FLAG_TOKEN_MAJOR needs the tensor-core path (C=128, 16 <= H*W <= 2048)");
+    return EMIP_ENOSYS;
   }
   if ((rc = launch_coords_grid(ws.grid, H, W, st))) return rc;
 

@@ -80,6 +80,7 @@ struct SplitParams {
   const float* src[4];       // q, k, v (, dout): [B][h*w][128]
   __nv_bfloat16* dst[4];     // [nprob][n][256] token-major hi|lo
   int B, h, w, n;
+  int kv_shift;              // k, v (tensors 1, 2) of image i are read from image (i + kv_shift) % B
   int r0[MAXBLK], c0[MAXBLK], bw[MAXBLK];
 };
 
@@ -89,7 +90,8 @@ __global__ void __launch_bounds__(256)
 win_split_kernel(const __grid_constant__ SplitParams sp) {
   const int z = blockIdx.z, prob = blockIdx.y, t0 = blockIdx.x * TOK;
   const int blk = prob / sp.B, img = prob - blk * sp.B;
-  const float* src = sp.src[z] + (size_t)img * sp.h * sp.w * KC;
+  const int simg = (z == 1 || z == 2) ? (img + sp.kv_shift) % sp.B : img;
+  const float* src = sp.src[z] + (size_t)simg * sp.h * sp.w * KC;
   __nv_bfloat16* dst = sp.dst[z] + (size_t)prob * sp.n * 256;
   const int r0 = sp.r0[blk], c0 = sp.c0[blk], bw = sp.bw[blk];
   const int c4 = threadIdx.x & 31, tw = threadIdx.x >> 5;           // 8 warps x 8 tokens each
@@ -152,7 +154,18 @@ extern "C" size_t emip_window_attention_tc_workspace(int B, int h, int w, int C,
 extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, const float* v, float* out, float* lse,
                                             void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
                                             int with_shift, void* stream) {
+  return emip_window_attention_fwd_tc_ex(q, k, v, out, lse, workspace, ws_bytes, B, h, w, C, num_splits, with_shift, 0, stream);
+}
+
+// EMIP_WINATTN_KV_SWAP_HALVES: image i attends to the keys / values of image (i + B/2) % B -- the cross-attention layers of
+// the FeatureTransformer, whose target is the source with the two batch halves swapped (transformer.py:462, :473): the
+// swapped copy `concat1` is never made
+extern "C" int emip_window_attention_fwd_tc_ex(const float* q, const float* k, const float* v, float* out, float* lse,
+                                               void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
+                                               int with_shift, int flags, void* stream) {
   if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG((flags & ~EMIP_WINATTN_KV_SWAP_HALVES) == 0, "window_attention_fwd_tc: unknown flag");
+  EMIP_CHECK_ARG(!(flags & EMIP_WINATTN_KV_SWAP_HALVES) || B % 2 == 0, "window_attention_fwd_tc: KV_SWAP_HALVES needs an even batch");
   EMIP_CHECK_ARG(q && k && v && out && workspace, "window_attention_fwd_tc: null pointer");
   EMIP_CHECK_ARG(B > 0 && h > 0 && w > 0, "window_attention_fwd_tc: bad shape B=%d h=%d w=%d", B, h, w);
   if (C != KC) {
@@ -181,6 +194,7 @@ extern "C" int emip_window_attention_fwd_tc(const float* q, const float* k, cons
     sp.dst[1] = reinterpret_cast<__nv_bfloat16*>(base + tok_bytes);
     sp.dst[2] = reinterpret_cast<__nv_bfloat16*>(base + 2 * tok_bytes);
     sp.B = B; sp.h = h; sp.w = w; sp.n = n;
+    sp.kv_shift = (flags & EMIP_WINATTN_KV_SWAP_HALVES) ? B / 2 : 0;
     AttnTcArgs a = {};
     a.win.enabled = 1; a.win.B = B; a.win.h = h; a.win.w = w;
     for (int j = 0; j < MAXBLK; ++j) {
@@ -246,7 +260,7 @@ extern "C" int emip_window_attention_bwd_tc(const float* q, const float* k, cons
     SplitParams sp;
     sp.src[0] = q; sp.src[1] = k; sp.src[2] = v; sp.src[3] = dout;
     for (int j = 0; j < 4; ++j) sp.dst[j] = reinterpret_cast<__nv_bfloat16*>(base + j * tok_bytes);
-    sp.B = B; sp.h = h; sp.w = w; sp.n = n;
+    sp.B = B; sp.h = h; sp.w = w; sp.n = n; sp.kv_shift = 0;
     AttnWinMap wm = {};
     wm.enabled = 1; wm.B = B; wm.h = h; wm.w = w;
     for (int j = 0; j < MAXBLK; ++j) {

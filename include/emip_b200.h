@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EMIP_ABI_VERSION 3
+#define EMIP_ABI_VERSION 4
 
 #define EMIP_PAD_BORDER 0
 #define EMIP_PAD_ZEROS 1
@@ -45,6 +45,10 @@ extern "C" {
 #define EMIP_FLAG_BF16 4            /* bf16 inference mode: single-pass bf16 operands (no hi/lo split), fp32 accumulate and
                                        fp32 softmax; results within the 2e-2 tolerance instead of 1e-3 */
 #define EMIP_FLAG_CHANNEL_MAJOR 8  /* flow_attn_fwd / _bwd: q, k (and dq, dk) are channel-major [B,C,N] instead of [B,N,C] */
+#define EMIP_FLAG_TOKEN_MAJOR 16   /* global_matching_fwd: f0, f1 are token-major [B,H*W,C] -- the FeatureTransformer's own
+                                       output layout (transformer.py:476, before the permute of :479-480) */
+#define EMIP_LAYOUT_TOKEN_MAJOR 0  /* [B][H*W][C] */
+#define EMIP_LAYOUT_CHANNEL_MAJOR 1 /* [B][C][H*W]  (NCHW feature maps) */
 
 /* ---- plumbing ------------------------------------------------------------ */
 const char* emip_last_error(void);
@@ -263,6 +267,14 @@ size_t emip_conv_corr_workspace(int B, int C, int H, int W, int O);
 int emip_conv_corr_fwd(const float* f0, const float* f1, const void* w_prep, const float* bias, float* out,
                        void* workspace, size_t ws_bytes, int B, int C, int H, int W, int O, void* stream);
 
+/* As emip_conv_corr_fwd with (i) `layout` of f0 / f1 (EMIP_LAYOUT_*) and (ii) the eval-mode BatchNorm2d + ReLU that follow
+ * conv_corr[0] (model.py:60-61) folded into the epilogue: ep_scale != NULL => out = act(conv * ep_scale[o] + ep_shift[o])
+ * with ep_scale = gamma / sqrt(running_var + eps), ep_shift = (bias - running_mean) * ep_scale + beta (bias is then
+ * ignored); relu != 0 => act = ReLU. */
+int emip_conv_corr_fwd_ex(const float* f0, const float* f1, const void* w_prep, const float* bias, const float* ep_scale,
+                          const float* ep_shift, int relu, int layout, float* out, void* workspace, size_t ws_bytes, int B, int C,
+                          int H, int W, int O, void* stream);
+
 /* Backward of emip_conv_corr_fwd on the tensor cores: df0, df1 [B,C,H,W], dweight [O,H*W,3,3], dbias [O] (NULL = not
  * wanted) from dout [B,O,H,W]; weight = the fp32 parameter, w_prep = its prepared copy.  Five split-bf16 GEMMs
  * (csrc/gemm_tc.cu); workspace of emip_conv_corr_bwd_workspace() bytes, 1024-byte aligned. */
@@ -315,6 +327,40 @@ size_t emip_window_attention_bwd_tc_workspace(int B, int h, int w, int C, int nu
 int emip_window_attention_bwd_tc(const float* q, const float* k, const float* v, const float* out, const float* lse,
                                  const float* dout, float* dq, float* dk, float* dv, void* workspace, size_t ws_bytes, int B,
                                  int h, int w, int C, int num_splits, int with_shift, void* stream);
+
+/* EMIP_WINATTN_KV_SWAP_HALVES: image i attends to the keys / values of image (i + B/2) % B: the cross-attention layers of
+ * the FeatureTransformer, whose `target` is `source` with the two batch halves swapped (transformer.py:462, :473) -- the
+ * swapped copy is never made.  Forward only. */
+#define EMIP_WINATTN_KV_SWAP_HALVES 1
+int emip_window_attention_fwd_tc_ex(const float* q, const float* k, const float* v, float* out, float* lse, void* workspace,
+                                    size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift, int flags,
+                                    void* stream);
+
+/* ---- the chained path between the backbones and the decoder (CoUpdater.forward, model.py:92-97) -------------------- */
+/* 3x3 convolution, stride 1, zero padding 1, on the tensor cores (csrc/conv_tm.cu): replaces GMFlow.upsampler[0] + ReLU
+ * (gmflow.py:43-44 on cat(flow, feature), :62-64) and conv_corr[3] (model.py:62).
+ *   input  = channel concatenation of x0 (C0 channels) and, optionally, x1 (C1 channels); each source is channel-major
+ *            [B,C,H,W] or token-major [B,H*W,C] (layout0 / layout1 = EMIP_LAYOUT_*)
+ *   w_prep = emip_conv3x3_prepare_weight(w [O, C0+C1, 3, 3]) in a caller-owned buffer of emip_conv3x3_weight_bytes() bytes
+ *   out [B,O,H,W] = act(scale[o] * conv + shift[o]); scale NULL = 1, shift NULL = 0 (shift = the bias), relu != 0 = ReLU
+ *   workspace >= emip_conv3x3_workspace(B, C0+C1, H, W) bytes, 1024-byte aligned (the bf16 hi | lo token rows). */
+int emip_conv3x3_supported(int Cin, int H, int W);
+size_t emip_conv3x3_weight_bytes(int O, int Cin);
+int emip_conv3x3_prepare_weight(const float* w, void* w_prep, int O, int Cin, void* stream);
+size_t emip_conv3x3_workspace(int B, int Cin, int H, int W);
+int emip_conv3x3_fwd(const float* x0, int C0, int layout0, const float* x1, int C1, int layout1, const void* w_prep,
+                     const float* scale, const float* shift, int relu, float* out, void* workspace, size_t ws_bytes, int B,
+                     int H, int W, int O, void* stream);
+
+/* out[b][n][c] = x[b][c][n] + pos[c][n] (pos NULL: plain transpose): gmflow.py:114 feature_add_position (utils.py:66-86; pos
+ * = the window-tiled sine embedding) + transformer.py:439-440 (flatten / permute to token rows) in one pass. */
+int emip_tokens_from_cn(const float* x, const float* pos, float* out, int B, int C, int N, void* stream);
+
+/* y [L][M] = x [L][K] w^T + bias [M]: nn.Linear with bias on token rows -- FeatureFlowAttention.q_proj / k_proj
+ * (transformer.py:523-524) applied to the FeatureTransformer's token-major output.  Forward only; workspace as
+ * emip_linear_tm_workspace(L, M, K). */
+int emip_linear_tm_bias_fwd(const float* x, const float* w, const float* bias, float* y, void* workspace, size_t ws_bytes, int L,
+                            int M, int K, void* stream);
 
 /* Diagnostics: device buffer of (CTAs x 16) cycle counters filled by the next fused-attention launches (NULL = off). */
 void emip_attn_tc_set_profile_buffer(unsigned long long* dev_buf);

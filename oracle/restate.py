@@ -370,3 +370,107 @@ def transformer_layer(source, target, p, no_ffn, num_splits, with_shift, h, w, e
         hid = torch.cat([source, msg], -1) @ p["mlp.0.weight"].T
         msg = ln(_gelu_erf(hid) @ p["mlp.2.weight"].T, p["norm2.weight"], p["norm2.bias"])
     return source + msg
+
+
+# --------------------------------------------------------------------------- the chained path (VERDICT r1 row g)
+def position_embedding_sine(h, w, num_pos_feats=64, temperature=10000.0, dtype=torch.float32):
+    """DETR sine position embedding of one h x w window, normalised, scale 2 pi: [2*num_pos_feats, h, w] with the y half
+    first.  Reference: model/EMIP_short/motion/gmflow/position.py:24-46 (mask of ones => embed = 1..h / 1..w)."""
+    eps, scale = 1e-6, 2 * math.pi
+    y = torch.arange(1, h + 1, dtype=torch.float32)
+    x = torch.arange(1, w + 1, dtype=torch.float32)
+    y = y / (y[-1] + eps) * scale                                     # position.py:32-35
+    x = x / (x[-1] + eps) * scale
+    i = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)   # position.py:37-38
+    px = x[:, None] / dim_t                                            # [w, F]
+    py = y[:, None] / dim_t                                            # [h, F]
+    px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)   # position.py:42
+    py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)   # position.py:43
+    pos = torch.cat((py[:, None, :].expand(h, w, num_pos_feats), px[None, :, :].expand(h, w, num_pos_feats)), dim=2)
+    return pos.permute(2, 0, 1).to(dtype)                             # position.py:44-45
+
+
+def feature_add_position(feature0, feature1, attn_splits, feature_channels):
+    """Adds the window-local sine embedding to both feature maps: with attn_splits = K the map is cut into K x K windows
+    and every window gets the same [C, H/K, W/K] embedding.  Reference: .../gmflow/utils.py:66-86 (+ :5-58)."""
+    b, c, h, w = feature0.shape
+    K = attn_splits if attn_splits > 1 else 1
+    pos = position_embedding_sine(h // K, w // K, feature_channels // 2, dtype=feature0.dtype).repeat(1, K, K)
+    return feature0 + pos[None], feature1 + pos[None]
+
+
+def feature_transformer(feature0, feature1, layers, num_splits):
+    """GMFlow FeatureTransformer: 6 blocks of (self-attention layer, cross-attention + FFN layer) on the two maps stacked on the
+    batch axis; odd blocks use shifted windows.  ``layers[i]`` = {"self_attn": {...}, "cross_attn_ffn": {...}} (state_dict
+    keys of one TransformerLayer each).  Reference: .../gmflow/transformer.py:433-482 and :349-401 (TransformerBlock)."""
+    b, c, h, w = feature0.shape
+    f0 = feature0.flatten(-2).permute(0, 2, 1)                         # :439-440
+    f1 = feature1.flatten(-2).permute(0, 2, 1)
+    concat0 = torch.cat((f0, f1), dim=0)                               # :461-462
+    concat1 = torch.cat((f1, f0), dim=0)
+    for i, blk in enumerate(layers):
+        shift = (i % 2 == 1)                                           # :425
+        concat0 = transformer_layer(concat0, concat0, blk["self_attn"], True, num_splits, shift, h, w)        # :388-393
+        concat0 = transformer_layer(concat0, concat1, blk["cross_attn_ffn"], False, num_splits, shift, h, w)  # :396-401
+        concat1 = torch.cat(concat0.chunk(2, dim=0)[::-1], dim=0)      # :473
+    f0, f1 = concat0.chunk(2, dim=0)
+    back = lambda t: t.reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()   # :478-480
+    return back(f0), back(f1)
+
+
+def upsampler_mask(flow, feature, p):
+    """GMFlow.upsampler on cat(flow, feature): Conv2d(130, 256, 3, 1, 1) - ReLU - Conv2d(256, 576, 1).
+    Reference: .../gmflow/gmflow.py:43-46, :62-64."""
+    F = torch.nn.functional
+    x = torch.cat((flow, feature), dim=1)
+    x = F.relu(F.conv2d(x, p["0.weight"], p["0.bias"], padding=1))
+    return F.conv2d(x, p["2.weight"], p["2.bias"])
+
+
+def conv_corr_tail(y, p, eps=1e-5):
+    """conv_corr[1:] in eval mode: BatchNorm2d(968) with running statistics - ReLU - Conv2d(968, 128, 3, 1, 1).
+    Reference: model/EMIP_short/model.py:59-62."""
+    F = torch.nn.functional
+    v = lambda t: t.view(1, -1, 1, 1)
+    y = (y - v(p["1.running_mean"])) / torch.sqrt(v(p["1.running_var"]) + eps) * v(p["1.weight"]) + v(p["1.bias"])
+    return F.conv2d(F.relu(y), p["3.weight"], p["3.bias"], padding=1)
+
+
+def sub_params(P, prefix):
+    """{key without prefix: tensor} for the keys of P that start with prefix."""
+    return {k[len(prefix):]: v for k, v in P.items() if k.startswith(prefix)}
+
+
+def motion_chain(gm, seg, P, attn_splits=2, want=()):
+    """The chained hot path of ``CoUpdater.forward`` between the backbones and the decoder, eval mode.
+
+    gm, seg [2B, 128, H, W]: GMFlow-encoder and segmentation-backbone features of (frame 1 | frame 2) stacked on the batch
+    axis; P maps ``CoUpdater.state_dict()`` keys to tensors.  Returns a dict with flow_fw / flow_bw [B,2,8H,8W], corr
+    (= conv_corr output [B,128,H,W]) and fea_new (= injector1 output), plus the intermediates named in ``want``.
+
+    Reference: model/EMIP_short/model.py:92-97 and .../gmflow/gmflow.py:81-162 (num_scales 1, pred_bidir_flow, eval).
+    """
+    B = gm.shape[0] // 2
+    C = gm.shape[1]
+    ab = injector(gm, seg, sub_params(P, "injector.transformer."))                        # model.py:92-93 (same weights)
+    f0, f1 = feature_add_position(ab[:B], ab[B:], attn_splits, C)                          # gmflow.py:114
+    layers = [{"self_attn": sub_params(P, f"GMFlow.transformer.layers.{i}.self_attn."),
+               "cross_attn_ffn": sub_params(P, f"GMFlow.transformer.layers.{i}.cross_attn_ffn.")} for i in range(6)]
+    f0, f1 = feature_transformer(f0, f1, layers, attn_splits)                              # gmflow.py:117
+    flow_pred, _, corr = global_correlation_softmax(f0, f1, True)                          # gmflow.py:121
+    feat = torch.cat((f0, f1), dim=0)                                                      # gmflow.py:136
+    ffa = sub_params(P, "GMFlow.feature_flow_attn.")
+    flow = feature_flow_attention(feat, flow_pred, ffa["q_proj.weight"], ffa["q_proj.bias"], ffa["k_proj.weight"],
+                                  ffa["k_proj.bias"])                                      # gmflow.py:137
+    mask = upsampler_mask(flow, feat, sub_params(P, "GMFlow.upsampler."))                  # gmflow.py:64
+    flow_up = upsample_flow_convex(flow, mask)                                             # gmflow.py:148
+    cc = sub_params(P, "conv_corr.")
+    corr1 = torch.nn.functional.conv2d(corr, cc["0.weight"], cc["0.bias"], padding=1)      # model.py:59, :96
+    corr_out = conv_corr_tail(corr1, cc)
+    fea_new = injector(seg[:B], corr_out, sub_params(P, "injector1.transformer."))         # model.py:97
+    out = dict(flow_fw=flow_up[:B], flow_bw=flow_up[B:], corr=corr_out, fea_new=fea_new)   # gmflow.py:152-155
+    loc = dict(ab=ab, feat=feat, flow_pred=flow_pred, flow_prop=flow, mask=mask, corr1=corr1)
+    for k in want:
+        out[k] = loc[k]
+    return out

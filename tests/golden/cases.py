@@ -235,3 +235,66 @@ def check_packed(t, packed, rtol, what=""):
     l2 = t.reshape(-1).double().norm().item()
     assert abs(l2 - packed["l2"]) <= 10 * rtol * max(packed["l2"], 1e-30), f"{what}: L2 norm {l2} vs {packed['l2']}"
     return err
+
+
+# chain: the chained hot path of CoUpdater.forward (model.py:92-97 + gmflow.py:81-162) on post-backbone features.
+# Every weight of the path is regenerated from seeds (distributions follow the reference's initialisers: xavier-uniform
+# for the transformer / flow-attention Linear weights, kaiming-uniform(a = sqrt 5) bounds for the convolutions) and loaded
+# into the reference CoUpdater by make_golden.py, so no weight tensor is stored.
+def uniform(seed, shape, bound):
+    return (2.0 * rand(seed, shape) - 1.0) * bound
+
+
+def chain_params(seed=7, hw=44 * 44, corr_mid=968):
+    P = {}
+    s = [seed * 1000]
+
+    def nxt():
+        s[0] += 1
+        return s[0]
+
+    for pre in ("injector.transformer.", "injector1.transformer."):
+        for k, v in injector_params(nxt()).items():
+            P[pre + k] = v
+    xav = lambda o, i: uniform(nxt(), (o, i), (6.0 / (o + i)) ** 0.5)
+    for i in range(6):
+        for lay in ("self_attn", "cross_attn_ffn"):
+            pre = f"GMFlow.transformer.layers.{i}.{lay}."
+            for n in ("q_proj", "k_proj", "v_proj", "merge"):
+                P[pre + n + ".weight"] = xav(128, 128)
+            P[pre + "norm1.weight"] = 1 + 0.05 * randn(nxt(), (128,))
+            P[pre + "norm1.bias"] = 0.05 * randn(nxt(), (128,))
+            if lay == "cross_attn_ffn":
+                P[pre + "mlp.0.weight"] = xav(1024, 256)
+                P[pre + "mlp.2.weight"] = xav(128, 1024)
+                P[pre + "norm2.weight"] = 1 + 0.05 * randn(nxt(), (128,))
+                P[pre + "norm2.bias"] = 0.05 * randn(nxt(), (128,))
+    for n in ("q_proj", "k_proj"):
+        P[f"GMFlow.feature_flow_attn.{n}.weight"] = xav(128, 128)
+        P[f"GMFlow.feature_flow_attn.{n}.bias"] = uniform(nxt(), (128,), 128 ** -0.5)
+
+    def conv(pre, o, i, k):
+        b = (i * k * k) ** -0.5
+        P[pre + ".weight"] = uniform(nxt(), (o, i, k, k), b)
+        P[pre + ".bias"] = uniform(nxt(), (o,), b)
+    conv("GMFlow.upsampler.0", 256, 130, 3)
+    conv("GMFlow.upsampler.2", 576, 256, 1)
+    conv("conv_corr.0", corr_mid, hw, 3)
+    P["conv_corr.1.weight"] = 1 + 0.1 * randn(nxt(), (corr_mid,))
+    P["conv_corr.1.bias"] = 0.1 * randn(nxt(), (corr_mid,))
+    P["conv_corr.1.running_mean"] = 5.0 * randn(nxt(), (corr_mid,))
+    P["conv_corr.1.running_var"] = 50.0 * (0.5 + rand(nxt(), (corr_mid,)))
+    conv("conv_corr.3", 128, corr_mid, 3)
+    return P
+
+
+CHAIN_CASES = {
+    # seeded features at the scales measured inside the model (GMFlow-encoder features std 2.2, PVT features std 1.0)
+    "chain_randn": dict(b=2, h=44, w=44, gm_scale=2.2, seg_scale=1.0, seed=151, pseed=7),
+}
+CHAIN_KEYS = ("ab", "feat", "flow_pred", "flow_prop", "mask", "corr1", "corr", "fea_new", "flow_fw", "flow_bw")
+
+
+def chain_inputs(s):
+    shp = (2 * s["b"], 128, s["h"], s["w"])
+    return dict(gm=randn(s["seed"], shp, s["gm_scale"]), seg=randn(s["seed"] + 1, shp, s["seg_scale"]))

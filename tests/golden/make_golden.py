@@ -248,7 +248,84 @@ def gen_c1():
     print("c1 stats", s_max, cap["flow"].abs().mean().item())
 
 
+def _chain_model():
+    from model.EMIP_short.model import CoUpdater
+    torch.manual_seed(123)  # configs/configs.yaml:69
+    net = CoUpdater(ref_shim.model_args()).eval()
+    P = cases.chain_params()
+    missing, unexpected = net.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    return net, P
+
+
+def _chain_capture(net, run):
+    """Runs ``run()`` with hooks that record the intermediates of the chained path inside the unmodified reference."""
+    import model.EMIP_short.motion.gmflow.gmflow as gm
+    cap = {"ab": []}
+    orig = gm.global_correlation_softmax
+
+    def spy(f0, f1, bidir):
+        out = orig(f0, f1, bidir)
+        cap["feat"] = torch.cat((f0, f1), 0).detach().clone()
+        cap["flow_pred"] = out[0].detach().clone()
+        return out
+
+    hooks = [
+        net.injector.register_forward_hook(lambda m, a, o: cap["ab"].append(o.detach().clone())),
+        net.GMFlow.feature_flow_attn.register_forward_hook(lambda m, a, o: cap.__setitem__("flow_prop", o.detach().clone())),
+        net.GMFlow.upsampler.register_forward_hook(lambda m, a, o: cap.__setitem__("mask", o.detach().clone())),
+        net.conv_corr[0].register_forward_hook(lambda m, a, o: cap.__setitem__("corr1", o.detach().clone())),
+        net.conv_corr.register_forward_hook(lambda m, a, o: cap.__setitem__("corr", o.detach().clone())),
+        net.injector1.register_forward_hook(lambda m, a, o: cap.__setitem__("fea_new", o.detach().clone())),
+    ]
+    gm.global_correlation_softmax = spy
+    try:
+        with torch.no_grad():
+            res = run()
+    finally:
+        gm.global_correlation_softmax = orig
+        for h in hooks:
+            h.remove()
+    cap["ab"] = torch.cat(cap["ab"], 0)
+    return cap, res
+
+
+def gen_chain():
+    """The chained hot path (model.py:92-97 + gmflow.py:81-162, eval) inside the unmodified reference CoUpdater whose
+    path weights were overwritten with cases.chain_params(): (i) seeded post-backbone features, (ii) config c1 in situ --
+    backbone features recorded by hooks from a full ``CoUpdater.forward`` on one seeded 352x352 pair."""
+    net, P = _chain_model()
+    for name, s in cases.CHAIN_CASES.items():
+        d = cases.chain_inputs(s)
+        B = s["b"]
+
+        def run(d=d, B=B):
+            a = net.injector(d["gm"][:B], d["seg"][:B])                    # model.py:92
+            b = net.injector(d["gm"][B:], d["seg"][B:])                    # model.py:93
+            flow_fw, flow_bw, corr = net.GMFlow([a], [b])                  # model.py:94
+            corr = net.conv_corr(corr)                                     # model.py:96
+            net.injector1(d["seg"][:B], corr)                              # model.py:97
+            return flow_fw, flow_bw
+        cap, (ffw, fbw) = _chain_capture(net, run)
+        cap["flow_fw"], cap["flow_bw"] = ffw[-1], fbw[-1]
+        save(name, dict(spec=s, **{k: cases.pack(cap[k], True) for k in cases.CHAIN_KEYS}))
+    # in situ (config c1): the features the real backbones produce
+    im1 = cases.randn(0, (1, 3, 352, 352))
+    im2 = cases.randn(1, (1, 3, 352, 352))
+    feats = {"gm": [], "seg": []}
+    hb = [net.GMFlow.backbone.register_forward_hook(lambda m, a, o: feats["gm"].append(o[0].detach().clone())),
+          net.backbone.feat_net.register_forward_hook(lambda m, a, o: feats["seg"].append(o[0].detach().clone()))]
+    cap, (mask, ffw, fbw) = _chain_capture(net, lambda: net(im1, im2))
+    for h in hb:
+        h.remove()
+    cap["flow_fw"], cap["flow_bw"] = ffw[-1], fbw[-1]
+    save("chain_insitu", dict(gm=torch.cat(feats["gm"], 0), seg=torch.cat(feats["seg"], 0), seg_mask=cases.pack(mask, True),
+                              **{k: cases.pack(cap[k], True) for k in cases.CHAIN_KEYS}))
+    print("chain_insitu stats: feat std", cap["feat"].std().item(), "flow_pred |mean|", cap["flow_pred"].abs().mean().item(),
+          "corr std", cap["corr"].std().item(), "fea_new std", cap["fea_new"].std().item(), "mask std", mask.std().item())
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f2b", "f3", "f3b", "f4", "c1"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f2b", "f3", "f3b", "f4", "c1", "chain"]
     for w in which:
         globals()["gen_" + w]()

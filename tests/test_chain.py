@@ -1,0 +1,159 @@
+"""The chained hot path (emip_b200.chain.MotionChain = model.py:92-97 + gmflow.py:81-162 on our kernels) against hook
+captures from the unmodified reference CoUpdater (tests/golden/chain_*.pt) and against the CPU oracle."""
+import pytest
+import torch
+
+import cases
+from oracle import restate as O
+
+FLOW_TOL = 1e-3        # north_star: flow within 1e-3 relative in fp32 (model features: measured 1.4e-4 ... 2.1e-4)
+FEAT_TOL = 1e-3
+# Unstructured (iid gaussian) features make the matching ill-conditioned: every FeatureTransformer block amplifies a
+# perturbation of its input ~1.7x (attention logits up to +-93) and the two near-one-hot softmaxes of a1 / a2 another ~6x.
+# The reference's own fp32 arithmetic is 8e-5 ... 9e-5 away from fp64 on these flows (tools/chain_err.py; test_oracle_golden);
+# the split-bf16 GEMMs (2^-17 operands instead of 2^-24) land at 7e-4 ... 1.2e-3.  The bound for this synthetic-feature
+# case is therefore 2e-3; the model-feature case (config c1 in situ) keeps the 1e-3 of north_star.
+FLOW_TOL_RANDN = 2e-3
+
+
+def _chain(P, **kw):
+    from emip_b200.chain import MotionChain
+    m = MotionChain(**kw)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    return m
+
+
+def test_chain_state_dict_keys_are_the_references():
+    """CPU: the chain owns exactly the path's parameters under CoUpdater's state_dict keys."""
+    from emip_b200.chain import MotionChain
+    m = MotionChain()
+    keys = {k for k in m.state_dict() if not k.endswith("num_batches_tracked")}
+    P = cases.chain_params()
+    assert keys == set(P), (sorted(keys - set(P))[:5], sorted(set(P) - keys)[:5])
+    for k, v in m.state_dict().items():
+        if k in P:
+            assert tuple(v.shape) == tuple(P[k].shape), k
+    from oracle import ref_shim
+    if ref_shim.available():
+        ref_shim.install()
+        from model.EMIP_short.model import CoUpdater
+        ref = CoUpdater(ref_shim.model_args()).state_dict()
+        assert keys <= set(ref)
+        assert all(tuple(ref[k].shape) == tuple(P[k].shape) for k in keys)
+
+
+def test_chain_refuses_cpu_tensors():
+    m = _chain(cases.chain_params(hw=16 * 16, corr_mid=64), hw=16 * 16, corr_mid=64).eval()
+    from emip_b200._lib import EmipError
+    with torch.no_grad(), pytest.raises(EmipError):
+        m(torch.zeros(2, 128, 16, 16), torch.zeros(2, 128, 16, 16))
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _run_and_check(m, gm, seg, g, tol_flow=FLOW_TOL, tol_feat=FEAT_TOL):
+    B2, C, H, W = gm.shape
+    with torch.no_grad():
+        ffw, fbw, corr, fea_new, loc = m(gm.cuda(), seg.cuda(), want=("ab", "feat_tok", "flow_pred", "flow_prop", "mask"))
+    feat = loc["feat_tok"].view(B2, H, W, C).permute(0, 3, 1, 2)
+    big = 1e9
+    errs = {
+        "ab": cases.check_packed(loc["ab"], g["ab"], big, "ab"),
+        "feat": cases.check_packed(feat, g["feat"], big, "feat"),
+        "flow_pred": cases.check_packed(loc["flow_pred"], g["flow_pred"], big, "flow_pred"),
+        "flow_prop": cases.check_packed(loc["flow_prop"], g["flow_prop"], big, "flow_prop"),
+        "mask": cases.check_packed(loc["mask"], g["mask"], big, "upsampler mask"),
+        "flow_fw": cases.check_packed(ffw, g["flow_fw"], big, "flow_fw"),
+        "flow_bw": cases.check_packed(fbw, g["flow_bw"], big, "flow_bw"),
+        "corr": cases.check_packed(corr, g["corr"], big, "conv_corr output"),
+        "fea_new": cases.check_packed(fea_new, g["fea_new"], big, "injector1 output"),
+    }
+    print("chain rel-L2 vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})
+    tol = dict(ab=tol_feat, feat=tol_feat, corr=tol_feat, fea_new=tol_feat)
+    bad = {k: v for k, v in errs.items() if not v <= tol.get(k, tol_flow)}
+    assert not bad, f"over tolerance: {bad} (all: {errs})"
+    return errs, loc
+
+
+@pytest.mark.gpu
+def test_chain_randn_vs_reference(golden):
+    s = cases.CHAIN_CASES["chain_randn"]
+    d = cases.chain_inputs(s)
+    m = _chain(cases.chain_params(s["pseed"])).cuda().eval()
+    _run_and_check(m, d["gm"], d["seg"], golden("chain_randn"), tol_flow=FLOW_TOL_RANDN)
+
+
+@pytest.mark.gpu
+def test_chain_insitu_c1_vs_reference(golden):
+    """config c1: the features the real backbones produce for one seeded 352x352 pair (captured by hooks inside CoUpdater)."""
+    g = golden("chain_insitu")
+    m = _chain(cases.chain_params()).cuda().eval()
+    _run_and_check(m, g["gm"], g["seg"], g)
+
+
+@pytest.mark.gpu
+def test_chain_conv_corr_first_layer_token_major(golden):
+    """conv_corr[0] alone (no folded BatchNorm) from the chain's token rows against the reference's conv_corr[0] output."""
+    import ctypes
+    from emip_b200 import _lib
+    from emip_b200._lib import I, SZ, ptr, stream_ptr
+    from emip_b200._ws import workspace
+    from emip_b200.conv_corr import _prepared_weight
+    g = golden("chain_randn")
+    s = cases.CHAIN_CASES["chain_randn"]
+    d = cases.chain_inputs(s)
+    P = cases.chain_params(s["pseed"])
+    m = _chain(P).cuda().eval()
+    with torch.no_grad():
+        *_, loc = m(d["gm"].cuda(), d["seg"].cuda(), want=("feat_tok",))
+    tok = loc["feat_tok"]
+    B, H, W, C, Oc = s["b"], s["h"], s["w"], 128, 968
+    L = _lib.lib()
+    L.emip_conv_corr_workspace.restype = ctypes.c_size_t
+    ws, wp, wn = workspace(L.emip_conv_corr_workspace(I(B), I(C), I(H), I(W), I(Oc)), tok.device)
+    out = torch.empty((B, Oc, H, W), device=tok.device)
+    wprep = _prepared_weight(m.conv_corr[0].weight)[1]
+    _lib.check(L.emip_conv_corr_fwd_ex(ptr(tok[:B]), ptr(tok[B:]), ctypes.c_void_p(wprep), ptr(m.conv_corr[0].bias.detach()), None, None,
+                                       I(0), I(0), ptr(out), ctypes.c_void_p(wp), SZ(wn), I(B), I(C), I(H), I(W), I(Oc), stream_ptr()),
+               "emip_conv_corr_fwd_ex")
+    cases.check_packed(out, g["corr1"], FEAT_TOL, "conv_corr[0] output")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,b", [(16, 16, 1), (12, 20, 2)])
+def test_chain_small_vs_oracle(h, w, b):
+    """Fresh seeded inputs at sizes the oracle finishes in seconds (windows of 8x8 / 6x10 tokens, ragged pixel tiles)."""
+    P = cases.chain_params(seed=9, hw=h * w, corr_mid=72)
+    gm = cases.randn(301, (2 * b, 128, h, w), 2.2)
+    seg = cases.randn(302, (2 * b, 128, h, w), 1.0)
+    ref = O.motion_chain(gm, seg, P, want=("ab", "feat", "flow_pred", "flow_prop", "mask"))
+    m = _chain(P, hw=h * w, corr_mid=72).cuda().eval()
+    with torch.no_grad():
+        ffw, fbw, corr, fea_new, loc = m(gm.cuda(), seg.cuda(), want=("ab", "feat_tok", "flow_pred", "flow_prop", "mask"))
+    feat = loc["feat_tok"].view(2 * b, h, w, 128).permute(0, 3, 1, 2)
+    errs = dict(ab=_rel(loc["ab"], ref["ab"]), feat=_rel(feat, ref["feat"]), flow_pred=_rel(loc["flow_pred"], ref["flow_pred"]),
+                flow_prop=_rel(loc["flow_prop"], ref["flow_prop"]), mask=_rel(loc["mask"], ref["mask"]), flow_fw=_rel(ffw, ref["flow_fw"]),
+                flow_bw=_rel(fbw, ref["flow_bw"]), corr=_rel(corr, ref["corr"]), fea_new=_rel(fea_new, ref["fea_new"]))
+    print("chain small rel-L2 vs oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v <= FLOW_TOL_RANDN for v in errs.values()), errs
+    assert all(errs[k] <= 1e-3 for k in ("ab", "feat", "corr", "fea_new")), errs
+
+
+@pytest.mark.gpu
+def test_chain_batch_consistency():
+    """B = 3 pairs in one call == the same pairs one at a time (kernels pick different schedules / tile counts)."""
+    P = cases.chain_params()
+    m = _chain(P).cuda().eval()
+    gm = cases.randn(311, (6, 128, 44, 44), 2.2).cuda()
+    seg = cases.randn(312, (6, 128, 44, 44), 1.0).cuda()
+    with torch.no_grad():
+        full = m(gm, seg)
+        for i in range(3):
+            idx = torch.tensor([i, 3 + i], device="cuda")
+            one = m(gm[idx].contiguous(), seg[idx].contiguous())
+            for a, b_ in zip(one, full):
+                assert _rel(a, b_[i:i + 1]) < 2e-4

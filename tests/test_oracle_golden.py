@@ -225,3 +225,27 @@ def test_f2b_transformer_layer(golden, name):
             (out * d["wout"]).sum().backward()
             cases.check_packed(src.grad, g[tag]["dsource"], GTOL, tag + " dsource")
             cases.check_packed(tgt.grad, g[tag]["dtarget"], GTOL, tag + " dtarget")
+
+
+# ---- the chained path (model.py:92-97 + gmflow.py:81-162) against hook captures from the unmodified reference CoUpdater
+CHAIN_TOL = 2e-4       # twelve layers of fp32 re-association in front of near-one-hot softmaxes
+
+
+def _check_chain(out, g):
+    errs = {}
+    for k in cases.CHAIN_KEYS:
+        errs[k] = cases.check_packed(out[k], g[k], CHAIN_TOL, k)
+    return errs
+
+
+def test_chain_randn(golden):
+    s = cases.CHAIN_CASES["chain_randn"]
+    d = cases.chain_inputs(s)
+    out = O.motion_chain(d["gm"], d["seg"], cases.chain_params(s["pseed"]), want=("ab", "feat", "flow_pred", "flow_prop", "mask", "corr1"))
+    _check_chain(out, golden("chain_randn"))
+
+
+def test_chain_insitu_c1(golden):
+    g = golden("chain_insitu")
+    out = O.motion_chain(g["gm"], g["seg"], cases.chain_params(), want=("ab", "feat", "flow_pred", "flow_prop", "mask", "corr1"))
+    _check_chain(out, g)
