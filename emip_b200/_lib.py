@@ -55,8 +55,27 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Current stream of the CURRENT device -- call it inside ``on_device`` (or ``torch.cuda.device(t.device)``)."""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: the C ABI launches on the current device and
+    ``stream_ptr()`` hands it that device's current stream, so a tensor on cuda:1 must not be processed under cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        import torch
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 I = ctypes.c_int

@@ -42,6 +42,7 @@ def _prepared_weight(weight):
 
 class _ConvCorr(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, f0, f1, weight, bias):
         L = _lib.lib()
         B, C, H, W = f0.shape
@@ -60,6 +61,7 @@ class _ConvCorr(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         # five split-bf16 tensor-core GEMMs (csrc/gemm_tc.cu, conv_corr_bwd_tc): G recomputed, dG, dX9 -> df0, dW, df1
         f0, f1, weight, bias = ctx.saved_tensors

@@ -497,12 +497,8 @@ int attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st) {
   if (a.mode != ATTN_BWD_PV &&
       (rc = make_bf16_map(&mg, a.g_split, 256, (uint64_t)a.nr, (uint64_t)a.nb, 512, (uint64_t)a.nr * 512)))
     return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(attn_bwd_tc_kernel<false>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(attn_bwd_tc_kernel<true>), SMEM_BYTES)) return rc__;
   BParams bp;
   bp.a = a;
   bp.inv_sqrt_c = 1.0f / a.sqrt_c;

@@ -449,12 +449,8 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
     const uint64_t ld = ((uint64_t)a.nk + 7) / 8 * 8;     // = pair_bwd_tc_chn_ld
     if ((rc = make_bf16_map(&mv, a.v_split, (uint64_t)a.nk, 256, (uint64_t)a.nb, ld * 2, ld * 2 * 256))) return rc;
   } else if ((rc = make_bf16_map(&mv, a.v_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<false>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<true>), SMEM_BYTES)) return rc__;
   AParams ap;
   ap.a = a;
   ap.inv_sqrt_c = 1.0f / a.sqrt_c;

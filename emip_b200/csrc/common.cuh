@@ -40,16 +40,11 @@ void emip_set_error(const char* fmt, ...);
     }                                                                        \
   } while (0)
 
-static inline int emip_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+// SM count of the CURRENT device (cached per device; one process may drive several GPUs).
+int emip_num_sms();
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes) once per (kernel, device): the attribute is per device.
+// Mutex-guarded; returns EMIP_OK or the cudaError_t.
+int emip_func_max_smem(const void* func, int bytes);
 
 static inline size_t emip_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

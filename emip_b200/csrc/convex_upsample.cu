@@ -168,12 +168,8 @@ extern "C" int emip_convex_upsample_fwd(const float* flow, const float* mask, fl
   int rc = check("convex_upsample_fwd", B, h, w, k);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    EMIP_CUDA(cudaFuncSetAttribute(convex_up_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    EMIP_CUDA(cudaFuncSetAttribute(convex_up_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(convex_up_fwd_kernel), 200 * 1024)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(convex_up_bwd_kernel), 200 * 1024)) return rc__;
   convex_up_fwd_kernel<<<dim3(h, B), NT, fwd_smem(w), st>>>(flow, mask, out, h, w);
   EMIP_CHECK_LAUNCH("convex_up_fwd");
   return EMIP_OK;
@@ -187,12 +183,8 @@ extern "C" int emip_convex_upsample_bwd(const float* flow, const float* mask, co
   if (rc) return rc;
   if (ws_bytes < emip_convex_upsample_workspace(B, h, w)) { emip_set_error("convex_upsample_bwd: workspace too small"); return EMIP_ENOMEM; }
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    EMIP_CUDA(cudaFuncSetAttribute(convex_up_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    EMIP_CUDA(cudaFuncSetAttribute(convex_up_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(convex_up_fwd_kernel), 200 * 1024)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(convex_up_bwd_kernel), 200 * 1024)) return rc__;
   float* part = static_cast<float*>(workspace);
   convex_up_bwd_kernel<<<dim3(h, B), NT, bwd_smem(w), st>>>(flow, mask, dout, dmask, part, h, w, bwd_groups(w));
   EMIP_CHECK_LAUNCH("convex_up_bwd");

@@ -50,6 +50,7 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
     a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
     a.sqrt_c = sqrtf((float)C);
     a.sk_ws = static_cast<char*>(workspace) + sk_off; a.sk_bytes = sk_bytes;
+    a.schedule = (flags & EMIP_FLAG_SCHED_STREAMK) ? 1 : (flags & EMIP_FLAG_SCHED_ITEMS) ? 2 : 0;
     return match_tc_fwd(a, st);
   }
   PairFwdArgs a = {};

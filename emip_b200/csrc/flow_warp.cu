@@ -397,25 +397,20 @@ flow_warp_border3_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-int g_k3_ctas_per_sm = 2;
-bool g_k3_staged = true;
 }  // namespace
-
-extern "C" void emip_debug_flow_warp_staged_ctas(int v);
-extern "C" void emip_debug_flow_warp_staged_policy(int v);
-// Experiment switch (tools/k3_bench.py): v in 1..99 = direct-gather fast path with v persistent CTAs per SM;
-// 100 + v = shared-memory-staged fast path (flow_warp_staged.cu) with v persistent CTAs per SM and the adaptive
-// fallback to the direct kernel; 200 + v = staged kernel always; 0 = default (adaptive, 2 CTAs per SM).
-extern "C" void emip_debug_flow_warp_variant(int v) {
-  if (v >= 200) { g_k3_staged = true; emip_debug_flow_warp_staged_policy(1); emip_debug_flow_warp_staged_ctas(v - 200); }
-  else if (v >= 100) { g_k3_staged = true; emip_debug_flow_warp_staged_policy(0); emip_debug_flow_warp_staged_ctas(v - 100); }
-  else if (v > 0) { g_k3_staged = false; g_k3_ctas_per_sm = v; }
-  else { g_k3_staged = true; g_k3_ctas_per_sm = 2; emip_debug_flow_warp_staged_policy(0); emip_debug_flow_warp_staged_ctas(2); }
-}
 
 extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                                   long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream) {
+  return emip_flow_warp_fwd_ex(x, flow, out, B, C, H, W, flow_stride_b, flow_stride_c, pad_mode, EMIP_WARP_KERNEL_AUTO, nullptr,
+                               nullptr, 0u, stream);
+}
+
+extern "C" int emip_flow_warp_fwd_ex(const float* x, const float* flow, float* out, int B, int C, int H, int W,
+                                     long long flow_stride_b, long long flow_stride_c, int pad_mode, int kernel,
+                                     unsigned* dev_stats, unsigned* host_stats, unsigned seq, void* stream) {
   if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(kernel >= 0 && (kernel & 0xff) <= EMIP_WARP_KERNEL_STAGED, "flow_warp_fwd: bad kernel selector %d", kernel);
+  const int ksel = kernel & 0xff, ctas = (kernel >> 8) == 1 ? 1 : 2;     // bits 8..: persistent CTAs per SM (tools; default 2)
   EMIP_CHECK_ARG(x && flow && out, "flow_warp_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_fwd: bad pad_mode %d", pad_mode);
@@ -428,10 +423,12 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
   const bool border = pad_mode == EMIP_PAD_BORDER;
   if (C == 3 && border && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
-    const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    const int grid = (int)(nblk < (long long)emip_num_sms() * ctas ? nblk : (long long)emip_num_sms() * ctas);
     int rc = EMIP_ENOSYS;
-    if (g_k3_staged) rc = flow_warp_staged_launch(false, x, flow, nullptr, out, B, H, W, flow_stride_b, flow_stride_c, st);
+    if (ksel != EMIP_WARP_KERNEL_DIRECT)
+      rc = flow_warp_staged_launch(false, x, flow, nullptr, out, B, H, W, flow_stride_b, flow_stride_c, ctas, dev_stats, host_stats, seq, st);
     if (rc != EMIP_OK && rc != EMIP_ENOSYS) return rc;
+    if (rc == EMIP_ENOSYS && ksel == EMIP_WARP_KERNEL_STAGED) { emip_set_error("flow_warp_fwd: the staged kernel does not cover this shape / alignment"); return rc; }
     if (rc == EMIP_ENOSYS)
     flow_warp_border3_kernel<false><<<grid, 256, 0, st>>>(x, flow, nullptr, out, H, W, flow_stride_b, flow_stride_c,
                                                          tiles_x, tiles_y, (int)nblk, rcw, rch);
@@ -446,7 +443,17 @@ extern "C" int emip_flow_warp_fwd(const float* x, const float* flow, float* out,
 extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float* dout, float* dflow, float* dx,
                                   int B, int C, int H, int W, long long flow_stride_b, long long flow_stride_c,
                                   int pad_mode, void* stream) {
+  return emip_flow_warp_bwd_ex(x, flow, dout, dflow, dx, B, C, H, W, flow_stride_b, flow_stride_c, pad_mode, EMIP_WARP_KERNEL_AUTO,
+                               nullptr, nullptr, 0u, stream);
+}
+
+extern "C" int emip_flow_warp_bwd_ex(const float* x, const float* flow, const float* dout, float* dflow, float* dx,
+                                     int B, int C, int H, int W, long long flow_stride_b, long long flow_stride_c,
+                                     int pad_mode, int kernel, unsigned* dev_stats, unsigned* host_stats, unsigned seq,
+                                     void* stream) {
   if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(kernel >= 0 && (kernel & 0xff) <= EMIP_WARP_KERNEL_STAGED, "flow_warp_bwd: bad kernel selector %d", kernel);
+  const int ksel = kernel & 0xff, ctas = (kernel >> 8) == 1 ? 1 : 2;
   EMIP_CHECK_ARG(x && flow && dout && dflow, "flow_warp_bwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && C > 0 && H > 1 && W > 1, "flow_warp_bwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   EMIP_CHECK_ARG(pad_mode == EMIP_PAD_BORDER || pad_mode == EMIP_PAD_ZEROS, "flow_warp_bwd: bad pad_mode %d", pad_mode);
@@ -460,10 +467,12 @@ extern "C" int emip_flow_warp_bwd(const float* x, const float* flow, const float
   const bool border = pad_mode == EMIP_PAD_BORDER;
   if (C == 3 && border && dx == nullptr && (long long)H * W * 4 < 0x7fffffffLL) {
     const float rcw = 1.0f / (float)(W - 1), rch = 1.0f / (float)(H - 1);
-    const int grid = (int)(nblk < (long long)emip_num_sms() * g_k3_ctas_per_sm ? nblk : (long long)emip_num_sms() * g_k3_ctas_per_sm);
+    const int grid = (int)(nblk < (long long)emip_num_sms() * ctas ? nblk : (long long)emip_num_sms() * ctas);
     int rc = EMIP_ENOSYS;
-    if (g_k3_staged) rc = flow_warp_staged_launch(true, x, flow, dout, dflow, B, H, W, flow_stride_b, flow_stride_c, st);
+    if (ksel != EMIP_WARP_KERNEL_DIRECT)
+      rc = flow_warp_staged_launch(true, x, flow, dout, dflow, B, H, W, flow_stride_b, flow_stride_c, ctas, dev_stats, host_stats, seq, st);
     if (rc != EMIP_OK && rc != EMIP_ENOSYS) return rc;
+    if (rc == EMIP_ENOSYS && ksel == EMIP_WARP_KERNEL_STAGED) { emip_set_error("flow_warp_bwd: the staged kernel does not cover this shape / alignment"); return rc; }
     if (rc == EMIP_ENOSYS)
     flow_warp_border3_kernel<true><<<grid, 256, 0, st>>>(x, flow, dout, dflow, H, W, flow_stride_b, flow_stride_c, tiles_x,
                                                         tiles_y, (int)nblk, rcw, rch);

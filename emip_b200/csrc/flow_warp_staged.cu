@@ -454,63 +454,23 @@ int make_flow_map(CUtensorMap* m, const float* flow, int B, int H, int W, long l
   return make_map(m, flow, 4, dims, strides, box);
 }
 
-int g_staged_ctas_per_sm = 2;
-long long* g_staged_prof = nullptr;
-
-// Kernel choice feedback.  The staged kernel is ~15 % faster than the direct-gather kernel on smooth flow fields and
-// several times slower when most tiles fall back to global gathers (noisy flow: random-init / early training), and
-// both produce bit-identical results.  Every staged launch publishes its share of fallback tiles into mapped host
-// memory; the launcher reads the most recent value without synchronising (it may lag by a launch or two) and
-// switches to the direct kernel while that share is high, probing with the staged kernel every 32nd call.
-struct Feedback {
-  unsigned* dev = nullptr;            // device counters, one slot of 4 per in-flight launch (8 slots)
-  volatile unsigned* host = nullptr;  // mapped host memory: {seq, per-mille}
-  unsigned seq = 0, seen_seq = 0;
-  bool direct = false;
-  int direct_calls = 0;
-  bool failed = false;
-};
-Feedback g_fb;
-int g_staged_policy = 0;              // 0 = adaptive, 1 = always staged (tools)
-
-bool feedback_init() {
-  if (g_fb.dev != nullptr) return true;
-  if (g_fb.failed) return false;
-  void* h = nullptr;
-  if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaMalloc((void**)&g_fb.dev, 8 * 4 * sizeof(unsigned)) != cudaSuccess ||
-      cudaMemset(g_fb.dev, 0, 8 * 4 * sizeof(unsigned)) != cudaSuccess) {
-    cudaGetLastError();
-    g_fb.failed = true;
-    g_fb.dev = nullptr;
-    return false;
-  }
-  g_fb.host = static_cast<volatile unsigned*>(h);
-  g_fb.host[0] = 0; g_fb.host[1] = 0;
-  return true;
-}
+long long* g_staged_prof = nullptr;   // diagnostic switch (tools/k3_roles.py), documented in include/emip_b200.h
 
 }  // namespace
 
-// Experiment switch (tools/k3_bench.py): persistent CTAs per SM of the staged kernel (1 or 2).
 // Wait-cycle profile buffer: device pointer to [grid][8] int64 (producer: total, flow_empty, flow_full, win_empty;
-// worker warp 0: total, flow_full, win_full, tiles) or null.
+// worker warp 0: total, flow_full, win_full, tiles) or null.  Diagnostic, not thread-safe.
 extern "C" void emip_debug_flow_warp_staged_profile(long long* buf) { g_staged_prof = buf; }
-// Experiment switch: 1 = always use the staged kernel (no adaptive fallback to the direct kernel), 0 = adaptive.
-extern "C" void emip_debug_flow_warp_staged_policy(int v) { g_staged_policy = v; }
-extern "C" void emip_debug_flow_warp_staged_ctas(int v) { g_staged_ctas_per_sm = v >= 1 && v <= 2 ? v : 2; }
 
+// Stateless: launches the staged kernel or returns EMIP_ENOSYS when the shape / alignment is not covered.  The kernel-choice
+// feedback lives with the CALLER: when dev_stats (device, 16 zeroed bytes, not shared between launches in flight) and
+// host_stats (device-accessible pinned host memory, 8 bytes) are given, the last CTA publishes
+// host_stats = {seq, per-mille of tiles that had to gather from global memory} -- the staged kernel is ~15 % faster than
+// the direct-gather kernel on smooth flow fields and several times slower when most tiles fall back (noisy flow); both
+// produce bit-identical results, so a caller may switch kernels on that number (emip_b200/warp.py does).
 int flow_warp_staged_launch(bool bwd, const float* x, const float* flow, const float* dout, float* out, int B, int H, int W,
-                            long long fsb, long long fsc, cudaStream_t st) {
-  const bool adaptive = g_staged_policy == 0 && feedback_init();
-  if (adaptive) {
-    const unsigned seq = g_fb.host[0];
-    if (seq != g_fb.seen_seq) {                          // a staged launch has finished since the last look
-      g_fb.seen_seq = seq;
-      g_fb.direct = g_fb.host[1] > 300u;                 // > 30 % of the tiles gathered from global memory
-      g_fb.direct_calls = 0;
-    }
-    if (g_fb.direct && (++g_fb.direct_calls & 31) != 0) return EMIP_ENOSYS;   // caller uses the direct kernel
-  }
+                            long long fsb, long long fsc, int ctas_per_sm, unsigned* dev_stats, unsigned* host_stats,
+                            unsigned seq, cudaStream_t st) {
   // TMA: 16-byte aligned bases and pitches; tap coordinates are packed 16 bits per axis (dp2a operands are signed)
   auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
   if ((W & 3) != 0 || W >= 32768 || H >= 32768 || W < 2 || H < 2 || misaligned(x) || misaligned(flow) ||
@@ -547,17 +507,11 @@ int flow_warp_staged_launch(bool bwd, const float* x, const float* flow, const f
     c.dout = dout;
   }
   const int smem = bwd ? Layout<true>::BYTES : Layout<false>::BYTES;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bwd]) {
-    cudaError_t e = bwd ? cudaFuncSetAttribute(flow_warp_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                        : cudaFuncSetAttribute(flow_warp_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { emip_set_error("flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set[bwd] = true;
-  }
+  if (int rc__ = emip_func_max_smem(bwd ? (const void*)flow_warp_staged_kernel<true> : (const void*)flow_warp_staged_kernel<false>, smem)) return rc__;
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * ROWS - 1) / (8 * ROWS);
   const long long nblk = (long long)B * tiles_x * tiles_y;
   if (nblk >= 0x7fffffffLL) return EMIP_ENOSYS;
-  const long long cap = (long long)emip_num_sms() * g_staged_ctas_per_sm;
+  const long long cap = (long long)emip_num_sms() * (ctas_per_sm == 1 ? 1 : 2);
   const int grid = (int)(nblk < cap ? nblk : cap);
   StagedParams P;
   P.x = x; P.out = out;
@@ -566,14 +520,10 @@ int flow_warp_staged_launch(bool bwd, const float* x, const float* flow, const f
   P.rcw = 1.0f / (float)(W - 1); P.rch = 1.0f / (float)(H - 1);
   P.prof = g_staged_prof;
   P.dev_stats = nullptr; P.host_stats = nullptr; P.seq = 0;
-  if (adaptive) {
-    // publishing costs ~3 us of kernel tail (system-scope write): sample every 8th launch, and every probe
-    const unsigned s = ++g_fb.seq;
-    if (g_fb.direct || s <= 2 || (s & 7u) == 0) {
-      P.seq = s ? s : 1u;
-      P.dev_stats = g_fb.dev + 4 * ((s >> 3) & 7u);
-      P.host_stats = g_fb.host;
-    }
+  if (dev_stats != nullptr && host_stats != nullptr) {      // publishing costs ~3 us of kernel tail (system-scope write)
+    P.seq = seq ? seq : 1u;
+    P.dev_stats = dev_stats;
+    P.host_stats = host_stats;
   }
   if (bwd) flow_warp_staged_kernel<true><<<grid, THREADS, smem, st>>>(c.maps, P);
   else flow_warp_staged_kernel<false><<<grid, THREADS, smem, st>>>(c.maps, P);

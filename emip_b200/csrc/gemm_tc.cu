@@ -550,11 +550,7 @@ int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_
 int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b, GemmTcParams p, int batch,
                    cudaStream_t st) {
   const int max_smem = 227 * 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(gemm_tc_kernel), max_smem)) return rc__;
   if (p.stages == 0) {
     p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024);
     p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;

@@ -718,16 +718,12 @@ int make_store_map(CUtensorMap* m, float* base, int slabs, int nq, int nk, bool 
 
 static unsigned long long* g_prof = nullptr;
 static int g_softmax_warps = 0;
-static int g_schedule = 0;   // 0 = choose, 1 = stream-K spans, 2 = grid-strided items
 // Diagnostics: force 8 or 16 softmax warps per CTA (tools/k1_roles.py compares them); 0 = choose by mode:
 // 8 for the 3-term split (UMMA-bound: fewer warps = no spills, less smem/L1 traffic next to the operand reads),
 // 16 for single-pass bf16 (softmax-bound: r1p 70 vs 76 us).
 extern "C" void emip_match_tc_set_variant(int softmax_warps) {
   g_softmax_warps = (softmax_warps == 16 || softmax_warps == 8) ? softmax_warps : 0;
 }
-
-// Diagnostics: force the work schedule (0 = choose by batch size, 1 = stream-K spans, 2 = grid-strided whole items).
-extern "C" void emip_match_tc_set_schedule(int mode) { g_schedule = (mode == 1 || mode == 2) ? mode : 0; }
 
 // Diagnostics: device buffer of gridDim.x * 8 counters filled by the next launches (NULL switches it off).
 extern "C" void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf) { g_prof = dev_buf; }
@@ -786,14 +782,10 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
     s_mode = tma_ok ? 1 : 2;
     if (!tma_ok) ms = mx;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EMIP_CUDA(cudaFuncSetAttribute(match_tc_fwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(match_tc_fwd_kernel<8, false>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(match_tc_fwd_kernel<16, false>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(match_tc_fwd_kernel<8, true>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(match_tc_fwd_kernel<16, true>), SMEM_BYTES)) return rc__;
   KParams p;
   p.v = a.v; p.v_stride_b = a.v_stride_b; p.out = a.out; p.lse = a.lse; p.s_out = a.s_out;
   p.nb = a.nb; p.nq = a.nq; p.nk = a.nk; p.y_shift = a.y_shift; p.y_mod = a.y_mod;
@@ -810,7 +802,7 @@ int match_tc_fwd(const MatchTcArgs& a, cudaStream_t st) {
   // and the score-emitting items -- the second half of the list -- unbalance contiguous spans.)
   const int sms = emip_num_sms();
   const int waves = (n_items + sms - 1) / sms;
-  const int stream_k = g_schedule == 1 ? 1 : g_schedule == 2 ? 0 : ((double)n_items < 0.8 * waves * sms ? 1 : 0);
+  const int stream_k = a.schedule == 1 ? 1 : a.schedule == 2 ? 0 : ((double)n_items < 0.8 * waves * sms ? 1 : 0);
   const int grid = stream_k ? (int)(units < sms ? units : sms) : (n_items < sms ? n_items : sms);
   p.cnt = nullptr; p.part = nullptr; p.pmax = 1;
   if (stream_k) {

@@ -20,6 +20,7 @@ struct MatchTcArgs {
   int s_first, s_count;
   float sqrt_c;
   int terms;               // 3 = bf16 hi/lo split (hi.hi + lo.hi + hi.lo, fp32-accurate); 1 = single-pass bf16
+  int schedule;            // 0 = choose by batch size, 1 = stream-K spans, 2 = grid-strided whole items (EMIP_FLAG_SCHED_*)
   void* sk_ws;             // stream-K bookkeeping, match_tc_streamk_bytes(nb, nq, nk) bytes, 16-byte aligned
   size_t sk_bytes;
 };

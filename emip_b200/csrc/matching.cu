@@ -87,6 +87,7 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
     a.sqrt_c = sqrtf((float)C);
     a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
     a.sk_ws = ws.sk; a.sk_bytes = ws.sk_bytes;
+    a.schedule = (flags & EMIP_FLAG_SCHED_STREAMK) ? 1 : (flags & EMIP_FLAG_SCHED_ITEMS) ? 2 : 0;
     return match_tc_fwd(a, st);
   }
   if (flags & EMIP_FLAG_TOKEN_MAJOR) {

@@ -310,11 +310,7 @@ extern "C" int emip_memory_read_fwd(const float* m_in, const float* m_out, const
   p.part_o = reinterpret_cast<float*>(w); w += 8 * al((size_t)B * KC * Q);
   p.part_m = reinterpret_cast<float*>(w); w += 8 * al((size_t)B * Q);
   p.part_l = reinterpret_cast<float*>(w);
-  static bool attr = false;
-  if (!attr) {
-    EMIP_CUDA(cudaFuncSetAttribute(mem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD));
-    attr = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(mem_fwd_kernel), (int)SMEM_FWD)) return rc__;
   const int nqb = (Q + BM - 1) / BM;
   mem_fwd_kernel<<<B * p.nsplit * nqb, NT, SMEM_FWD, st>>>(p);
   EMIP_CHECK_LAUNCH("mem_fwd");
@@ -349,12 +345,8 @@ extern "C" int emip_memory_read_bwd(const float* m_in, const float* m_out, const
   p.part_dq = reinterpret_cast<float*>(w); w += 8 * al((size_t)B * KC * Q) + 16 * al((size_t)B * Q);
   float* dvec = reinterpret_cast<float*>(w);
   p.dvec = dvec;
-  static bool attr = false;
-  if (!attr) {
-    EMIP_CUDA(cudaFuncSetAttribute(mem_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BQ));
-    EMIP_CUDA(cudaFuncSetAttribute(mem_bwd_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BM));
-    attr = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(mem_bwd_q_kernel), (int)SMEM_BQ)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(mem_bwd_m_kernel), (int)SMEM_BM)) return rc__;
   mem_dvec_kernel<<<dim3((Q + 127) / 128, B), 128, 0, st>>>(dmem, dmem_stride_b, mem, mem_stride_b, dvec, Q);
   EMIP_CHECK_LAUNCH("mem_dvec");
   const int nqb = (Q + BM - 1) / BM, nmb = (M + BM - 1) / BM;

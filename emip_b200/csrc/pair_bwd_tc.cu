@@ -444,11 +444,7 @@ int pair_bwd_tc(const PairBwdTcArgs& a, cudaStream_t st) {
   if ((rc = make_bf16_map(&my1, a.tok_split_y, 256, (uint64_t)a.nc, (uint64_t)a.n_split, 512, (uint64_t)a.nc * 512))) return rc;
   const uint64_t ld = (uint64_t)pair_bwd_tc_chn_ld(a.nc);
   if ((rc = make_bf16_map(&my2, a.chn_split_y, (uint64_t)a.nc, 256, (uint64_t)a.n_split, ld * 2, ld * 2 * 256))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(pair_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(pair_bwd_tc_kernel), SMEM_BYTES)) return rc__;
   BParams bp;
   bp.a = a;
   bp.inv_sqrt_c = 1.0f / a.sqrt_c;

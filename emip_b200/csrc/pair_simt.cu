@@ -296,12 +296,7 @@ size_t pair_bwd_simt_smem() { return sizeof(float) * (BM * LDX + BN * LDX + BM *
 
 int pair_fwd_simt(const PairFwdArgs& a, cudaStream_t st) {
   if (a.nb == 0 || a.nq == 0) return EMIP_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(pair_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)pair_fwd_simt_smem()));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(pair_fwd_simt_kernel), (int)pair_fwd_simt_smem())) return rc__;
   int nrb = (a.nq + BM - 1) / BM;
   pair_fwd_simt_kernel<<<a.nb * nrb, NT, pair_fwd_simt_smem(), st>>>(a);
   EMIP_CHECK_LAUNCH("pair_fwd_simt");
@@ -310,12 +305,7 @@ int pair_fwd_simt(const PairFwdArgs& a, cudaStream_t st) {
 
 int pair_bwd_simt(const PairBwdArgs& a, cudaStream_t st) {
   if (a.nb == 0 || a.nr == 0) return EMIP_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EMIP_CUDA(cudaFuncSetAttribute(pair_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)pair_bwd_simt_smem()));
-    attr_done = true;
-  }
+  if (int rc__ = emip_func_max_smem((const void*)(pair_bwd_simt_kernel), (int)pair_bwd_simt_smem())) return rc__;
   int nrb = (a.nr + BM - 1) / BM;
   pair_bwd_simt_kernel<<<a.nb * nrb, NT, pair_bwd_simt_smem(), st>>>(a);
   EMIP_CHECK_LAUNCH("pair_bwd_simt");

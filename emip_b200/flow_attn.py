@@ -17,6 +17,7 @@ class _LinearCN(torch.autograd.Function):
     without permuting it (csrc/linear_cn.cu: split-bf16 tensor-core GEMMs, forward and backward)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, w, bias):
         B, K, N = x.shape
         M = w.shape[0]
@@ -33,6 +34,7 @@ class _LinearCN(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         B, K, N = x.shape
@@ -54,6 +56,7 @@ class _FlowAttnCore(torch.autograd.Function):
     to v)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, q, k, v, flags):
         if flags & FLAG_CHANNEL_MAJOR:
             B, C, N = q.shape
@@ -75,8 +78,11 @@ class _FlowAttnCore(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
+        if ctx.flags & 4:
+            raise _lib.EmipError("emip_b200 flow attention: bf16=True is the forward-only inference mode")
         if ctx.needs_input_grad[2]:
             raise NotImplementedError("emip_b200 flow attention has no gradient w.r.t. the value: the model passes "
                                       "flow.detach() (gmflow.py:137)")
@@ -96,10 +102,11 @@ class _FlowAttnCore(torch.autograd.Function):
         return dq, dk, None, None
 
 
-def flow_attention_core(q, k, v, exact_fp32=False, bf16=False, channel_major=False):
+def flow_attention_core(q, k, v, exact_fp32=False, bf16=False, channel_major=False, schedule=None):
     if not q.is_cuda:
         raise _lib.EmipError("emip_b200 flow attention needs CUDA tensors (no CPU fallback)")
-    return _FlowAttnCore.apply(q, k, v, (1 if exact_fp32 else (4 if bf16 else 0)) | (FLAG_CHANNEL_MAJOR if channel_major else 0))
+    sched = {None: 0, "auto": 0, "stream_k": 32, "items": 64}[schedule]
+    return _FlowAttnCore.apply(q, k, v, (1 if exact_fp32 else (4 if bf16 else 0)) | (FLAG_CHANNEL_MAJOR if channel_major else 0) | sched)
 
 
 class FeatureFlowAttention(nn.Module):
@@ -121,6 +128,7 @@ class FeatureFlowAttention(nn.Module):
                 nn.init.xavier_uniform_(p)
         self.exact_fp32 = False
         self.bf16 = False        # bf16 inference mode (single-pass bf16 operands, 2e-2 tolerance)
+        self.schedule = None     # "stream_k" / "items": force the fused kernel's work schedule (same results)
 
     def forward(self, feature0, flow, local_window_attn=False, local_window_radius=1, **kwargs):
         if local_window_attn:
@@ -135,10 +143,10 @@ class FeatureFlowAttention(nn.Module):
             # the projections on the feature map as it lies in memory (channel-major), on the tensor cores
             query = _LinearCN.apply(feature0.reshape(b, c, h * w), self.q_proj.weight, self.q_proj.bias)      # transformer.py:523
             key = _LinearCN.apply(query, self.k_proj.weight, self.k_proj.bias)                              # transformer.py:524
-            out = flow_attention_core(query, key, value, bf16=self.bf16, channel_major=True)
+            out = flow_attention_core(query, key, value, bf16=self.bf16, channel_major=True, schedule=self.schedule)
             return out.view(b, 2, h, w)
         query = feature0.view(b, c, h * w).permute(0, 2, 1)       # [B, HW, C]
         query = self.q_proj(query)                                 # transformer.py:523 (exact-fp32 path: library GEMM)
         key = self.k_proj(query)                                   # transformer.py:524
-        out = flow_attention_core(query, key, value, exact_fp32=self.exact_fp32, bf16=self.bf16)
+        out = flow_attention_core(query, key, value, exact_fp32=self.exact_fp32, bf16=self.bf16, schedule=self.schedule)
         return out.view(b, 2, h, w)

@@ -34,6 +34,7 @@ def _ptr_array(tensors):
 
 class _InjectorFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, x1, flags, *params):
         B, C, H, W = x.shape
         x = x.contiguous()
@@ -55,6 +56,7 @@ class _InjectorFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         x, x1, saved, *params = ctx.saved_tensors
         B, C, H, W = x.shape

@@ -13,6 +13,7 @@ BF16 = 4         # EMIP_FLAG_BF16
 
 class _GlobalMatching(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, f0, f1, bidir, want_corr, flags):
         B, C, H, W = f0.shape
         N = H * W
@@ -40,11 +41,15 @@ class _GlobalMatching(torch.autograd.Function):
         return flow, smem
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dflow, dsmem):
         f0, f1, flow, lse = ctx.saved_tensors
         B, C, H, W = f0.shape
         if dflow is None and dsmem is None:
             return None, None, None, None, None
+        if ctx.flags & BF16:
+            raise _lib.EmipError("emip_b200 global matching: bf16=True is the forward-only inference mode (its saved log-sum-exp "
+                                 "comes from bf16 scores); train with the default split-bf16 mode")
         L = _lib.lib()
         L.emip_global_matching_workspace.restype = ctypes.c_size_t
         nbytes = L.emip_global_matching_workspace(I(B), I(C), I(H), I(W))
@@ -65,8 +70,11 @@ class _GlobalMatching(torch.autograd.Function):
 _lazy_corr = [False]
 
 
+SCHED = {None: 0, "auto": 0, "stream_k": 32, "items": 64}   # EMIP_FLAG_SCHED_STREAMK / EMIP_FLAG_SCHED_ITEMS
+
+
 def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return_corr=True, exact_fp32=False,
-                               bf16=False):
+                               bf16=False, schedule=None):
     """GMFlow global matching: returns ``(flow, prob, corr)`` like the reference.
 
     Same positional signature and results as
@@ -81,7 +89,8 @@ def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return
     ``exact_fp32=True`` selects the exact-fp32 CUDA-core kernel instead of the
     tcgen05 kernel (bf16 hi/lo operand split, fp32 accumulation).  ``bf16=True``
     is the bf16 inference mode: operands rounded once to bf16 (no split), fp32
-    accumulation and softmax; forward only, 2e-2 tolerance.
+    accumulation and softmax; forward only, 2e-2 tolerance.  ``schedule`` ("stream_k" / "items"; default: chosen by
+    batch size) forces the work schedule of the fused kernel -- same results either way.
     """
     if not (feature0.is_cuda and feature1.is_cuda):
         raise _lib.EmipError("emip_b200.global_correlation_softmax needs CUDA tensors (no CPU fallback)")
@@ -96,7 +105,7 @@ def global_correlation_softmax(feature0, feature1, pred_bidir_flow=False, return
     if lazy:
         return_corr = False
     flow, smem = _GlobalMatching.apply(feature0, feature1, bool(pred_bidir_flow), bool(return_corr),
-                                       EXACT_FP32 if exact_fp32 else (BF16 if bf16 else 0))
+                                       (EXACT_FP32 if exact_fp32 else (BF16 if bf16 else 0)) | SCHED[schedule])
     corr = None
     if smem is not None:
         corr = smem if pred_bidir_flow else smem.view(B, H, W, H * W).permute(0, 3, 1, 2)

@@ -13,6 +13,7 @@ class _MemoryRead(torch.autograd.Function):
     """out[:, :Do] = m_out softmax_m(m_in^T q_in / sqrt(De)); out[:, Do:] = q_out  (one [B,2*Do,H,W] tensor)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, m_in, m_out, q_in, q_out, exact_fp32):
         B, De, T, H, W = m_in.shape
         Do = m_out.shape[1]
@@ -41,11 +42,14 @@ class _MemoryRead(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         m_in, m_out, q_in, out, lse = ctx.saved_tensors
         B, De, T, H, W = m_in.shape
         Do = m_out.shape[1]
         M, Q = T * H * W, H * W
+        if lse is None:                                   # only q_out needs a gradient: the pass-through half of dout
+            return None, None, None, dout[:, Do:].reshape(ctx.q_out_shape), None
         dout = dout.contiguous()
         L = _lib.lib()
         dm_in, dm_out, dq_in = torch.empty_like(m_in), torch.empty_like(m_out), torch.empty_like(q_in)

@@ -14,6 +14,7 @@ from ._ws import workspace
 
 class _Photometric(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, im, rec, mask, w_l1, w_ssim):
         B, C, H, W = im.shape
         im, rec, mask = im.contiguous(), rec.contiguous(), mask.contiguous()
@@ -28,6 +29,7 @@ class _Photometric(torch.autograd.Function):
         return sums[3].clone()
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, gloss):
         im, rec, mask, sums = ctx.saved_tensors
         B, C, H, W = im.shape

@@ -29,6 +29,7 @@ W_TRANS = 2
 GELU_BWD_IN = 4
 
 
+@_lib.on_device
 def _linear_call(x2, w, flags, aux=None):
     """x2 [L, in] contiguous fp32 CUDA, w [M, K] -> [L, M] (or [L, K] with W_TRANS); aux: rows for GELU_BWD_IN."""
     L_, M, K = x2.shape[0], w.shape[0], w.shape[1]
@@ -46,6 +47,7 @@ def _linear_call(x2, w, flags, aux=None):
 
 class _LinearTM(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, w, gelu_in):
         if ctx.needs_input_grad[1]:
             raise NotImplementedError("emip_b200 linear_tm: weight gradients are not built (the GMFlow weights are frozen, "
@@ -58,6 +60,7 @@ class _LinearTM(torch.autograd.Function):
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dy):
         x2, w = ctx.saved_tensors
         dx = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w, W_TRANS)
@@ -70,6 +73,7 @@ class _LinearMultiTM(torch.autograd.Function):
     """Several bias-free layers of one shape on the same rows: one operand split, n GEMMs (``emip_linear_tm_multi_fwd``)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, *ws):
         if any(ctx.needs_input_grad[1:]):
             raise NotImplementedError("emip_b200 linear_tm: weight gradients are not built (the GMFlow weights are frozen, "
@@ -93,6 +97,7 @@ class _LinearMultiTM(torch.autograd.Function):
         return tuple(y.view(*x.shape[:-1], M) for y in ys)
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, *dys):
         dx = None
         for w, dy in zip(ctx.saved_tensors, dys):
@@ -116,6 +121,7 @@ class _MlpTM(torch.autograd.Function):
     operand split of the mlp[0] input-gradient GEMM (no elementwise pass over the [L, 1024] tensors)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, w1, w2):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             raise NotImplementedError("emip_b200 mlp: weight gradients are not built (the GMFlow weights are frozen, train.py:340-342)")
@@ -128,6 +134,7 @@ class _MlpTM(torch.autograd.Function):
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dy):
         h, w1, w2 = ctx.saved_tensors
         dh = _linear_call(dy.reshape(-1, dy.shape[-1]).contiguous(), w2, W_TRANS)
@@ -135,6 +142,7 @@ class _MlpTM(torch.autograd.Function):
         return dx.view(ctx.in_shape), None, None
 
 
+@_lib.on_device
 def linear_ln_tm(x, weight, ln_weight, ln_bias, eps=1e-5, residual=None):
     """``residual + F.layer_norm(F.linear(x, weight), (128,), ln_weight, ln_bias, eps)`` in one C-ABI call: the LayerNorm runs in
     the GEMM epilogue (no autograd graph: inference / no-grad path)."""
@@ -156,6 +164,7 @@ def linear_ln_tm(x, weight, ln_weight, ln_bias, eps=1e-5, residual=None):
     return y.view(*x.shape[:-1], M)
 
 
+@_lib.on_device
 def mlp_tm(x, w1, w2, ln_weight=None, ln_bias=None, eps=1e-5, residual=None):
     """``F.linear(F.gelu(F.linear(x, w1)), w2)`` in one C-ABI call (no autograd graph: inference / no-grad path); with
     ``ln_weight`` the result is ``residual + F.layer_norm(..., ln_weight, ln_bias, eps)`` (LayerNorm in the last epilogue)."""
@@ -198,6 +207,7 @@ def linear_tm(x, weight, gelu_in=False):
 
 class _LayerNormTM(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x, gamma, beta, eps, res):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             raise NotImplementedError("emip_b200 layer_norm_tm: affine-parameter gradients are not built (frozen GMFlow)")
@@ -212,6 +222,7 @@ class _LayerNormTM(torch.autograd.Function):
         return y.view(x.shape)
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dy):
         x2, gamma = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()

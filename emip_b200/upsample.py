@@ -11,6 +11,7 @@ from ._ws import workspace
 
 class _ConvexUpsample(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, flow, mask, k):
         B, _, h, w = flow.shape
         flow, mask = flow.contiguous(), mask.contiguous()
@@ -22,6 +23,7 @@ class _ConvexUpsample(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         flow, mask = ctx.saved_tensors
         B, _, h, w = flow.shape

@@ -1,4 +1,7 @@
 """flow_warp: drop-in for reference loss/warp_utils.py:83-93 (K3)."""
+import ctypes
+import threading
+
 import torch
 
 from . import _lib
@@ -16,20 +19,88 @@ def _flow_strides(flow12):
     return flow12, flow12.stride(0), flow12.stride(1)
 
 
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_STAGED = 0, 1, 2
+
+
+class _KernelChoice:
+    """Caller-side state of the staged-vs-direct kernel choice for one device (the C library keeps none).
+
+    Every few staged launches are handed a small device counter block and a pinned host word pair; the kernel's last CTA
+    publishes ``{seq, per-mille of tiles that fell back to global gathers}`` there.  The host reads the most recent value
+    without synchronising (it may lag by a launch or two) and uses the direct-gather kernel while that share is above 30 %,
+    probing with the staged kernel every 32nd call.  Both kernels are bit-identical, so the choice never changes results.
+    Guarded by a lock: forward runs on the Python thread, backward on autograd-engine threads.
+    """
+
+    def __init__(self, device):
+        self.lock = threading.Lock()
+        self.dev = torch.zeros(8 * 4, dtype=torch.int32, device=device)       # one slot of 4 counters per launch in flight
+        self.host = torch.zeros(2, dtype=torch.int32).pin_memory()             # device-accessible (UVA) pinned words
+        self.seq = 0
+        self.seen = 0
+        self.direct = False
+        self.direct_calls = 0
+
+    def pick(self):
+        """-> (kernel, dev_stats pointer or None, host_stats pointer or None, seq)."""
+        with self.lock:
+            if torch.cuda.is_current_stream_capturing():
+                return (KERNEL_DIRECT if self.direct else KERNEL_AUTO), None, None, 0
+            seq = int(self.host[0]) & 0xffffffff
+            if seq != self.seen:                                  # a staged launch has finished since the last look
+                self.seen = seq
+                self.direct = (int(self.host[1]) & 0xffffffff) > 300
+                self.direct_calls = 0
+            if self.direct:
+                self.direct_calls += 1
+                if self.direct_calls & 31:
+                    return KERNEL_DIRECT, None, None, 0
+            self.seq = (self.seq + 1) & 0x7fffffff or 1
+            s = self.seq
+            if self.direct or s <= 2 or (s & 7) == 0:             # publishing costs ~3 us of kernel tail: sample
+                return KERNEL_AUTO, self.dev.data_ptr() + 16 * ((s >> 3) & 7), self.host.data_ptr(), s
+            return KERNEL_AUTO, None, None, 0
+
+
+_choices = {}
+_choices_lock = threading.Lock()
+
+
+def _choice(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    c = _choices.get(key)
+    if c is None:
+        with _choices_lock:
+            c = _choices.get(key)
+            if c is None:
+                c = _choices[key] = _KernelChoice(torch.device("cuda", key))
+    return c
+
+
+def _pick(x, kernel):
+    if kernel is not None:
+        return kernel, None, None, 0
+    return _choice(x.device).pick()
+
+
 class _FlowWarp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, flow12, pad_mode):
+    @_lib.on_device
+    def forward(ctx, x, flow12, pad_mode, kernel):
         B, C, H, W = x.shape
         x = x.contiguous()
         flow12, sb, sc = _flow_strides(flow12)
         out = torch.empty_like(x)
-        _lib.check(_lib.lib().emip_flow_warp_fwd(ptr(x), ptr(flow12), ptr(out), I(B), I(C), I(H), I(W),
-                                                 LL(sb), LL(sc), I(pad_mode), stream_ptr()), "emip_flow_warp_fwd")
+        k, ds, hs, seq = _pick(x, kernel)
+        _lib.check(_lib.lib().emip_flow_warp_fwd_ex(ptr(x), ptr(flow12), ptr(out), I(B), I(C), I(H), I(W), LL(sb), LL(sc), I(pad_mode),
+                                                    I(k), ctypes.c_void_p(ds), ctypes.c_void_p(hs), ctypes.c_uint(seq), stream_ptr()),
+                   "emip_flow_warp_fwd_ex")
         ctx.save_for_backward(x, flow12)
-        ctx.pad_mode = pad_mode
+        ctx.pad_mode, ctx.kernel = pad_mode, kernel
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         x, flow12 = ctx.saved_tensors
         B, C, H, W = x.shape
@@ -37,19 +108,22 @@ class _FlowWarp(torch.autograd.Function):
         need_dx, need_dflow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dflow = torch.empty((B, 2, H, W), dtype=x.dtype, device=x.device)
         dx = torch.zeros_like(x) if need_dx else None
-        _lib.check(_lib.lib().emip_flow_warp_bwd(ptr(x), ptr(flow12), ptr(dout), ptr(dflow), ptr(dx),
-                                                 I(B), I(C), I(H), I(W), LL(flow12.stride(0)), LL(flow12.stride(1)),
-                                                 I(ctx.pad_mode), stream_ptr()), "emip_flow_warp_bwd")
-        return dx, (dflow if need_dflow else None), None
+        k, ds, hs, seq = _pick(x, ctx.kernel)
+        _lib.check(_lib.lib().emip_flow_warp_bwd_ex(ptr(x), ptr(flow12), ptr(dout), ptr(dflow), ptr(dx), I(B), I(C), I(H), I(W),
+                                                    LL(flow12.stride(0)), LL(flow12.stride(1)), I(ctx.pad_mode), I(k),
+                                                    ctypes.c_void_p(ds), ctypes.c_void_p(hs), ctypes.c_uint(seq), stream_ptr()),
+                   "emip_flow_warp_bwd_ex")
+        return dx, (dflow if need_dflow else None), None, None
 
 
-def flow_warp(x, flow12, pad="border", mode="bilinear"):
+def flow_warp(x, flow12, pad="border", mode="bilinear", kernel=None):
     """Bilinear warp of ``x`` [B,C,H,W] by ``flow12`` [B,2,H,W] (pixels; ch0 = dx, ch1 = dy).
 
     Same signature, argument meaning and result as the reference's
     ``loss.warp_utils.flow_warp`` (warp_utils.py:83-93): align_corners=True,
     ``pad`` in {'border', 'zeros'}.  ``flow12`` may be a channel slice of a wider
-    tensor (loss_flow.py:90-91); no copy is made.
+    tensor (loss_flow.py:90-91); no copy is made.  ``kernel`` (not in the reference): None = adaptive choice between
+    the two bit-identical kernels (``_KernelChoice``), or KERNEL_AUTO / KERNEL_DIRECT / KERNEL_STAGED to force one.
     """
     if mode != "bilinear":
         raise NotImplementedError("emip_b200.flow_warp implements mode='bilinear' only (the reference's only use)")
@@ -61,9 +135,10 @@ def flow_warp(x, flow12, pad="border", mode="bilinear"):
         raise TypeError("emip_b200.flow_warp computes in fp32; cast inputs explicitly")
     if flow12.shape[0] != x.shape[0] or flow12.shape[1] != 2 or flow12.shape[2:] != x.shape[2:]:
         raise ValueError(f"flow12 {tuple(flow12.shape)} does not match x {tuple(x.shape)}")
-    return _FlowWarp.apply(x, flow12, _PAD[pad])
+    return _FlowWarp.apply(x, flow12, _PAD[pad], kernel)
 
 
+@_lib.on_device
 def get_occu_mask_backward(flow21, th=0.2):
     """Occlusion mask from the backward flow: drop-in for reference loss/warp_utils.py:106-112.
 

@@ -26,6 +26,7 @@ from ._ws import workspace
 
 class _Attention(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, q, k, v):
         nb, n, c = q.shape
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -39,6 +40,7 @@ class _Attention(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         q, k, v = ctx.saved_tensors
         return _attention_bwd(q, k, v, dout.contiguous())
@@ -103,6 +105,7 @@ class _WindowAttention(torch.autograd.Function):
     """One C-ABI call per layer: the window partition is address arithmetic inside the kernels (csrc/window_attn.cu)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, q, k, v, num_splits, with_shift, h, w):
         b, _, c = q.shape
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -123,6 +126,7 @@ class _WindowAttention(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
         num_splits, with_shift, h, w = ctx.geom

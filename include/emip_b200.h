@@ -18,7 +18,23 @@
  *    cudaError_t for launch failures; emip_last_error() holds the message
  *    (thread-local).
  *  - re-entrant: forward is called on the Python thread, backward on autograd
- *    engine threads.  The only shared state is a mutex-guarded tensor-map cache.
+ *    engine threads.  Compute entry points keep NO state between calls.  The
+ *    complete list of process-wide mutable state in the library:
+ *      (1) one mutex-guarded cache in csrc/abi.cu: the SM count per device and the
+ *          set of (kernel, device) pairs whose dynamic-shared-memory limit has been
+ *          raised (cudaFuncSetAttribute is per device) -- one process may drive
+ *          several GPUs; the pointers must belong to the CURRENT device and the
+ *          stream to that device (the Python host wraps calls in
+ *          torch.cuda.device(tensor.device));
+ *      (2) the address of the driver's cuTensorMapEncodeTiled, resolved once;
+ *      (3) thread-local: the last error string, and flow_warp's two most recent
+ *          tensor maps (keyed by pointer / shape / strides; never shared);
+ *      (4) diagnostic switches for the profiling scripts under tools/ --
+ *          emip_match_tc_set_profile_buffer, emip_match_tc_set_variant,
+ *          emip_attn_tc_set_profile_buffer, emip_debug_flow_warp_staged_profile --
+ *          NOT thread-safe, never touched by the host package, default off.
+ *    No entry point allocates or frees memory (cudaMalloc / cudaHostAlloc), so all
+ *    of them may be captured into CUDA graphs once (1) is warm (first call).
  *  - there is NO CPU fallback: on a machine without an sm_100 device every
  *    compute entry point fails.
  */
@@ -47,6 +63,8 @@ extern "C" {
 #define EMIP_FLAG_CHANNEL_MAJOR 8  /* flow_attn_fwd / _bwd: q, k (and dq, dk) are channel-major [B,C,N] instead of [B,N,C] */
 #define EMIP_FLAG_TOKEN_MAJOR 16   /* global_matching_fwd: f0, f1 are token-major [B,H*W,C] -- the FeatureTransformer's own
                                        output layout (transformer.py:476, before the permute of :479-480) */
+#define EMIP_FLAG_SCHED_STREAMK 32  /* global_matching_fwd / flow_attn_fwd: force the stream-K work schedule (default: chosen by */
+#define EMIP_FLAG_SCHED_ITEMS 64    /* batch size) / force grid-strided whole items -- results are identical either way */
 #define EMIP_LAYOUT_TOKEN_MAJOR 0  /* [B][H*W][C] */
 #define EMIP_LAYOUT_CHANNEL_MAJOR 1 /* [B][C][H*W]  (NCHW feature maps) */
 
@@ -61,6 +79,10 @@ int emip_device_check(void);
  * [producer: q_empty, k_empty | issuer: s_empty, k_full, q_full, total | softmax warp 2: s_full, total].
  * NULL (the default) switches it off.  Not thread-safe; for profiling scripts only. */
 void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf);
+/* Diagnostics: force 8 or 16 softmax warps per CTA in the same kernel (0 = default choice). */
+void emip_match_tc_set_variant(int softmax_warps);
+/* Diagnostics: wait-cycle profile of the staged flow_warp kernel, device pointer to [grid][8] int64 or NULL. */
+void emip_debug_flow_warp_staged_profile(long long* buf);
 
 /* ---- a3: flow_warp ------------------------------------------------------- */
 /* Replaces loss/warp_utils.py:83-93 flow_warp(x, flow12, pad, mode='bilinear')
@@ -73,7 +95,26 @@ void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf);
  *   pad_mode EMIP_PAD_BORDER ('border', the photometric loss) or EMIP_PAD_ZEROS. */
 int emip_flow_warp_fwd(const float* x, const float* flow, float* out, int B, int C, int H, int W,
                        long long flow_stride_b, long long flow_stride_c, int pad_mode, void* stream);
-/* Backward of the above.  dflow [B,2,H,W] contiguous is overwritten.  dx may be
+/* As emip_flow_warp_fwd / _bwd with an explicit kernel choice and CALLER-OWNED kernel-choice feedback (the library keeps
+ * none).  For C = 3, border padding, no image gradient there are two bit-identical kernels: a TMA-staged one (taps from
+ * shared memory: ~15 % faster on smooth flow such as the model's convex-upsampled output) and a direct-gather one (several
+ * times faster than the staged kernel when most 32x32 tiles have a flow range > ~14 px, e.g. iid noise).
+ *   kernel     EMIP_WARP_KERNEL_AUTO (staged when shape / alignment allow, else direct), _DIRECT, _STAGED (ENOSYS if not
+ *              covered); bits 8.. = persistent CTAs per SM (0 = default 2; tools only)
+ *   dev_stats  NULL or 16 bytes of zeroed device memory owned by the caller, not shared by launches in flight at once
+ *   host_stats NULL or 8 bytes of device-accessible pinned host memory: when both are given and the staged kernel runs, its
+ *              last CTA writes host_stats[1] = per-mille of tiles that fell back to global gathers, then host_stats[0] = seq
+ *              (and re-zeroes dev_stats).  emip_b200/warp.py keeps such buffers per device and switches kernels on it. */
+#define EMIP_WARP_KERNEL_AUTO 0
+#define EMIP_WARP_KERNEL_DIRECT 1
+#define EMIP_WARP_KERNEL_STAGED 2
+int emip_flow_warp_fwd_ex(const float* x, const float* flow, float* out, int B, int C, int H, int W, long long flow_stride_b,
+                          long long flow_stride_c, int pad_mode, int kernel, unsigned* dev_stats, unsigned* host_stats,
+                          unsigned seq, void* stream);
+int emip_flow_warp_bwd_ex(const float* x, const float* flow, const float* dout, float* dflow, float* dx, int B, int C, int H,
+                          int W, long long flow_stride_b, long long flow_stride_c, int pad_mode, int kernel, unsigned* dev_stats,
+                          unsigned* host_stats, unsigned seq, void* stream);
+/* Backward of emip_flow_warp_fwd.  dflow [B,2,H,W] contiguous is overwritten.  dx may be
  * NULL (images need no gradient in the photometric loss); otherwise it must be
  * zero-filled [B,C,H,W] and receives the scatter-added image gradient. */
 int emip_flow_warp_bwd(const float* x, const float* flow, const float* dout, float* dflow, float* dx,

@@ -194,43 +194,37 @@ def test_a1_odd_tile_count_and_batches():
         assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
 
 
-@pytest.mark.parametrize("schedule", [1, 2], ids=["stream_k", "strided_items"])
+@pytest.mark.parametrize("schedule", ["stream_k", "items"])
 def test_a1_a2_work_schedules(schedule):
     """Both work schedules of the fused tcgen05 kernel (equal spans of key tiles with a cross-CTA merge of the
-    online-softmax rows / whole items grid-strided) against the CPU restatement: small and c2-sized batches."""
-    from emip_b200 import _lib
+    online-softmax rows / whole items grid-strided) against the CPU oracle: small and c2-sized batches."""
     from emip_b200.matching import global_correlation_softmax
     from emip_b200.flow_attn import FeatureFlowAttention
-    L = _lib.lib()
-    L.emip_match_tc_set_schedule(schedule)
-    try:
-        for (b, h, w) in ((1, 44, 44), (3, 20, 16), (11, 24, 20)):
-            f0 = cases.randn(170 + b, (b, 128, h, w), 1.5)
-            f1 = cases.randn(180 + b, (b, 128, h, w), 1.5)
-            ref_flow, _, ref_corr = O.global_correlation_softmax(f0, f1, True)
-            flow, _, corr = global_correlation_softmax(dev(f0), dev(f1), True)
-            assert rel(flow, ref_flow) < TOL_OUT, (b, h, w)
-            assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
-        # c2 size: against the exact-fp32 CUDA-core path
-        f0 = dev(cases.randn(2, (16, 128, 44, 44), 4.1))
-        f1 = dev(cases.randn(3, (16, 128, 44, 44), 4.1))
-        flow_tc, _, corr_tc = global_correlation_softmax(f0, f1, True)
-        flow_ex, _, corr_ex = global_correlation_softmax(f0, f1, True, exact_fp32=True)
-        assert rel(flow_tc, flow_ex) < TOL_OUT and rel(corr_tc, corr_ex) < TOL_EXACT
-        # a2 (value table mode) against its golden vector
-        name = list(cases.A2_CASES)[0]
-        sp = cases.A2_CASES[name]
-        d = cases.a2_inputs(sp)
-        m = FeatureFlowAttention(sp["c"]).cuda()
-        m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
-        ref = O.feature_flow_attention(d["x"], d["flow"], d["q_proj.weight"], d["q_proj.bias"], d["k_proj.weight"],
-                                       d["k_proj.bias"])
-        assert rel(m(dev(d["x"]), dev(d["flow"])), ref) < TOL_OUT
-    finally:
-        L.emip_match_tc_set_schedule(0)
+    for (b, h, w) in ((1, 44, 44), (3, 20, 16), (11, 24, 20)):
+        f0 = cases.randn(170 + b, (b, 128, h, w), 1.5)
+        f1 = cases.randn(180 + b, (b, 128, h, w), 1.5)
+        ref_flow, _, ref_corr = O.global_correlation_softmax(f0, f1, True)
+        flow, _, corr = global_correlation_softmax(dev(f0), dev(f1), True, schedule=schedule)
+        assert rel(flow, ref_flow) < TOL_OUT, (b, h, w)
+        assert rel(corr, ref_corr) < TOL_EXACT, (b, h, w)
+    # c2 size (16 pairs, 44 x 44): against the oracle itself
+    f0 = cases.randn(2, (16, 128, 44, 44), 4.1)
+    f1 = cases.randn(3, (16, 128, 44, 44), 4.1)
+    ref_flow, _, ref_corr = O.global_correlation_softmax(f0, f1, True)
+    flow_tc, _, corr_tc = global_correlation_softmax(dev(f0), dev(f1), True, schedule=schedule)
+    assert rel(flow_tc, ref_flow) < TOL_OUT and rel(corr_tc, ref_corr) < TOL_EXACT
+    # a2 (value table mode) against its golden vector
+    name = list(cases.A2_CASES)[0]
+    sp = cases.A2_CASES[name]
+    d = cases.a2_inputs(sp)
+    m = FeatureFlowAttention(sp["c"]).cuda()
+    m.schedule = schedule
+    m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
+    ref = O.feature_flow_attention(d["x"], d["flow"], d["q_proj.weight"], d["q_proj.bias"], d["k_proj.weight"],
+                                   d["k_proj.bias"])
+    assert rel(m(dev(d["x"]), dev(d["flow"])), ref) < TOL_OUT
 
 
-# ----------------------------------------------------------------------------- a2
 @pytest.mark.parametrize("exact", [True, False], ids=["exact_fp32", "tcgen05"])
 @pytest.mark.parametrize("name", list(cases.A2_CASES))
 def test_a2_flow_attention_golden(golden, name, exact):
@@ -795,3 +789,150 @@ def test_f2b_self_layer_shared_split_vs_separate_calls():
     ys = linear_tm_multi(dev(xs), [dev(w) for w in ws])
     for y, w in zip(ys, ws):
         assert rel(y, xs.double() @ w.double().T) < TOL_EXACT
+
+
+# ------------------------------------------------------------------- BASELINE config sizes against the oracle itself
+def test_a1_c2_vs_oracle():
+    """c2 (B = 16, 44 x 44, C = 128, bidirectional, corr): the tensor-core path against the CPU oracle, forward + backward."""
+    from emip_b200.matching import global_correlation_softmax
+    f0 = cases.randn(2, (16, 128, 44, 44), 4.1)
+    f1 = cases.randn(3, (16, 128, 44, 44), 4.1)
+    wf = cases.randn(4, (32, 2, 44, 44))
+    c0, c1 = f0.clone().requires_grad_(True), f1.clone().requires_grad_(True)
+    rflow, _, rcorr = O.global_correlation_softmax(c0, c1, True)
+    (rflow * wf).sum().backward()
+    g0, g1 = dev(f0).requires_grad_(True), dev(f1).requires_grad_(True)
+    flow, _, corr = global_correlation_softmax(g0, g1, True)
+    (flow * dev(wf)).sum().backward()
+    assert rel(flow, rflow) < TOL_OUT and rel(corr, rcorr) < TOL_EXACT
+    assert rel(g0.grad, c0.grad) < TOL_GRAD and rel(g1.grad, c1.grad) < TOL_GRAD
+
+
+def test_a1_a2_c3_batch64_vs_oracle():
+    """c3 / c5 size (B = 64 pairs): one call on the GPU, the oracle on chunks of 16 samples of the same batch."""
+    from emip_b200.matching import global_correlation_softmax
+    from emip_b200.flow_attn import FeatureFlowAttention
+    f0 = cases.randn(5, (64, 128, 44, 44), 4.1)
+    f1 = cases.randn(6, (64, 128, 44, 44), 4.1)
+    flow, _, _ = global_correlation_softmax(dev(f0), dev(f1), True, return_corr=False)
+    prm = cases.ffa_params(5)
+    m = FeatureFlowAttention(128).cuda()
+    m.load_state_dict(prm)
+    with torch.no_grad():
+        prop = m(torch.cat((dev(f0), dev(f1)), 0), flow)
+    for c in range(0, 64, 16):
+        sl = slice(c, c + 16)
+        rflow, _, _ = O.global_correlation_softmax(f0[sl], f1[sl], True)
+        assert rel(flow[sl], rflow[:16]) < TOL_OUT and rel(flow[64:][sl], rflow[16:]) < TOL_OUT, c
+        if c == 16:       # flow propagation (2B = 128 maps on the GPU) on one chunk: forward flows of f0, backward flows of f1
+            x = torch.cat((f0[sl], f1[sl]), 0)
+            ref = O.feature_flow_attention(x, rflow, prm["q_proj.weight"], prm["q_proj.bias"], prm["k_proj.weight"], prm["k_proj.bias"])
+            assert rel(prop[sl], ref[:16]) < TOL_OUT and rel(prop[64:][sl], ref[16:]) < TOL_OUT
+
+
+def test_a2_c2_batch32_vs_oracle():
+    """a2 at 2B = 32 maps (the c2 batch) against the oracle, forward + backward to the features."""
+    from emip_b200.flow_attn import FeatureFlowAttention
+    x = cases.randn(7, (32, 128, 44, 44), 4.1)
+    fl = cases.randn(8, (32, 2, 44, 44), 12.0)
+    wo = cases.randn(9, (32, 2, 44, 44))
+    prm = cases.ffa_params(6)
+    m = FeatureFlowAttention(128).cuda()
+    m.load_state_dict(prm)
+    cx = x.clone().requires_grad_(True)
+    ref = O.feature_flow_attention(cx, fl, prm["q_proj.weight"], prm["q_proj.bias"], prm["k_proj.weight"], prm["k_proj.bias"])
+    (ref * wo).sum().backward()
+    gx = dev(x).requires_grad_(True)
+    out = m(gx, dev(fl))
+    (out * dev(wo)).sum().backward()
+    assert rel(out, ref) < TOL_OUT and rel(gx.grad, cx.grad) < TOL_GRAD
+
+
+@pytest.mark.parametrize("name", list(cases.A2_CASES))
+def test_a2_bf16_mode(golden, name):
+    """FeatureFlowAttention.bf16 = True (c3's single-pass bf16 operand mode): within 2e-2 of the fp32 reference."""
+    from emip_b200.flow_attn import FeatureFlowAttention
+    g = golden(name)
+    s = cases.A2_CASES[name]
+    d = cases.a2_inputs(s)
+    m = FeatureFlowAttention(s["c"]).cuda()
+    m.load_state_dict({k: d[k] for k in ("q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias")})
+    m.bf16 = True
+    with torch.no_grad():
+        out = m(dev(d["x"]), dev(d["flow"]))
+    e = cases.check_packed(out, g["out"], TOL_BF16, "out")
+    print(f"{name} a2 bf16: rel-L2 {e:.2e}")
+    x = dev(d["x"]).requires_grad_(True)
+    with pytest.raises(Exception):                  # forward-only mode: the backward refuses
+        m(x, dev(d["flow"])).sum().backward()
+
+
+def test_a4_batch64_subsampled_vs_oracle():
+    """a4 at the c3 batch (64 samples in one call): four samples of the batch against the oracle."""
+    from emip_b200.injector import injector_forward
+    p = cases.injector_params(44)
+    x = cases.randn(441, (64, 128, 44, 44), 2.2)
+    x1 = cases.randn(442, (64, 128, 44, 44), 1.0)
+    with torch.no_grad():
+        out = injector_forward(dev(x), dev(x1), {k: dev(v) for k, v in p.items()})
+    idx = [0, 21, 42, 63]
+    ref = O.injector(x[idx], x1[idx], p)
+    assert rel(out[idx], ref) < 1e-4
+
+
+def test_a3_c5_batch64_vs_oracle():
+    """a3 at B = 64, 3 x 352 x 352 (config c5's call): two samples of the batch against the oracle, both flow slices."""
+    from emip_b200.warp import flow_warp
+    B, H, W = 64, 352, 352
+    x = cases.randn(91, (B, 3, H, W))
+    fl4 = torch.cat([cases.smooth_flow(92, B, H, W, 12.0), cases.smooth_flow(93, B, H, W, 12.0)], 1)
+    xg, fg = dev(x), dev(fl4)
+    for sl in (slice(0, 2), slice(2, 4)):
+        out = flow_warp(xg, fg[:, sl])
+        for b in (5, 63):
+            ref = O.flow_warp(x[b:b + 1], fl4[b:b + 1, sl])
+            assert rel(out[b:b + 1], ref) < 1e-5
+
+
+def test_a3_two_threads_two_streams():
+    """Forward on one thread / stream and backward on another at the same time (the autograd engine does exactly that):
+    the library keeps no kernel-choice state, the host-side choice is lock-guarded; results stay bit-identical."""
+    import threading
+    from emip_b200.warp import flow_warp, KERNEL_DIRECT, KERNEL_STAGED
+    B, H, W = 8, 352, 352
+    x = dev(cases.randn(95, (B, 3, H, W)))
+    smooth = dev(cases.smooth_flow(96, B, H, W, 6.0))
+    noisy = dev(cases.randn(97, (B, 2, H, W), 20.0))
+    wout = dev(cases.randn(98, (B, 3, H, W)))
+    ref = {}
+    for name, fl in (("smooth", smooth), ("noisy", noisy)):
+        f = fl.clone().requires_grad_(True)
+        o = flow_warp(x, f, kernel=KERNEL_DIRECT)
+        (o * wout).sum().backward()
+        ref[name] = (o.detach().clone(), f.grad.clone())
+        f2 = fl.clone().requires_grad_(True)
+        o2 = flow_warp(x, f2, kernel=KERNEL_STAGED)
+        (o2 * wout).sum().backward()
+        assert torch.equal(o2, ref[name][0]) and torch.equal(f2.grad, ref[name][1])     # the two kernels are bit-identical
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(name, fl, n):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(n):
+                    f = fl.clone().requires_grad_(True)
+                    o = flow_warp(x, f)                    # adaptive choice, shared per-device state
+                    (o * wout).sum().backward()
+                    if not (torch.equal(o, ref[name][0]) and torch.equal(f.grad, ref[name][1])):
+                        errors.append(name)
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=("smooth", smooth, 60)), threading.Thread(target=worker, args=("noisy", noisy, 60))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]

@@ -30,7 +30,17 @@ def flows(dev, g):
             "iid20px": 20.0 * torch.randn(B, 4, H, W, device=dev, generator=g)}
 
 
-def run(dev, hbm_peak, iters=50):
+def variant_kernel(v):
+    """1-99: direct gather, v CTAs per SM; 1xx: staged (auto), v - 100 CTAs per SM; 2xx: staged only."""
+    if v >= 200:
+        return 2 | ((v - 200) << 8)
+    if v >= 100:
+        return 0 | ((v - 100) << 8)
+    return 1 | (v << 8)
+
+
+def run(dev, hbm_peak, iters=50, variant=0):
+    from emip_b200 import warp
     L = _lib.lib()
     g = torch.Generator(device=dev).manual_seed(5)
     x = torch.randn(B, C, H, W, device=dev, generator=g)
@@ -44,18 +54,26 @@ def run(dev, hbm_peak, iters=50):
     for name, fl in flows(dev, g).items():
         f = fl[:, 2:]      # the channel-slice call pattern of loss_flow.py:91
 
+        def pick():
+            if variant == 0:
+                return warp._choice(dev).pick()           # the product's adaptive choice (emip_b200/warp.py)
+            return variant_kernel(variant), None, None, 0
+
         def fwd():
-            _lib.check(L.emip_flow_warp_fwd(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)),
-                                            LL(f.stride(1)), I(0), sp), "fwd")
+            k, ds, hs, seq = pick()
+            _lib.check(L.emip_flow_warp_fwd_ex(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0),
+                                               I(k), ctypes.c_void_p(ds), ctypes.c_void_p(hs), ctypes.c_uint(seq), sp), "fwd")
 
         def bwd():
-            _lib.check(L.emip_flow_warp_bwd(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W),
-                                            LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "bwd")
+            k, ds, hs, seq = pick()
+            _lib.check(L.emip_flow_warp_bwd_ex(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W), LL(f.stride(0)),
+                                               LL(f.stride(1)), I(0), I(k), ctypes.c_void_p(ds), ctypes.c_void_p(hs), ctypes.c_uint(seq),
+                                               sp), "bwd")
         r = {}
         for tag, fn, nbytes in (("fwd", fwd, fw_bytes), ("bwd", bwd, bw_bytes)):
             for _ in range(10):
                 fn()
-            torch.cuda.synchronize()      # lets the launcher's kernel-choice feedback land (see flow_warp_staged.cu)
+            torch.cuda.synchronize()      # lets the kernel-choice feedback land (emip_b200/warp.py)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(iters):
@@ -77,9 +95,8 @@ if __name__ == "__main__":
     import sys as _sys
     variants = [int(a, 0) for a in _sys.argv[1:]] or [0]
     for variant in variants:
-      _lib.lib().emip_debug_flow_warp_variant(variant)
-      print("variant (0 = default: staged + adaptive; 1-99 direct, 1xx staged adaptive, 2xx staged always):", variant)
-      r = run(torch.device("cuda", 0), pk)
+      print("variant (0 = product: adaptive choice in emip_b200/warp.py; 1-99 direct, 1xx staged if covered, 2xx staged only):", variant)
+      r = run(torch.device("cuda", 0), pk, variant=variant)
       for k, v in r.items():
           print(f"{k:11s} fwd {v['fwd']['launch_ms']*1e3:7.1f} us {v['fwd']['achieved']:7.0f} GB/s ({100*v['fwd']['frac']:4.1f}%)   "
                 f"bwd {v['bwd']['launch_ms']*1e3:7.1f} us {v['bwd']['achieved']:7.0f} GB/s ({100*v['bwd']['frac']:4.1f}%)")

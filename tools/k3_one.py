@@ -13,7 +13,8 @@ variant, field = int(sys.argv[1]), sys.argv[2]
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda", 0)
 L = _lib.lib()
-L.emip_debug_flow_warp_variant(variant)
+kern = k3_bench.variant_kernel(variant) if variant else 0
+nul = ctypes.c_void_p(None)
 g = torch.Generator(device=dev).manual_seed(5)
 B, C, H, W = k3_bench.B, k3_bench.C, k3_bench.H, k3_bench.W
 x = torch.randn(B, C, H, W, device=dev, generator=g)
@@ -23,7 +24,7 @@ dflow = torch.empty(B, 2, H, W, device=dev)
 f = k3_bench.flows(dev, g)[field][:, 2:]
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(iters):
-    _lib.check(L.emip_flow_warp_fwd(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "fwd")
-    _lib.check(L.emip_flow_warp_bwd(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "bwd")
+    _lib.check(L.emip_flow_warp_fwd_ex(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), I(kern), nul, nul, ctypes.c_uint(0), sp), "fwd")
+    _lib.check(L.emip_flow_warp_bwd_ex(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), I(kern), nul, nul, ctypes.c_uint(0), sp), "bwd")
 torch.cuda.synchronize()
 print("done", variant, field)

@@ -10,7 +10,8 @@ from emip_b200._lib import I, LL, ptr
 field = sys.argv[1] if len(sys.argv) > 1 else "model_like"
 dev = torch.device("cuda", 0)
 L = _lib.lib()
-L.emip_debug_flow_warp_variant(202)
+kern = k3_bench.variant_kernel(202)
+nul = ctypes.c_void_p(None)
 g = torch.Generator(device=dev).manual_seed(5)
 B, C, H, W = k3_bench.B, k3_bench.C, k3_bench.H, k3_bench.W
 x = torch.randn(B, C, H, W, device=dev, generator=g); out = torch.empty_like(x)
@@ -18,8 +19,8 @@ dout = torch.randn(B, C, H, W, device=dev, generator=g); dflow = torch.empty(B, 
 f = k3_bench.flows(dev, g)[field][:, 2:]
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 prof = torch.zeros(296, 8, dtype=torch.int64, device=dev)
-def fwd(): _lib.check(L.emip_flow_warp_fwd(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "fwd")
-def bwd(): _lib.check(L.emip_flow_warp_bwd(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), sp), "bwd")
+def fwd(): _lib.check(L.emip_flow_warp_fwd_ex(ptr(x), ptr(f), ptr(out), I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), I(kern), nul, nul, ctypes.c_uint(0), sp), "fwd")
+def bwd(): _lib.check(L.emip_flow_warp_bwd_ex(ptr(x), ptr(f), ptr(dout), ptr(dflow), None, I(B), I(C), I(H), I(W), LL(f.stride(0)), LL(f.stride(1)), I(0), I(kern), nul, nul, ctypes.c_uint(0), sp), "bwd")
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     for _ in range(3): fn()
     L.emip_debug_flow_warp_staged_profile(ctypes.c_void_p(prof.data_ptr()))
