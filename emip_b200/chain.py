@@ -102,6 +102,7 @@ class _VersionCache:
 
 
 _pos_cache = {}
+_ft_cache = _VersionCache()
 
 
 def window_position(h, w, splits, channels, device):
@@ -272,6 +273,56 @@ def conv_corr_head(tok, B, h, w, conv0, w_prep, scale, shift):
     return out
 
 
+FT_KEYS = ("self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.merge.weight",
+           "self_attn.norm1.weight", "self_attn.norm1.bias", "cross_attn_ffn.q_proj.weight", "cross_attn_ffn.k_proj.weight",
+           "cross_attn_ffn.v_proj.weight", "cross_attn_ffn.merge.weight", "cross_attn_ffn.norm1.weight", "cross_attn_ffn.norm1.bias",
+           "cross_attn_ffn.mlp.0.weight", "cross_attn_ffn.mlp.2.weight", "cross_attn_ffn.norm2.weight", "cross_attn_ffn.norm2.bias")
+
+
+def _ft_weights(transformer):
+    """[n_blocks][16] parameter tensors of a FeatureTransformer in the C ABI's order (= the reference's state_dict order)."""
+    out = []
+    for blk in transformer.layers:
+        sd = dict(blk.named_parameters())
+        out.append([sd[k] for k in FT_KEYS])
+    return out
+
+
+def feature_transformer_tokens(x, transformer, h, w, num_splits, cache=None):
+    """The whole FeatureTransformer (transformer.py:433-482) on token rows x [2B, h*w, 128] (frame 1 | frame 2) in one C-ABI
+    call, inference only; ``transformer`` = any module with ``.layers[i].self_attn / .cross_attn_ffn`` (ours or the reference's)."""
+    _need_cuda(x, "feature_transformer")
+    B2, N, C = x.shape
+    x = x.contiguous()
+    ws_list = _ft_weights(transformer)
+    flat = [t for blk in ws_list for t in blk]
+    nb = len(ws_list)
+    L = _lib.lib()
+
+    def make():
+        L.emip_feature_transformer_weight_bytes.restype = ctypes.c_size_t
+        buf, p, _ = workspace(L.emip_feature_transformer_weight_bytes(I(nb)), x.device)
+        cont = [t.detach().contiguous() for t in flat]
+        arr = (ctypes.c_void_p * len(cont))(*[t.data_ptr() for t in cont])
+        with torch.cuda.device(x.device):
+            _lib.check(L.emip_feature_transformer_prepare(arr, I(nb), ctypes.c_void_p(p), stream_ptr()), "emip_feature_transformer_prepare")
+        return buf, p, cont, arr
+    cache = cache if cache is not None else _ft_cache
+    buf, prep, cont, arr = cache.get(("ft", id(transformer), str(x.device)), flat, make)
+    L.emip_feature_transformer_workspace.restype = ctypes.c_size_t
+    need = L.emip_feature_transformer_workspace(I(B2), I(h), I(w), I(C))
+    if need == 0:
+        raise _lib.EmipError(f"emip_b200 feature_transformer: unsupported shape B={B2} h={h} w={w} C={C}")
+    ws, ws_ptr, ws_n = workspace(need, x.device)
+    out = torch.empty_like(x)
+    eps = transformer.layers[0].self_attn.norm1.eps
+    with torch.cuda.device(x.device):
+        _lib.check(L.emip_feature_transformer_fwd(ptr(x), ptr(out), arr, ctypes.c_void_p(prep), I(nb), ctypes.c_void_p(ws_ptr), SZ(ws_n),
+                                                  I(B2), I(h), I(w), I(C), I(num_splits), ctypes.c_float(eps), stream_ptr()),
+                   "emip_feature_transformer_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ the chain
 def transformer_block(blk, x, h, w, num_splits):
     """One FeatureTransformer block (transformer.py:377-401) on token rows x [2B, h*w, C] = (frame 1 | frame 2), inference:
@@ -311,6 +362,7 @@ class MotionChain(nn.Module):
         else:
             self.injector, self.injector1, self.GMFlow, self.conv_corr = _borrow
         self.attn_splits = attn_splits
+        self.fused_transformer = True        # one C-ABI call for the six blocks; False = one call per layer op (same kernels)
         self._cache = _VersionCache()
 
     @classmethod
@@ -352,8 +404,11 @@ class MotionChain(nn.Module):
         with torch.cuda.device(dev):
             ab = self.injector(gm, seg)                                                          # model.py:92-93, one call
             x = tokens_from_cn(ab, window_position(H, W, self.attn_splits, C, dev))              # gmflow.py:114 + transformer.py:439-462
-            for blk in gmf.transformer.layers:                                                   # transformer.py:464-473
-                x = transformer_block(blk, x, H, W, self.attn_splits)
+            if self.fused_transformer:
+                x = feature_transformer_tokens(x, gmf.transformer, H, W, self.attn_splits, self._cache)   # transformer.py:433-482
+            else:
+                for blk in gmf.transformer.layers:                                               # transformer.py:464-473
+                    x = transformer_block(blk, x, H, W, self.attn_splits)
             flow_pred = global_matching_tokens(x, B, H, W)              # gmflow.py:121
             ffa = gmf.feature_flow_attn
             q = linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)                            # transformer.py:523

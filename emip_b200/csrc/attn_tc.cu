@@ -377,11 +377,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               OUT = p.out;
               orow = p.win.pixel(prob, row);
             }
+            if (p.out != nullptr || ns != 1) {
             float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               dst[q] = make_float4(__uint_as_float(r[4 * q]) * sc, __uint_as_float(r[4 * q + 1]) * sc,
                                    __uint_as_float(r[4 * q + 2]) * sc, __uint_as_float(r[4 * q + 3]) * sc);
+            }
+            if (p.out_hi != nullptr && ns == 1) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const float v0 = __uint_as_float(r[2 * q]) * sc, v1 = __uint_as_float(r[2 * q + 1]) * sc;
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi[q] << 16), v1 - __uint_as_float(hi[q] & 0xffff0000u));
+                lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_hi) + orow * p.out_ld + cb);
+              uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_lo) + orow * p.out_ld + cb);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+              }
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) OUT[(size_t)(cb + i) * p.nq + row] = __uint_as_float(r[i]) * sc;

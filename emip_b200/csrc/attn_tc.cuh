@@ -35,6 +35,9 @@ struct AttnTcArgs {
   float sqrt_c;
   int ksplit;                // > 1: the key tiles of a row tile are dealt to ksplit CTAs (few row tiles, many keys)
   AttnWinMap win;            // enabled: out is the [B][h][w][128] image, rows are scattered (needs ksplit == 1, NC layout)
+  // optional (ksplit == 1, NC layout): the output rows as bf16 hi / lo (rows out_ld elements apart, same row order as `out`) --
+  // the pre-split A operand of the merge GEMM (ft.cu); `out` may then be NULL
+  void* out_hi; void* out_lo; int out_ld;
 };
 
 bool attn_tc_supported(int nq, int nk, int c);

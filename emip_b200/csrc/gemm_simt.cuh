@@ -38,6 +38,12 @@ struct GemmNT {
   // tensor-core path only, K == 128: c = c_res + LayerNorm over the K outputs of a row (gamma, beta [K]; c_res rows ldc apart or NULL)
   const float* ln_gamma; const float* ln_beta; float ln_eps; const float* c_res;
   const float* c_bias;                                                             // tensor-core path only: [K] added per output column
+  // tensor-core path only (ft.cu): pitch of the pre-split A rows (0: kpad(N)); B operand already split ([K][2 * kpad(N)] hi | lo
+  // rows, as split_rows_kernel writes it); LayerNorm epilogue also / only emitting bf16 hi | lo rows (c may then be NULL);
+  // window-ordered split output (see GemmTcParams::split_dst)
+  int a_ld_pre; const void* b_pre;
+  void* ln_hi; void* ln_lo; int ln_ld;
+  void* split_dst[4]; const void* rowmap; int npix, n_img, img_shift;
 };
 int gemm_nt(const GemmNT& a, cudaStream_t st);
 

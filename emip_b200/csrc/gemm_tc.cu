@@ -247,6 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_wait(r);
         if (row < p.M) {
           float4* d = reinterpret_cast<float4*>(o + c0);
+          __nv_bfloat16* sh = p.ln_hi ? p.ln_hi + (size_t)row * p.ln_ld + c0 : nullptr;
+          __nv_bfloat16* sl = p.ln_hi ? p.ln_lo + (size_t)row * p.ln_ld + c0 : nullptr;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0) + i);
@@ -259,7 +261,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
               v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
             }
-            d[i] = v;
+            if (p.y != nullptr) d[i] = v;
+            if (sh != nullptr) {                                 // the same row as the next GEMM's pre-split A operand
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+              const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+              const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __uint_as_float(u0 << 16), v.y - __uint_as_float(u0 & 0xffff0000u));
+              const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __uint_as_float(u1 << 16), v.w - __uint_as_float(u1 & 0xffff0000u));
+              *reinterpret_cast<uint2*>(sh + 4 * i) = make_uint2(u0, u1);
+              *reinterpret_cast<uint2*>(sl + 4 * i) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            }
           }
         }
       }
@@ -311,9 +321,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t* sp = stg + rr * 33 + w0;
             const uint4 vh = make_uint4(sp[0], sp[1], sp[2], sp[3]), vl = make_uint4(sp[16], sp[17], sp[18], sp[19]);
             if (grow < p.M) {
+              if (p.out_split == 3) {                           // row (image, pixel) -> its slot in the window-ordered operand
+                const int img = grow / p.npix, pix = grow - img * p.npix;
+                const int2 m = __ldg(p.rowmap + pix);
+                int im2 = img + p.img_shift;
+                if (im2 >= p.n_img) im2 -= p.n_img;
+                __nv_bfloat16* d = p.split_dst[nt] + ((size_t)m.x + (size_t)im2 * m.y) * 256 + c0 + w0 * 2;
+                *reinterpret_cast<uint4*>(d) = vh;
+                *reinterpret_cast<uint4*>(d + 128) = vl;
+              } else {
               const size_t off = (size_t)grow * p.ldg + n0 + c0 + w0 * 2;
               *reinterpret_cast<uint4*>(p.g_hi + off) = vh;
               *reinterpret_cast<uint4*>(p.g_lo + off) = vl;
+              }
             }
           }
           __syncwarp();
@@ -653,16 +673,27 @@ int gemm_tc_split_rows(const float* x, int M, int K, void* hi, void* lo, cudaStr
   EMIP_CHECK_LAUNCH("gemm_tc_split_rows");
   return EMIP_OK;
 }
+// weight [K][N] fp32 (rows ldb apart) -> the B operand of gemm_nt_tc as GemmNT::b_pre takes it: bf16 [K][2 * kpad(N)] (hi | lo)
+int gemm_tc_split_b(const float* w, int ldb, int K, int N, void* dst, cudaStream_t st) {
+  const int Np = kpad(N);
+  split_rows_kernel<<<dim3((Np + 2047) / 2048, K, 1), 256, 0, st>>>(w, 0, ldb, nullptr, nullptr, nullptr, nullptr,
+                                                                 static_cast<__nv_bfloat16*>(dst), K, N, Np);
+  EMIP_CHECK_LAUNCH("gemm_tc_split_b");
+  return EMIP_OK;
+}
+size_t gemm_tc_split_b_bytes(int K, int N) { return emip_align_up((size_t)K * 2 * kpad(N) * 2, 1024); }
 size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N) { return emip_align_up((size_t)K * 2 * kpad(N) * 2, 1024) + 1024; }
 
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit) {
   if (a.B == 0 || a.M == 0 || a.K == 0) return EMIP_OK;
   if (!gemm_nt_tc_supported(a) || (a.c_hi != nullptr && nsplit > 1)) { emip_set_error("gemm_nt_tc: unsupported arguments"); return EMIP_ENOSYS; }
   const bool pre = a.a_hi_pre != nullptr;
+  if (a.b_pre == nullptr || !pre) {
   if (scratch == nullptr ||
       scratch_bytes < (pre ? gemm_nt_tc_scratch_bytes_presplit(a.K, a.N) : gemm_nt_tc_scratch_bytes(a.B, a.M, a.K, a.N))) {
     emip_set_error("gemm_nt_tc: scratch too small");
     return EMIP_ENOMEM;
+  }
   }
   const int Np = kpad(a.N);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
@@ -676,13 +707,18 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
     split_w_kernel<<<dim3(split_w_blocks(a.M, Np), 1, a.B), 256, 0, st>>>(a.a, a.a_stride_b, a.lda, 0, a_hi, a_lo, a.M, a.N, Np, a.a_act, a.a_aux);
     EMIP_CHECK_LAUNCH("gemm_nt_tc (A)");
   }
+  if (a.b_pre != nullptr) {
+    bt = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a.b_pre));
+  } else {
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.bm, a.b_stride_b, a.ldb, a.mean, a.rstd, a.gamma, a.beta, bt,
                                                                     a.K, a.N, Np);
   EMIP_CHECK_LAUNCH("gemm_nt_tc (B)");
+  }
   CUtensorMap ma_hi, ma_lo, mb;
   int rc;
+  const cuuint64_t ald = (pre && a.a_ld_pre > 0) ? (cuuint64_t)a.a_ld_pre : (cuuint64_t)Np;
   const cuuint64_t adims[3] = {(cuuint64_t)Np, (cuuint64_t)a.M, (cuuint64_t)a.B};
-  const cuuint64_t astr[2] = {(cuuint64_t)Np * 2, (cuuint64_t)a.M * Np * 2};
+  const cuuint64_t astr[2] = {ald * 2, (cuuint64_t)a.M * ald * 2};
   const cuuint32_t abox[3] = {KCH, TM, 1};
   if ((rc = gemm_tc_make_map(&ma_hi, a_hi, 3, adims, astr, abox))) return rc;
   if ((rc = gemm_tc_make_map(&ma_lo, a_lo, 3, adims, astr, abox))) return rc;
@@ -708,6 +744,22 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
     }
     p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
     p.res = a.c_res; p.res_stride_b = 0; p.ldr = a.ldc;
+  }
+  if (a.ln_hi != nullptr) {
+    if (a.ln_gamma == nullptr || a.ln_lo == nullptr || a.ln_ld % 4 != 0 || ((reinterpret_cast<uintptr_t>(a.ln_hi) | reinterpret_cast<uintptr_t>(a.ln_lo)) & 7) != 0) {
+      emip_set_error("gemm_nt_tc: ln_hi needs the LayerNorm epilogue and 8-byte aligned rows"); return EMIP_EINVAL;
+    }
+    p.ln_hi = static_cast<__nv_bfloat16*>(a.ln_hi); p.ln_lo = static_cast<__nv_bfloat16*>(a.ln_lo); p.ln_ld = a.ln_ld;
+  }
+  if (a.split_dst[0] != nullptr) {
+    if (a.B != 1 || ns != 1 || ntile != TM || a.K > 4 * TM || a.K % TM != 0 || a.rowmap == nullptr || a.npix <= 0 || a.n_img <= 0 ||
+        a.M != a.npix * a.n_img || a.ln_gamma != nullptr || a.c_hi != nullptr) {
+      emip_set_error("gemm_nt_tc: bad window-ordered split output"); return EMIP_EINVAL;
+    }
+    for (int i = 0; i < 4; ++i) p.split_dst[i] = static_cast<__nv_bfloat16*>(a.split_dst[i]);
+    p.rowmap = static_cast<const int2*>(a.rowmap); p.npix = a.npix; p.n_img = a.n_img; p.img_shift = a.img_shift;
+    p.out_split = 3; p.ldg = 256;
+    p.g_hi = p.split_dst[0]; p.g_lo = p.split_dst[0] + 128;
   }
   if (a.c_bias != nullptr) {
     if (a.ln_gamma != nullptr || a.c_hi != nullptr || ns != 1) { emip_set_error("gemm_nt_tc: c_bias needs the plain fp32 epilogue"); return EMIP_ENOSYS; }

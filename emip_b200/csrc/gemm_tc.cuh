@@ -41,6 +41,13 @@ struct GemmTcParams {
   // mode 2, ln_gamma != NULL (N == n_tile == 128, one output row per thread): y = res + LayerNorm_N(tile) * gamma + beta
   const float* ln_gamma; const float* ln_beta; float ln_eps;
   const float* bias_n;      // mode 2, plain fp32 epilogue: per-column bias [N] (NULL: none)
+  // mode 2, LayerNorm epilogue: the normalised row also as bf16 hi | lo (rows ln_ld elements apart) -- the pre-split A operand
+  // of the next GEMM; y may then be NULL (only the split is wanted)
+  __nv_bfloat16* ln_hi; __nv_bfloat16* ln_lo; int ln_ld;
+  // mode 2, out_split == 3 (n_tile == 128, batch 1): column tile nt goes to the bf16 buffer split_dst[nt] whose rows are
+  // [hi 128 | lo 128]; row r = (image, pixel) lands in row rowmap[pixel].x + ((image + img_shift) % n_img) * rowmap[pixel].y --
+  // the window-ordered q / k / v operands of the FeatureTransformer attention (ft.cu), no separate gather / split pass
+  __nv_bfloat16* split_dst[4]; const int2* rowmap; int npix, n_img, img_shift;
   int epi_stage;            // mode 2: per-warp shared-memory staging of the epilogue (set by gemm_tc_launch): coalesced row stores
 };
 
@@ -65,7 +72,10 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
 bool gemm_nt_tc_supported(const GemmNT& a);
 size_t gemm_nt_tc_scratch_bytes(int B, int M, int K, int N);
 int gemm_tc_split_rows(const float* x, int M, int K, void* hi, void* lo, cudaStream_t st);   // fp32 rows -> bf16 hi, lo [M][kpad(K)]
-size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N);    // GemmNT::a_hi_pre set: only the B operand is split
+size_t gemm_nt_tc_scratch_bytes_presplit(int K, int N);
+// weight [K][N] fp32 -> GemmNT::b_pre format (bf16 [K][2 * kpad(N)], hi | lo per row), gemm_tc_split_b_bytes(K, N) bytes
+int gemm_tc_split_b(const float* w, int ldb, int K, int N, void* dst, cudaStream_t st);
+size_t gemm_tc_split_b_bytes(int K, int N);    // GemmNT::a_hi_pre set: only the B operand is split
 // nsplit > 1: the contraction axis is dealt to nsplit CTAs per tile; c then holds B * nsplit partial matrices
 // (c_stride_b apart, partial (b, s) at index b * nsplit + s) for the caller's batch reduction
 int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_t st, int nsplit = 1);

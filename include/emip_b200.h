@@ -377,6 +377,25 @@ int emip_window_attention_fwd_tc_ex(const float* q, const float* k, const float*
                                     size_t ws_bytes, int B, int h, int w, int C, int num_splits, int with_shift, int flags,
                                     void* stream);
 
+/* The whole FeatureTransformer (transformer.py:433-482: n_blocks x (self-attention layer, cross-attention + FFN layer)) as ONE
+ * call on token rows, inference only (csrc/window_attn.cu, second half): x, out [B][h*w][128] with B = 2 x pairs (frame 1 |
+ * frame 2 on the batch axis, transformer.py:461); out may alias x; odd blocks use shifted windows (:425).
+ *   weights  n_blocks x 16 device pointers, per block in the reference's state_dict order: self_attn.{q_proj,k_proj,v_proj,merge}
+ *            .weight [128,128], self_attn.norm1.{weight,bias}, cross_attn_ffn.{q_proj,k_proj,v_proj,merge}.weight,
+ *            .norm1.{weight,bias}, .mlp.0.weight [1024,256], .mlp.2.weight [128,1024], .norm2.{weight,bias}
+ *   prep     emip_feature_transformer_prepare(weights) in a caller-owned buffer of emip_feature_transformer_weight_bytes()
+ *            bytes (bf16 hi | lo matrices; redo when a weight changes); the LayerNorm vectors are read in place
+ *   workspace >= emip_feature_transformer_workspace(B, h, w, 128) bytes, 1024-byte aligned.
+ * Every intermediate is written by its producer's epilogue in the form its consumer reads (window-ordered bf16 hi | lo
+ * q / k / v, pre-split merge / MLP operands, LayerNorm + residual inside the GEMM epilogues); the batch-swapped `concat1`
+ * (transformer.py:462, :473) and torch.cat([source, message]) (:175) are never materialised. */
+size_t emip_feature_transformer_weight_bytes(int n_blocks);
+int emip_feature_transformer_prepare(const float* const* weights, int n_blocks, void* prep, void* stream);
+size_t emip_feature_transformer_workspace(int B, int h, int w, int C);
+int emip_feature_transformer_fwd(const float* x, float* out, const float* const* weights, const void* prep, int n_blocks,
+                                 void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits, float eps,
+                                 void* stream);
+
 /* ---- the chained path between the backbones and the decoder (CoUpdater.forward, model.py:92-97) -------------------- */
 /* 3x3 convolution, stride 1, zero padding 1, on the tensor cores (csrc/conv_tm.cu): replaces GMFlow.upsampler[0] + ReLU
  * (gmflow.py:43-44 on cat(flow, feature), :62-64) and conv_corr[3] (model.py:62).

@@ -157,3 +157,33 @@ def test_chain_batch_consistency():
             one = m(gm[idx].contiguous(), seg[idx].contiguous())
             for a, b_ in zip(one, full):
                 assert _rel(a, b_[i:i + 1]) < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,h,w,k", [(1, 44, 44, 2), (2, 16, 24, 2), (1, 12, 18, 3)])
+def test_feature_transformer_fused_call_vs_oracle_and_per_layer_path(b, h, w, k):
+    """The one-call FeatureTransformer (window-ordered operands written by the projection GEMMs, pre-split merge / MLP
+    operands, no concat1 / cat) against the fp64 oracle and against the per-layer path built from the separately tested ops."""
+    from emip_b200 import chain as ch
+    P = cases.chain_params(seed=5)
+    m = ch._FeatureTransformer()
+    m.load_state_dict(O.sub_params(P, "GMFlow.transformer."))
+    m = m.cuda()
+    x = cases.randn(321, (2 * b, h * w, 128), 2.0)
+    c0 = x.double()
+    c1 = torch.cat(c0.chunk(2, 0)[::-1], 0)
+    P64 = {kk: v.double() for kk, v in P.items()}
+    for i in range(6):
+        ps, pc = (O.sub_params(P64, f"GMFlow.transformer.layers.{i}.{n}.") for n in ("self_attn", "cross_attn_ffn"))
+        c0 = O.transformer_layer(c0, c0, ps, True, k, i % 2 == 1, h, w)
+        c0 = O.transformer_layer(c0, c1, pc, False, k, i % 2 == 1, h, w)
+        c1 = torch.cat(c0.chunk(2, 0)[::-1], 0)
+    with torch.no_grad():
+        xg = x.cuda()
+        fused = ch.feature_transformer_tokens(xg, m, h, w, k)
+        per = xg
+        for blk in m.layers:
+            per = ch.transformer_block(blk, per, h, w, k)
+    e_f, e_p, e_fp = _rel(fused, c0), _rel(per, c0), _rel(fused, per)
+    print(f"feature transformer {b}x{h}x{w} k={k}: fused vs fp64 {e_f:.2e}, per-layer vs fp64 {e_p:.2e}, fused vs per-layer {e_fp:.2e}")
+    assert e_f < 3e-4 and e_p < 3e-4 and e_fp < 3e-4
