@@ -80,11 +80,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    long long w_empty = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     int nt, mt, b;
     decode(tile, nt, mt, b);
     for (int kc = 0; kc < p.kchunks; ++kc) {
-      mbar_wait(empty(stage), phase ^ 1);
+      w_empty += mbar_wait(empty(stage), phase ^ 1);
       if (leader) {
         const uint32_t sa = sbase + stage * p.stage_bytes;
         mbar_expect_tx(full(stage), 2 * A_BYTES + 2 * p.b_bytes);
@@ -128,19 +130,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     }
     __syncwarp();
+    if (p.prof != nullptr && lane == 0) { p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 1] = w_empty; }
   } else if (warp == 5) {
     // ===================== UMMA issuer =====================
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(p.n_tile);
     int stage = 0;
     uint32_t phase = 0, it = 0;
+    long long w_full = 0, w_acc = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
     const int acc = it & 1;
     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-    mbar_wait(acc_empty(acc), ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (two tiles ago)
+    w_acc += mbar_wait(acc_empty(acc), ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (two tiles ago)
     tc_fence_after();
     for (int kc = 0; kc < p.kchunks; ++kc) {
-      mbar_wait(full(stage), phase);
+      w_full += mbar_wait(full(stage), phase);
       tc_fence_after();
       if (leader) {
         const uint32_t sa = sbase + stage * p.stage_bytes;
@@ -171,6 +176,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     }
+    if (p.prof != nullptr && lane == 0) {
+      p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 3] = w_full; p.prof[blockIdx.x * 8 + 4] = w_acc;
+    }
   } else {
     // ===================== epilogue warps: thread <-> output row =====================
     // two groups of four warps (0-3 and 6-9), one per accumulator: group g drains the CTA's tiles g, g + 2, ... so two
@@ -182,12 +190,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint32_t* stg = reinterpret_cast<uint32_t*>(smem + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 15) & ~15)) +
                     (grp * 4 + qw) * (32 * 33);
     uint32_t it = grp;
+    long long w_accf = 0, n_tiles = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     int nt, mt, b;
     decode(tile, nt, mt, b);
     const int acc = it & 1;
     const int row = mt * TM + qw * 32 + lane;
-    mbar_wait(acc_full(acc), (it >> 1) & 1);
+    w_accf += mbar_wait(acc_full(acc), (it >> 1) & 1);
+    ++n_tiles;
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 256);
     if (p.mode == 0) {
@@ -221,15 +232,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (p.mode == 2 && p.ln_gamma != nullptr) {
       // the whole 128-wide output row lives in this thread's TMEM lane: LayerNorm over it (+ residual) before the store --
       // three passes over TMEM (mean, centred variance, write), no fp32 round trip of the pre-norm tensor through HBM
-      float* o = p.y + (size_t)row * p.ldy;
-      const float* rs = p.res ? p.res + (size_t)row * p.ldr : nullptr;
+      // residual rows of the staged third pass: all eight 16-byte loads of a chunk are issued together and one chunk ahead
+      // (r2k role profile: one dependent load per row segment made the epilogue 38.7 k cycles per tile -- eight HBM
+      // round trips per chunk in sequence -- and the whole GEMM epilogue-bound)
+      const int ecc = (lane & 7) * 4;
+      float4 qn[8];
+      auto load_res = [&](int c0) {
+#pragma unroll
+        for (int it2 = 0; it2 < 8; ++it2) {
+          const int grow = mt * TM + qw * 32 + it2 * 4 + (lane >> 3);
+          qn[it2] = (p.res != nullptr && grow < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)grow * p.ldr + c0 + ecc))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_res(0);
       float sum = 0.f;
       for (int c0 = 0; c0 < TM; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) s4[i & 3] += __uint_as_float(r[i]);
+        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       const float mean = sum * (1.f / 128.f);
       float sq = 0.f;
@@ -237,47 +262,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mean; sq = fmaf(d, d, sq); }
+        for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mean; s4[i & 3] = fmaf(d, d, s4[i & 3]); }
+        sq += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       const float rstd = rsqrtf(sq * (1.f / 128.f) + p.ln_eps);
+      // third pass: the normalised chunk goes through the warp-private staging tile so that the residual read, the fp32 store
+      // and the bf16 hi | lo stores are row segments of 128 / 64 bytes (r2: one 16-byte piece per row and instruction made
+      // merge + norm1 224 us instead of 108 at 64 pairs)
       for (int c0 = 0; c0 < TM; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
-        if (row < p.M) {
-          float4* d = reinterpret_cast<float4*>(o + c0);
-          __nv_bfloat16* sh = p.ln_hi ? p.ln_hi + (size_t)row * p.ln_ld + c0 : nullptr;
-          __nv_bfloat16* sl = p.ln_hi ? p.ln_lo + (size_t)row * p.ln_ld + c0 : nullptr;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0) + i);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0) + i);
-            float4 v = make_float4((__uint_as_float(r[4 * i]) - mean) * rstd * g.x + be.x,
-                                   (__uint_as_float(r[4 * i + 1]) - mean) * rstd * g.y + be.y,
-                                   (__uint_as_float(r[4 * i + 2]) - mean) * rstd * g.z + be.z,
-                                   (__uint_as_float(r[4 * i + 3]) - mean) * rstd * g.w + be.w);
-            if (rs) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(rs + c0) + i);
-              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-            }
-            if (p.y != nullptr) d[i] = v;
-            if (sh != nullptr) {                                 // the same row as the next GEMM's pre-split A operand
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __float_as_uint((__uint_as_float(r[i]) - mean) * rstd);
+        __syncwarp();
+        const int cc = ecc;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0 + cc));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0 + cc));
+        float4 qc[8];
+#pragma unroll
+        for (int it2 = 0; it2 < 8; ++it2) qc[it2] = qn[it2];
+        if (c0 + 32 < TM) load_res(c0 + 32);
+#pragma unroll
+        for (int it2 = 0; it2 < 8; ++it2) {
+          const int rr = it2 * 4 + (lane >> 3);
+          const int grow = mt * TM + qw * 32 + rr;
+          const uint32_t* sp = stg + rr * 33 + cc;
+          float4 v = make_float4(__uint_as_float(sp[0]) * g.x + be.x, __uint_as_float(sp[1]) * g.y + be.y,
+                                 __uint_as_float(sp[2]) * g.z + be.z, __uint_as_float(sp[3]) * g.w + be.w);
+          if (grow < p.M) {
+            v.x += qc[it2].x; v.y += qc[it2].y; v.z += qc[it2].z; v.w += qc[it2].w;
+            if (p.y != nullptr) *reinterpret_cast<float4*>(p.y + (size_t)grow * p.ldy + c0 + cc) = v;
+            if (p.ln_hi != nullptr) {                            // the same row as the next GEMM's pre-split A operand
               const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
               const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
               const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __uint_as_float(u0 << 16), v.y - __uint_as_float(u0 & 0xffff0000u));
               const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __uint_as_float(u1 << 16), v.w - __uint_as_float(u1 & 0xffff0000u));
-              *reinterpret_cast<uint2*>(sh + 4 * i) = make_uint2(u0, u1);
-              *reinterpret_cast<uint2*>(sl + 4 * i) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+              *reinterpret_cast<uint2*>(p.ln_hi + (size_t)grow * p.ln_ld + c0 + cc) = make_uint2(u0, u1);
+              *reinterpret_cast<uint2*>(p.ln_lo + (size_t)grow * p.ln_ld + c0 + cc) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
             }
           }
         }
+        __syncwarp();
       }
     } else if (p.mode == 2 && p.out_split != 0) {
       // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
       const int n0 = nt * p.n_tile;
       __nv_bfloat16* gh = p.g_hi + (size_t)row * p.ldg + n0;
       __nv_bfloat16* gl = p.g_lo + (size_t)row * p.ldg + n0;
+      // out_split == 3: the four rows this lane stores per chunk go to the same slots for every chunk: one map lookup per tile
+      __nv_bfloat16* wrow[4] = {nullptr, nullptr, nullptr, nullptr};
+      if (p.out_split == 3) {
+#pragma unroll
+        for (int it2 = 0; it2 < 4; ++it2) {
+          const int grow = mt * TM + qw * 32 + it2 * 8 + (lane >> 2);
+          if (grow < p.M) {
+            const int img = grow / p.npix, pix = grow - img * p.npix;
+            const int2 m = __ldg(p.rowmap + pix);
+            int im2 = img + p.img_shift;
+            if (im2 >= p.n_img) im2 -= p.n_img;
+            __nv_bfloat16* dbase = nt == 0 ? p.split_dst[0] : nt == 1 ? p.split_dst[1] : nt == 2 ? p.split_dst[2] : p.split_dst[3];
+            wrow[it2] = dbase + ((size_t)m.x + (size_t)im2 * m.y) * 256 + (lane & 3) * 8;
+          }
+        }
+      }
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
@@ -322,11 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint4 vh = make_uint4(sp[0], sp[1], sp[2], sp[3]), vl = make_uint4(sp[16], sp[17], sp[18], sp[19]);
             if (grow < p.M) {
               if (p.out_split == 3) {                           // row (image, pixel) -> its slot in the window-ordered operand
-                const int img = grow / p.npix, pix = grow - img * p.npix;
-                const int2 m = __ldg(p.rowmap + pix);
-                int im2 = img + p.img_shift;
-                if (im2 >= p.n_img) im2 -= p.n_img;
-                __nv_bfloat16* d = p.split_dst[nt] + ((size_t)m.x + (size_t)im2 * m.y) * 256 + c0 + w0 * 2;
+                __nv_bfloat16* d = wrow[it2] + c0;
                 *reinterpret_cast<uint4*>(d) = vh;
                 *reinterpret_cast<uint4*>(d + 128) = vl;
               } else {
@@ -442,6 +489,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     tc_fence_before();
     mbar_arrive(acc_empty(acc));                          // every TMEM read of this tile has completed
+    }
+    if (p.prof != nullptr && warp == 0 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 5] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 6] = w_accf; p.prof[blockIdx.x * 8 + 7] = n_tiles;
     }
   }
   tc_fence_before();
@@ -562,6 +612,10 @@ unsigned split_w_blocks(int M, int Kp) { return (unsigned)(((long long)M * (Kp >
 
 }  // namespace
 
+static unsigned long long* g_gemm_prof = nullptr;
+// Diagnostics (tools/gemm_roles.py): device buffer of (SM count) x 8 cycle counters filled by the next launches; NULL = off.
+extern "C" void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf) { g_gemm_prof = dev_buf; }
+
 int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                      const cuuint32_t* box) {
   return make_map_bf16_impl(m, base, rank, dims, strides_bytes, box);
@@ -577,8 +631,9 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
     p.epi_stage = p.mode == 2 ? 1 : 0;
     p.stages = (max_smem - 2048 - (p.epi_stage ? EPI_STAGE_BYTES : 0)) / p.stage_bytes;
     if (p.stages > 3) p.stages = 3;
-    if (p.stages > p.kchunks) p.stages = p.kchunks;
+    // (the ring runs on across tiles: with K = 128 a third stage prefetches the next tile's first chunk)
   }
+  p.prof = g_gemm_prof;
   const long long tiles = (long long)batch * p.n_mtiles * p.n_ntiles;
   EMIP_CHECK_ARG(tiles > 0 && tiles < 0x7fffffffLL, "gemm_tc: bad tile count");
   p.total_tiles = (int)tiles;

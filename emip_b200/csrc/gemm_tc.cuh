@@ -48,6 +48,7 @@ struct GemmTcParams {
   // [hi 128 | lo 128]; row r = (image, pixel) lands in row rowmap[pixel].x + ((image + img_shift) % n_img) * rowmap[pixel].y --
   // the window-ordered q / k / v operands of the FeatureTransformer attention (ft.cu), no separate gather / split pass
   __nv_bfloat16* split_dst[4]; const int2* rowmap; int npix, n_img, img_shift;
+  unsigned long long* prof; // diagnostics (tools/gemm_roles.py): [grid][8] cycles: producer total, wait empty | issuer total, wait full, wait acc_empty | epilogue warp 0 total, wait acc_full, tiles
   int epi_stage;            // mode 2: per-warp shared-memory staging of the epilogue (set by gemm_tc_launch): coalesced row stores
 };
 

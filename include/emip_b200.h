@@ -31,7 +31,8 @@
  *          tensor maps (keyed by pointer / shape / strides; never shared);
  *      (4) diagnostic switches for the profiling scripts under tools/ --
  *          emip_match_tc_set_profile_buffer, emip_match_tc_set_variant,
- *          emip_attn_tc_set_profile_buffer, emip_debug_flow_warp_staged_profile --
+ *          emip_attn_tc_set_profile_buffer, emip_gemm_tc_set_profile_buffer,
+ *          emip_debug_flow_warp_staged_profile --
  *          NOT thread-safe, never touched by the host package, default off.
  *    No entry point allocates or frees memory (cudaMalloc / cudaHostAlloc), so all
  *    of them may be captured into CUDA graphs once (1) is warm (first call).
@@ -81,6 +82,8 @@ int emip_device_check(void);
 void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf);
 /* Diagnostics: force 8 or 16 softmax warps per CTA in the same kernel (0 = default choice). */
 void emip_match_tc_set_variant(int softmax_warps);
+/* Diagnostics: role wait-cycle profile of gemm_tc_kernel, device pointer to [SM count][8] uint64 or NULL (tools/gemm_roles.py). */
+void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf);
 /* Diagnostics: wait-cycle profile of the staged flow_warp kernel, device pointer to [grid][8] int64 or NULL. */
 void emip_debug_flow_warp_staged_profile(long long* buf);
 
