@@ -50,6 +50,7 @@ class _TransformerLayer(nn.Module):             # transformer.py:108-149 (parame
     def __init__(self, d_model=128, no_ffn=False, with_shift=False, ffn_dim_expansion=4):
         super().__init__()
         self.no_ffn, self.with_shift = no_ffn, with_shift
+        self.attention_type, self.nhead = "swin", 1
         self.q_proj = nn.Linear(d_model, d_model, bias=False)
         self.k_proj = nn.Linear(d_model, d_model, bias=False)
         self.v_proj = nn.Linear(d_model, d_model, bias=False)
@@ -147,6 +148,19 @@ def tokens_from_cn(x, pos=None):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().emip_tokens_from_cn(ptr(x), ptr(pos), ptr(out), I(B), I(C), I(N), stream_ptr()), "emip_tokens_from_cn")
     return out
+
+
+class _TokensFromCN(torch.autograd.Function):
+    """tokens_from_cn with autograd: the backward is the same transposing kernel with the roles of the axes swapped."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        ctx.shape = x.shape
+        return tokens_from_cn(x, pos)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return tokens_from_cn(dy.contiguous()).reshape(ctx.shape), None
 
 
 def linear_tm_bias(x, weight, bias):
@@ -385,6 +399,49 @@ class MotionChain(nn.Module):
         srcs = [bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([cc[0].bias] if cc[0].bias is not None else [])
         scale, shift = c.get("bn", srcs, fold)
         return w_up, w_c3, scale, shift
+
+    def freeze_like_reference(self):
+        """train.py:340-342: everything under ``GMFlow`` is frozen, the prompt fusion and conv_corr train."""
+        for n, p in self.named_parameters():
+            p.requires_grad_(not n.startswith("GMFlow"))
+        return self
+
+    def forward_train(self, gm, seg):
+        """Training-mode pass with autograd through the per-op drop-ins (every op's backward is one of our kernels; the rest of
+        conv_corr -- BatchNorm on batch statistics, ReLU, conv_corr[3] -- and the upsampler convolutions stay library modules,
+        as in the reference).  Returns ``(flow_fw, flow_bw, corr, fea_new)`` with two-entry flow lists: index 0 = bilinear x8 of
+        the matching flow, 1 = convex-upsampled propagated flow (gmflow.py:130-132, :147-155; consumed by train.py:53-57)."""
+        from .matching import global_correlation_softmax
+        from .conv_corr import conv_corr_first_layer
+        from .transformer_layer import transformer_layer_forward
+        import torch.nn.functional as F
+        _need_cuda(gm, "MotionChain")
+        B2, C, H, W = gm.shape
+        B = B2 // 2
+        gmf = self.GMFlow
+        with torch.cuda.device(gm.device):
+            ab = self.injector(gm, seg)                                                          # model.py:92-93
+            x = _TokensFromCN.apply(ab, window_position(H, W, self.attn_splits, C, gm.device))   # gmflow.py:114, transformer.py:439-462
+            x1 = torch.cat(x.chunk(2, 0)[::-1], 0)
+            dummy = x.new_zeros(1)
+            for blk in gmf.transformer.layers:                                                   # transformer.py:464-473
+                x = transformer_layer_forward(blk.self_attn, x, x, height=H, width=W, shifted_window_attn_mask=dummy,
+                                              attn_num_splits=self.attn_splits)
+                x = transformer_layer_forward(blk.cross_attn_ffn, x, x1, height=H, width=W, shifted_window_attn_mask=dummy,
+                                              attn_num_splits=self.attn_splits)
+                x1 = torch.cat(x.chunk(2, 0)[::-1], 0)
+            feat = _TokensFromCN.apply(x, None).view(B2, C, H, W)                                # transformer.py:479-480 ([B,N,C] -> [B,C,H,W])
+            f0, f1 = feat[:B], feat[B:]
+            cc = self.conv_corr
+            flow_pred, _, _ = global_correlation_softmax(f0, f1, True, return_corr=False)        # gmflow.py:121
+            flow_bil = F.interpolate(flow_pred, scale_factor=8, mode="bilinear", align_corners=True) * 8   # gmflow.py:58-60, :131
+            flow = gmf.feature_flow_attn(feat, flow_pred.detach())                               # gmflow.py:137
+            mask = gmf.upsampler(torch.cat((flow, feat), dim=1))                                 # gmflow.py:62-64
+            flow_up = upsample_flow_convex(flow, mask, 8)                                        # gmflow.py:66-77
+            c1 = conv_corr_first_layer(f0, f1, cc[0].weight, cc[0].bias)                         # model.py:59, :96 (cost volume never formed)
+            corr = cc[3](cc[2](cc[1](c1)))                                                       # model.py:60-62
+            fea_new = self.injector1(seg[:B], corr)                                              # model.py:97
+        return [flow_bil[:B], flow_up[:B]], [flow_bil[B:], flow_up[B:]], corr, fea_new
 
     def forward(self, gm, seg, want=()):
         if torch.is_grad_enabled() and (gm.requires_grad or seg.requires_grad or any(p.requires_grad for p in self.injector.parameters())):

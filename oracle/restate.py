@@ -474,3 +474,67 @@ def motion_chain(gm, seg, P, attn_splits=2, want=()):
     for k in want:
         out[k] = loc[k]
     return out
+
+
+# --------------------------------------------------------------------------- training side of the chain (config c5)
+def unflow_loss(pyramid_flows, image_pair, w_scales=(1.0, 1.0, 1.0, 1.0, 0.0), th=0.2):
+    """Photometric part of the unsupervised flow loss as the reference trains it (the smoothness term is computed and then
+    discarded there, loss_flow.py:134-136): per pyramid entry i, warp frame 2 by the forward flow and frame 1 by the
+    backward flow, occlusion masks from entry 0's flows, L1 + SSIM photometric term of both directions averaged.
+
+    pyramid_flows: list of [B,4,H,W] (channels 0:2 forward, 2:4 backward); image_pair [B,6,H0,W0].  Returns the total loss.
+    Reference: loss/loss_flow.py:60-138 (unFlowLoss.compute_loss) with the cfg of :19-31.
+    """
+    F = torch.nn.functional
+    im1o, im2o = image_pair[:, :3], image_pair[:, 3:]
+    total = 0.0
+    occ1_0 = occ2_0 = None
+    for i, flow in enumerate(pyramid_flows):
+        if w_scales[i] == 0:
+            continue
+        h, w = flow.shape[2:]
+        im1 = F.interpolate(im1o, (h, w), mode="area")                 # :84-85
+        im2 = F.interpolate(im2o, (h, w), mode="area")
+        rec1 = flow_warp(im2, flow[:, :2])                             # :90
+        rec2 = flow_warp(im1, flow[:, 2:])                             # :91
+        if i == 0:
+            occ1 = 1 - occu_mask_backward(flow[:, 2:].detach(), th)    # :95-96
+            occ2 = 1 - occu_mask_backward(flow[:, :2].detach(), th)
+            occ1_0, occ2_0 = occ1, occ2
+        else:
+            occ1 = F.interpolate(occ1_0, (h, w), mode="nearest")       # :101-104
+            occ2 = F.interpolate(occ2_0, (h, w), mode="nearest")
+        lw = (photometric_loss(im1, rec1, occ1) + photometric_loss(im2, rec2, occ2)) / 2.0    # :109, :117-121
+        total = total + lw * w_scales[i]                               # :126-127, :131
+    return total
+
+
+def motion_chain_train(gm, seg, P, attn_splits=2, bn_eps=1e-5):
+    """The chained path in TRAINING mode: GMFlow also returns the bilinear x8 upsampling of the matching flow (gmflow.py:130-132)
+    and conv_corr's BatchNorm normalises with the batch statistics (model.py:60).  Returns (flow_fw list, flow_bw list, corr,
+    fea_new) with list index 0 = bilinear(matching flow), 1 = convex-upsampled propagated flow, as train.py:53-57 consumes them.
+    Reference: model/EMIP_short/model.py:92-97, .../gmflow/gmflow.py:81-162 with self.training."""
+    F = torch.nn.functional
+    B = gm.shape[0] // 2
+    C = gm.shape[1]
+    ab = injector(gm, seg, sub_params(P, "injector.transformer."))
+    f0, f1 = feature_add_position(ab[:B], ab[B:], attn_splits, C)
+    layers = [{"self_attn": sub_params(P, f"GMFlow.transformer.layers.{i}.self_attn."),
+               "cross_attn_ffn": sub_params(P, f"GMFlow.transformer.layers.{i}.cross_attn_ffn.")} for i in range(6)]
+    f0, f1 = feature_transformer(f0, f1, layers, attn_splits)
+    flow_pred, _, corr = global_correlation_softmax(f0, f1, True)
+    flow_bil = F.interpolate(flow_pred, scale_factor=8, mode="bilinear", align_corners=True) * 8      # gmflow.py:58-60, :131
+    feat = torch.cat((f0, f1), dim=0)
+    ffa = sub_params(P, "GMFlow.feature_flow_attn.")
+    flow = feature_flow_attention(feat, flow_pred.detach(), ffa["q_proj.weight"], ffa["q_proj.bias"], ffa["k_proj.weight"],
+                                  ffa["k_proj.bias"])                                                  # gmflow.py:137
+    mask = upsampler_mask(flow, feat, sub_params(P, "GMFlow.upsampler."))
+    flow_up = upsample_flow_convex(flow, mask)
+    cc = sub_params(P, "conv_corr.")
+    y = F.conv2d(corr, cc["0.weight"], cc["0.bias"], padding=1)
+    mu = y.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((y - mu) ** 2).mean(dim=(0, 2, 3), keepdim=True)                                            # biased, as BatchNorm normalises
+    y = (y - mu) / torch.sqrt(var + bn_eps) * cc["1.weight"].view(1, -1, 1, 1) + cc["1.bias"].view(1, -1, 1, 1)
+    corr_out = F.conv2d(F.relu(y), cc["3.weight"], cc["3.bias"], padding=1)
+    fea_new = injector(seg[:B], corr_out, sub_params(P, "injector1.transformer."))
+    return [flow_bil[:B], flow_up[:B]], [flow_bil[B:], flow_up[B:]], corr_out, fea_new

@@ -325,7 +325,49 @@ def gen_chain():
           "corr std", cap["corr"].std().item(), "fea_new std", cap["fea_new"].std().item(), "mask std", mask.std().item())
 
 
+def gen_loss():
+    """unFlowLoss.compute_loss (loss_flow.py:60-138) on seeded smooth flows: total loss and its gradients w.r.t. both flow entries."""
+    from loss.loss_flow import unFlowLoss
+    crit = unFlowLoss()
+    for name, s in cases.LOSS_CASES.items():
+        d = cases.loss_inputs(s)
+        flows = [f.clone().requires_grad_(True) for f in d["flows"]]
+        total, warp, smooth, mean_abs = crit.compute_loss(flows, d["images"])
+        total.backward()
+        save(name, dict(spec=s, loss=float(total), dflows=[cases.pack(f.grad, False) for f in flows]))
+
+
+def gen_trainchain():
+    """One training-mode pass of the chained path inside the unmodified reference modules (GMFlow.train(): two flow
+    predictions; conv_corr's BatchNorm on batch statistics) + unFlowLoss + a fixed cotangent on the motion collector's output
+    (standing in for decoder + hybrid_e_loss, out of scope), backward: loss and gradients of the trainable path parameters."""
+    from loss.loss_flow import unFlowLoss
+    net, P = _chain_model()
+    s = cases.TRAIN_CHAIN_CASE
+    d = cases.train_chain_inputs(s)
+    B = s["b"]
+    net.train()
+    for n, p in net.named_parameters():
+        p.requires_grad_(not ("GMFlow" in n))                         # train.py:340-342 (the unused dwconv / adaptor params aside)
+    gm, seg = d["gm"].clone().requires_grad_(True), d["seg"].clone().requires_grad_(True)
+    a = net.injector(gm[:B], seg[:B])
+    b = net.injector(gm[B:], seg[B:])
+    flow_fw, flow_bw, corr = net.GMFlow([a], [b])
+    corr = net.conv_corr(corr)
+    fea_new = net.injector1(seg[:B], corr)
+    pairs = [torch.cat((flow_fw[i], flow_bw[i]), 1) for i in range(len(flow_fw))]                # train.py:55-57
+    lflow = unFlowLoss().compute_loss(pairs, d["images"])[0]
+    loss = lflow + (fea_new * d["wseg"]).sum()
+    loss.backward()
+    grads = dict(net.named_parameters())
+    save("trainchain", dict(spec=s, loss_flow=float(lflow), loss=float(loss), n_flows=len(flow_fw),
+                            flow_fw=[cases.pack(f, True) for f in flow_fw], fea_new=cases.pack(fea_new, True),
+                            dgm=cases.pack(gm.grad, True), dseg=cases.pack(seg.grad, True),
+                            dparams={k: cases.pack(grads[k].grad, True) for k in cases.TRAIN_GRAD_KEYS}))
+    print("trainchain: loss_flow", float(lflow), "loss", float(loss))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f2b", "f3", "f3b", "f4", "c1", "chain"]
+    which = sys.argv[1:] or ["a1", "a2", "a3", "a4", "a5", "f1", "f2", "f2b", "f3", "f3b", "f4", "c1", "chain", "loss", "trainchain"]
     for w in which:
         globals()["gen_" + w]()

@@ -187,3 +187,35 @@ def test_feature_transformer_fused_call_vs_oracle_and_per_layer_path(b, h, w, k)
     e_f, e_p, e_fp = _rel(fused, c0), _rel(per, c0), _rel(fused, per)
     print(f"feature transformer {b}x{h}x{w} k={k}: fused vs fp64 {e_f:.2e}, per-layer vs fp64 {e_p:.2e}, fused vs per-layer {e_fp:.2e}")
     assert e_f < 3e-4 and e_p < 3e-4 and e_fp < 3e-4
+
+
+@pytest.mark.gpu
+def test_train_chain_vs_reference(golden):
+    """Config c5's training step on the chained path: forward in training mode (two flow predictions, BatchNorm on batch
+    statistics), unFlowLoss on our kernels, backward through every op's own backward kernel -- against the same pass through the
+    unmodified reference modules (tests/golden/trainchain.pt).  Gradients that pass through the matching path are compared at
+    the fp32 noise floor of that path (see cases.TRAIN_CHAIN_CASE), the others at 5e-3."""
+    from emip_b200.flow_loss import unflow_loss
+    g = golden("trainchain")
+    s = cases.TRAIN_CHAIN_CASE
+    d = cases.train_chain_inputs(s)
+    m = _chain(cases.chain_params(s["pseed"])).cuda().train().freeze_like_reference()
+    gm, seg = d["gm"].cuda().requires_grad_(True), d["seg"].cuda().requires_grad_(True)
+    ffw, fbw, corr, fea_new = m.forward_train(gm, seg)
+    assert len(ffw) == len(fbw) == g["n_flows"] == 2
+    errs = {f"flow_fw[{i}]": cases.check_packed(ffw[i], g["flow_fw"][i], 2e-3, f"flow_fw[{i}]") for i in range(2)}
+    errs["fea_new"] = cases.check_packed(fea_new, g["fea_new"], 1e-3, "fea_new")
+    lflow = unflow_loss([torch.cat((ffw[i], fbw[i]), 1) for i in range(2)], d["images"].cuda())[0]
+    loss = lflow + (fea_new * d["wseg"].cuda()).sum()
+    assert abs(float(lflow) - g["loss_flow"]) <= 2e-3 * abs(g["loss_flow"]), (float(lflow), g["loss_flow"])
+    loss.backward()
+    errs["dgm"] = cases.check_packed(gm.grad, g["dgm"], 0.2, "dgm")
+    errs["dseg"] = cases.check_packed(seg.grad, g["dseg"], 0.1, "dseg")
+    grads = dict(m.named_parameters())
+    for k in cases.TRAIN_GRAD_KEYS:
+        if k == "conv_corr.0.bias":
+            assert grads[k].grad.abs().max() < 1e-2
+            continue
+        errs[k] = cases.check_packed(grads[k].grad, g["dparams"][k], 0.2 if k.startswith(cases.TRAIN_NOISY) else 5e-3, k)
+    assert all(p.grad is None for n, p in m.named_parameters() if n.startswith("GMFlow"))
+    print("train chain rel-L2 vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from emip_b200.dist import FlatGradAllReduce, shard_batch
+from emip_b200.dist import BucketedGradAllReduce, FlatGradAllReduce, shard_batch
 
 
 def _free_port():
@@ -128,3 +128,59 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     env = dict(os.environ, WORLD_SIZE="2", RANK="1", LOCAL_RANK="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _worker_bucketed(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = [torch.nn.Linear(6, 6) for _ in range(4)]
+        unused = torch.nn.Parameter(torch.randn(3))                      # never touched by the loss on any rank
+        params = [p for m in lin for p in m.parameters()] + [unused]
+        red = BucketedGradAllReduce(params, bucket_mb=1e-4)              # tiny buckets: several collectives per step
+        data = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+        lo, hi = shard_batch(8, world, rank)
+        for step in range(2):                                            # the second step checks zero_grad / re-arming
+            red.zero_grad()
+            x = data[lo:hi]
+            for m in lin:
+                x = torch.tanh(m(x))
+            x.sum().backward()
+            red.finish()
+        out[rank] = [p.grad.clone() for p in params[:-1]] + [params[-1].grad.clone()]
+        # single-process expectation on this rank: every shard in turn, averaged over the ranks
+        ref = [torch.zeros_like(p) for p in params]
+        for r in range(world):
+            a, b = shard_batch(8, world, r)
+            for p in params:
+                p.grad = None
+            x = data[a:b]
+            for m in lin:
+                x = torch.tanh(m(x))
+            x.sum().backward()
+            for acc, p in zip(ref, params):
+                if p.grad is not None:
+                    acc += p.grad / world
+        out[f"ref{rank}"] = ref
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_grad_allreduce_world2_gloo():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_bucketed, args=(world, port, out), nprocs=world, join=True)
+        g0, g1, ref = out[0], out[1], out["ref0"]
+    for a, b, r in zip(g0, g1, ref):
+        assert torch.equal(a, b)
+        assert torch.allclose(a, r, atol=1e-6)
+    assert float(g0[-1].abs().max()) == 0.0                              # the unused parameter's bucket view stays zero
+
+
+def test_flat_grad_allreduce_keeps_globally_unused_grads_none():
+    p_used, p_unused = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(2))
+    (p_used * 2).sum().backward()
+    FlatGradAllReduce([p_used, p_unused])()
+    assert p_unused.grad is None and torch.equal(p_used.grad, torch.full((3,), 2.0))

@@ -249,3 +249,41 @@ def test_chain_insitu_c1(golden):
     g = golden("chain_insitu")
     out = O.motion_chain(g["gm"], g["seg"], cases.chain_params(), want=("ab", "feat", "flow_pred", "flow_prop", "mask", "corr1"))
     _check_chain(out, g)
+
+
+# ---- training side (config c5): unFlowLoss.compute_loss and the training-mode chain against the unmodified reference
+@pytest.mark.parametrize("name", list(cases.LOSS_CASES))
+def test_unflow_loss(golden, name):
+    g = golden(name)
+    d = cases.loss_inputs(cases.LOSS_CASES[name])
+    flows = [f.clone().requires_grad_(True) for f in d["flows"]]
+    loss = O.unflow_loss(flows, d["images"])
+    assert abs(float(loss) - g["loss"]) <= 1e-5 * abs(g["loss"])
+    loss.backward()
+    for f, gd in zip(flows, g["dflows"]):
+        cases.check_packed(f.grad, gd, 1e-4, "dflow")
+
+
+def test_train_chain(golden):
+    g = golden("trainchain")
+    s = cases.TRAIN_CHAIN_CASE
+    d = cases.train_chain_inputs(s)
+    P = {k: v.clone().requires_grad_(not k.startswith("GMFlow") and "running" not in k) for k, v in cases.chain_params(s["pseed"]).items()}
+    gm, seg = d["gm"].clone().requires_grad_(True), d["seg"].clone().requires_grad_(True)
+    ffw, fbw, corr, fea_new = O.motion_chain_train(gm, seg, P)
+    assert len(ffw) == g["n_flows"] == 2
+    for f, gf in zip(ffw, g["flow_fw"]):
+        cases.check_packed(f, gf, 2e-4, "flow_fw")
+    cases.check_packed(fea_new, g["fea_new"], 2e-4, "fea_new")
+    lflow = O.unflow_loss([torch.cat((ffw[i], fbw[i]), 1) for i in range(2)], d["images"])
+    loss = lflow + (fea_new * d["wseg"]).sum()
+    assert abs(float(lflow) - g["loss_flow"]) <= 2e-4 * abs(g["loss_flow"])
+    loss.backward()
+    # the feeder-side gradients carry the fp32 noise of the matching path (cases.TRAIN_CHAIN_CASE): 2 % at this scale
+    cases.check_packed(gm.grad, g["dgm"], 8e-2, "dgm")
+    cases.check_packed(seg.grad, g["dseg"], 2e-2, "dseg")
+    for k in cases.TRAIN_GRAD_KEYS:
+        if k == "conv_corr.0.bias":                      # analytically zero: a BatchNorm on batch statistics follows
+            assert P[k].grad.abs().max() < 1e-3
+            continue
+        cases.check_packed(P[k].grad, g["dparams"][k], 8e-2 if k.startswith(cases.TRAIN_NOISY) else 5e-3, k)
