@@ -18,6 +18,8 @@ struct GemmNN {
   int B, M, K, N;
   int accumulate;                                                                  // y += instead of y =
   const float* bias;                                                               // NULL or [M]: added per output row (tensor-core path only)
+  int x_presplit;                                                                  // tensor-core path: the caller already wrote the bf16 hi | lo
+                                                                                   // activation operand at gemm_nn_tc_act_operand(scratch, ...)
 };
 int gemm_nn(const GemmNN& a, cudaStream_t st);
 

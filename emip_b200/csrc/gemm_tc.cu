@@ -392,14 +392,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
       const float rb = (p.bias != nullptr && row < p.M) ? __ldg(p.bias + row) : 0.f;      // per-row bias (linear layers)
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32_async(taddr + c0, r);
-        tmem_wait(r);
         const int n = min(32, p.N - n0 - c0);
         const float* yb = p.y + (size_t)b * p.y_stride_b + n0 + c0;
         const float* rb0 = p.res ? p.res + (size_t)b * p.res_stride_b + n0 + c0 : nullptr;
-        if (p.epi_stage && n == 32 && (p.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yb) & 15) == 0 &&
-            (!rb0 || ((p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(rb0) & 15) == 0))) {       // warp-uniform
+        const bool staged = p.epi_stage && n == 32 && (p.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yb) & 15) == 0 &&
+                            (!rb0 || ((p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(rb0) & 15) == 0));      // warp-uniform
+        // the residual row segments of this chunk: eight independent loads in flight while the accumulator chunk is read from
+        // TMEM and staged (one dependent load per store made the residual GEMMs of the prompt fusion 3x slower than the plain ones)
+        float4 q8[8];
+        if (staged && rb0 != nullptr) {
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const int grow = mt * TM + qw * 32 + it2 * 4 + (lane >> 3);
+            q8[it2] = grow < p.M ? __ldg(reinterpret_cast<const float4*>(rb0 + (size_t)grow * p.ldr + (lane & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        if (staged) {
           if (p.bias_n != nullptr) {                         // per-column bias (nn.Linear on token rows), warp-uniform branch
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias_n + n0 + c0 + i));
@@ -414,10 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t* sp = stg + rr * 33 + cc;
             float4 v = make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
             if (grow < p.M) {
-              if (rb0) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(rb0 + (size_t)grow * p.ldr + cc));
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-              }
+              if (rb0) { v.x += q8[it2].x; v.y += q8[it2].y; v.z += q8[it2].z; v.w += q8[it2].w; }
               *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)grow * p.ldy + cc) = v;
             }
           }
@@ -654,6 +662,13 @@ size_t gemm_nn_tc_scratch_bytes(int B, int M, int K, int N, bool per_sample_w) {
   return emip_align_up((size_t)(per_sample_w ? B : 1) * M * Kp * 2 * 2, 1024) + emip_align_up((size_t)B * K * 2 * Np * 2, 1024) + 1024;
 }
 
+void* gemm_nn_tc_act_operand(void* scratch, int B, int M, int K, int N, bool per_sample_w, int* np_out) {
+  const int Kp = kpad(K), nbw = per_sample_w ? B : 1;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+  if (np_out) *np_out = kpad(N);
+  return base + emip_align_up((size_t)nbw * M * Kp * 2 * 2, 1024);
+}
+
 int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   if (a.B == 0 || a.M == 0 || a.N == 0) return EMIP_OK;
   if (!gemm_nn_tc_supported(a)) { emip_set_error("gemm_nn_tc: unsupported arguments"); return EMIP_ENOSYS; }
@@ -673,9 +688,11 @@ int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_
   // applied on the way), read by the GEMM as an MN-major operand.  (r1 / r2a re-laid them out token-major with
   // a transposing kernel: 64-byte store segments, 200 us of the Injector's forward + backward.)
   const int Np = kpad(a.N);
+  if (!a.x_presplit) {
   split_rows_kernel<<<dim3((Np + 2047) / 2048, a.K, a.B), 256, 0, st>>>(a.x, a.x_stride_b, a.ldx, a.mean, a.rstd, a.gamma, a.beta, bt,
                                                                     a.K, a.N, Np);
   EMIP_CHECK_LAUNCH("gemm_nn_tc (activations)");
+  }
   CUtensorMap ma_hi, ma_lo, mb;
   int rc;
   const cuuint64_t adims[3] = {(cuuint64_t)Kp, (cuuint64_t)a.M, (cuuint64_t)nbw};

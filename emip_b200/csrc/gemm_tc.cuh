@@ -68,6 +68,9 @@ bool gemm_nn_tc_supported(const GemmNN& a);
 // scratch for the bf16 hi|lo operands: weights [nbw][M][Kp] x 2 and token-major activations [B][N][2*Kp]
 size_t gemm_nn_tc_scratch_bytes(int B, int M, int K, int N, bool per_sample_w);
 int gemm_nn_tc(const GemmNN& a, void* scratch, size_t scratch_bytes, cudaStream_t st);
+// where gemm_nn_tc expects the activation operand inside its scratch: bf16 [B][K][2 * Np] (hi | lo per row, zero padded to
+// Np = *np_out); a producer may write it there itself and set GemmNN::x_presplit
+void* gemm_nn_tc_act_operand(void* scratch, int B, int M, int K, int N, bool per_sample_w, int* np_out);
 
 // c[b][m][k] = sum_n A(b)[m][n] * B'(b)[k][n] -- the arguments of gemm_nt (one result per batch entry, no N split).
 bool gemm_nt_tc_supported(const GemmNT& a);

@@ -746,8 +746,11 @@ dwconv_bwd_v4_kernel(const float* __restrict__ in, const float* __restrict__ w, 
   if (threadIdx.x < 9) dw_part[((size_t)b * C + c) * 9 + threadIdx.x] = t;
 }
 
+// gs != NULL: the gate is written as the bf16 hi | lo B operand of the project_out GEMM ([B][HID][2 * Np], zero padded to Np)
+// instead of fp32 g -- no fp32 round trip, no split pass (inference / tensor-core path)
 __global__ void __launch_bounds__(256)
-gdfn_gate_fwd_v4_kernel(const float* __restrict__ tpre, const float* __restrict__ w, float* __restrict__ g, int H, int W) {
+gdfn_gate_fwd_v4_kernel(const float* __restrict__ tpre, const float* __restrict__ w, float* __restrict__ g,
+                        __nv_bfloat16* __restrict__ gs, int Np, int H, int W) {
   extern __shared__ __align__(16) float sm[];
   const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, P = (H + 2) * PW, W4 = W >> 2;
   load_plane4(sm, tpre + ((size_t)b * HID2 + c) * N, H, W);
@@ -764,7 +767,22 @@ gdfn_gate_fwd_v4_kernel(const float* __restrict__ tpre, const float* __restrict_
     conv9x4(v, k1, t1);
     window4(sm + P, PW, y, x0, v);
     conv9x4(v, k2, t2);
-    o[i] = make_float4(gelu_erf(t1[0]) * t2[0], gelu_erf(t1[1]) * t2[1], gelu_erf(t1[2]) * t2[2], gelu_erf(t1[3]) * t2[3]);
+    const float4 r = make_float4(gelu_erf(t1[0]) * t2[0], gelu_erf(t1[1]) * t2[1], gelu_erf(t1[2]) * t2[2], gelu_erf(t1[3]) * t2[3]);
+    if (gs == nullptr) {
+      o[i] = r;
+    } else {
+      __nv_bfloat16* d = gs + ((size_t)b * HID + c) * 2 * Np + 4 * i;
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(r.x, r.y), h1 = __floats2bfloat162_rn(r.z, r.w);
+      const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(r.x - __uint_as_float(u0 << 16), r.y - __uint_as_float(u0 & 0xffff0000u));
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(r.z - __uint_as_float(u1 << 16), r.w - __uint_as_float(u1 & 0xffff0000u));
+      *reinterpret_cast<uint2*>(d) = make_uint2(u0, u1);
+      *reinterpret_cast<uint2*>(d + Np) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  }
+  if (gs != nullptr) {                                             // the K-padding columns [N, Np) of both halves read as zero
+    __nv_bfloat16* d = gs + ((size_t)b * HID + c) * 2 * Np;
+    for (int i = N + threadIdx.x; i < Np; i += blockDim.x) { d[i] = __float2bfloat16(0.f); d[Np + i] = __float2bfloat16(0.f); }
   }
 }
 
@@ -1396,12 +1414,19 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   if ((rc = gemm_nn(a, st))) return rc;
   const size_t sm2 = plane_smem(H, W, 2);
   if ((rc = v4 ? ensure_smem(gdfn_gate_fwd_v4_kernel, sm2) : ensure_smem(gdfn_gate_fwd_kernel, sm2))) return rc;
-  if (v4) gdfn_gate_fwd_v4_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
-  else gdfn_gate_fwd_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
-  EMIP_CHECK_LAUNCH("gdfn_gate_fwd");
   a = {};
   a.B = B; a.M = DIM; a.K = HID; a.N = N; a.w = params[P_FOW]; a.ldw = HID;
   a.x = g; a.x_stride_b = (long long)HID * N; a.ldx = N;
+  // tensor-core path: the gate kernel writes the GEMM's bf16 hi | lo activation operand in place (no fp32 g, no split pass)
+  __nv_bfloat16* gs = nullptr;
+  int gnp = 0;
+  if (v4 && g_tc.ws != nullptr && gemm_nn_tc_supported(a) && g_tc.bytes >= gemm_nn_tc_scratch_bytes(B, DIM, HID, N, false)) {
+    gs = static_cast<__nv_bfloat16*>(gemm_nn_tc_act_operand(g_tc.ws, B, DIM, HID, N, false, &gnp));
+    a.x_presplit = 1;
+  }
+  if (v4) gdfn_gate_fwd_v4_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, gs, gnp, H, W);
+  else gdfn_gate_fwd_kernel<<<dim3(HID, B), 256, sm2, st>>>(s.tpre, params[P_FDW], g, H, W);
+  EMIP_CHECK_LAUNCH("gdfn_gate_fwd");
   a.res = s.y; a.res_stride_b = (long long)DIM * N; a.ldr = N;
   a.y = out; a.y_stride_b = (long long)DIM * N; a.ldy = N;
   return gemm_nn(a, st);
