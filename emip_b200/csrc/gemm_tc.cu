@@ -38,6 +38,11 @@ __device__ __forceinline__ float gelu_epi(float x) {
   return x * (x >= 0.f ? 1.f - g : g);
 }
 
+// EPI selects the epilogue at compile time (0: mode 0 | 1: mode 1 | 2: mode 2 + LayerNorm | 3: mode 2 bf16 hi | lo output |
+// 4: mode 2 plain fp32): one function for all of them put every branch under the register allocation of the hungriest one
+// (168 registers at 10 warps) and spilled; per-instantiation allocation has no spills and lets the split epilogue keep two
+// TMEM chunks in flight
+template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b, const GemmTcParams p) {
@@ -201,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     ++n_tiles;
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 256);
-    if (p.mode == 0) {
+    if constexpr (EPI == 0) {
       __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
       __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -229,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
-    } else if (p.mode == 2 && p.ln_gamma != nullptr) {
+    } else if constexpr (EPI == 2) {
       // the whole 128-wide output row lives in this thread's TMEM lane: LayerNorm over it (+ residual) before the store --
       // three passes over TMEM (mean, centred variance, write), no fp32 round trip of the pre-norm tensor through HBM
       // residual rows of the staged third pass: all eight 16-byte loads of a chunk are issued together and one chunk ahead
@@ -308,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         __syncwarp();
       }
-    } else if (p.mode == 2 && p.out_split != 0) {
+    } else if constexpr (EPI == 3) {
       // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
       const int n0 = nt * p.n_tile;
       __nv_bfloat16* gh = p.g_hi + (size_t)row * p.ldg + n0;
@@ -329,10 +334,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32_async(taddr + c0, r);
-        tmem_wait(r);
+      // one 32-column chunk: r = the accumulator chunk just read from TMEM
+      auto chunk = [&](uint32_t (&r)[32], const int c0) {
         if (row < p.M && n0 + c0 < p.N) {
           uint32_t hi[16], lo[16];
           float v[32];
@@ -385,8 +388,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           __syncwarp();
         }
+      };
+      // (r2u: keeping the next chunk's TMEM read in flight while this one is converted did not help -- the GELU / split
+      // epilogue is issue- and dependency-bound, not TMEM-latency-bound -- and cost the 256 -> 1024 layer 10 %: not kept)
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_async(taddr + c0, r);
+        tmem_wait(r);
+        chunk(r, c0);
       }
-    } else if (p.mode == 2) {
+    } else if constexpr (EPI == 4) {
       const int n0 = nt * p.n_tile;
       float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
       const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
@@ -632,7 +643,10 @@ int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_
 int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b, GemmTcParams p, int batch,
                    cudaStream_t st) {
   const int max_smem = 227 * 1024;
-  if (int rc__ = emip_func_max_smem((const void*)(gemm_tc_kernel), max_smem)) return rc__;
+  const int epi = p.mode == 0 ? 0 : p.mode == 1 ? 1 : p.ln_gamma != nullptr ? 2 : p.out_split != 0 ? 3 : 4;
+  const void* kfn = epi == 0 ? (const void*)gemm_tc_kernel<0> : epi == 1 ? (const void*)gemm_tc_kernel<1> : epi == 2 ? (const void*)gemm_tc_kernel<2>
+                  : epi == 3 ? (const void*)gemm_tc_kernel<3> : (const void*)gemm_tc_kernel<4>;
+  if (int rc__ = emip_func_max_smem(kfn, max_smem)) return rc__;
   if (p.stages == 0) {
     p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024);
     p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
@@ -647,7 +661,13 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   p.total_tiles = (int)tiles;
   const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
   const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0);
-  gemm_tc_kernel<<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p);
+  switch (epi) {
+    case 0: gemm_tc_kernel<0><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+    case 1: gemm_tc_kernel<1><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+    case 2: gemm_tc_kernel<2><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+    case 3: gemm_tc_kernel<3><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+    default: gemm_tc_kernel<4><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+  }
   EMIP_CHECK_LAUNCH("gemm_tc");
   return EMIP_OK;
 }
