@@ -369,6 +369,7 @@ def main():
             st = chain_time.stage_times(chain, sets[0][0], sets[0][1], iters=5)
         line["chain_stage_ms"] = {k: round(v, 4) for k, v in st.items()}
         line["roofline"] = dominant_kernel_roofline(torch, chain, per, dev, pk)
+        line["roofline_feature_transformer"] = ft_roofline(torch, chain, per, dev, pk)
         line["roofline_k1_c2"] = k1_roofline(torch, dev, pk, max(K, 50))
         import k3_bench
         line["flow_warp_roofline"] = {"kernel": "flow_warp_staged_kernel<fwd|bwd> (TMA-staged; smooth flow) / flow_warp_border3_kernel (direct gather; noisy flow)",
@@ -445,6 +446,36 @@ def dominant_kernel_roofline(torch, chain, per, dev, pk):
             "peak_source": pk["src"] + " burst bf16 (cuBLAS)", "call_ms": ms, "rows": Lr,
             "executed_mma_tflops": 3 * ach, "executed_mma_frac": 3 * ach / pk["tf"],
             "note": "achieved = algorithmic 2*L*(256*1024 + 1024*128) FLOP / time; executed = x3 (bf16 hi/lo split keeps fp32 accuracy)"}
+
+
+def ft_roofline(torch, chain, per, dev, pk):
+    """The FeatureTransformer call (emip_feature_transformer_fwd: 54 gemm_tc_kernel + 24..48 attn_fwd_tc_kernel launches) = half of
+    the step: algorithmic FLOPs of its twelve layers / CUDA-event time of the call."""
+    from emip_b200.chain import feature_transformer_tokens
+    maps = 2 * per
+    Lr = maps * N
+    xs = [torch.randn(maps, N, C, device=dev) for _ in range(2)]
+    with torch.no_grad():
+        for i in range(2):
+            feature_transformer_tokens(xs[i], chain.GMFlow.transformer, H, W, 2)
+        torch.cuda.synchronize()
+        n = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            feature_transformer_tokens(xs[i % 2], chain.GMFlow.transformer, H, W, 2)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    lin = 2.0 * Lr * (8 * 128 * 128 + 256 * 1024 + 1024 * 128)                    # per block: q k v merge x2, mlp
+    pairs_plain = 4 * 484 * 484                                                  # token pairs attended per map, unshifted layer
+    pairs_shift = 484 * 484 + 4 * 242 * 242 + 4 * 121 * 121                      # shifted layer (block decomposition of the mask)
+    att = lambda pr: 2 * (2.0 * pr * 128 * 2) * maps                              # two attention layers per block, QK^T and PV
+    alg = 3 * (lin + att(pairs_plain)) + 3 * (lin + att(pairs_shift))
+    ach = alg / (ms * 1e-3) / 1e12
+    return {"call": "emip_feature_transformer_fwd (6 blocks)", "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": ach / pk["tf"], "call_ms": ms, "rows": Lr, "executed_mma_tflops": 3 * ach, "executed_mma_frac": 3 * ach / pk["tf"],
+            "note": "algorithmic FLOPs of the six block pairs (linear layers + window attention); executed = x3 (bf16 hi/lo split)"}
 
 
 def k1_roofline(torch, dev, pk, K):

@@ -39,8 +39,12 @@ def stage_times(m, gm, seg, iters=10):
         gmf = m.GMFlow
         ab = timed("a4 injector x2 (one call, 2B maps)", lambda: m.injector(gm, seg))
         x = timed("pos add + token rows", lambda: ch.tokens_from_cn(ab, ch.window_position(H, W, m.attn_splits, C, dev)))
-        for blk in gmf.transformer.layers:
-            x = timed("f2/f2b transformer blocks (x6)", lambda blk=blk, x=x: ch.transformer_block(blk, x, H, W, m.attn_splits))
+        if m.fused_transformer:
+            x = timed("f2/f2b FeatureTransformer (one C-ABI call, 6 blocks)",
+                      lambda x=x: ch.feature_transformer_tokens(x, gmf.transformer, H, W, m.attn_splits, m._cache))
+        else:
+            for blk in gmf.transformer.layers:
+                x = timed("f2/f2b transformer blocks (x6, per-layer calls)", lambda blk=blk, x=x: ch.transformer_block(blk, x, H, W, m.attn_splits))
         flow_pred = timed("a1 matching (lazy corr)", lambda: ch.global_matching_tokens(x, B, H, W))
         ffa = gmf.feature_flow_attn
 
