@@ -152,3 +152,43 @@ def fuse_conv_corr(model):
     model.forward = forward
     model._emip_fused_forward = True
     return model
+
+
+def fuse_chain(model):
+    """Route a constructed ``CoUpdater``'s inference forward through ``emip_b200.chain.MotionChain`` (the chained hot path as
+    one object: both frames through the feeder in one call, the FeatureTransformer in one C-ABI call, token-major layouts, the
+    cost volume never formed, BatchNorm + ReLU folded, tensor-core 3x3 convolutions -- DESIGN.md section 4 CHAIN).
+
+    ``model.forward(image1, image2)`` keeps its signature and results (model.py:86-102): the backbones, ``dr1-3`` and the
+    decoder stay the model's own modules; lines 92-97 become one ``MotionChain`` call on the stacked post-backbone features.
+    In training mode (or with autograd enabled) the original forward runs (per-op drop-ins with their backward kernels).
+    Requires ``install()`` before the model is constructed (the chain borrows the model's ``Injector`` modules).  Returns ``model``.
+    """
+    import functools
+    import torch
+    from .chain import MotionChain
+    if getattr(model, "_emip_chain", None) is not None:
+        return model
+    chain = MotionChain.wrap(model)
+    inner = model.forward
+
+    @functools.wraps(inner)
+    def forward(image1, image2):
+        if model.training or torch.is_grad_enabled():
+            return inner(image1, image2)
+        fea_1 = model.backbone.feat_net(image1)                                   # model.py:87-90
+        fea_2 = model.backbone.feat_net(image2)
+        fea_1_gm = model.GMFlow.backbone(image1)
+        fea_2_gm = model.GMFlow.backbone(image2)
+        gm = torch.cat((fea_1_gm[0], fea_2_gm[0]), dim=0)
+        seg = torch.cat((fea_1[0], fea_2[0]), dim=0)
+        flow_fw, flow_bw, _, fea_new = chain(gm, seg)                             # model.py:92-97
+        fea_new = model.dr1(fea_new)                                              # model.py:98-101
+        f_2 = model.dr2(fea_1[1])
+        f_3 = model.dr3(fea_1[2])
+        mask = model.decoder(f_3, f_2, fea_new)
+        return mask, [flow_fw], [flow_bw]                                         # eval: one-entry flow lists (gmflow.py:147-155)
+
+    model.forward = forward
+    model._emip_chain = chain
+    return model

@@ -224,3 +224,38 @@ def test_train_chain_vs_reference(golden):
     bad = {k: v for k, v in errs.items() if k in tol and not v <= tol[k]}
     assert not bad, bad
     assert all(p.grad is None for n, p in m.named_parameters() if n.startswith("GMFlow"))
+
+
+def test_fuse_chain_glue_reproduces_the_reference_forward_on_cpu():
+    """Row (g), the part that needs the reference: ``dropin.fuse_chain`` replaces model.py:92-97 inside the UNMODIFIED reference
+    ``CoUpdater`` (its own backbones, dr1-3 and decoder).  With the chain object's kernel call swapped for the CPU oracle's
+    ``motion_chain`` (the GPU tests pin our kernels to that oracle), the fused model must return the reference's own mask logits
+    and flows: same stacking of the two frames, same outputs wired into dr1 / the decoder, argmax mask bit-exact."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not mounted")
+    ref_shim.install()
+    from model.EMIP_short.model import CoUpdater
+    from emip_b200 import dropin
+    torch.manual_seed(123)
+    net = CoUpdater(ref_shim.model_args()).eval()
+    net.load_state_dict(cases.chain_params(), strict=False)
+    im1, im2 = cases.randn(0, (1, 3, 352, 352)), cases.randn(1, (1, 3, 352, 352))
+    with torch.no_grad():
+        mask_ref, ffw_ref, fbw_ref = net(im1, im2)
+    dropin.fuse_chain(net)
+    P = {k: v.detach() for k, v in net.state_dict().items()}
+
+    def oracle_forward(gm, seg, want=()):
+        out = O.motion_chain(gm, seg, P)
+        return out["flow_fw"], out["flow_bw"], out["corr"], out["fea_new"]
+    net._emip_chain.forward = oracle_forward
+    with torch.no_grad():
+        mask, ffw, fbw = net(im1, im2)
+    assert len(ffw) == len(ffw_ref) == 1 and len(fbw) == 1
+    assert _rel(ffw[0], ffw_ref[0]) < 2e-4 and _rel(fbw[0], fbw_ref[0]) < 2e-4
+    assert _rel(mask, mask_ref) < 1e-4
+    assert torch.equal(mask > 0, mask_ref > 0)                                     # argmax mask (1-channel logit > 0), SURVEY F5
+    # in training mode the original forward runs
+    net.train()
+    assert net.forward.__wrapped__ is not None
