@@ -259,3 +259,52 @@ def test_fuse_chain_glue_reproduces_the_reference_forward_on_cpu():
     # in training mode the original forward runs
     net.train()
     assert net.forward.__wrapped__ is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,c0,c1,o,h,w,lay0,lay1,relu,scale", [
+    (2, 2, 128, 256, 44, 44, 1, 0, True, False),      # upsampler[0]: cat(flow [CN], tokens [NC]) -> 256, ReLU
+    (1, 968, 0, 128, 44, 44, 1, 1, False, False),     # conv_corr[3]
+    (3, 37, 0, 72, 12, 20, 0, 0, False, True),        # ragged: Cin / O not multiples of the tile sizes, token-major input, BN-style affine
+    (2, 70, 11, 130, 16, 16, 1, 1, True, True),       # two channel-major sources, partial M tile
+])
+def test_conv3x3_vs_library_convolution(b, c0, c1, o, h, w, lay0, lay1, relu, scale):
+    """emip_conv3x3_fwd (shifted-TMA-box im2col, split-bf16 tcgen05) against the fp64 convolution of the concatenated input."""
+    from emip_b200 import chain as ch
+    x0 = cases.randn(401, (b, c0, h, w), 1.5)
+    x1 = cases.randn(402, (b, c1, h, w), 0.7) if c1 else None
+    wt = cases.randn(403, (o, c0 + c1, 3, 3), (9 * (c0 + c1)) ** -0.5)
+    sh = cases.randn(404, (o,), 0.3)
+    sc = (1 + 0.2 * cases.randn(405, (o,))) if scale else None
+    xin = x0 if x1 is None else torch.cat((x0, x1), 1)
+    ref = torch.nn.functional.conv2d(xin.double(), wt.double(), None, padding=1)
+    ref = ref * (sc.double().view(1, -1, 1, 1) if scale else 1.0) + sh.double().view(1, -1, 1, 1)
+    if relu:
+        ref = ref.clamp_min(0)
+    tok = lambda t: t.flatten(2).transpose(1, 2).contiguous()
+    g0 = (x0 if lay0 == 1 else tok(x0)).cuda()
+    g1 = None if x1 is None else (x1 if lay1 == 1 else tok(x1)).cuda()
+    wp = ch.prepare_conv3x3(wt.cuda())
+    out = ch.conv3x3(g0, lay0, g1, lay1, wp, o, h, w, scale=None if sc is None else sc.cuda(), shift=sh.cuda(), relu=relu)
+    assert _rel(out, ref) < 2e-5
+
+
+@pytest.mark.gpu
+def test_tokens_from_cn_and_bias_linear_and_kv_swap():
+    """The small pieces of the chain against torch: transpose + position add, nn.Linear with bias on token rows, and the
+    cross-attention call that reads the keys / values of the other batch half (no swapped copy)."""
+    from emip_b200 import chain as ch
+    x = cases.randn(411, (3, 128, 10, 14))
+    pos = ch.window_position(10, 14, 2, 128, torch.device("cuda", 0))
+    ref = (x + pos.cpu().view(1, 128, 10, 14)).flatten(2).transpose(1, 2)
+    assert torch.equal(ch.tokens_from_cn(x.cuda(), pos).cpu(), ref)
+    assert torch.equal(pos.cpu().view(128, 10, 14), O.position_embedding_sine(5, 7, 64).repeat(1, 2, 2))
+    t = cases.randn(412, (2, 300, 128), 2.0)
+    wt, bs = cases.randn(413, (128, 128), 128 ** -0.5), cases.randn(414, (128,), 0.2)
+    assert _rel(ch.linear_tm_bias(t.cuda(), wt.cuda(), bs.cuda()), t.double() @ wt.double().T + bs.double()) < 1e-5
+    q, k, v = (cases.randn(415 + i, (4, 16 * 24, 128), 1.5 if i < 2 else 1.0) for i in range(3))
+    swap = lambda z: torch.cat(z.chunk(2, 0)[::-1], 0)
+    for shift in (False, True):
+        ref = O.split_window_attention(q.double(), swap(k).double(), swap(v).double(), 2, shift, 16, 24)
+        out = ch.window_attention(q.cuda(), k.cuda(), v.cuda(), 2, shift, 16, 24, kv_swap_halves=True)
+        assert _rel(out, ref) < 5e-5

@@ -936,3 +936,21 @@ def test_a3_two_threads_two_streams():
     for t in ts:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_bf16_modes_are_forward_only_and_memory_q_out_only_grad():
+    """the bf16 inference modes refuse a backward pass (their saved log-sum-exp comes from bf16 scores); a memory read
+    whose only differentiable input is q_out returns the pass-through half of the incoming gradient."""
+    from emip_b200.matching import global_correlation_softmax
+    from emip_b200.memory import Memory
+    f0 = dev(cases.randn(501, (1, 128, 8, 8))).requires_grad_(True)
+    f1 = dev(cases.randn(502, (1, 128, 8, 8)))
+    flow, _, _ = global_correlation_softmax(f0, f1, True, bf16=True)
+    with pytest.raises(Exception):
+        flow.sum().backward()
+    d5 = cases.a5_inputs(dict(b=1, t=2, h=5, w=6, scale=1.0, seed=58))
+    q_out = dev(d5["q_out"]).requires_grad_(True)
+    out, _ = Memory()(dev(d5["m_in"]), dev(d5["m_out"]), dev(d5["q_in"]), q_out)
+    wout = dev(d5["wout"])
+    (out * wout).sum().backward()
+    assert torch.equal(q_out.grad.reshape(1, 128, 5, 6), wout[:, 128:])
