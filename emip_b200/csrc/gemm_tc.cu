@@ -42,6 +42,34 @@ __device__ __forceinline__ float gelu_epi(float x) {
 // 4: mode 2 plain fp32): one function for all of them put every branch under the register allocation of the hungriest one
 // (168 registers at 10 warps) and spilled; per-instantiation allocation has no spills and lets the split epilogue keep two
 // TMEM chunks in flight
+// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2: sm_100 executes two fp32 FMAs per instruction): the GELU / split
+// epilogue of the 256 -> 1024 layer is instruction-issue bound (r3i: 25 instructions per element on eight warps).
+// gelu(x) = max(x, 0) - |x| Phi(-|x|): no select, no 1 - g.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void gelu_epi2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 ax = pk2(a0, a1);
+  const f32x2 z = mul2(ax, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  float d0, d1, q0, q1, t0, t1, e0, e1;
+  upk2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.f, 1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  upk2(mul2(mul2(z, pk2(-1.44269504088896340736f, -1.44269504088896340736f)), z), q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const f32x2 t = pk2(t0, t1);
+  f32x2 p = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));
+  p = fma2(p, t, pk2(0.7107068705f, 0.7107068705f));
+  p = fma2(p, t, pk2(-0.142248368f, -0.142248368f));
+  p = fma2(p, t, pk2(0.127414796f, 0.127414796f));
+  const f32x2 g = mul2(mul2(p, t), pk2(e0, e1));                         // Phi(-|x|) of both elements
+  upk2(fma2(pk2(-a0, -a1), g, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -53,9 +81,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   auto full = [&](int s) { return bar0 + 8 * s; };
   auto empty = [&](int s) { return bar0 + 8 * (p.stages + s); };
   // two accumulator tiles of <= 256 TMEM columns: the epilogue of tile i overlaps the main loop of tile i + 1
+  // accumulator tiles in TMEM: two of <= 256 columns, or FOUR of <= 128 columns -- then each epilogue group owns two and the
+  // MMAs of its next tile run while it still drains the previous one (r3b role profile: with one accumulator per group the
+  // issuer waited 43 % of the 256 -> 1024 launch for `acc_empty` and the epilogue warps 31 % for `acc_full`: MMA and epilogue
+  // of a group ran strictly one after the other)
+  const int nacc = p.n_tile <= 128 ? 4 : 2, acc_cols = 512 / nacc, acc_shift = nacc == 4 ? 2 : 1;
   auto acc_full = [&](int a) { return bar0 + 8 * (2 * p.stages + a); };
-  auto acc_empty = [&](int a) { return bar0 + 8 * (2 * p.stages + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 4));
+  auto acc_empty = [&](int a) { return bar0 + 8 * (2 * p.stages + 4 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 8));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the (batch, m tile, n tile) list
@@ -67,7 +100,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 128); }
+    for (int a = 0; a < 4; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -135,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     }
     __syncwarp();
-    if (p.prof != nullptr && lane == 0) { p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 1] = w_empty; }
+    if (p.prof != nullptr && lane == 0) { p.prof[blockIdx.x * 8 + 0] += clock64() - t_begin; p.prof[blockIdx.x * 8 + 1] += w_empty; }
   } else if (warp == 5) {
     // ===================== UMMA issuer =====================
     const bool leader = elect_one();
@@ -145,9 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     long long w_full = 0, w_acc = 0;
     const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-    const int acc = it & 1;
-    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-    w_acc += mbar_wait(acc_empty(acc), ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (two tiles ago)
+    const int acc = it & (nacc - 1);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+    w_acc += mbar_wait(acc_empty(acc), ((it >> acc_shift) & 1) ^ 1);       // the epilogue has drained this accumulator (nacc tiles ago)
     tc_fence_after();
     for (int kc = 0; kc < p.kchunks; ++kc) {
       w_full += mbar_wait(full(stage), phase);
@@ -182,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     }
     if (p.prof != nullptr && lane == 0) {
-      p.prof[blockIdx.x * 8 + 2] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 3] = w_full; p.prof[blockIdx.x * 8 + 4] = w_acc;
+      p.prof[blockIdx.x * 8 + 2] += clock64() - t_begin; p.prof[blockIdx.x * 8 + 3] += w_full; p.prof[blockIdx.x * 8 + 4] += w_acc;
     }
   } else {
     // ===================== epilogue warps: thread <-> output row =====================
@@ -192,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int grp = warp >= 6 ? 1 : 0, qw = warp & 3;
     // warp-private staging tile [32 rows][33 words] behind the barriers: a thread's 32 accumulator columns go in as a row,
     // come out as 4 rows x 128 B per warp store (r3h: the row-per-thread stores touched 32 lines per instruction)
-    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 15) & ~15)) +
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 15) & ~15)) +
                     (grp * 4 + qw) * (32 * 33);
     uint32_t it = grp;
     long long w_accf = 0, n_tiles = 0;
@@ -200,12 +233,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     int nt, mt, b;
     decode(tile, nt, mt, b);
-    const int acc = it & 1;
+    const int acc = it & (nacc - 1);
     const int row = mt * TM + qw * 32 + lane;
-    w_accf += mbar_wait(acc_full(acc), (it >> 1) & 1);
+    w_accf += mbar_wait(acc_full(acc), (it >> acc_shift) & 1);
     ++n_tiles;
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * 256);
+    const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * acc_cols);
     if constexpr (EPI == 0) {
       __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
       __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
@@ -251,29 +284,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       };
       load_res(0);
-      float sum = 0.f;
+      // statistics in ONE pass over the TMEM lane (r3c: three passes made this epilogue 18 k cycles per tile, the bound of every
+      // merge + norm1 launch): sums of (x - c) and (x - c)^2 around c = the row's first element, so that the variance
+      // s2/n - (s1/n)^2 cancels at most one bit (|c - mean| is of the order of the row's own deviation)
+      float s1 = 0.f, s2 = 0.f, cshift = 0.f;
       for (int c0 = 0; c0 < TM; c0 += 32) {
         uint32_t r[32];
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c0 == 0) cshift = __uint_as_float(r[0]);
+        float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s4[i & 3] += __uint_as_float(r[i]);
-        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        for (int i = 0; i < 32; ++i) {
+          const float d = __uint_as_float(r[i]) - cshift;
+          a4[i & 3] += d;
+          b4[i & 3] = fmaf(d, d, b4[i & 3]);
+        }
+        s1 += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+        s2 += (b4[0] + b4[1]) + (b4[2] + b4[3]);
       }
-      const float mean = sum * (1.f / 128.f);
-      float sq = 0.f;
-      for (int c0 = 0; c0 < TM; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32_async(taddr + c0, r);
-        tmem_wait(r);
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mean; s4[i & 3] = fmaf(d, d, s4[i & 3]); }
-        sq += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      }
+      const float m1 = s1 * (1.f / 128.f);
+      const float mean = cshift + m1;
+      const float sq = fmaxf(s2 - s1 * m1, 0.f);                   // = sum (x - mean)^2
       const float rstd = rsqrtf(sq * (1.f / 128.f) + p.ln_eps);
-      // third pass: the normalised chunk goes through the warp-private staging tile so that the residual read, the fp32 store
+      // second pass: the normalised chunk goes through the warp-private staging tile so that the residual read, the fp32 store
       // and the bf16 hi | lo stores are row segments of 128 / 64 bytes (r2: one 16-byte piece per row and instruction made
       // merge + norm1 224 us instead of 108 at 64 pairs)
       for (int c0 = 0; c0 < TM; c0 += 32) {
@@ -343,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (p.out_split == 2) {                             // one uniform branch per chunk, not per element
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_epi(v[i]);
+            for (int i = 0; i < 16; ++i) gelu_epi2(v[2 * i], v[2 * i + 1]);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -510,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     mbar_arrive(acc_empty(acc));                          // every TMEM read of this tile has completed
     }
     if (p.prof != nullptr && warp == 0 && lane == 0) {
-      p.prof[blockIdx.x * 8 + 5] = clock64() - t_begin; p.prof[blockIdx.x * 8 + 6] = w_accf; p.prof[blockIdx.x * 8 + 7] = n_tiles;
+      p.prof[blockIdx.x * 8 + 5] += clock64() - t_begin; p.prof[blockIdx.x * 8 + 6] += w_accf; p.prof[blockIdx.x * 8 + 7] += n_tiles;
     }
   }
   tc_fence_before();
@@ -631,8 +665,11 @@ unsigned split_w_blocks(int M, int Kp) { return (unsigned)(((long long)M * (Kp >
 
 }  // namespace
 
+static int g_gemm_wide_tiles = 0;   // r3c: with four accumulators 128-column tiles are as fast at 64 pairs and 3.5 % faster at 8
+// Diagnostics / tuning: 0 (default) = 128-column tiles (four TMEM accumulators) also for wide outputs, 1 = 256-column tiles for N >= 512.
+extern "C" void emip_debug_gemm_wide_tiles(int v) { g_gemm_wide_tiles = v ? 1 : 0; }
 static unsigned long long* g_gemm_prof = nullptr;
-// Diagnostics (tools/gemm_roles.py): device buffer of (SM count) x 8 cycle counters filled by the next launches; NULL = off.
+// Diagnostics (tools/gemm_roles.py): device buffer of (SM count) x 8 cycle counters the next launches ADD to; NULL = off.
 extern "C" void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf) { g_gemm_prof = dev_buf; }
 
 int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -660,7 +697,7 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   EMIP_CHECK_ARG(tiles > 0 && tiles < 0x7fffffffLL, "gemm_tc: bad tile count");
   p.total_tiles = (int)tiles;
   const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0);
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0);
   switch (epi) {
     case 0: gemm_tc_kernel<0><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
     case 1: gemm_tc_kernel<1><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
@@ -818,7 +855,7 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
   const cuuint64_t bstr[2] = {(cuuint64_t)2 * Np * 2, (cuuint64_t)a.K * 2 * Np * 2};
   // wide outputs (the 256 -> 1024 MLP layer): 256-column tiles -- the A tile (hi + lo) is fetched once per 256 instead
   // of once per 128 output columns (r3: that GEMM was bound by the L2 -> shared-memory operand stream, 991 MB per call)
-  const int ntile = (a.K % 256 == 0 && a.K >= 512 && nsplit <= 1) ? 256 : TM;
+  const int ntile = (g_gemm_wide_tiles && a.K % 256 == 0 && a.K >= 512 && nsplit <= 1) ? 256 : TM;
   const cuuint32_t bbox[3] = {KCH, (cuuint32_t)ntile, 1};
   if ((rc = gemm_tc_make_map(&mb, bt, 3, bdims, bstr, bbox))) return rc;
   GemmTcParams p = {};

@@ -32,7 +32,7 @@
  *      (4) diagnostic switches for the profiling scripts under tools/ --
  *          emip_match_tc_set_profile_buffer, emip_match_tc_set_variant,
  *          emip_attn_tc_set_profile_buffer, emip_gemm_tc_set_profile_buffer,
- *          emip_debug_flow_warp_staged_profile --
+ *          emip_debug_flow_warp_staged_profile, emip_debug_gemm_wide_tiles --
  *          NOT thread-safe, never touched by the host package, default off.
  *    No entry point allocates or frees memory (cudaMalloc / cudaHostAlloc), so all
  *    of them may be captured into CUDA graphs once (1) is warm (first call).
@@ -84,6 +84,8 @@ void emip_match_tc_set_profile_buffer(unsigned long long* dev_buf);
 void emip_match_tc_set_variant(int softmax_warps);
 /* Diagnostics: role wait-cycle profile of gemm_tc_kernel, device pointer to [SM count][8] uint64 or NULL (tools/gemm_roles.py). */
 void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf);
+/* Diagnostics / tuning: gemm_tc tile width for outputs of >= 512 columns: 0 = 128-column tiles, four TMEM accumulators (default), 1 = 256-column tiles. */
+void emip_debug_gemm_wide_tiles(int v);
 /* Diagnostics: wait-cycle profile of the staged flow_warp kernel, device pointer to [grid][8] int64 or NULL. */
 void emip_debug_flow_warp_staged_profile(long long* buf);
 

@@ -17,11 +17,13 @@ w = torch.randn(128, 128, device=dev) / 11
 w1 = torch.randn(1024, 256, device=dev) / 16
 w2 = torch.randn(128, 1024, device=dev) / 32
 g, b = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+h = torch.randn(rows, 1024, device=dev)
 prof = torch.zeros(148, 8, dtype=torch.int64, device=dev)
 cases = {
     "linear 128->128 (plain fp32 epilogue)": lambda: linear_tm(x, w),
     "linear 128->128 + LN + residual": lambda: linear_ln_tm(x, w, g, b, 1e-5, residual=x),
-    "mlp 256->1024->128 + LN (2 GEMM launches, last one profiled)": lambda: mlp_tm(x2, w1, w2, g, b, 1e-5, residual=x),
+    "linear 1024->128 + LN + residual (= the mlp[2] launch)": lambda: linear_ln_tm(h, w2, g, b, 1e-5, residual=x),
+    "mlp 256->1024->128 + LN (SUM of the mlp[0] + GELU / split launch and the mlp[2] launch)": lambda: mlp_tm(x2, w1, w2, g, b, 1e-5, residual=x),
 }
 with torch.no_grad():
     for name, fn in cases.items():
