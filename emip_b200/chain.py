@@ -271,6 +271,29 @@ def global_matching_tokens(tok, B, h, w, bf16=False):
     return flow
 
 
+def conv_corr_fused(tok, B, h, w, conv0, w_prep0, scale, shift, conv3, w_prep3):
+    """conv_corr in eval mode from the token rows: conv_corr[0] on the never-materialised cost volume with BatchNorm + ReLU in
+    its epilogue, which writes conv_corr[3]'s token-major bf16 hi | lo operand directly (no fp32 [B,968,h,w] round trip, no split
+    pass), then the 3x3 convolution on the tensor cores -> [B, 128, h, w]  (model.py:59-62, :96)."""
+    L = _lib.lib()
+    C, O, O3 = tok.shape[-1], conv0.weight.shape[0], conv3.weight.shape[0]
+    cp = (O + 127) // 128 * 128
+    if cp != (O + 63) // 64 * 64 or not L.emip_conv_corr_supported(I(C), I(h), I(w)) or not L.emip_conv3x3_supported(I(O), I(h), I(w)):
+        return None
+    L.emip_conv_corr_workspace.restype = ctypes.c_size_t
+    ws, ws_ptr, ws_n = workspace(L.emip_conv_corr_workspace(I(B), I(C), I(h), I(w), I(O)), tok.device)
+    tb, tb_ptr, _ = workspace(B * h * w * 2 * cp * 2, tok.device)
+    out = torch.empty((B, O3, h, w), dtype=torch.float32, device=tok.device)
+    with torch.cuda.device(tok.device):
+        _lib.check(L.emip_conv_corr_fwd_tokens(ptr(tok[:B]), ptr(tok[B:]), ctypes.c_void_p(w_prep0), None, ptr(scale), ptr(shift), I(1),
+                                               I(LAYOUT_NC), None, ctypes.c_void_p(tb_ptr), ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C),
+                                               I(h), I(w), I(O), stream_ptr()), "emip_conv_corr_fwd_tokens")
+        _lib.check(L.emip_conv3x3_fwd_tokens(ctypes.c_void_p(tb_ptr), I(O), I(cp), ctypes.c_void_p(w_prep3[1]), None,
+                                             ptr(conv3.bias.detach()), I(0), ptr(out), I(B), I(h), I(w), I(O3), stream_ptr()),
+                   "emip_conv3x3_fwd_tokens")
+    return out
+
+
 def conv_corr_head(tok, B, h, w, conv0, w_prep, scale, shift):
     """conv_corr[0:3] on the never-materialised cost volume of the token rows: relu(bn(conv(corr))) -> [B, O, h, w]."""
     L = _lib.lib()
@@ -476,8 +499,12 @@ class MotionChain(nn.Module):
             mask = conv1x1_cn(hid, up[2].weight, up[2].bias)                                     # gmflow.py:64
             flow_up = upsample_flow_convex(flow, mask, 8)                                        # gmflow.py:66-77
             cc = self.conv_corr
-            c1 = conv_corr_head(x, B, H, W, cc[0], _prepared_corr_weight(cc[0].weight)[1], bn_scale, bn_shift)      # model.py:59-61, :96
-            corr = conv3x3(c1, LAYOUT_CN, None, LAYOUT_CN, w_c3, cc[3].weight.shape[0], H, W, shift=cc[3].bias.detach())
+            c1 = None
+            corr = None if "corr1" in want else conv_corr_fused(x, B, H, W, cc[0], _prepared_corr_weight(cc[0].weight)[1], bn_scale, bn_shift,
+                                                                cc[3], w_c3)                     # model.py:59-62, :96
+            if corr is None:                                                                     # odd channel counts / corr1 wanted
+                c1 = conv_corr_head(x, B, H, W, cc[0], _prepared_corr_weight(cc[0].weight)[1], bn_scale, bn_shift)
+                corr = conv3x3(c1, LAYOUT_CN, None, LAYOUT_CN, w_c3, cc[3].weight.shape[0], H, W, shift=cc[3].bias.detach())
             fea_new = self.injector1(seg[:B], corr)                                              # model.py:97
         if want:
             loc = dict(ab=ab, feat_tok=x, flow_pred=flow_pred, flow_prop=flow, mask=mask, corr1=c1)

@@ -109,10 +109,22 @@ extern "C" int emip_conv_corr_fwd(const float* f0, const float* f1, const void* 
 extern "C" int emip_conv_corr_fwd_ex(const float* f0, const float* f1, const void* w_prep, const float* bias, const float* ep_scale,
                                      const float* ep_shift, int relu, int layout, float* out, void* workspace, size_t ws_bytes,
                                      int B, int C, int H, int W, int O, void* stream) {
+  return emip_conv_corr_fwd_tokens(f0, f1, w_prep, bias, ep_scale, ep_shift, relu, layout, out, nullptr, workspace, ws_bytes, B, C, H, W, O,
+                                   stream);
+}
+
+// tok_out != NULL (out may then be NULL): the result is written as the token-major bf16 hi | lo input operand of a following
+// emip_conv3x3_fwd_tokens -- [B][H*W][2 * Cp] with Cp = O rounded up to 128, hi at [0, Cp), lo at [Cp, 2 Cp), padding channels
+// zero -- instead of fp32 [B,O,H,W]: conv_corr[0] + BatchNorm + ReLU hand conv_corr[3] its operand without an fp32 round trip
+extern "C" int emip_conv_corr_fwd_tokens(const float* f0, const float* f1, const void* w_prep, const float* bias, const float* ep_scale,
+                                         const float* ep_shift, int relu, int layout, float* out, void* tok_out, void* workspace,
+                                         size_t ws_bytes, int B, int C, int H, int W, int O, void* stream) {
   if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(out != nullptr || tok_out != nullptr, "conv_corr_fwd: no output");
+  EMIP_CHECK_ARG(tok_out == nullptr || reinterpret_cast<uintptr_t>(tok_out) % 1024 == 0, "conv_corr_fwd: tok_out must be 1024-byte aligned");
   EMIP_CHECK_ARG((ep_scale == nullptr) == (ep_shift == nullptr), "conv_corr_fwd: ep_scale and ep_shift come together");
   EMIP_CHECK_ARG(layout == EMIP_LAYOUT_NC || layout == EMIP_LAYOUT_CN, "conv_corr_fwd: layout must be 0 (token-major) or 1 (channel-major)");
-  EMIP_CHECK_ARG(f0 && f1 && w_prep && out, "conv_corr_fwd: null pointer");
+  EMIP_CHECK_ARG(f0 && f1 && w_prep, "conv_corr_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0 && O > 0, "conv_corr_fwd: bad shape B=%d H=%d W=%d O=%d", B, H, W, O);
   if (!emip_conv_corr_supported(C, H, W)) {
     emip_set_error("conv_corr_fwd: unsupported shape C=%d H=%d W=%d (needs C=128 and R*W %% 16 == 0 for some R*W <= 256)", C, H, W);
@@ -175,6 +187,10 @@ extern "C" int emip_conv_corr_fwd_ex(const float* f0, const float* f1, const voi
     p.kchunks = 18; p.cpt = 2; p.lo_off = 128;
     p.W = W; p.H = H; p.R = R;
     p.bias = ep_scale ? ep_shift : bias; p.ep_scale = ep_scale; p.ep_relu = relu; p.out = out;
+    if (tok_out != nullptr) {
+      const int Cp = (O + TM - 1) / TM * TM;
+      p.tok_hi = static_cast<__nv_bfloat16*>(tok_out); p.tok_ld = 2 * Cp; p.tok_lo_off = Cp;
+    }
     if ((rc = gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st))) return rc;
   }
   return EMIP_OK;

@@ -194,6 +194,38 @@ extern "C" int emip_conv3x3_fwd(const float* x0, int C0, int layout0, const floa
   return gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st);
 }
 
+// As emip_conv3x3_fwd for an input that already is the token-major bf16 hi | lo operand ([B][H*W][2 * Cp], Cp = Cp_in: what
+// emip_conv_corr_fwd_tokens writes): no split pass, no workspace.  w_prep = emip_conv3x3_prepare_weight(w, O, Cin) with
+// cpad(Cin) == Cp_in.
+extern "C" int emip_conv3x3_fwd_tokens(const void* tok, int Cin, int Cp_in, const void* w_prep, const float* scale, const float* shift,
+                                       int relu, float* out, int B, int H, int W, int O, void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(tok && w_prep && out && Cin > 0, "conv3x3_fwd_tokens: null pointer");
+  EMIP_CHECK_ARG(Cp_in % KCH == 0 && Cp_in >= Cin && cpad(Cin) == Cp_in, "conv3x3_fwd_tokens: Cp_in must be Cin rounded up to %d", KCH);
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(tok) % 128 == 0, "conv3x3_fwd_tokens: tok must be 128-byte aligned");
+  if (!emip_conv3x3_supported(Cin, H, W)) { emip_set_error("conv3x3_fwd_tokens: unsupported shape Cin=%d H=%d W=%d", Cin, H, W); return EMIP_ENOSYS; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = Cp_in, R = rows_per_tile(H, W), N = H * W;
+  const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(w_prep);
+  const __nv_bfloat16* w_lo = w_hi + (size_t)O * 9 * Cp;
+  int rc;
+  CUtensorMap ma_hi, ma_lo, mb;
+  const cuuint64_t adims[3] = {(cuuint64_t)9 * Cp, (cuuint64_t)O, 1}, astr[2] = {(cuuint64_t)9 * Cp * 2, (cuuint64_t)O * 9 * Cp * 2};
+  const cuuint32_t abox[3] = {KCH, TM, 1};
+  if ((rc = gemm_tc_make_map(&ma_hi, w_hi, 3, adims, astr, abox))) return rc;
+  if ((rc = gemm_tc_make_map(&ma_lo, w_lo, 3, adims, astr, abox))) return rc;
+  const cuuint64_t bdims[4] = {(cuuint64_t)2 * Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t bstr[3] = {(cuuint64_t)2 * Cp * 2, (cuuint64_t)W * 2 * Cp * 2, (cuuint64_t)N * 2 * Cp * 2};
+  const cuuint32_t bbox[4] = {KCH, (cuuint32_t)W, (cuuint32_t)R, 1};
+  if ((rc = gemm_tc_make_map(&mb, tok, 4, bdims, bstr, bbox))) return rc;
+  GemmTcParams p = {};
+  p.mode = 1; p.M = O; p.n_mtiles = (O + TM - 1) / TM; p.n_ntiles = (H + R - 1) / R; p.n_tile = R * W;
+  p.cpt = Cp / KCH; p.kchunks = 9 * p.cpt; p.lo_off = Cp; p.a_shared = 1;
+  p.W = W; p.H = H; p.R = R;
+  p.bias = shift; p.ep_scale = scale; p.ep_relu = relu ? 1 : 0; p.out = out;
+  return gemm_tc_launch(ma_hi, ma_lo, mb, p, B, st);
+}
+
 extern "C" int emip_tokens_from_cn(const float* x, const float* pos, float* out, int B, int C, int N, void* stream) {
   if (B == 0) return EMIP_OK;
   EMIP_CHECK_ARG(x && out && B > 0 && C > 0 && N > 0, "tokens_from_cn: bad arguments");

@@ -509,6 +509,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const float esc = (row < p.M && p.ep_scale != nullptr) ? __ldg(p.ep_scale + row) : 1.f;
       const float efl = p.ep_relu ? 0.f : -INFINITY;
       float* o = p.out + ((size_t)b * p.M + row) * npix + px0;
+      if (p.tok_hi != nullptr) {
+        // token-major bf16 hi | lo output: transpose each [32 channels x 32 pixels] chunk through the warp's staging tile
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+          uint32_t r[32];
+          if (c0 + 32 <= p.n_tile) {
+            tmem_ld32_async(taddr + c0, r);
+            tmem_wait(r);
+          } else {
+            uint32_t h[32];
+            tmem_ld32_async(taddr + p.n_tile - 32, h);
+            tmem_wait(h);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = h[16 + i];
+#pragma unroll
+            for (int i = 16; i < 32; ++i) r[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            stg[i * 33 + lane] = row < p.M ? __float_as_uint(fmaxf(fmaf(__uint_as_float(r[i]), esc, bias), efl)) : 0u;
+          __syncwarp();
+          const int cc = (lane & 7) * 4;
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const int pr = it2 * 4 + (lane >> 3);                      // pixel of the chunk
+            const uint32_t* sp = stg + pr * 33 + cc;
+            const float v0 = __uint_as_float(sp[0]), v1 = __uint_as_float(sp[1]), v2 = __uint_as_float(sp[2]), v3 = __uint_as_float(sp[3]);
+            if (c0 + pr < min(p.n_tile, nvalid)) {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+              const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+              const __nv_bfloat162 l0 = __floats2bfloat162_rn(v0 - __uint_as_float(u0 << 16), v1 - __uint_as_float(u0 & 0xffff0000u));
+              const __nv_bfloat162 l1 = __floats2bfloat162_rn(v2 - __uint_as_float(u1 << 16), v3 - __uint_as_float(u1 & 0xffff0000u));
+              __nv_bfloat16* d = p.tok_hi + ((size_t)b * npix + px0 + c0 + pr) * p.tok_ld + mt * TM + qw * 32 + cc;
+              *reinterpret_cast<uint2*>(d) = make_uint2(u0, u1);
+              *reinterpret_cast<uint2*>(d + p.tok_lo_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            }
+          }
+          __syncwarp();
+        }
+      } else
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t r[32];
         // n_tile is a multiple of 16: the last group may be a half group
@@ -687,7 +726,7 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   if (p.stages == 0) {
     p.b_bytes = (int)emip_align_up((size_t)p.n_tile * 128, 1024);
     p.stage_bytes = 2 * A_BYTES + 2 * p.b_bytes;
-    p.epi_stage = p.mode == 2 ? 1 : 0;
+    p.epi_stage = (p.mode == 2 || (p.mode == 1 && p.tok_hi != nullptr)) ? 1 : 0;
     p.stages = (max_smem - 2048 - (p.epi_stage ? EPI_STAGE_BYTES : 0)) / p.stage_bytes;
     if (p.stages > 3) p.stages = 3;
     // (the ring runs on across tiles: with K = 128 a third stage prefetches the next tile's first chunk)

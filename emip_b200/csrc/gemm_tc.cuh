@@ -25,6 +25,10 @@ struct GemmTcParams {
   const float* bias;        // mode 1 (and per-row bias of mode 2)
   const float* ep_scale;    // mode 1: out = act(acc * ep_scale[row] + bias[row]) (NULL: scale 1)
   int ep_relu;              // mode 1: act = ReLU
+  // mode 1, tok_hi != NULL: the tile goes out as TOKEN-MAJOR bf16 hi | lo rows [b][pixel][hi tok_lo_off | lo] of pitch tok_ld --
+  // the input operand of a following emip_conv3x3 (conv_corr[0] + BN + ReLU -> conv_corr[3]) -- instead of fp32 [b][o][pixel];
+  // rows >= M (the channel padding up to a multiple of 128) are written as zeros
+  __nv_bfloat16* tok_hi; int tok_ld, tok_lo_off;
   __nv_bfloat16* g_hi;      // mode 0 output: [B][M][128] hi, lo
   __nv_bfloat16* g_lo;
   float* out;               // mode 1 output: [B][M][H*W]

@@ -321,6 +321,13 @@ int emip_conv_corr_fwd_ex(const float* f0, const float* f1, const void* w_prep, 
                           const float* ep_shift, int relu, int layout, float* out, void* workspace, size_t ws_bytes, int B, int C,
                           int H, int W, int O, void* stream);
 
+/* As emip_conv_corr_fwd_ex; tok_out != NULL (out may then be NULL): the result goes out as the token-major bf16 hi | lo input
+ * operand of a following emip_conv3x3_fwd_tokens -- [B][H*W][2*Cp], Cp = O rounded up to 128, hi at [0,Cp), lo at [Cp,2Cp), padding
+ * channels zero; 1024-byte aligned -- so conv_corr[0] + BatchNorm + ReLU hand conv_corr[3] its operand with no fp32 round trip. */
+int emip_conv_corr_fwd_tokens(const float* f0, const float* f1, const void* w_prep, const float* bias, const float* ep_scale,
+                              const float* ep_shift, int relu, int layout, float* out, void* tok_out, void* workspace,
+                              size_t ws_bytes, int B, int C, int H, int W, int O, void* stream);
+
 /* Backward of emip_conv_corr_fwd on the tensor cores: df0, df1 [B,C,H,W], dweight [O,H*W,3,3], dbias [O] (NULL = not
  * wanted) from dout [B,O,H,W]; weight = the fp32 parameter, w_prep = its prepared copy.  Five split-bf16 GEMMs
  * (csrc/gemm_tc.cu); workspace of emip_conv_corr_bwd_workspace() bytes, 1024-byte aligned. */
@@ -416,6 +423,11 @@ size_t emip_conv3x3_workspace(int B, int Cin, int H, int W);
 int emip_conv3x3_fwd(const float* x0, int C0, int layout0, const float* x1, int C1, int layout1, const void* w_prep,
                      const float* scale, const float* shift, int relu, float* out, void* workspace, size_t ws_bytes, int B,
                      int H, int W, int O, void* stream);
+
+/* emip_conv3x3_fwd on an input that already is the token-major bf16 hi | lo operand [B][H*W][2*Cp_in] (Cp_in = Cin rounded up to
+ * 64; what emip_conv_corr_fwd_tokens writes): no split pass, no workspace. */
+int emip_conv3x3_fwd_tokens(const void* tok, int Cin, int Cp_in, const void* w_prep, const float* scale, const float* shift, int relu,
+                            float* out, int B, int H, int W, int O, void* stream);
 
 /* out[b][n][c] = x[b][c][n] + pos[c][n] (pos NULL: plain transpose): gmflow.py:114 feature_add_position (utils.py:66-86; pos
  * = the window-tiled sine embedding) + transformer.py:439-440 (flatten / permute to token rows) in one pass. */

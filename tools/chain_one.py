@@ -16,7 +16,11 @@ m = MotionChain().to(dev).eval()
 gm = 2.2 * torch.randn(2 * pairs, 128, 44, 44, device=dev)
 seg = torch.randn(2 * pairs, 128, 44, 44, device=dev)
 with torch.no_grad():
-    for _ in range(passes):
+    m(gm, seg)                                   # warm-up: prepared weights, function attributes (not profiled with --profile-from-start off)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for _ in range(passes - 1):
         m(gm, seg)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print("done", pairs, passes)

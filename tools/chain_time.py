@@ -58,8 +58,7 @@ def stage_times(m, gm, seg, iters=10):
         mask = timed("upsampler conv1x1", lambda: ch.conv1x1_cn(hid, up[2].weight, up[2].bias))
         timed("f4 convex upsample", lambda: upsample_flow_convex(flow, mask, 8))
         cc = m.conv_corr
-        c1 = timed("f1 conv_corr[0] + bn + relu", lambda: ch.conv_corr_head(x, B, H, W, cc[0], _prepared_weight(cc[0].weight)[1], bn_scale, bn_shift))
-        corr = timed("conv_corr[3] conv3x3", lambda: ch.conv3x3(c1, 1, None, 1, w_c3, 128, H, W, shift=cc[3].bias.detach()))
+        corr = timed("conv_corr: f1 + bn + relu -> token operand -> conv3x3", lambda: ch.conv_corr_fused(x, B, H, W, cc[0], _prepared_weight(cc[0].weight)[1], bn_scale, bn_shift, cc[3], w_c3))
         timed("a4 injector1", lambda: m.injector1(seg[:B], corr))
 
     with torch.no_grad():
