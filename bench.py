@@ -39,6 +39,7 @@ GM_STD, SEG_STD = 2.2, 1.0          # feature scales measured inside the model (
 N_INPUT_SETS = 4                    # rotated: inputs + the step's intermediates exceed the 126 MB L2 at every shard size
 CPU_SAMPLE_PAIRS = 2                # bounded sample of the c3 batch for the CPU arms
 # K1 sub-record (BASELINE.json configs[1], "c2")
+NCU_MLP_DRAM_BYTES, NCU_MLP_ROWS = 2.592e9, 247808     # measured once per kernel change with ncu (profiles/)
 K1_B = 16
 K1_ALG_FLOP_PER_PAIR = 2.0 * N * N * C + 8.0 * N * N          # S counted once
 K1_EXEC_MMA_FLOP_PER_PAIR = 2.0 * N * N * C * 3 * 2           # bf16 hi/lo split (x3), both directions (x2)
@@ -442,7 +443,11 @@ def dominant_kernel_roofline(torch, chain, per, dev, pk):
     alg = 2.0 * Lr * (256 * 1024 + 1024 * 128)
     ach = alg / (ms * 1e-3) / 1e12
     return {"kernel": "gemm_tc_kernel (FeatureTransformer MLP call: 2 launches + operand split)", "bound": "tensor", "achieved": ach,
-            "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+            "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"],
+            "traffic": NCU_MLP_DRAM_BYTES * Lr / NCU_MLP_ROWS, "traffic_unit": "bytes per call",
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the two launches at 247808 rows "
+                              "(profiles/r2j_gemm_tc_transformer_full.txt: mlp[0] 0.255 GB read + 0.961 GB written, mlp[2] 1.146 + 0.230), "
+                              "scaled by rows; algorithmic: 0.25 + 1.02 | 1.02 + 0.13 (residual) + 0.13 (out) + 0.13 (hi | lo out) GB",
             "peak_source": pk["src"] + " burst bf16 (cuBLAS)", "call_ms": ms, "rows": Lr,
             "executed_mma_tflops": 3 * ach, "executed_mma_frac": 3 * ach / pk["tf"],
             "note": "achieved = algorithmic 2*L*(256*1024 + 1024*128) FLOP / time; executed = x3 (bf16 hi/lo split keeps fp32 accuracy)"}
