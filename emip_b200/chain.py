@@ -26,7 +26,6 @@ checkpoint loads with ``strict=False`` key filtering exactly as test.py:85-89 do
 """
 import ctypes
 import math
-import weakref
 
 import torch
 import torch.nn as nn

@@ -6,7 +6,6 @@ computed here).  Per pyramid entry: a3 ``flow_warp`` of each frame by the flow t
 flows, f3b fused photometric term, both directions averaged.  ``dropin.install()`` gives the reference's own class the same
 kernels; this module is the stand-alone form used by ``MotionChain``'s training step and by the benchmarks.
 """
-import torch
 import torch.nn.functional as F
 
 from .photometric import photometric_loss
