@@ -278,9 +278,9 @@ def main():
     value = GLOBAL_PAIRS / (ms_step / 1e3)
 
     # ---------------- e2e: host buffers; H2D of the step's features + chain + D2H of its results inside the timed region ----
-    # Double-buffered: the H2D of step i+1 and the D2H of step i-1 (two copy streams) overlap the kernels of step i; the host
-    # waits for every step's results before it reuses that step's buffers.
-    nb = 2
+    # Triple-buffered: the H2D of step i+1 and the D2H of step i-1 (two copy streams) overlap the kernels of step i; the host reads
+    # every step's results, two steps behind the launches, before that step's buffers are reused.
+    nb = 3                                                              # buffers in flight: H2D(i+1) | kernels(i) | D2H(i-1), host reads step i-2
     pin = lambda t_: torch.empty(t_.shape, dtype=t_.dtype).pin_memory().copy_(t_)
     h_in = [(pin(sets[j][0].cpu()), pin(sets[j][1].cpu())) for j in range(nb)]
     with torch.no_grad():
@@ -328,9 +328,10 @@ def main():
                 for k_, idx in enumerate(res_idx):
                     h_out[j][k_].copy_(outs[j][idx], non_blocking=True)
                 d2h_done[j].record(d2h_stream)
-            if i >= 1:
-                d2h_done[(i - 1) % nb].synchronize()  # the caller reads step i-1's results on the host
-        d2h_done[(n - 1) % nb].synchronize()
+            if i >= nb - 1:
+                d2h_done[(i - (nb - 1)) % nb].synchronize()  # the caller reads step i-2's results on the host
+        for k_ in range(max(0, n - (nb - 1)), n):
+            d2h_done[k_ % nb].synchronize()
 
     with torch.no_grad():
         for ev in comp_done + d2h_done:
