@@ -17,7 +17,7 @@ using namespace tc;
 
 constexpr int KCH = GEMM_TC_KCH;
 constexpr int A_BYTES = GEMM_TC_A_BYTES;
-constexpr int EPI_STAGE_BYTES = 8 * 32 * 33 * 4;   // eight epilogue warps x [32 rows][33 words]
+constexpr int EPI_STAGE_BYTES = 8 * 32 * 128;      // eight epilogue warps x [32 rows][128 B] (swizzled: tc_common.cuh::stg_swz)
 constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA producer; 5: UMMA issuer
 
 // exact-GELU x Phi(x) for the epilogue (where the instruction count is the critical path): Phi through the rational
@@ -223,10 +223,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // epilogues run side by side (r3: with K <= 256 the epilogue, not the MMA loop, bounds a tile).  A warp reads the TMEM
     // lane quarter warp % 4.
     const int grp = warp >= 6 ? 1 : 0, qw = warp & 3;
-    // warp-private staging tile [32 rows][33 words] behind the barriers: a thread's 32 accumulator columns go in as a row,
-    // come out as 4 rows x 128 B per warp store (r3h: the row-per-thread stores touched 32 lines per instruction)
+    // warp-private staging tile [32 rows][128 B] behind the barriers (16-byte pieces swizzled, tc_common.cuh::stg_swz): a thread's
+    // 32 accumulator columns go in as a row, come out as 4 rows x 128 B per warp store (r3h: the row-per-thread stores touched
+    // 32 lines per instruction)
     uint32_t* stg = reinterpret_cast<uint32_t*>(smem + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 15) & ~15)) +
-                    (grp * 4 + qw) * (32 * 33);
+                    (grp * 4 + qw) * (32 * 32);
     uint32_t it = grp;
     long long w_accf = 0, n_tiles = 0;
     const long long t_begin = clock64();
@@ -274,6 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       // (r2k role profile: one dependent load per row segment made the epilogue 38.7 k cycles per tile -- eight HBM
       // round trips per chunk in sequence -- and the whole GEMM epilogue-bound)
       const int ecc = (lane & 7) * 4;
+      const uint32_t s_stg = smem_u32(stg), wr_base = s_stg + lane * 128, wr_key = stg_swz(lane);      // staging: see EPI 3
       float4 qn[8];
       auto load_res = [&](int c0) {
 #pragma unroll
@@ -315,8 +317,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_ld32_async(taddr + c0, r);
         tmem_wait(r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __float_as_uint((__uint_as_float(r[i]) - mean) * rstd);
+        for (int c = 0; c < 8; ++c)
+          sts128(wr_base + ((c ^ wr_key) << 4), make_float4((__uint_as_float(r[4 * c]) - mean) * rstd, (__uint_as_float(r[4 * c + 1]) - mean) * rstd,
+                                                            (__uint_as_float(r[4 * c + 2]) - mean) * rstd, (__uint_as_float(r[4 * c + 3]) - mean) * rstd));
         __syncwarp();
+        float4 v8[8];
+#pragma unroll
+        for (int it2 = 0; it2 < 8; ++it2) {
+          const uint32_t rr = it2 * 4 + (lane >> 3);
+          v8[it2] = lds128(s_stg + rr * 128 + (((lane & 7) ^ stg_swz(rr)) << 4));
+        }
         const int cc = ecc;
         const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0 + cc));
         const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0 + cc));
@@ -328,9 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int it2 = 0; it2 < 8; ++it2) {
           const int rr = it2 * 4 + (lane >> 3);
           const int grow = mt * TM + qw * 32 + rr;
-          const uint32_t* sp = stg + rr * 33 + cc;
-          float4 v = make_float4(__uint_as_float(sp[0]) * g.x + be.x, __uint_as_float(sp[1]) * g.y + be.y,
-                                 __uint_as_float(sp[2]) * g.z + be.z, __uint_as_float(sp[3]) * g.w + be.w);
+          float4 v = make_float4(v8[it2].x * g.x + be.x, v8[it2].y * g.y + be.y, v8[it2].z * g.z + be.z, v8[it2].w * g.w + be.w);
           if (grow < p.M) {
             v.x += qc[it2].x; v.y += qc[it2].y; v.z += qc[it2].z; v.w += qc[it2].w;
             if (p.y != nullptr) *reinterpret_cast<float4*>(p.y + (size_t)grow * p.ldy + c0 + cc) = v;
@@ -350,27 +358,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if constexpr (EPI == 3) {
       // the tile as the bf16 hi | lo A operand of the next GEMM (optionally through the exact GELU): the fp32 tensor never exists
       const int n0 = nt * p.n_tile;
-      __nv_bfloat16* gh = p.g_hi + (size_t)row * p.ldg + n0;
-      __nv_bfloat16* gl = p.g_lo + (size_t)row * p.ldg + n0;
-      // out_split == 3: the four rows this lane stores per chunk go to the same slots for every chunk: one map lookup per tile
+      // The four rows this lane stores per chunk (rows it2 * 8 + lane / 4 of the warp's 32, 16 bytes = 8 columns each): their
+      // addresses are the same for every chunk -- one computation (out_split == 3: one map lookup) per tile
       __nv_bfloat16* wrow[4] = {nullptr, nullptr, nullptr, nullptr};
-      if (p.out_split == 3) {
+      ptrdiff_t lo_delta = 128;
 #pragma unroll
-        for (int it2 = 0; it2 < 4; ++it2) {
-          const int grow = mt * TM + qw * 32 + it2 * 8 + (lane >> 2);
-          if (grow < p.M) {
+      for (int it2 = 0; it2 < 4; ++it2) {
+        const int grow = mt * TM + qw * 32 + it2 * 8 + (lane >> 2);
+        if (grow < p.M) {
+          if (p.out_split == 3) {                         // row (image, pixel) -> its slot in the window-ordered operand
             const int img = grow / p.npix, pix = grow - img * p.npix;
             const int2 m = __ldg(p.rowmap + pix);
             int im2 = img + p.img_shift;
             if (im2 >= p.n_img) im2 -= p.n_img;
             __nv_bfloat16* dbase = nt == 0 ? p.split_dst[0] : nt == 1 ? p.split_dst[1] : nt == 2 ? p.split_dst[2] : p.split_dst[3];
             wrow[it2] = dbase + ((size_t)m.x + (size_t)im2 * m.y) * 256 + (lane & 3) * 8;
+          } else {
+            wrow[it2] = p.g_hi + (size_t)grow * p.ldg + n0 + (lane & 3) * 8;
           }
         }
       }
+      if (p.out_split != 3) lo_delta = p.g_lo - p.g_hi;
+      // staging tile (tc_common.cuh::stg_swz): this lane's row goes in as eight 16-byte pieces (hi 0..3 | lo 4..7), comes out as
+      // piece lane % 4 of hi and of lo of the rows above: 8 STS.128 + 8 LDS.128 per chunk, no bank conflicts (r4a: the [32][33]
+      // word tile with scalar generic LD / ST was 50 % of the epilogue warps' samples -- 64 instructions per chunk, the reads 2-way
+      // conflicted, every store waiting on the long scoreboard)
+      const uint32_t s_stg = smem_u32(stg);
+      const uint32_t wr_base = s_stg + lane * 128, wr_key = stg_swz(lane), rd_key = stg_swz(lane >> 2);
+      const uint32_t rd_hi = s_stg + (lane >> 2) * 128 + (((lane & 3) ^ rd_key) << 4);
+      const uint32_t rd_lo = s_stg + (lane >> 2) * 128 + ((((lane & 3) + 4) ^ rd_key) << 4);
       // one 32-column chunk: r = the accumulator chunk just read from TMEM
       auto chunk = [&](uint32_t (&r)[32], const int c0) {
-        if (row < p.M && n0 + c0 < p.N) {
+        if (n0 + c0 >= p.N) return;                            // warp-uniform
+        if (row < p.M) {
           uint32_t hi[16], lo[16];
           float v[32];
 #pragma unroll
@@ -387,41 +407,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                                            v[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
           }
-          if (p.epi_stage) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { stg[lane * 33 + i] = hi[i]; stg[lane * 33 + 16 + i] = lo[i]; }
-          } else {
-            uint4* dh = reinterpret_cast<uint4*>(gh + c0);
-            uint4* dl = reinterpret_cast<uint4*>(gl + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-            }
+          for (int c = 0; c < 4; ++c) {
+            sts128u(wr_base + ((c ^ wr_key) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            sts128u(wr_base + (((c + 4) ^ wr_key) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
           }
         }
-        if (p.epi_stage && n0 + c0 < p.N) {                 // warp-uniform
-          __syncwarp();
+        __syncwarp();
+        uint4 vh[4], vl[4];
 #pragma unroll
-          for (int it2 = 0; it2 < 4; ++it2) {
-            const int rr = it2 * 8 + (lane >> 2), w0 = (lane & 3) * 4;
-            const int grow = mt * TM + qw * 32 + rr;
-            const uint32_t* sp = stg + rr * 33 + w0;
-            const uint4 vh = make_uint4(sp[0], sp[1], sp[2], sp[3]), vl = make_uint4(sp[16], sp[17], sp[18], sp[19]);
-            if (grow < p.M) {
-              if (p.out_split == 3) {                           // row (image, pixel) -> its slot in the window-ordered operand
-                __nv_bfloat16* d = wrow[it2] + c0;
-                *reinterpret_cast<uint4*>(d) = vh;
-                *reinterpret_cast<uint4*>(d + 128) = vl;
-              } else {
-              const size_t off = (size_t)grow * p.ldg + n0 + c0 + w0 * 2;
-              *reinterpret_cast<uint4*>(p.g_hi + off) = vh;
-              *reinterpret_cast<uint4*>(p.g_lo + off) = vl;
-              }
-            }
+        for (int it2 = 0; it2 < 4; ++it2) { vh[it2] = lds128u(rd_hi + it2 * 1024); vl[it2] = lds128u(rd_lo + it2 * 1024); }
+#pragma unroll
+        for (int it2 = 0; it2 < 4; ++it2) {
+          if (wrow[it2] != nullptr) {
+            *reinterpret_cast<uint4*>(wrow[it2] + c0) = vh[it2];
+            *reinterpret_cast<uint4*>(wrow[it2] + c0 + lo_delta) = vl[it2];
           }
-          __syncwarp();
         }
+        __syncwarp();
       };
       // (r2u: keeping the next chunk's TMEM read in flight while this one is converted did not help -- the GELU / split
       // epilogue is issue- and dependency-bound, not TMEM-latency-bound -- and cost the 256 -> 1024 layer 10 %: not kept)
@@ -436,6 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       float* o = p.y + (size_t)b * p.y_stride_b + (size_t)row * p.ldy + n0;
       const float* rs = p.res ? p.res + (size_t)b * p.res_stride_b + (size_t)row * p.ldr + n0 : nullptr;
       const float rb = (p.bias != nullptr && row < p.M) ? __ldg(p.bias + row) : 0.f;      // per-row bias (linear layers)
+      const uint32_t s_stg = smem_u32(stg), wr_base = s_stg + lane * 128, wr_key = stg_swz(lane);      // staging: see EPI 3
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         const int n = min(32, p.N - n0 - c0);
         const float* yb = p.y + (size_t)b * p.y_stride_b + n0 + c0;
@@ -461,14 +465,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias_n + n0 + c0 + i));
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __float_as_uint(__uint_as_float(r[i]) + rb);
+          for (int c = 0; c < 8; ++c)
+            sts128(wr_base + ((c ^ wr_key) << 4), make_float4(__uint_as_float(r[4 * c]) + rb, __uint_as_float(r[4 * c + 1]) + rb,
+                                                              __uint_as_float(r[4 * c + 2]) + rb, __uint_as_float(r[4 * c + 3]) + rb));
           __syncwarp();
+          float4 v8[8];
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const uint32_t rr = it2 * 4 + (lane >> 3);
+            v8[it2] = lds128(s_stg + rr * 128 + (((lane & 7) ^ stg_swz(rr)) << 4));
+          }
 #pragma unroll
           for (int it2 = 0; it2 < 8; ++it2) {
             const int rr = it2 * 4 + (lane >> 3), cc = (lane & 7) * 4;
             const int grow = mt * TM + qw * 32 + rr;
-            const uint32_t* sp = stg + rr * 33 + cc;
-            float4 v = make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
+            float4 v = v8[it2];
             if (grow < p.M) {
               if (rb0) { v.x += q8[it2].x; v.y += q8[it2].y; v.z += q8[it2].z; v.w += q8[it2].w; }
               *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)grow * p.ldy + cc) = v;
@@ -510,6 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const float efl = p.ep_relu ? 0.f : -INFINITY;
       float* o = p.out + ((size_t)b * p.M + row) * npix + px0;
       if (p.tok_hi != nullptr) {
+        const uint32_t s_stg = smem_u32(stg);
         // token-major bf16 hi | lo output: transpose each [32 channels x 32 pixels] chunk through the warp's staging tile
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
           uint32_t r[32];
@@ -525,16 +537,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int i = 16; i < 32; ++i) r[i] = 0u;
           }
+          // staging tile rows = pixels (tc_common.cuh::stg_swz): lane = channel writes word `lane` of every pixel row
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            stg[i * 33 + lane] = row < p.M ? __float_as_uint(fmaxf(fmaf(__uint_as_float(r[i]), esc, bias), efl)) : 0u;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_stg + i * 128 + ((((uint32_t)lane >> 2) ^ stg_swz(i)) << 4) + (lane & 3) * 4),
+                         "r"(row < p.M ? __float_as_uint(fmaxf(fmaf(__uint_as_float(r[i]), esc, bias), efl)) : 0u)
+                         : "memory");
           __syncwarp();
           const int cc = (lane & 7) * 4;
+          float4 v8[8];
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const uint32_t pr = it2 * 4 + (lane >> 3);
+            v8[it2] = lds128(s_stg + pr * 128 + (((lane & 7) ^ stg_swz(pr)) << 4));
+          }
 #pragma unroll
           for (int it2 = 0; it2 < 8; ++it2) {
             const int pr = it2 * 4 + (lane >> 3);                      // pixel of the chunk
-            const uint32_t* sp = stg + pr * 33 + cc;
-            const float v0 = __uint_as_float(sp[0]), v1 = __uint_as_float(sp[1]), v2 = __uint_as_float(sp[2]), v3 = __uint_as_float(sp[3]);
+            const float v0 = v8[it2].x, v1 = v8[it2].y, v2 = v8[it2].z, v3 = v8[it2].w;
             if (c0 + pr < min(p.n_tile, nvalid)) {
               const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
               const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);

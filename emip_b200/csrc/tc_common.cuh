@@ -177,6 +177,19 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Warp-private epilogue staging tile: 32 rows x 128 B, the 16-byte piece c (0..7) of row r at piece c ^ stg_swz(r).  Eight
+// consecutive rows have eight different keys, so a row-per-lane 16-byte store is conflict-free (each quarter warp covers all 32
+// banks); rows r, r + 1 (r even) differ in bit 2, so a quarter warp reading pieces 0..3 of both rows is conflict-free as well,
+// and so is one reading all eight pieces of one row.
+__device__ __forceinline__ uint32_t stg_swz(uint32_t r) { return ((r & 1u) << 2) | ((r >> 1) & 3u); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
