@@ -52,11 +52,35 @@ constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
+constexpr int MAXSEG = 3;
 struct AParams {
   AttnTcArgs a;
   float inv_sqrt_c;
   unsigned long long* prof;   // optional [gridDim.x][16] cycle counters (emip_attn_tc_set_profile_buffer)
+  // problem sets of the launch (set 0 = the main arguments): items of set s are [sum of seg_items[< s], + seg_items[s])
+  int nseg, seg_items[MAXSEG], seg_nq[MAXSEG], seg_nk[MAXSEG], seg_prob0[MAXSEG];      // seg_prob0 = blk0 * win.B
 };
+struct AMaps { CUtensorMap q[MAXSEG], k[MAXSEG], v[MAXSEG]; };
+
+// item -> (set, problem, row tile, key split) and the set's sizes
+struct AItem {
+  int seg, prob, rt, ks, nq, nk, nkt, kb, ke;
+};
+__device__ __forceinline__ AItem locate_item(const AParams& ap, int item, int ns) {
+  AItem r;
+  r.seg = 0;
+  while (r.seg + 1 < ap.nseg && item >= ap.seg_items[r.seg]) { item -= ap.seg_items[r.seg]; ++r.seg; }
+  r.nq = ap.seg_nq[r.seg];
+  r.nk = ap.seg_nk[r.seg];
+  const int nrt = (r.nq + TM - 1) / TM;
+  r.nkt = (r.nk + TN - 1) / TN;
+  r.ks = item % ns;
+  r.rt = (item / ns) % nrt;
+  r.prob = item / (ns * nrt);
+  r.kb = r.ks * r.nkt / ns;
+  r.ke = (r.ks + 1) * r.nkt / ns;
+  return r;
+}
 
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -80,8 +104,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AParams ap) {
+attn_fwd_tc_kernel(const __grid_constant__ AMaps maps, const __grid_constant__ AParams ap) {
   const AttnTcArgs& p = ap.a;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -96,11 +119,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nrt = (p.nq + TM - 1) / TM;
-  const int nkt = (p.nk + TN - 1) / TN;
-  // an item is (problem, row tile, key split): split ks covers key tiles [ks*nkt/ns, (ks+1)*nkt/ns)
+  // an item is (problem set, problem, row tile, key split): split ks covers key tiles [ks*nkt/ns, (ks+1)*nkt/ns)
   const int ns = p.ksplit > 1 ? p.ksplit : 1;
-  const int n_items = p.nb * nrt * ns;
+  int n_items = 0;
+  for (int s = 0; s < ap.nseg; ++s) n_items += ap.seg_items[s];
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -138,24 +160,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
-      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
+      const AItem w = locate_item(ap, item, ns);
+      const int rt = w.rt, prob = w.prob, kb = w.kb, ke = w.ke;
+      const CUtensorMap* map_q = &maps.q[w.seg];
+      const CUtensorMap* map_k = &maps.k[w.seg];
+      const CUtensorMap* map_v = &maps.v[w.seg];
       mbar_wait(q_empty, (it & 1) ^ 1);
       if (leader) {
         mbar_expect_tx(q_full, 4 * CHUNK_BYTES);
-        for (int c = 0; c < 4; ++c) tma_load_3d(sbase + OFF_Q + c * CHUNK_BYTES, &map_q, q_full, c * CH_ELEMS, rt * TM, prob);
+        for (int c = 0; c < 4; ++c) tma_load_3d(sbase + OFF_Q + c * CHUNK_BYTES, map_q, q_full, c * CH_ELEMS, rt * TM, prob);
       }
       // ring order = consumption order of the issuer: K(0), then per tile { K(t+1), V(t) }
-      for (int c = 0; c < 4; ++c) push(&map_k, c * CH_ELEMS, kb * TN, prob);
+      for (int c = 0; c < 4; ++c) push(map_k, c * CH_ELEMS, kb * TN, prob);
       for (int t = kb; t < ke; ++t) {
         if (t + 1 < ke)
-          for (int c = 0; c < 4; ++c) push(&map_k, c * CH_ELEMS, (t + 1) * TN, prob);
+          for (int c = 0; c < 4; ++c) push(map_k, c * CH_ELEMS, (t + 1) * TN, prob);
         if (p.v_chn)
           for (int c = 0; c < 4; ++c)     // channel-major V: hi keys[0:64], hi keys[64:128], lo keys[0:64], lo keys[64:128]
-            push(&map_v, t * TN + (c & 1) * CH_ELEMS, (c >> 1) * 128, prob);
+            push(map_v, t * TN + (c & 1) * CH_ELEMS, (c >> 1) * 128, prob);
         else
           for (int c = 0; c < 4; ++c)     // token-major V like K: hi ch[0:64], hi ch[64:128], lo ch[0:64], lo ch[64:128]
-            push(&map_v, c * CH_ELEMS, t * TN, prob);
+            push(map_v, c * CH_ELEMS, t * TN, prob);
       }
     }
     __syncwarp();
@@ -164,8 +189,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0, it = 0, tile = 0;
-    const int n_tail = ((p.nk - (nkt - 1) * TN) + 15) & ~15;
-    const uint32_t idesc_full = make_idesc(TN), idesc_tail = make_idesc(n_tail);
+    const uint32_t idesc_full = make_idesc(TN);
+    uint32_t idesc_tail = idesc_full;                      // per item: the set's last key tile, rounded up to 16 columns
     const uint64_t qd = make_kmajor_sw128_desc(sbase + OFF_Q);
     const uint32_t t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
     long long w_se = 0, w_rf = 0, w_pf = 0, w_oe = 0, w_qf = 0;
@@ -239,8 +264,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int ks = item % ns;
-      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
+      const AItem w = locate_item(ap, item, ns);
+      const int kb = w.kb, ke = w.ke, nkt = w.nkt;
+      idesc_tail = make_idesc(((w.nk - (nkt - 1) * TN) + 15) & ~15);
       prof_add<PROF>(w_qf, mbar_wait(q_full, it & 1));
       tc_fence_after();
       // Q is read by UMMA-1 only: it is handed back as soon as the LAST S tile of the item has been issued, so the
@@ -275,10 +301,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     long long w_sf = 0, t_ld = 0, t_x = 0, t_e = 0, w_pe = 0, t_st = 0, w_of = 0;
     const long long t_begin = PROF ? clock64() : 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int ks = item % ns, rt = (item / ns) % nrt, prob = item / (ns * nrt);
-      const int kb = ks * nkt / ns, ke = (ks + 1) * nkt / ns;
+      const AItem w = locate_item(ap, item, ns);
+      const int ks = w.ks, rt = w.rt, prob = w.prob, kb = w.kb, ke = w.ke, nq = w.nq, nk = w.nk;
+      const int wprob = prob + ap.seg_prob0[w.seg];        // window map: block index counted over all sets
       const int row = rt * TM + quarter * 32 + lane;
-      const bool row_ok = row < p.nq;
+      const bool row_ok = row < nq;
       float mref = -INFINITY, l = 0.f;                     // reference exponent (log2 units), my part of the row sum
       for (int kt = kb; kt < ke; ++kt, ++tile) {
         const int buf = tile & 1;
@@ -291,7 +318,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_fence_before();
         mbar_arrive(s_empty(buf));                          // my part of the S tile is in registers
         if (PROF) { const long long c1 = clock64(); t_ld += c1 - c0; c0 = c1; }
-        const int nv = p.nk - (kt * TN + cb);               // valid columns of my part (warp-uniform)
+        const int nv = nk - (kt * TN + cb);                 // valid columns of my part (warp-uniform)
         if (nv < 32) {                                      // key tail: masked scores = -inf -> max ignores them, P = 0
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = (i < nv) ? r[i] : 0xff800000u;
@@ -364,18 +391,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           OUT = p.out + (size_t)prob * p.out_stride_b;
           sc = 1.0f / l_row;
           if (part == 0 && row_ok && p.lse != nullptr)
-            p.lse[p.win.enabled ? p.win.pixel(prob, row) : (size_t)prob * p.nq + row] = mref * LN2 + logf(l_row);
+            p.lse[p.win.enabled ? p.win.pixel(wprob, row) : (size_t)prob * nq + row] = mref * LN2 + logf(l_row);
         } else {
-          OUT = p.part_o + ((size_t)ks * p.nb + prob) * p.nq * 128;
+          OUT = p.part_o + ((size_t)ks * p.nb + prob) * nq * 128;
           sc = 1.0f;
-          if (part == 0 && row_ok) p.part_ml[((size_t)ks * p.nb + prob) * p.nq + row] = make_float2(mref, l_row);
+          if (part == 0 && row_ok) p.part_ml[((size_t)ks * p.nb + prob) * nq + row] = make_float2(mref, l_row);
         }
         if (row_ok) {
           if (p.out_layout == EMIP_LAYOUT_NC) {
             size_t orow = (size_t)row;
             if (p.win.enabled) {                          // scatter: token `row` of block (prob / B) of image (prob % B)
               OUT = p.out;
-              orow = p.win.pixel(prob, row);
+              orow = p.win.pixel(wprob, row);
             }
             if (p.out != nullptr || ns != 1) {
             float4* dst = reinterpret_cast<float4*>(OUT + orow * 128 + cb);
@@ -404,7 +431,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) OUT[(size_t)(cb + i) * p.nq + row] = __uint_as_float(r[i]) * sc;
+            for (int i = 0; i < 32; ++i) OUT[(size_t)(cb + i) * nq + row] = __uint_as_float(r[i]) * sc;
           }
         }
       }
@@ -461,25 +488,45 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   if (a.ksplit > nkt) { emip_set_error("attn_tc_fwd: ksplit %d exceeds the %d key tiles", a.ksplit, nkt); return EMIP_EINVAL; }
   if (a.win.enabled && (a.ksplit > 1 || a.out_layout != EMIP_LAYOUT_NC)) { emip_set_error("attn_tc_fwd: the window scatter needs ksplit == 1 and the NC layout"); return EMIP_EINVAL; }
   if (a.ksplit > 1 && (a.part_o == nullptr || a.part_ml == nullptr)) { emip_set_error("attn_tc_fwd: ksplit needs partial buffers"); return EMIP_EINVAL; }
-  CUtensorMap mq, mk, mv;
-  int rc;
-  if ((rc = make_bf16_map(&mq, a.q_split, 256, (uint64_t)a.nq, (uint64_t)a.nb, 512, (uint64_t)a.nq * 512))) return rc;
-  if ((rc = make_bf16_map(&mk, a.k_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
-  if (a.v_chn) {
-    const uint64_t ld = ((uint64_t)a.nk + 7) / 8 * 8;     // = pair_bwd_tc_chn_ld
-    if ((rc = make_bf16_map(&mv, a.v_split, (uint64_t)a.nk, 256, (uint64_t)a.nb, ld * 2, ld * 2 * 256))) return rc;
-  } else if ((rc = make_bf16_map(&mv, a.v_split, 256, (uint64_t)a.nk, (uint64_t)a.nb, 512, (uint64_t)a.nk * 512))) return rc;
-  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<false>), SMEM_BYTES)) return rc__;
-  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<true>), SMEM_BYTES)) return rc__;
+  if (a.n_more < 0 || a.n_more > MAXSEG - 1 || (a.n_more > 0 && (!a.win.enabled || a.ksplit > 1 || a.v_chn))) {
+    emip_set_error("attn_tc_fwd: further problem sets need the window scatter, ksplit == 1 and token-major values");
+    return EMIP_EINVAL;
+  }
+  AMaps maps;
   AParams ap;
   ap.a = a;
   ap.inv_sqrt_c = 1.0f / a.sqrt_c;
   ap.prof = g_attn_prof;
-  const int nrt = (a.nq + TM - 1) / TM;
-  long long grid = (long long)a.nb * nrt * (a.ksplit > 1 ? a.ksplit : 1);
+  ap.nseg = 1 + a.n_more;
+  int rc;
+  long long grid = 0;
+  for (int s = 0; s < MAXSEG; ++s) {
+    const bool used = s < ap.nseg;
+    const void* q = s == 0 ? a.q_split : used ? a.more[s - 1].q_split : a.q_split;
+    const void* k = s == 0 ? a.k_split : used ? a.more[s - 1].k_split : a.k_split;
+    const void* v = s == 0 ? a.v_split : used ? a.more[s - 1].v_split : a.v_split;
+    const int nb = s == 0 ? a.nb : used ? a.more[s - 1].nb : a.nb, nq = s == 0 ? a.nq : used ? a.more[s - 1].nq : a.nq;
+    const int nk = s == 0 ? a.nk : used ? a.more[s - 1].nk : a.nk;
+    if (used && (nb < 1 || !attn_tc_supported(nq, nk, 128))) { emip_set_error("attn_tc_fwd: unsupported shape in problem set %d", s); return EMIP_ENOSYS; }
+    if ((rc = make_bf16_map(&maps.q[s], q, 256, (uint64_t)nq, (uint64_t)nb, 512, (uint64_t)nq * 512))) return rc;
+    if ((rc = make_bf16_map(&maps.k[s], k, 256, (uint64_t)nk, (uint64_t)nb, 512, (uint64_t)nk * 512))) return rc;
+    if (a.v_chn) {
+      const uint64_t ld = ((uint64_t)nk + 7) / 8 * 8;     // = pair_bwd_tc_chn_ld
+      if ((rc = make_bf16_map(&maps.v[s], v, (uint64_t)nk, 256, (uint64_t)nb, ld * 2, ld * 2 * 256))) return rc;
+    } else if ((rc = make_bf16_map(&maps.v[s], v, 256, (uint64_t)nk, (uint64_t)nb, 512, (uint64_t)nk * 512))) return rc;
+    const long long items = used ? (long long)nb * ((nq + TM - 1) / TM) * (a.ksplit > 1 ? a.ksplit : 1) : 0;
+    if (items > 0x3fffffffLL) { emip_set_error("attn_tc_fwd: too many items"); return EMIP_EINVAL; }
+    ap.seg_items[s] = (int)items;
+    ap.seg_nq[s] = nq;
+    ap.seg_nk[s] = nk;
+    ap.seg_prob0[s] = (s > 0 && used) ? a.more[s - 1].blk0 * a.win.B : 0;
+    grid += items;
+  }
+  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<false>), SMEM_BYTES)) return rc__;
+  if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<true>), SMEM_BYTES)) return rc__;
   if (grid > emip_num_sms()) grid = emip_num_sms();
-  if (ap.prof) attn_fwd_tc_kernel<true><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, ap);   // diagnostics build
-  else attn_fwd_tc_kernel<false><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, ap);
+  if (ap.prof) attn_fwd_tc_kernel<true><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(maps, ap);   // diagnostics build
+  else attn_fwd_tc_kernel<false><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(maps, ap);
   EMIP_CHECK_LAUNCH("attn_tc_fwd");
   return EMIP_OK;
 }

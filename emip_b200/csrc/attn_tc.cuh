@@ -38,6 +38,12 @@ struct AttnTcArgs {
   // optional (ksplit == 1, NC layout): the output rows as bf16 hi / lo (rows out_ld elements apart, same row order as `out`) --
   // the pre-split A operand of the merge GEMM (ft.cu); `out` may then be NULL
   void* out_hi; void* out_lo; int out_ld;
+  // optional: up to two MORE problem sets run by the same launch (window attention: the block groups of a shifted layer have
+  // different token counts; as three launches each ended in its own partial wave -- at 8 pairs 64 + 128 + 64 items on 148 SMs).
+  // Set i has its own operands and sizes; its problem p is block more[i].blk0 + p / win.B of image p % win.B.  Everything else is
+  // shared.  Needs win.enabled, ksplit == 1, v_chn == 0; list the sets with the most key tiles first (items are dealt round-robin).
+  int n_more;
+  struct More { const void* q_split; const void* k_split; const void* v_split; int nb, nq, nk, blk0; } more[2];
 };
 
 bool attn_tc_supported(int nq, int nk, int c);

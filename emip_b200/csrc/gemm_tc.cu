@@ -108,6 +108,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // EPI 2: gamma | beta (2 x 128 floats) behind the staging tiles -- read once per 32-column chunk by every epilogue warp (r4d:
+  // as __ldg in the chunk loop the pair sat on the long scoreboard in front of the first FFMA, ~20 % of the epilogue warps' samples)
+  const uint32_t s_gb = sbase + ((p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 15) & ~15) + EPI_STAGE_BYTES;
+  if constexpr (EPI == 2) {
+    if (threadIdx.x < 256) {
+      const float v = threadIdx.x < 128 ? __ldg(p.ln_gamma + threadIdx.x) : __ldg(p.ln_beta + threadIdx.x - 128);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_gb + threadIdx.x * 4), "f"(v) : "memory");
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,7 +134,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     decode(tile, nt, mt, b);
     for (int kc = 0; kc < p.kchunks; ++kc) {
       w_empty += mbar_wait(empty(stage), phase ^ 1);
-      if (leader) {
+      if (leader && (p.dbg & 2)) {
+        mbar_arrive(full(stage));                              // diagnostics (bit 3): no operand loads at all -- UMMA issue rate alone
+      } else if (leader) {
         const uint32_t sa = sbase + stage * p.stage_bytes;
         mbar_expect_tx(full(stage), 2 * A_BYTES + 2 * p.b_bytes);
         if (p.mode == 0) {
@@ -240,7 +251,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     ++n_tiles;
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * acc_cols);
-    if constexpr (EPI == 0) {
+    if (p.dbg & 1) {
+      // diagnostics only (emip_debug_gemm_wide_tiles bit 1): the accumulator is handed back unread
+    } else if constexpr (EPI == 0) {
       __nv_bfloat16* gh = p.g_hi + ((size_t)b * p.M + row) * 128;
       __nv_bfloat16* gl = p.g_lo + ((size_t)b * p.M + row) * 128;
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -328,8 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           v8[it2] = lds128(s_stg + rr * 128 + (((lane & 7) ^ stg_swz(rr)) << 4));
         }
         const int cc = ecc;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0 + cc));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0 + cc));
+        const float4 g = lds128(s_gb + (c0 + cc) * 4), be = lds128(s_gb + 512 + (c0 + cc) * 4);
         float4 qc[8];
 #pragma unroll
         for (int it2 = 0; it2 < 8; ++it2) qc[it2] = qn[it2];
@@ -726,7 +738,11 @@ unsigned split_w_blocks(int M, int Kp) { return (unsigned)(((long long)M * (Kp >
 
 static int g_gemm_wide_tiles = 0;   // r3c: with four accumulators 128-column tiles are as fast at 64 pairs and 3.5 % faster at 8
 // Diagnostics / tuning: 0 (default) = 128-column tiles (four TMEM accumulators) also for wide outputs, 1 = 256-column tiles for N >= 512.
-extern "C" void emip_debug_gemm_wide_tiles(int v) { g_gemm_wide_tiles = v ? 1 : 0; }
+static int g_gemm_dbg = 0;   // diagnostics: bits 1 and 3 of the switch below (tools/gemm_floor.py); results are garbage while set
+extern "C" void emip_debug_gemm_wide_tiles(int v) {
+  g_gemm_wide_tiles = (v & 1) ? 1 : 0;
+  g_gemm_dbg = ((v & 2) ? 1 : 0) | ((v & 8) ? 2 : 0);
+}
 static unsigned long long* g_gemm_prof = nullptr;
 // Diagnostics (tools/gemm_roles.py): device buffer of (SM count) x 8 cycle counters the next launches ADD to; NULL = off.
 extern "C" void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf) { g_gemm_prof = dev_buf; }
@@ -752,11 +768,12 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
     // (the ring runs on across tiles: with K = 128 a third stage prefetches the next tile's first chunk)
   }
   p.prof = g_gemm_prof;
+  p.dbg = g_gemm_dbg;
   const long long tiles = (long long)batch * p.n_mtiles * p.n_ntiles;
   EMIP_CHECK_ARG(tiles > 0 && tiles < 0x7fffffffLL, "gemm_tc: bad tile count");
   p.total_tiles = (int)tiles;
   const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
-  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0);
+  const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0) + (epi == 2 ? 1024 : 0);
   switch (epi) {
     case 0: gemm_tc_kernel<0><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
     case 1: gemm_tc_kernel<1><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;

@@ -53,6 +53,7 @@ struct GemmTcParams {
   // the window-ordered q / k / v operands of the FeatureTransformer attention (ft.cu), no separate gather / split pass
   __nv_bfloat16* split_dst[4]; const int2* rowmap; int npix, n_img, img_shift;
   unsigned long long* prof; // diagnostics (tools/gemm_roles.py): [grid][8] cycles: producer total, wait empty | issuer total, wait full, wait acc_empty | epilogue warp 0 total, wait acc_full, tiles
+  int dbg;                  // diagnostics (emip_debug_gemm_wide_tiles): bit 0 = epilogue warps skip their work, bit 1 = producer skips the TMA loads
   int epi_stage;            // mode 2: per-warp shared-memory staging of the epilogue (set by gemm_tc_launch): coalesced row stores
 };
 

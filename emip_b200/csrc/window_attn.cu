@@ -406,25 +406,40 @@ int ft_geom(int B, int h, int w, int splits, int shift, FtGeom* out) {
 
 // one attention layer on the window-ordered operands: per block group one fused flash launch, rows scattered to pixel order
 int ft_attention(const FtWs& ws, const FtGeom& ge, int B, int h, int w, cudaStream_t st) {
-  for (int i = 0; i < ge.ng; ++i) {
-    const Group& g = ge.g[i];
-    AttnTcArgs a = {};
-    a.win.enabled = 1; a.win.B = B; a.win.h = h; a.win.w = w;
-    for (int j = 0; j < MAXBLK; ++j) {
-      a.win.r0[j] = j < g.nblk ? g.r0[j] : 0;
-      a.win.c0[j] = j < g.nblk ? g.c0[j] : 0;
-      a.win.bw[j] = j < g.nblk ? g.bw[j] : 1;
+  // ONE launch for all block groups of the layer (attn_tc.cuh: AttnTcArgs::more).  The groups of a shifted layer (22 x 22, 22 x 11 /
+  // 11 x 22 and 11 x 11 token blocks) were three launches, each ending in its own partial wave: at 8 pairs 64 + 128 + 64 items
+  // for 148 persistent CTAs.  Sets ordered by token count, largest first: items are dealt round-robin, heavy ones first.
+  if (ge.ng < 1 || ge.ng > 3) { emip_set_error("feature_transformer: %d block groups", ge.ng); return EMIP_ENOSYS; }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < ge.ng; ++i)
+    for (int j = i + 1; j < ge.ng; ++j)
+      if (ge.g[order[j]].n > ge.g[order[i]].n) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  AttnTcArgs a = {};
+  a.win.enabled = 1; a.win.B = B; a.win.h = h; a.win.w = w;
+  int blk = 0;
+  for (int s = 0; s < ge.ng; ++s) {
+    const Group& g = ge.g[order[s]];
+    if (blk + g.nblk > 16) { emip_set_error("feature_transformer: more than 16 attention blocks"); return EMIP_ENOSYS; }
+    for (int j = 0; j < g.nblk; ++j) { a.win.r0[blk + j] = g.r0[j]; a.win.c0[blk + j] = g.c0[j]; a.win.bw[blk + j] = g.bw[j]; }
+    const size_t off = (size_t)ge.base[order[s]] * 256;
+    if (s == 0) {
+      a.q_split = ws.q + off; a.k_split = ws.k + off; a.v_split = ws.v + off;
+      a.nb = g.nblk * B; a.nq = g.n; a.nk = g.n;
+    } else {
+      AttnTcArgs::More& m = a.more[s - 1];
+      m.q_split = ws.q + off; m.k_split = ws.k + off; m.v_split = ws.v + off;
+      m.nb = g.nblk * B; m.nq = g.n; m.nk = g.n; m.blk0 = blk;
     }
-    const size_t off = (size_t)ge.base[i] * 256;
-    a.q_split = ws.q + off; a.k_split = ws.k + off; a.v_split = ws.v + off;
-    a.out = nullptr; a.out_stride_b = 0; a.lse = nullptr;
-    a.out_hi = ws.msg_hi; a.out_lo = ws.msg_lo; a.out_ld = KC;
-    a.nb = g.nblk * B; a.nq = g.n; a.nk = g.n; a.out_layout = EMIP_LAYOUT_NC;
-    a.sqrt_c = sqrtf((float)KC);
-    a.ksplit = 1;
-    if (int rc = attn_tc_fwd(a, st)) return rc;
+    blk += g.nblk;
   }
-  return EMIP_OK;
+  for (int j = blk; j < 16; ++j) a.win.bw[j] = 1;
+  a.n_more = ge.ng - 1;
+  a.out = nullptr; a.out_stride_b = 0; a.lse = nullptr;
+  a.out_hi = ws.msg_hi; a.out_lo = ws.msg_lo; a.out_ld = KC;
+  a.out_layout = EMIP_LAYOUT_NC;
+  a.sqrt_c = sqrtf((float)KC);
+  a.ksplit = 1;
+  return attn_tc_fwd(a, st);
 }
 }  // namespace
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""FeatureTransformer call time with 256- and 128-column tiles for the 256 -> 1024 layer: ft_time.py [pairs]."""
+"""FeatureTransformer call time under the gemm_tc diagnostics switches (emip_debug_gemm_wide_tiles: bit 0 = 256-column tiles for
+the 256 -> 1024 layer): ft_time.py [pairs] [flags ...]."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,7 +15,8 @@ m = ch._FeatureTransformer().to(dev)
 x = torch.randn(2 * pairs, 1936, 128, device=dev)
 L = _lib.lib()
 ref = None
-for wide in (1, 0, 1, 0):
+flag_list = [int(a) for a in sys.argv[2:]] or [0, 1]
+for wide in flag_list * 2:
     L.emip_debug_gemm_wide_tiles(wide)
     with torch.no_grad():
         for _ in range(2):
@@ -28,5 +30,5 @@ for wide in (1, 0, 1, 0):
         torch.cuda.synchronize()
     if ref is None:
         ref = y.clone()
-    print(f"wide tiles {wide}: {e0.elapsed_time(e1) / 5:7.3f} ms per FeatureTransformer call   max|diff| {(y - ref).abs().max().item():.1e}")
+    print(f"gemm flags {wide}: {e0.elapsed_time(e1) / 5:7.3f} ms per FeatureTransformer call   max|diff| {(y - ref).abs().max().item():.1e}")
 L.emip_debug_gemm_wide_tiles(0)
