@@ -41,6 +41,7 @@ from .upsample import upsample_flow_convex
 
 LAYOUT_NC, LAYOUT_CN = 0, 1
 TOKEN_MAJOR = 16
+PRESPLIT = 128      # EMIP_FLAG_PRESPLIT
 KV_SWAP = 1
 
 
@@ -255,19 +256,45 @@ def conv1x1_cn(x, weight, bias):
 
 
 def global_matching_tokens(tok, B, h, w, bf16=False):
-    """Bidirectional global matching on the transformer's token rows: tok [2B, h*w, 128] (frame 1 | frame 2) ->
+    """Bidirectional global matching on the transformer's token rows: tok fp32 [2B, h*w, 128] (frame 1 | frame 2), or the bf16
+    [2B, h*w, 256] hi | lo operand of ``feature_transformer_tokens(want_split=True)`` (no split pass then) ->
     flow [2B, 2, h, w] (forward flows, then backward flows); the cost volume is not written (matching.py:8-41)."""
     L = _lib.lib()
-    C = tok.shape[-1]
+    presplit = tok.dtype == torch.bfloat16
+    C = tok.shape[-1] // 2 if presplit else tok.shape[-1]
     L.emip_global_matching_workspace.restype = ctypes.c_size_t
     ws, ws_ptr, ws_n = workspace(L.emip_global_matching_workspace(I(B), I(C), I(h), I(w)), tok.device)
     flow = torch.empty((2 * B, 2, h, w), dtype=torch.float32, device=tok.device)
     f0, f1 = tok[:B], tok[B:]
     with torch.cuda.device(tok.device):
         _lib.check(L.emip_global_matching_fwd(ptr(f0), ptr(f1), ptr(flow), None, None, ctypes.c_void_p(ws_ptr), SZ(ws_n), I(B), I(C),
-                                              I(h), I(w), I(1), I(TOKEN_MAJOR | (4 if bf16 else 0)), stream_ptr()),
+                                              I(h), I(w), I(1), I((PRESPLIT if presplit else TOKEN_MAJOR) | (4 if bf16 else 0)), stream_ptr()),
                    "emip_global_matching_fwd")
     return flow
+
+
+def flow_attention_tokens(tok_split, ffa, flow):
+    """FeatureFlowAttention.forward (transformer.py:519-532) on the transformer's pre-split token rows in one C-ABI call:
+    tok_split bf16 [B, N, 256] (hi | lo), ffa = the module holding q_proj / k_proj, flow [B, 2, N] -> propagated flow [B, 2, N].
+    The projections write query / key as the attention kernel's operands; inference only."""
+    _need_cuda(flow, "flow_attention_tokens")
+    if tok_split.dtype != torch.bfloat16 or not tok_split.is_cuda or not tok_split.is_contiguous():
+        raise TypeError("emip_b200 flow_attention_tokens reads the contiguous bf16 hi | lo rows of feature_transformer_tokens(want_split=True)")
+    L = _lib.lib()
+    Bn, N, C2 = tok_split.shape
+    C = C2 // 2
+    flow = flow.contiguous()
+    L.emip_flow_attn_tokens_workspace.restype = ctypes.c_size_t
+    need = L.emip_flow_attn_tokens_workspace(I(Bn), I(N), I(C))
+    if need == 0:
+        raise _lib.EmipError(f"emip_b200 flow_attention_tokens: unsupported shape B={Bn} N={N} C={C}")
+    ws, ws_ptr, ws_n = workspace(need, tok_split.device)
+    out = torch.empty_like(flow)
+    wq, bq, wk, bk = (t.detach().contiguous() for t in (ffa.q_proj.weight, ffa.q_proj.bias, ffa.k_proj.weight, ffa.k_proj.bias))
+    with torch.cuda.device(tok_split.device):
+        _lib.check(L.emip_flow_attn_tokens_fwd(ptr(tok_split), ptr(wq), ptr(bq), ptr(wk), ptr(bk), ptr(flow), ptr(out), ctypes.c_void_p(ws_ptr),
+                                               SZ(ws_n), I(Bn), I(N), I(C), I(0), stream_ptr()), "emip_flow_attn_tokens_fwd")
+    return out
 
 
 def conv_corr_fused(tok, B, h, w, conv0, w_prep0, scale, shift, conv3, w_prep3):
@@ -324,9 +351,11 @@ def _ft_weights(transformer):
     return out
 
 
-def feature_transformer_tokens(x, transformer, h, w, num_splits, cache=None):
+def feature_transformer_tokens(x, transformer, h, w, num_splits, cache=None, want_split=False):
     """The whole FeatureTransformer (transformer.py:433-482) on token rows x [2B, h*w, 128] (frame 1 | frame 2) in one C-ABI
-    call, inference only; ``transformer`` = any module with ``.layers[i].self_attn / .cross_attn_ffn`` (ours or the reference's)."""
+    call, inference only; ``transformer`` = any module with ``.layers[i].self_attn / .cross_attn_ffn`` (ours or the reference's).
+    ``want_split``: also return the rows as the bf16 [2B, h*w, 256] hi | lo operand (written by the last LayerNorm epilogue)
+    that ``global_matching_tokens`` / ``flow_attention_tokens`` read without a split pass."""
     _need_cuda(x, "feature_transformer")
     B2, N, C = x.shape
     x = x.contiguous()
@@ -351,12 +380,13 @@ def feature_transformer_tokens(x, transformer, h, w, num_splits, cache=None):
         raise _lib.EmipError(f"emip_b200 feature_transformer: unsupported shape B={B2} h={h} w={w} C={C}")
     ws, ws_ptr, ws_n = workspace(need, x.device)
     out = torch.empty_like(x)
+    split = torch.empty((B2, N, 2 * C), dtype=torch.bfloat16, device=x.device) if want_split else None
     eps = transformer.layers[0].self_attn.norm1.eps
     with torch.cuda.device(x.device):
-        _lib.check(L.emip_feature_transformer_fwd(ptr(x), ptr(out), arr, ctypes.c_void_p(prep), I(nb), ctypes.c_void_p(ws_ptr), SZ(ws_n),
-                                                  I(B2), I(h), I(w), I(C), I(num_splits), ctypes.c_float(eps), stream_ptr()),
-                   "emip_feature_transformer_fwd")
-    return out
+        _lib.check(L.emip_feature_transformer_fwd_ex(ptr(x), ptr(out), ptr(split), arr, ctypes.c_void_p(prep), I(nb), ctypes.c_void_p(ws_ptr),
+                                                     SZ(ws_n), I(B2), I(h), I(w), I(C), I(num_splits), ctypes.c_float(eps), stream_ptr()),
+                   "emip_feature_transformer_fwd_ex")
+    return (out, split) if want_split else out
 
 
 # ------------------------------------------------------------------------------------------------ the chain
@@ -483,16 +513,19 @@ class MotionChain(nn.Module):
         with torch.cuda.device(dev):
             ab = self.injector(gm, seg)                                                          # model.py:92-93, one call
             x = tokens_from_cn(ab, window_position(H, W, self.attn_splits, C, dev))              # gmflow.py:114 + transformer.py:439-462
+            ffa = gmf.feature_flow_attn
             if self.fused_transformer:
-                x = feature_transformer_tokens(x, gmf.transformer, H, W, self.attn_splits, self._cache)   # transformer.py:433-482
+                # the last LayerNorm epilogue also writes the rows as the bf16 hi | lo operand a1 and a2 read: no split passes
+                x, xs = feature_transformer_tokens(x, gmf.transformer, H, W, self.attn_splits, self._cache, want_split=True)   # transformer.py:433-482
+                flow_pred = global_matching_tokens(xs, B, H, W)                                  # gmflow.py:121
+                flow = flow_attention_tokens(xs, ffa, flow_pred.view(B2, 2, N)).view(B2, 2, H, W)    # gmflow.py:137, transformer.py:519-532
             else:
                 for blk in gmf.transformer.layers:                                               # transformer.py:464-473
                     x = transformer_block(blk, x, H, W, self.attn_splits)
-            flow_pred = global_matching_tokens(x, B, H, W)              # gmflow.py:121
-            ffa = gmf.feature_flow_attn
-            q = linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)                            # transformer.py:523
-            k = linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)                            # transformer.py:524
-            flow = flow_attention_core(q, k, flow_pred.view(B2, 2, N)).view(B2, 2, H, W)   # gmflow.py:137
+                flow_pred = global_matching_tokens(x, B, H, W)          # gmflow.py:121
+                q = linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)                        # transformer.py:523
+                k = linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)                        # transformer.py:524
+                flow = flow_attention_core(q, k, flow_pred.view(B2, 2, N)).view(B2, 2, H, W)     # gmflow.py:137
             up = gmf.upsampler
             hid = conv3x3(flow, LAYOUT_CN, x, LAYOUT_NC, w_up, up[0].weight.shape[0], H, W, shift=up[0].bias.detach(), relu=True)
             mask = conv1x1_cn(hid, up[2].weight, up[2].bias)                                     # gmflow.py:64

@@ -8,6 +8,7 @@
 #include "pair_common.cuh"
 #include "match_tc.cuh"
 #include "pair_bwd_tc.cuh"
+#include "gemm_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -60,6 +61,61 @@ extern "C" int emip_flow_attn_fwd(const float* q, const float* k, const float* v
   a.x_layout = a.y_layout = lay;
   a.sqrt_c = sqrtf((float)C);                       // transformer.py:528
   return pair_fwd_simt(a, st);
+}
+
+// a2 in one call from the transformer's pre-split token rows: see include/emip_b200.h
+extern "C" size_t emip_flow_attn_tokens_workspace(int B, int N, int C) {
+  if (B < 0 || N <= 0 || C != 128) return 0;
+  return 2 * match_tc_split_bytes(B, N, C) + 2 * emip_align_up(gemm_nt_tc_scratch_bytes_presplit(C, C) + 1024, 1024) + match_tc_streamk_bytes(B, N, N);
+}
+
+extern "C" int emip_flow_attn_tokens_fwd(const void* x_split, const float* wq, const float* bq, const float* wk, const float* bk,
+                                         const float* v, float* out, void* workspace, size_t ws_bytes, int B, int N, int C, int flags,
+                                         void* stream) {
+  if (B == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(x_split && wq && bq && wk && bk && v && out && workspace, "flow_attn_tokens_fwd: null pointer");
+  EMIP_CHECK_ARG(B > 0 && N > 0, "flow_attn_tokens_fwd: bad shape B=%d N=%d", B, N);
+  if (C != 128 || !match_tc_supported(N, N, C) || (flags & EMIP_FLAG_EXACT_FP32)) {
+    emip_set_error("flow_attn_tokens_fwd: needs the tensor-core path (C=128, 16 <= N <= 2048, no EMIP_FLAG_EXACT_FP32)");
+    return EMIP_ENOSYS;
+  }
+  EMIP_CHECK_ARG((long long)B * N < 0x7fffffffLL, "flow_attn_tokens_fwd: too many rows");
+  if (ws_bytes < emip_flow_attn_tokens_workspace(B, N, C) || reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) {
+    emip_set_error("flow_attn_tokens_fwd: workspace too small or not 1024-byte aligned");
+    return EMIP_ENOMEM;
+  }
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(x_split) % 128 == 0 && ((reinterpret_cast<uintptr_t>(bq) | reinterpret_cast<uintptr_t>(bk)) & 15) == 0,
+                 "flow_attn_tokens_fwd: x_split must be 128-byte, bq / bk 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sb = match_tc_split_bytes(B, N, C), wb = emip_align_up(gemm_nt_tc_scratch_bytes_presplit(C, C) + 1024, 1024);
+  char* base = static_cast<char*>(workspace);
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(base);             // query rows [B*N][hi 128 | lo 128]
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(base + sb);        // key rows
+  const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(x_split);
+  const float* w[2] = {wq, wk};
+  const float* bias[2] = {bq, bk};
+  __nv_bfloat16* dst[2] = {qs, ks};
+  for (int i = 0; i < 2; ++i) {                                            // transformer.py:523-524: key = k_proj(q_proj(x))
+    GemmNT t = {};
+    t.B = 1; t.M = B * N; t.K = C; t.N = C;
+    t.a_hi_pre = src; t.a_lo_pre = src + C; t.a_ld_pre = 2 * C;
+    t.bm = w[i]; t.ldb = C;
+    t.c_hi = dst[i]; t.c_lo = dst[i] + C; t.ldc_split = 2 * C;
+    t.c_bias = bias[i];
+    t.ldc = C;
+    if (int rc = gemm_nt_tc(t, base + 2 * sb + i * wb, wb, st, 1)) return rc;
+    src = dst[i];
+  }
+  MatchTcArgs a = {};
+  a.x_split = qs; a.y_split = ks; a.nbx = B; a.nby = B;
+  a.v = v; a.v_stride_b = 2LL * N; a.grid_w = 0; a.sub_grid = 0;
+  a.terms = (flags & EMIP_FLAG_BF16) ? 1 : 3;
+  a.out = out; a.lse = nullptr; a.nb = B; a.nq = N; a.nk = N; a.y_shift = 0; a.y_mod = B;
+  a.s_out = nullptr; a.s_first = 0; a.s_count = 0;
+  a.sqrt_c = sqrtf((float)C);
+  a.sk_ws = base + 2 * sb + 2 * wb; a.sk_bytes = match_tc_streamk_bytes(B, N, N);
+  a.schedule = (flags & EMIP_FLAG_SCHED_STREAMK) ? 1 : (flags & EMIP_FLAG_SCHED_ITEMS) ? 2 : 0;
+  return match_tc_fwd(a, st);
 }
 
 extern "C" int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,

@@ -407,6 +407,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias_n != nullptr) {                          // per-column bias (nn.Linear with bias feeding another GEMM), uniform branch
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias_n + n0 + c0) + i);
+              v[4 * i] += bq.x; v[4 * i + 1] += bq.y; v[4 * i + 2] += bq.z; v[4 * i + 3] += bq.w;
+            }
+          }
           if (p.out_split == 2) {                             // one uniform branch per chunk, not per element
 #pragma unroll
             for (int i = 0; i < 16; ++i) gelu_epi2(v[2 * i], v[2 * i + 1]);
@@ -967,7 +974,10 @@ int gemm_nt_tc(const GemmNT& a, void* scratch, size_t scratch_bytes, cudaStream_
     p.g_hi = p.split_dst[0]; p.g_lo = p.split_dst[0] + 128;
   }
   if (a.c_bias != nullptr) {
-    if (a.ln_gamma != nullptr || a.c_hi != nullptr || ns != 1) { emip_set_error("gemm_nt_tc: c_bias needs the plain fp32 epilogue"); return EMIP_ENOSYS; }
+    if (a.ln_gamma != nullptr || a.split_dst[0] != nullptr || ns != 1 || (a.c_hi != nullptr && (reinterpret_cast<uintptr_t>(a.c_bias) & 15) != 0)) {
+      emip_set_error("gemm_nt_tc: c_bias needs the plain fp32 or the bf16 hi | lo epilogue (bias 16-byte aligned there)");
+      return EMIP_ENOSYS;
+    }
     p.bias_n = a.c_bias;
   }
   if (a.c_hi != nullptr) {

@@ -60,7 +60,7 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
                                         void* workspace, size_t ws_bytes, int B, int C, int H, int W, int bidir,
                                         int flags, void* stream) {
   if (B == 0) return EMIP_OK;
-  EMIP_CHECK_ARG(f0 && f1 && flow, "global_matching_fwd: null pointer");
+  EMIP_CHECK_ARG(f0 && (f1 || (flags & EMIP_FLAG_PRESPLIT)) && flow, "global_matching_fwd: null pointer");
   EMIP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "global_matching_fwd: bad shape B=%d H=%d W=%d", B, H, W);
   if (C != 128) {
     emip_set_error("global_matching_fwd: C=%d unsupported (kernels are built for the model's C=128)", C);
@@ -77,9 +77,12 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
   if (!(flags & EMIP_FLAG_EXACT_FP32) && match_tc_supported(N, N, C)) {
     // tensor-core path: one operand-split launch + one fused launch covering both directions
     const int layout = (flags & EMIP_FLAG_TOKEN_MAJOR) ? EMIP_LAYOUT_NC : EMIP_LAYOUT_CN;
-    if (!reuse && (rc = match_tc_split(f0, f1, ws.split, B, N, C, layout, 0, st))) return rc;
+    const bool presplit = (flags & EMIP_FLAG_PRESPLIT) != 0;      // f0 = the bf16 hi | lo operand of both frames
+    if (presplit) EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(f0) % 16 == 0, "global_matching_fwd: the pre-split operand must be 16-byte aligned");
+    if (!presplit && !reuse && (rc = match_tc_split(f0, f1, ws.split, B, N, C, layout, 0, st))) return rc;
+    const void* split = presplit ? static_cast<const void*>(f0) : ws.split;
     MatchTcArgs a = {};
-    a.x_split = ws.split; a.y_split = ws.split; a.nbx = 2 * B; a.nby = 2 * B;
+    a.x_split = split; a.y_split = split; a.nbx = 2 * B; a.nby = 2 * B;
     a.v = nullptr; a.v_stride_b = 0; a.grid_w = W; a.sub_grid = 1;   // analytic pixel grid (geometry.py:5-21)
     a.out = flow; a.lse = lse;
     a.nb = nd * B; a.nq = N; a.nk = N; a.y_shift = B; a.y_mod = 2 * B;
@@ -90,8 +93,8 @@ extern "C" int emip_global_matching_fwd(const float* f0, const float* f1, float*
     a.schedule = (flags & EMIP_FLAG_SCHED_STREAMK) ? 1 : (flags & EMIP_FLAG_SCHED_ITEMS) ? 2 : 0;
     return match_tc_fwd(a, st);
   }
-  if (flags & EMIP_FLAG_TOKEN_MAJOR) {
-    emip_set_error("global_matching_fwd: EMIP_FLAG_TOKEN_MAJOR needs the tensor-core path (C=128, 16 <= H*W <= 2048)");
+  if (flags & (EMIP_FLAG_TOKEN_MAJOR | EMIP_FLAG_PRESPLIT)) {
+    emip_set_error("global_matching_fwd: EMIP_FLAG_TOKEN_MAJOR / EMIP_FLAG_PRESPLIT need the tensor-core path (C=128, 16 <= H*W <= 2048)");
     return EMIP_ENOSYS;
   }
   if ((rc = launch_coords_grid(ws.grid, H, W, st))) return rc;

@@ -485,7 +485,16 @@ extern "C" size_t emip_feature_transformer_workspace(int B, int h, int w, int C)
 extern "C" int emip_feature_transformer_fwd(const float* x, float* out, const float* const* weights, const void* prep, int n_blocks,
                                             void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
                                             float eps, void* stream) {
+  return emip_feature_transformer_fwd_ex(x, out, nullptr, weights, prep, n_blocks, workspace, ws_bytes, B, h, w, C, num_splits, eps, stream);
+}
+
+// out_split (optional): the output rows once more as bf16 [B][h*w][hi 128 | lo 128] -- the operand format of the matching / flow
+// attention kernels and of the token-row GEMMs -- written by the last block's LayerNorm epilogue (no split pass over `out`)
+extern "C" int emip_feature_transformer_fwd_ex(const float* x, float* out, void* out_split, const float* const* weights, const void* prep,
+                                               int n_blocks, void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
+                                               float eps, void* stream) {
   if (B == 0 || n_blocks == 0) return EMIP_OK;
+  EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(out_split) % 128 == 0, "feature_transformer_fwd: out_split must be 128-byte aligned");
   EMIP_CHECK_ARG(x && out && weights && prep && workspace, "feature_transformer_fwd: null pointer");
   EMIP_CHECK_ARG(B > 0 && B % 2 == 0 && h > 0 && w > 0 && n_blocks > 0, "feature_transformer_fwd: bad shape B=%d (even) h=%d w=%d", B, h, w);
   if (C != KC) { emip_set_error("feature_transformer_fwd: C=%d unsupported (kernels are built for the model's C=128)", C); return EMIP_ENOSYS; }
@@ -578,6 +587,9 @@ extern "C" int emip_feature_transformer_fwd(const float* x, float* out, const fl
       t.ln_gamma = wt[14]; t.ln_beta = wt[15]; t.ln_eps = eps; t.c_res = ws.xf[1];
       t.c = xnext_f;
       t.ln_hi = ws.xs_hi[0]; t.ln_lo = ws.xs_lo[0]; t.ln_ld = 256;
+      if (blk == n_blocks - 1 && out_split != nullptr) {
+        t.ln_hi = out_split; t.ln_lo = static_cast<__nv_bfloat16*>(out_split) + KC;
+      }
       if ((rc = gemm_nt_tc(t, nullptr, 0, st, 1))) return rc;
     }
   }

@@ -64,6 +64,9 @@ extern "C" {
 #define EMIP_FLAG_CHANNEL_MAJOR 8  /* flow_attn_fwd / _bwd: q, k (and dq, dk) are channel-major [B,C,N] instead of [B,N,C] */
 #define EMIP_FLAG_TOKEN_MAJOR 16   /* global_matching_fwd: f0, f1 are token-major [B,H*W,C] -- the FeatureTransformer's own
                                        output layout (transformer.py:476, before the permute of :479-480) */
+#define EMIP_FLAG_PRESPLIT 128      /* global_matching_fwd: f0 is not fp32 features but the bf16 operand [2B][H*W][hi 128 | lo 128] of
+                                     * BOTH frames (frame-1 maps, then frame-2 maps) as emip_feature_transformer_fwd_ex writes it
+                                     * (out_split); f1 is ignored and no operand-split pass runs.  Tensor-core path only. */
 #define EMIP_FLAG_SCHED_STREAMK 32  /* global_matching_fwd / flow_attn_fwd: force the stream-K work schedule (default: chosen by */
 #define EMIP_FLAG_SCHED_ITEMS 64    /* batch size) / force grid-strided whole items -- results are identical either way */
 #define EMIP_LAYOUT_TOKEN_MAJOR 0  /* [B][H*W][C] */
@@ -162,6 +165,16 @@ int emip_global_matching_bwd(const float* f0, const float* f1, const float* flow
 size_t emip_flow_attn_workspace(int B, int N, int C);
 int emip_flow_attn_fwd(const float* q, const float* k, const float* v, float* out, float* lse, void* workspace,
                        size_t ws_bytes, int B, int N, int C, int flags, void* stream);
+/* a2 as one call on the FeatureTransformer's token rows (transformer.py:519-532; inference, forward only): query = q_proj(x),
+ * key = k_proj(query) -- the reference projects the key from the PROJECTED query (:523-524) --, out = softmax(query key^T /
+ * sqrt(C)) v.  x_split = the bf16 rows [B][N][hi 128 | lo 128] (emip_feature_transformer_fwd_ex out_split); both projection
+ * GEMMs read their row operand pre-split and write query / key as the bf16 hi | lo operands of the attention kernel
+ * (bias added in the epilogue), so no fp32 query / key and no split pass exist.  wq, wk [C,C] and bq, bk [C] fp32 (x_split
+ * 128-byte, bq / bk 16-byte aligned); v, out [B,2,N]; workspace >= emip_flow_attn_tokens_workspace(B, N, C) bytes, 1024-byte aligned.
+ * flags: 0, EMIP_FLAG_BF16, EMIP_FLAG_SCHED_*.  Bit-identical to emip_linear_tm_bias_fwd x 2 + emip_flow_attn_fwd. */
+size_t emip_flow_attn_tokens_workspace(int B, int N, int C);
+int emip_flow_attn_tokens_fwd(const void* x_split, const float* wq, const float* bq, const float* wk, const float* bk, const float* v,
+                              float* out, void* workspace, size_t ws_bytes, int B, int N, int C, int flags, void* stream);
 /* Backward w.r.t. q and k only: the value is flow.detach() in the model (gmflow.py:137). */
 int emip_flow_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* lse,
                        const float* dout, float* dq, float* dk, void* workspace, size_t ws_bytes, int B, int N,
@@ -410,6 +423,12 @@ size_t emip_feature_transformer_workspace(int B, int h, int w, int C);
 int emip_feature_transformer_fwd(const float* x, float* out, const float* const* weights, const void* prep, int n_blocks,
                                  void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits, float eps,
                                  void* stream);
+/* Same, plus out_split (may be NULL): the output rows once more as bf16 [B][h*w][hi 128 | lo 128] (128-byte aligned), written by
+ * the last block's LayerNorm epilogue -- the operand emip_global_matching_fwd (EMIP_FLAG_PRESPLIT) and
+ * emip_flow_attn_tokens_fwd read, so that no split pass over `out` runs (gmflow.py:117-137 after the transformer). */
+int emip_feature_transformer_fwd_ex(const float* x, float* out, void* out_split, const float* const* weights, const void* prep,
+                                    int n_blocks, void* workspace, size_t ws_bytes, int B, int h, int w, int C, int num_splits,
+                                    float eps, void* stream);
 
 /* ---- the chained path between the backbones and the decoder (CoUpdater.forward, model.py:92-97) -------------------- */
 /* 3x3 convolution, stride 1, zero padding 1, on the tensor cores (csrc/conv_tm.cu): replaces GMFlow.upsampler[0] + ReLU

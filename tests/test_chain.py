@@ -290,6 +290,37 @@ def test_conv3x3_vs_library_convolution(b, c0, c1, o, h, w, lay0, lay1, relu, sc
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("b,h,w", [(1, 44, 44), (3, 16, 24)])
+def test_presplit_handover_of_the_transformer_rows_is_bit_identical(b, h, w):
+    """The bf16 hi | lo rows the last LayerNorm epilogue writes (emip_feature_transformer_fwd_ex out_split) are the split of the
+    fp32 output, and a1 (EMIP_FLAG_PRESPLIT) / a2 (emip_flow_attn_tokens_fwd) fed with them return exactly what they return
+    from the fp32 rows through their own split passes."""
+    from emip_b200 import chain as ch
+    from emip_b200.flow_attn import flow_attention_core
+    P = cases.chain_params(seed=9)
+    m = ch._FeatureTransformer()
+    m.load_state_dict(O.sub_params(P, "GMFlow.transformer."))
+    m = m.cuda()
+    ffa = _chain(P).GMFlow.feature_flow_attn.cuda()
+    x = cases.randn(331, (2 * b, h * w, 128), 2.0).cuda()
+    with torch.no_grad():
+        out, split = ch.feature_transformer_tokens(x, m, h, w, 2, want_split=True)
+        assert torch.equal(out, ch.feature_transformer_tokens(x, m, h, w, 2))
+        hi = out.to(torch.bfloat16)
+        lo = (out - hi.float()).to(torch.bfloat16)
+        assert torch.equal(split[..., :128], hi) and torch.equal(split[..., 128:], lo)
+        flow_a = ch.global_matching_tokens(out, b, h, w)
+        flow_b = ch.global_matching_tokens(split, b, h, w)
+        assert torch.equal(flow_a, flow_b)
+        q = ch.linear_tm_bias(out, ffa.q_proj.weight, ffa.q_proj.bias)
+        k = ch.linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)
+        v = flow_a.view(2 * b, 2, h * w)
+        prop_a = flow_attention_core(q, k, v)
+        prop_b = ch.flow_attention_tokens(split, ffa, v)
+        assert torch.equal(prop_a, prop_b)
+
+
+@pytest.mark.gpu
 def test_tokens_from_cn_and_bias_linear_and_kv_swap():
     """The small pieces of the chain against torch: transpose + position add, nn.Linear with bias on token rows, and the
     cross-attention call that reads the keys / values of the other batch half (no swapped copy)."""

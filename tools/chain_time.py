@@ -39,20 +39,23 @@ def stage_times(m, gm, seg, iters=10):
         gmf = m.GMFlow
         ab = timed("a4 injector x2 (one call, 2B maps)", lambda: m.injector(gm, seg))
         x = timed("pos add + token rows", lambda: ch.tokens_from_cn(ab, ch.window_position(H, W, m.attn_splits, C, dev)))
+        ffa = gmf.feature_flow_attn
         if m.fused_transformer:
-            x = timed("f2/f2b FeatureTransformer (one C-ABI call, 6 blocks)",
-                      lambda x=x: ch.feature_transformer_tokens(x, gmf.transformer, H, W, m.attn_splits, m._cache))
+            x, xs = timed("f2/f2b FeatureTransformer (one C-ABI call, 6 blocks; also writes the bf16 hi | lo rows for a1 / a2)",
+                          lambda x=x: ch.feature_transformer_tokens(x, gmf.transformer, H, W, m.attn_splits, m._cache, want_split=True))
+            flow_pred = timed("a1 matching (lazy corr, pre-split rows)", lambda: ch.global_matching_tokens(xs, B, H, W))
+            flow = timed("a2 flow attention (projections + core, one call on the pre-split rows)",
+                         lambda: ch.flow_attention_tokens(xs, ffa, flow_pred.view(2 * B, 2, N)).view(2 * B, 2, H, W))
         else:
             for blk in gmf.transformer.layers:
                 x = timed("f2/f2b transformer blocks (x6, per-layer calls)", lambda blk=blk, x=x: ch.transformer_block(blk, x, H, W, m.attn_splits))
-        flow_pred = timed("a1 matching (lazy corr)", lambda: ch.global_matching_tokens(x, B, H, W))
-        ffa = gmf.feature_flow_attn
+            flow_pred = timed("a1 matching (lazy corr)", lambda: ch.global_matching_tokens(x, B, H, W))
 
-        def a2():
-            q = ch.linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)
-            k = ch.linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)
-            return flow_attention_core(q, k, flow_pred.view(2 * B, 2, N)).view(2 * B, 2, H, W)
-        flow = timed("a2 flow attention (+ projections)", a2)
+            def a2():
+                q = ch.linear_tm_bias(x, ffa.q_proj.weight, ffa.q_proj.bias)
+                k = ch.linear_tm_bias(q, ffa.k_proj.weight, ffa.k_proj.bias)
+                return flow_attention_core(q, k, flow_pred.view(2 * B, 2, N)).view(2 * B, 2, H, W)
+            flow = timed("a2 flow attention (+ projections)", a2)
         up = gmf.upsampler
         hid = timed("upsampler conv3x3 + relu", lambda: ch.conv3x3(flow, 1, x, 0, w_up, 256, H, W, shift=up[0].bias.detach(), relu=True))
         mask = timed("upsampler conv1x1", lambda: ch.conv1x1_cn(hid, up[2].weight, up[2].bias))
