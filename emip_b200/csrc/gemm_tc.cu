@@ -20,56 +20,10 @@ constexpr int A_BYTES = GEMM_TC_A_BYTES;
 constexpr int EPI_STAGE_BYTES = 8 * 32 * 128;      // eight epilogue warps x [32 rows][128 B] (swizzled: tc_common.cuh::stg_swz)
 constexpr int THREADS = 10 * 32;     // warps 0-3, 6-9: epilogue groups; 4: TMA producer; 5: UMMA issuer
 
-// exact-GELU x Phi(x) for the epilogue (where the instruction count is the critical path): Phi through the rational
-// erfc form of Abramowitz & Stegun 7.1.26, erfc(z) = poly5(t) e^{-z^2}, t = 1 / (1 + 0.3275911 z), |error| <= 1.5e-7 --
-// below the 2^-17 relative resolution of the bf16 hi | lo pair the value is stored as.  One MUFU.RCP + one MUFU.EX2 and
-// ~12 FP32 instructions instead of erff's two-branch polynomial; no 1 + erf cancellation for negative x.
-__device__ __forceinline__ float gelu_epi(float x) {
-  // 0.5 folded into the polynomial; rcp / ex2 as single MUFU instructions (.ftz: t is in (0, 1], e^{-z^2} may flush to 0)
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.44269504088896340736f * z));
-  float p = fmaf(0.5307027145f, t, -0.7265760135f);
-  p = fmaf(p, t, 0.7107068705f);
-  p = fmaf(p, t, -0.142248368f);
-  p = fmaf(p, t, 0.127414796f);
-  const float g = p * t * e;                                   // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
-  return x * (x >= 0.f ? 1.f - g : g);
-}
-
 // EPI selects the epilogue at compile time (0: mode 0 | 1: mode 1 | 2: mode 2 + LayerNorm | 3: mode 2 bf16 hi | lo output |
 // 4: mode 2 plain fp32): one function for all of them put every branch under the register allocation of the hungriest one
 // (168 registers at 10 warps) and spilled; per-instantiation allocation has no spills and lets the split epilogue keep two
 // TMEM chunks in flight
-// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2: sm_100 executes two fp32 FMAs per instruction): the GELU / split
-// epilogue of the 256 -> 1024 layer is instruction-issue bound (r3i: 25 instructions per element on eight warps).
-// gelu(x) = max(x, 0) - |x| Phi(-|x|): no select, no 1 - g.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ void gelu_epi2(float& x0, float& x1) {
-  const float a0 = fabsf(x0), a1 = fabsf(x1);
-  const f32x2 ax = pk2(a0, a1);
-  const f32x2 z = mul2(ax, pk2(0.70710678118654752440f, 0.70710678118654752440f));
-  float d0, d1, q0, q1, t0, t1, e0, e1;
-  upk2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.f, 1.f)), d0, d1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  upk2(mul2(mul2(z, pk2(-1.44269504088896340736f, -1.44269504088896340736f)), z), q0, q1);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
-  const f32x2 t = pk2(t0, t1);
-  f32x2 p = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));
-  p = fma2(p, t, pk2(0.7107068705f, 0.7107068705f));
-  p = fma2(p, t, pk2(-0.142248368f, -0.142248368f));
-  p = fma2(p, t, pk2(0.127414796f, 0.127414796f));
-  const f32x2 g = mul2(mul2(p, t), pk2(e0, e1));                         // Phi(-|x|) of both elements
-  upk2(fma2(pk2(-a0, -a1), g, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
-}
-
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -745,11 +699,14 @@ unsigned split_w_blocks(int M, int Kp) { return (unsigned)(((long long)M * (Kp >
 
 static int g_gemm_wide_tiles = 0;   // r3c: with four accumulators 128-column tiles are as fast at 64 pairs and 3.5 % faster at 8
 // Diagnostics / tuning: 0 (default) = 128-column tiles (four TMEM accumulators) also for wide outputs, 1 = 256-column tiles for N >= 512.
+static int g_ft_two_launch_mlp = 0;   // diagnostics: bit 2 -- the FeatureTransformer runs its FFN as two gemm_tc launches instead of mlp_fused.cu
 static int g_gemm_dbg = 0;   // diagnostics: bits 1 and 3 of the switch below (tools/gemm_floor.py); results are garbage while set
 extern "C" void emip_debug_gemm_wide_tiles(int v) {
   g_gemm_wide_tiles = (v & 1) ? 1 : 0;
   g_gemm_dbg = ((v & 2) ? 1 : 0) | ((v & 8) ? 2 : 0);
+  g_ft_two_launch_mlp = (v & 4) ? 1 : 0;
 }
+int gemm_tc_debug_two_launch_mlp() { return g_ft_two_launch_mlp; }
 static unsigned long long* g_gemm_prof = nullptr;
 // Diagnostics (tools/gemm_roles.py): device buffer of (SM count) x 8 cycle counters the next launches ADD to; NULL = off.
 extern "C" void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf) { g_gemm_prof = dev_buf; }

@@ -60,6 +60,8 @@ struct GemmTcParams {
 constexpr int GEMM_TC_KCH = 64;                    // K elements per chunk (one 128-byte swizzle row of bf16)
 constexpr int GEMM_TC_A_BYTES = 128 * 128;         // one [128 x 64] bf16 operand tile
 
+// diagnostics (emip_debug_gemm_wide_tiles bit 2): the FeatureTransformer's FFN as two gemm_tc launches (A / B runs, parity tests)
+int gemm_tc_debug_two_launch_mlp();
 // bf16 tiled tensor map with 128-byte swizzle (rank 3 or 4), out-of-bounds elements read as zero
 int gemm_tc_make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                      const cuuint32_t* box);

@@ -197,6 +197,53 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 
+// exact-GELU x Phi(x) for the epilogue (where the instruction count is the critical path): Phi through the rational
+// erfc form of Abramowitz & Stegun 7.1.26, erfc(z) = poly5(t) e^{-z^2}, t = 1 / (1 + 0.3275911 z), |error| <= 1.5e-7 --
+// below the 2^-17 relative resolution of the bf16 hi | lo pair the value is stored as.  One MUFU.RCP + one MUFU.EX2 and
+// ~12 FP32 instructions instead of erff's two-branch polynomial; no 1 + erf cancellation for negative x.
+__device__ __forceinline__ float gelu_epi(float x) {
+  // 0.5 folded into the polynomial; rcp / ex2 as single MUFU instructions (.ftz: t is in (0, 1], e^{-z^2} may flush to 0)
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.44269504088896340736f * z));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float g = p * t * e;                                   // 0.5 erfc(|x| / sqrt 2) = Phi(-|x|)
+  return x * (x >= 0.f ? 1.f - g : g);
+}
+
+// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2: sm_100 executes two fp32 FMAs per instruction): the GELU / split
+// epilogue of the 256 -> 1024 layer is instruction-issue bound (r3i: 25 instructions per element on eight warps).
+// gelu(x) = max(x, 0) - |x| Phi(-|x|): no select, no 1 - g.
+typedef unsigned long long f32x2;   // two packed fp32 (FFMA2 / FMUL2 operands)
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void gelu_epi2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 ax = pk2(a0, a1);
+  const f32x2 z = mul2(ax, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  float d0, d1, q0, q1, t0, t1, e0, e1;
+  upk2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.f, 1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  upk2(mul2(mul2(z, pk2(-1.44269504088896340736f, -1.44269504088896340736f)), z), q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const f32x2 t = pk2(t0, t1);
+  f32x2 p = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));
+  p = fma2(p, t, pk2(0.7107068705f, 0.7107068705f));
+  p = fma2(p, t, pk2(-0.142248368f, -0.142248368f));
+  p = fma2(p, t, pk2(0.127414796f, 0.127414796f));
+  const f32x2 g = mul2(mul2(p, t), pk2(e0, e1));                         // Phi(-|x|) of both elements
+  upk2(fma2(pk2(-a0, -a1), g, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
+}
+
+
 // fp32 pair -> packed bf16 hi (round to nearest, ties away from zero) + packed bf16 lo (truncated residual) on the
 // integer / FMA pipes only.  cvt.rn.bf16x2.f32 (F2FP) shares the 16-lanes-per-clock XU pipe with MUFU.EX2: in the
 // softmax loops, which need that pipe for the exponentials, two conversions per pair doubled the time per element

@@ -16,6 +16,7 @@
 #include "match_tc.cuh"
 #include "pair_bwd_tc.cuh"
 #include "attn_tc.cuh"
+#include "mlp_fused.cuh"
 #include "attn_bwd_tc.cuh"
 #include "gemm_tc.cuh"
 #include <math.h>
@@ -576,6 +577,19 @@ extern "C" int emip_feature_transformer_fwd_ex(const float* x, float* out, void*
       t.c = nullptr;
       t.ln_hi = ws.xs_hi[1] + KC; t.ln_lo = ws.xs_lo[1] + KC; t.ln_ld = 256;
       if ((rc = gemm_nt_tc(t, nullptr, 0, st, 1))) return rc;
+    }
+    const bool last_split = blk == n_blocks - 1 && out_split != nullptr;
+    MlpFusedArgs f = {};                                  // mlp + norm2 + source in ONE kernel, the hidden rows stay in TMEM (mlp_fused.cu)
+    f.x_hi = ws.xs_hi[1]; f.x_lo = ws.xs_lo[1]; f.ldx = 256;
+    f.w1 = pb + po.mlp0; f.w2 = pb + po.mlp2; f.L = (int)L; f.hid = FT_HID;
+    f.gamma = wt[14]; f.beta = wt[15]; f.eps = eps; f.res = ws.xf[1]; f.ldr = KC;
+    f.y = xnext_f; f.ldy = KC;
+    f.out_hi = last_split ? out_split : static_cast<void*>(ws.xs_hi[0]);
+    f.out_lo = last_split ? static_cast<void*>(static_cast<__nv_bfloat16*>(out_split) + KC) : static_cast<void*>(ws.xs_lo[0]);
+    f.out_ld = 256;
+    if (!gemm_tc_debug_two_launch_mlp() && mlp_fused_supported(f)) {
+      if ((rc = mlp_fused_tc(f, st))) return rc;
+      continue;
     }
     {
       GemmNT t = base_gemm(ws.xs_hi[1], ws.xs_lo[1], 256, 2 * KC, pb + po.mlp0, FT_HID);        // mlp[0] on [source | message] + GELU (:175)

@@ -290,6 +290,36 @@ def test_conv3x3_vs_library_convolution(b, c0, c1, o, h, w, lay0, lay1, relu, sc
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("b,h,w", [(1, 44, 44), (5, 16, 24), (19, 44, 44)])
+def test_fused_mlp_kernel_vs_two_gemm_launches(b, h, w):
+    """mlp_fused.cu (hidden rows kept in TMEM, LayerNorm in its epilogue) against the two gemm_tc launches it replaces, through
+    the whole FeatureTransformer call (six feed-forward networks deep): same products, another summation order in the second GEMM."""
+    from emip_b200 import chain as ch, _lib
+    P = cases.chain_params(seed=11)
+    x = cases.randn(341, (2 * b, h * w, 128), 2.0).cuda()
+    L = _lib.lib()
+    # one block: the kernels' own difference (summation order); six blocks: the same, amplified by the (random-weight) network --
+    # both paths sit at the same distance from the fp64 oracle (test_feature_transformer_fused_call_vs_oracle_and_per_layer_path)
+    for n_blocks, tol in ((1, 2e-6), (6, 3e-4)):
+        m = ch._FeatureTransformer()
+        m.load_state_dict(O.sub_params(P, "GMFlow.transformer."))
+        m.layers = m.layers[:n_blocks]
+        m = m.cuda()
+        with torch.no_grad():
+            try:
+                L.emip_debug_gemm_wide_tiles(4)                      # bit 2: two-launch feed-forward network
+                two, two_split = ch.feature_transformer_tokens(x, m, h, w, 2, want_split=True)
+            finally:
+                L.emip_debug_gemm_wide_tiles(0)
+            fused, fused_split = ch.feature_transformer_tokens(x, m, h, w, 2, want_split=True)
+        err = _rel(fused, two)
+        print(f"fused mlp vs two launches, {n_blocks} block(s), {2 * b} maps of {h}x{w}: rel-L2 {err:.2e}, max |d| {(fused - two).abs().max().item():.2e}")
+        assert err < tol
+        hi = fused.to(torch.bfloat16)
+        assert torch.equal(fused_split[..., :128], hi) and torch.equal(fused_split[..., 128:], (fused - hi.float()).to(torch.bfloat16))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("b,h,w", [(1, 44, 44), (3, 16, 24)])
 def test_presplit_handover_of_the_transformer_rows_is_bit_identical(b, h, w):
     """The bf16 hi | lo rows the last LayerNorm epilogue writes (emip_feature_transformer_fwd_ex out_split) are the split of the
