@@ -39,7 +39,7 @@ GM_STD, SEG_STD = 2.2, 1.0          # feature scales measured inside the model (
 N_INPUT_SETS = 4                    # rotated: inputs + the step's intermediates exceed the 126 MB L2 at every shard size
 CPU_SAMPLE_PAIRS = 2                # bounded sample of the c3 batch for the CPU arms
 # K1 sub-record (BASELINE.json configs[1], "c2")
-NCU_MLP_DRAM_BYTES, NCU_MLP_ROWS = 2.592e9, 247808     # measured once per kernel change with ncu (profiles/)
+NCU_MLP_DRAM_BYTES, NCU_MLP_ROWS = 0.4874e9, 247808    # measured once per kernel change with ncu (profiles/r4v_mlp_fused_full.txt)
 K1_B = 16
 K1_ALG_FLOP_PER_PAIR = 2.0 * N * N * C + 8.0 * N * N          # S counted once
 K1_EXEC_MMA_FLOP_PER_PAIR = 2.0 * N * N * C * 3 * 2           # bf16 hi/lo split (x3), both directions (x2)
@@ -420,9 +420,10 @@ def main():
 
 
 def dominant_kernel_roofline(torch, chain, per, dev, pk):
-    """gemm_tc_kernel is the chain's dominant kernel (every Linear / 1x1 / 3x3 convolution); its largest single call is
-    the FeatureTransformer MLP (256 -> 1024 -> GELU -> 128 + LayerNorm + residual, transformer.py:139-147, :175-180) on the
-    shard's 2 * pairs * 1936 token rows: timed alone with CUDA events on its stream, algorithmic FLOPs / time."""
+    """The chain's dominant kernel is the FeatureTransformer's feed-forward network (256 -> 1024 -> GELU -> 128 + LayerNorm +
+    residual, transformer.py:139-147, :175-180; mlp_fused_kernel, six launches per pass, a quarter of the step) on the shard's
+    2 * pairs * 1936 token rows: the public call (operand split of the fp32 rows + the fused kernel) timed alone with CUDA events
+    on its stream, algorithmic FLOPs / time."""
     from emip_b200.transformer_layer import mlp_tm
     lay = chain.GMFlow.transformer.layers[0].cross_attn_ffn
     Lr = 2 * per * N
@@ -443,20 +444,23 @@ def dominant_kernel_roofline(torch, chain, per, dev, pk):
     ms = e0.elapsed_time(e1) / n
     alg = 2.0 * Lr * (256 * 1024 + 1024 * 128)
     ach = alg / (ms * 1e-3) / 1e12
-    return {"kernel": "gemm_tc_kernel (FeatureTransformer MLP call: 2 launches + operand split)", "bound": "tensor", "achieved": ach,
+    return {"kernel": "mlp_fused_kernel (FeatureTransformer feed-forward call: operand split of the fp32 rows + ONE fused kernel, hidden rows kept in TMEM)",
+            "bound": "tensor", "achieved": ach,
             "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"],
-            "traffic": NCU_MLP_DRAM_BYTES * Lr / NCU_MLP_ROWS, "traffic_unit": "bytes per call",
-            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the two launches at 247808 rows "
-                              "(profiles/r2j_gemm_tc_transformer_full.txt: mlp[0] 0.255 GB read + 0.961 GB written, mlp[2] 1.146 + 0.230), "
-                              "scaled by rows; algorithmic: 0.25 + 1.02 | 1.02 + 0.13 (residual) + 0.13 (out) + 0.13 (hi | lo out) GB",
+            "traffic": NCU_MLP_DRAM_BYTES * Lr / NCU_MLP_ROWS, "traffic_unit": "bytes per launch of the fused kernel",
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of mlp_fused_kernel at 247808 rows "
+                              "(profiles/r4v_mlp_fused_full.txt: 0.382 GB read + 0.105 GB written, 546 us, tensor pipe 52 % of elapsed), scaled "
+                              "by rows; algorithmic: 0.25 (rows, bf16 hi | lo) + 0.13 (residual) + 0.13 (out) GB -- the two-launch version "
+                              "it replaces moved 2.59 GB (hidden rows out and back in); the operand split in front of the kernel in THIS call "
+                              "(0.25 GB read + 0.25 GB written) does not exist inside the FeatureTransformer call, where the rows arrive pre-split",
             "peak_source": pk["src"] + " burst bf16 (cuBLAS)", "call_ms": ms, "rows": Lr,
             "executed_mma_tflops": 3 * ach, "executed_mma_frac": 3 * ach / pk["tf"],
             "note": "achieved = algorithmic 2*L*(256*1024 + 1024*128) FLOP / time; executed = x3 (bf16 hi/lo split keeps fp32 accuracy)"}
 
 
 def ft_roofline(torch, chain, per, dev, pk):
-    """The FeatureTransformer call (emip_feature_transformer_fwd: 54 gemm_tc_kernel + 24..48 attn_fwd_tc_kernel launches) = half of
-    the step: algorithmic FLOPs of its twelve layers / CUDA-event time of the call."""
+    """The FeatureTransformer call (emip_feature_transformer_fwd: 36 gemm_tc_kernel + 6 mlp_fused_kernel + 12 attn_fwd_tc_kernel launches)
+    = half of the step: algorithmic FLOPs of its twelve layers / CUDA-event time of the call."""
     from emip_b200.chain import feature_transformer_tokens
     maps = 2 * per
     Lr = maps * N

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "../../include/emip_b200.h"
 #include "gemm_tc.cuh"
+#include "mlp_fused.cuh"
 
 namespace {
 // wt[k][m] = w[m][k]  (the weights are at most 1 MB: 32 x 32 tiles through shared memory)
@@ -224,6 +225,24 @@ extern "C" int emip_mlp_ln_tm_fwd(const float* x, const float* w1, const float* 
   if (ws_bytes < emip_mlp_tm_workspace(L, K1, Hd, M)) { emip_set_error("mlp_tm_fwd: workspace too small"); return EMIP_ENOMEM; }
   EMIP_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "mlp_tm_fwd: workspace must be 1024-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  // the transformer's shape with its LayerNorm: one kernel, hidden rows kept on the SM (mlp_fused.cu); the workspace then only holds
+  // the operand splits of x, w1, w2 (always smaller than the hidden tensor it is sized for, except for a handful of rows)
+  if (gamma != nullptr && K1 == 256 && M == 128 && Hd % 128 == 0 && !gemm_tc_debug_two_launch_mlp()) {
+    const size_t xb = emip_align_up((size_t)L * K1 * 2 * 2, 1024), w1b = emip_align_up(gemm_tc_split_b_bytes(Hd, K1), 1024),
+                 w2b = emip_align_up(gemm_tc_split_b_bytes(M, Hd), 1024);
+    MlpFusedArgs f = {};
+    char* base = static_cast<char*>(workspace);
+    f.x_hi = base; f.x_lo = base + (size_t)L * K1 * 2; f.ldx = K1;
+    f.w1 = base + xb; f.w2 = base + xb + w1b; f.L = L; f.hid = Hd;
+    f.gamma = gamma; f.beta = beta; f.eps = eps; f.res = res; f.ldr = M; f.y = y; f.ldy = M;
+    if (xb + w1b + w2b <= ws_bytes && mlp_fused_supported(f)) {
+      int rc;
+      if ((rc = gemm_tc_split_rows(x, L, K1, base, base + (size_t)L * K1 * 2, st))) return rc;
+      if ((rc = gemm_tc_split_b(w1, K1, Hd, K1, base + xb, st))) return rc;
+      if ((rc = gemm_tc_split_b(w2, Hd, M, Hd, base + xb + w1b, st))) return rc;
+      return mlp_fused_tc(f, st);
+    }
+  }
   __nv_bfloat16* h_hi = static_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* h_lo = h_hi + (size_t)L * Hd;
   void* scratch = static_cast<char*>(workspace) + hid_bytes(L, Hd);
