@@ -37,8 +37,10 @@ constexpr float NORM_EPS = 1e-12f;
 // walking 2 x 128 strided loads filled a tenth of the chip (15 us for a 16 MB read).
 constexpr int LN_PX = 32, LN_GR = 8, LN_CPT = DIM / LN_GR;
 __global__ void __launch_bounds__(LN_PX * LN_GR)
-ln_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int C, int N) {
+ln_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int C, int N,
+                const float* __restrict__ x2 = nullptr, float* __restrict__ mean2 = nullptr, float* __restrict__ rstd2 = nullptr) {
   __shared__ float red[LN_GR][LN_PX];
+  if (blockIdx.z == 1) { x = x2; mean = mean2; rstd = rstd2; }      // gridDim.z == 2: the statistics of two tensors in one launch
   const int b = blockIdx.y, px = threadIdx.x & (LN_PX - 1), gr = threadIdx.x / LN_PX;
   const int n = blockIdx.x * LN_PX + px;
   const bool ok = n < N;
@@ -482,7 +484,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // sumsq (optional): per (b, c) sum of squares of the output (for F.normalize over the pixels).
 __global__ void __launch_bounds__(256)
 dwconv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, float* __restrict__ out2,
-                  float* __restrict__ sumsq, int C, int split, int H, int W) {
+                  float* __restrict__ sumsq, int C, int split, int H, int W, int sq_C) {
   extern __shared__ float sm[];
   __shared__ float red[8];
   const int c = blockIdx.x, b = blockIdx.y, N = H * W, Wp = W + 2;
@@ -498,9 +500,9 @@ dwconv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, flo
     o[i] = v;
     ss = fmaf(v, v, ss);
   }
-  if (sumsq != nullptr) {
+  if (sumsq != nullptr && c < sq_C) {                     // block-uniform: |row|^2 of the first sq_C channels, [B][sq_C]
     ss = block_sum(ss, red);
-    if (threadIdx.x == 0) sumsq[(size_t)b * C + c] = ss;
+    if (threadIdx.x == 0) sumsq[(size_t)b * sq_C + c] = ss;
   }
 }
 
@@ -681,7 +683,7 @@ __device__ __forceinline__ float block_sums(const float (&v)[N], float* red /* [
 
 __global__ void __launch_bounds__(256)
 dwconv_fwd_v4_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, float* __restrict__ out2,
-                     float* __restrict__ sumsq, int C, int split, int H, int W) {
+                     float* __restrict__ sumsq, int C, int split, int H, int W, int sq_C) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float red[8];
   const int c = blockIdx.x, b = blockIdx.y, N = H * W, PW = W + 8, W4 = W >> 2;
@@ -700,9 +702,9 @@ dwconv_fwd_v4_kernel(const float* __restrict__ in, const float* __restrict__ w, 
     reinterpret_cast<float4*>(o)[i] = make_float4(r[0], r[1], r[2], r[3]);
     ss = fmaf(r[0], r[0], fmaf(r[1], r[1], fmaf(r[2], r[2], fmaf(r[3], r[3], ss))));
   }
-  if (sumsq != nullptr) {
+  if (sumsq != nullptr && c < sq_C) {                     // block-uniform: |row|^2 of the first sq_C channels, [B][sq_C]
     ss = block_sum(ss, red);
-    if (threadIdx.x == 0) sumsq[(size_t)b * C + c] = ss;
+    if (threadIdx.x == 0) sumsq[(size_t)b * sq_C + c] = ss;
   }
 }
 
@@ -1106,26 +1108,17 @@ ln_bwd_param_kernel(const float* __restrict__ dn, const float* __restrict__ x, c
 }
 
 // ------------------------------------------------------------------ host-side launch helpers
-__global__ void __launch_bounds__(256) row_sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int N) {
-  __shared__ float red[8];
-  const size_t row = blockIdx.x;
-  float s = 0.f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    const float v = __ldg(x + row * N + n);
-    s = fmaf(v, v, s);
-  }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) out[row] = s;
-}
-int launch_row_sumsq(const float* x, float* out, int rows, int N, cudaStream_t st) {
-  row_sumsq_kernel<<<rows, 256, 0, st>>>(x, out, N);
-  EMIP_CHECK_LAUNCH("row_sumsq");
-  return EMIP_OK;
-}
-
 int launch_ln_stats(const float* x, float* mean, float* rstd, int B, int C, int N, cudaStream_t st) {
   if (C != DIM) { emip_set_error("ln_stats: C=%d unsupported", C); return EMIP_ENOSYS; }
   ln_stats_kernel<<<dim3((N + LN_PX - 1) / LN_PX, B), LN_PX * LN_GR, 0, st>>>(x, mean, rstd, C, N);
+  EMIP_CHECK_LAUNCH("ln_stats");
+  return EMIP_OK;
+}
+// the statistics of two tensors of one shape (norm1 of x, norm2 of x1) in one launch
+int launch_ln_stats2(const float* x, float* mean, float* rstd, const float* x2, float* mean2, float* rstd2, int B, int C, int N,
+                     cudaStream_t st) {
+  if (C != DIM) { emip_set_error("ln_stats: C=%d unsupported", C); return EMIP_ENOSYS; }
+  ln_stats_kernel<<<dim3((N + LN_PX - 1) / LN_PX, B, 2), LN_PX * LN_GR, 0, st>>>(x, mean, rstd, C, N, x2, mean2, rstd2);
   EMIP_CHECK_LAUNCH("ln_stats");
   return EMIP_OK;
 }
@@ -1358,8 +1351,7 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   }
 
   // norm1 / norm2 statistics (PromptInteract.py:447, :346-349)
-  if ((rc = launch_ln_stats(x, s.mean1, s.rstd1, B, DIM, N, st))) return rc;
-  if ((rc = launch_ln_stats(x1, s.mean2, s.rstd2, B, DIM, N, st))) return rc;
+  if ((rc = launch_ln_stats2(x, s.mean1, s.rstd1, x1, s.mean2, s.rstd2, B, DIM, N, st))) return rc;
   // q = q_dwconv(q(LN1 x)), kv = kv_dwconv(kv(LN2 x1))      (:413-415)
   GemmNN a = {};
   a.B = B; a.N = N; a.K = DIM; a.ldx = N; a.x_stride_b = (long long)DIM * N; a.ldy = N;
@@ -1372,12 +1364,13 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
   const size_t sm1 = plane_smem(H, W, 1);
   const bool v4 = (W & 3) == 0;
   if ((rc = v4 ? ensure_smem(dwconv_fwd_v4_kernel, sm1) : ensure_smem(dwconv_fwd_kernel, sm1))) return rc;
-  if (v4) dwconv_fwd_v4_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
-  else dwconv_fwd_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W);
+  if (v4) dwconv_fwd_v4_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W, DIM);
+  else dwconv_fwd_kernel<<<dim3(DIM, B), 256, sm1, st>>>(s.qpre, params[P_QDW], s.q, nullptr, s.sq, DIM, DIM, H, W, DIM);
   EMIP_CHECK_LAUNCH("dwconv q");
-  // k = channels [0,128), v = [128,256) of kv (:415); only k is L2-normalised
-  if (v4) dwconv_fwd_v4_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
-  else dwconv_fwd_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, nullptr, 2 * DIM, DIM, H, W);
+  // k = channels [0,128), v = [128,256) of kv (:415); only k is L2-normalised: |k_d|^2 over the pixels (F.normalize, :422) comes
+  // out of this kernel like |q_c|^2 out of the one above (r5: a separate row_sumsq pass over k, 49 us at 64 pairs, is gone)
+  if (v4) dwconv_fwd_v4_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, s.sk, 2 * DIM, DIM, H, W, DIM);
+  else dwconv_fwd_kernel<<<dim3(2 * DIM, B), 256, sm1, st>>>(s.kvpre, params[P_KVDW], s.k, s.v, s.sk, 2 * DIM, DIM, H, W, DIM);
   EMIP_CHECK_LAUNCH("dwconv kv");
   // G[c][d] = sum_n q[c][n] k[d][n] per (sample, head)      (:421-424, normalisation folded in afterwards)
   {
@@ -1393,8 +1386,6 @@ extern "C" int emip_injector_fwd_ex(const float* x, const float* x1, const float
     sum_splits_kernel<<<(B * HEADS * HD * HD + 255) / 256, 256, 0, st>>>(gpart, s.G, B * HEADS, G_SPLIT, HD * HD);
     EMIP_CHECK_LAUNCH("sum_splits");
   }
-  // |k_d|^2 over the pixels (F.normalize, :422); |q_c|^2 came out of the q depthwise kernel
-  if ((rc = launch_row_sumsq(s.k, s.sk, B * DIM, N, st))) return rc;
   mdta_attn_fwd_kernel<<<dim3(B * HEADS, 4), 256, 0, st>>>(s.G, s.sq, s.sk, params[P_TEMP], params[P_POW], s.attn, s.M);
   EMIP_CHECK_LAUNCH("mdta_attn_fwd");
   // y = x + project_out(attn @ v) = x + M[b] v             (:427-431, :447)
