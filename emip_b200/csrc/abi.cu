@@ -69,3 +69,8 @@ extern "C" int emip_device_check(void) {
   }
   return EMIP_OK;
 }
+
+// Diagnostics: programmatic dependent launch of the persistent tensor-core kernels on / off (common.cuh::emip_launch_pdl)
+static int g_pdl = 1;
+int emip_pdl_enabled() { return g_pdl; }
+void emip_pdl_set(int on) { g_pdl = on ? 1 : 0; }

@@ -106,6 +106,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ AMaps maps, const __grid_constant__ AParams ap) {
   const AttnTcArgs& p = ap.a;
+  pdl_trigger();                                          // common.cuh: the next kernel's prologue may overlap this kernel's tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -145,6 +146,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AMaps maps, const __grid_constant__ A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                             // everything below reads what the kernel in front of this one wrote
 
   if (warp == NMATH) {
     // ===================== TMA producer =====================
@@ -526,7 +528,7 @@ int attn_tc_fwd(const AttnTcArgs& a, cudaStream_t st) {
   if (int rc__ = emip_func_max_smem((const void*)(attn_fwd_tc_kernel<true>), SMEM_BYTES)) return rc__;
   if (grid > emip_num_sms()) grid = emip_num_sms();
   if (ap.prof) attn_fwd_tc_kernel<true><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(maps, ap);   // diagnostics build
-  else attn_fwd_tc_kernel<false><<<(int)grid, NTHREADS, SMEM_BYTES, st>>>(maps, ap);
+  else EMIP_CUDA(emip_launch_pdl(attn_fwd_tc_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, maps, ap));
   EMIP_CHECK_LAUNCH("attn_tc_fwd");
   return EMIP_OK;
 }

@@ -28,6 +28,7 @@ template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b, const GemmTcParams p) {
+  pdl_trigger();                                          // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -75,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                             // everything below reads what the kernel in front of this one wrote
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -705,6 +707,7 @@ extern "C" void emip_debug_gemm_wide_tiles(int v) {
   g_gemm_wide_tiles = (v & 1) ? 1 : 0;
   g_gemm_dbg = ((v & 2) ? 1 : 0) | ((v & 8) ? 2 : 0);
   g_ft_two_launch_mlp = (v & 4) ? 1 : 0;
+  emip_pdl_set((v & 16) ? 0 : 1);
 }
 int gemm_tc_debug_two_launch_mlp() { return g_ft_two_launch_mlp; }
 static unsigned long long* g_gemm_prof = nullptr;
@@ -739,11 +742,11 @@ int gemm_tc_launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
   const int grid = (int)(tiles < emip_num_sms() ? tiles : emip_num_sms());      // persistent CTAs, one per SM
   const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 8) + 16 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES + 16 : 0) + (epi == 2 ? 1024 : 0);
   switch (epi) {
-    case 0: gemm_tc_kernel<0><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
-    case 1: gemm_tc_kernel<1><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
-    case 2: gemm_tc_kernel<2><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
-    case 3: gemm_tc_kernel<3><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
-    default: gemm_tc_kernel<4><<<grid, THREADS, smem, st>>>(a_hi, a_lo, b, p); break;
+    case 0: EMIP_CUDA(emip_launch_pdl(gemm_tc_kernel<0>, dim3(grid), dim3(THREADS), (size_t)smem, st, a_hi, a_lo, b, p)); break;
+    case 1: EMIP_CUDA(emip_launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(THREADS), (size_t)smem, st, a_hi, a_lo, b, p)); break;
+    case 2: EMIP_CUDA(emip_launch_pdl(gemm_tc_kernel<2>, dim3(grid), dim3(THREADS), (size_t)smem, st, a_hi, a_lo, b, p)); break;
+    case 3: EMIP_CUDA(emip_launch_pdl(gemm_tc_kernel<3>, dim3(grid), dim3(THREADS), (size_t)smem, st, a_hi, a_lo, b, p)); break;
+    default: EMIP_CUDA(emip_launch_pdl(gemm_tc_kernel<4>, dim3(grid), dim3(THREADS), (size_t)smem, st, a_hi, a_lo, b, p)); break;
   }
   EMIP_CHECK_LAUNCH("gemm_tc");
   return EMIP_OK;

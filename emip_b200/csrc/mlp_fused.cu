@@ -58,6 +58,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                  const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                  const __grid_constant__ MParams mp) {
   const MlpFusedArgs& p = mp.a;
+  pdl_trigger();                                          // common.cuh: the next kernel's prologue may overlap this kernel's tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -97,6 +98,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                             // everything below reads what the kernel in front of this one wrote
 
   if (warp == NMATH) {
     // ===================== TMA producer =====================
@@ -429,7 +431,7 @@ int mlp_fused_tc(const MlpFusedArgs& a, cudaStream_t st) {
   mp.nj = a.hid / TN;
   const int grid = mp.n_tiles < emip_num_sms() ? mp.n_tiles : emip_num_sms();
   if (mp.prof) mlp_fused_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mxh, mxl, mw1, mw2, mp);      // diagnostics build
-  else mlp_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mxh, mxl, mw1, mw2, mp);
+  else EMIP_CUDA(emip_launch_pdl(mlp_fused_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, mxh, mxl, mw1, mw2, mp));
   EMIP_CHECK_LAUNCH("mlp_fused_tc");
   return EMIP_OK;
 }

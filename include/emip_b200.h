@@ -91,7 +91,8 @@ void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf);
  * accumulators (default), 1 = 256-column tiles.  Bit 1: the epilogue warps of gemm_tc_kernel skip their work (no math, no stores:
  * the OUTPUT IS GARBAGE) so that tools/gemm_floor.py can time the TMA + MMA pipeline alone.  Bit 2: emip_feature_transformer_fwd runs
  * the feed-forward network as two GEMM launches (hidden rows through HBM) instead of the fused kernel -- for A / B timing and the
- * parity test of the fused kernel.  Bit 3: the producer warp skips the operand loads as well (UMMA issue rate alone; garbage).  0 restores the defaults. */
+ * parity test of the fused kernel.  Bit 3: the producer warp skips the operand loads as well (UMMA issue rate alone; garbage).  Bit 4: the
+ * persistent tensor-core kernels are launched without programmatic dependent launch (A / B timing).  0 restores the defaults. */
 void emip_debug_gemm_wide_tiles(int v);
 /* Diagnostics: wait-cycle profile of the staged flow_warp kernel, device pointer to [grid][8] int64 or NULL. */
 void emip_debug_flow_warp_staged_profile(long long* buf);
