@@ -8,8 +8,8 @@
 //   warps 0..15 GELU + operand split, then the LayerNorm epilogue (thread <-> TMEM lane <-> row; warp w: lane quarter w % 4,
 //               32-column part w / 4 of every 128-column block)
 //   warp 16     TMA producer: the row tile X (4 K chunks x hi, lo = 128 KB, resident for the 8 hidden blocks), then per
-//               hidden block j the W1 rows of the block (4 K chunks x hi, lo) and the W2 columns of the block (2 K chunks
-//               x hi, lo) through a 6-stage ring of 16 KB tiles, in the issuer's consumption order
+//               hidden block j the W1 rows of the block (4 K chunks x (hi, lo)) and the W2 columns of the block (2 K chunks
+//               x (hi, lo)) through a 6-stage ring of 16 KB tiles, in the issuer's consumption order
 //   warp 17     UMMA issuer
 // TMEM (512 columns): S double-buffered [0, 256) | H as bf16 hi [256, 320) + lo [320, 384) | OUT accumulator [384, 512).
 //   UMMA-1 (SS): S_j  = X.hi W1_j.hi^T + X.lo W1_j.hi^T + X.hi W1_j.lo^T         (K = 256, the 3-term bf16 split)
@@ -18,7 +18,7 @@
 // The issuer runs UMMA-1 of block j + 1 ahead of UMMA-2 of block j, so the GELU of block j overlaps the first GEMM of the next.
 // S_j accumulates in the order of gemm_tc_kernel (per 64-wide K chunk: hi.hi, lo.hi, hi.lo) and H is split with the same
 // round-to-nearest conversions as its epilogue, so the hidden operand is bit-identical to the two-launch path; OUT sums the same
-// products in a different order (per block hi.hi / lo.hi interleaved per K16 step, then hi.lo), ~1e-7 relative.
+// products in a different order (per 64-wide K half: hi.hi / lo.hi interleaved per K16 step, then hi.lo), ~1e-7 relative.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/emip_b200.h"
@@ -140,10 +140,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         push(&map_w1, KX + kc * 64, j * TN);
       }
     };
-    auto push_w2 = [&](int j) {          // columns j*128.. of W2: hi (k 0..63, 64..127), then lo
+    auto push_w2 = [&](int j) {          // columns j*128.. of W2: per 64-wide K half the hi tile, then the lo tile (like W1)
       push(&map_w2, j * TN, 0);
-      push(&map_w2, j * TN + 64, 0);
       push(&map_w2, p.hid + j * TN, 0);
+      push(&map_w2, j * TN + 64, 0);
       push(&map_w2, p.hid + j * TN + 64, 0);
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -165,7 +165,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     }
     if (PROF && mp.prof && leader) {
       unsigned long long* o = mp.prof + blockIdx.x * 16;
-      o[13] = w_re; o[14] = w_xe; o[15] = clock64() - t_begin;
+      o[13] = w_re + w_xe; o[15] = clock64() - t_begin;
     }
     __syncwarp();
   } else if (warp == NMATH + 1) {
@@ -175,7 +175,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     uint32_t phase = 0, it = 0, tile = 0;
     const uint32_t idesc = make_idesc(TN);
     const uint32_t t_h = tmem_base + COL_H, t_o = tmem_base + COL_O;
-    long long w_se = 0, w_rf = 0, w_hf = 0, w_oe = 0, w_xf = 0;
+    long long w_se = 0, w_rf = 0, w_rf2 = 0, w_hf = 0, w_oe = 0, w_xf = 0;
     const long long t_begin = PROF ? clock64() : 0;
     auto mma1 = [&](uint32_t T, bool first_of_tile) {      // S block T -> TMEM buffer T & 1
       const int buf = T & 1;
@@ -214,22 +214,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     auto mma2 = [&](uint32_t T, bool first, bool last) {   // OUT += H(T) W2(T)^T, H read from TMEM
       prof_add<PROF>(w_hf, mbar_wait(h_full, T & 1));
       if (first) prof_add<PROF>(w_oe, mbar_wait(o_empty, (it & 1) ^ 1));          // the LayerNorm epilogue of the previous row tile has drained OUT
-      for (int half = 0; half < 2; ++half) {                // W2.hi tiles, then W2.lo tiles
+      // per 64-wide K half of the block: (W2.hi tile, W2.lo tile) = one ring pair, 12 UMMAs -- the same bytes per UMMA cycle as a
+      // UMMA-1 group (r5: as [hi k0, hi k1 | 16 UMMAs][lo k0, lo k1 | 8 UMMAs] the second pair had to arrive within 512 cycles)
+      for (int kh = 0; kh < 2; ++kh) {
         const int s0 = stage;
-        prof_add<PROF>(w_rf, mbar_wait(r_full(s0), phase));
-        prof_add<PROF>(w_rf, mbar_wait(r_full(s0 + 1), phase));
+        prof_add<PROF>(w_rf2, mbar_wait(r_full(s0), phase));
+        prof_add<PROF>(w_rf2, mbar_wait(r_full(s0 + 1), phase));
         tc_fence_after();
         if (leader) {
-          const uint64_t bd = make_kmajor_sw128_desc(sbase + OFF_RING + s0 * CHUNK_BYTES);
+          const uint64_t bh = make_kmajor_sw128_desc(sbase + OFF_RING + s0 * CHUNK_BYTES);
+          const uint64_t bl = make_kmajor_sw128_desc(sbase + OFF_RING + (s0 + 1) * CHUNK_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t b = bd + (uint64_t)((kk >> 2) * (CHUNK_BYTES >> 4) + 2 * (kk & 3));
-            umma_bf16_ts(t_o, t_h + (uint32_t)(8 * kk), b, idesc, (first && half == 0 && kk == 0) ? 0u : 1u);   // H.hi W2.(hi | lo)
-            if (half == 0) umma_bf16_ts(t_o, t_h + 64 + (uint32_t)(8 * kk), b, idesc, 1u);                      // H.lo W2.hi
-            if (kk == 3) umma_commit(r_empty(s0));          // k 0..63 done: that tile goes back early
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t ka = (uint32_t)(8 * (kh * 4 + k4));            // 16 k = 8 packed columns of H
+            umma_bf16_ts(t_o, t_h + ka, bh + 2 * k4, idesc, (first && kh == 0 && k4 == 0) ? 0u : 1u);     // H.hi W2.hi
+            umma_bf16_ts(t_o, t_h + 64 + ka, bh + 2 * k4, idesc, 1u);                                    // H.lo W2.hi
           }
+          umma_commit(r_empty(s0));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) umma_bf16_ts(t_o, t_h + (uint32_t)(8 * (kh * 4 + k4)), bl + 2 * k4, idesc, 1u);   // H.hi W2.lo
           umma_commit(r_empty(s0 + 1));
-          if (half == 1) {
+          if (kh == 1) {
             umma_commit(h_empty);
             if (last) umma_commit(o_full);
           }
@@ -259,7 +264,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     }
     if (PROF && mp.prof && leader) {
       unsigned long long* o = mp.prof + blockIdx.x * 16;
-      o[7] = w_se; o[8] = w_rf; o[9] = w_hf; o[10] = w_oe; o[11] = w_xf; o[12] = clock64() - t_begin;
+      o[7] = w_se; o[8] = w_rf + w_rf2; o[9] = w_hf; o[10] = w_oe; o[11] = w_xf; o[12] = clock64() - t_begin; o[14] = w_rf2;
     }
     __syncwarp();
   } else {

@@ -18,7 +18,7 @@ x = torch.randn(2 * pairs, 1936, 128, device=dev)
 L = _lib.lib()
 names = ["math: wait s_full", "math: tmem ld + GELU + split", "math: wait h_empty", "math: tmem st + arrive", "math: wait o_full", "math: LayerNorm epilogue",
          "math: total", "mma: wait s_empty", "mma: wait ring", "mma: wait h_full", "mma: wait o_empty", "mma: wait x_full", "mma: total",
-         "tma: wait ring slot", "tma: wait x_empty", "tma: total"]
+         "tma: wait ring slot / x_empty", "mma: wait ring (UMMA-2 part of it)", "tma: total"]
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 with torch.no_grad():
     for rep in range(3):
