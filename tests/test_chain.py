@@ -50,6 +50,21 @@ def test_chain_refuses_cpu_tensors():
         m(torch.zeros(2, 128, 16, 16), torch.zeros(2, 128, 16, 16))
 
 
+def test_token_row_entry_points_refuse_cpu_and_wrong_operands():
+    """The hand-over wrappers fail loudly instead of falling back: CPU tensors, fp32 rows where the bf16 hi | lo operand is expected."""
+    from emip_b200 import chain as ch
+    from emip_b200._lib import EmipError
+    ft = ch._FeatureTransformer()
+    with pytest.raises(EmipError):
+        ch.feature_transformer_tokens(torch.zeros(2, 64, 128), ft, 8, 8, 2, want_split=True)
+    ffa = _chain(cases.chain_params(hw=16 * 16, corr_mid=64), hw=16 * 16, corr_mid=64).GMFlow.feature_flow_attn
+    with pytest.raises((EmipError, TypeError)):
+        ch.flow_attention_tokens(torch.zeros(2, 64, 256, dtype=torch.bfloat16), ffa, torch.zeros(2, 2, 64))
+    if torch.cuda.is_available():
+        with pytest.raises(TypeError):                           # fp32 rows are not the pre-split operand
+            ch.flow_attention_tokens(torch.zeros(2, 64, 256, device="cuda"), ffa.cuda(), torch.zeros(2, 2, 64, device="cuda"))
+
+
 def _rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
