@@ -25,6 +25,7 @@ The module owns (or borrows, ``MotionChain.wrap``) parameters under the referenc
 checkpoint loads with ``strict=False`` key filtering exactly as test.py:85-89 does.  There is no CPU / library fallback.
 """
 import ctypes
+import threading
 import math
 
 import torch
@@ -544,6 +545,9 @@ class MotionChain(nn.Module):
         return flow_up[:B], flow_up[B:], corr, fea_new                                           # gmflow.py:152-155
 
 
+_capture_lock = threading.Lock()
+
+
 class GraphedChain:
     """One ``MotionChain.forward`` on fixed device buffers captured into a CUDA graph: ``replay()`` re-runs the ~150 kernel
     launches of a step as one graph launch (the per-GPU shards of c3 are launch-latency sized: 8 pairs at 8 GPUs).
@@ -553,7 +557,10 @@ class GraphedChain:
     stream it is handed and takes caller-owned workspaces, so the capture contains no allocation and no host sync.
     """
 
-    def __init__(self, chain, gm, seg, pool=None):
+    def __init__(self, chain, gm, seg, pool=None, pdl=True):
+        """``pdl``: capture the persistent tensor-core kernels with programmatic dependent launch (``emip_set_programmatic_launch``;
+        ~1 % of the step).  Right when this graph's stream owns the GPU, as in ``bench.py``; pass ``False`` when several such graphs
+        replay concurrently on different streams (an early-launched CTA then blocks an SM another stream could use)."""
         self.chain, self.gm, self.seg = chain, gm, seg
         dev = gm.device
         side = torch.cuda.Stream(device=dev)
@@ -567,8 +574,14 @@ class GraphedChain:
             self.graph = torch.cuda.CUDAGraph(keep_graph=True)
         except TypeError:
             self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool):
-            self.outputs = chain(gm, seg)
+        L = _lib.lib()
+        with _capture_lock:                           # the launch policy is process-wide: frozen into this graph, then restored
+            prev = L.emip_set_programmatic_launch(I(1 if pdl else 0))
+            try:
+                with torch.no_grad(), torch.cuda.graph(self.graph, pool=pool):
+                    self.outputs = chain(gm, seg)
+            finally:
+                L.emip_set_programmatic_launch(I(prev))
         self.kernel_nodes = _count_kernel_nodes(self.graph)
         self.graph.replay()                           # instantiate now, not inside somebody's timed region
         torch.cuda.synchronize(dev)

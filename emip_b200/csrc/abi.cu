@@ -70,7 +70,12 @@ extern "C" int emip_device_check(void) {
   return EMIP_OK;
 }
 
-// Diagnostics: programmatic dependent launch of the persistent tensor-core kernels on / off (common.cuh::emip_launch_pdl)
-static int g_pdl = 1;
+// Launch policy (include/emip_b200.h): programmatic dependent launch of the persistent tensor-core kernels
+// (common.cuh::emip_launch_pdl).  Off unless the caller, who knows that ONE stream owns the GPU, switches it on.
+static int g_pdl = 0;
 int emip_pdl_enabled() { return g_pdl; }
-void emip_pdl_set(int on) { g_pdl = on ? 1 : 0; }
+extern "C" int emip_set_programmatic_launch(int on) {
+  const int prev = g_pdl;
+  g_pdl = on ? 1 : 0;
+  return prev;
+}

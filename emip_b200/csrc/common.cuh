@@ -55,9 +55,9 @@ int emip_func_max_smem(const void* func, int bytes);
 // mlp_fused_kernel (one CTA per SM: nothing of the next kernel can start on an SM before this kernel's CTA there is gone).  Same-box
 // A / B of the chain step (tools/pdl_ab.py, profiles/r5h_pdl_ab.txt): -0.8 % at 64 pairs, -1.3 % at 8.  Extending it to the small
 // many-block kernels around them (operand splits, the prompt fusion's glue) was +1.4 % at 64 pairs (r5i: their blocks co-reside with
-// the running persistent CTAs and wait there): not kept.
-int emip_pdl_enabled();     // abi.cu: 1 unless switched off for an A / B run (emip_debug_gemm_wide_tiles bit 4)
-void emip_pdl_set(int on);
+// the running persistent CTAs and wait there): not kept.  OFF by default (emip_set_programmatic_launch): with several streams on
+// one GPU an early-launched CTA holds an SM another stream's kernel could use -- c4 with four clip streams lost 28 % (r5q).
+int emip_pdl_enabled();     // abi.cu: the process-wide launch policy set through emip_set_programmatic_launch (default 0)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

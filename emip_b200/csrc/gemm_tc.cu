@@ -707,7 +707,6 @@ extern "C" void emip_debug_gemm_wide_tiles(int v) {
   g_gemm_wide_tiles = (v & 1) ? 1 : 0;
   g_gemm_dbg = ((v & 2) ? 1 : 0) | ((v & 8) ? 2 : 0);
   g_ft_two_launch_mlp = (v & 4) ? 1 : 0;
-  emip_pdl_set((v & 16) ? 0 : 1);
 }
 int gemm_tc_debug_two_launch_mlp() { return g_ft_two_launch_mlp; }
 static unsigned long long* g_gemm_prof = nullptr;

@@ -32,7 +32,8 @@
  *      (4) diagnostic switches for the profiling scripts under tools/ --
  *          emip_match_tc_set_profile_buffer, emip_match_tc_set_variant,
  *          emip_attn_tc_set_profile_buffer, emip_gemm_tc_set_profile_buffer,
- *          emip_debug_flow_warp_staged_profile, emip_debug_gemm_wide_tiles --
+ *          emip_debug_flow_warp_staged_profile, emip_debug_gemm_wide_tiles, and the launch policy
+ *          emip_set_programmatic_launch (default off) --
  *          NOT thread-safe, never touched by the host package, default off.
  *    No entry point allocates or frees memory (cudaMalloc / cudaHostAlloc), so all
  *    of them may be captured into CUDA graphs once (1) is warm (first call).
@@ -91,9 +92,17 @@ void emip_gemm_tc_set_profile_buffer(unsigned long long* dev_buf);
  * accumulators (default), 1 = 256-column tiles.  Bit 1: the epilogue warps of gemm_tc_kernel skip their work (no math, no stores:
  * the OUTPUT IS GARBAGE) so that tools/gemm_floor.py can time the TMA + MMA pipeline alone.  Bit 2: emip_feature_transformer_fwd runs
  * the feed-forward network as two GEMM launches (hidden rows through HBM) instead of the fused kernel -- for A / B timing and the
- * parity test of the fused kernel.  Bit 3: the producer warp skips the operand loads as well (UMMA issue rate alone; garbage).  Bit 4: the
- * persistent tensor-core kernels are launched without programmatic dependent launch (A / B timing).  0 restores the defaults. */
+ * parity test of the fused kernel.  Bit 3: the producer warp skips the operand loads as well (UMMA issue rate alone; garbage).
+ * 0 restores the defaults. */
 void emip_debug_gemm_wide_tiles(int v);
+/* Launch policy, process-wide, default 0; returns the previous value.  1: the persistent tensor-core kernels (gemm_tc / attention /
+ * fused feed-forward) are launched with programmatic stream serialisation -- a kernel's prologue (barrier init, TMEM allocation)
+ * may start on an SM as soon as the previous kernel's CTA there has exited, and waits (griddepcontrol.wait) for that kernel to
+ * complete before it touches memory.  Worth ~1 % of the chain step when ONE stream owns the GPU (bench.py c3; captured into a CUDA
+ * graph the setting is frozen into the graph's edges); leave it off when several streams share the GPU: an early-launched CTA
+ * holds an SM that another stream's kernel could use (c4 with four clip streams per GPU: -28 %).  Not thread-safe: set it before
+ * launching / capturing, e.g. emip_b200.chain.GraphedChain(pdl=True) sets it around its capture only. */
+int emip_set_programmatic_launch(int on);
 /* Diagnostics: wait-cycle profile of the staged flow_warp kernel, device pointer to [grid][8] int64 or NULL. */
 void emip_debug_flow_warp_staged_profile(long long* buf);
 

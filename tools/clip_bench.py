@@ -70,7 +70,12 @@ def main():
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--pdl", action="store_true", help="capture the graphs with programmatic dependent launch (A / B: it costs 28 %% "
+                                                        "with four concurrent clip streams, profiles/r5q_clips_pdl_ab.txt)")
     args = ap.parse_args()
+    if args.pdl:
+        from emip_b200 import _lib
+        _lib.lib().emip_set_programmatic_launch(1)
     from emip_b200.chain import MotionChain
     from emip_b200.injector import Injector
     from emip_b200.memory import Memory

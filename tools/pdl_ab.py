@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Same-box A / B of programmatic dependent launch: the CUDA-graph chain step with and without it (emip_debug_gemm_wide_tiles bit 4;
-the graph is re-captured for each setting): pdl_ab.py [pairs ...]."""
+"""Same-box A / B of programmatic dependent launch: the CUDA-graph chain step with and without it (GraphedChain(pdl=...) =
+emip_set_programmatic_launch around the capture; the graph is re-captured for each setting): pdl_ab.py [pairs ...]."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,8 +18,7 @@ for pairs in [int(a) for a in sys.argv[1:]] or [64, 8]:
     res = {}
     for rnd in range(3):
         for flag in (0, 16):
-            L.emip_debug_gemm_wide_tiles(flag)
-            g = GraphedChain(m, gm, seg)
+            g = GraphedChain(m, gm, seg, pdl=(flag == 0))
             for _ in range(3):
                 g.replay()
             torch.cuda.synchronize()
@@ -32,5 +31,4 @@ for pairs in [int(a) for a in sys.argv[1:]] or [64, 8]:
             torch.cuda.synchronize()
             res.setdefault(flag, []).append(e0.elapsed_time(e1) / n)
             del g
-    L.emip_debug_gemm_wide_tiles(0)
     print(f"{pairs} pairs: with PDL {min(res[0]):.4f} ms {['%.3f' % v for v in res[0]]} | without {min(res[16]):.4f} ms {['%.3f' % v for v in res[16]]}")
